@@ -1,0 +1,441 @@
+"""Python veneer over the krets_b200 C ABI.
+
+Two layers, both thin:
+  * `Circuit`, `Solver`, `Analysis`, `AnalysisResult` mirror the krets public API (parser.rs:27,156; solver.rs:17-52;
+    lib.rs:13-77) through the C++ host mirror (krh_* in include/krets_b200_host.h);
+  * `Plan` exposes the array-level drop-in boundary (krb_* in include/krets_b200.h) for lane batches: numpy arrays are
+    passed as host memory, torch CUDA tensors as device memory on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import KrbConfig, KrbIO, KrbOverrides, KrbPlanInfo, KrbPlanOpts
+
+MODE_DC, MODE_AC, MODE_TRAN = 0, 1, 2
+MEM_HOST, MEM_DEVICE = 0, 1
+LAYOUT_POINT_MAJOR, LAYOUT_LANE_INTERLEAVED = 0, 1
+LANE_ZERO_PIVOT, LANE_NOT_CONVERGED, LANE_NONFINITE = 1, 2, 4
+
+_ERR_NAMES = {
+    1: "InvalidArgument", 3: "ElementNotFound", 4: "InvalidElementFormat", 5: "MaximumIterationsExceeded",
+    6: "DecompositionFailed", 7: "Unsupported", 20: "NoDevice", 21: "Cuda", 22: "OutOfMemory", 23: "Internal",
+    30: "ParseError", 31: "EmptyNetlist", 32: "UnsupportedElement", 33: "MissingModel", 34: "Io",
+}
+
+
+class KretsError(RuntimeError):
+    """krets_solver::Error / krets_parser::Error carried across the C ABI."""
+
+    def __init__(self, code: int, message: str):
+        self.code = code
+        self.kind = _ERR_NAMES.get(code, str(code))
+        super().__init__(f"{self.kind}: {message}")
+
+
+def _check_krb(rc: int):
+    if rc:
+        raise KretsError(rc, _lib.lib().krb_last_error_string().decode(errors="replace"))
+
+
+def _check_krh(rc: int):
+    if rc:
+        raise KretsError(rc, _lib.lib().krh_last_error_string().decode(errors="replace"))
+
+
+def version() -> str:
+    return _lib.lib().krb_version().decode()
+
+
+def device_count() -> int:
+    return int(_lib.lib().krb_device_count())
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.lib().krb_kernel_launch_count())
+
+
+def last_kernel_ms() -> float:
+    return float(_lib.lib().krb_last_kernel_ms())
+
+
+class SolverConfig:
+    """krets_solver::config::SolverConfig (config.rs:4-37)."""
+
+    def __init__(self, relative_tolerance=0.001, current_absolute_tolerance=1e-12, voltage_absolute_tolerance=1e-6,
+                 maximum_iterations=300):
+        self.c = KrbConfig(relative_tolerance, current_absolute_tolerance, voltage_absolute_tolerance, maximum_iterations)
+
+    @staticmethod
+    def default():
+        return SolverConfig()
+
+
+# ---- krets_parser::analyses ---------------------------------------------------------------------------------
+@dataclass
+class DcAnalysis:            # analyses.rs:44-54
+    element: str
+    start: float
+    stop: float
+    step_size: float
+
+
+@dataclass
+class AcSweep:               # analyses.rs:56-65
+    variation: str           # "Linear" | "Decade" | "Octave"
+    points: int
+
+    @staticmethod
+    def Linear(total_points):
+        return AcSweep("Linear", total_points)
+
+    @staticmethod
+    def Decade(points_per_decade):
+        return AcSweep("Decade", points_per_decade)
+
+    @staticmethod
+    def Octave(points_per_octave):
+        return AcSweep("Octave", points_per_octave)
+
+
+@dataclass
+class AcAnalysis:            # analyses.rs:68-76
+    sweep: AcSweep
+    fstart: float
+    fstop: float
+
+    def generate_frequencies(self):
+        return generate_frequencies(self.sweep.variation, self.sweep.points, self.fstart, self.fstop)
+
+
+@dataclass
+class TransientAnalysis:     # analyses.rs:161-165
+    time_step: float
+    stop_time: float
+
+
+class Analysis:              # analyses.rs:27-41
+    def __init__(self, kind, params=None):
+        self.kind, self.params = kind, params
+
+    @staticmethod
+    def Op():
+        return Analysis("op")
+
+    @staticmethod
+    def Dc(p: DcAnalysis):
+        return Analysis("dc", p)
+
+    @staticmethod
+    def Ac(p: AcAnalysis):
+        return Analysis("ac", p)
+
+    @staticmethod
+    def Transient(p: TransientAnalysis):
+        return Analysis("transient", p)
+
+
+_SWEEP_KIND = {"Linear": 0, "Decade": 1, "Octave": 2}
+
+
+def generate_frequencies(variation: str, points: int, fstart: float, fstop: float) -> np.ndarray:
+    """AcAnalysis::generate_frequencies (analyses.rs:80-158), computed by the C++ host mirror."""
+    L = _lib.lib()
+    k = _SWEEP_KIND[variation]
+    n = L.krh_generate_frequencies(k, points, fstart, fstop, None, 0)
+    out = np.empty(max(int(n), 1), dtype=np.float64)
+    n2 = L.krh_generate_frequencies(k, points, fstart, fstop, out.ctypes.data_as(C.POINTER(C.c_double)), out.size)
+    assert n2 == n
+    return out[:n]
+
+
+# ---- krets_parser::circuit::Circuit ---------------------------------------------------------------------------
+class Circuit:
+    def __init__(self, handle):
+        L = _lib.lib()
+        self._h = handle
+        self.n = L.krh_circuit_num_unknowns(handle)
+        self.num_elements = L.krh_circuit_num_elements(handle)
+        self.names = [L.krh_circuit_unknown_name(handle, i).decode() for i in range(self.n)]
+        self.index_map = {nm: i for i, nm in enumerate(self.names)}
+        self.identifiers = [L.krh_circuit_element_identifier(handle, e).decode() for e in range(self.num_elements)]
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib._lib is not None:
+            _lib._lib.krh_circuit_free(self._h)
+            self._h = None
+
+    def element_index(self, identifier: str) -> int:
+        try:
+            return self.identifiers.index(identifier)
+        except ValueError:
+            return -1
+
+    def element(self, e: int):
+        return _lib.lib().krh_circuit_elements(self._h)[e]
+
+    def element_value(self, e: int) -> float:
+        return float(self.element(e).value)
+
+
+def parse_circuit_description(text: str) -> Circuit:
+    h = C.c_void_p()
+    _check_krh(_lib.lib().krh_parse_circuit_description(text.encode(), C.byref(h)))
+    return Circuit(h)
+
+
+def parse_circuit_description_file(path) -> Circuit:
+    h = C.c_void_p()
+    _check_krh(_lib.lib().krh_parse_circuit_description_file(str(path).encode(), C.byref(h)))
+    return Circuit(h)
+
+
+# ---- krets_solver::AnalysisResult ------------------------------------------------------------------------------
+class AnalysisResult:
+    """lib.rs:13-77.  `.array` is [rows][n] (complex for AC) in index-map order, `.axis` the step/frequency/time column."""
+
+    def __init__(self, kind: str, names, array: np.ndarray, axis):
+        self.kind, self.names, self.array, self.axis = kind, names, array, axis
+
+    def _rows(self, axis_key, cast=float):
+        out = []
+        for r in range(self.array.shape[0]):
+            d = {nm: (complex(v) if self.kind == "ac" else float(v)) for nm, v in zip(self.names, self.array[r])}
+            if axis_key:
+                d[axis_key] = complex(self.axis[r], 0.0) if self.kind == "ac" else float(self.axis[r])
+            out.append(d)
+        return out
+
+    def into_op(self):
+        if self.kind != "op":
+            raise RuntimeError("Called `into_op()` on a non-Op result")
+        return self._rows(None)[0]
+
+    def into_dc(self):
+        if self.kind != "dc":
+            raise RuntimeError("Called `into_dc()` on a non-Dc result")
+        return self._rows("step")
+
+    def into_ac(self):
+        if self.kind != "ac":
+            raise RuntimeError("Called `into_ac()` on a non-Ac result")
+        return self._rows("frequency")
+
+    def into_transient(self):
+        if self.kind != "transient":
+            raise RuntimeError("Called `into_transient()` on a non-Transient result")
+        return self._rows("time")
+
+
+class Solver:
+    """krets_solver::solver::Solver (solver.rs:17-52) over the CUDA backend."""
+
+    def __init__(self, circuit: Circuit, config: SolverConfig | None = None):
+        self.circuit = circuit
+        self.config = config or SolverConfig()
+        h = C.c_void_p()
+        _check_krh(_lib.lib().krh_solver_new(circuit._h, C.byref(self.config.c), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib._lib is not None:
+            _lib._lib.krh_solver_free(self._h)
+            self._h = None
+
+    def solve(self, analysis: Analysis) -> AnalysisResult:
+        L = _lib.lib()
+        r = C.c_void_p()
+        p = analysis.params
+        if analysis.kind == "op":
+            _check_krh(L.krh_solver_solve_op(self._h, C.byref(r)))
+        elif analysis.kind == "dc":
+            _check_krh(L.krh_solver_solve_dc(self._h, p.element.encode(), p.start, p.stop, p.step_size, C.byref(r)))
+        elif analysis.kind == "ac":
+            _check_krh(L.krh_solver_solve_ac(self._h, _SWEEP_KIND[p.sweep.variation], p.sweep.points, p.fstart, p.fstop, C.byref(r)))
+        elif analysis.kind == "transient":
+            _check_krh(L.krh_solver_solve_transient(self._h, p.time_step, p.stop_time, C.byref(r)))
+        else:
+            raise ValueError(analysis.kind)
+        try:
+            rows, n = int(L.krh_result_rows(r)), int(L.krh_result_num_unknowns(r))
+            width = n * (2 if analysis.kind == "ac" else 1)
+            data = np.ctypeslib.as_array(L.krh_result_data(r), shape=(rows * max(width, 1),)).copy() if rows * width else np.zeros(0)
+            arr = data.view(np.complex128).reshape(rows, n) if analysis.kind == "ac" else data.reshape(rows, n)
+            ax_ptr = L.krh_result_axis(r)
+            axis = np.ctypeslib.as_array(ax_ptr, shape=(rows,)).copy() if (ax_ptr and rows) else None
+        finally:
+            L.krh_result_free(r)
+        return AnalysisResult(analysis.kind, self.circuit.names, arr, axis)
+
+
+# ---- array-level boundary (krb_*) -------------------------------------------------------------------------------
+def _is_device(x) -> bool:
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_device(x):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(x.ctypes.data)
+
+
+class Plan:
+    """One-time symbolic analysis of a circuit for one stamp mode (krb_analyze) + lane-batch solves (krb_solve_*)."""
+
+    def __init__(self, circuit: Circuit, mode: int, *, sweep_element: int = -1, varied=(), time_step: float = 0.0,
+                 nominal_frequency: float = 0.0, scratch_slots: int = 0, threads_per_block: int = 0):
+        L = _lib.lib()
+        self.circuit, self.mode = circuit, mode
+        self.varied = list(varied)
+        kc = C.c_void_p()
+        _check_krb(L.krb_circuit_create(L.krh_circuit_elements(circuit._h), circuit.num_elements, circuit.n,
+                                        L.krh_circuit_is_current(circuit._h), C.byref(kc)))
+        self._kc = kc
+        o = KrbPlanOpts()
+        L.krb_default_plan_opts(C.byref(o))
+        o.sweep_element = sweep_element
+        o.time_step = time_step
+        o.nominal_frequency = nominal_frequency
+        o.scratch_slots = scratch_slots
+        o.threads_per_block = threads_per_block
+        self._varied_arr = (C.c_int32 * max(len(self.varied), 1))(*self.varied)
+        o.n_varied = len(self.varied)
+        o.varied_elements = C.cast(self._varied_arr, C.POINTER(C.c_int32))
+        h = C.c_void_p()
+        try:
+            _check_krb(L.krb_analyze(kc, mode, C.byref(o), C.byref(h)))
+        except Exception:
+            L.krb_circuit_destroy(kc)
+            self._kc = None
+            raise
+        self._h = h
+        info = KrbPlanInfo()
+        _check_krb(L.krb_plan_get_info(h, C.byref(info)))
+        self.info = info
+        self.n = info.n
+
+    def __del__(self):
+        if _lib._lib is None:
+            return
+        if getattr(self, "_h", None):
+            _lib._lib.krb_plan_destroy(self._h)
+            self._h = None
+        if getattr(self, "_kc", None):
+            _lib._lib.krb_circuit_destroy(self._kc)
+            self._kc = None
+
+    # -- introspection --
+    def pattern(self):
+        colptr = np.zeros(self.n + 1, dtype=np.int32)
+        rowidx = np.zeros(max(self.info.nnz, 1), dtype=np.int32)
+        _check_krb(_lib.lib().krb_plan_get_pattern(self._h, colptr.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                   rowidx.ctypes.data_as(C.POINTER(C.c_int32))))
+        return colptr, rowidx[: self.info.nnz]
+
+    def pivot_order(self):
+        r = np.zeros(max(self.n, 1), dtype=np.int32)
+        c = np.zeros(max(self.n, 1), dtype=np.int32)
+        _check_krb(_lib.lib().krb_plan_get_pivot_order(self._h, r.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       c.ctypes.data_as(C.POINTER(C.c_int32))))
+        return r[: self.n], c[: self.n]
+
+    def program(self, section: int = 0) -> np.ndarray:
+        n = int(_lib.lib().krb_plan_program_size(self._h, section))
+        ops = np.zeros((max(n, 0), 2), dtype=np.uint32)
+        if n > 0:
+            _check_krb(_lib.lib().krb_plan_get_program(self._h, section, ops.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return ops
+
+    # -- solves --
+    def _io(self, arrays, layout):
+        io = KrbIO()
+        _lib.lib().krb_default_io(C.byref(io))
+        dev = [_is_device(a) for a in arrays if a is not None]
+        if any(dev) and not all(dev):
+            raise ValueError("all lane-sized arrays of one call must be on the same side (host numpy or CUDA tensors)")
+        io.memory = MEM_DEVICE if any(dev) else MEM_HOST
+        io.layout = layout
+        if io.memory == MEM_DEVICE:
+            import torch
+            io.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return io
+
+    def _ov(self, values):
+        if not self.varied:
+            return None, None
+        ov = KrbOverrides()
+        ov.n_varied = len(self.varied)
+        ov.values = _ptr(values)
+        return ov, values
+
+    def solve_op(self, lanes: int = 1, varied_values=None, out=None, cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR,
+                 return_iterations=False):
+        cfg = cfg or SolverConfig()
+        out = out if out is not None else np.zeros((lanes, self.n), dtype=np.float64)
+        status = _like_int(out, lanes)
+        iters = _like_int(out, lanes) if return_iterations else None
+        ov, _keep = self._ov(varied_values)
+        io = self._io([out, varied_values], layout)
+        _check_krb(_lib.lib().krb_solve_op(self._h, C.byref(cfg.c), lanes, C.byref(ov) if ov else None, _ptr(out), _ptr(iters),
+                                           _ptr(status), C.byref(io)))
+        return (out, status, iters) if return_iterations else (out, status)
+
+    def solve_dc_sweep(self, sweep_values, varied_values=None, out=None, cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR):
+        cfg = cfg or SolverConfig()
+        lanes = int(sweep_values.shape[0])
+        out = out if out is not None else _like_out(sweep_values, (lanes, self.n), False)
+        status = _like_int(out, lanes)
+        ov, _keep = self._ov(varied_values)
+        io = self._io([sweep_values, out, varied_values], layout)
+        _check_krb(_lib.lib().krb_solve_dc_sweep(self._h, C.byref(cfg.c), _ptr(sweep_values), lanes, C.byref(ov) if ov else None,
+                                                 _ptr(out), _ptr(status), C.byref(io)))
+        return out, status
+
+    def solve_ac(self, frequencies, varied_values=None, op_solution=None, out=None, cfg: SolverConfig | None = None,
+                 layout=LAYOUT_POINT_MAJOR):
+        cfg = cfg or SolverConfig()
+        lanes = int(frequencies.shape[0])
+        out = out if out is not None else _like_out(frequencies, (lanes, self.n), True)
+        status = _like_int(out, lanes)
+        ov, _keep = self._ov(varied_values)
+        lanes_op = 0
+        if op_solution is not None:
+            lanes_op = 1 if op_solution.ndim == 1 else int(op_solution.shape[0])
+        io = self._io([frequencies, out, varied_values, op_solution], layout)
+        _check_krb(_lib.lib().krb_solve_ac(self._h, C.byref(cfg.c), _ptr(frequencies), lanes, C.byref(ov) if ov else None,
+                                           _ptr(op_solution), lanes_op, _ptr(out), _ptr(status), C.byref(io)))
+        return out, status
+
+    def solve_transient(self, plan_dc: "Plan", n_steps: int, lanes: int = 1, varied_values=None, out=None,
+                        cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR):
+        """self must be a MODE_TRAN plan; plan_dc the MODE_DC plan of the same circuit (row 0 = OP, transient.rs:21)."""
+        cfg = cfg or SolverConfig()
+        if out is None:
+            shape = (lanes, n_steps + 1, self.n) if layout == LAYOUT_POINT_MAJOR else (n_steps + 1, self.n, lanes)
+            out = _like_out(varied_values, shape, False) if varied_values is not None else np.zeros(shape, dtype=np.float64)
+        status = _like_int(out, lanes)
+        ov, _keep = self._ov(varied_values)
+        io = self._io([out, varied_values], layout)
+        _check_krb(_lib.lib().krb_solve_transient(plan_dc._h, self._h, C.byref(cfg.c), n_steps, lanes, C.byref(ov) if ov else None,
+                                                  _ptr(out), _ptr(status), C.byref(io)))
+        return out, status
+
+
+def _like_out(ref, shape, complex_):
+    if _is_device(ref):
+        import torch
+        return torch.empty(shape, dtype=torch.complex128 if complex_ else torch.float64, device=ref.device)
+    return np.zeros(shape, dtype=np.complex128 if complex_ else np.float64)
+
+
+def _like_int(ref, n):
+    if _is_device(ref):
+        import torch
+        return torch.zeros(n, dtype=torch.int32, device=ref.device)
+    return np.zeros(n, dtype=np.int32)

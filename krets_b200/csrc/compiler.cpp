@@ -1,0 +1,547 @@
+// Plan compiler: symbolic stamps + static pivot plan  ->  straight-line lane program (vm_ops.h).
+//
+// The numeric method is a row-wise (up-looking) Crout/LDU factorisation without pivoting,  A = L~ * U^  with U^ unit
+// upper triangular, fused with the forward substitution; the back substitution follows in the same program:
+//     row k:   w   = A[k,:]                                  (MNA stamping, contributions summed in stamp order)
+//              w  -= w[j] * U^[j,:]      for j in Lpat[k]    (y_k -= w[j] * y^_j alongside)
+//              U^[k,l] = w[l] / w[k],  y^_k = y_k / w[k]
+//     back:    x_k = y^_k - sum_l U^[k,l] x_l
+// Every value is a "cell"; the allocator below maps cells to per-lane on-chip scratch slots with Belady
+// (farthest-next-use) eviction, rematerialises constants/inputs instead of spilling them, and spills the rest to
+// HBM value planes in production order (so the fused back substitution re-reads them as a reverse stream).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+#include "plan.hpp"
+
+namespace krb {
+
+namespace {
+
+constexpr uint8_t VOP_PERSIST = 0xFF;   // marker: cell `a` is final and must survive the section
+
+struct VOp {
+    uint8_t opc;
+    uint8_t flags;
+    int d, a, b;
+    uint32_t imm;
+};
+enum Remat : uint8_t { R_NONE = 0, R_LDB = 1, R_LDI = 2 };
+struct Cell {
+    Remat remat = R_NONE;
+    uint32_t rimm = 0;
+    int home = -1;        // HBM plane
+    bool persist = false; // produced in the factor-once section, consumed in the per-step section
+    int pin_slot = -1;
+};
+
+struct Builder {
+    Plan &plan;
+    std::vector<Cell> cells;
+    std::vector<int> input_of_elem;
+    std::map<std::tuple<int, int, int, uint64_t>, int> pool_index;   // (kind, neg, elem, bits(c)) -> pool idx
+    std::map<int, int> pool_cells;                                   // pool idx -> shared remat cell
+    std::map<int, int> diode_pool_base;
+
+    explicit Builder(Plan &p) : plan(p) {}
+
+    int new_cell() { cells.emplace_back(); return (int)cells.size() - 1; }
+    int pool_idx(PoolKind k, bool neg, int elem, double c = 0.0) {
+        uint64_t bits;
+        std::memcpy(&bits, &c, 8);
+        auto key = std::make_tuple((int)k, (int)neg, elem, bits);
+        auto it = pool_index.find(key);
+        if (it != pool_index.end()) return it->second;
+        plan.pool.push_back({k, neg, elem, c});
+        int idx = (int)plan.pool.size() - 1;
+        pool_index[key] = idx;
+        return idx;
+    }
+    int shared_pool_cell(int idx) {
+        auto it = pool_cells.find(idx);
+        if (it != pool_cells.end()) return it->second;
+        int c = new_cell();
+        cells[c].remat = R_LDB; cells[c].rimm = (uint32_t)idx;
+        pool_cells[idx] = c;
+        return c;
+    }
+    int fresh_pool_cell(int idx) {
+        int c = new_cell();
+        cells[c].remat = R_LDB; cells[c].rimm = (uint32_t)idx;
+        return c;
+    }
+    int fresh_input_cell(int plane) {
+        int c = new_cell();
+        cells[c].remat = R_LDI; cells[c].rimm = (uint32_t)plane;
+        return c;
+    }
+    int diode_base(int e) {
+        auto it = diode_pool_base.find(e);
+        if (it != diode_pool_base.end()) return it->second;
+        // four consecutive entries: {is/(n*Vt), n*Vt, is, vcrit}
+        plan.pool.push_back({P_DIO_ISNVT, false, e, 0.0});
+        int base = (int)plan.pool.size() - 1;
+        plan.pool.push_back({P_DIO_NVT, false, e, 0.0});
+        plan.pool.push_back({P_DIO_IS, false, e, 0.0});
+        plan.pool.push_back({P_DIO_VCRIT, false, e, 0.0});
+        diode_pool_base[e] = base;
+        return base;
+    }
+};
+
+// A source reference that can be materialised either as a shared read-only cell or a fresh mutable one
+struct Section {
+    Builder &B;
+    std::vector<VOp> vops;
+    int ldx_which_guess;   // LDX flag for "the linearisation point": 1 = NR guess (DC/TRAN), 0 = prev row (AC: OP solution)
+    std::map<std::tuple<int, int, int>, int> derived;   // (tag, elem, neg) -> shared cell, valid inside this section
+    std::map<int, int> input_cells;                    // plane -> shared remat cell
+
+    explicit Section(Builder &b, int which_guess) : B(b), ldx_which_guess(which_guess) {}
+
+    int op(uint8_t opc, int d, int a = -1, int b = -1, uint32_t imm = 0, uint8_t flags = 0) {
+        vops.push_back({opc, flags, d, a, b, imm});
+        return d;
+    }
+    int un(uint8_t opc, int a, uint32_t imm = 0) { return op(opc, B.new_cell(), a, -1, imm); }
+    int bin(uint8_t opc, int a, int b) { return op(opc, B.new_cell(), a, b); }
+    int shared_input(int plane) {
+        auto it = input_cells.find(plane);
+        if (it != input_cells.end()) return it->second;
+        int c = B.fresh_input_cell(plane);
+        input_cells[plane] = c;
+        return c;
+    }
+    int ldx(int which, int unknown, bool half_default) {
+        return op(KOP_LDX, B.new_cell(), -1, -1, (uint32_t)unknown, (uint8_t)((which & 1) | (half_default ? 2 : 0)));
+    }
+    enum Tag { T_G = 1, T_VAL, T_VOH, T_TWOPIF, T_JWV, T_VD, T_DIOG, T_DIOI, T_CAPH, T_INDH };
+    int cached(Tag t, int e, bool neg, int (Section::*make)(int)) {
+        auto key = std::make_tuple((int)t, e, (int)neg);
+        auto it = derived.find(key);
+        if (it != derived.end()) return it->second;
+        int c;
+        if (neg) c = un(KOP_NEG, cached(t, e, false, make));
+        else c = (this->*make)(e);
+        derived[key] = c;
+        return c;
+    }
+    bool varied(int e) const { return B.input_of_elem[e] >= 0; }
+    int elem_value(int e) { return varied(e) ? shared_input(B.input_of_elem[e]) : B.shared_pool_cell(B.pool_idx(P_VAL, false, e)); }
+    int make_g(int e) { return un(KOP_INV, elem_value(e)); }                                   // 1.0 / value
+    int h_cell() { return B.shared_pool_cell(B.pool_idx(P_CONST, false, -1, B.plan.opts.time_step)); }
+    int make_voh(int e) { return varied(e) ? bin(KOP_DIVR, elem_value(e), h_cell()) : B.shared_pool_cell(B.pool_idx(P_VOH, false, e)); }
+    int make_twopif(int) {
+        const double two_pi = 2.0 * 3.14159265358979323846264338327950288;                     // 2.0 * PI
+        return bin(KOP_MUL, B.shared_pool_cell(B.pool_idx(P_CONST, false, -1, two_pi)), shared_input(B.plan.input_freq));
+    }
+    int make_jwv(int e) {                                                                      // (0, ((2.0*PI)*f)*value)
+        int w = cached(T_TWOPIF, -1, false, &Section::make_twopif);
+        return un(KOP_MULJ, bin(KOP_MUL, w, elem_value(e)));
+    }
+    int make_vd(int e) {                                                                       // diode.rs:26-40
+        const krb_element &el = B.plan.circuit.el[e];
+        int vp = el.ip >= 0 ? ldx(ldx_which_guess, el.ip, true) : B.shared_pool_cell(B.pool_idx(P_CONST, false, -1, 0.5));
+        if (el.im < 0) return vp;                                                              // vp - 0.0 == vp
+        int vm = ldx(ldx_which_guess, el.im, false);
+        return bin(KOP_SUB, vp, vm);
+    }
+    int make_diog(int e) { return un(KOP_DIOG, cached(T_VD, e, false, &Section::make_vd), (uint32_t)B.diode_base(e)); }
+    int make_dioi(int e) { return un(KOP_DIOI, cached(T_VD, e, false, &Section::make_vd), (uint32_t)B.diode_base(e)); }
+    int make_caph(int e) {                                                                     // (value/h) * (v+_prev - v-_prev)
+        const krb_element &el = B.plan.circuit.el[e];
+        int coef = varied(e) ? cached(T_VOH, e, false, &Section::make_voh) : make_voh(e);
+        int v;
+        if (el.ip >= 0 && el.im >= 0) v = bin(KOP_SUB, ldx(0, el.ip, false), ldx(0, el.im, false));
+        else if (el.ip >= 0) v = ldx(0, el.ip, false);
+        else v = un(KOP_NEG, ldx(0, el.im, false));
+        return bin(KOP_MUL, coef, v);
+    }
+    int make_indh(int e) {                                                                     // (value/h) * i_prev
+        const krb_element &el = B.plan.circuit.el[e];
+        int coef = varied(e) ? cached(T_VOH, e, false, &Section::make_voh) : make_voh(e);
+        return bin(KOP_MUL, coef, ldx(0, el.ic, false));
+    }
+
+    // Returns a cell holding the contribution.  `fresh` is set when the cell is private (safe to mutate in place).
+    int src_cell(const Src &s, bool &fresh) {
+        fresh = false;
+        const int e = s.elem;
+        switch (s.kind) {
+        case S_ONE: fresh = true; return B.fresh_pool_cell(B.pool_idx(P_CONST, s.neg, -1, 1.0));
+        case S_G:
+            if (!varied(e)) { fresh = true; return B.fresh_pool_cell(B.pool_idx(P_G, s.neg, e)); }
+            return cached(T_G, e, s.neg, &Section::make_g);
+        case S_VAL:
+            if (!varied(e)) { fresh = true; return B.fresh_pool_cell(B.pool_idx(P_VAL, s.neg, e)); }
+            if (!s.neg) { fresh = true; return B.fresh_input_cell(B.input_of_elem[e]); }
+            return cached(T_VAL, e, true, &Section::elem_value_wrap);
+        case S_VOH:
+            if (!varied(e)) { fresh = true; return B.fresh_pool_cell(B.pool_idx(P_VOH, s.neg, e)); }
+            return cached(T_VOH, e, s.neg, &Section::make_voh);
+        case S_JWV: return cached(T_JWV, e, s.neg, &Section::make_jwv);
+        case S_ACAMP: fresh = true; return B.fresh_pool_cell(B.pool_idx(P_ACAMP, s.neg, e));
+        case S_WAVE: {
+            auto &we = B.plan.wave_elems;
+            int col = (int)(std::find(we.begin(), we.end(), e) - we.begin());
+            if (col == (int)we.size()) we.push_back(e);
+            int c = op(KOP_LDBS, B.new_cell(), -1, -1, (uint32_t)col);
+            fresh = true;
+            return s.neg ? un(KOP_NEG, c) : c;
+        }
+        case S_DIODE_G: return cached(T_DIOG, e, s.neg, &Section::make_diog);
+        case S_DIODE_IEQ: return cached(T_DIOI, e, s.neg, &Section::make_dioi);
+        case S_CAP_HIST: return cached(T_CAPH, e, s.neg, &Section::make_caph);
+        case S_IND_HIST: return cached(T_INDH, e, s.neg, &Section::make_indh);
+        }
+        return -1;
+    }
+    int elem_value_wrap(int e) { return elem_value(e); }
+
+    // sum of contributions in stamp order (sum_triplets, solver.rs:59-70); result is a private mutable cell
+    int sum_cell(const std::vector<Src> &srcs) {
+        if (srcs.empty()) return op(KOP_ZERO, B.new_cell());
+        bool fresh;
+        int acc = src_cell(srcs[0], fresh);
+        if (srcs.size() == 1) return fresh ? acc : un(KOP_MOV, acc);
+        bool f2;
+        int c2 = src_cell(srcs[1], f2);
+        acc = bin(KOP_ADD, acc, c2);
+        for (size_t i = 2; i < srcs.size(); i++) {
+            int ci = src_cell(srcs[i], f2);
+            op(KOP_ADD, acc, acc, ci);
+        }
+        return acc;
+    }
+};
+
+// ---- allocation --------------------------------------------------------------------------------------------
+struct AllocResult { std::vector<uint32_t> ops; int64_t n_ops = 0; int max_slot = -1; int64_t ldg = 0, stg = 0; };
+
+struct Allocator {
+    std::vector<Cell> &cells;
+    int S;                 // total scratch slots
+    int first_free_slot;   // slots below are pinned
+    int &n_planes;
+    std::vector<int> slot_of;      // cell -> slot
+    std::vector<int> cell_in;      // slot -> cell
+    std::vector<char> dirty, stored, valid;   // valid: the slot holds the cell's current value
+    bool pinned_valid;                         // pinned cells were computed by an earlier section
+    AllocResult out;
+
+    Allocator(std::vector<Cell> &c, int S_, int first_free, int &planes, bool pinned_valid_)
+        : cells(c), S(S_), first_free_slot(first_free), n_planes(planes), pinned_valid(pinned_valid_) {
+        slot_of.assign(cells.size(), -1);
+        cell_in.assign(S, -1);
+        dirty.assign(cells.size(), 0);
+        stored.assign(cells.size(), 0);
+        valid.assign(cells.size(), 0);
+    }
+    void emit(uint32_t opc, uint32_t d, uint32_t a, uint32_t b, uint32_t imm) {
+        out.ops.push_back(krb_op_w0(opc, d, a, b));
+        out.ops.push_back(imm);
+        out.n_ops++;
+    }
+    void track(int s) { out.max_slot = std::max(out.max_slot, s); }
+
+    bool run(const std::vector<VOp> &vops, std::string &err) {
+        const int nv = (int)vops.size();
+        // use lists
+        std::vector<std::vector<int>> uses(cells.size());
+        auto add_use = [&](int c, int i) { if (c >= 0 && (uses[c].empty() || uses[c].back() != i)) uses[c].push_back(i); };
+        for (int i = 0; i < nv; i++) { add_use(vops[i].d, i); add_use(vops[i].a, i); add_use(vops[i].b, i); }
+        std::vector<int> up(cells.size(), 0);   // pointer into uses
+        auto next_use = [&](int c, int now) {
+            auto &u = uses[c];
+            int &p = up[c];
+            while (p < (int)u.size() && u[p] <= now) p++;
+            return p < (int)u.size() ? u[p] : INT32_MAX;
+        };
+        // pinned cells are resident from the start
+        for (size_t c = 0; c < cells.size(); c++)
+            if (cells[c].pin_slot >= 0) {
+                slot_of[c] = cells[c].pin_slot; cell_in[cells[c].pin_slot] = (int)c; track(cells[c].pin_slot);
+                valid[c] = pinned_valid ? 1 : 0;
+            }
+        // persistent home-mode cells produced by an earlier section are already in their planes
+        for (size_t c = 0; c < cells.size(); c++)
+            if (cells[c].persist && cells[c].home >= 0 && cells[c].pin_slot < 0) stored[c] = 1;
+
+        for (int i = 0; i < nv; i++) {
+            const VOp &v = vops[i];
+            if (v.opc == VOP_PERSIST) {
+                const int c = v.a;
+                // a persistent value that nothing in this section consumed (e.g. an L~ entry whose pivot row has no
+                // U part) still has to be materialised from its constant/input source
+                if (!valid[c] && !stored[c]) {
+                    int excl1[3] = {c, -1, -1};
+                    int s = slot_of[c];
+                    if (s < 0) s = get_slot(excl1, i, next_use, err);
+                    if (s < 0) return false;
+                    if (cells[c].remat == R_LDB) emit(KOP_LDB, s, 0, 0, cells[c].rimm);
+                    else if (cells[c].remat == R_LDI) emit(KOP_LDI, s, 0, 0, cells[c].rimm);
+                    else { err = "internal: persistent cell never defined"; return false; }
+                    slot_of[c] = s; cell_in[s] = c; track(s); valid[c] = 1; dirty[c] = 1;
+                }
+                if (cells[c].pin_slot >= 0) continue;
+                if (cells[c].home < 0) cells[c].home = n_planes++;
+                if (slot_of[c] >= 0) {
+                    if (dirty[c] || !stored[c]) { emit(KOP_STG, 0, slot_of[c], 0, (uint32_t)cells[c].home); out.stg++; }
+                    dirty[c] = 0; stored[c] = 1;
+                } else if (!stored[c]) { err = "internal: persistent cell lost"; return false; }
+                if (next_use(c, i) == INT32_MAX) release(c);
+                continue;
+            }
+            const bool reads_d = (v.opc == KOP_FNMA);
+            int excl[3] = {v.d, v.a, v.b};
+            // operands
+            int rd[3]; int nr = 0;
+            if (v.a >= 0) rd[nr++] = v.a;
+            if (v.b >= 0 && v.b != v.a) rd[nr++] = v.b;
+            if (reads_d && v.d >= 0 && v.d != v.a && v.d != v.b) rd[nr++] = v.d;
+            for (int r = 0; r < nr; r++) {
+                const int c = rd[r];
+                if (slot_of[c] >= 0 && valid[c]) continue;
+                int s = slot_of[c];
+                if (s < 0) s = get_slot(excl, i, next_use, err);
+                if (s < 0) return false;
+                valid[c] = 1;
+                if (!dirty[c] && cells[c].remat == R_LDB && !stored[c]) emit(KOP_LDB, s, 0, 0, cells[c].rimm);
+                else if (!dirty[c] && cells[c].remat == R_LDI && !stored[c]) emit(KOP_LDI, s, 0, 0, cells[c].rimm);
+                else if (stored[c]) { emit(KOP_LDG, s, 0, 0, (uint32_t)cells[c].home); out.ldg++; }
+                else { err = "internal: read of an undefined cell"; return false; }
+                slot_of[c] = s; cell_in[s] = c; track(s);
+            }
+            int sd = 0;
+            if (v.d >= 0) {
+                if (slot_of[v.d] < 0) {
+                    const int s = get_slot(excl, i, next_use, err);
+                    if (s < 0) return false;
+                    slot_of[v.d] = s; cell_in[s] = v.d; track(s);
+                }
+                sd = slot_of[v.d];
+                dirty[v.d] = 1; stored[v.d] = 0; valid[v.d] = 1;
+            }
+            const int sa = v.a >= 0 ? slot_of[v.a] : 0, sb = v.b >= 0 ? slot_of[v.b] : 0;
+            uint32_t bfield = (uint32_t)sb;
+            if (v.opc == KOP_LDX || v.opc == KOP_XOUT) bfield = v.flags;
+            emit(v.opc, (uint32_t)sd, (uint32_t)sa, bfield, v.imm);
+            // free dead cells
+            for (int r = 0; r < 3; r++) {
+                const int c = excl[r];
+                if (c < 0 || slot_of[c] < 0) continue;
+                if (cells[c].pin_slot >= 0) continue;
+                if (next_use(c, i) == INT32_MAX) release(c);
+            }
+        }
+        emit(KOP_END, 0, 0, 0, 0);
+        return true;
+    }
+    void release(int c) {
+        if (cells[c].pin_slot >= 0) return;
+        const int s = slot_of[c];
+        if (s >= 0) { cell_in[s] = -1; slot_of[c] = -1; valid[c] = 0; }
+    }
+    template <class NU>
+    int get_slot(const int excl[3], int now, NU &next_use, std::string &err) {
+        for (int s = first_free_slot; s < S; s++)
+            if (cell_in[s] < 0) return s;
+        int victim = -1, far = -1;
+        for (int s = first_free_slot; s < S; s++) {
+            const int c = cell_in[s];
+            if (c == excl[0] || c == excl[1] || c == excl[2]) continue;
+            if (cells[c].pin_slot >= 0) continue;
+            int nu = next_use(c, now - 1 < 0 ? -1 : now - 1);
+            // operands of the current op that are already resident must stay: their next use is `now`
+            if (nu == now) continue;
+            // prefer victims that need no store: clean remat cells or cells whose plane copy is current
+            int cost_free = (!dirty[c] && (cells[c].remat != R_NONE || stored[c])) ? 1 : 0;
+            int key = (nu == INT32_MAX) ? INT32_MAX : nu;
+            if (key > far || (key == far && cost_free)) { far = key; victim = s; }
+        }
+        if (victim < 0) { err = "scratch capacity too small for one operation"; return -1; }
+        const int c = cell_in[victim];
+        const int nu = next_use(c, now - 1 < 0 ? -1 : now - 1);
+        const bool needed_later = (nu != INT32_MAX) || (cells[c].persist && !stored[c]);
+        if (needed_later && (dirty[c] || (cells[c].remat == R_NONE && !stored[c]))) {
+            if (cells[c].home < 0) cells[c].home = n_planes++;
+            emit(KOP_STG, 0, (uint32_t)victim, 0, (uint32_t)cells[c].home);
+            out.stg++;
+            stored[c] = 1; dirty[c] = 0;
+        }
+        cell_in[victim] = -1; slot_of[c] = -1; valid[c] = 0;
+        return victim;
+    }
+};
+
+std::vector<Src> entry_srcs(const Plan &p, int entry) {
+    std::vector<Src> v;
+    if (entry < 0) return v;
+    for (int ci : p.pattern.contribs[entry]) v.push_back(p.stamps.mat[ci].s);
+    return v;
+}
+std::vector<Src> rhs_srcs(const Plan &p, int row) {
+    std::vector<Src> v;
+    for (int ri : p.pattern.rhs_contribs[row]) v.push_back(p.stamps.rhs[ri].s);
+    return v;
+}
+
+}  // namespace
+
+int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan, std::string &err) {
+    plan.circuit = c;
+    plan.mode = mode;
+    plan.opts = opts_in;
+    plan.is_complex = (mode == KRB_MODE_AC);
+    plan.varied.assign(opts_in.varied_elements, opts_in.varied_elements + (opts_in.n_varied > 0 ? opts_in.n_varied : 0));
+    plan.opts.varied_elements = nullptr;
+    const int n = c.n;
+    if (mode == KRB_MODE_TRAN && !(plan.opts.time_step > 0.0)) { err = "transient plan needs time_step > 0"; return KRB_ERR_INVALID_ARGUMENT; }
+    if (plan.opts.integrator != KRB_INTEGRATOR_BE_KRETS) { err = "only KRB_INTEGRATOR_BE_KRETS is implemented"; return KRB_ERR_UNSUPPORTED; }
+    for (int e : plan.varied) {
+        if (e < 0 || e >= (int)c.el.size()) { err = "varied element ordinal out of range"; return KRB_ERR_INVALID_ARGUMENT; }
+        const int k = c.el[e].kind;
+        if (!(k == KRB_R || k == KRB_C || k == KRB_L || k == KRB_V || k == KRB_I)) { err = "only R/C/L/V/I values can vary per lane"; return KRB_ERR_INVALID_ARGUMENT; }
+    }
+    int rc = build_stamps(c, mode, plan.stamps);
+    if (rc) { err = "element not supported in this analysis mode (the reference panics here)"; return rc; }
+    build_pattern(n, plan.stamps, plan.pattern);
+
+    // ---- static pivot plan ----
+    std::vector<double> mag;
+    const double fnom = plan.opts.nominal_frequency > 0.0 ? plan.opts.nominal_frequency : 1000.0;
+    nominal_magnitudes(c, plan.stamps, plan.pattern, mode, plan.opts.time_step, fnom, mag);
+    std::vector<int> match_row, order;
+    if (!weighted_matching(plan.pattern, mag, match_row)) { err = "matrix is structurally singular"; return KRB_ERR_DECOMPOSITION_FAILED; }
+    minimum_degree(plan.pattern, match_row, order);
+    symbolic_lu(plan.pattern, match_row, order, plan.sym);
+    const Symbolic &S = plan.sym;
+
+    // ---- per-lane inputs ----
+    Builder B(plan);
+    B.input_of_elem.assign(c.el.size(), -1);
+    plan.n_inputs = 0;
+    plan.input_sweep = plan.input_freq = -1;
+    if (mode == KRB_MODE_AC) plan.input_freq = plan.n_inputs++;
+    if (mode == KRB_MODE_DC && plan.opts.sweep_element >= 0) {
+        if (plan.opts.sweep_element >= (int)c.el.size()) { err = "sweep element out of range"; return KRB_ERR_ELEMENT_NOT_FOUND; }
+        const int k = c.el[plan.opts.sweep_element].kind;
+        if (k != KRB_V && k != KRB_I) { err = "DC sweep element must be a voltage or current source"; return KRB_ERR_INVALID_ELEMENT_FORMAT; }
+        plan.input_sweep = plan.n_inputs++;
+        B.input_of_elem[plan.opts.sweep_element] = plan.input_sweep;
+    }
+    plan.input_of_varied.clear();
+    for (int e : plan.varied) {
+        if (B.input_of_elem[e] >= 0) { plan.input_of_varied.push_back(B.input_of_elem[e]); continue; }
+        B.input_of_elem[e] = plan.n_inputs++;
+        plan.input_of_varied.push_back(B.input_of_elem[e]);
+    }
+
+    // ---- emission ----
+    const bool split = (mode == KRB_MODE_TRAN) && !c.nonlinear;   // linear transient: factor once, then one solve per step
+    plan.has_step_sections = split;
+    const int which_guess = (mode == KRB_MODE_AC) ? 0 : 1;
+    Section main_sec(B, which_guess), fac_sec(B, which_guess), step_sec(B, which_guess);
+    std::vector<std::vector<int>> Ucell(n), Lcell(n);
+    std::vector<int> yhat(n, -1), invd(n, -1);
+
+    auto emit_factor_rows = [&](Section &sec, bool with_rhs, bool persist) {
+        std::vector<int> W(n, -1);
+        for (int k = 0; k < n; k++) {
+            const auto &Lp = S.Lpat[k];
+            const auto &Up = S.Upat[k];
+            for (size_t t = 0; t < Lp.size(); t++) W[Lp[t]] = sec.sum_cell(entry_srcs(plan, S.Lent[k][t]));
+            W[k] = sec.sum_cell(entry_srcs(plan, S.Dent[k]));
+            for (size_t t = 0; t < Up.size(); t++) W[Up[t]] = sec.sum_cell(entry_srcs(plan, S.Uent[k][t]));
+            int Y = -1;
+            if (with_rhs) Y = sec.sum_cell(rhs_srcs(plan, S.row_order[k]));
+            for (size_t t = 0; t < Lp.size(); t++) {
+                const int j = Lp[t];
+                const int wj = W[j];
+                for (size_t q = 0; q < S.Upat[j].size(); q++) sec.op(KOP_FNMA, W[S.Upat[j][q]], wj, Ucell[j][q]);
+                if (with_rhs) sec.op(KOP_FNMA, Y, wj, yhat[j]);
+                if (persist) { B.cells[wj].persist = true; sec.vops.push_back({VOP_PERSIST, 0, -1, wj, -1, 0}); }
+            }
+            Lcell[k].clear();
+            for (size_t t = 0; t < Lp.size(); t++) Lcell[k].push_back(W[Lp[t]]);
+            const int inv = sec.op(KOP_RCP, B.new_cell(), W[k]);
+            invd[k] = inv;
+            Ucell[k].clear();
+            for (size_t t = 0; t < Up.size(); t++) {
+                const int u = W[Up[t]];
+                sec.op(KOP_MUL, u, u, inv);
+                Ucell[k].push_back(u);
+                if (persist) { B.cells[u].persist = true; sec.vops.push_back({VOP_PERSIST, 0, -1, u, -1, 0}); }
+            }
+            if (with_rhs) { sec.op(KOP_MUL, Y, Y, inv); yhat[k] = Y; }
+            if (persist) { B.cells[inv].persist = true; sec.vops.push_back({VOP_PERSIST, 0, -1, inv, -1, 0}); }
+        }
+    };
+    auto emit_back = [&](Section &sec) {
+        std::vector<int> X(n, -1);
+        for (int k = n - 1; k >= 0; k--) {
+            const int x = yhat[k];
+            for (size_t t = 0; t < S.Upat[k].size(); t++) sec.op(KOP_FNMA, x, Ucell[k][t], X[S.Upat[k][t]]);
+            const int u = S.col_order[k];
+            sec.op(KOP_XOUT, -1, x, -1, (uint32_t)u, c.is_current[u] ? 1 : 0);
+            X[k] = x;
+        }
+    };
+
+    if (!split) {
+        emit_factor_rows(main_sec, true, false);
+        emit_back(main_sec);
+    } else {
+        emit_factor_rows(fac_sec, false, true);
+        for (int k = 0; k < n; k++) {
+            int Y = step_sec.sum_cell(rhs_srcs(plan, S.row_order[k]));
+            for (size_t t = 0; t < S.Lpat[k].size(); t++) step_sec.op(KOP_FNMA, Y, Lcell[k][t], yhat[S.Lpat[k][t]]);
+            step_sec.op(KOP_MUL, Y, Y, invd[k]);
+            yhat[k] = Y;
+        }
+        emit_back(step_sec);
+    }
+
+    // ---- allocation ----
+    int Scap = plan.opts.scratch_slots > 0 ? plan.opts.scratch_slots : (plan.is_complex ? 28 : 48);
+    Scap = std::max(8, std::min(Scap, KRB_MAX_SLOTS));
+    plan.n_planes = 0;
+    int first_free = 0;
+    if (split) {
+        int64_t npersist = 0;
+        for (auto &cl : B.cells) npersist += cl.persist ? 1 : 0;
+        if (npersist + 10 <= Scap) {
+            int s = 0;
+            for (auto &cl : B.cells) if (cl.persist) cl.pin_slot = s++;
+            first_free = s;
+        }
+    }
+    int max_slot = -1;
+    auto run_alloc = [&](Section &sec, Program &prog, bool pinned_valid) -> bool {
+        Allocator A(B.cells, Scap, first_free, plan.n_planes, pinned_valid);
+        if (!A.run(sec.vops, err)) return false;
+        prog.ops.swap(A.out.ops);
+        prog.n_ops = A.out.n_ops;
+        max_slot = std::max(max_slot, A.out.max_slot);
+        plan.hbm_bytes_per_point += (A.out.ldg + A.out.stg);   // counted in values here, scaled below
+        return true;
+    };
+    plan.hbm_bytes_per_point = 0;
+    if (!split) {
+        if (!run_alloc(main_sec, plan.sec[0], false)) return KRB_ERR_INTERNAL;
+    } else {
+        if (!run_alloc(fac_sec, plan.sec[1], false)) return KRB_ERR_INTERNAL;
+        if (!run_alloc(step_sec, plan.sec[2], true)) return KRB_ERR_INTERNAL;
+    }
+    plan.n_slots = max_slot + 1;
+    const int64_t s = plan.is_complex ? 16 : 8;
+    plan.hbm_bytes_per_point = plan.hbm_bytes_per_point * s + (int64_t)n * s + 8 * (int64_t)plan.n_inputs;
+    plan.flops_per_point = S.flops * (plan.is_complex ? 4 : 1);
+    plan.alg_bytes_per_point = 8 * (int64_t)std::max(1, plan.n_inputs) + s * (4 * S.nnz_lu + 3 * (int64_t)n);
+    return KRB_OK;
+}
+
+}  // namespace krb

@@ -1,0 +1,352 @@
+#include "netlist.hpp"
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdlib>
+#include <unordered_set>
+
+namespace krh {
+
+namespace {
+
+// A tiny cursor over one netlist line, mirroring the nom combinators the reference composes.
+struct Cursor {
+    const std::string &s;
+    size_t i = 0;
+    explicit Cursor(const std::string &str) : s(str) {}
+    bool eof() const { return i >= s.size(); }
+    char peek() const { return i < s.size() ? s[i] : '\0'; }
+    static bool blank(char c) { return c == ' ' || c == '\t'; }
+    void space0() { while (blank(peek())) ++i; }
+    bool space1() { if (!blank(peek())) return false; space0(); return true; }
+    bool tag_no_case(const char *t) {
+        size_t k = 0;
+        while (t[k]) {
+            if (i + k >= s.size() || std::tolower((unsigned char)s[i + k]) != std::tolower((unsigned char)t[k])) return false;
+            ++k;
+        }
+        i += k;
+        return true;
+    }
+    // utils.rs:66-69
+    bool ident(std::string &out) {
+        size_t b = i;
+        while (i < s.size() && (((unsigned char)s[i] < 128 && std::isalnum((unsigned char)s[i])) || s[i] == '_')) ++i;
+        out = s.substr(b, i - b);
+        return i > b;
+    }
+    // utils.rs:72-78: token = is_not(" \t\r\n()")
+    bool value(double &out) {
+        size_t b = i;
+        while (i < s.size() && !blank(s[i]) && s[i] != '\r' && s[i] != '\n' && s[i] != '(' && s[i] != ')') ++i;
+        if (i == b) return false;
+        if (parse_value(s.substr(b, i - b), out) != 0) { i = b; return false; }
+        return true;
+    }
+    // nom::number::complete::double (decimal prefix)
+    bool nom_double(double &out) {
+        size_t b = i, j = i;
+        if (j < s.size() && (s[j] == '+' || s[j] == '-')) ++j;
+        size_t digits = 0;
+        while (j < s.size() && std::isdigit((unsigned char)s[j])) { ++j; ++digits; }
+        if (j < s.size() && s[j] == '.') {
+            size_t k = j + 1, frac = 0;
+            while (k < s.size() && std::isdigit((unsigned char)s[k])) { ++k; ++frac; }
+            if (digits + frac > 0) { j = k; digits += frac; }
+        }
+        if (digits == 0) return false;
+        if (j < s.size() && (s[j] == 'e' || s[j] == 'E')) {
+            size_t k = j + 1;
+            if (k < s.size() && (s[k] == '+' || s[k] == '-')) ++k;
+            if (k >= s.size() || !std::isdigit((unsigned char)s[k])) return false;
+            while (k < s.size() && std::isdigit((unsigned char)s[k])) ++k;
+            j = k;
+        }
+        out = std::strtod(s.substr(b, j - b).c_str(), nullptr);
+        i = j;
+        return true;
+    }
+};
+
+// <f64 as FromStr> on the upper-cased numeric part
+bool rust_f64(const std::string &u, double &out) {
+    size_t j = 0;
+    if (j < u.size() && (u[j] == '+' || u[j] == '-')) ++j;
+    const std::string rest = u.substr(j);
+    if (rest == "INF" || rest == "INFINITY") { out = (u[0] == '-') ? -INFINITY : INFINITY; return true; }
+    if (rest == "NAN") { out = NAN; return true; }
+    size_t digits = 0;
+    while (j < u.size() && std::isdigit((unsigned char)u[j])) { ++j; ++digits; }
+    if (j < u.size() && u[j] == '.') { ++j; while (j < u.size() && std::isdigit((unsigned char)u[j])) { ++j; ++digits; } }
+    if (!digits) return false;
+    if (j < u.size() && u[j] == 'E') {
+        ++j;
+        if (j < u.size() && (u[j] == '+' || u[j] == '-')) ++j;
+        if (j >= u.size() || !std::isdigit((unsigned char)u[j])) return false;
+        while (j < u.size() && std::isdigit((unsigned char)u[j])) ++j;
+    }
+    if (j != u.size()) return false;
+    out = std::strtod(u.c_str(), nullptr);
+    return true;
+}
+
+bool two_node_head(Cursor &c, ParsedElement &e) {
+    std::string name;
+    if (!c.ident(name)) return false;
+    e.identifier += name;
+    if (!c.space1() || !c.ident(e.nodes[0])) return false;
+    if (!c.space1() || !c.ident(e.nodes[1])) return false;
+    return true;
+}
+bool paren_values(Cursor &c, double *v, int count) {
+    c.space0();
+    if (c.peek() != '(') return false;
+    ++c.i;
+    c.space0();
+    for (int k = 0; k < count; k++) {
+        if (k && !c.space1()) return false;
+        if (!c.value(v[k])) return false;
+    }
+    c.space0();
+    if (c.peek() != ')') return false;
+    ++c.i;
+    return true;
+}
+
+struct ModelCard { int type; double is, n; };   // type: 0 D, 1 NMOS, 2 PMOS
+
+std::string trim(const std::string &s) {
+    size_t b = 0, e = s.size();
+    while (b < e && std::isspace((unsigned char)s[b])) ++b;
+    while (e > b && std::isspace((unsigned char)s[e - 1])) --e;
+    return s.substr(b, e - b);
+}
+bool starts_with_nc(const std::string &s, const char *t) { Cursor c(s); return c.tag_no_case(t); }
+
+}  // namespace
+
+int parse_value(const std::string &token, double &out) {
+    std::string u(token);
+    for (auto &ch : u) ch = (char)std::toupper((unsigned char)ch);
+    if (u.empty()) return 1;
+    double mult = 1.0;
+    if (u.size() >= 3 && u.compare(u.size() - 3, 3, "MEG") == 0) { u.resize(u.size() - 3); mult = 1e6; }
+    else {
+        switch (u.back()) {
+        case 'F': mult = 1e-15; u.pop_back(); break;
+        case 'P': mult = 1e-12; u.pop_back(); break;
+        case 'N': mult = 1e-9; u.pop_back(); break;
+        case 'U': mult = 1e-6; u.pop_back(); break;
+        case 'M': mult = 1e-3; u.pop_back(); break;
+        case 'K': mult = 1e3; u.pop_back(); break;
+        case 'G': mult = 1e9; u.pop_back(); break;
+        case 'T': mult = 1e12; u.pop_back(); break;
+        default: break;
+        }
+    }
+    double base;
+    if (!rust_f64(u, base)) return 1;
+    out = base * mult;
+    return 0;
+}
+
+int parse_circuit_description(const std::string &text, ParsedCircuit &out, std::string &err) {
+    out = ParsedCircuit();
+    std::unordered_map<std::string, ModelCard> models;
+    bool in_control = false, in_subckt = false;
+    size_t pos = 0;
+    int lineno = 0;
+    auto fail = [&](int code, const std::string &line) {
+        err = "Parse error on line " + std::to_string(lineno) + ": " + line;
+        return code;
+    };
+    while (pos <= text.size()) {
+        size_t eol = text.find('\n', pos);
+        std::string raw = text.substr(pos, eol == std::string::npos ? std::string::npos : eol - pos);
+        if (eol == std::string::npos) { if (pos >= text.size() && raw.empty()) break; pos = text.size() + 1; } else pos = eol + 1;
+        ++lineno;
+        const std::string line = trim(raw);
+        if (line.empty() || line[0] == '%' || line[0] == '*') continue;             // parser.rs:43-45
+        if (starts_with_nc(line, ".control")) { in_control = true; continue; }
+        if (starts_with_nc(line, ".endc")) { in_control = false; continue; }
+        if (in_control) continue;
+        if (starts_with_nc(line, ".subckt")) { in_subckt = true; continue; }
+        if (starts_with_nc(line, ".ends")) { in_subckt = false; continue; }
+        if (in_subckt) continue;
+        if (line.size() == 4 && starts_with_nc(line, ".end")) continue;
+        if (starts_with_nc(line, ".model")) {                                       // models.rs:52-95
+            std::string body = line.substr(0, line.find('%'));
+            Cursor c(body);
+            c.i = 6;
+            std::string name;
+            if (!c.space1() || !c.ident(name) || !c.space1()) return fail(PARSE_ERROR, line);
+            ModelCard m{0, 1e-12, 1.0};                                             // models/diode.rs:14-23
+            if (body.compare(c.i, 4, "NMOS") == 0) { m.type = 1; c.i += 4; }
+            else if (body.compare(c.i, 4, "PMOS") == 0) { m.type = 2; c.i += 4; }
+            else if (c.peek() == 'D') { m.type = 0; c.i += 1; }
+            else return fail(PARSE_ERROR, line);
+            c.space0();
+            if (c.peek() == '(') ++c.i;
+            for (;;) {
+                Cursor t = c;
+                t.space0();
+                std::string key;
+                double v;
+                if (!t.ident(key)) break;
+                t.space0();
+                if (t.peek() != '=') break;
+                ++t.i;
+                t.space0();
+                if (!t.value(v)) break;
+                for (auto &ch : key) ch = (char)std::tolower((unsigned char)ch);
+                if (m.type == 0) { if (key == "is") m.is = v; else if (key == "n") m.n = v; }   // models/diode.rs:26-39
+                c.i = t.i;
+            }
+            models[name] = m;
+            continue;
+        }
+        // element line: the reference tries R, C, L, V, I, D, BJT, NMOS, subckt in that order (elements.rs:45-55);
+        // each alternative is keyed by its leading tag, so dispatching on it is equivalent
+        ParsedElement e;
+        e.pod.ip = e.pod.im = e.pod.ic = -1;
+        e.pod.n = 1.0; e.pod.is = 1e-12;
+        Cursor c(line);
+        const char c0 = (char)std::toupper((unsigned char)line[0]);
+        bool ok = false;
+        auto rcli = [&](int kind, char letter) {
+            ++c.i;
+            e.identifier = std::string(1, letter);
+            e.pod.kind = kind;
+            return two_node_head(c, e) && c.space1() && c.value(e.pod.value);
+        };
+        if (c0 == 'R') ok = rcli(KRB_R, 'R');
+        else if (c0 == 'C') {
+            ok = rcli(KRB_C, 'C');
+            if (ok) { Cursor t = c; if (t.space1() && t.tag_no_case("G2")) e.pod.flags |= KRB_ELEM_FLAG_G2; }   // capacitor.rs:31
+        } else if (c0 == 'L') ok = rcli(KRB_L, 'L');
+        else if (c0 == 'I') ok = rcli(KRB_I, 'I');
+        else if (c0 == 'V') {                                                        // voltage_source.rs:188-235
+            ++c.i;
+            e.identifier = "V";
+            e.pod.kind = KRB_V;
+            ok = two_node_head(c, e);
+            if (ok) {
+                double dc = 0.0, v;
+                { Cursor t = c; if (t.space1() && t.nom_double(v)) { dc = v; c.i = t.i; } }
+                for (;;) {
+                    Cursor t = c;
+                    if (!t.space1()) break;
+                    Cursor k = t;
+                    if (k.tag_no_case("dc") && k.space1() && k.nom_double(v)) { dc = v; c.i = k.i; continue; }
+                    k.i = t.i;
+                    if (k.tag_no_case("ac") && k.space1() && k.nom_double(v)) { e.pod.ac_amplitude = v; c.i = k.i; continue; }
+                    k.i = t.i;
+                    double w[7] = {0, 0, 0, 0, 0, 0, 0};
+                    if (k.tag_no_case("pulse") && paren_values(k, w, 7)) { e.pod.waveform = KRB_WAVE_PULSE; std::copy(w, w + 7, e.pod.wave); c.i = k.i; continue; }
+                    k.i = t.i;
+                    if (k.tag_no_case("sin") && paren_values(k, w, 6)) {
+                        // a later SIN does not displace an earlier PULSE: transient_value_at prefers pulse (voltage_source.rs:245-249)
+                        if (e.pod.waveform != KRB_WAVE_PULSE) { e.pod.waveform = KRB_WAVE_SIN; std::copy(w, w + 6, e.pod.wave); }
+                        c.i = k.i;
+                        continue;
+                    }
+                    break;
+                }
+                e.pod.value = dc;
+            }
+        } else if (c0 == 'D') {                                                      // diode.rs:74-92
+            ++c.i;
+            e.identifier = "D";
+            e.pod.kind = KRB_D;
+            ok = two_node_head(c, e);
+            e.model_name = "default";
+            if (ok) { Cursor t = c; std::string m; if (t.space1() && t.ident(m)) e.model_name = m; }
+        } else if (c0 == 'M' && line.size() > 1 && std::toupper((unsigned char)line[1]) == 'N') {   // nmosfet.rs:113-166
+            c.i = 2;
+            e.identifier = "M";
+            e.pod.kind = KRB_NMOS;
+            std::string name, bulk;
+            ok = c.ident(name) && c.space1() && c.ident(e.nodes[0]) && c.space1() && c.ident(e.nodes[1]) && c.space1() && c.ident(e.nodes[2]) &&
+                 c.space1() && c.ident(bulk) && c.space1() && c.ident(e.model_name);
+            e.identifier += name;
+        } else if (c0 == 'Q' || c0 == 'X') {
+            return fail(PARSE_UNSUPPORTED, line);
+        }
+        if (!ok) return fail(PARSE_ERROR, line);
+        out.elements.push_back(e);
+    }
+    // ---- index map: parser.rs:105-125 ----
+    std::unordered_set<std::string> seen_nodes;
+    for (auto &e : out.elements) {
+        const int kind = e.pod.kind;
+        const bool g2 = kind == KRB_V || kind == KRB_L || kind == KRB_I || (kind == KRB_C && (e.pod.flags & KRB_ELEM_FLAG_G2));   // elements.rs:125-140
+        if (g2) {
+            const std::string key = "I(" + e.identifier + ")";
+            if (out.index_map.count(key)) { err = "duplicate element identifier " + e.identifier; return PARSE_ERROR; }
+            out.index_map[key] = (int)out.unknown_names.size();
+            out.unknown_names.push_back(key);
+        }
+        const int nn = (kind == KRB_NMOS) ? 3 : 2;
+        for (int k = 0; k < nn; k++) {
+            if (!seen_nodes.insert(e.nodes[k]).second) continue;
+            if (e.nodes[k] == "0") continue;
+            const std::string key = "V(" + e.nodes[k] + ")";
+            out.index_map[key] = (int)out.unknown_names.size();
+            out.unknown_names.push_back(key);
+        }
+    }
+    if (out.elements.empty()) { err = "The netlist is empty"; return PARSE_EMPTY_NETLIST; }   // parser.rs:127-129
+    // ---- models: parser.rs:132-149 ----
+    for (auto &e : out.elements) {
+        if (e.pod.kind == KRB_D || e.pod.kind == KRB_NMOS) {
+            auto it = models.find(e.model_name);
+            const int want = e.pod.kind == KRB_D ? 0 : 1;
+            if (it == models.end() || it->second.type != want) { err = "model '" + e.model_name + "' is not defined"; return PARSE_MISSING_MODEL; }
+            e.pod.is = it->second.is;
+            e.pod.n = it->second.n;
+        }
+    }
+    auto lookup = [&](const std::string &key) { auto it = out.index_map.find(key); return it == out.index_map.end() ? -1 : it->second; };
+    for (auto &e : out.elements) {
+        e.pod.ip = lookup("V(" + e.nodes[0] + ")");
+        e.pod.im = lookup("V(" + e.nodes[1] + ")");
+        e.pod.ic = lookup("I(" + e.identifier + ")");
+        out.pod.push_back(e.pod);
+    }
+    out.is_current.resize(out.unknown_names.size());
+    for (size_t i = 0; i < out.unknown_names.size(); i++) out.is_current[i] = out.unknown_names[i][0] == 'I';   // solver.rs:96
+    return PARSE_OK;
+}
+
+std::vector<double> generate_frequencies(int kind, uint32_t points, double fstart, double fstop) {
+    std::vector<double> f;
+    if (fstart <= 0.0 || fstop <= 0.0 || fstart > fstop) return f;                 // analyses.rs:85-90
+    if (kind == 0) {                                                               // :93-102
+        if (points == 1) f.push_back(fstart);
+        else if (points > 1) {
+            const double step = (fstop - fstart) / (double)(points - 1);
+            for (uint32_t i = 0; i < points; i++) f.push_back(fstart + (double)i * step);
+        }
+    } else {                                                                       // :104-154
+        if (points == 0) return f;
+        const double span = (kind == 1) ? std::log10(fstop / fstart) : std::log2(fstop / fstart);
+        const double r = std::round(span * (double)points);
+        uint64_t total = r <= 0.0 ? 0u : (r >= 4294967295.0 ? 4294967295ull : (uint64_t)r);   // `as u32` saturates
+        total += 1;
+        const double factor = std::pow(kind == 1 ? 10.0 : 2.0, 1.0 / (double)points);
+        double cur = fstart;
+        for (uint64_t i = 0; i < total; i++) {
+            if (cur > fstop * (1.0 + 1e-9)) break;
+            f.push_back(cur);
+            cur *= factor;
+            if (cur > fstop && (f.empty() || f.back() < fstop)) { f.push_back(fstop); break; }
+        }
+        if (f.empty() || f.back() < fstop * (1.0 - 1e-9)) f.push_back(fstop);
+    }
+    std::sort(f.begin(), f.end());                                                 // :155-156
+    f.erase(std::unique(f.begin(), f.end()), f.end());
+    return f;
+}
+
+}  // namespace krh

@@ -1,0 +1,116 @@
+// Host-side plan objects for the batched lane solver (one-time symbolic analysis, north-star "Rust host" role,
+// written in C++ because this image has no Rust toolchain).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/krets_b200.h"
+#include "vm_ops.h"
+
+namespace krb {
+
+struct Circuit {
+    std::vector<krb_element> el;
+    int n = 0;
+    std::vector<uint8_t> is_current;
+    bool nonlinear = false;   // elements.rs:143-148
+};
+
+// ---- symbolic stamps -----------------------------------------------------------------------------------
+// Where a stamped value comes from (stampable.rs).  `neg` is an exact sign flip.
+enum SrcKind : uint8_t {
+    S_ONE,        // 1.0 (group-2 coupling entries)
+    S_G,          // 1.0 / value                           resistor   :232
+    S_VAL,        // value                                 I / V DC right-hand side  :567, :1017
+    S_VOH,        // value / h                             C, L backward-Euler companions  :449, :781
+    S_JWV,        // (0, 2*pi*f*value)                     C, L AC    :379-382, :715
+    S_ACAMP,      // (ac_amplitude, 0)                     V AC RHS   :1031
+    S_WAVE,       // transient_value_at(time of guess)     V transient RHS  :1043-1048
+    S_DIODE_G,    // linearised diode conductance          :597, :622
+    S_DIODE_IEQ,  // diode equivalent current              :651
+    S_CAP_HIST,   // (value/h) * (v+_prev - v-_prev)       :480-493  (== -i_eq)
+    S_IND_HIST    // (value/h) * i_prev                    :806-812
+};
+struct Src { SrcKind kind; bool neg; int elem; };
+struct MatContrib { int row, col; Src s; };
+struct RhsContrib { int row; Src s; };
+struct Stamps {
+    std::vector<MatContrib> mat;   // in the reference's push order (element order, then push order within the element)
+    std::vector<RhsContrib> rhs;
+};
+// returns KRB_OK / KRB_ERR_UNSUPPORTED
+int build_stamps(const Circuit &c, int mode, Stamps &out);
+
+// unique (row,col) set in CSC order + the contributions of each entry in stamp order (== sum_triplets order)
+struct Pattern {
+    int n = 0, nnz = 0;
+    std::vector<int> colptr, rowidx;
+    std::vector<std::vector<int>> contribs;   // per entry: indices into Stamps::mat
+    std::vector<std::vector<int>> rhs_contribs;   // per row: indices into Stamps::rhs
+};
+void build_pattern(int n, const Stamps &s, Pattern &p);
+
+// nominal |value| of every entry (for the weighted static pivot matching)
+void nominal_magnitudes(const Circuit &c, const Stamps &s, const Pattern &p, int mode, double h, double fnom, std::vector<double> &mag);
+
+// ---- static pivot plan ----------------------------------------------------------------------------------
+// maximum-product transversal: match_row[col] = row used as the pivot equation of unknown `col`; false if
+// structurally singular
+bool weighted_matching(const Pattern &p, const std::vector<double> &mag, std::vector<int> &match_row);
+// minimum-degree ordering of the symmetrised, row-permuted pattern; returns order[k] = unknown eliminated k-th
+void minimum_degree(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order);
+
+struct Symbolic {
+    int n = 0;
+    std::vector<int> row_order, col_order;        // pivot k: equation row_order[k], unknown col_order[k]
+    // permuted matrix C[k][l] = A[row_order[k]][col_order[l]]; per pivot row: L part (l<k), U part (l>k), both sorted
+    std::vector<std::vector<int>> Lpat, Upat;
+    // A entry id for (k, l) positions present in A: parallel to Lpat/Upat (-1 for fill) and the diagonal
+    std::vector<std::vector<int>> Lent, Uent;
+    std::vector<int> Dent;
+    int64_t nnz_lu = 0, flops = 0;
+};
+void symbolic_lu(const Pattern &p, const std::vector<int> &match_row, const std::vector<int> &order, Symbolic &s);
+
+// ---- compiled lane program -----------------------------------------------------------------------------
+enum PoolKind : uint8_t { P_CONST, P_G, P_VAL, P_VOH, P_ACAMP, P_DIO_ISNVT, P_DIO_NVT, P_DIO_IS, P_DIO_VCRIT };
+struct PoolEntry { PoolKind kind; bool neg; int elem; double c; };
+
+struct Program {
+    std::vector<uint32_t> ops;   // 2 words per op, KOP_END terminated
+    int64_t n_ops = 0;
+};
+
+struct DeviceState;
+
+struct Plan {
+    Circuit circuit;
+    DeviceState *dev = nullptr;        // device-side buffers, created lazily by the runtime
+    int mode = 0;
+    krb_plan_opts opts{};
+    std::vector<int> varied;            // element ordinals with per-lane values
+    bool is_complex = false;
+    Stamps stamps;
+    Pattern pattern;
+    Symbolic sym;
+    // program
+    Program sec[3];                     // 0: main (one-shot / per-NR-iteration), 1: factor-once, 2: per-step
+    bool has_step_sections = false;     // linear transient: sec[1] once + sec[2] per step
+    std::vector<PoolEntry> pool;        // B table layout (static part)
+    std::vector<int> wave_elems;        // per-step table columns (LDBS): V sources with a transient RHS
+    int n_slots = 0, n_planes = 0, n_inputs = 0;
+    int input_sweep = -1, input_freq = -1;   // input plane holding the DC sweep value / the AC frequency
+    std::vector<int> input_of_varied;        // input plane of varied[k]
+    int64_t flops_per_point = 0, hbm_bytes_per_point = 0, alg_bytes_per_point = 0;
+};
+
+// full pipeline; returns KRB_* status and fills `err`
+int analyze(const Circuit &c, int mode, const krb_plan_opts &opts, Plan &plan, std::string &err);
+
+// evaluate the static B table for the circuit's current element values (host, per call)
+void evaluate_pool(const Plan &plan, const Circuit &c, double h, std::vector<double> &out);
+// reference waveform evaluation (voltage_source.rs:52-93, 244-252)
+double transient_value_at(const krb_element &e, double time);
+
+}  // namespace krb

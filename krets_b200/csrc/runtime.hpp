@@ -1,0 +1,34 @@
+// Internal interface between the C ABI (api.cpp) and the CUDA runtime (runtime.cu).
+#pragma once
+#include <string>
+
+#include "plan.hpp"
+
+namespace krb {
+
+struct RunArgs {
+    krb_config cfg;
+    long long lanes = 0;
+    int rows = 1;                        // result rows per lane (transient: n_steps + 1)
+    const double *lane_param = nullptr;  // [lanes] DC sweep values or AC frequencies
+    const double *varied_values = nullptr;   // [n_varied][lanes]
+    const double *op_solution = nullptr; // AC linearisation point
+    long long lanes_op = 0;
+    void *x_out = nullptr;
+    int *lane_status = nullptr;
+    int *iterations = nullptr;
+    int memory = KRB_MEM_HOST, layout = KRB_LAYOUT_POINT_MAJOR;
+    void *stream = nullptr;
+    long long chunk_lanes = 0;
+};
+
+void set_error(const std::string &s);
+const char *get_error();
+int device_count();
+long long launch_count();
+double last_kernel_ms();
+void device_state_free(DeviceState *d);
+// plan_steps != nullptr: transient (plan_first = DC plan for row 0, plan_steps = TRAN plan for rows 1..)
+int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a);
+
+}  // namespace krb

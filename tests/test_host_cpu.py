@@ -1,0 +1,246 @@
+"""CPU tier: the C-ABI library loads and exports what the headers declare; host-side logic (netlist front end,
+index map, frequency grids, symbolic plan, lane-program compiler) checked against the oracle.  No GPU calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import netgen
+from helpers import assert_close
+from vm_emulator import Emulator, input_layout
+
+import krets_b200 as kb
+from krets_b200 import _lib, api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def kcirc(golden, key):
+    if key.startswith("resistor_ladder_"):
+        return kb.parse_circuit_description(netgen.resistor_ladder(int(key.rsplit("_", 1)[1])))
+    return kb.parse_circuit_description(golden["netlists"][key])
+
+
+def ocirc(oracle, golden, key):
+    if key.startswith("resistor_ladder_"):
+        return oracle.Circuit(netgen.resistor_ladder(int(key.rsplit("_", 1)[1])))
+    return oracle.Circuit(golden["netlists"][key])
+
+
+ALL = ["low_pass_filter", "low_pass_filter_transient", "dual_rc_ladder", "high_pass_filter", "high_pass_filter_transient",
+       "voltage_divider", "basic_001", "diode_iv_curve", "rectifier", "farid_n_najm", "inverter", "test_case_1", "resistor_ladder_500"]
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    declared = set()
+    for hdr in ("krets_b200.h", "krets_b200_host.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        declared |= set(re.findall(r"\b(kr[bh]_[a-z0-9_]+)\s*\(", src))
+    assert declared, "no declarations found"
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(_lib.SYMBOLS) == declared            # the ctypes table binds exactly the public surface
+    assert "sm_100a" in kb.version()
+
+
+def test_no_device_fails_loudly(golden):
+    """No CPU fallback: without a GPU every numeric entry point returns KRB_ERR_NO_DEVICE."""
+    if kb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    c = kcirc(golden, "voltage_divider")
+    with pytest.raises(kb.KretsError) as e:
+        kb.Solver(c).solve(kb.Analysis.Op())
+    assert e.value.kind == "NoDevice"
+
+
+@pytest.mark.parametrize("key", ALL)
+def test_index_map_bit_exact(oracle, golden, key):
+    """parser.rs:105-125 — MNA unknown numbering must be identical to the reference's."""
+    kc, oc = kcirc(golden, key), ocirc(oracle, golden, key)
+    assert kc.names == oc.names
+    assert kc.num_elements == oc.num_elements
+    for e in range(kc.num_elements):
+        el = kc.element(e)
+        assert (el.ip, el.im, el.ic) == oc.element_indices(e)
+        assert kc.identifiers[e] == oc.element_ident(e)
+        assert el.kind == oc.element_kind(e)
+        assert el.value == oc.element_value(e)
+
+
+def test_parser_errors():
+    for text, kind in [("* nothing\n", "EmptyNetlist"), ("R1 a 0 1.5x\n", "ParseError"), ("D1 a 0 NOPE\nR1 a 0 1\n", "MissingModel"),
+                       ("Q1 a b c\n", "UnsupportedElement")]:
+        with pytest.raises(kb.KretsError) as e:
+            kb.parse_circuit_description(text)
+        assert e.value.kind == kind
+
+
+def test_frequency_grids_bit_exact(oracle):
+    for kind, pts, f0, f1 in [("Linear", 10, 0.1, 1000.0), ("Linear", 100, 1.0, 1000.0), ("Decade", 10, 1.0, 1e6),
+                              ("Decade", 1250, 1.0, 1e8), ("Octave", 7, 3.0, 5000.0), ("Linear", 1, 5.0, 9.0), ("Decade", 3, 0.0, 1.0)]:
+        a, b = kb.generate_frequencies(kind, pts, f0, f1), oracle.generate_frequencies(kind, pts, f0, f1)
+        assert a.tobytes() == b.tobytes(), (kind, pts)
+
+
+MODES = {"dc": api.MODE_DC, "ac": api.MODE_AC, "tran": api.MODE_TRAN}
+
+
+@pytest.mark.parametrize("key,mode", [("resistor_ladder_500", "dc"), ("farid_n_najm", "dc"), ("basic_001", "dc"), ("low_pass_filter", "ac"),
+                                      ("high_pass_filter", "ac"), ("dual_rc_ladder", "tran"), ("high_pass_filter_transient", "tran"),
+                                      ("rectifier", "tran"), ("diode_iv_curve", "dc"), ("inverter", "dc")])
+def test_sparsity_pattern_bit_exact(oracle, golden, key, mode):
+    """The stamped (row,col) set after sum_triplets must equal the reference's CSC pattern."""
+    kc, oc = kcirc(golden, key), ocirc(oracle, golden, key)
+    plan = kb.Plan(kc, MODES[mode], time_step=1e-5)
+    colptr, rowidx = plan.pattern()
+    ocp, ori, _ = oc.stamp_matrix(mode, 1e-5 if mode == "tran" else 1000.0)
+    assert colptr.tolist() == ocp.tolist() and rowidx.tolist() == ori.tolist()
+    r, c = plan.pivot_order()
+    assert sorted(r.tolist()) == list(range(kc.n)) and sorted(c.tolist()) == list(range(kc.n))
+
+
+def test_ladder_plan_is_fill_free():
+    """the 5000 ladder has a zero-fill order: nnz(L+U) must be 15 000 (= nnz(A))."""
+    kc = kb.parse_circuit_description(netgen.resistor_ladder(5000))
+    plan = kb.Plan(kc, api.MODE_DC, sweep_element=0)
+    assert (plan.info.n, plan.info.nnz, plan.info.nnz_lu) == (5001, 15000, 15000)
+    assert plan.info.alg_bytes_per_point == 8 + 8 * (4 * 15000 + 3 * 5001)      # 600 032 B, SURVEY §8(d)
+    kc = kb.parse_circuit_description(netgen.rc_ladder(5000))
+    plan = kb.Plan(kc, api.MODE_AC)
+    assert (plan.info.n, plan.info.nnz, plan.info.nnz_lu) == (5001, 15000, 15000)
+    assert plan.info.alg_bytes_per_point == 8 + 16 * (4 * 15000 + 3 * 5001)     # 1 200 056 B
+
+
+def test_structural_singularity_and_unsupported(golden):
+    # AC + current source -> empty row -> DecompositionFailed at analysis time
+    with pytest.raises(kb.KretsError) as e:
+        kb.Plan(kcirc(golden, "basic_001"), api.MODE_AC)
+    assert e.value.kind == "DecompositionFailed"
+    # NMOS AC is todo!() in the reference
+    with pytest.raises(kb.KretsError) as e:
+        kb.Plan(kcirc(golden, "inverter"), api.MODE_AC)
+    assert e.value.kind == "Unsupported"
+    with pytest.raises(kb.KretsError) as e:
+        kb.Plan(kcirc(golden, "voltage_divider"), api.MODE_DC, sweep_element=1)   # R1 is not a source
+    assert e.value.kind == "InvalidElementFormat"
+
+
+# ---- the compiled lane program, emulated on the CPU, against the oracle ----------------------------------------
+def test_program_dc_sweep_ladder(oracle):
+    kc = kb.parse_circuit_description(netgen.resistor_ladder(500))
+    oc = oracle.Circuit(netgen.resistor_ladder(500))
+    plan = kb.Plan(kc, api.MODE_DC, sweep_element=0, scratch_slots=16)
+    vals = np.linspace(-2.0, 3.0, 7)
+    em = Emulator(plan, len(vals))
+    X = em.run(vals[None, :])
+    ref = oc.solve_dc("V1", -2.0, 3.0, 5.0 / 6.0)
+    assert ref.shape[0] == 7
+    assert_close(X[0].T, ref, what="ladder DC sweep")
+    assert not em.status.any()
+    assert em.stats["stg"] == em.stats["ldg"] > 0            # spilled U^/y^ go out once and come back once
+
+
+@pytest.mark.parametrize("slots", [8, 12, 48])
+def test_program_op_small_circuits(oracle, golden, slots):
+    for key in ["farid_n_najm", "test_case_1", "voltage_divider", "basic_001", "high_pass_filter", "low_pass_filter", "inverter"]:
+        kc, oc = kcirc(golden, key), ocirc(oracle, golden, key)
+        plan = kb.Plan(kc, api.MODE_DC, scratch_slots=slots)
+        em = Emulator(plan, 1)
+        X = em.run(np.zeros((0, 1)))
+        assert_close(X[0][:, 0], oc.solve_op(), what=key)
+
+
+def test_program_nr_diode(oracle, golden):
+    kc, oc = kcirc(golden, "diode_iv_curve"), ocirc(oracle, golden, "diode_iv_curve")
+    plan = kb.Plan(kc, api.MODE_DC)
+    em = Emulator(plan, 1)
+    X = em.run(np.zeros((0, 1)))
+    ref, it = oc.solve_op(return_iterations=True)
+    assert_close(X[0][:, 0], ref, what="diode OP")
+    assert em.iters[0] == it and em.status[0] == 0
+
+
+def test_program_ac(oracle, golden):
+    for key, n in [("low_pass_filter", 0), ("high_pass_filter", 0), ("rc", 60)]:
+        text = netgen.rc_ladder(n) if key == "rc" else golden["netlists"][key]
+        kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+        freqs = oracle.generate_frequencies("Decade", 3, 1.0, 1e7)
+        plan = kb.Plan(kc, api.MODE_AC, nominal_frequency=1e3, scratch_slots=14)
+        em = Emulator(plan, len(freqs))
+        X = em.run(freqs[None, :])
+        _, ref = oc.solve_ac(freqs)
+        assert_close(X[0].T, ref, what=key)
+
+
+def test_program_transient_linear(oracle, golden):
+    for key, h, stop in [("dual_rc_ladder", 50e-6, 5e-3), ("low_pass_filter_transient", 50e-6, 3e-3), ("high_pass_filter_transient", 10e-6, 1e-3)]:
+        kc, oc = kcirc(golden, key), ocirc(oracle, golden, key)
+        pdc = kb.Plan(kc, api.MODE_DC)
+        ptr = kb.Plan(kc, api.MODE_TRAN, time_step=h)
+        t, ref = oc.solve_tran(h, stop)
+        rows = len(t)
+        X = Emulator(pdc, 1, rows=rows).run(np.zeros((0, 1)), row_begin=0, row_end=1)
+        em = Emulator(ptr, 1, rows=rows, h=h)
+        assert em.split
+        X = em.run(np.zeros((0, 1)), X=X, row_begin=1, guess_empty_at_iter0=False, pseudo_time=True)
+        assert_close(X[:, :, 0], ref, what=key)
+
+
+def test_program_transient_nonlinear(oracle, golden):
+    kc, oc = kcirc(golden, "rectifier"), ocirc(oracle, golden, "rectifier")
+    h, stop = 50e-6, 5e-3
+    pdc = kb.Plan(kc, api.MODE_DC)
+    ptr = kb.Plan(kc, api.MODE_TRAN, time_step=h)
+    t, ref = oc.solve_tran(h, stop)
+    rows = len(t)
+    X = Emulator(pdc, 1, rows=rows).run(np.zeros((0, 1)), row_begin=0, row_end=1)
+    em = Emulator(ptr, 1, rows=rows, h=h)
+    assert not em.split
+    X = em.run(np.zeros((0, 1)), X=X, row_begin=1, guess_empty_at_iter0=False, pseudo_time=True)
+    assert_close(X[:, :, 0], ref, rtol=1e-7, what="rectifier")
+    assert not em.status.any()
+
+
+def test_program_monte_carlo_transient(oracle, golden):
+    """BASELINE config 4 shape: dual_rc_ladder, R1 R2 C1 C2 varied per lane (splitmix64 rule of SURVEY §8d)."""
+    text = golden["netlists"]["dual_rc_ladder"]
+    kc = kb.parse_circuit_description(text)
+    names = ["R1", "R2", "C1", "C2"]
+    varied = [kc.element_index(nm) for nm in names]
+    lanes, h, nsteps = 5, 5e-6, 40
+    vals = np.array([[kc.element_value(e) * netgen.mc_factor(l, j, 4) for l in range(lanes)] for j, e in enumerate(varied)])
+    pdc = kb.Plan(kc, api.MODE_DC, varied=varied)
+    ptr = kb.Plan(kc, api.MODE_TRAN, varied=varied, time_step=h)
+    _, _, iov = input_layout(ptr)
+    IN = np.zeros((ptr.info.n_inputs, lanes))
+    for k, pl in enumerate(iov):
+        IN[pl] = vals[k]
+    rows = nsteps + 1
+    X = Emulator(pdc, lanes, rows=rows).run(IN, row_begin=0, row_end=1)
+    X = Emulator(ptr, lanes, rows=rows, h=h).run(IN, X=X, row_begin=1, guess_empty_at_iter0=False, pseudo_time=True)
+    for l in range(lanes):
+        oc = oracle.Circuit(text)
+        for j, nm in enumerate(names):
+            oc.set_element_value(oc.element_index(nm), vals[j, l])
+        _, ref = oc.solve_tran(h, nsteps * h)
+        assert_close(X[:, :, l], ref, what=f"lane {l}")
+
+
+def test_program_mesh_with_fill(oracle):
+    """A small RLC mesh: fill-in, structurally zero diagonals (L branches in DC), spills with a tiny scratch."""
+    text = netgen.rlc_mesh(5, 6, transient=True)
+    kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    plan = kb.Plan(kc, api.MODE_DC, scratch_slots=10)
+    assert plan.info.nnz_lu >= plan.info.nnz
+    X = Emulator(plan, 1).run(np.zeros((0, 1)))
+    assert_close(X[0][:, 0], oc.solve_op(), what="mesh OP")
+    text = netgen.rlc_mesh(5, 6, transient=False)
+    kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    freqs = np.array([1.0, 1e3, 1e6, 1e9])
+    plan = kb.Plan(kc, api.MODE_AC, nominal_frequency=1e4, scratch_slots=12)
+    X = Emulator(plan, len(freqs)).run(freqs[None, :])
+    _, ref = oc.solve_ac(freqs)
+    assert_close(X[0].T, ref, what="mesh AC")

@@ -1,0 +1,158 @@
+"""numpy emulator of the krets_b200 lane program (vm_ops.h) — TEST INFRASTRUCTURE ONLY.
+
+Lets the CPU-only test tier check the host plan compiler (stamps -> pivot plan -> symbolic LU -> scratch allocation)
+against the oracle without a GPU: every op is lane-invariant, so numpy executes each op on the whole lane vector.
+It mirrors krb_lane_vm in krets_b200/csrc/vm_kernel.cuh; the product never imports it.
+"""
+import ctypes as C
+
+import numpy as np
+
+from krets_b200 import _lib
+
+(END, LDB, LDBS, LDI, LDG, STG, LDX, XOUT, ZERO, MOV, NEG, ADD, SUB, MUL, FNMA, RCP, INV, DIVR, MULJ, DIOG, DIOI) = range(21)
+ZERO_PIVOT, NOT_CONVERGED, NONFINITE = 1, 2, 4
+
+
+def _plan_tables(plan, rows, h):
+    L = _lib.lib()
+    npool = int(L.krb_plan_pool_size(plan._h))
+    pool = np.zeros(max(npool, 1))
+    L.krb_plan_eval_pool(plan._h, pool.ctypes.data_as(C.POINTER(C.c_double)))
+    nw = int(L.krb_plan_wave_count(plan._h))
+    bstep = np.zeros((max(rows, 1), 2, max(nw, 1)))
+    for r in range(1, rows):
+        for k in range(nw):
+            v = C.c_double()
+            L.krb_plan_wave_value(plan._h, k, (r - 1) * h, C.byref(v))
+            bstep[r, 0, k] = v.value
+            L.krb_plan_wave_value(plan._h, k, r * h, C.byref(v))
+            bstep[r, 1, k] = v.value
+    return pool, bstep
+
+
+def input_layout(plan):
+    L = _lib.lib()
+    a, b = C.c_int32(), C.c_int32()
+    arr = (C.c_int32 * max(len(plan.varied), 1))()
+    L.krb_plan_input_layout(plan._h, C.byref(a), C.byref(b), arr)
+    return a.value, b.value, list(arr)[: len(plan.varied)]
+
+
+class Emulator:
+    def __init__(self, plan, lanes, *, rows=1, h=0.0, cfg=None, nonlinear=None, cplx=None):
+        self.plan, self.L, self.rows, self.h = plan, lanes, rows, h
+        self.n = plan.n
+        self.cplx = (plan.mode == 1) if cplx is None else cplx
+        self.dtype = np.complex128 if self.cplx else np.float64
+        self.pool, self.bstep = _plan_tables(plan, rows, h)
+        self.nonlinear = bool(plan.info.nonlinear) if nonlinear is None else nonlinear
+        self.cfg = cfg or dict(reltol=1e-3, iabstol=1e-12, vabstol=1e-6, max_iter=300)
+        self.split = bool(_lib.lib().krb_plan_has_step_sections(plan._h))
+        self.progs = [plan.program(s) for s in range(3)]
+        self.scr, self.G = {}, {}
+        self.status = np.zeros(lanes, dtype=np.int32)
+        self.iters = np.zeros(lanes, dtype=np.int32)
+        self.stats = dict(ldg=0, stg=0, ops=0)
+
+    def run_prog(self, prog, IN, X, row, it, guess_empty, guess, prev, active):
+        scr, G = self.scr, self.G
+        notconv = np.zeros(self.L, dtype=bool)
+        with np.errstate(all="ignore"):
+            for w0, imm in prog:
+                w0 = int(w0); imm = int(imm)
+                opc, d, a, b = w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, (w0 >> 24) & 0xFF
+                self.stats["ops"] += 1
+                if opc == END:
+                    break
+                elif opc == LDB:
+                    scr[d] = np.full(self.L, self.pool[imm], dtype=self.dtype)
+                elif opc == LDBS:
+                    scr[d] = np.full(self.L, self.bstep[row, 1 if it > 0 else 0, imm], dtype=self.dtype)
+                elif opc == LDI:
+                    scr[d] = IN[imm].astype(self.dtype)
+                elif opc == LDG:
+                    scr[d] = G[imm].copy(); self.stats["ldg"] += 1
+                elif opc == STG:
+                    G[imm] = scr[a].copy(); self.stats["stg"] += 1
+                elif opc == LDX:
+                    if b & 1:
+                        v = np.full(self.L, 0.5 if (b & 2) else 0.0) if guess_empty else guess[imm]
+                    else:
+                        v = prev[imm]
+                    scr[d] = np.asarray(v).real.astype(self.dtype)
+                elif opc == XOUT:
+                    v = scr[a]
+                    self.status[~np.isfinite(v)] |= NONFINITE
+                    if (not self.cplx) and self.nonlinear and not guess_empty:
+                        ov = guess[imm]
+                        diff = np.abs(v - ov)
+                        scale = np.maximum(np.abs(v), np.abs(ov))
+                        atol = self.cfg["iabstol"] if (b & 1) else self.cfg["vabstol"]
+                        notconv |= ~(diff <= self.cfg["reltol"] * scale + atol)
+                    X[row][imm] = np.where(active, v, X[row][imm])
+                elif opc == ZERO:
+                    scr[d] = np.zeros(self.L, dtype=self.dtype)
+                elif opc == MOV:
+                    scr[d] = scr[a].copy()
+                elif opc == NEG:
+                    scr[d] = -scr[a]
+                elif opc == ADD:
+                    scr[d] = scr[a] + scr[b]
+                elif opc == SUB:
+                    scr[d] = scr[a] - scr[b]
+                elif opc == MUL:
+                    scr[d] = scr[a] * scr[b]
+                elif opc == FNMA:
+                    scr[d] = scr[d] - scr[a] * scr[b]
+                elif opc == RCP:
+                    bad = ~(np.abs(scr[a]) > 0) | ~np.isfinite(scr[a])
+                    self.status[bad] |= ZERO_PIVOT
+                    scr[d] = 1.0 / scr[a]
+                elif opc == INV:
+                    scr[d] = (1.0 / scr[a].real).astype(self.dtype)
+                elif opc == DIVR:
+                    scr[d] = (scr[a].real / scr[b].real).astype(self.dtype)
+                elif opc == MULJ:
+                    scr[d] = (1j * scr[a].real).astype(self.dtype)
+                elif opc in (DIOG, DIOI):
+                    vd = scr[a].real
+                    isnvt, nvt, is_, vcrit = self.pool[imm: imm + 4]
+                    vl = np.minimum(np.maximum(vd, -vcrit), vcrit)
+                    ex = np.exp(vl / nvt)
+                    g = isnvt * ex
+                    scr[d] = (g if opc == DIOG else (is_ * (ex - 1.0) - g * vd)).astype(self.dtype)
+                else:
+                    raise ValueError(f"bad opcode {opc}")
+        return notconv
+
+    def run(self, IN, X=None, row_begin=0, row_end=None, guess_empty_at_iter0=True, pseudo_time=False, Xprev0=None):
+        """IN: [n_inputs][L]; X: preallocated [rows][n][L] (transient continuation) or None."""
+        row_end = self.rows if row_end is None else row_end
+        if X is None:
+            X = np.zeros((self.rows, self.n, self.L), dtype=self.dtype)
+        max_iter = self.cfg["max_iter"] if self.nonlinear and not self.cplx else 1
+        for row in range(row_begin, row_end):
+            prev = Xprev0 if (row == row_begin and Xprev0 is not None) else X[max(row - 1, 0)]
+            active = np.ones(self.L, dtype=bool)
+            passes = [1, 2] if (self.split and row == row_begin) else ([2] if self.split else [0])
+            for sec in passes:
+                solve_pass = sec != 1
+                for it in range(max_iter):
+                    guess_empty = guess_empty_at_iter0 and it == 0
+                    guess = prev if (it == 0 and not guess_empty_at_iter0) else X[row].copy()
+                    notconv = self.run_prog(self.progs[sec], IN, X, row, it, guess_empty, guess, prev, active)
+                    if not solve_pass or not self.nonlinear or self.cplx:
+                        break
+                    pseudo_ok = True
+                    if pseudo_time and it == 0:
+                        tn, tp = row * self.h, (row - 1) * self.h
+                        pseudo_ok = abs(tn - tp) <= self.cfg["reltol"] * max(abs(tn), abs(tp)) + self.cfg["vabstol"]
+                    self.iters[active] = it + 1
+                    conv = (not guess_empty) & (~notconv) & pseudo_ok
+                    active = active & ~conv
+                    if it == max_iter - 1:
+                        self.status[active] |= NOT_CONVERGED
+                    if not active.any():
+                        break
+        return X
