@@ -61,8 +61,11 @@ struct DeviceState {
 };
 
 DeviceState *device_state_new() { return new DeviceState(); }
+static double sum_event_ms(DeviceState *d);
+static DeviceState *g_last_timed_fwd();
 void device_state_free(DeviceState *d) {
     if (!d) return;
+    if (g_last_timed_fwd() == d) { extern void krb_snapshot_last_ms(DeviceState *); krb_snapshot_last_ms(d); }
     for (int i = 0; i < 3; i++) if (d->sec[i]) cudaFree(d->sec[i]);
     d->B.release(); d->Bstep.release(); d->IN.release(); d->G.release(); d->X.release(); d->XOP.release();
     d->packed.release(); d->status.release(); d->iters.release();
@@ -71,8 +74,8 @@ void device_state_free(DeviceState *d) {
 }
 
 static DeviceState *g_last_timed = nullptr;
-double last_kernel_ms() {
-    DeviceState *d = g_last_timed;
+static double g_last_ms = -1.0;   // kept when the plan that owned the events is destroyed
+static double sum_event_ms(DeviceState *d) {
     if (!d || d->events_used == 0) return -1.0;
     double total = 0.0;
     for (size_t i = 0; i < d->events_used; i++) {
@@ -83,6 +86,9 @@ double last_kernel_ms() {
     }
     return total;
 }
+double last_kernel_ms() { return g_last_timed ? sum_event_ms(g_last_timed) : g_last_ms; }
+static DeviceState *g_last_timed_fwd() { return g_last_timed; }
+void krb_snapshot_last_ms(DeviceState *d) { g_last_ms = sum_event_ms(d); g_last_timed = nullptr; }
 
 static int upload_programs(Plan &plan, DeviceState &d) {
     if (d.uploaded) return KRB_OK;
