@@ -280,13 +280,13 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "krb_lane_vm<f64> (stamp + LDU refactor + forward/back substitution fused per lane)",
+                         "kernel": ("krb_chain_kernel<f64>" if info.executor == 1 else "krb_lane_vm<f64>") + " (stamp + LDU refactor + forward/back substitution fused per lane)",
                          "kernel_ms": kernel_ms, "alg_bytes_per_point": alg, "peak_source": peak_src,
                          "model_hbm_bytes_per_point": int(info.hbm_bytes_per_point),
                          "fused_floor_bytes_per_point": floor_bytes,
                          "note": "achieved uses the 3-pass algorithmic bytes of SURVEY §8(d) (P + s*(4*nnz_lu + 3*n)); the fused lane program "
                                  "moves fewer bytes than that (model_hbm_bytes_per_point), so frac can exceed 1 — see DESIGN.md §Roofline"},
-            "plan": {"nnz_lu": int(info.nnz_lu), "scratch_slots": int(info.scratch_slots), "spill_planes": int(info.spill_planes),
+            "plan": {"executor": "chain" if info.executor == 1 else "lane_vm", "nnz_lu": int(info.nnz_lu), "scratch_slots": int(info.scratch_slots), "spill_planes": int(info.spill_planes),
                      "program_ops": int(info.program_ops)},
             "parity_spot_check": {"linearity_max_rel_err": lin_err},
         }

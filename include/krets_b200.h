@@ -94,8 +94,10 @@ void krb_circuit_destroy(krb_circuit *c);
 enum { KRB_MODE_DC = 0, KRB_MODE_AC = 1, KRB_MODE_TRAN = 2 };          /* stamp_*_dc / _ac / _transient */
 enum { KRB_INTEGRATOR_BE_KRETS = 0,   /* backward Euler incl. the reference's one-step source lag */
        KRB_INTEGRATOR_TRAP = 1 };     /* trapezoidal companion models (north-star extension; no reference oracle) */
-enum { KRB_EXEC_FUSED = 0,            /* stamp+factor+solve in one lane program, L/U only spilled when needed */
-       KRB_EXEC_STAGED = 1 };         /* stamp, factor, solve as separate launches through HBM value arrays */
+enum { KRB_EXEC_FUSED = 0,            /* default: stamp+factor+solve fused per lane; the executor is chosen from the plan's
+                                         structure (native chain kernel for tridiagonal-after-permutation plans, lane VM otherwise) */
+       KRB_EXEC_STAGED = 1,           /* stamp, factor, solve as separate launches through HBM value arrays (not implemented yet) */
+       KRB_EXEC_LANE_VM = 2 };        /* force the general lane-program interpreter */
 
 typedef struct krb_plan_opts {
     int32_t struct_size;              /* sizeof(krb_plan_opts), for ABI evolution */
@@ -132,6 +134,8 @@ typedef struct krb_plan_info {
     int64_t flops_per_point;  /* real flops of factor+solve for one lane (complex counted x4/x2) */
     int64_t hbm_bytes_per_point;   /* bytes the lane program itself moves through HBM per point (model) */
     int64_t alg_bytes_per_point;   /* P + s*(4*nnz_lu + 3*n) */
+    int32_t executor;              /* 0 lane VM, 1 chain kernel */
+    int32_t reserved;
 } krb_plan_info;
 
 int32_t krb_plan_get_info(const krb_plan *p, krb_plan_info *info);

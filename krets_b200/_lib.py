@@ -33,7 +33,8 @@ class KrbPlanOpts(C.Structure):         # krb_plan_opts
 class KrbPlanInfo(C.Structure):         # krb_plan_info
     _fields_ = [("n", C.c_int32), ("nnz", C.c_int32), ("nnz_lu", C.c_int32), ("mode", C.c_int32), ("nonlinear", C.c_int32),
                 ("scratch_slots", C.c_int32), ("spill_planes", C.c_int32), ("n_inputs", C.c_int32), ("program_ops", C.c_int64),
-                ("flops_per_point", C.c_int64), ("hbm_bytes_per_point", C.c_int64), ("alg_bytes_per_point", C.c_int64)]
+                ("flops_per_point", C.c_int64), ("hbm_bytes_per_point", C.c_int64), ("alg_bytes_per_point", C.c_int64),
+                ("executor", C.c_int32), ("reserved", C.c_int32)]
 
 
 class KrbIO(C.Structure):               # krb_io
@@ -107,6 +108,8 @@ _DEBUG_SYMBOLS = {
     "krb_plan_wave_value": (_i32, [_vp, _i32, _f64, _pf64]),
     "krb_plan_input_layout": (_i32, [_vp, _pi32, _pi32, _pi32]),
     "krb_plan_has_step_sections": (_i32, [_vp]),
+    "krb_plan_chain_size": (_i64, [_vp]),
+    "krb_plan_get_chain": (_i32, [_vp, _vp, _pi32]),
 }
 
 _lib = None

@@ -289,7 +289,7 @@ class Plan:
     """One-time symbolic analysis of a circuit for one stamp mode (krb_analyze) + lane-batch solves (krb_solve_*)."""
 
     def __init__(self, circuit: Circuit, mode: int, *, sweep_element: int = -1, varied=(), time_step: float = 0.0,
-                 nominal_frequency: float = 0.0, scratch_slots: int = 0, threads_per_block: int = 0):
+                 nominal_frequency: float = 0.0, scratch_slots: int = 0, threads_per_block: int = 0, force_lane_vm: bool = False):
         L = _lib.lib()
         self.circuit, self.mode = circuit, mode
         self.varied = list(varied)
@@ -304,6 +304,7 @@ class Plan:
         o.nominal_frequency = nominal_frequency
         o.scratch_slots = scratch_slots
         o.threads_per_block = threads_per_block
+        o.exec = 2 if force_lane_vm else 0
         self._varied_arr = (C.c_int32 * max(len(self.varied), 1))(*self.varied)
         o.n_varied = len(self.varied)
         o.varied_elements = C.cast(self._varied_arr, C.POINTER(C.c_int32))

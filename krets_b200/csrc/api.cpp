@@ -67,7 +67,7 @@ int32_t krb_analyze(const krb_circuit *c, int32_t mode, const krb_plan_opts *opt
         o = *opts;
     }
     if (o.n_varied < 0 || (o.n_varied > 0 && !o.varied_elements)) { set_error("krb_analyze: varied_elements missing"); return KRB_ERR_INVALID_ARGUMENT; }
-    if (o.exec != KRB_EXEC_FUSED) { set_error("KRB_EXEC_STAGED is not implemented in this build"); return KRB_ERR_UNSUPPORTED; }
+    if (o.exec != KRB_EXEC_FUSED && o.exec != KRB_EXEC_LANE_VM) { set_error("KRB_EXEC_STAGED is not implemented in this build"); return KRB_ERR_UNSUPPORTED; }
     krb_plan *p = new (std::nothrow) krb_plan();
     if (!p) return KRB_ERR_OUT_OF_MEMORY;
     std::string err;
@@ -103,6 +103,8 @@ int32_t krb_plan_get_info(const krb_plan *p, krb_plan_info *info) {
     info->flops_per_point = P.flops_per_point;
     info->hbm_bytes_per_point = P.hbm_bytes_per_point;
     info->alg_bytes_per_point = P.alg_bytes_per_point;
+    info->executor = P.use_chain ? 1 : 0;
+    info->reserved = 0;
     return KRB_OK;
 }
 int32_t krb_plan_get_pattern(const krb_plan *p, int32_t *colptr, int32_t *rowidx) {
@@ -148,6 +150,13 @@ int32_t krb_plan_input_layout(const krb_plan *p, int32_t *input_sweep, int32_t *
     if (input_sweep) *input_sweep = p->p.input_sweep;
     if (input_freq) *input_freq = p->p.input_freq;
     if (input_of_varied) for (size_t i = 0; i < p->p.input_of_varied.size(); i++) input_of_varied[i] = p->p.input_of_varied[i];
+    return KRB_OK;
+}
+int64_t krb_plan_chain_size(const krb_plan *p) { return (p && p->p.chain.valid) ? (int64_t)p->p.chain.terms.size() : 0; }
+int32_t krb_plan_get_chain(const krb_plan *p, void *terms /*16 B each*/, int32_t *unknown_of_row) {
+    if (!p || !p->p.chain.valid) return KRB_ERR_INVALID_ARGUMENT;
+    if (terms) std::memcpy(terms, p->p.chain.terms.data(), p->p.chain.terms.size() * sizeof(ChainTerm));
+    if (unknown_of_row) std::memcpy(unknown_of_row, p->p.chain.unknown_of_row.data(), p->p.chain.unknown_of_row.size() * sizeof(int));
     return KRB_OK;
 }
 int32_t krb_plan_has_step_sections(const krb_plan *p) { return p ? (p->p.has_step_sections ? 1 : 0) : -1; }

@@ -389,6 +389,76 @@ std::vector<Src> rhs_srcs(const Plan &p, int row) {
     return v;
 }
 
+// ---- chain executor tables ------------------------------------------------------------------------------------
+// Applicable when the circuit is linear, the solve is one-shot (DC / AC) and the permuted matrix has lower bandwidth
+// <= 1 and upper bandwidth <= 2:  Lpat[k] in {k-1},  Upat[k] in {k+1, k+2}.
+void build_chain_plan(Plan &plan, const std::vector<int> &input_of_elem) {
+    ChainPlan &ch = plan.chain;
+    ch = ChainPlan();
+    const Symbolic &S = plan.sym;
+    const int n = S.n;
+    if (plan.circuit.nonlinear || plan.mode == KRB_MODE_TRAN || n == 0) return;
+    for (int k = 0; k < n; k++) {
+        for (int j : S.Lpat[k]) if (j != k - 1) return;
+        for (int l : S.Upat[k]) if (l != k + 1 && l != k + 2) return;
+    }
+    auto emit_terms = [&](const std::vector<Src> &srcs, uint32_t target, std::vector<ChainTerm> &out) -> bool {
+        bool have_const = false;     // a constant run being folded (consecutive lane-invariant contributions)
+        double acc = 0.0;
+        auto flush = [&]() { if (have_const) { out.push_back({target, 0u, acc}); have_const = false; acc = 0.0; } };
+        for (const Src &s : srcs) {
+            const krb_element &el = plan.circuit.el[s.elem];
+            const int pl = input_of_elem[s.elem];
+            double cv = 0.0;
+            bool is_const = true;
+            uint32_t kind = 0;
+            double K = 0.0;
+            switch (s.kind) {
+            case S_ONE: cv = 1.0; break;
+            case S_G: if (pl < 0) cv = 1.0 / el.value; else { is_const = false; kind = 2; } break;
+            case S_VAL: if (pl < 0) cv = el.value; else { is_const = false; kind = 1; } break;
+            case S_VOH: if (pl < 0) cv = el.value / plan.opts.time_step; else { is_const = false; kind = 3; K = plan.opts.time_step; } break;
+            case S_ACAMP: cv = el.ac_amplitude; break;
+            case S_JWV: is_const = false; if (pl < 0) { kind = 4; K = el.value; } else kind = 5; break;
+            default: return false;   // nonlinear / history sources never reach the chain executor
+            }
+            if (is_const) {
+                if (s.neg) cv = -cv;
+                acc = have_const ? acc + cv : 0.0 + cv;   // same left-to-right order as sum_triplets
+                have_const = true;
+            } else {
+                flush();   // keep the summation order: the running constant goes first
+                out.push_back({target | (kind << 4) | (s.neg ? (1u << 8) : 0u), (uint32_t)(pl < 0 ? 0 : pl), K});
+            }
+        }
+        flush();
+        return true;
+    };
+    std::vector<ChainTerm> terms;
+    int n_u2 = 0;
+    for (int k = 0; k < n; k++) {
+        std::vector<ChainTerm> row;
+        if (!S.Lpat[k].empty() && !emit_terms(entry_srcs(plan, S.Lent[k][0]), 0u, row)) return;
+        if (!emit_terms(entry_srcs(plan, S.Dent[k]), 1u, row)) return;
+        bool has_u2 = false;
+        for (size_t t = 0; t < S.Upat[k].size(); t++) {
+            const bool far = S.Upat[k][t] == k + 2;
+            has_u2 = has_u2 || far;
+            if (!emit_terms(entry_srcs(plan, S.Uent[k][t]), far ? 3u : 2u, row)) return;
+        }
+        if (!emit_terms(rhs_srcs(plan, S.row_order[k]), 4u, row)) return;
+        if (row.empty()) row.push_back({1u, 0u, 0.0});
+        row.back().meta |= (1u << 31);
+        if (has_u2) { row.back().meta |= (1u << 30); n_u2++; }
+        terms.insert(terms.end(), row.begin(), row.end());
+    }
+    terms.push_back({1u | (1u << 31), 0u, 0.0});   // sentinel: the kernel prefetches one term ahead
+    ch.terms.swap(terms);
+    ch.unknown_of_row = S.col_order;
+    ch.n_u2 = n_u2;
+    ch.valid = true;
+}
+
 }  // namespace
 
 int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan, std::string &err) {
@@ -416,7 +486,23 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
     nominal_magnitudes(c, plan.stamps, plan.pattern, mode, plan.opts.time_step, fnom, mag);
     std::vector<int> match_row, order;
     if (!weighted_matching(plan.pattern, mag, match_row)) { err = "matrix is structurally singular"; return KRB_ERR_DECOMPOSITION_FAILED; }
-    minimum_degree(plan.pattern, match_row, order);
+    // Band-friendly candidates first (netlist order, reverse Cuthill-McKee both ways): ladders and lines come out with
+    // lower bandwidth 1 / upper bandwidth 2 and no fill, which the native chain executor needs; otherwise minimum degree.
+    {
+        bool banded = false;
+        std::vector<int> cand(n);
+        for (int i = 0; i < n; i++) cand[i] = i;
+        if (band_ok(plan.pattern, match_row, cand)) { order = cand; banded = true; }
+        if (!banded && n <= 2000000) {
+            rcm_order(plan.pattern, match_row, cand);
+            if (band_ok(plan.pattern, match_row, cand)) { order = cand; banded = true; }
+            else {
+                std::reverse(cand.begin(), cand.end());
+                if (band_ok(plan.pattern, match_row, cand)) { order = cand; banded = true; }
+            }
+        }
+        if (!banded) minimum_degree(plan.pattern, match_row, order);
+    }
     symbolic_lu(plan.pattern, match_row, order, plan.sym);
     const Symbolic &S = plan.sym;
 
@@ -537,10 +623,14 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
         if (!run_alloc(step_sec, plan.sec[2], true)) return KRB_ERR_INTERNAL;
     }
     plan.n_slots = max_slot + 1;
+    build_chain_plan(plan, B.input_of_elem);
     const int64_t s = plan.is_complex ? 16 : 8;
     plan.hbm_bytes_per_point = plan.hbm_bytes_per_point * s + (int64_t)n * s + 8 * (int64_t)plan.n_inputs;
     plan.flops_per_point = S.flops * (plan.is_complex ? 4 : 1);
     plan.alg_bytes_per_point = 8 * (int64_t)std::max(1, plan.n_inputs) + s * (4 * S.nnz_lu + 3 * (int64_t)n);
+    plan.vm_hbm_bytes_per_point = plan.hbm_bytes_per_point;
+    plan.use_chain = plan.chain.valid && plan.opts.exec != KRB_EXEC_LANE_VM;
+    if (plan.use_chain) plan.hbm_bytes_per_point = s * (5 * (int64_t)n + 2 * plan.chain.n_u2) + 8 * (int64_t)plan.n_inputs;   // 2n(+) out, back, n results
     return KRB_OK;
 }
 

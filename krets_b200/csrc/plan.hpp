@@ -60,6 +60,8 @@ void nominal_magnitudes(const Circuit &c, const Stamps &s, const Pattern &p, int
 bool weighted_matching(const Pattern &p, const std::vector<double> &mag, std::vector<int> &match_row);
 // minimum-degree ordering of the symmetrised, row-permuted pattern; returns order[k] = unknown eliminated k-th
 void minimum_degree(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order);
+void rcm_order(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order);
+bool band_ok(const Pattern &p, const std::vector<int> &match_row, const std::vector<int> &order);
 
 struct Symbolic {
     int n = 0;
@@ -84,6 +86,16 @@ struct Program {
 
 struct DeviceState;
 
+// "chain" executor tables (chain_kernel.cuh): the permuted matrix is tridiagonal, so each pivot row is described by a
+// short run of stamp terms for its sub-diagonal, diagonal, super-diagonal and right-hand side.
+struct ChainTerm { uint32_t meta; uint32_t plane; double K; };   // 16 B, read as one uint4 on the device
+struct ChainPlan {
+    bool valid = false;
+    std::vector<ChainTerm> terms;        // rows in pivot order, last term of a row flagged; one sentinel at the end
+    std::vector<int> unknown_of_row;     // = Symbolic::col_order
+    int n_u2 = 0;                        // rows with a second super-diagonal entry (extra planes 2n .. 2n+n_u2)
+};
+
 struct Plan {
     Circuit circuit;
     DeviceState *dev = nullptr;        // device-side buffers, created lazily by the runtime
@@ -103,6 +115,9 @@ struct Plan {
     int input_sweep = -1, input_freq = -1;   // input plane holding the DC sweep value / the AC frequency
     std::vector<int> input_of_varied;        // input plane of varied[k]
     int64_t flops_per_point = 0, hbm_bytes_per_point = 0, alg_bytes_per_point = 0;
+    ChainPlan chain;                    // filled when the structure allows the native chain executor
+    bool use_chain = false;             // executor selected for krb_solve_* (chain.valid and not forced to the lane VM)
+    int64_t vm_hbm_bytes_per_point = 0;
 };
 
 // full pipeline; returns KRB_* status and fills `err`

@@ -13,6 +13,7 @@
 #include "plan.hpp"
 #include "runtime.hpp"
 #include "vm_kernel.cuh"
+#include "chain_kernel.cuh"
 
 namespace krb {
 
@@ -55,6 +56,9 @@ struct Buf {
 struct DeviceState {
     bool uploaded = false;
     uint2 *sec[3] = {nullptr, nullptr, nullptr};
+    ChainTermDev *chain_terms = nullptr;
+    int *chain_unknown = nullptr;
+    uint32_t *chain_u2_flags = nullptr;
     Buf B, Bstep, IN, G, X, XOP, packed, status, iters;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     size_t events_used = 0;
@@ -67,6 +71,9 @@ void device_state_free(DeviceState *d) {
     if (!d) return;
     if (g_last_timed_fwd() == d) { extern void krb_snapshot_last_ms(DeviceState *); krb_snapshot_last_ms(d); }
     for (int i = 0; i < 3; i++) if (d->sec[i]) cudaFree(d->sec[i]);
+    if (d->chain_terms) cudaFree(d->chain_terms);
+    if (d->chain_unknown) cudaFree(d->chain_unknown);
+    if (d->chain_u2_flags) cudaFree(d->chain_u2_flags);
     d->B.release(); d->Bstep.release(); d->IN.release(); d->G.release(); d->X.release(); d->XOP.release();
     d->packed.release(); d->status.release(); d->iters.release();
     for (auto &e : d->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -103,8 +110,44 @@ static int upload_programs(Plan &plan, DeviceState &d) {
         CUDA_TRY(cudaMalloc(&d.sec[s], padded.size() * sizeof(uint32_t)));
         CUDA_TRY(cudaMemcpy(d.sec[s], padded.data(), padded.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
+    if (plan.use_chain) {
+        static_assert(sizeof(ChainTermDev) == sizeof(ChainTerm) && sizeof(ChainTerm) == 16, "term layout");
+        CUDA_TRY(cudaMalloc(&d.chain_terms, plan.chain.terms.size() * sizeof(ChainTerm)));
+        CUDA_TRY(cudaMemcpy(d.chain_terms, plan.chain.terms.data(), plan.chain.terms.size() * sizeof(ChainTerm), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.chain_unknown, plan.chain.unknown_of_row.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(d.chain_unknown, plan.chain.unknown_of_row.data(), plan.chain.unknown_of_row.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (plan.chain.n_u2 > 0) {
+            const int nrows = (int)plan.chain.unknown_of_row.size();
+            std::vector<uint32_t> bits((nrows + 31) / 32, 0u);
+            int row = 0;
+            for (const ChainTerm &t : plan.chain.terms) {
+                if (row >= nrows) break;
+                if (t.meta & (1u << 31)) { if (t.meta & (1u << 30)) bits[row >> 5] |= 1u << (row & 31); row++; }
+            }
+            CUDA_TRY(cudaMalloc(&d.chain_u2_flags, bits.size() * 4));
+            CUDA_TRY(cudaMemcpy(d.chain_u2_flags, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
     d.uploaded = true;
     return KRB_OK;
+}
+
+template <bool CPLX, int TPB>
+static int launch_chain_t(const ChainParams &p, long long Lpad, cudaStream_t st) {
+    krb_chain_kernel<CPLX, TPB><<<(unsigned)(Lpad / TPB), TPB, 0, st>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return KRB_OK;
+}
+static int launch_chain(bool cplx, int tpb, const ChainParams &p, long long Lpad, cudaStream_t st) {
+    if (cplx) {
+        if (tpb == 32) return launch_chain_t<true, 32>(p, Lpad, st);
+        if (tpb == 128) return launch_chain_t<true, 128>(p, Lpad, st);
+        return launch_chain_t<true, 64>(p, Lpad, st);
+    }
+    if (tpb == 32) return launch_chain_t<false, 32>(p, Lpad, st);
+    if (tpb == 128) return launch_chain_t<false, 128>(p, Lpad, st);
+    return launch_chain_t<false, 64>(p, Lpad, st);
 }
 
 template <bool CPLX, int TPB>
@@ -193,7 +236,8 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     CUDA_TRY(cudaStreamSynchronize(st));   // host vectors above go out of scope
 
     // ---- chunking: bound the per-call device footprint ----
-    const int planes0 = P0.n_planes, planesS = PS ? PS->n_planes : 0;
+    const bool chain = P0.use_chain && !PS;
+    const int planes0 = chain ? 2 * n + P0.chain.n_u2 : P0.n_planes, planesS = PS ? PS->n_planes : 0;
     const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)rows * n * ts * 2 + (size_t)P0.n_inputs * 8 + (a.op_solution ? (size_t)n * 8 : 0) + 16;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -289,7 +333,12 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         cudaEvent_t e0, e1;
         if ((rc = next_events(e0, e1))) return rc;
         CUDA_TRY(cudaEventRecord(e0, st));
-        if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st))) return rc;
+        if (chain) {
+            ChainParams c{};
+            c.terms = D0.chain_terms; c.unknown_of_row = D0.chain_unknown; c.IN = IN; c.UY = D0.G.p; c.X = D0.X.p;
+            c.n = n; c.input_freq = P0.input_freq; c.n_u2 = P0.chain.n_u2; c.u2_flags = D0.chain_u2_flags; c.L = Lpad; c.status = (int *)D0.status.p;
+            if ((rc = launch_chain(cplx, tpb, c, Lpad, st))) return rc;
+        } else if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st))) return rc;
         if (PS) {
             DeviceState &DS = *PS->dev;
             VmParams q = p;

@@ -114,6 +114,28 @@ void minimum_degree(const Pattern &p, const std::vector<int> &match_row, std::ve
             if (j != l) { adj[j].push_back(l); adj[l].push_back(j); }
         }
     for (auto &a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+    // A path graph (every ladder / transmission line) is eliminated end to end: zero fill, and the permuted matrix is
+    // tridiagonal, which the native chain executor relies on.  (Minimum degree gives the same fill but may alternate ends.)
+    {
+        int leaves = 0, first_leaf = -1;
+        bool path = n >= 1;
+        for (int i = 0; i < n && path; i++) {
+            if (adj[i].size() > 2) path = false;
+            else if (adj[i].size() <= 1) { leaves++; if (first_leaf < 0) first_leaf = i; }
+        }
+        if (path && ((n == 1 && leaves == 1) || (n > 1 && leaves == 2))) {
+            order.clear();
+            int prev = -1, cur = first_leaf;
+            while (cur >= 0 && (int)order.size() < n) {
+                order.push_back(cur);
+                int nxt = -1;
+                for (int w : adj[cur]) if (w != prev) nxt = w;
+                prev = cur; cur = nxt;
+            }
+            if ((int)order.size() == n) return;   // connected path
+            order.clear();
+        }
+    }
     std::set<std::pair<int, int>> pq;
     std::vector<int> deg(n);
     for (int i = 0; i < n; i++) { deg[i] = (int)adj[i].size(); pq.insert({deg[i], i}); }
@@ -139,6 +161,65 @@ void minimum_degree(const Pattern &p, const std::vector<int> &match_row, std::ve
         }
         std::vector<int>().swap(adj[v]);
     }
+}
+
+// Reverse Cuthill-McKee on B + B^T from a pseudo-peripheral node (candidate order for the banded chain executor).
+void rcm_order(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order) {
+    const int n = p.n;
+    std::vector<int> col_of_row(n, -1);
+    for (int j = 0; j < n; j++) col_of_row[match_row[j]] = j;
+    std::vector<std::vector<int>> adj(n);
+    for (int l = 0; l < n; l++)
+        for (int q = p.colptr[l]; q < p.colptr[l + 1]; q++) {
+            const int j = col_of_row[p.rowidx[q]];
+            if (j != l) { adj[j].push_back(l); adj[l].push_back(j); }
+        }
+    for (auto &a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+    for (auto &a : adj) std::sort(a.begin(), a.end(), [&](int x, int z) { return adj[x].size() != adj[z].size() ? adj[x].size() < adj[z].size() : x < z; });
+    order.clear();
+    std::vector<int> level(n, -1);
+    auto bfs = [&](int root, std::vector<int> &out) {
+        out.clear();
+        out.push_back(root);
+        level[root] = 0;
+        for (size_t h = 0; h < out.size(); h++)
+            for (int w : adj[out[h]]) if (level[w] < 0) { level[w] = level[out[h]] + 1; out.push_back(w); }
+    };
+    std::vector<char> done(n, 0);
+    std::vector<int> comp, comp2;
+    for (int s = 0; s < n; s++) {
+        if (done[s]) continue;
+        int root = s;
+        for (int iter = 0; iter < 4; iter++) {          // pseudo-peripheral: restart from a deepest, lowest-degree node
+            bfs(root, comp);
+            int far = comp.back();
+            const int depth = level[far];
+            for (int v : comp) if (level[v] == depth && adj[v].size() < adj[far].size()) far = v;
+            for (int v : comp) level[v] = -1;
+            if (far == root) break;
+            bfs(far, comp2);
+            const int depth2 = level[comp2.back()];
+            for (int v : comp2) level[v] = -1;
+            if (depth2 <= depth && iter > 0) break;
+            root = far;
+        }
+        bfs(root, comp);
+        for (int v : comp) { done[v] = 1; order.push_back(v); }
+    }
+    std::reverse(order.begin(), order.end());
+}
+
+// lower bandwidth <= 1 and upper bandwidth <= 2 of the row/column-permuted pattern (the class is closed under LU fill)
+bool band_ok(const Pattern &p, const std::vector<int> &match_row, const std::vector<int> &order) {
+    const int n = p.n;
+    std::vector<int> pos_of_col(n), pos_of_row(n);
+    for (int k = 0; k < n; k++) { pos_of_col[order[k]] = k; pos_of_row[match_row[order[k]]] = k; }
+    for (int col = 0; col < n; col++)
+        for (int q = p.colptr[col]; q < p.colptr[col + 1]; q++) {
+            const int d = pos_of_col[col] - pos_of_row[p.rowidx[q]];   // > 0: upper part
+            if (d < -1 || d > 2) return false;
+        }
+    return true;
 }
 
 void symbolic_lu(const Pattern &p, const std::vector<int> &match_row, const std::vector<int> &order, Symbolic &s) {

@@ -337,3 +337,48 @@ def test_config3_chunk_rc_ladder_5000(oracle):
     assert_close(host[idx], ref, what="RC ladder 5000 sampled lanes")
     # residual of the source row: V(1) = 1 for every lane (row I(V1): V(1) = ac amplitude)
     assert np.max(np.abs(host[:, circuit.index_map["V(1)"]] - 1.0)) < 1e-12
+
+
+# ---- both executors on the same inputs ---------------------------------------------------------------------------
+def test_executors_agree_on_ladder(oracle):
+    """chain kernel (default for ladders) and the general lane VM (forced) against the oracle and each other."""
+    text = netgen.resistor_ladder(500)
+    circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    vals = np.linspace(-3.0, 3.0, 257)
+    ref = oc.solve_dc("V1", -3.0, 3.0, 6.0 / 256, nthreads=8)
+    outs = []
+    for force in (False, True):
+        plan = kb.Plan(circuit, api.MODE_DC, sweep_element=0, force_lane_vm=force)
+        assert plan.info.executor == (0 if force else 1)
+        out, status = plan.solve_dc_sweep(vals)
+        assert not status.any()
+        assert_close(out, ref, what=f"ladder DC force_vm={force}")
+        outs.append(out)
+    assert_close(outs[0], outs[1], rtol=1e-12, what="chain vs lane VM")
+    text = netgen.rc_ladder(200)
+    circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    freqs = kb.generate_frequencies("Decade", 20, 1.0, 1e8)
+    _, ref = oc.solve_ac(freqs, nthreads=8)
+    for force in (False, True):
+        out, status = kb.Plan(circuit, api.MODE_AC, nominal_frequency=1e4, force_lane_vm=force).solve_ac(freqs)
+        assert not status.any()
+        assert_close(out, ref, what=f"RC ladder AC force_vm={force}")
+
+
+def test_chain_monte_carlo_ac(oracle):
+    text = netgen.rc_ladder(30)
+    circuit = kb.parse_circuit_description(text)
+    varied = [circuit.element_index(f"R{k}") for k in range(1, 31)] + [circuit.element_index(f"C{k}") for k in range(1, 31)]
+    lanes = 70
+    rng = np.random.default_rng(11)
+    vals = np.array([[circuit.element_value(e) * (0.95 + 0.1 * rng.random()) for _ in range(lanes)] for e in varied])
+    freqs = np.logspace(1, 7, lanes)
+    plan = kb.Plan(circuit, api.MODE_AC, varied=varied)
+    assert plan.info.executor == 1
+    out, status = plan.solve_ac(freqs, varied_values=np.ascontiguousarray(vals))
+    assert not status.any()
+    for l in (0, 33, 69):
+        oc = oracle.Circuit(text)
+        for k, e in enumerate(varied):
+            oc.set_element_value(e, vals[k, l])
+        assert_close(out[l], oc.solve_ac([freqs[l]])[1][0], what=f"chain MC AC lane {l}")

@@ -244,3 +244,72 @@ def test_program_mesh_with_fill(oracle):
     X = Emulator(plan, len(freqs)).run(freqs[None, :])
     _, ref = oc.solve_ac(freqs)
     assert_close(X[0].T, ref, what="mesh AC")
+
+
+# ---- chain executor tables ---------------------------------------------------------------------------------------
+def test_chain_plan_selected_for_ladders(golden):
+    from vm_emulator import run_chain  # noqa: F401
+    ladder = kb.parse_circuit_description(netgen.resistor_ladder(300))
+    assert kb.Plan(ladder, api.MODE_DC, sweep_element=0).info.executor == 1
+    assert kb.Plan(ladder, api.MODE_DC, sweep_element=0, force_lane_vm=True).info.executor == 0
+    assert kb.Plan(kb.parse_circuit_description(netgen.rc_ladder(300)), api.MODE_AC).info.executor == 1
+    assert kb.Plan(kcirc(golden, "low_pass_filter"), api.MODE_AC).info.executor == 1          # n = 3 path
+    assert kb.Plan(kcirc(golden, "farid_n_najm"), api.MODE_DC).info.executor == 0             # not a path graph
+    assert kb.Plan(kcirc(golden, "diode_iv_curve"), api.MODE_DC).info.executor == 0           # nonlinear -> lane VM
+    assert kb.Plan(kcirc(golden, "dual_rc_ladder"), api.MODE_TRAN, time_step=1e-6).info.executor == 0
+    mesh = kb.parse_circuit_description(netgen.rlc_mesh(4, 4))
+    assert kb.Plan(mesh, api.MODE_AC).info.executor == 0
+
+
+def test_chain_terms_dc_sweep(oracle):
+    from vm_emulator import run_chain
+    kc, oc = kb.parse_circuit_description(netgen.resistor_ladder(500)), oracle.Circuit(netgen.resistor_ladder(500))
+    plan = kb.Plan(kc, api.MODE_DC, sweep_element=0)
+    vals = np.linspace(-2.0, 3.0, 7)
+    X, status = run_chain(plan, vals[None, :], False)
+    assert_close(X.T, oc.solve_dc("V1", -2.0, 3.0, 5.0 / 6.0), what="chain DC sweep")
+    assert not status.any()
+    assert plan.info.hbm_bytes_per_point == 8 * (5 * 501 + 2) + 8      # one row (the source's KCL row) owns a u2 plane
+
+
+def test_chain_terms_ac_and_monte_carlo(oracle, golden):
+    from vm_emulator import run_chain
+    text = netgen.rc_ladder(120)
+    kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    freqs = oracle.generate_frequencies("Decade", 2, 1.0, 1e8)
+    plan = kb.Plan(kc, api.MODE_AC, nominal_frequency=1e4)
+    X, status = run_chain(plan, freqs[None, :], True)
+    _, ref = oc.solve_ac(freqs)
+    assert_close(X.T, ref, what="chain AC")
+    # an RLC line: the weighted matching pairs inductor-branch equations with node voltages (better pivots), which takes
+    # it out of the (1,2)-band class -> general lane VM, same answers
+    text = "V1 a 0 1 AC 1\nL1 a b 1u\nC1 b 0 1n\nL2 b c 2u\nC2 c 0 1n\nR1 c 0 50\n"
+    kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    plan = kb.Plan(kc, api.MODE_AC, nominal_frequency=1e6)
+    freqs = np.array([1.0, 1e5, 3e6, 1e9])
+    if plan.info.executor == 1:
+        X, _ = run_chain(plan, freqs[None, :], True)
+    else:
+        X = Emulator(plan, len(freqs)).run(freqs[None, :])[0]
+    assert_close(X.T, oc.solve_ac(freqs)[1], what="RLC line")
+    # Monte-Carlo: every resistor of a ladder varied + AC with varied capacitors
+    text = netgen.rc_ladder(12)
+    kc = kb.parse_circuit_description(text)
+    varied = [kc.element_index(f"R{k}") for k in (1, 5, 12)] + [kc.element_index(f"C{k}") for k in (2, 7)]
+    lanes = 4
+    rng = np.random.default_rng(3)
+    vals = np.array([[kc.element_value(e) * (0.9 + 0.2 * rng.random()) for _ in range(lanes)] for e in varied])
+    plan = kb.Plan(kc, api.MODE_AC, varied=varied)
+    assert plan.info.executor == 1
+    _, fi, iov = input_layout(plan)
+    IN = np.zeros((plan.info.n_inputs, lanes))
+    f = np.array([10.0, 1e3, 1e5, 1e7])
+    IN[fi] = f
+    for k, pl in enumerate(iov):
+        IN[pl] = vals[k]
+    X, _ = run_chain(plan, IN, True)
+    for l in range(lanes):
+        oc = oracle.Circuit(text)
+        for k, e in enumerate(varied):
+            oc.set_element_value(e, vals[k, l])
+        assert_close(X[:, l], oc.solve_ac([f[l]])[1][0], what=f"chain MC lane {l}")

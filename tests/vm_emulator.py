@@ -156,3 +156,74 @@ class Emulator:
                     if not active.any():
                         break
         return X
+
+
+# ---- chain executor term stream (chain_kernel.cuh) --------------------------------------------------------------
+def run_chain(plan, IN, cplx):
+    """numpy restatement of krb_chain_kernel: IN [n_inputs][L] -> X [n][L]."""
+    L_ = _lib.lib()
+    nt = int(L_.krb_plan_chain_size(plan._h))
+    assert nt > 0, "plan has no chain tables"
+    raw = np.zeros(nt, dtype=np.dtype([("meta", "<u4"), ("plane", "<u4"), ("K", "<f8")]))
+    unk = np.zeros(plan.n, dtype=np.int32)
+    L_.krb_plan_get_chain(plan._h, raw.ctypes.data_as(C.c_void_p), unk.ctypes.data_as(C.POINTER(C.c_int32)))
+    lanes = IN.shape[1]
+    sweep, freq, _ = input_layout(plan)
+    w = (2.0 * np.pi) * IN[freq] if (cplx and freq >= 0) else np.zeros(lanes)
+    dt = np.complex128 if cplx else np.float64
+    n = plan.n
+    U1 = np.zeros((n, lanes), dtype=dt)
+    U2 = np.zeros((n, lanes), dtype=dt)
+    Y = np.zeros((n, lanes), dtype=dt)
+    pu1 = np.zeros(lanes, dtype=dt)
+    pu2 = np.zeros(lanes, dtype=dt)
+    py = np.zeros(lanes, dtype=dt)
+    status = np.zeros(lanes, dtype=np.int32)
+    has_u2 = np.zeros(n, dtype=bool)
+    i = 0
+    with np.errstate(all="ignore"):
+        for k in range(n):
+            e = [np.zeros(lanes, dtype=dt) for _ in range(5)]
+            while True:
+                meta, plane, K = int(raw["meta"][i]), int(raw["plane"][i]), float(raw["K"][i])
+                i += 1
+                kind = (meta >> 4) & 0xF
+                if kind == 0:
+                    v = np.full(lanes, K, dtype=dt)
+                elif kind == 1:
+                    v = IN[plane].astype(dt)
+                elif kind == 2:
+                    v = (1.0 / IN[plane]).astype(dt)
+                elif kind == 3:
+                    v = (IN[plane] / K).astype(dt)
+                elif kind == 4:
+                    v = 1j * (w * K)
+                elif kind == 5:
+                    v = 1j * (w * IN[plane])
+                else:
+                    raise ValueError(kind)
+                if meta & (1 << 8):
+                    v = -v
+                e[meta & 7] = e[meta & 7] + v
+                if meta & (1 << 31):
+                    has_u2[k] = bool(meta & (1 << 30))
+                    break
+            wk = e[1] - e[0] * pu1
+            s1 = e[2] - e[0] * pu2
+            yk = e[4] - e[0] * py
+            inv = 1.0 / wk
+            status[~np.isfinite(inv)] |= ZERO_PIVOT
+            pu1, pu2, py = s1 * inv, e[3] * inv, yk * inv
+            assert has_u2[k] or not np.any(pu2 != 0), "u2 plane flag missing"
+            U1[k], U2[k], Y[k] = pu1, pu2, py
+        X = np.zeros((n, lanes), dtype=dt)
+        x1 = np.zeros(lanes, dtype=dt)
+        x2 = np.zeros(lanes, dtype=dt)
+        for k in range(n - 1, -1, -1):
+            x = Y[k] - U1[k] * x1
+            if has_u2[k]:
+                x = x - U2[k] * x2
+            X[unk[k]] = x
+            x2, x1 = x1, x
+    assert i == nt - 1, "term stream must end with exactly one sentinel"
+    return X, status
