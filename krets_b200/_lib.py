@@ -109,7 +109,7 @@ _DEBUG_SYMBOLS = {
     "krb_plan_input_layout": (_i32, [_vp, _pi32, _pi32, _pi32]),
     "krb_plan_has_step_sections": (_i32, [_vp]),
     "krb_plan_chain_size": (_i64, [_vp]),
-    "krb_plan_get_chain": (_i32, [_vp, _vp, _pi32]),
+    "krb_plan_get_chain": (_i32, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), _pi32]),
 }
 
 _lib = None

@@ -152,11 +152,13 @@ int32_t krb_plan_input_layout(const krb_plan *p, int32_t *input_sweep, int32_t *
     if (input_of_varied) for (size_t i = 0; i < p->p.input_of_varied.size(); i++) input_of_varied[i] = p->p.input_of_varied[i];
     return KRB_OK;
 }
-int64_t krb_plan_chain_size(const krb_plan *p) { return (p && p->p.chain.valid) ? (int64_t)p->p.chain.terms.size() : 0; }
-int32_t krb_plan_get_chain(const krb_plan *p, void *terms /*16 B each*/, int32_t *unknown_of_row) {
+int64_t krb_plan_chain_size(const krb_plan *p) { return (p && p->p.chain.valid) ? (int64_t)p->p.chain.stream.size() : 0; }   /* 8-byte words */
+int32_t krb_plan_get_chain(const krb_plan *p, uint32_t *rowinfo /*n+1*/, uint64_t *stream, int32_t *unknown_of_row) {
     if (!p || !p->p.chain.valid) return KRB_ERR_INVALID_ARGUMENT;
-    if (terms) std::memcpy(terms, p->p.chain.terms.data(), p->p.chain.terms.size() * sizeof(ChainTerm));
-    if (unknown_of_row) std::memcpy(unknown_of_row, p->p.chain.unknown_of_row.data(), p->p.chain.unknown_of_row.size() * sizeof(int));
+    const ChainPlan &ch = p->p.chain;
+    if (rowinfo) std::memcpy(rowinfo, ch.rowinfo.data(), ch.rowinfo.size() * 4);
+    if (stream) std::memcpy(stream, ch.stream.data(), ch.stream.size() * 8);
+    if (unknown_of_row) std::memcpy(unknown_of_row, ch.unknown_of_row.data(), ch.unknown_of_row.size() * sizeof(int));
     return KRB_OK;
 }
 int32_t krb_plan_has_step_sections(const krb_plan *p) { return p ? (p->p.has_step_sections ? 1 : 0) : -1; }

@@ -1,21 +1,25 @@
-// "Chain" executor: plans whose permuted matrix has lower bandwidth <= 1 and upper bandwidth <= 2 (ladders, RC/RLC
-// lines and other path-like circuits, including the source row that couples two neighbours).
+// "Chain" executor: plans whose permuted matrix has lower bandwidth <= 1 and upper bandwidth <= 2 (ladders, RC lines
+// and other path-like circuits, including the source row that couples two neighbours).
 //
-// One thread = one lane.  The forward sweep stamps row k from a lane-invariant TERM STREAM (16 B per term, one broadcast
-// load per warp, prefetched one term ahead), eliminates it against the previous row kept in registers (Thomas-style
-// recurrence on the LDU form  u^_k = sup_k / w_k,  y^_k = y_k / w_k) and streams u^_k, y^_k to lane-interleaved HBM
-// planes; the backward sweep re-reads them in reverse with an 8-row register prefetch ring and delivers x.  Per point
-// the kernel moves 2n values out, 2n back and n results — a third of the 3-pass stamp/factor/solve traffic of SURVEY §8(d).
+// One thread = one lane.  The forward sweep stamps row k from a lane-invariant ROW STREAM, eliminates it against the
+// previous row kept in registers (Thomas-style recurrence on the LDU form  u^_k = sup_k / w_k,  y^_k = y_k / w_k) and
+// streams u^_k, y^_k to lane-interleaved HBM planes; the backward sweep re-reads them in reverse through a
+// double-buffered register prefetch ring and delivers x.  Per point the kernel moves 2n values out, 2n back and n
+// results — a third of the 3-pass stamp/factor/solve traffic of SURVEY §8(d).
+//
+// Row stream (built by the host, compiler.cpp::build_chain_plan), 16-byte units, one broadcast load per warp:
+//   FIXED row   : every entry is one folded lane-invariant constant (+ at most one j*w*K term)  ->  the record is just
+//                 {sub, diag, sup1, rhs} (real: 2 units) or {re[4], K[4]} (complex: 4 units): no per-term decoding;
+//   GENERIC row : a run of 16-byte terms (target, kind, input plane, K) for Monte-Carlo values, swept sources, rows
+//                 with a second super-diagonal, several reactive elements on one node, ...
+// Both keep the reference's left-to-right summation order of duplicate stamps (solver.rs:59-70).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/krets_b200.h"
-#include "vm_kernel.cuh"
 
 namespace krb {
-
-struct ChainTermDev { uint32_t meta; uint32_t plane; double K; };   // same layout as krb::ChainTerm (plan.hpp)
 
 enum : uint32_t {
     CT_SUB = 0, CT_DIAG = 1, CT_SUP1 = 2, CT_SUP2 = 3, CT_RHS = 4,
@@ -26,22 +30,29 @@ enum : uint32_t {
     CK_JW_K = 4,        // (0, ((2 pi) f) K)               (C / L admittance, stampable.rs:379-382, 715)
     CK_JW_IN = 5,       // (0, ((2 pi) f) IN[plane])
     CT_NEG = 1u << 8,
-    CT_HAS_U2 = 1u << 30,   // (on the last term of a row) the row has a second super-diagonal: u2 lives in plane 2n + rank
-    CT_LAST = 1u << 31
+    // row info word (one uint32 per row)
+    RI_FIXED = 1u,            // bit 0: FIXED record, else GENERIC
+    RI_HAS_U2 = 2u,           // bit 1: the row owns a u2 plane (second super-diagonal)
+    RI_NTERMS_SHIFT = 8       // GENERIC: number of terms
 };
 
 struct ChainParams {
-    const ChainTermDev *terms;
+    const uint32_t *rowinfo;     // [n + 1] (one sentinel)
+    const uint4 *stream;         // row records, 16-byte units, padded with 4 zero units
     const int *unknown_of_row;   // pivot row k delivers unknown unknown_of_row[k]
-    const uint32_t *u2_flags;    // bitset over rows (null when n_u2 == 0)
     const double *IN;            // [n_inputs][L]
     void *UY;                    // [2n + n_u2][L] of T: plane 2k = u^_{k,k+1}, 2k+1 = y^_k, 2n + r = u^_{k,k+2} of the r-th flagged row
-    void *X;                     // [n][L] of T
+    void *X;                     // [n][L] of T (staging for the pack kernel / lane-interleaved delivery), or
+    void *OUT;                   // point-major x_out[lane][unknown] written directly (when the pivot order is the unknown order)
+    long long out_lanes;         // lanes actually delivered to OUT (lanes >= out_lanes are padding)
+    const int *u2_rows;          // rows owning a u2 plane, ascending (n_u2 entries)
     int n;
     int input_freq;              // input plane holding the AC frequency, or -1
     int n_u2;
-    long long L;
+    long long L;                 // lane stride of every plane (padded lane count)
     int *status;
+    int pf_units;                // L1 prefetch distance of the row stream, in 16-byte units (0 = off)
+    int debug;                   // profiling only: 1 = no forward stores, 2 = skip backward, 4 = skip forward
 };
 
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -59,14 +70,17 @@ template <bool CPLX> struct ChainSc;
 template <> struct ChainSc<false> {
     typedef double T;
     static __device__ __forceinline__ T zero() { return 0.0; }
+    static __device__ __forceinline__ T make(double re, double) { return re; }
     static __device__ __forceinline__ T fnma(T d, T a, T b) { return fma(-a, b, d); }
     static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
     static __device__ __forceinline__ T rcp(T a, bool &bad) { const double r = fast_rcp(a); bad = !isfinite(r); return r; }
     static __device__ __forceinline__ bool finite(T a) { return isfinite(a); }
+    static __device__ __forceinline__ void add(T &acc, double re, double) { acc = __dadd_rn(acc, re); }
 };
 template <> struct ChainSc<true> {
     typedef double2 T;
     static __device__ __forceinline__ T zero() { return make_double2(0.0, 0.0); }
+    static __device__ __forceinline__ T make(double re, double im) { return make_double2(re, im); }
     static __device__ __forceinline__ T fnma(T d, T a, T b) {
         return make_double2(fma(a.y, b.y, fma(-a.x, b.x, d.x)), fma(-a.y, b.x, fma(-a.x, b.y, d.y)));
     }
@@ -78,63 +92,95 @@ template <> struct ChainSc<true> {
         return make_double2(a.x * r, -a.y * r);
     }
     static __device__ __forceinline__ bool finite(T a) { return isfinite(a.x) && isfinite(a.y); }
+    static __device__ __forceinline__ void add(T &acc, double re, double im) { acc.x = __dadd_rn(acc.x, re); acc.y = __dadd_rn(acc.y, im); }
 };
 
-template <bool CPLX>
-__device__ __forceinline__ void chain_add(typename ChainSc<CPLX>::T &acc, double re, double im);
-template <> __device__ __forceinline__ void chain_add<false>(double &acc, double re, double) { acc = __dadd_rn(acc, re); }
-template <> __device__ __forceinline__ void chain_add<true>(double2 &acc, double re, double im) {
-    acc.x = __dadd_rn(acc.x, re);
-    acc.y = __dadd_rn(acc.y, im);
-}
+__device__ __forceinline__ double u4lo(const uint4 &v) { return __hiloint2double((int)v.y, (int)v.x); }
+__device__ __forceinline__ double u4hi(const uint4 &v) { return __hiloint2double((int)v.w, (int)v.z); }
 
-template <bool CPLX, int TPB>
-__global__ void __launch_bounds__(TPB) krb_chain_kernel(const ChainParams p) {
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// DIRECT: deliver point-major results straight from the backward sweep (pivot row k == unknown k), staging 32 lanes x R
+// rows per warp through shared memory so that every store instruction writes 64-byte runs of the caller's rows.
+template <bool CPLX, int TPB, bool DIRECT>
+__global__ void __launch_bounds__(TPB, (TPB == 32 ? 14 : TPB == 64 ? 7 : 3)) krb_chain_kernel(const ChainParams p) {
     typedef ChainSc<CPLX> S;
     typedef typename S::T T;
+    constexpr int FIX_UNITS = CPLX ? 4 : 2;
     const long long lane = (long long)blockIdx.x * TPB + threadIdx.x;
     const long long L = p.L;
     const double *__restrict__ IN = p.IN + lane;
+    const int n = p.n;
+    // lane-interleaved planes P[idx][lane]: at any moment the whole grid writes (forward) or reads (backward) the same
+    // few planes, i.e. the GPU walks HBM sequentially (measured faster than per-block tiling of the planes)
     T *__restrict__ UY = reinterpret_cast<T *>(p.UY) + lane;
     T *__restrict__ X = reinterpret_cast<T *>(p.X) + lane;
-    const int n = p.n;
     int status = 0;
 
     double w = 0.0;                                   // (2.0 * PI) * f, rounded once as the reference does
     if (CPLX && p.input_freq >= 0) w = __dmul_rn(2.0 * 3.14159265358979323846264338327950288, IN[(size_t)p.input_freq * L]);
 
-    // ---- forward: stamp + eliminate + forward-substitute, row by row ----
-    const uint4 *__restrict__ tp = reinterpret_cast<const uint4 *>(p.terms);
+    // ---- forward: stamp + eliminate + forward-substitute, row by row; the next row's record is prefetched ----
+    const uint4 *__restrict__ dp = p.stream;
     T pu1 = S::zero(), pu2 = S::zero(), py = S::zero();   // u^_{k-1,k}, u^_{k-1,k+1}, y^_{k-1}
     int r2 = 0;                                         // rank of the next row that owns a u2 plane (warp-uniform)
-    uint4 t = __ldg(tp);
-    for (int k = 0; k < n; ++k) {
-        T e0 = S::zero(), e1 = S::zero(), e2 = S::zero(), e3 = S::zero(), e4 = S::zero();
-        uint32_t meta;
-        for (;;) {
-            const uint4 cur = t;
-            t = __ldg(++tp);                          // next term (the stream ends with one sentinel)
-            const double K = __hiloint2double((int)cur.w, (int)cur.z);
-            const uint32_t kind = (cur.x >> 4) & 0xfu;
-            double re = 0.0, im = 0.0;
-            if (kind == CK_CONST) re = K;
-            else if (kind == CK_JW_K) im = __dmul_rn(w, K);
-            else {
-                const double v = IN[(size_t)cur.y * L];
-                if (kind == CK_IN) re = v;
-                else if (kind == CK_INV_IN) re = __ddiv_rn(1.0, v);
-                else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
-                else im = __dmul_rn(w, v);
+    uint32_t info = __ldg(p.rowinfo);
+    uint4 q[FIX_UNITS];
+#pragma unroll
+    for (int i = 0; i < FIX_UNITS; ++i) q[i] = __ldg(dp + i);
+    for (int k = 0; k < ((p.debug & 4) ? 0 : n); ++k) {
+        const uint32_t ci = info;
+        uint4 c[FIX_UNITS];
+#pragma unroll
+        for (int i = 0; i < FIX_UNITS; ++i) c[i] = q[i];
+        const uint4 *__restrict__ row = dp;
+        dp += (ci & RI_FIXED) ? FIX_UNITS : (int)(ci >> RI_NTERMS_SHIFT);
+        info = __ldg(p.rowinfo + k + 1);              // sentinel at n
+#pragma unroll
+        for (int i = 0; i < FIX_UNITS; ++i) q[i] = __ldg(dp + i);   // next row's record (the stream is padded)
+        if (p.pf_units > 0) {                         // keep the (warp-shared, read-once) row stream well ahead in L1
+            prefetch_l1(dp + p.pf_units);
+            if ((k & 7) == 0) prefetch_l1(p.rowinfo + k + p.pf_units);
+        }
+
+        T e0, e1, e2, e3 = S::zero(), e4;
+        if (ci & RI_FIXED) {
+            if (CPLX) {
+                e0 = S::make(u4lo(c[0]), __dmul_rn(w, u4lo(c[2])));
+                e1 = S::make(u4hi(c[0]), __dmul_rn(w, u4hi(c[2])));
+                e2 = S::make(u4lo(c[1]), __dmul_rn(w, u4lo(c[FIX_UNITS - 1])));
+                e4 = S::make(u4hi(c[1]), 0.0);
+            } else {
+                e0 = S::make(u4lo(c[0]), 0.0);
+                e1 = S::make(u4hi(c[0]), 0.0);
+                e2 = S::make(u4lo(c[1]), 0.0);
+                e4 = S::make(u4hi(c[1]), 0.0);
             }
-            if (cur.x & CT_NEG) { re = -re; im = -im; }
-            const uint32_t tgt = cur.x & 7u;            // warp-uniform: no divergence, accumulators stay in registers
-            if (tgt == CT_SUB) chain_add<CPLX>(e0, re, im);
-            else if (tgt == CT_DIAG) chain_add<CPLX>(e1, re, im);
-            else if (tgt == CT_SUP1) chain_add<CPLX>(e2, re, im);
-            else if (tgt == CT_SUP2) chain_add<CPLX>(e3, re, im);
-            else chain_add<CPLX>(e4, re, im);
-            meta = cur.x;
-            if (meta & CT_LAST) break;
+        } else {
+            e0 = e1 = e2 = e4 = S::zero();
+            const int nt = (int)(ci >> RI_NTERMS_SHIFT);
+            for (int t = 0; t < nt; ++t) {
+                const uint4 cur = __ldg(row + t);
+                const double K = u4hi(cur);
+                const uint32_t kind = (cur.x >> 4) & 0xfu;
+                double re = 0.0, im = 0.0;
+                if (kind == CK_CONST) re = K;
+                else if (kind == CK_JW_K) im = __dmul_rn(w, K);
+                else {
+                    const double v = IN[(size_t)cur.y * L];
+                    if (kind == CK_IN) re = v;
+                    else if (kind == CK_INV_IN) re = __ddiv_rn(1.0, v);
+                    else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
+                    else im = __dmul_rn(w, v);
+                }
+                if (cur.x & CT_NEG) { re = -re; im = -im; }
+                const uint32_t tgt = cur.x & 7u;       // warp-uniform: no divergence, accumulators stay in registers
+                if (tgt == CT_SUB) S::add(e0, re, im);
+                else if (tgt == CT_DIAG) S::add(e1, re, im);
+                else if (tgt == CT_SUP1) S::add(e2, re, im);
+                else if (tgt == CT_SUP2) S::add(e3, re, im);
+                else S::add(e4, re, im);
+            }
         }
         const T wk = S::fnma(e1, e0, pu1);            // w_k     = diag - sub * u^_{k-1,k}
         const T s1 = S::fnma(e2, e0, pu2);            // sup1'   = sup1 - sub * u^_{k-1,k+1}
@@ -145,43 +191,86 @@ __global__ void __launch_bounds__(TPB) krb_chain_kernel(const ChainParams p) {
         pu1 = S::mul(s1, inv);
         pu2 = S::mul(e3, inv);
         py = S::mul(yk, inv);
+        if (!(p.debug & 1)) {
         __stcs(&UY[(size_t)(2 * k) * L], pu1);
         __stcs(&UY[(size_t)(2 * k + 1) * L], py);
-        if (meta & CT_HAS_U2) { __stcs(&UY[(size_t)(2 * n + r2) * L], pu2); ++r2; }
+        }
+        if (ci & RI_HAS_U2) { __stcs(&UY[(size_t)(2 * n + r2) * L], pu2); ++r2; }
     }
 
-    // ---- backward: x_k = y^_k - u^_{k,k+1} x_{k+1} - u^_{k,k+2} x_{k+2}, reverse stream with an 8-row prefetch ring ----
-    constexpr int R = 8;
+    // ---- backward: x_k = y^_k - u^_{k,k+1} x_{k+1} - u^_{k,k+2} x_{k+2}; reverse stream, double-buffered prefetch ----
+    constexpr int R = CPLX ? 4 : 8;
+    __shared__ T tile[DIRECT ? TPB / 32 : 1][DIRECT ? 32 : 1][R + 1];
+    const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31;
+    const long long lane_w0 = lane - lid;             // first lane of this warp
     T x1 = S::zero(), x2 = S::zero();                 // x_{k+1}, x_{k+2}
-    const uint32_t *__restrict__ flags = p.u2_flags;  // bit per row: owns a u2 plane
-    for (int k0 = n - 1; k0 >= 0; k0 -= R) {
-        T u[R], y[R];
-        int un[R];
+    const size_t rs = (size_t)2 * (size_t)L;          // plane stride between consecutive rows, in T
+    int nu = p.n_u2 - 1;                              // next (largest remaining) row that owns a u2 plane
+    int next_u2 = nu >= 0 ? __ldg(p.u2_rows + nu) : -1;
+    T ua[R], ya[R], ub[R], yb[R];
+    auto load_group = [&](int k0, T *u, T *y) {       // rows k0 .. k0-R+1, all valid
+        const T *base = UY + (size_t)k0 * rs;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            const int k = k0 - j;
-            if (k >= 0) {
-                u[j] = __ldcs(&UY[(size_t)(2 * k) * L]);
-                y[j] = __ldcs(&UY[(size_t)(2 * k + 1) * L]);
-                un[j] = __ldg(p.unknown_of_row + k);
-            }
+            u[j] = __ldcs(base - (size_t)j * rs);
+            y[j] = __ldcs(base - (size_t)j * rs + L);
         }
+    };
+    auto solve_row = [&](int k, T u, T y) -> T {
+        T x = S::fnma(y, u, x1);
+        if (k == next_u2) {                           // rare (e.g. the source's KCL row): not prefetched
+            x = S::fnma(x, __ldcs(&UY[(size_t)(2 * n + nu) * L]), x2);
+            --nu;
+            next_u2 = nu >= 0 ? __ldg(p.u2_rows + nu) : -1;
+        }
+        x2 = x1;
+        x1 = x;
+        return x;
+    };
+    auto deliver_group = [&](int k0, const T *u, const T *y) {
+        T xs[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-            const int k = k0 - j;
-            if (k >= 0) {
-                T x = S::fnma(y[j], u[j], x1);
-                if (flags && ((__ldg(flags + (k >> 5)) >> (k & 31)) & 1u)) {   // rare (e.g. the source row): not prefetched
-                    --r2;
-                    x = S::fnma(x, __ldcs(&UY[(size_t)(2 * n + r2) * L]), x2);
-                }
-                if (!S::finite(x)) status |= KRB_LANE_NONFINITE;
-                X[(size_t)un[j] * L] = x;
-                x2 = x1;
-                x1 = x;
+        for (int j = 0; j < R; ++j) xs[j] = solve_row(k0 - j, u[j], y[j]);
+        if (DIRECT) {
+            // tile[lane][j] holds unknown k0-j of that lane; thread t then writes R-long runs of 32/R... lanes per pass
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < R; ++j) tile[warp][lid][j] = xs[j];
+            __syncwarp();
+            T *out = reinterpret_cast<T *>(p.OUT);
+            constexpr int LANES_PER_PASS = 32 / R;
+#pragma unroll
+            for (int pass = 0; pass < R; ++pass) {
+                const int l = pass * LANES_PER_PASS + lid / R, j = R - 1 - (lid % R);   // ascending unknown within a run
+                const long long gl = lane_w0 + l;
+                if (gl < p.out_lanes) out[(size_t)gl * (size_t)n + (size_t)(k0 - j)] = tile[warp][l][j];
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) X[(size_t)__ldg(p.unknown_of_row + (k0 - j)) * L] = xs[j];
         }
+    };
+    int k0 = (p.debug & 2) ? -1 : n - 1;
+    if (p.debug & 1) x1 = S::fnma(pu1, py, pu2);
+    if (k0 >= R - 1) {
+        load_group(k0, ua, ya);
+        while (k0 >= 2 * R - 1 + R) {                 // two more full groups follow the current one
+            load_group(k0 - R, ub, yb);
+            deliver_group(k0, ua, ya);
+            load_group(k0 - 2 * R, ua, ya);
+            deliver_group(k0 - R, ub, yb);
+            k0 -= 2 * R;
+        }
+        deliver_group(k0, ua, ya);
+        k0 -= R;
+        while (k0 >= R - 1) { load_group(k0, ua, ya); deliver_group(k0, ua, ya); k0 -= R; }
     }
+    for (; k0 >= 0; --k0) {                           // tail: fewer than R rows
+        const T x = solve_row(k0, __ldcs(&UY[(size_t)(2 * k0) * L]), __ldcs(&UY[(size_t)(2 * k0 + 1) * L]));
+        if (DIRECT) { if (lane < p.out_lanes) reinterpret_cast<T *>(p.OUT)[(size_t)lane * (size_t)n + (size_t)k0] = x; }
+        else X[(size_t)__ldg(p.unknown_of_row + k0) * L] = x;
+    }
+    if (!S::finite(x1)) status |= KRB_LANE_NONFINITE;   // non-finite values propagate down the recurrence to x_0
     if (p.status) p.status[lane] |= status;
 }
 

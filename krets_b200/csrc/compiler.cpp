@@ -434,8 +434,9 @@ void build_chain_plan(Plan &plan, const std::vector<int> &input_of_elem) {
         flush();
         return true;
     };
-    std::vector<ChainTerm> terms;
-    int n_u2 = 0;
+    auto dbits = [](double v) { uint64_t b; std::memcpy(&b, &v, 8); return b; };
+    const bool cplx = plan.is_complex;
+    int n_u2 = 0, n_fixed = 0;
     for (int k = 0; k < n; k++) {
         std::vector<ChainTerm> row;
         if (!S.Lpat[k].empty() && !emit_terms(entry_srcs(plan, S.Lent[k][0]), 0u, row)) return;
@@ -447,15 +448,45 @@ void build_chain_plan(Plan &plan, const std::vector<int> &input_of_elem) {
             if (!emit_terms(entry_srcs(plan, S.Uent[k][t]), far ? 3u : 2u, row)) return;
         }
         if (!emit_terms(rhs_srcs(plan, S.row_order[k]), 4u, row)) return;
-        if (row.empty()) row.push_back({1u, 0u, 0.0});
-        row.back().meta |= (1u << 31);
-        if (has_u2) { row.back().meta |= (1u << 30); n_u2++; }
-        terms.insert(terms.end(), row.begin(), row.end());
+        // FIXED record: per entry one folded constant run and at most one j*w*K term (components are independent, so the
+        // reference's summation order is preserved); no second super-diagonal, no per-lane inputs.
+        bool fixed = !has_u2;
+        double re[5] = {0, 0, 0, 0, 0}, jw[5] = {0, 0, 0, 0, 0};
+        int nre[5] = {0, 0, 0, 0, 0}, njw[5] = {0, 0, 0, 0, 0};
+        for (const ChainTerm &t : row) {
+            const uint32_t tgt = t.meta & 7u, kind = (t.meta >> 4) & 0xfu;
+            if (kind == 0) { re[tgt] = t.K; nre[tgt]++; }
+            else if (kind == 4 && cplx) { jw[tgt] = (t.meta & (1u << 8)) ? -t.K : t.K; njw[tgt]++; }
+            else fixed = false;
+        }
+        for (int g = 0; g < 5; g++) if (nre[g] > 1 || njw[g] > 1) fixed = false;
+        if (njw[4] || nre[3] || njw[3]) fixed = false;
+        if (fixed) {
+            ch.rowinfo.push_back(1u);
+            ch.stream.push_back(dbits(re[0])); ch.stream.push_back(dbits(re[1]));
+            ch.stream.push_back(dbits(re[2])); ch.stream.push_back(dbits(re[4]));
+            if (cplx) {
+                ch.stream.push_back(dbits(jw[0])); ch.stream.push_back(dbits(jw[1]));
+                ch.stream.push_back(dbits(jw[2])); ch.stream.push_back(dbits(0.0));
+            }
+            n_fixed++;
+        } else {
+            ch.rowinfo.push_back((has_u2 ? 2u : 0u) | ((uint32_t)row.size() << 8));
+            for (const ChainTerm &t : row) {
+                ch.stream.push_back((uint64_t)t.meta | ((uint64_t)t.plane << 32));
+                ch.stream.push_back(dbits(t.K));
+            }
+            if (has_u2) { n_u2++; ch.u2_rows.push_back(k); }
+        }
     }
-    terms.push_back({1u | (1u << 31), 0u, 0.0});   // sentinel: the kernel prefetches one term ahead
-    ch.terms.swap(terms);
+    ch.rowinfo.push_back(1u);                                   // sentinel row (prefetched, never used)
+    for (int i = 0; i < 2 * 1100; i++) ch.stream.push_back(0);   // the kernel reads one record and prefetches up to 1024 units past the end
+    for (int i = 0; i < 1100; i++) ch.rowinfo.push_back(1u);
     ch.unknown_of_row = S.col_order;
+    ch.identity_order = true;
+    for (int k = 0; k < n; k++) if (S.col_order[k] != k) ch.identity_order = false;
     ch.n_u2 = n_u2;
+    ch.n_fixed = n_fixed;
     ch.valid = true;
 }
 

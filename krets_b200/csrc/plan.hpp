@@ -88,12 +88,16 @@ struct DeviceState;
 
 // "chain" executor tables (chain_kernel.cuh): the permuted matrix is tridiagonal, so each pivot row is described by a
 // short run of stamp terms for its sub-diagonal, diagonal, super-diagonal and right-hand side.
-struct ChainTerm { uint32_t meta; uint32_t plane; double K; };   // 16 B, read as one uint4 on the device
+struct ChainTerm { uint32_t meta; uint32_t plane; double K; };   // 16 B, one GENERIC-row term (chain_kernel.cuh)
 struct ChainPlan {
     bool valid = false;
-    std::vector<ChainTerm> terms;        // rows in pivot order, last term of a row flagged; one sentinel at the end
+    std::vector<uint32_t> rowinfo;       // per pivot row (+1 sentinel): bit0 FIXED, bit1 HAS_U2, bits 8.. = #terms of a GENERIC row
+    std::vector<uint64_t> stream;        // 16-byte units (2 words each): FIXED records / GENERIC terms, padded with 4 zero units
     std::vector<int> unknown_of_row;     // = Symbolic::col_order
     int n_u2 = 0;                        // rows with a second super-diagonal entry (extra planes 2n .. 2n+n_u2)
+    int n_fixed = 0;                     // rows encoded as FIXED records
+    std::vector<int> u2_rows;            // rows owning a u2 plane, ascending
+    bool identity_order = false;         // unknown_of_row[k] == k: results can be delivered point-major straight from the kernel
 };
 
 struct Plan {

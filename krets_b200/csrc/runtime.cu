@@ -1,19 +1,26 @@
-// Device runtime behind the C ABI: device buffers owned by plans, lane chunking, kernel launches, result packing.
+// Device runtime behind the C ABI: device buffers owned by plans, lane chunking, kernel launches, result delivery.
 // No CPU fallback: every entry point that computes fails with KRB_ERR_NO_DEVICE when there is no CUDA device.
+//
+// Stream discipline
+//   * device-memory calls enqueue everything on the caller's stream and return without synchronising (lane chunks reuse
+//     the staging buffers in stream order);
+//   * host-memory calls pipeline lane chunks over the caller's stream (H2D + kernels + pack) and an internal copy stream
+//     (D2H of the previous chunk), double-buffered, and return when the last byte has landed in the caller's buffer.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include "chain_kernel.cuh"
 #include "plan.hpp"
 #include "runtime.hpp"
 #include "vm_kernel.cuh"
-#include "chain_kernel.cuh"
 
 namespace krb {
 
@@ -56,29 +63,23 @@ struct Buf {
 struct DeviceState {
     bool uploaded = false;
     uint2 *sec[3] = {nullptr, nullptr, nullptr};
-    ChainTermDev *chain_terms = nullptr;
+    uint32_t *chain_rowinfo = nullptr;
+    uint4 *chain_stream = nullptr;
     int *chain_unknown = nullptr;
-    uint32_t *chain_u2_flags = nullptr;
-    Buf B, Bstep, IN, G, X, XOP, packed, status, iters;
+    int *chain_u2_rows = nullptr;
+    double *B = nullptr;                 // static constant pool (uploaded once: the plan owns a fixed copy of the circuit)
+    Buf Bstep, IN, G, XOP, status, iters;
+    Buf X[2], packed[2];                 // double-buffered for host delivery
+    std::vector<double> bstep_host;
+    int bstep_rows = -1;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t compute_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     size_t events_used = 0;
+    long long chunk_lanes = 0;           // lane capacity the buffers were sized for
 };
 
 DeviceState *device_state_new() { return new DeviceState(); }
-static double sum_event_ms(DeviceState *d);
-static DeviceState *g_last_timed_fwd();
-void device_state_free(DeviceState *d) {
-    if (!d) return;
-    if (g_last_timed_fwd() == d) { extern void krb_snapshot_last_ms(DeviceState *); krb_snapshot_last_ms(d); }
-    for (int i = 0; i < 3; i++) if (d->sec[i]) cudaFree(d->sec[i]);
-    if (d->chain_terms) cudaFree(d->chain_terms);
-    if (d->chain_unknown) cudaFree(d->chain_unknown);
-    if (d->chain_u2_flags) cudaFree(d->chain_u2_flags);
-    d->B.release(); d->Bstep.release(); d->IN.release(); d->G.release(); d->X.release(); d->XOP.release();
-    d->packed.release(); d->status.release(); d->iters.release();
-    for (auto &e : d->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    delete d;
-}
 
 static DeviceState *g_last_timed = nullptr;
 static double g_last_ms = -1.0;   // kept when the plan that owned the events is destroyed
@@ -94,60 +95,62 @@ static double sum_event_ms(DeviceState *d) {
     return total;
 }
 double last_kernel_ms() { return g_last_timed ? sum_event_ms(g_last_timed) : g_last_ms; }
-static DeviceState *g_last_timed_fwd() { return g_last_timed; }
-void krb_snapshot_last_ms(DeviceState *d) { g_last_ms = sum_event_ms(d); g_last_timed = nullptr; }
 
-static int upload_programs(Plan &plan, DeviceState &d) {
+void device_state_free(DeviceState *d) {
+    if (!d) return;
+    if (g_last_timed == d) { g_last_ms = sum_event_ms(d); g_last_timed = nullptr; }
+    for (int i = 0; i < 3; i++) if (d->sec[i]) cudaFree(d->sec[i]);
+    if (d->chain_rowinfo) cudaFree(d->chain_rowinfo);
+    if (d->chain_stream) cudaFree(d->chain_stream);
+    if (d->chain_unknown) cudaFree(d->chain_unknown);
+    if (d->chain_u2_rows) cudaFree(d->chain_u2_rows);
+    if (d->B) cudaFree(d->B);
+    d->Bstep.release(); d->IN.release(); d->G.release(); d->XOP.release(); d->status.release(); d->iters.release();
+    for (int i = 0; i < 2; i++) {
+        d->X[i].release(); d->packed[i].release();
+        if (d->compute_done[i]) cudaEventDestroy(d->compute_done[i]);
+        if (d->copy_done[i]) cudaEventDestroy(d->copy_done[i]);
+    }
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    for (auto &e : d->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    delete d;
+}
+
+template <typename V>
+static int upload_vec(const std::vector<V> &v, V **out) {
+    CUDA_TRY(cudaMalloc((void **)out, std::max<size_t>(v.size(), 1) * sizeof(V)));
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice));
+    return KRB_OK;
+}
+
+static int upload_plan(Plan &plan, DeviceState &d) {
     if (d.uploaded) return KRB_OK;
+    int rc;
     for (int s = 0; s < 3; s++) {
         const auto &ops = plan.sec[s].ops;
         if (ops.empty()) continue;
         // pad with END ops: the interpreter prefetches one 32-op chunk ahead
         std::vector<uint32_t> padded(ops);
         const size_t n_ops = padded.size() / 2;
-        const size_t total = ((n_ops + 31) / 32) * 32 + 64;
-        padded.resize(total * 2, 0u);
-        CUDA_TRY(cudaMalloc(&d.sec[s], padded.size() * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemcpy(d.sec[s], padded.data(), padded.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        padded.resize((((n_ops + 31) / 32) * 32 + 64) * 2, 0u);
+        if ((rc = upload_vec(padded, (uint32_t **)&d.sec[s]))) return rc;
     }
-    if (plan.use_chain) {
-        static_assert(sizeof(ChainTermDev) == sizeof(ChainTerm) && sizeof(ChainTerm) == 16, "term layout");
-        CUDA_TRY(cudaMalloc(&d.chain_terms, plan.chain.terms.size() * sizeof(ChainTerm)));
-        CUDA_TRY(cudaMemcpy(d.chain_terms, plan.chain.terms.data(), plan.chain.terms.size() * sizeof(ChainTerm), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&d.chain_unknown, plan.chain.unknown_of_row.size() * sizeof(int)));
-        CUDA_TRY(cudaMemcpy(d.chain_unknown, plan.chain.unknown_of_row.data(), plan.chain.unknown_of_row.size() * sizeof(int), cudaMemcpyHostToDevice));
-        if (plan.chain.n_u2 > 0) {
-            const int nrows = (int)plan.chain.unknown_of_row.size();
-            std::vector<uint32_t> bits((nrows + 31) / 32, 0u);
-            int row = 0;
-            for (const ChainTerm &t : plan.chain.terms) {
-                if (row >= nrows) break;
-                if (t.meta & (1u << 31)) { if (t.meta & (1u << 30)) bits[row >> 5] |= 1u << (row & 31); row++; }
-            }
-            CUDA_TRY(cudaMalloc(&d.chain_u2_flags, bits.size() * 4));
-            CUDA_TRY(cudaMemcpy(d.chain_u2_flags, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
-        }
+    if (plan.chain.valid) {
+        if ((rc = upload_vec(plan.chain.rowinfo, &d.chain_rowinfo))) return rc;
+        if ((rc = upload_vec(plan.chain.stream, (uint64_t **)&d.chain_stream))) return rc;
+        if ((rc = upload_vec(plan.chain.unknown_of_row, &d.chain_unknown))) return rc;
+        if ((rc = upload_vec(plan.chain.u2_rows, &d.chain_u2_rows))) return rc;
+    }
+    std::vector<double> pool;
+    evaluate_pool(plan, plan.circuit, plan.opts.time_step, pool);
+    if ((rc = upload_vec(pool, &d.B))) return rc;
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&d.compute_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.copy_done[i], cudaEventDisableTiming));
     }
     d.uploaded = true;
     return KRB_OK;
-}
-
-template <bool CPLX, int TPB>
-static int launch_chain_t(const ChainParams &p, long long Lpad, cudaStream_t st) {
-    krb_chain_kernel<CPLX, TPB><<<(unsigned)(Lpad / TPB), TPB, 0, st>>>(p);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    return KRB_OK;
-}
-static int launch_chain(bool cplx, int tpb, const ChainParams &p, long long Lpad, cudaStream_t st) {
-    if (cplx) {
-        if (tpb == 32) return launch_chain_t<true, 32>(p, Lpad, st);
-        if (tpb == 128) return launch_chain_t<true, 128>(p, Lpad, st);
-        return launch_chain_t<true, 64>(p, Lpad, st);
-    }
-    if (tpb == 32) return launch_chain_t<false, 32>(p, Lpad, st);
-    if (tpb == 128) return launch_chain_t<false, 128>(p, Lpad, st);
-    return launch_chain_t<false, 64>(p, Lpad, st);
 }
 
 template <bool CPLX, int TPB>
@@ -163,7 +166,6 @@ static int launch_vm_t(const VmParams &p, long long Lpad, int n_slots, cudaStrea
     CUDA_TRY(cudaGetLastError());
     return KRB_OK;
 }
-
 static int launch_vm(bool cplx, int tpb, const VmParams &p, long long Lpad, int n_slots, cudaStream_t st) {
     if (cplx) {
         if (tpb == 32) return launch_vm_t<true, 32>(p, Lpad, n_slots, st);
@@ -175,19 +177,32 @@ static int launch_vm(bool cplx, int tpb, const VmParams &p, long long Lpad, int 
     return launch_vm_t<false, 64>(p, Lpad, n_slots, st);
 }
 
-static int pick_tpb(const Plan &plan) {
-    int t = plan.opts.threads_per_block;
-    if (t == 32 || t == 64 || t == 128) return t;
-    return 64;
+template <bool CPLX, int TPB, bool DIRECT>
+static int launch_chain_t(const ChainParams &p, long long Lpad, cudaStream_t st) {
+    krb_chain_kernel<CPLX, TPB, DIRECT><<<(unsigned)(Lpad / TPB), TPB, 0, st>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return KRB_OK;
+}
+template <bool DIRECT>
+static int launch_chain_d(bool cplx, int tpb, const ChainParams &p, long long Lpad, cudaStream_t st) {
+    if (cplx) {
+        if (tpb == 32) return launch_chain_t<true, 32, DIRECT>(p, Lpad, st);
+        if (tpb == 128) return launch_chain_t<true, 128, DIRECT>(p, Lpad, st);
+        return launch_chain_t<true, 64, DIRECT>(p, Lpad, st);
+    }
+    if (tpb == 32) return launch_chain_t<false, 32, DIRECT>(p, Lpad, st);
+    if (tpb == 128) return launch_chain_t<false, 128, DIRECT>(p, Lpad, st);
+    return launch_chain_t<false, 64, DIRECT>(p, Lpad, st);
+}
+static int launch_chain(bool cplx, int tpb, bool direct, const ChainParams &p, long long Lpad, cudaStream_t st) {
+    return direct ? launch_chain_d<true>(cplx, tpb, p, Lpad, st) : launch_chain_d<false>(cplx, tpb, p, Lpad, st);
 }
 
-// Copy `count` doubles per plane from a caller pointer (host or device) into rows of a padded device plane array.
-static int load_planes(double *dst, long long Lpad, const double *src, long long src_stride, long long lane0, long long lanes,
-                       int planes, bool src_device, cudaStream_t st) {
-    if (planes <= 0) return KRB_OK;
-    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)Lpad * 8, src + lane0, (size_t)src_stride * 8, (size_t)lanes * 8, (size_t)planes,
-                               src_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    return KRB_OK;
+static int pick_tpb(const Plan &plan) {
+    const int t = plan.opts.threads_per_block;
+    if (t == 32 || t == 64 || t == 128) return t;
+    return 64;
 }
 
 int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
@@ -204,61 +219,65 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const int rows = a.rows;
     const int tpb = pick_tpb(P0);
     int rc;
-    if ((rc = upload_programs(P0, D0))) return rc;
-    if (PS && (rc = upload_programs(*PS, *PS->dev))) return rc;
+    if ((rc = upload_plan(P0, D0))) return rc;
+    if (PS && (rc = upload_plan(*PS, *PS->dev))) return rc;
     if (PS && PS->n_inputs != P0.n_inputs) { set_error("plan_dc and plan_tran must be analysed with the same varied elements"); return KRB_ERR_INVALID_ARGUMENT; }
     if (n == 0 || a.lanes <= 0) return KRB_OK;
+    const bool chain = P0.use_chain && !PS;
+    const bool out_dev = (a.memory == KRB_MEM_DEVICE);
+    // the chain kernel can write point-major results itself when pivot row k is unknown k (no X staging, no pack kernel)
+    const bool direct = chain && P0.chain.identity_order && a.layout == KRB_LAYOUT_POINT_MAJOR && rows == 1;
 
-    // ---- lane-invariant tables ----
-    std::vector<double> pool;
-    evaluate_pool(P0, P0.circuit, P0.opts.time_step, pool);
-    if ((rc = D0.B.ensure(std::max<size_t>(pool.size(), 1) * 8))) return rc;
-    if (!pool.empty()) CUDA_TRY(cudaMemcpyAsync(D0.B.p, pool.data(), pool.size() * 8, cudaMemcpyHostToDevice, st));
-    std::vector<double> pool_s, bstep;
+    // ---- per-step source table (transient) ----
     if (PS) {
         DeviceState &DS = *PS->dev;
-        evaluate_pool(*PS, PS->circuit, PS->opts.time_step, pool_s);
-        if ((rc = DS.B.ensure(std::max<size_t>(pool_s.size(), 1) * 8))) return rc;
-        if (!pool_s.empty()) CUDA_TRY(cudaMemcpyAsync(DS.B.p, pool_s.data(), pool_s.size() * 8, cudaMemcpyHostToDevice, st));
-        // source table: row r, iteration 0 sees the time key of the previous row, later iterations see r*h
-        const int nw = (int)PS->wave_elems.size();
-        const double h = PS->opts.time_step;
-        bstep.assign((size_t)rows * 2 * std::max(nw, 1), 0.0);
-        for (int r = 1; r < rows; r++)
-            for (int k = 0; k < nw; k++) {
-                const krb_element &el = PS->circuit.el[PS->wave_elems[k]];
-                bstep[((size_t)r * 2 + 0) * nw + k] = transient_value_at(el, (double)(r - 1) * h);   // stampable.rs:1043 + transient.rs:49
-                bstep[((size_t)r * 2 + 1) * nw + k] = transient_value_at(el, (double)r * h);         // transient.rs:95,105
-            }
-        if ((rc = DS.Bstep.ensure(bstep.size() * 8))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(DS.Bstep.p, bstep.data(), bstep.size() * 8, cudaMemcpyHostToDevice, st));
+        if (DS.bstep_rows != rows) {
+            // row r, iteration 0 sees the time key of the previous row, later iterations see r*h
+            const int nw = (int)PS->wave_elems.size();
+            const double h = PS->opts.time_step;
+            DS.bstep_host.assign((size_t)rows * 2 * std::max(nw, 1), 0.0);
+            for (int r = 1; r < rows; r++)
+                for (int k = 0; k < nw; k++) {
+                    const krb_element &el = PS->circuit.el[PS->wave_elems[k]];
+                    DS.bstep_host[((size_t)r * 2 + 0) * nw + k] = transient_value_at(el, (double)(r - 1) * h);   // stampable.rs:1043 + transient.rs:49
+                    DS.bstep_host[((size_t)r * 2 + 1) * nw + k] = transient_value_at(el, (double)r * h);         // transient.rs:95,105
+                }
+            if ((rc = DS.Bstep.ensure(DS.bstep_host.size() * 8))) return rc;
+            CUDA_TRY(cudaMemcpy(DS.Bstep.p, DS.bstep_host.data(), DS.bstep_host.size() * 8, cudaMemcpyHostToDevice));
+            DS.bstep_rows = rows;
+        }
     }
-    CUDA_TRY(cudaStreamSynchronize(st));   // host vectors above go out of scope
 
     // ---- chunking: bound the per-call device footprint ----
-    const bool chain = P0.use_chain && !PS;
     const int planes0 = chain ? 2 * n + P0.chain.n_u2 : P0.n_planes, planesS = PS ? PS->n_planes : 0;
-    const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)rows * n * ts * 2 + (size_t)P0.n_inputs * 8 + (a.op_solution ? (size_t)n * 8 : 0) + 16;
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    size_t reusable = D0.G.bytes + D0.X.bytes + D0.packed.bytes + D0.IN.bytes + (PS ? PS->dev->G.bytes : 0);
-    long long max_chunk = (long long)(((free_b + reusable) * 0.80) / (double)per_lane);
-    max_chunk = (max_chunk / tpb) * tpb;
-    if (max_chunk < tpb) { set_error("not enough device memory for one block of lanes"); return KRB_ERR_OUT_OF_MEMORY; }
-    long long chunk_cap = a.chunk_lanes > 0 ? a.chunk_lanes : 65536;
-    chunk_cap = std::max<long long>(tpb, (chunk_cap / tpb) * tpb);
-    const long long chunk = std::min<long long>(std::min(max_chunk, chunk_cap), ((a.lanes + tpb - 1) / tpb) * tpb);
-
+    const int nbuf = out_dev ? 1 : 2;
+    const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)rows * n * ts * (out_dev ? 1 : 4) +
+                            (size_t)P0.n_inputs * 8 + (a.op_solution ? (size_t)n * 8 : 0) + 16;
+    long long want = a.chunk_lanes > 0 ? a.chunk_lanes : (out_dev ? 65536 : 16384);
+    want = std::min<long long>(want, ((a.lanes + tpb - 1) / tpb) * tpb);
+    want = std::max<long long>(tpb, (want / tpb) * tpb);
+    if (want > D0.chunk_lanes || (PS && want > PS->dev->chunk_lanes)) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        size_t reusable = D0.G.bytes + D0.X[0].bytes + D0.X[1].bytes + D0.packed[0].bytes + D0.packed[1].bytes + D0.IN.bytes + (PS ? PS->dev->G.bytes : 0);
+        long long max_chunk = (long long)(((free_b + reusable) * 0.80) / (double)per_lane);
+        max_chunk = (max_chunk / tpb) * tpb;
+        if (max_chunk < tpb) { set_error("not enough device memory for one block of lanes"); return KRB_ERR_OUT_OF_MEMORY; }
+        want = std::min(want, max_chunk);
+    }
+    const long long chunk = want;
     if ((rc = D0.IN.ensure(std::max<size_t>((size_t)P0.n_inputs, 1) * chunk * 8))) return rc;
     if ((rc = D0.G.ensure(std::max<size_t>((size_t)planes0, 1) * chunk * ts))) return rc;
     if (PS && (rc = PS->dev->G.ensure(std::max<size_t>((size_t)planesS, 1) * chunk * ts))) return rc;
-    if ((rc = D0.X.ensure((size_t)rows * n * chunk * ts))) return rc;
-    if ((rc = D0.status.ensure((size_t)chunk * 4))) return rc;
-    if (a.iterations && (rc = D0.iters.ensure((size_t)chunk * 4))) return rc;
+    for (int b = 0; b < nbuf; b++) {
+        if (!direct && (rc = D0.X[b].ensure((size_t)rows * n * chunk * ts))) return rc;
+        if (!out_dev && (rc = D0.packed[b].ensure((size_t)rows * n * chunk * ts))) return rc;
+    }
+    if ((rc = D0.status.ensure((size_t)chunk * 4 * 2))) return rc;
+    if (a.iterations && (rc = D0.iters.ensure((size_t)chunk * 4 * 2))) return rc;
     if (a.op_solution && (rc = D0.XOP.ensure((size_t)n * chunk * 8))) return rc;
-    const bool out_dev = (a.memory == KRB_MEM_DEVICE);
-    const bool need_packed = !out_dev;   // host delivery goes through a packed device buffer
-    if (need_packed && (rc = D0.packed.ensure((size_t)rows * n * chunk * ts))) return rc;
+    D0.chunk_lanes = std::max(D0.chunk_lanes, chunk);
+    if (PS) PS->dev->chunk_lanes = std::max(PS->dev->chunk_lanes, chunk);
 
     D0.events_used = 0;
     g_last_timed = &D0;
@@ -275,14 +294,19 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         return KRB_OK;
     };
 
-    for (long long lane0 = 0; lane0 < a.lanes; lane0 += chunk) {
+    Buf op_tmp;
+    int chunk_idx = 0;
+    for (long long lane0 = 0; lane0 < a.lanes; lane0 += chunk, ++chunk_idx) {
         const long long lanes = std::min<long long>(chunk, a.lanes - lane0);
         const long long Lpad = ((lanes + tpb - 1) / tpb) * tpb;
+        const int b = out_dev ? 0 : (chunk_idx & 1);
         double *IN = (double *)D0.IN.p;
-        // inputs
+        int *status_d = (int *)D0.status.p + (size_t)b * chunk;
+        int *iters_d = a.iterations ? (int *)D0.iters.p + (size_t)b * chunk : nullptr;
+        if (!out_dev && chunk_idx >= 2) CUDA_TRY(cudaStreamWaitEvent(st, D0.copy_done[b], 0));   // buffer set b is free again
+        // ---- inputs ----
         for (int k = 0; k < P0.n_inputs; k++) {
             const double *src = nullptr;
-            long long stride = a.lanes;
             if (k == P0.input_sweep || k == P0.input_freq) src = a.lane_param;
             else {
                 int vk = -1;
@@ -290,7 +314,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
                 if (vk < 0 || !a.varied_values) { set_error("missing per-lane values for a varied element"); return KRB_ERR_INVALID_ARGUMENT; }
                 src = a.varied_values + (size_t)vk * a.lanes;
             }
-            if ((rc = load_planes(IN + (size_t)k * Lpad, Lpad, src, stride, lane0, lanes, 1, out_dev, st))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(IN + (size_t)k * Lpad, src + lane0, (size_t)lanes * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         }
         if (Lpad > lanes && P0.n_inputs > 0) {
             const long long work = (long long)P0.n_inputs * (Lpad - lanes);
@@ -298,84 +322,111 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             g_launches++;
         }
         if (a.op_solution) {
-            const double *src = a.op_solution;
-            Buf tmp;
             const bool bc = (a.lanes_op == 1);
             const size_t cnt = bc ? (size_t)n : (size_t)lanes * n;
-            const double *dsrc = src + (bc ? 0 : (size_t)lane0 * n);
+            const double *dsrc = a.op_solution + (bc ? 0 : (size_t)lane0 * n);
             if (!out_dev) {
-                if ((rc = tmp.ensure(cnt * 8))) return rc;
-                CUDA_TRY(cudaMemcpyAsync(tmp.p, dsrc, cnt * 8, cudaMemcpyHostToDevice, st));
-                dsrc = (const double *)tmp.p;
+                if ((rc = op_tmp.ensure(cnt * 8))) return rc;
+                CUDA_TRY(cudaMemcpyAsync(op_tmp.p, dsrc, cnt * 8, cudaMemcpyHostToDevice, st));
+                dsrc = (const double *)op_tmp.p;
             }
             const long long work = (long long)n * Lpad;
             krb_spread_op<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(dsrc, (double *)D0.XOP.p, n, Lpad, lanes, bc ? 1 : 0);
             g_launches++;
-            CUDA_TRY(cudaStreamSynchronize(st));
-            tmp.release();
         }
-        CUDA_TRY(cudaMemsetAsync(D0.status.p, 0, (size_t)Lpad * 4, st));
+        CUDA_TRY(cudaMemsetAsync(status_d, 0, (size_t)Lpad * 4, st));
 
-        VmParams p{};
-        p.sec0 = D0.sec[0]; p.sec1 = D0.sec[1]; p.sec2 = D0.sec[2];
-        if (P0.has_step_sections) p.sec0 = nullptr; else { p.sec1 = nullptr; p.sec2 = nullptr; }
-        p.B = (const double *)D0.B.p; p.Bstep = nullptr; p.n_wave = 0;
-        p.IN = IN; p.G = D0.G.p; p.X = D0.X.p;
-        p.Xprev0 = a.op_solution ? (const double *)D0.XOP.p : nullptr;
-        p.n = n; p.L = Lpad;
-        p.row_begin = 0; p.row_end = PS ? 1 : rows;
-        p.nonlinear = P0.circuit.nonlinear ? 1 : 0;
-        p.max_iter = p.nonlinear ? std::max(1, a.cfg.maximum_iterations) : 1;
-        if (cplx) { p.nonlinear = 0; p.max_iter = 1; }
-        p.guess_empty_at_iter0 = 1; p.pseudo_time = 0;
-        p.h = P0.opts.time_step; p.reltol = a.cfg.relative_tolerance; p.iabstol = a.cfg.current_absolute_tolerance; p.vabstol = a.cfg.voltage_absolute_tolerance;
-        p.status = (int *)D0.status.p; p.iters = a.iterations ? (int *)D0.iters.p : nullptr;
+        // ---- compute ----
         cudaEvent_t e0, e1;
         if ((rc = next_events(e0, e1))) return rc;
         CUDA_TRY(cudaEventRecord(e0, st));
         if (chain) {
             ChainParams c{};
-            c.terms = D0.chain_terms; c.unknown_of_row = D0.chain_unknown; c.IN = IN; c.UY = D0.G.p; c.X = D0.X.p;
-            c.n = n; c.input_freq = P0.input_freq; c.n_u2 = P0.chain.n_u2; c.u2_flags = D0.chain_u2_flags; c.L = Lpad; c.status = (int *)D0.status.p;
-            if ((rc = launch_chain(cplx, tpb, c, Lpad, st))) return rc;
-        } else if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st))) return rc;
-        if (PS) {
-            DeviceState &DS = *PS->dev;
-            VmParams q = p;
-            q.sec0 = DS.sec[0]; q.sec1 = DS.sec[1]; q.sec2 = DS.sec[2];
-            if (PS->has_step_sections) q.sec0 = nullptr; else { q.sec1 = nullptr; q.sec2 = nullptr; }
-            q.B = (const double *)DS.B.p; q.Bstep = (const double *)DS.Bstep.p; q.n_wave = (int)PS->wave_elems.size();
-            q.G = DS.G.p; q.Xprev0 = nullptr;
-            q.row_begin = 1; q.row_end = rows;
-            q.nonlinear = PS->circuit.nonlinear ? 1 : 0;
-            q.max_iter = q.nonlinear ? std::max(1, a.cfg.maximum_iterations) : 1;
-            q.guess_empty_at_iter0 = 0; q.pseudo_time = 1;
-            q.h = PS->opts.time_step;
-            q.iters = nullptr;
-            if (rows > 1 && (rc = launch_vm(false, tpb, q, Lpad, PS->n_slots, st))) return rc;
+            c.rowinfo = D0.chain_rowinfo; c.stream = D0.chain_stream; c.unknown_of_row = D0.chain_unknown; c.IN = IN;
+            c.UY = D0.G.p; c.X = D0.X[b].p; c.n = n; c.input_freq = P0.input_freq; c.n_u2 = P0.chain.n_u2; c.L = Lpad; c.status = status_d;
+            c.u2_rows = D0.chain_u2_rows; c.out_lanes = lanes;
+            { const char *dbg = getenv("KRB_CHAIN_DEBUG"); c.debug = dbg ? atoi(dbg) : 0; }
+            { const char *pf = getenv("KRB_CHAIN_PF"); c.pf_units = pf ? atoi(pf) : 256; }
+            c.OUT = direct ? (out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p) : nullptr;
+            if ((rc = launch_chain(cplx, tpb, direct, c, Lpad, st))) return rc;
+        } else {
+            VmParams p{};
+            p.sec0 = D0.sec[0]; p.sec1 = D0.sec[1]; p.sec2 = D0.sec[2];
+            if (P0.has_step_sections) p.sec0 = nullptr; else { p.sec1 = nullptr; p.sec2 = nullptr; }
+            p.B = D0.B; p.Bstep = nullptr; p.n_wave = 0;
+            p.IN = IN; p.G = D0.G.p; p.X = D0.X[b].p;
+            p.Xprev0 = a.op_solution ? (const double *)D0.XOP.p : nullptr;
+            p.n = n; p.L = Lpad;
+            p.row_begin = 0; p.row_end = PS ? 1 : rows;
+            p.nonlinear = (P0.circuit.nonlinear && !cplx) ? 1 : 0;
+            p.max_iter = p.nonlinear ? std::max(1, a.cfg.maximum_iterations) : 1;
+            p.guess_empty_at_iter0 = 1; p.pseudo_time = 0;
+            p.h = P0.opts.time_step; p.reltol = a.cfg.relative_tolerance; p.iabstol = a.cfg.current_absolute_tolerance; p.vabstol = a.cfg.voltage_absolute_tolerance;
+            p.status = status_d; p.iters = iters_d;
+            if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st))) return rc;
+            if (PS && rows > 1) {
+                DeviceState &DS = *PS->dev;
+                VmParams q = p;
+                q.sec0 = DS.sec[0]; q.sec1 = DS.sec[1]; q.sec2 = DS.sec[2];
+                if (PS->has_step_sections) q.sec0 = nullptr; else { q.sec1 = nullptr; q.sec2 = nullptr; }
+                q.B = DS.B; q.Bstep = (const double *)DS.Bstep.p; q.n_wave = (int)PS->wave_elems.size();
+                q.G = DS.G.p; q.Xprev0 = nullptr;
+                q.row_begin = 1; q.row_end = rows;
+                q.nonlinear = PS->circuit.nonlinear ? 1 : 0;
+                q.max_iter = q.nonlinear ? std::max(1, a.cfg.maximum_iterations) : 1;
+                q.guess_empty_at_iter0 = 0; q.pseudo_time = 1;
+                q.h = PS->opts.time_step;
+                q.iters = nullptr;
+                if ((rc = launch_vm(false, tpb, q, Lpad, PS->n_slots, st))) return rc;
+            }
         }
         CUDA_TRY(cudaEventRecord(e1, st));
 
         // ---- delivery ----
         const size_t per_point = (size_t)rows * n;
-        if (a.layout == KRB_LAYOUT_POINT_MAJOR) {
-            void *dst = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * per_point * ts) : D0.packed.p;
-            dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)rows), block(32, 8);
-            if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X.p, (double2 *)dst, rows, n, Lpad, lanes);
-            else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X.p, (double *)dst, rows, n, Lpad, lanes);
-            g_launches++;
-            CUDA_TRY(cudaGetLastError());
-            if (!out_dev) CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * per_point * ts, D0.packed.p, (size_t)lanes * per_point * ts, cudaMemcpyDeviceToHost, st));
+        if (out_dev) {
+            if (direct) {
+                // already delivered by the kernel
+            } else if (a.layout == KRB_LAYOUT_POINT_MAJOR) {
+                void *dst = (char *)a.x_out + (size_t)lane0 * per_point * ts;
+                dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)rows), block(32, 8);
+                if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)dst, rows, n, Lpad, lanes);
+                else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)dst, rows, n, Lpad, lanes);
+                g_launches++;
+                CUDA_TRY(cudaGetLastError());
+            } else {
+                CUDA_TRY(cudaMemcpy2DAsync((char *)a.x_out + (size_t)lane0 * ts, (size_t)a.lanes * ts, D0.X[b].p, (size_t)Lpad * ts, (size_t)lanes * ts, per_point, cudaMemcpyDeviceToDevice, st));
+            }
+            if (a.lane_status) CUDA_TRY(cudaMemcpyAsync(a.lane_status + lane0, status_d, (size_t)lanes * 4, cudaMemcpyDeviceToDevice, st));
+            if (a.iterations) CUDA_TRY(cudaMemcpyAsync(a.iterations + lane0, iters_d, (size_t)lanes * 4, cudaMemcpyDeviceToDevice, st));
         } else {
-            // lane-interleaved delivery: x_out[row][u][lane] with the caller's lane stride (= total lanes)
-            CUDA_TRY(cudaMemcpy2DAsync((char *)a.x_out + (size_t)lane0 * ts, (size_t)a.lanes * ts, D0.X.p, (size_t)Lpad * ts, (size_t)lanes * ts, per_point,
-                                       out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+            cudaStream_t cs = D0.copy_stream;
+            if (a.layout == KRB_LAYOUT_POINT_MAJOR && !direct) {
+                dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)rows), block(32, 8);
+                if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)D0.packed[b].p, rows, n, Lpad, lanes);
+                else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)D0.packed[b].p, rows, n, Lpad, lanes);
+                g_launches++;
+                CUDA_TRY(cudaGetLastError());
+            }
+            CUDA_TRY(cudaEventRecord(D0.compute_done[b], st));
+            CUDA_TRY(cudaStreamWaitEvent(cs, D0.compute_done[b], 0));
+            if (a.layout == KRB_LAYOUT_POINT_MAJOR)
+                CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * per_point * ts, D0.packed[b].p, (size_t)lanes * per_point * ts, cudaMemcpyDeviceToHost, cs));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync((char *)a.x_out + (size_t)lane0 * ts, (size_t)a.lanes * ts, D0.X[b].p, (size_t)Lpad * ts, (size_t)lanes * ts, per_point, cudaMemcpyDeviceToHost, cs));
+            if (a.lane_status) CUDA_TRY(cudaMemcpyAsync(a.lane_status + lane0, status_d, (size_t)lanes * 4, cudaMemcpyDeviceToHost, cs));
+            if (a.iterations) CUDA_TRY(cudaMemcpyAsync(a.iterations + lane0, iters_d, (size_t)lanes * 4, cudaMemcpyDeviceToHost, cs));
+            CUDA_TRY(cudaEventRecord(D0.copy_done[b], cs));
         }
-        if (a.lane_status)
-            CUDA_TRY(cudaMemcpyAsync(a.lane_status + lane0, D0.status.p, (size_t)lanes * 4, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        if (a.iterations)
-            CUDA_TRY(cudaMemcpyAsync(a.iterations + lane0, D0.iters.p, (size_t)lanes * 4, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        if (!out_dev || lane0 + chunk < a.lanes) CUDA_TRY(cudaStreamSynchronize(st));   // staging buffers are reused by the next chunk
+    }
+    if (!out_dev) {
+        // host buffers must be complete on return
+        CUDA_TRY(cudaStreamSynchronize(D0.copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        op_tmp.release();
+    } else if (op_tmp.p) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        op_tmp.release();
     }
     return KRB_OK;
 }

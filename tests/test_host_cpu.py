@@ -269,6 +269,7 @@ def test_chain_terms_dc_sweep(oracle):
     X, status = run_chain(plan, vals[None, :], False)
     assert_close(X.T, oc.solve_dc("V1", -2.0, 3.0, 5.0 / 6.0), what="chain DC sweep")
     assert not status.any()
+    assert run_chain.last_fixed_rows >= 498          # all but the source rows are fixed-shape records
     assert plan.info.hbm_bytes_per_point == 8 * (5 * 501 + 2) + 8      # one row (the source's KCL row) owns a u2 plane
 
 

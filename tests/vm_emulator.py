@@ -160,18 +160,21 @@ class Emulator:
 
 # ---- chain executor term stream (chain_kernel.cuh) --------------------------------------------------------------
 def run_chain(plan, IN, cplx):
-    """numpy restatement of krb_chain_kernel: IN [n_inputs][L] -> X [n][L]."""
+    """numpy restatement of krb_chain_kernel (row-info words + 16-byte record stream): IN [n_inputs][L] -> X [n][L]."""
     L_ = _lib.lib()
-    nt = int(L_.krb_plan_chain_size(plan._h))
-    assert nt > 0, "plan has no chain tables"
-    raw = np.zeros(nt, dtype=np.dtype([("meta", "<u4"), ("plane", "<u4"), ("K", "<f8")]))
-    unk = np.zeros(plan.n, dtype=np.int32)
-    L_.krb_plan_get_chain(plan._h, raw.ctypes.data_as(C.c_void_p), unk.ctypes.data_as(C.POINTER(C.c_int32)))
+    nw = int(L_.krb_plan_chain_size(plan._h))
+    assert nw > 0, "plan has no chain tables"
+    n = plan.n
+    rowinfo = np.zeros(n + 1 + 1100, dtype=np.uint32)
+    words = np.zeros(nw, dtype=np.uint64)
+    unk = np.zeros(n, dtype=np.int32)
+    L_.krb_plan_get_chain(plan._h, rowinfo.ctypes.data_as(C.POINTER(C.c_uint32)), words.ctypes.data_as(C.POINTER(C.c_uint64)),
+                          unk.ctypes.data_as(C.POINTER(C.c_int32)))
+    dwords = words.view(np.float64)
     lanes = IN.shape[1]
     sweep, freq, _ = input_layout(plan)
     w = (2.0 * np.pi) * IN[freq] if (cplx and freq >= 0) else np.zeros(lanes)
     dt = np.complex128 if cplx else np.float64
-    n = plan.n
     U1 = np.zeros((n, lanes), dtype=dt)
     U2 = np.zeros((n, lanes), dtype=dt)
     Y = np.zeros((n, lanes), dtype=dt)
@@ -180,34 +183,47 @@ def run_chain(plan, IN, cplx):
     py = np.zeros(lanes, dtype=dt)
     status = np.zeros(lanes, dtype=np.int32)
     has_u2 = np.zeros(n, dtype=bool)
-    i = 0
+    fix_units = 4 if cplx else 2
+    i = 0          # position in 16-byte units
+    n_fixed = 0
     with np.errstate(all="ignore"):
         for k in range(n):
+            info = int(rowinfo[k])
             e = [np.zeros(lanes, dtype=dt) for _ in range(5)]
-            while True:
-                meta, plane, K = int(raw["meta"][i]), int(raw["plane"][i]), float(raw["K"][i])
-                i += 1
-                kind = (meta >> 4) & 0xF
-                if kind == 0:
-                    v = np.full(lanes, K, dtype=dt)
-                elif kind == 1:
-                    v = IN[plane].astype(dt)
-                elif kind == 2:
-                    v = (1.0 / IN[plane]).astype(dt)
-                elif kind == 3:
-                    v = (IN[plane] / K).astype(dt)
-                elif kind == 4:
-                    v = 1j * (w * K)
-                elif kind == 5:
-                    v = 1j * (w * IN[plane])
+            has_u2[k] = bool(info & 2)
+            if info & 1:
+                d = dwords[2 * i: 2 * (i + fix_units)]
+                n_fixed += 1
+                if cplx:
+                    e[0] = d[0] + 1j * (w * d[4]); e[1] = d[1] + 1j * (w * d[5]); e[2] = d[2] + 1j * (w * d[6])
+                    e[4] = np.full(lanes, d[3], dtype=dt)
                 else:
-                    raise ValueError(kind)
-                if meta & (1 << 8):
-                    v = -v
-                e[meta & 7] = e[meta & 7] + v
-                if meta & (1 << 31):
-                    has_u2[k] = bool(meta & (1 << 30))
-                    break
+                    e[0] = np.full(lanes, d[0]); e[1] = np.full(lanes, d[1]); e[2] = np.full(lanes, d[2]); e[4] = np.full(lanes, d[3])
+                i += fix_units
+            else:
+                nt = info >> 8
+                for t in range(nt):
+                    mw = int(words[2 * (i + t)])
+                    meta, plane, K = mw & 0xFFFFFFFF, mw >> 32, float(dwords[2 * (i + t) + 1])
+                    kind = (meta >> 4) & 0xF
+                    if kind == 0:
+                        v = np.full(lanes, K, dtype=dt)
+                    elif kind == 1:
+                        v = IN[plane].astype(dt)
+                    elif kind == 2:
+                        v = (1.0 / IN[plane]).astype(dt)
+                    elif kind == 3:
+                        v = (IN[plane] / K).astype(dt)
+                    elif kind == 4:
+                        v = 1j * (w * K)
+                    elif kind == 5:
+                        v = 1j * (w * IN[plane])
+                    else:
+                        raise ValueError(kind)
+                    if meta & (1 << 8):
+                        v = -v
+                    e[meta & 7] = e[meta & 7] + v
+                i += nt
             wk = e[1] - e[0] * pu1
             s1 = e[2] - e[0] * pu2
             yk = e[4] - e[0] * py
@@ -225,5 +241,6 @@ def run_chain(plan, IN, cplx):
                 x = x - U2[k] * x2
             X[unk[k]] = x
             x2, x1 = x1, x
-    assert i == nt - 1, "term stream must end with exactly one sentinel"
+    assert 2 * i == nw - 2200, "record stream must end with the prefetch padding"
+    run_chain.last_fixed_rows = n_fixed
     return X, status
