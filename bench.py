@@ -97,7 +97,7 @@ def ncu_traffic():
     if os.path.exists(p):
         try:
             with open(p) as f:
-                return json.load(f).get("krb_lane_vm_dc_config2_bytes_per_launch")
+                return json.load(f).get("krb_chain_kernel_dc_config2_bytes_per_launch")
         except Exception:
             return None
     return None
