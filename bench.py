@@ -253,6 +253,8 @@ def main():
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         bufs = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        warm = [torch.empty_like(out[:64]) for _ in range(world)] if rank == 0 else None
+        dist.gather(out[:64].contiguous(), warm, dst=0)          # NCCL connection setup is not part of the gather time
         barrier()
         g0.record()
         dist.gather(out, bufs, dst=0)
