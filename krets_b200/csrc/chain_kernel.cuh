@@ -200,7 +200,12 @@ __global__ void __launch_bounds__(TPB, (TPB == 32 ? 14 : TPB == 64 ? 7 : 3)) krb
 
     // ---- backward: x_k = y^_k - u^_{k,k+1} x_{k+1} - u^_{k,k+2} x_{k+2}; reverse stream, double-buffered prefetch ----
     constexpr int R = CPLX ? 4 : 8;
-    __shared__ T tile[DIRECT ? TPB / 32 : 1][DIRECT ? 32 : 1][R + 1];
+    // DIRECT delivery: a warp collects FW consecutive unknowns of its 32 lanes in shared memory and then writes, per
+    // instruction, FW*sizeof(T)-byte runs of the caller's point-major rows (longer runs = better DRAM page locality)
+    constexpr int FW = CPLX ? 16 : 32;
+    __shared__ T tile[DIRECT ? TPB / 32 : 1][DIRECT ? 32 : 1][FW + 1];
+    int fill = 0;                                     // unknowns currently staged in the tile (warp-uniform)
+    int tile_top = 0;                                 // unknown index of tile column 0 (columns go downwards)
     const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31;
     const long long lane_w0 = lane - lid;             // first lane of this warp
     T x1 = S::zero(), x2 = S::zero();                 // x_{k+1}, x_{k+2}
@@ -227,24 +232,31 @@ __global__ void __launch_bounds__(TPB, (TPB == 32 ? 14 : TPB == 64 ? 7 : 3)) krb
         x1 = x;
         return x;
     };
+    auto flush_tile = [&]() {
+        // column c of the tile holds unknown tile_top - c; each pass writes one lane-group's run in ascending order
+        __syncwarp();
+        T *out = reinterpret_cast<T *>(p.OUT);
+        constexpr int LANES_PER_PASS = 32 / FW > 0 ? 32 / FW : 1;
+        constexpr int PASSES = 32 / LANES_PER_PASS;
+#pragma unroll 4
+        for (int pass = 0; pass < PASSES; ++pass) {
+            const int l = pass * LANES_PER_PASS + lid / FW, c = FW - 1 - (lid % FW);
+            const long long gl = lane_w0 + l;
+            if (c < fill && gl < p.out_lanes) out[(size_t)gl * (size_t)n + (size_t)(tile_top - c)] = tile[warp][l][c];
+        }
+        __syncwarp();
+        fill = 0;
+    };
     auto deliver_group = [&](int k0, const T *u, const T *y) {
         T xs[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) xs[j] = solve_row(k0 - j, u[j], y[j]);
         if (DIRECT) {
-            // tile[lane][j] holds unknown k0-j of that lane; thread t then writes R-long runs of 32/R... lanes per pass
-            __syncwarp();
+            if (fill == 0) tile_top = k0;
 #pragma unroll
-            for (int j = 0; j < R; ++j) tile[warp][lid][j] = xs[j];
-            __syncwarp();
-            T *out = reinterpret_cast<T *>(p.OUT);
-            constexpr int LANES_PER_PASS = 32 / R;
-#pragma unroll
-            for (int pass = 0; pass < R; ++pass) {
-                const int l = pass * LANES_PER_PASS + lid / R, j = R - 1 - (lid % R);   // ascending unknown within a run
-                const long long gl = lane_w0 + l;
-                if (gl < p.out_lanes) out[(size_t)gl * (size_t)n + (size_t)(k0 - j)] = tile[warp][l][j];
-            }
+            for (int j = 0; j < R; ++j) tile[warp][lid][fill + j] = xs[j];
+            fill += R;
+            if (fill == FW) flush_tile();
         } else {
 #pragma unroll
             for (int j = 0; j < R; ++j) X[(size_t)__ldg(p.unknown_of_row + (k0 - j)) * L] = xs[j];
@@ -267,9 +279,13 @@ __global__ void __launch_bounds__(TPB, (TPB == 32 ? 14 : TPB == 64 ? 7 : 3)) krb
     }
     for (; k0 >= 0; --k0) {                           // tail: fewer than R rows
         const T x = solve_row(k0, __ldcs(&UY[(size_t)(2 * k0) * L]), __ldcs(&UY[(size_t)(2 * k0 + 1) * L]));
-        if (DIRECT) { if (lane < p.out_lanes) reinterpret_cast<T *>(p.OUT)[(size_t)lane * (size_t)n + (size_t)k0] = x; }
-        else X[(size_t)__ldg(p.unknown_of_row + k0) * L] = x;
+        if (DIRECT) {
+            if (fill == 0) tile_top = k0;
+            tile[warp][lid][fill++] = x;
+            if (fill == FW) flush_tile();
+        } else X[(size_t)__ldg(p.unknown_of_row + k0) * L] = x;
     }
+    if (DIRECT && fill > 0) flush_tile();
     if (!S::finite(x1)) status |= KRB_LANE_NONFINITE;   // non-finite values propagate down the recurrence to x_0
     if (p.status) p.status[lane] |= status;
 }
