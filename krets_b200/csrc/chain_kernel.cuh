@@ -37,7 +37,9 @@ enum : uint32_t {
 };
 
 struct ChainParams {
-    const uint32_t *rowinfo;     // [n + 1] (one sentinel)
+    const uint32_t *rowinfo;     // [n + ...] per-row info (GENERIC rows: #terms, HAS_U2)
+    const uint32_t *runs;        // run table: (count << 1) | is_fixed
+    int n_runs;
     const uint4 *stream;         // row records, 16-byte units, padded with 4 zero units
     const int *unknown_of_row;   // pivot row k delivers unknown unknown_of_row[k]
     const double *IN;            // [n_inputs][L]
@@ -55,15 +57,18 @@ struct ChainParams {
     int debug;                   // profiling only: 1 = no forward stores, 2 = skip backward, 4 = skip forward
 };
 
-__device__ __forceinline__ double fast_rcp(double x) {
-    // MUFU.RCP64H seed + two Newton steps: <= 1-2 ulp, no slow path (the LU is not bit-pinned; stamps use exact division)
+__device__ __forceinline__ double rcp_seed(double x) {   // MUFU.RCP64H: ~2^-20 relative error, no slow path
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
     return r;
+}
+// 1/x to ~1 ulp with a three-deep dependent chain: r0 (1 + e + e^2), e = 1 - x r0, error e^3 <= 2^-60.
+// (The LU is not bit-pinned; stamps use exact IEEE division.)
+__device__ __forceinline__ double fast_rcp(double x) {
+    const double r0 = rcp_seed(x);
+    const double e = fma(-x, r0, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r0, t, r0);
 }
 
 template <bool CPLX> struct ChainSc;
@@ -73,9 +78,17 @@ template <> struct ChainSc<false> {
     static __device__ __forceinline__ T make(double re, double) { return re; }
     static __device__ __forceinline__ T fnma(T d, T a, T b) { return fma(-a, b, d); }
     static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
-    static __device__ __forceinline__ T rcp(T a, bool &bad) { const double r = fast_rcp(a); bad = !isfinite(r); return r; }
     static __device__ __forceinline__ bool finite(T a) { return isfinite(a); }
     static __device__ __forceinline__ void add(T &acc, double re, double) { acc = __dadd_rn(acc, re); }
+    // (a, b, c) / w with the quotients folded into the reciprocal's correction step: critical path = seed + 3 fma
+    static __device__ __forceinline__ bool scale3(T w, T a, T b, T c, T &qa, T &qb, T &qc) {
+        const double r0 = rcp_seed(w);
+        const double e = fma(-w, r0, 1.0);
+        const double t = fma(e, e, e);
+        const double a0 = a * r0, b0 = b * r0, c0 = c * r0;
+        qa = fma(a0, t, a0); qb = fma(b0, t, b0); qc = fma(c0, t, c0);
+        return !(fabs(w) > 0.0) || !isfinite(w);
+    }
 };
 template <> struct ChainSc<true> {
     typedef double2 T;
@@ -85,14 +98,15 @@ template <> struct ChainSc<true> {
         return make_double2(fma(a.y, b.y, fma(-a.x, b.x, d.x)), fma(-a.y, b.x, fma(-a.x, b.y, d.y)));
     }
     static __device__ __forceinline__ T mul(T a, T b) { return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
-    static __device__ __forceinline__ T rcp(T a, bool &bad) {
-        const double ns = fma(a.x, a.x, a.y * a.y);
-        const double r = fast_rcp(ns);
-        bad = !isfinite(r);
-        return make_double2(a.x * r, -a.y * r);
-    }
     static __device__ __forceinline__ bool finite(T a) { return isfinite(a.x) && isfinite(a.y); }
     static __device__ __forceinline__ void add(T &acc, double re, double im) { acc.x = __dadd_rn(acc.x, re); acc.y = __dadd_rn(acc.y, im); }
+    static __device__ __forceinline__ bool scale3(T w, T a, T b, T c, T &qa, T &qb, T &qc) {
+        const double ns = fma(w.x, w.x, w.y * w.y);
+        const double r = fast_rcp(ns);
+        const T inv = make_double2(w.x * r, -w.y * r);
+        qa = mul(a, inv); qb = mul(b, inv); qc = mul(c, inv);
+        return !(ns > 0.0) || !isfinite(ns);
+    }
 };
 
 __device__ __forceinline__ double u4lo(const uint4 &v) { return __hiloint2double((int)v.y, (int)v.x); }
@@ -120,82 +134,81 @@ __global__ void __launch_bounds__(TPB, (TPB == 32 ? 14 : TPB == 64 ? 7 : 3)) krb
     double w = 0.0;                                   // (2.0 * PI) * f, rounded once as the reference does
     if (CPLX && p.input_freq >= 0) w = __dmul_rn(2.0 * 3.14159265358979323846264338327950288, IN[(size_t)p.input_freq * L]);
 
-    // ---- forward: stamp + eliminate + forward-substitute, row by row; the next row's record is prefetched ----
+    // ---- forward: stamp + eliminate + forward-substitute, row by row --------------------------------------------
+    // The host groups the rows into runs: a FIXED run is a tight loop over fixed-shape records (one-ahead register
+    // prefetch, no per-row decoding); GENERIC rows (swept source, Monte-Carlo terms, second super-diagonal) go one by one.
     const uint4 *__restrict__ dp = p.stream;
     T pu1 = S::zero(), pu2 = S::zero(), py = S::zero();   // u^_{k-1,k}, u^_{k-1,k+1}, y^_{k-1}
     int r2 = 0;                                         // rank of the next row that owns a u2 plane (warp-uniform)
-    uint32_t info = __ldg(p.rowinfo);
-    uint4 q[FIX_UNITS];
-#pragma unroll
-    for (int i = 0; i < FIX_UNITS; ++i) q[i] = __ldg(dp + i);
-    for (int k = 0; k < ((p.debug & 4) ? 0 : n); ++k) {
-        const uint32_t ci = info;
-        uint4 c[FIX_UNITS];
-#pragma unroll
-        for (int i = 0; i < FIX_UNITS; ++i) c[i] = q[i];
-        const uint4 *__restrict__ row = dp;
-        dp += (ci & RI_FIXED) ? FIX_UNITS : (int)(ci >> RI_NTERMS_SHIFT);
-        info = __ldg(p.rowinfo + k + 1);              // sentinel at n
-#pragma unroll
-        for (int i = 0; i < FIX_UNITS; ++i) q[i] = __ldg(dp + i);   // next row's record (the stream is padded)
-        if (p.pf_units > 0) {                         // keep the (warp-shared, read-once) row stream well ahead in L1
-            prefetch_l1(dp + p.pf_units);
-            if ((k & 7) == 0) prefetch_l1(p.rowinfo + k + p.pf_units);
-        }
-
-        T e0, e1, e2, e3 = S::zero(), e4;
-        if (ci & RI_FIXED) {
-            if (CPLX) {
-                e0 = S::make(u4lo(c[0]), __dmul_rn(w, u4lo(c[2])));
-                e1 = S::make(u4hi(c[0]), __dmul_rn(w, u4hi(c[2])));
-                e2 = S::make(u4lo(c[1]), __dmul_rn(w, u4lo(c[FIX_UNITS - 1])));
-                e4 = S::make(u4hi(c[1]), 0.0);
-            } else {
-                e0 = S::make(u4lo(c[0]), 0.0);
-                e1 = S::make(u4hi(c[0]), 0.0);
-                e2 = S::make(u4lo(c[1]), 0.0);
-                e4 = S::make(u4hi(c[1]), 0.0);
-            }
-        } else {
-            e0 = e1 = e2 = e4 = S::zero();
-            const int nt = (int)(ci >> RI_NTERMS_SHIFT);
-            for (int t = 0; t < nt; ++t) {
-                const uint4 cur = __ldg(row + t);
-                const double K = u4hi(cur);
-                const uint32_t kind = (cur.x >> 4) & 0xfu;
-                double re = 0.0, im = 0.0;
-                if (kind == CK_CONST) re = K;
-                else if (kind == CK_JW_K) im = __dmul_rn(w, K);
-                else {
-                    const double v = IN[(size_t)cur.y * L];
-                    if (kind == CK_IN) re = v;
-                    else if (kind == CK_INV_IN) re = __ddiv_rn(1.0, v);
-                    else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
-                    else im = __dmul_rn(w, v);
-                }
-                if (cur.x & CT_NEG) { re = -re; im = -im; }
-                const uint32_t tgt = cur.x & 7u;       // warp-uniform: no divergence, accumulators stay in registers
-                if (tgt == CT_SUB) S::add(e0, re, im);
-                else if (tgt == CT_DIAG) S::add(e1, re, im);
-                else if (tgt == CT_SUP1) S::add(e2, re, im);
-                else if (tgt == CT_SUP2) S::add(e3, re, im);
-                else S::add(e4, re, im);
-            }
-        }
+    T *__restrict__ up = UY;                            // &UY[2k][lane]
+    const size_t up_step = (size_t)2 * (size_t)L;
+    auto finish_row = [&](T e0, T e1, T e2, T e3, T e4, bool has_u2) {
         const T wk = S::fnma(e1, e0, pu1);            // w_k     = diag - sub * u^_{k-1,k}
         const T s1 = S::fnma(e2, e0, pu2);            // sup1'   = sup1 - sub * u^_{k-1,k+1}
         const T yk = S::fnma(e4, e0, py);             // y_k     = rhs  - sub * y^_{k-1}
-        bool bad;
-        const T inv = S::rcp(wk, bad);
-        if (bad) status |= KRB_LANE_ZERO_PIVOT;
-        pu1 = S::mul(s1, inv);
-        pu2 = S::mul(e3, inv);
-        py = S::mul(yk, inv);
-        if (!(p.debug & 1)) {
-        __stcs(&UY[(size_t)(2 * k) * L], pu1);
-        __stcs(&UY[(size_t)(2 * k + 1) * L], py);
+        if (S::scale3(wk, s1, e3, yk, pu1, pu2, py)) status |= KRB_LANE_ZERO_PIVOT;
+        __stcs(up, pu1);
+        __stcs(up + L, py);
+        up += up_step;
+        if (has_u2) { __stcs(&UY[(size_t)(2 * n + r2) * L], pu2); ++r2; }
+    };
+    int k = 0;
+    const int n_runs = (p.debug & 4) ? 0 : p.n_runs;
+    for (int run = 0; run < n_runs; ++run) {
+        const uint32_t rd = __ldg(p.runs + run);
+        const int cnt = (int)(rd >> 1);
+        if (rd & 1u) {
+            uint4 q[FIX_UNITS];
+#pragma unroll
+            for (int i = 0; i < FIX_UNITS; ++i) q[i] = __ldg(dp + i);
+#pragma unroll 2
+            for (int r = 0; r < cnt; ++r) {
+                uint4 c[FIX_UNITS];
+#pragma unroll
+                for (int i = 0; i < FIX_UNITS; ++i) c[i] = q[i];
+                dp += FIX_UNITS;
+#pragma unroll
+                for (int i = 0; i < FIX_UNITS; ++i) q[i] = __ldg(dp + i);   // next record (the stream is padded past the end)
+                if ((r & 3) == 0 && p.pf_units > 0) prefetch_l1(dp + p.pf_units);
+                if (CPLX) {
+                    finish_row(S::make(u4lo(c[0]), __dmul_rn(w, u4lo(c[2]))), S::make(u4hi(c[0]), __dmul_rn(w, u4hi(c[2]))),
+                               S::make(u4lo(c[1]), __dmul_rn(w, u4lo(c[FIX_UNITS - 1]))), S::zero(), S::make(u4hi(c[1]), 0.0), false);
+                } else {
+                    finish_row(S::make(u4lo(c[0]), 0.0), S::make(u4hi(c[0]), 0.0), S::make(u4lo(c[1]), 0.0), S::zero(), S::make(u4hi(c[1]), 0.0), false);
+                }
+            }
+            k += cnt;
+        } else {
+            for (int r = 0; r < cnt; ++r, ++k) {
+                const uint32_t ci = __ldg(p.rowinfo + k);
+                const int nt = (int)(ci >> RI_NTERMS_SHIFT);
+                T e0 = S::zero(), e1 = S::zero(), e2 = S::zero(), e3 = S::zero(), e4 = S::zero();
+                for (int t = 0; t < nt; ++t) {
+                    const uint4 cur = __ldg(dp + t);
+                    const double K = u4hi(cur);
+                    const uint32_t kind = (cur.x >> 4) & 0xfu;
+                    double re = 0.0, im = 0.0;
+                    if (kind == CK_CONST) re = K;
+                    else if (kind == CK_JW_K) im = __dmul_rn(w, K);
+                    else {
+                        const double v = IN[(size_t)cur.y * L];
+                        if (kind == CK_IN) re = v;
+                        else if (kind == CK_INV_IN) re = __ddiv_rn(1.0, v);
+                        else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
+                        else im = __dmul_rn(w, v);
+                    }
+                    if (cur.x & CT_NEG) { re = -re; im = -im; }
+                    const uint32_t tgt = cur.x & 7u;   // warp-uniform: no divergence, accumulators stay in registers
+                    if (tgt == CT_SUB) S::add(e0, re, im);
+                    else if (tgt == CT_DIAG) S::add(e1, re, im);
+                    else if (tgt == CT_SUP1) S::add(e2, re, im);
+                    else if (tgt == CT_SUP2) S::add(e3, re, im);
+                    else S::add(e4, re, im);
+                }
+                dp += nt;
+                finish_row(e0, e1, e2, e3, e4, (ci & RI_HAS_U2) != 0);
+            }
         }
-        if (ci & RI_HAS_U2) { __stcs(&UY[(size_t)(2 * n + r2) * L], pu2); ++r2; }
     }
 
     // ---- backward: x_k = y^_k - u^_{k,k+1} x_{k+1} - u^_{k,k+2} x_{k+2}; reverse stream, double-buffered prefetch ----
@@ -263,7 +276,6 @@ __global__ void __launch_bounds__(TPB, (TPB == 32 ? 14 : TPB == 64 ? 7 : 3)) krb
         }
     };
     int k0 = (p.debug & 2) ? -1 : n - 1;
-    if (p.debug & 1) x1 = S::fnma(pu1, py, pu2);
     if (k0 >= R - 1) {
         load_group(k0, ua, ya);
         while (k0 >= 2 * R - 1 + R) {                 // two more full groups follow the current one

@@ -479,6 +479,11 @@ void build_chain_plan(Plan &plan, const std::vector<int> &input_of_elem) {
             if (has_u2) { n_u2++; ch.u2_rows.push_back(k); }
         }
     }
+    for (int k = 0; k < n; k++) {                                 // run table
+        const uint32_t fx = ch.rowinfo[k] & 1u;
+        if (!ch.runs.empty() && (ch.runs.back() & 1u) == fx) ch.runs.back() += 2u;
+        else ch.runs.push_back(2u | fx);
+    }
     ch.rowinfo.push_back(1u);                                   // sentinel row (prefetched, never used)
     for (int i = 0; i < 2 * 1100; i++) ch.stream.push_back(0);   // the kernel reads one record and prefetches up to 1024 units past the end
     for (int i = 0; i < 1100; i++) ch.rowinfo.push_back(1u);

@@ -97,6 +97,7 @@ struct ChainPlan {
     int n_u2 = 0;                        // rows with a second super-diagonal entry (extra planes 2n .. 2n+n_u2)
     int n_fixed = 0;                     // rows encoded as FIXED records
     std::vector<int> u2_rows;            // rows owning a u2 plane, ascending
+    std::vector<uint32_t> runs;          // (count << 1) | is_fixed: consecutive rows of the same record type
     bool identity_order = false;         // unknown_of_row[k] == k: results can be delivered point-major straight from the kernel
 };
 

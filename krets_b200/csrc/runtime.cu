@@ -67,6 +67,7 @@ struct DeviceState {
     uint4 *chain_stream = nullptr;
     int *chain_unknown = nullptr;
     int *chain_u2_rows = nullptr;
+    uint32_t *chain_runs = nullptr;
     double *B = nullptr;                 // static constant pool (uploaded once: the plan owns a fixed copy of the circuit)
     Buf Bstep, IN, G, XOP, status, iters;
     Buf X[2], packed[2];                 // double-buffered for host delivery
@@ -104,6 +105,7 @@ void device_state_free(DeviceState *d) {
     if (d->chain_stream) cudaFree(d->chain_stream);
     if (d->chain_unknown) cudaFree(d->chain_unknown);
     if (d->chain_u2_rows) cudaFree(d->chain_u2_rows);
+    if (d->chain_runs) cudaFree(d->chain_runs);
     if (d->B) cudaFree(d->B);
     d->Bstep.release(); d->IN.release(); d->G.release(); d->XOP.release(); d->status.release(); d->iters.release();
     for (int i = 0; i < 2; i++) {
@@ -140,6 +142,7 @@ static int upload_plan(Plan &plan, DeviceState &d) {
         if ((rc = upload_vec(plan.chain.stream, (uint64_t **)&d.chain_stream))) return rc;
         if ((rc = upload_vec(plan.chain.unknown_of_row, &d.chain_unknown))) return rc;
         if ((rc = upload_vec(plan.chain.u2_rows, &d.chain_u2_rows))) return rc;
+        if ((rc = upload_vec(plan.chain.runs, &d.chain_runs))) return rc;
     }
     std::vector<double> pool;
     evaluate_pool(plan, plan.circuit, plan.opts.time_step, pool);
@@ -344,7 +347,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             ChainParams c{};
             c.rowinfo = D0.chain_rowinfo; c.stream = D0.chain_stream; c.unknown_of_row = D0.chain_unknown; c.IN = IN;
             c.UY = D0.G.p; c.X = D0.X[b].p; c.n = n; c.input_freq = P0.input_freq; c.n_u2 = P0.chain.n_u2; c.L = Lpad; c.status = status_d;
-            c.u2_rows = D0.chain_u2_rows; c.out_lanes = lanes;
+            c.u2_rows = D0.chain_u2_rows; c.out_lanes = lanes; c.runs = D0.chain_runs; c.n_runs = (int)P0.chain.runs.size();
             { const char *dbg = getenv("KRB_CHAIN_DEBUG"); c.debug = dbg ? atoi(dbg) : 0; }
             { const char *pf = getenv("KRB_CHAIN_PF"); c.pf_units = pf ? atoi(pf) : 256; }
             c.OUT = direct ? (out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p) : nullptr;
