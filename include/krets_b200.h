@@ -93,7 +93,8 @@ void krb_circuit_destroy(krb_circuit *c);
 /* ---- one-time symbolic analysis ----------------------------------------------------------------------- */
 enum { KRB_MODE_DC = 0, KRB_MODE_AC = 1, KRB_MODE_TRAN = 2 };          /* stamp_*_dc / _ac / _transient */
 enum { KRB_INTEGRATOR_BE_KRETS = 0,   /* backward Euler incl. the reference's one-step source lag */
-       KRB_INTEGRATOR_TRAP = 1 };     /* trapezoidal companion models (north-star extension; no reference oracle) */
+       KRB_INTEGRATOR_TRAP = 1,       /* trapezoidal companion models, sources at t_n (north-star extension; not in the reference) */
+       KRB_INTEGRATOR_BE = 2 };       /* backward Euler with sources evaluated at t_n (no lag; not reference behaviour) */
 enum { KRB_EXEC_FUSED = 0,            /* default: stamp+factor+solve fused per lane; the executor is chosen from the plan's
                                          structure (native chain kernel for tridiagonal-after-permutation plans, lane VM otherwise) */
        KRB_EXEC_STAGED = 1,           /* stamp, factor, solve as separate launches through HBM value arrays (not implemented yet) */

@@ -56,6 +56,8 @@ int32_t krh_solver_solve_op(krh_solver *s, krh_result **out);                   
 int32_t krh_solver_solve_dc(krh_solver *s, const char *element, double start, double stop, double step_size, krh_result **out);
 int32_t krh_solver_solve_ac(krh_solver *s, int32_t sweep_kind, uint32_t points, double fstart, double fstop, krh_result **out);
 int32_t krh_solver_solve_transient(krh_solver *s, double time_step, double stop_time, krh_result **out);
+/* extension (not in the reference): same driver with KRB_INTEGRATOR_TRAP / KRB_INTEGRATOR_BE instead of the reference's lagged backward Euler */
+int32_t krh_solver_solve_transient_with(krh_solver *s, double time_step, double stop_time, int32_t integrator, krh_result **out);
 
 /* ---- krets_solver::AnalysisResult ---- */
 enum { KRH_RESULT_OP = 0, KRH_RESULT_DC = 1, KRH_RESULT_AC = 2, KRH_RESULT_TRANSIENT = 3 };

@@ -92,6 +92,7 @@ SYMBOLS = {
     "krh_solver_solve_dc": (_i32, [_vp, C.c_char_p, _f64, _f64, _f64, C.POINTER(_vp)]),
     "krh_solver_solve_ac": (_i32, [_vp, _i32, C.c_uint32, _f64, _f64, C.POINTER(_vp)]),
     "krh_solver_solve_transient": (_i32, [_vp, _f64, _f64, C.POINTER(_vp)]),
+    "krh_solver_solve_transient_with": (_i32, [_vp, _f64, _f64, _i32, C.POINTER(_vp)]),
     "krh_result_kind": (_i32, [_vp]),
     "krh_result_rows": (_i64, [_vp]),
     "krh_result_num_unknowns": (_i32, [_vp]),
@@ -108,6 +109,8 @@ _DEBUG_SYMBOLS = {
     "krb_plan_wave_value": (_i32, [_vp, _i32, _f64, _pf64]),
     "krb_plan_input_layout": (_i32, [_vp, _pi32, _pi32, _pi32]),
     "krb_plan_has_step_sections": (_i32, [_vp]),
+    "krb_plan_state_columns": (_i32, [_vp]),
+    "krb_plan_integrator": (_i32, [_vp]),
     "krb_plan_chain_size": (_i64, [_vp]),
     "krb_plan_get_chain": (_i32, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), _pi32]),
 }

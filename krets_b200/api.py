@@ -112,10 +112,14 @@ class AcAnalysis:            # analyses.rs:68-76
         return generate_frequencies(self.sweep.variation, self.sweep.points, self.fstart, self.fstop)
 
 
+INTEGRATOR_BE_KRETS, INTEGRATOR_TRAP, INTEGRATOR_BE = 0, 1, 2
+
+
 @dataclass
 class TransientAnalysis:     # analyses.rs:161-165
     time_step: float
     stop_time: float
+    integrator: int = 0      # extension: 0 = the reference's backward Euler (incl. its source lag), 1 = trapezoidal, 2 = BE at t_n
 
 
 class Analysis:              # analyses.rs:27-41
@@ -257,7 +261,7 @@ class Solver:
         elif analysis.kind == "ac":
             _check_krh(L.krh_solver_solve_ac(self._h, _SWEEP_KIND[p.sweep.variation], p.sweep.points, p.fstart, p.fstop, C.byref(r)))
         elif analysis.kind == "transient":
-            _check_krh(L.krh_solver_solve_transient(self._h, p.time_step, p.stop_time, C.byref(r)))
+            _check_krh(L.krh_solver_solve_transient_with(self._h, p.time_step, p.stop_time, p.integrator, C.byref(r)))
         else:
             raise ValueError(analysis.kind)
         try:
@@ -289,7 +293,8 @@ class Plan:
     """One-time symbolic analysis of a circuit for one stamp mode (krb_analyze) + lane-batch solves (krb_solve_*)."""
 
     def __init__(self, circuit: Circuit, mode: int, *, sweep_element: int = -1, varied=(), time_step: float = 0.0,
-                 nominal_frequency: float = 0.0, scratch_slots: int = 0, threads_per_block: int = 0, force_lane_vm: bool = False):
+                 nominal_frequency: float = 0.0, scratch_slots: int = 0, threads_per_block: int = 0, force_lane_vm: bool = False,
+                 integrator: int = 0):
         L = _lib.lib()
         self.circuit, self.mode = circuit, mode
         self.varied = list(varied)
@@ -305,6 +310,7 @@ class Plan:
         o.scratch_slots = scratch_slots
         o.threads_per_block = threads_per_block
         o.exec = 2 if force_lane_vm else 0
+        o.integrator = integrator
         self._varied_arr = (C.c_int32 * max(len(self.varied), 1))(*self.varied)
         o.n_varied = len(self.varied)
         o.varied_elements = C.cast(self._varied_arr, C.POINTER(C.c_int32))

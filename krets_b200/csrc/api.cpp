@@ -135,7 +135,7 @@ int64_t krb_plan_pool_size(const krb_plan *p) { return p ? (int64_t)p->p.pool.si
 int32_t krb_plan_eval_pool(const krb_plan *p, double *out) {
     if (!p || !out) return KRB_ERR_INVALID_ARGUMENT;
     std::vector<double> v;
-    evaluate_pool(p->p, p->p.circuit, p->p.opts.time_step, v);
+    evaluate_pool(p->p, p->p.circuit, p->p.h_comp, v);
     if (!v.empty()) std::memcpy(out, v.data(), v.size() * 8);
     return KRB_OK;
 }
@@ -161,6 +161,8 @@ int32_t krb_plan_get_chain(const krb_plan *p, uint32_t *rowinfo /*n+1*/, uint64_
     if (unknown_of_row) std::memcpy(unknown_of_row, ch.unknown_of_row.data(), ch.unknown_of_row.size() * sizeof(int));
     return KRB_OK;
 }
+int32_t krb_plan_integrator(const krb_plan *p) { return p ? p->p.opts.integrator : -1; }
+int32_t krb_plan_state_columns(const krb_plan *p) { return p ? (int32_t)p->p.state_elems.size() : -1; }
 int32_t krb_plan_has_step_sections(const krb_plan *p) { return p ? (p->p.has_step_sections ? 1 : 0) : -1; }
 
 static int check_io(const krb_io *io, krb_io &o) {

@@ -118,7 +118,7 @@ struct Section {
     int ldx(int which, int unknown, bool half_default) {
         return op(KOP_LDX, B.new_cell(), -1, -1, (uint32_t)unknown, (uint8_t)((which & 1) | (half_default ? 2 : 0)));
     }
-    enum Tag { T_G = 1, T_VAL, T_VOH, T_TWOPIF, T_JWV, T_VD, T_DIOG, T_DIOI, T_CAPH, T_INDH };
+    enum Tag { T_G = 1, T_VAL, T_VOH, T_TWOPIF, T_JWV, T_VD, T_DIOG, T_DIOI, T_CAPH, T_INDH, T_CAPI, T_INDV };
     int cached(Tag t, int e, bool neg, int (Section::*make)(int)) {
         auto key = std::make_tuple((int)t, e, (int)neg);
         auto it = derived.find(key);
@@ -132,7 +132,7 @@ struct Section {
     bool varied(int e) const { return B.input_of_elem[e] >= 0; }
     int elem_value(int e) { return varied(e) ? shared_input(B.input_of_elem[e]) : B.shared_pool_cell(B.pool_idx(P_VAL, false, e)); }
     int make_g(int e) { return un(KOP_INV, elem_value(e)); }                                   // 1.0 / value
-    int h_cell() { return B.shared_pool_cell(B.pool_idx(P_CONST, false, -1, B.plan.opts.time_step)); }
+    int h_cell() { return B.shared_pool_cell(B.pool_idx(P_CONST, false, -1, B.plan.h_comp)); }
     int make_voh(int e) { return varied(e) ? bin(KOP_DIVR, elem_value(e), h_cell()) : B.shared_pool_cell(B.pool_idx(P_VOH, false, e)); }
     int make_twopif(int) {
         const double two_pi = 2.0 * 3.14159265358979323846264338327950288;                     // 2.0 * PI
@@ -159,6 +159,18 @@ struct Section {
         else if (el.ip >= 0) v = ldx(0, el.ip, false);
         else v = un(KOP_NEG, ldx(0, el.im, false));
         return bin(KOP_MUL, coef, v);
+    }
+    int make_capi(int e) {                                                                     // trapezoidal: i_C of the previous row
+        auto &se = B.plan.state_elems;
+        const int j = (int)(std::find(se.begin(), se.end(), e) - se.begin());
+        return ldx(0, B.plan.circuit.n + j, false);
+    }
+    int make_indv(int e) {                                                                     // v+_prev - v-_prev across the inductor
+        const krb_element &el = B.plan.circuit.el[e];
+        if (el.ip >= 0 && el.im >= 0) return bin(KOP_SUB, ldx(0, el.ip, false), ldx(0, el.im, false));
+        if (el.ip >= 0) return ldx(0, el.ip, false);
+        if (el.im >= 0) return un(KOP_NEG, ldx(0, el.im, false));
+        return op(KOP_ZERO, B.new_cell());
     }
     int make_indh(int e) {                                                                     // (value/h) * i_prev
         const krb_element &el = B.plan.circuit.el[e];
@@ -196,6 +208,8 @@ struct Section {
         case S_DIODE_IEQ: return cached(T_DIOI, e, s.neg, &Section::make_dioi);
         case S_CAP_HIST: return cached(T_CAPH, e, s.neg, &Section::make_caph);
         case S_IND_HIST: return cached(T_INDH, e, s.neg, &Section::make_indh);
+        case S_CAP_IPREV: return cached(T_CAPI, e, s.neg, &Section::make_capi);
+        case S_IND_VPREV: return cached(T_INDV, e, s.neg, &Section::make_indv);
         }
         return -1;
     }
@@ -506,20 +520,24 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
     plan.opts.varied_elements = nullptr;
     const int n = c.n;
     if (mode == KRB_MODE_TRAN && !(plan.opts.time_step > 0.0)) { err = "transient plan needs time_step > 0"; return KRB_ERR_INVALID_ARGUMENT; }
-    if (plan.opts.integrator != KRB_INTEGRATOR_BE_KRETS) { err = "only KRB_INTEGRATOR_BE_KRETS is implemented"; return KRB_ERR_UNSUPPORTED; }
+    if (plan.opts.integrator < KRB_INTEGRATOR_BE_KRETS || plan.opts.integrator > KRB_INTEGRATOR_BE) { err = "unknown integrator"; return KRB_ERR_INVALID_ARGUMENT; }
+    const bool trap = (mode == KRB_MODE_TRAN && plan.opts.integrator == KRB_INTEGRATOR_TRAP);
+    plan.h_comp = trap ? plan.opts.time_step / 2.0 : plan.opts.time_step;
+    plan.state_elems.clear();
+    if (trap) for (int e = 0; e < (int)c.el.size(); e++) if (c.el[e].kind == KRB_C) plan.state_elems.push_back(e);
     for (int e : plan.varied) {
         if (e < 0 || e >= (int)c.el.size()) { err = "varied element ordinal out of range"; return KRB_ERR_INVALID_ARGUMENT; }
         const int k = c.el[e].kind;
         if (!(k == KRB_R || k == KRB_C || k == KRB_L || k == KRB_V || k == KRB_I)) { err = "only R/C/L/V/I values can vary per lane"; return KRB_ERR_INVALID_ARGUMENT; }
     }
-    int rc = build_stamps(c, mode, plan.stamps);
+    int rc = build_stamps(c, mode, plan.opts.integrator, plan.stamps);
     if (rc) { err = "element not supported in this analysis mode (the reference panics here)"; return rc; }
     build_pattern(n, plan.stamps, plan.pattern);
 
     // ---- static pivot plan ----
     std::vector<double> mag;
     const double fnom = plan.opts.nominal_frequency > 0.0 ? plan.opts.nominal_frequency : 1000.0;
-    nominal_magnitudes(c, plan.stamps, plan.pattern, mode, plan.opts.time_step, fnom, mag);
+    nominal_magnitudes(c, plan.stamps, plan.pattern, mode, plan.h_comp, fnom, mag);
     std::vector<int> match_row, order;
     if (!weighted_matching(plan.pattern, mag, match_row)) { err = "matrix is structurally singular"; return KRB_ERR_DECOMPOSITION_FAILED; }
     // Band-friendly candidates first (netlist order, reverse Cuthill-McKee both ways): ladders and lines come out with
@@ -610,6 +628,25 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
             const int u = S.col_order[k];
             sec.op(KOP_XOUT, -1, x, -1, (uint32_t)u, c.is_current[u] ? 1 : 0);
             X[k] = x;
+        }
+        // trapezoidal rule: carry each capacitor's current i_n = (2C/h)((v+ - v-)_n - (v+ - v-)_{n-1}) - i_{n-1} in a state column
+        if (!plan.state_elems.empty()) {
+            std::vector<int> pos_of_unknown(n);
+            for (int k = 0; k < n; k++) pos_of_unknown[S.col_order[k]] = k;
+            for (size_t j = 0; j < plan.state_elems.size(); j++) {
+                const int e = plan.state_elems[j];
+                const krb_element &el = c.el[e];
+                const int g = sec.varied(e) ? sec.cached(Section::T_VOH, e, false, &Section::make_voh) : sec.make_voh(e);
+                int vn, vp;
+                if (el.ip >= 0 && el.im >= 0) { vn = sec.bin(KOP_SUB, X[pos_of_unknown[el.ip]], X[pos_of_unknown[el.im]]); vp = sec.bin(KOP_SUB, sec.ldx(0, el.ip, false), sec.ldx(0, el.im, false)); }
+                else if (el.ip >= 0) { vn = X[pos_of_unknown[el.ip]]; vp = sec.ldx(0, el.ip, false); }
+                else if (el.im >= 0) { vn = sec.un(KOP_NEG, X[pos_of_unknown[el.im]]); vp = sec.un(KOP_NEG, sec.ldx(0, el.im, false)); }
+                else continue;
+                const int dv = sec.bin(KOP_SUB, vn, vp);
+                const int gi = sec.bin(KOP_MUL, g, dv);
+                const int inew = sec.bin(KOP_SUB, gi, sec.ldx(0, n + (int)j, false));
+                sec.op(KOP_XOUT, -1, inew, -1, (uint32_t)(n + j), 4);   // flag 4: state column (no convergence test, not delivered)
+            }
         }
     };
 

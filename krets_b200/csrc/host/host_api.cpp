@@ -28,7 +28,7 @@ struct krh_solver {                     // Solver { circuit, config }  solver.rs
     krb_circuit *kc = nullptr;
     std::map<int, std::unique_ptr<PlanHolder>> dc_plans;      // keyed by sweep element (-1: none)
     std::unique_ptr<PlanHolder> ac_plan;
-    std::map<double, std::unique_ptr<PlanHolder>> tran_plans; // keyed by time step
+    std::map<std::pair<double, int>, std::unique_ptr<PlanHolder>> tran_plans; // keyed by (time step, integrator)
     ~krh_solver() { dc_plans.clear(); ac_plan.reset(); tran_plans.clear(); krb_circuit_destroy(kc); }
 };
 
@@ -223,20 +223,25 @@ int32_t krh_solver_solve_ac(krh_solver *s, int32_t sweep_kind, uint32_t points, 
 
 // transient.rs:14-114
 int32_t krh_solver_solve_transient(krh_solver *s, double time_step, double stop_time, krh_result **out) {
+    return krh_solver_solve_transient_with(s, time_step, stop_time, KRB_INTEGRATOR_BE_KRETS, out);
+}
+int32_t krh_solver_solve_transient_with(krh_solver *s, double time_step, double stop_time, int32_t integrator, krh_result **out) {
     if (!s || !out) return fail(KRB_ERR_INVALID_ARGUMENT, "null argument");
     const int nsteps = krh_transient_num_steps(time_step, stop_time);                  // transient.rs:29
     int rc;
     krb_plan *pdc = get_dc_plan(s, -1, rc);
     if (!pdc) return fail_krb(rc);
-    auto it = s->tran_plans.find(time_step);
+    const auto key = std::make_pair(time_step, (int)integrator);
+    auto it = s->tran_plans.find(key);
     if (it == s->tran_plans.end()) {
         krb_plan_opts o;
         krb_default_plan_opts(&o);
         o.time_step = time_step;
+        o.integrator = integrator;
         auto h = std::make_unique<PlanHolder>();
         rc = krb_analyze(s->kc, KRB_MODE_TRAN, &o, &h->p);
         if (rc) return fail_krb(rc);
-        it = s->tran_plans.emplace(time_step, std::move(h)).first;
+        it = s->tran_plans.emplace(key, std::move(h)).first;
     }
     const int n = (int)s->pc.unknown_names.size();
     auto r = std::make_unique<krh_result>();

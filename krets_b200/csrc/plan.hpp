@@ -30,7 +30,10 @@ enum SrcKind : uint8_t {
     S_DIODE_G,    // linearised diode conductance          :597, :622
     S_DIODE_IEQ,  // diode equivalent current              :651
     S_CAP_HIST,   // (value/h) * (v+_prev - v-_prev)       :480-493  (== -i_eq)
-    S_IND_HIST    // (value/h) * i_prev                    :806-812
+    S_IND_HIST,   // (value/h) * i_prev                    :806-812
+    // trapezoidal companions (north-star extension; not in the reference). value/h is taken with h/2, i.e. 2*value/h.
+    S_CAP_IPREV,  // capacitor current of the previous time point (per-lane state column)
+    S_IND_VPREV   // v+_prev - v-_prev across an inductor
 };
 struct Src { SrcKind kind; bool neg; int elem; };
 struct MatContrib { int row, col; Src s; };
@@ -40,7 +43,7 @@ struct Stamps {
     std::vector<RhsContrib> rhs;
 };
 // returns KRB_OK / KRB_ERR_UNSUPPORTED
-int build_stamps(const Circuit &c, int mode, Stamps &out);
+int build_stamps(const Circuit &c, int mode, int integrator, Stamps &out);
 
 // unique (row,col) set in CSC order + the contributions of each entry in stamp order (== sum_triplets order)
 struct Pattern {
@@ -120,6 +123,8 @@ struct Plan {
     int input_sweep = -1, input_freq = -1;   // input plane holding the DC sweep value / the AC frequency
     std::vector<int> input_of_varied;        // input plane of varied[k]
     int64_t flops_per_point = 0, hbm_bytes_per_point = 0, alg_bytes_per_point = 0;
+    double h_comp = 0.0;                // companion-model step: h (backward Euler) or h/2 (trapezoidal: g = 2C/h)
+    std::vector<int> state_elems;       // trapezoidal: capacitors whose current is carried in result-row column n + j
     ChainPlan chain;                    // filled when the structure allows the native chain executor
     bool use_chain = false;             // executor selected for krb_solve_* (chain.valid and not forced to the lane VM)
     int64_t vm_hbm_bytes_per_point = 0;

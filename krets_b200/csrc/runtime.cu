@@ -145,7 +145,7 @@ static int upload_plan(Plan &plan, DeviceState &d) {
         if ((rc = upload_vec(plan.chain.runs, &d.chain_runs))) return rc;
     }
     std::vector<double> pool;
-    evaluate_pool(plan, plan.circuit, plan.opts.time_step, pool);
+    evaluate_pool(plan, plan.circuit, plan.h_comp, pool);
     if ((rc = upload_vec(pool, &d.B))) return rc;
     CUDA_TRY(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
@@ -227,6 +227,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if (PS && PS->n_inputs != P0.n_inputs) { set_error("plan_dc and plan_tran must be analysed with the same varied elements"); return KRB_ERR_INVALID_ARGUMENT; }
     if (n == 0 || a.lanes <= 0) return KRB_OK;
     const bool chain = P0.use_chain && !PS;
+    const int width = n + (PS ? (int)PS->state_elems.size() : 0);   // result-row columns incl. trapezoidal state
     const bool out_dev = (a.memory == KRB_MEM_DEVICE);
     // the chain kernel can write point-major results itself when pivot row k is unknown k (no X staging, no pack kernel)
     const bool direct = chain && P0.chain.identity_order && a.layout == KRB_LAYOUT_POINT_MAJOR && rows == 1;
@@ -242,7 +243,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             for (int r = 1; r < rows; r++)
                 for (int k = 0; k < nw; k++) {
                     const krb_element &el = PS->circuit.el[PS->wave_elems[k]];
-                    DS.bstep_host[((size_t)r * 2 + 0) * nw + k] = transient_value_at(el, (double)(r - 1) * h);   // stampable.rs:1043 + transient.rs:49
+                    DS.bstep_host[((size_t)r * 2 + 0) * nw + k] = transient_value_at(el, (double)(PS->opts.integrator == KRB_INTEGRATOR_BE_KRETS ? r - 1 : r) * h);   // stampable.rs:1043 + transient.rs:49 (lag only in reference mode)
                     DS.bstep_host[((size_t)r * 2 + 1) * nw + k] = transient_value_at(el, (double)r * h);         // transient.rs:95,105
                 }
             if ((rc = DS.Bstep.ensure(DS.bstep_host.size() * 8))) return rc;
@@ -254,7 +255,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     // ---- chunking: bound the per-call device footprint ----
     const int planes0 = chain ? 2 * n + P0.chain.n_u2 : P0.n_planes, planesS = PS ? PS->n_planes : 0;
     const int nbuf = out_dev ? 1 : 2;
-    const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)rows * n * ts * (out_dev ? 1 : 4) +
+    const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)rows * width * ts * (out_dev ? 1 : 4) +
                             (size_t)P0.n_inputs * 8 + (a.op_solution ? (size_t)n * 8 : 0) + 16;
     long long want = a.chunk_lanes > 0 ? a.chunk_lanes : (out_dev ? 65536 : 16384);
     want = std::min<long long>(want, ((a.lanes + tpb - 1) / tpb) * tpb);
@@ -273,7 +274,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if ((rc = D0.G.ensure(std::max<size_t>((size_t)planes0, 1) * chunk * ts))) return rc;
     if (PS && (rc = PS->dev->G.ensure(std::max<size_t>((size_t)planesS, 1) * chunk * ts))) return rc;
     for (int b = 0; b < nbuf; b++) {
-        if (!direct && (rc = D0.X[b].ensure((size_t)rows * n * chunk * ts))) return rc;
+        if (!direct && (rc = D0.X[b].ensure((size_t)rows * width * chunk * ts))) return rc;
         if (!out_dev && (rc = D0.packed[b].ensure((size_t)rows * n * chunk * ts))) return rc;
     }
     if ((rc = D0.status.ensure((size_t)chunk * 4 * 2))) return rc;
@@ -359,13 +360,14 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             p.B = D0.B; p.Bstep = nullptr; p.n_wave = 0;
             p.IN = IN; p.G = D0.G.p; p.X = D0.X[b].p;
             p.Xprev0 = a.op_solution ? (const double *)D0.XOP.p : nullptr;
-            p.n = n; p.L = Lpad;
+            p.n = n; p.row_width = width; p.L = Lpad;
             p.row_begin = 0; p.row_end = PS ? 1 : rows;
             p.nonlinear = (P0.circuit.nonlinear && !cplx) ? 1 : 0;
             p.max_iter = p.nonlinear ? std::max(1, a.cfg.maximum_iterations) : 1;
             p.guess_empty_at_iter0 = 1; p.pseudo_time = 0;
             p.h = P0.opts.time_step; p.reltol = a.cfg.relative_tolerance; p.iabstol = a.cfg.current_absolute_tolerance; p.vabstol = a.cfg.voltage_absolute_tolerance;
             p.status = status_d; p.iters = iters_d;
+            if (width > n) CUDA_TRY(cudaMemsetAsync((char *)D0.X[b].p + (size_t)n * Lpad * ts, 0, (size_t)(width - n) * Lpad * ts, st));   // i_C(0) = 0
             if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st))) return rc;
             if (PS && rows > 1) {
                 DeviceState &DS = *PS->dev;
@@ -393,12 +395,14 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             } else if (a.layout == KRB_LAYOUT_POINT_MAJOR) {
                 void *dst = (char *)a.x_out + (size_t)lane0 * per_point * ts;
                 dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)rows), block(32, 8);
-                if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)dst, rows, n, Lpad, lanes);
-                else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)dst, rows, n, Lpad, lanes);
+                if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)dst, rows, n, width, Lpad, lanes);
+                else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)dst, rows, n, width, Lpad, lanes);
                 g_launches++;
                 CUDA_TRY(cudaGetLastError());
             } else {
-                CUDA_TRY(cudaMemcpy2DAsync((char *)a.x_out + (size_t)lane0 * ts, (size_t)a.lanes * ts, D0.X[b].p, (size_t)Lpad * ts, (size_t)lanes * ts, per_point, cudaMemcpyDeviceToDevice, st));
+                for (int rr = 0; rr < (width == n ? 1 : rows); rr++)   // state columns are skipped row by row
+                    CUDA_TRY(cudaMemcpy2DAsync((char *)a.x_out + ((size_t)rr * n * a.lanes + (size_t)lane0) * ts, (size_t)a.lanes * ts, (char *)D0.X[b].p + (size_t)rr * width * Lpad * ts,
+                                               (size_t)Lpad * ts, (size_t)lanes * ts, width == n ? per_point : (size_t)n, cudaMemcpyDeviceToDevice, st));
             }
             if (a.lane_status) CUDA_TRY(cudaMemcpyAsync(a.lane_status + lane0, status_d, (size_t)lanes * 4, cudaMemcpyDeviceToDevice, st));
             if (a.iterations) CUDA_TRY(cudaMemcpyAsync(a.iterations + lane0, iters_d, (size_t)lanes * 4, cudaMemcpyDeviceToDevice, st));
@@ -406,8 +410,8 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             cudaStream_t cs = D0.copy_stream;
             if (a.layout == KRB_LAYOUT_POINT_MAJOR && !direct) {
                 dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)rows), block(32, 8);
-                if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)D0.packed[b].p, rows, n, Lpad, lanes);
-                else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)D0.packed[b].p, rows, n, Lpad, lanes);
+                if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)D0.packed[b].p, rows, n, width, Lpad, lanes);
+                else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)D0.packed[b].p, rows, n, width, Lpad, lanes);
                 g_launches++;
                 CUDA_TRY(cudaGetLastError());
             }
@@ -416,7 +420,9 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             if (a.layout == KRB_LAYOUT_POINT_MAJOR)
                 CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * per_point * ts, D0.packed[b].p, (size_t)lanes * per_point * ts, cudaMemcpyDeviceToHost, cs));
             else
-                CUDA_TRY(cudaMemcpy2DAsync((char *)a.x_out + (size_t)lane0 * ts, (size_t)a.lanes * ts, D0.X[b].p, (size_t)Lpad * ts, (size_t)lanes * ts, per_point, cudaMemcpyDeviceToHost, cs));
+                for (int rr = 0; rr < (width == n ? 1 : rows); rr++)
+                    CUDA_TRY(cudaMemcpy2DAsync((char *)a.x_out + ((size_t)rr * n * a.lanes + (size_t)lane0) * ts, (size_t)a.lanes * ts, (char *)D0.X[b].p + (size_t)rr * width * Lpad * ts,
+                                               (size_t)Lpad * ts, (size_t)lanes * ts, width == n ? per_point : (size_t)n, cudaMemcpyDeviceToHost, cs));
             if (a.lane_status) CUDA_TRY(cudaMemcpyAsync(a.lane_status + lane0, status_d, (size_t)lanes * 4, cudaMemcpyDeviceToHost, cs));
             if (a.iterations) CUDA_TRY(cudaMemcpyAsync(a.iterations + lane0, iters_d, (size_t)lanes * 4, cudaMemcpyDeviceToHost, cs));
             CUDA_TRY(cudaEventRecord(D0.copy_done[b], cs));

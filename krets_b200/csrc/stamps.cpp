@@ -30,7 +30,8 @@ struct Emit {
 };
 }  // namespace
 
-int build_stamps(const Circuit &c, int mode, Stamps &out) {
+int build_stamps(const Circuit &c, int mode, int integrator, Stamps &out) {
+    const bool trap = (mode == KRB_MODE_TRAN && integrator == KRB_INTEGRATOR_TRAP);
     out.mat.clear();
     out.rhs.clear();
     Emit E{out};
@@ -51,7 +52,9 @@ int build_stamps(const Circuit &c, int mode, Stamps &out) {
             } else {                          // :442-505
                 E.g1(ip, im, S_VOH, e);
                 E.b(ip, S_CAP_HIST, false, e);   // b[ip] += -i_eq = +(C/h) v_prev
+                if (trap) E.b(ip, S_CAP_IPREV, false, e);   // trapezoidal: ... + i_prev
                 E.b(im, S_CAP_HIST, true, e);    // b[im] += +i_eq
+                if (trap) E.b(im, S_CAP_IPREV, true, e);
             }
             break;
         case KRB_I:
@@ -83,6 +86,7 @@ int build_stamps(const Circuit &c, int mode, Stamps &out) {
                 E.m(ip, ic, S_ONE, false, e); E.m(ic, ip, S_ONE, false, e);
                 E.m(im, ic, S_ONE, true, e);  E.m(ic, im, S_ONE, true, e);
                 E.b(ic, S_IND_HIST, true, e);
+                if (trap) E.b(ic, S_IND_VPREV, true, e);    // trapezoidal: b[ic] = -(2L/h) i_prev - v_prev
             }
             break;
         case KRB_NMOS:

@@ -26,6 +26,7 @@ struct VmParams {
     void *X;                           // [rows][n][L] of T   (result rows, lane-interleaved)
     const double *Xprev0;              // real plane [n][L] used as "previous row" of row_begin (AC: OP solution); may be null
     int n;
+    int row_width;                     // columns per result row: n unknowns + per-lane state columns (trapezoidal capacitor currents)
     long long L;                       // lane stride of every plane (padded lane count)
     int row_begin, row_end;
     int nonlinear, max_iter;
@@ -97,10 +98,10 @@ __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
     int it_used = 0;
 
     for (int row = p.row_begin; row < p.row_end; ++row) {
-        T *Xcur = reinterpret_cast<T *>(p.X) + (size_t)row * (size_t)p.n * (size_t)L + lane;
+        T *Xcur = reinterpret_cast<T *>(p.X) + (size_t)row * (size_t)p.row_width * (size_t)L + lane;
         const double *Xprev;
         if (row == p.row_begin && p.Xprev0) Xprev = p.Xprev0 + lane;
-        else Xprev = reinterpret_cast<const double *>(reinterpret_cast<T *>(p.X) + (size_t)(row > 0 ? row - 1 : 0) * (size_t)p.n * (size_t)L) + lane;
+        else Xprev = reinterpret_cast<const double *>(reinterpret_cast<T *>(p.X) + (size_t)(row > 0 ? row - 1 : 0) * (size_t)p.row_width * (size_t)L) + lane;
         bool lane_active = true;
         const int n_pass = (p.sec1 && row == p.row_begin) ? 2 : 1;
         for (int pass = 0; pass < n_pass; ++pass) {
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
                         case KOP_XOUT: {
                             const T v = *pa;
                             if (!S::finite(v)) status |= KRB_LANE_NONFINITE;
-                            if (!CPLX && p.nonlinear && !guess_empty) {
+                            if (!CPLX && p.nonlinear && !guess_empty && !(bf & 4u)) {
                                 const double nv = S::re(v);
                                 const double ov = Xguess[(size_t)imm * L];
                                 const double diff = fabs(nv - ov);
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
 // x_out[lane][row][u] (point-major, what the reference returns per solved point) <- X[row][u][lane]
 // 32x32 tiles through shared memory so both sides are coalesced.
 template <typename T>
-__global__ void krb_pack_point_major(const T *__restrict__ X, T *__restrict__ out, int rows, int n, long long L, long long lanes) {
+__global__ void krb_pack_point_major(const T *__restrict__ X, T *__restrict__ out, int rows, int n, int width, long long L, long long lanes) {
     __shared__ T tile[32][33];
     const long long lane0 = (long long)blockIdx.x * 32;
     const int u0 = blockIdx.y * 32;
@@ -221,7 +222,7 @@ __global__ void krb_pack_point_major(const T *__restrict__ X, T *__restrict__ ou
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int u = u0 + j;
         const long long ln = lane0 + threadIdx.x;
-        if (u < n && ln < lanes) tile[j][threadIdx.x] = X[((size_t)row * n + u) * (size_t)L + ln];
+        if (u < n && ln < lanes) tile[j][threadIdx.x] = X[((size_t)row * width + u) * (size_t)L + ln];
     }
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {

@@ -600,12 +600,17 @@ static void stamp_g1(ko_trip *g, int ip, int im, double re, double imag) {
     if (ip >= 0 && im >= 0) { trip_push(g, ip, im, -re, -imag); trip_push(g, im, ip, -re, -imag); }
 }
 
-enum { MODE_DC = 0, MODE_AC = 1, MODE_TRAN = 2 };
+enum { MODE_DC = 0, MODE_AC = 1, MODE_TRAN = 2, MODE_TRAP = 3 };   /* MODE_TRAP: trapezoidal companions — NOT in the reference (no oracle upstream) */
 
 /* One element's matrix + RHS contribution.
  *   DC   : guess = NR guess map
  *   AC   : guess = OP solution, w = frequency
  *   TRAN : guess = NR guess, prev = previous time point, w = h */
+/* per-capacitor current state of the trapezoidal rule (indexed by element ordinal), set by the TRAP driver */
+static __thread const double *ko_trap_iprev = NULL;
+static __thread int ko_trap_elem = 0;
+static __thread double ko_trap_tnow = 0.0;
+
 static int stamp_element(const ko_elem *e, int mode, const ko_map *guess, const ko_map *prev, double w, ko_trip *g, ko_trip *b) {
     int ip = e->ip, im = e->im, ic = e->ic;
     switch (e->kind) {
@@ -616,6 +621,16 @@ static int stamp_element(const ko_elem *e, int mode, const ko_map *guess, const 
     }
     case KO_C:
         if (mode == MODE_DC) break;                          /* :361-368, :423-430 */
+        if (mode == MODE_TRAP) {                             /* i_n = (2C/h)(v_n - v_{n-1}) - i_{n-1}  (north-star extension) */
+            double gg = e->value / (w / 2.0);
+            stamp_g1(g, ip, im, gg, 0.0);
+            double vp = (prev->x && ip >= 0) ? prev->x[ip] : 0.0;
+            double vm = (prev->x && im >= 0) ? prev->x[im] : 0.0;
+            double hist = gg * (vp - vm) + ko_trap_iprev[ko_trap_elem];
+            if (ip >= 0) trip_push(b, ip, 0, hist, 0.0);
+            if (im >= 0) trip_push(b, im, 0, -hist, 0.0);
+            break;
+        }
         if (mode == MODE_AC) {                               /* :370-421 */
             double y = 2.0 * KO_PI * w * e->value;
             if (!e->g2) stamp_g1(g, ip, im, 0.0, y);
@@ -670,6 +685,13 @@ static int stamp_element(const ko_elem *e, int mode, const ko_map *guess, const 
             if (ip >= 0 && ic >= 0) trip_push(g, ic, ip, 1.0, 0.0);
             if (im >= 0 && ic >= 0) trip_push(g, ic, im, -1.0, 0.0);
             if (ic >= 0) trip_push(g, ic, ic, -0.0, -z);
+        } else if (mode == MODE_TRAP) {                      /* v_n - (2L/h) i_n = -(2L/h) i_{n-1} - v_{n-1} */
+            double zz = e->value / (w / 2.0);
+            if (ic >= 0) trip_push(g, ic, ic, -zz, 0.0);
+            if (ip >= 0 && ic >= 0) { trip_push(g, ip, ic, 1.0, 0.0); trip_push(g, ic, ip, 1.0, 0.0); }
+            if (im >= 0 && ic >= 0) { trip_push(g, im, ic, -1.0, 0.0); trip_push(g, ic, im, -1.0, 0.0); }
+            double vp = ip >= 0 ? prev->x[ip] : 0.0, vm = im >= 0 ? prev->x[im] : 0.0;
+            if (ic >= 0) { trip_push(b, ic, 0, -(zz * prev->x[ic]), 0.0); trip_push(b, ic, 0, -(vp - vm), 0.0); }
         } else {                                             /* :767-816 */
             if (ic >= 0) trip_push(g, ic, ic, -e->value / w, 0.0);
             if (ip >= 0 && ic >= 0) { trip_push(g, ip, ic, 1.0, 0.0); trip_push(g, ic, ip, 1.0, 0.0); }
@@ -687,6 +709,7 @@ static int stamp_element(const ko_elem *e, int mode, const ko_map *guess, const 
         if (ic >= 0) {
             if (mode == MODE_DC) trip_push(b, ic, 0, e->value, 0.0);
             else if (mode == MODE_AC) trip_push(b, ic, 0, e->ac_amplitude, 0.0);
+            else if (mode == MODE_TRAP) trip_push(b, ic, 0, vsrc_transient_value(e, ko_trap_tnow), 0.0);   /* source at t_n */
             else {
                 double t = guess->has_extra ? guess->extra : 0.0;   /* :1043 solution_map.get("time") */
                 trip_push(b, ic, 0, vsrc_transient_value(e, t), 0.0);
@@ -749,6 +772,7 @@ static void build_csc(const ko_trip *t, int n, int *Ap, int *Ai, double *Are, do
 static int assemble(const ko_circuit *c, int mode, const ko_map *guess, const ko_map *prev, double w, ko_trip *g, ko_trip *b) {
     for (int i = 0; i < c->ne; i++) {
         const ko_elem *e = &c->e[i];
+        ko_trap_elem = i;
         if (mode == MODE_DC && e->kind == KO_C) continue;    /* op.rs:20-24, dc.rs:60-64 */
         int rc = stamp_element(e, mode, guess, prev, w, g, b);
         if (rc) return rc;
@@ -1056,6 +1080,59 @@ int ko_solve_tran(const ko_circuit *c, const ko_config *cfg, double h, double st
         time[step] = t;
     }
     free(guess);
+    return rc;
+}
+
+/* Fixed-step transient with a selectable integrator.  integrator 0 = ko_solve_tran (reference backward Euler with the
+ * source lag); 1 = trapezoidal; 2 = backward Euler with the source evaluated at t_n.  1 and 2 are NOT reference
+ * behaviour: they restate the north-star extension so that the CUDA path has something to be checked against, and are
+ * themselves validated against closed-form RC / RL responses in tests/. */
+int ko_solve_tran_ex(const ko_circuit *c, const ko_config *cfg, double h, double stop, int integrator, double *out, double *time,
+                     int cap_rows, int *nrows) {
+    if (integrator == 0) return ko_solve_tran(c, cfg, h, stop, out, time, cap_rows, nrows);
+    int n = c->n;
+    int nsteps = ko_tran_num_steps(h, stop);
+    if (nrows) *nrows = nsteps + 1;
+    if (nsteps + 1 > cap_rows) return KO_ERR_BUFFER;
+    int rc = ko_solve_op(c, cfg, out, NULL);
+    if (rc) return rc;
+    time[0] = 0.0;
+    int nonlinear = ko_is_nonlinear(c);
+    double *guess = (double *)malloc(sizeof(double) * (n ? n : 1));
+    double *iprev = (double *)calloc(c->ne ? c->ne : 1, sizeof(double));   /* capacitor currents, 0 at the DC operating point */
+    ko_trap_iprev = iprev;
+    for (int step = 1; step <= nsteps && !rc; step++) {
+        double t = (double)step * h;
+        const double *prevx = out + (size_t)(step - 1) * n;
+        ko_map prev = { prevx, 1, time[step - 1] };
+        memcpy(guess, prevx, sizeof(double) * n);
+        ko_map g = { guess, 1, integrator == 2 ? t : time[step - 1] };
+        ko_trap_tnow = t;
+        double *x = out + (size_t)step * n;
+        for (int iter = 0; iter < cfg->maximum_iterations; iter++) {
+            rc = solve_point_real(c, integrator == 1 ? MODE_TRAP : MODE_TRAN, &g, &prev, h, x);
+            if (rc) break;
+            ko_map res = { x, 1, t };
+            if (!nonlinear) break;
+            ko_map gchk = { guess, 1, iter == 0 ? time[step - 1] : t };
+            if (convergence_check(c, cfg, &gchk, &res)) break;
+            memcpy(guess, x, sizeof(double) * n);
+            g.extra = t;
+            if (iter == cfg->maximum_iterations - 1) { rc = KO_ERR_MAX_ITERATIONS; break; }
+        }
+        if (integrator == 1)
+            for (int i = 0; i < c->ne; i++) {
+                const ko_elem *e = &c->e[i];
+                if (e->kind != KO_C) continue;
+                double gg = e->value / (h / 2.0);
+                double vn = (e->ip >= 0 ? x[e->ip] : 0.0) - (e->im >= 0 ? x[e->im] : 0.0);
+                double vp = (e->ip >= 0 ? prevx[e->ip] : 0.0) - (e->im >= 0 ? prevx[e->im] : 0.0);
+                iprev[i] = gg * (vn - vp) - iprev[i];
+            }
+        time[step] = t;
+    }
+    ko_trap_iprev = NULL;
+    free(guess); free(iprev);
     return rc;
 }
 

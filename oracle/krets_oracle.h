@@ -94,6 +94,10 @@ int ko_tran_num_steps(double h, double stop);
 int ko_solve_tran(const ko_circuit *c, const ko_config *cfg, double h, double stop, double *out, double *time,
                   int cap_rows, int *nrows);
 
+/* integrator: 0 reference BE (== ko_solve_tran), 1 trapezoidal, 2 BE without the source lag — 1 and 2 are not reference behaviour */
+int ko_solve_tran_ex(const ko_circuit *c, const ko_config *cfg, double h, double stop, int integrator, double *out, double *time,
+                     int cap_rows, int *nrows);
+
 /* Bounded faithful-work samples for bench.py's cpu_baseline: solve `npoints` DC points / AC points of the
  * circuit exactly as the drivers above do (full re-stamp, hash-sum, CSC, symbolic+numeric LU, solve per point). */
 const char *ko_version(void);

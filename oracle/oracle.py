@@ -80,6 +80,7 @@ def lib():
         L.ko_solve_ac.argtypes = [C.c_void_p, C.POINTER(_Config), dp, C.c_int, dp, ip, C.c_int]
         L.ko_tran_num_steps.argtypes = [C.c_double, C.c_double]
         L.ko_solve_tran.argtypes = [C.c_void_p, C.POINTER(_Config), C.c_double, C.c_double, dp, dp, C.c_int, ip]
+        L.ko_solve_tran_ex.argtypes = [C.c_void_p, C.POINTER(_Config), C.c_double, C.c_double, C.c_int, dp, dp, C.c_int, ip]
         L.ko_default_config.argtypes = [C.POINTER(_Config)]
         L.ko_version.restype = C.c_char_p
         _lib = L
@@ -220,13 +221,14 @@ class Circuit:
             raise OracleError(rc, "ac")
         return f[f > 0.0].copy(), out[: nout.value, : self.n]
 
-    def solve_tran(self, h: float, stop: float, cfg=None):
+    def solve_tran(self, h: float, stop: float, cfg=None, integrator: int = 0):
+        """integrator 0: reference backward Euler (transient.rs); 1: trapezoidal, 2: BE without source lag (non-reference)"""
         cfg = cfg or SolverConfig()
         ns = lib().ko_tran_num_steps(h, stop)
         out = np.zeros((ns + 1, max(self.n, 1)), dtype=np.float64)
         t = np.zeros(ns + 1, dtype=np.float64)
         nrows = C.c_int(0)
-        rc = lib().ko_solve_tran(self._h, C.byref(cfg.c), h, stop, _dp(out), _dp(t), ns + 1, C.byref(nrows))
+        rc = lib().ko_solve_tran_ex(self._h, C.byref(cfg.c), h, stop, integrator, _dp(out), _dp(t), ns + 1, C.byref(nrows))
         if rc:
             raise OracleError(rc, "tran")
         return t, out[:, : self.n]

@@ -382,3 +382,37 @@ def test_chain_monte_carlo_ac(oracle):
         for k, e in enumerate(varied):
             oc.set_element_value(e, vals[k, l])
         assert_close(out[l], oc.solve_ac([freqs[l]])[1][0], what=f"chain MC AC lane {l}")
+
+
+# ---- trapezoidal / lag-free backward Euler (extension; checked against the oracle's restatement) -----------------
+@pytest.mark.parametrize("integ", [1, 2])
+def test_transient_extension_integrators(oracle, golden, integ):
+    for key, h, stop, tol in [("dual_rc_ladder", 50e-6, 20e-3, 1e-9), ("low_pass_filter_transient", 50e-6, 5e-3, 1e-9),
+                              ("high_pass_filter_transient", 10e-6, 2e-3, 1e-9), ("rectifier", 50e-6, 20e-3, 1e-6)]:
+        circuit, oc = both(oracle, golden, key)
+        res = kb.Solver(circuit).solve(kb.Analysis.Transient(kb.TransientAnalysis(h, stop, integrator=integ)))
+        t, ref = oc.solve_tran(h, stop, integrator=integ)
+        assert res.array.shape == ref.shape
+        assert_close(res.array, ref, rtol=tol, what=f"{key} integrator {integ}")
+
+
+def test_monte_carlo_transient_trapezoidal(oracle, golden):
+    """BASELINE config 4 as written (trapezoidal steps x Monte-Carlo R/C variants) at reduced size."""
+    text = golden["netlists"]["dual_rc_ladder"]
+    circuit = kb.parse_circuit_description(text)
+    names = ["R1", "R2", "C1", "C2"]
+    varied = [circuit.element_index(nm) for nm in names]
+    lanes, h, nsteps = 96, 5e-6, 300
+    vals = np.array([[circuit.element_value(e) * netgen.mc_factor(l, j, 4) for l in range(lanes)] for j, e in enumerate(varied)])
+    pdc = kb.Plan(circuit, api.MODE_DC, varied=varied)
+    ptr = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=h, integrator=api.INTEGRATOR_TRAP)
+    out, status = ptr.solve_transient(pdc, nsteps, lanes, varied_values=np.ascontiguousarray(vals))
+    assert not status.any() and out.shape == (lanes, nsteps + 1, circuit.n)
+    out_li, _ = ptr.solve_transient(pdc, nsteps, lanes, varied_values=np.ascontiguousarray(vals), layout=api.LAYOUT_LANE_INTERLEAVED)
+    assert np.array_equal(np.transpose(out_li, (2, 0, 1)), out)
+    for l in (0, 41, 95):
+        oc = oracle.Circuit(text)
+        for j, nm in enumerate(names):
+            oc.set_element_value(oc.element_index(nm), vals[j, l])
+        _, ref = oc.solve_tran(h, nsteps * h, integrator=1)
+        assert_close(out[l], ref, what=f"MC trapezoidal lane {l}")

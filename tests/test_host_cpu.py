@@ -314,3 +314,39 @@ def test_chain_terms_ac_and_monte_carlo(oracle, golden):
         for k, e in enumerate(varied):
             oc.set_element_value(e, vals[k, l])
         assert_close(X[:, l], oc.solve_ac([f[l]])[1][0], what=f"chain MC lane {l}")
+
+
+# ---- trapezoidal / lag-free integrators (north-star extension; not reference behaviour) ---------------------------
+def test_trapezoidal_oracle_vs_closed_form(oracle):
+    """The non-reference integrators of the oracle are validated against the closed-form RC response to a sine source:
+    trapezoidal is second order (error drops ~4x per halving of h) and far more accurate than backward Euler."""
+    text = "V1 in 0 SIN(0 1 100 0 0 0)\nR1 in out 1k\nC1 out 0 1u\n"
+    oc = oracle.Circuit(text)
+    w, rc_ = 2 * np.pi * 100.0, 1e-3
+    def exact(t):
+        a = w * rc_
+        return (np.sin(w * t) - a * np.cos(w * t) + a * np.exp(-t / rc_)) / (1 + a * a)
+    errs = {}
+    for integ in (1, 2):
+        for h in (100e-6, 50e-6, 25e-6):
+            t, x = oc.solve_tran(h, 20e-3, integrator=integ)
+            errs[(integ, h)] = np.max(np.abs(x[:, oc.index_map["V(out)"]] - exact(t)))
+    assert errs[(1, 50e-6)] < 2e-4 and errs[(1, 50e-6)] < errs[(2, 50e-6)] / 20
+    assert 3.5 < errs[(1, 100e-6)] / errs[(1, 50e-6)] < 4.5 and 3.5 < errs[(1, 50e-6)] / errs[(1, 25e-6)] < 4.5
+    assert 1.7 < errs[(2, 100e-6)] / errs[(2, 50e-6)] < 2.3
+
+
+@pytest.mark.parametrize("integ", [1, 2])
+def test_program_transient_extensions(oracle, golden, integ):
+    cases = [("dual_rc_ladder", 50e-6, 5e-3), ("high_pass_filter_transient", 10e-6, 1e-3), ("rectifier", 50e-6, 3e-3)]
+    for key, h, stop in cases:
+        kc, oc = kcirc(golden, key), ocirc(oracle, golden, key)
+        pdc = kb.Plan(kc, api.MODE_DC)
+        ptr = kb.Plan(kc, api.MODE_TRAN, time_step=h, integrator=integ)
+        t, ref = oc.solve_tran(h, stop, integrator=integ)
+        rows = len(t)
+        em = Emulator(ptr, 1, rows=rows, h=h)
+        X = np.zeros((rows, em.width, 1))
+        X[:1, : kc.n] = Emulator(pdc, 1, rows=1).run(np.zeros((0, 1)))
+        X = em.run(np.zeros((0, 1)), X=X, row_begin=1, guess_empty_at_iter0=False, pseudo_time=True)
+        assert_close(X[:, : kc.n, 0], ref, rtol=1e-7 if key == "rectifier" else 1e-9, what=f"{key} integrator {integ}")

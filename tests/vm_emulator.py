@@ -16,6 +16,7 @@ ZERO_PIVOT, NOT_CONVERGED, NONFINITE = 1, 2, 4
 
 def _plan_tables(plan, rows, h):
     L = _lib.lib()
+    lag = 1 if int(L.krb_plan_integrator(plan._h)) == 0 else 0     # only the reference integrator lags the source
     npool = int(L.krb_plan_pool_size(plan._h))
     pool = np.zeros(max(npool, 1))
     L.krb_plan_eval_pool(plan._h, pool.ctypes.data_as(C.POINTER(C.c_double)))
@@ -24,7 +25,7 @@ def _plan_tables(plan, rows, h):
     for r in range(1, rows):
         for k in range(nw):
             v = C.c_double()
-            L.krb_plan_wave_value(plan._h, k, (r - 1) * h, C.byref(v))
+            L.krb_plan_wave_value(plan._h, k, (r - lag) * h, C.byref(v))
             bstep[r, 0, k] = v.value
             L.krb_plan_wave_value(plan._h, k, r * h, C.byref(v))
             bstep[r, 1, k] = v.value
@@ -43,6 +44,7 @@ class Emulator:
     def __init__(self, plan, lanes, *, rows=1, h=0.0, cfg=None, nonlinear=None, cplx=None):
         self.plan, self.L, self.rows, self.h = plan, lanes, rows, h
         self.n = plan.n
+        self.width = plan.n + max(int(_lib.lib().krb_plan_state_columns(plan._h)), 0)
         self.cplx = (plan.mode == 1) if cplx is None else cplx
         self.dtype = np.complex128 if self.cplx else np.float64
         self.pool, self.bstep = _plan_tables(plan, rows, h)
@@ -84,7 +86,7 @@ class Emulator:
                 elif opc == XOUT:
                     v = scr[a]
                     self.status[~np.isfinite(v)] |= NONFINITE
-                    if (not self.cplx) and self.nonlinear and not guess_empty:
+                    if (not self.cplx) and self.nonlinear and not guess_empty and not (b & 4):
                         ov = guess[imm]
                         diff = np.abs(v - ov)
                         scale = np.maximum(np.abs(v), np.abs(ov))
@@ -130,7 +132,7 @@ class Emulator:
         """IN: [n_inputs][L]; X: preallocated [rows][n][L] (transient continuation) or None."""
         row_end = self.rows if row_end is None else row_end
         if X is None:
-            X = np.zeros((self.rows, self.n, self.L), dtype=self.dtype)
+            X = np.zeros((self.rows, self.width, self.L), dtype=self.dtype)
         max_iter = self.cfg["max_iter"] if self.nonlinear and not self.cplx else 1
         for row in range(row_begin, row_end):
             prev = Xprev0 if (row == row_begin and Xprev0 is not None) else X[max(row - 1, 0)]

@@ -71,6 +71,11 @@ def main():
     outbuf = torch.empty((lanes, nsteps + 1, c.n), dtype=torch.float64, device="cuda")
     ms = timed(lambda: ptr.solve_transient(pdc, nsteps, lanes, varied_values=vals_d, out=outbuf), reps=2, warm=1)
     pts = lanes * nsteps
+    ptrap = kb.Plan(c, api.MODE_TRAN, varied=varied, time_step=5e-6, integrator=api.INTEGRATOR_TRAP)
+    ms_t = timed(lambda: ptrap.solve_transient(pdc, nsteps, lanes, varied_values=vals_d, out=outbuf), reps=2, warm=1)
+    out.append({"config": 4, "what": f"dual_rc_ladder transient TRAPEZOIDAL, {nsteps} steps x {lanes} MC lanes (n=4, f64)", "ms": ms_t,
+                "points_per_s": pts / (ms_t * 1e-3), "executor": ptrap.info.executor, "scratch_slots": int(ptrap.info.scratch_slots),
+                "spill_planes": int(ptrap.info.spill_planes)})
     out.append({"config": 4, "what": f"dual_rc_ladder transient BE_KRETS, {nsteps} steps x {lanes} MC lanes (n=4, f64)", "ms": ms,
                 "points_per_s": pts / (ms * 1e-3), "executor": ptr.info.executor, "scratch_slots": int(ptr.info.scratch_slots),
                 "spill_planes": int(ptr.info.spill_planes), "note": "lane VM, factor values pinned on chip; latency bound (512 warps on 592 schedulers)"})
