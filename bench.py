@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=LANES_PER_GPU)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--force-vm", action="store_true", help="profiling: run the workload on the general lane VM instead of the chain executor")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,7 +178,7 @@ def main():
     lanes = args.lanes
 
     circuit = kb.parse_circuit_description(netgen.resistor_ladder(LADDER_N))
-    plan = kb.Plan(circuit, api.MODE_DC, sweep_element=circuit.element_index("V1"))
+    plan = kb.Plan(circuit, api.MODE_DC, sweep_element=circuit.element_index("V1"), force_lane_vm=args.force_vm)
     info = plan.info
     n = info.n
     vals = (torch.arange(lanes, dtype=torch.float64, device="cuda") + float(rank * lanes)) * STEP

@@ -99,6 +99,10 @@ struct Section {
     int ldx_which_guess;   // LDX flag for "the linearisation point": 1 = NR guess (DC/TRAN), 0 = prev row (AC: OP solution)
     std::map<std::tuple<int, int, int>, int> derived;   // (tag, elem, neg) -> shared cell, valid inside this section
     std::map<int, int> input_cells;                    // plane -> shared remat cell
+    // linear transient, everything on chip: previous-row values and step-invariant companion coefficients are carried in
+    // pinned scratch cells instead of being re-read from HBM / re-derived at every step
+    std::map<int, int> *carry = nullptr;               // result-row column -> persistent cell holding its previous-row value
+    std::map<int, int> *coef_voh = nullptr;            // element -> persistent cell holding value / h (varied elements)
 
     explicit Section(Builder &b, int which_guess) : B(b), ldx_which_guess(which_guess) {}
 
@@ -116,6 +120,10 @@ struct Section {
         return c;
     }
     int ldx(int which, int unknown, bool half_default) {
+        if (carry && which == 0) {
+            auto it = carry->find(unknown);
+            if (it != carry->end()) return it->second;
+        }
         return op(KOP_LDX, B.new_cell(), -1, -1, (uint32_t)unknown, (uint8_t)((which & 1) | (half_default ? 2 : 0)));
     }
     enum Tag { T_G = 1, T_VAL, T_VOH, T_TWOPIF, T_JWV, T_VD, T_DIOG, T_DIOI, T_CAPH, T_INDH, T_CAPI, T_INDV };
@@ -133,7 +141,11 @@ struct Section {
     int elem_value(int e) { return varied(e) ? shared_input(B.input_of_elem[e]) : B.shared_pool_cell(B.pool_idx(P_VAL, false, e)); }
     int make_g(int e) { return un(KOP_INV, elem_value(e)); }                                   // 1.0 / value
     int h_cell() { return B.shared_pool_cell(B.pool_idx(P_CONST, false, -1, B.plan.h_comp)); }
-    int make_voh(int e) { return varied(e) ? bin(KOP_DIVR, elem_value(e), h_cell()) : B.shared_pool_cell(B.pool_idx(P_VOH, false, e)); }
+    int make_voh(int e) {
+        if (coef_voh && varied(e)) { auto it = coef_voh->find(e); if (it != coef_voh->end()) return it->second; }
+        return make_voh_raw(e);
+    }
+    int make_voh_raw(int e) { return varied(e) ? bin(KOP_DIVR, elem_value(e), h_cell()) : B.shared_pool_cell(B.pool_idx(P_VOH, false, e)); }
     int make_twopif(int) {
         const double two_pi = 2.0 * 3.14159265358979323846264338327950288;                     // 2.0 * PI
         return bin(KOP_MUL, B.shared_pool_cell(B.pool_idx(P_CONST, false, -1, two_pi)), shared_input(B.plan.input_freq));
@@ -244,6 +256,13 @@ struct Allocator {
     std::vector<int> cell_in;      // slot -> cell
     std::vector<char> dirty, stored, valid;   // valid: the slot holds the cell's current value
     bool pinned_valid;                         // pinned cells were computed by an earlier section
+    const std::vector<double> *pool_values = nullptr;   // constants are inlined into the op stream (KOP_LDK)
+    // Loads from HBM (inputs, spilled values, previous-row unknowns, source tables) are asynchronous (cp.async into the
+    // slot): the allocator issues them PREFETCH_DISTANCE ops ahead of their first use and emits KOP_WAIT before that use.
+    int PREFETCH_DISTANCE = 16;   // set from the scratch capacity: prefetched values must survive until they are used
+    std::vector<char> pending;
+    std::vector<int> pending_list;
+    int64_t waits = 0;
     AllocResult out;
 
     Allocator(std::vector<Cell> &c, int S_, int first_free, int &planes, bool pinned_valid_)
@@ -253,15 +272,57 @@ struct Allocator {
         dirty.assign(cells.size(), 0);
         stored.assign(cells.size(), 0);
         valid.assign(cells.size(), 0);
+        pending.assign(cells.size(), 0);
+        PREFETCH_DISTANCE = std::max(4, std::min(20, (S - first_free_slot) / 3));
     }
     void emit(uint32_t opc, uint32_t d, uint32_t a, uint32_t b, uint32_t imm) {
+        if (opc == KOP_LDB && pool_values) {
+            // inline constant: the value travels in the op stream (next slot) instead of a table in global memory;
+            // the interpreter fetches 32-op chunks, so the pair must not straddle a chunk
+            if (out.n_ops % 32 == 31) { out.ops.push_back(krb_op_w0(KOP_NOP, 0, 0, 0)); out.ops.push_back(0); out.n_ops++; }
+            uint64_t bits;
+            const double v = (*pool_values)[imm];
+            std::memcpy(&bits, &v, 8);
+            out.ops.push_back(krb_op_w0(KOP_LDK, d, 0, 0));
+            out.ops.push_back(0);
+            out.ops.push_back((uint32_t)(bits & 0xffffffffu));
+            out.ops.push_back((uint32_t)(bits >> 32));
+            out.n_ops += 2;
+            return;
+        }
         out.ops.push_back(krb_op_w0(opc, d, a, b));
         out.ops.push_back(imm);
         out.n_ops++;
     }
     void track(int s) { out.max_slot = std::max(out.max_slot, s); }
+    void mark_pending(int c) { if (!pending[c]) { pending[c] = 1; pending_list.push_back(c); } }
+    void emit_wait() {
+        if (pending_list.empty()) return;
+        emit(KOP_WAIT, 0, 0, 0, 0);
+        waits++;
+        for (int c : pending_list) pending[c] = 0;
+        pending_list.clear();
+    }
+    // issue the load that (re)materialises cell c into slot s
+    bool emit_load(int c, int s, std::string &err) {
+        if (!dirty[c] && cells[c].remat == R_LDB && !stored[c]) emit(KOP_LDB, s, 0, 0, cells[c].rimm);
+        else if (!dirty[c] && cells[c].remat == R_LDI && !stored[c]) { emit(KOP_LDI, s, 0, 0, cells[c].rimm); mark_pending(c); }
+        else if (stored[c]) { emit(KOP_LDG, s, 0, 0, (uint32_t)cells[c].home); out.ldg++; mark_pending(c); }
+        else { err = "internal: read of an undefined cell"; return false; }
+        return true;
+    }
 
-    bool run(const std::vector<VOp> &vops, std::string &err) {
+    bool run(const std::vector<VOp> &vops_in, std::string &err) {
+        // pure loads (previous-row unknowns, source-table entries) have no operands: hoist them so that their latency
+        // overlaps the ops in between
+        std::vector<VOp> vops;
+        vops.reserve(vops_in.size());
+        for (const VOp &v : vops_in) {
+            if (v.opc == KOP_LDX || v.opc == KOP_LDBS) {
+                const size_t pos = vops.size() > (size_t)PREFETCH_DISTANCE ? vops.size() - PREFETCH_DISTANCE : 0;
+                vops.insert(vops.begin() + pos, v);
+            } else vops.push_back(v);
+        }
         const int nv = (int)vops.size();
         // use lists
         std::vector<std::vector<int>> uses(cells.size());
@@ -296,18 +357,37 @@ struct Allocator {
                     if (s < 0) s = get_slot(excl1, i, next_use, err);
                     if (s < 0) return false;
                     if (cells[c].remat == R_LDB) emit(KOP_LDB, s, 0, 0, cells[c].rimm);
-                    else if (cells[c].remat == R_LDI) emit(KOP_LDI, s, 0, 0, cells[c].rimm);
+                    else if (cells[c].remat == R_LDI) { emit(KOP_LDI, s, 0, 0, cells[c].rimm); mark_pending(c); }
                     else { err = "internal: persistent cell never defined"; return false; }
                     slot_of[c] = s; cell_in[s] = c; track(s); valid[c] = 1; dirty[c] = 1;
                 }
                 if (cells[c].pin_slot >= 0) continue;
                 if (cells[c].home < 0) cells[c].home = n_planes++;
                 if (slot_of[c] >= 0) {
+                    if (pending[c]) emit_wait();
                     if (dirty[c] || !stored[c]) { emit(KOP_STG, 0, slot_of[c], 0, (uint32_t)cells[c].home); out.stg++; }
                     dirty[c] = 0; stored[c] = 1;
                 } else if (!stored[c]) { err = "internal: persistent cell lost"; return false; }
                 if (next_use(c, i) == INT32_MAX) release(c);
                 continue;
+            }
+            // ---- lookahead: bring the HBM-resident operands of the op PREFETCH_DISTANCE ahead on chip now ----
+            if (i + PREFETCH_DISTANCE < nv) {
+                const VOp &f = vops[i + PREFETCH_DISTANCE];
+                if (f.opc != VOP_PERSIST) {
+                    int fr[3] = {f.a, f.b, f.opc == KOP_FNMA ? f.d : -1};
+                    int cur_excl[3] = {v.d, v.a, v.b};
+                    for (int r = 0; r < 3; r++) {
+                        const int c = fr[r];
+                        if (c < 0 || slot_of[c] >= 0 || cells[c].pin_slot >= 0) continue;
+                        const bool loadable = (!dirty[c] && cells[c].remat == R_LDI && !stored[c]) || stored[c];
+                        if (!loadable) continue;
+                        const int s = get_slot(cur_excl, i, next_use, err, i + PREFETCH_DISTANCE);
+                        if (s < 0) { err.clear(); continue; }          // nothing can be evicted without hurting a nearer use
+                        if (!emit_load(c, s, err)) return false;
+                        slot_of[c] = s; cell_in[s] = c; track(s); valid[c] = 1;
+                    }
+                }
             }
             const bool reads_d = (v.opc == KOP_FNMA);
             int excl[3] = {v.d, v.a, v.b};
@@ -323,10 +403,7 @@ struct Allocator {
                 if (s < 0) s = get_slot(excl, i, next_use, err);
                 if (s < 0) return false;
                 valid[c] = 1;
-                if (!dirty[c] && cells[c].remat == R_LDB && !stored[c]) emit(KOP_LDB, s, 0, 0, cells[c].rimm);
-                else if (!dirty[c] && cells[c].remat == R_LDI && !stored[c]) emit(KOP_LDI, s, 0, 0, cells[c].rimm);
-                else if (stored[c]) { emit(KOP_LDG, s, 0, 0, (uint32_t)cells[c].home); out.ldg++; }
-                else { err = "internal: read of an undefined cell"; return false; }
+                if (!emit_load(c, s, err)) return false;
                 slot_of[c] = s; cell_in[s] = c; track(s);
             }
             int sd = 0;
@@ -339,10 +416,12 @@ struct Allocator {
                 sd = slot_of[v.d];
                 dirty[v.d] = 1; stored[v.d] = 0; valid[v.d] = 1;
             }
+            if ((v.a >= 0 && pending[v.a]) || (v.b >= 0 && pending[v.b]) || (v.d >= 0 && pending[v.d])) emit_wait();
             const int sa = v.a >= 0 ? slot_of[v.a] : 0, sb = v.b >= 0 ? slot_of[v.b] : 0;
             uint32_t bfield = (uint32_t)sb;
             if (v.opc == KOP_LDX || v.opc == KOP_XOUT) bfield = v.flags;
             emit(v.opc, (uint32_t)sd, (uint32_t)sa, bfield, v.imm);
+            if ((v.opc == KOP_LDX || v.opc == KOP_LDBS) && v.d >= 0) mark_pending(v.d);
             // free dead cells
             for (int r = 0; r < 3; r++) {
                 const int c = excl[r];
@@ -351,6 +430,7 @@ struct Allocator {
                 if (next_use(c, i) == INT32_MAX) release(c);
             }
         }
+        emit_wait();
         emit(KOP_END, 0, 0, 0, 0);
         return true;
     }
@@ -360,7 +440,7 @@ struct Allocator {
         if (s >= 0) { cell_in[s] = -1; slot_of[c] = -1; valid[c] = 0; }
     }
     template <class NU>
-    int get_slot(const int excl[3], int now, NU &next_use, std::string &err) {
+    int get_slot(const int excl[3], int now, NU &next_use, std::string &err, int min_far = -1) {
         for (int s = first_free_slot; s < S; s++)
             if (cell_in[s] < 0) return s;
         int victim = -1, far = -1;
@@ -377,7 +457,9 @@ struct Allocator {
             if (key > far || (key == far && cost_free)) { far = key; victim = s; }
         }
         if (victim < 0) { err = "scratch capacity too small for one operation"; return -1; }
+        if (min_far >= 0 && far <= min_far) { err = "no victim beyond the prefetch horizon"; return -1; }
         const int c = cell_in[victim];
+        if (pending[c]) emit_wait();   // the slot is the target of an in-flight asynchronous load
         const int nu = next_use(c, now - 1 < 0 ? -1 : now - 1);
         const bool needed_later = (nu != INT32_MAX) || (cells[c].persist && !stored[c]);
         if (needed_later && (dirty[c] || (cells[c].remat == R_NONE && !stored[c]))) {
@@ -620,8 +702,9 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
             if (persist) { B.cells[inv].persist = true; sec.vops.push_back({VOP_PERSIST, 0, -1, inv, -1, 0}); }
         }
     };
-    auto emit_back = [&](Section &sec) {
+    auto emit_back = [&](Section &sec, std::map<int, int> *carry_out = nullptr) {
         std::vector<int> X(n, -1);
+        std::vector<std::pair<int, int>> carry_updates;   // (persistent cell, new value cell)
         for (int k = n - 1; k >= 0; k--) {
             const int x = yhat[k];
             for (size_t t = 0; t < S.Upat[k].size(); t++) sec.op(KOP_FNMA, x, Ucell[k][t], X[S.Upat[k][t]]);
@@ -646,22 +729,68 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
                 const int gi = sec.bin(KOP_MUL, g, dv);
                 const int inew = sec.bin(KOP_SUB, gi, sec.ldx(0, n + (int)j, false));
                 sec.op(KOP_XOUT, -1, inew, -1, (uint32_t)(n + j), 4);   // flag 4: state column (no convergence test, not delivered)
+                if (carry_out && carry_out->count(n + (int)j)) carry_updates.push_back({(*carry_out)[n + (int)j], inew});
             }
+        }
+        if (carry_out) {
+            // the step's reads of the carried previous-row values are all above; now roll them forward
+            for (int k = 0; k < n; k++) {
+                auto it = carry_out->find(S.col_order[k]);
+                if (it != carry_out->end()) carry_updates.push_back({it->second, X[k]});
+            }
+            for (auto &cu : carry_updates) sec.op(KOP_MOV, cu.first, cu.second);
         }
     };
 
     if (!split) {
         emit_factor_rows(main_sec, true, false);
-        emit_back(main_sec);
+        emit_back(main_sec, nullptr);
     } else {
+        // Carry mode: when factors + state fit the scratch, the per-step section touches HBM only to deliver results.
+        int Scap0 = plan.opts.scratch_slots > 0 ? plan.opts.scratch_slots : (plan.is_complex ? 28 : 48);
+        Scap0 = std::max(8, std::min(Scap0, KRB_MAX_SLOTS));
+        const int width = n + (int)plan.state_elems.size();
+        const bool carry_mode = (S.nnz_lu + width + (int64_t)plan.varied.size() + 12 <= Scap0);
+        std::map<int, int> carry, coef_voh;
         emit_factor_rows(fac_sec, false, true);
+        if (carry_mode) {
+            // which previous-row columns does a step read?  (capacitor / inductor history, trapezoidal state)
+            std::vector<char> need(width, 0);
+            for (const RhsContrib &rc : plan.stamps.rhs) {
+                const krb_element &el = c.el[rc.s.elem];
+                if (rc.s.kind == S_CAP_HIST || rc.s.kind == S_IND_VPREV) { if (el.ip >= 0) need[el.ip] = 1; if (el.im >= 0) need[el.im] = 1; }
+                if (rc.s.kind == S_IND_HIST && el.ic >= 0) need[el.ic] = 1;
+            }
+            for (size_t j = 0; j < plan.state_elems.size(); j++) {
+                need[n + j] = 1;
+                const krb_element &el = c.el[plan.state_elems[j]];
+                if (el.ip >= 0) need[el.ip] = 1;
+                if (el.im >= 0) need[el.im] = 1;
+            }
+            for (int u = 0; u < width; u++)
+                if (need[u]) {
+                    const int cell = fac_sec.ldx(0, u, false);            // first step: previous row = the operating point (row 0)
+                    B.cells[cell].persist = true;
+                    fac_sec.vops.push_back({VOP_PERSIST, 0, -1, cell, -1, 0});
+                    carry[u] = cell;
+                }
+            for (int e : plan.varied) {
+                const int k = c.el[e].kind;
+                if (k != KRB_C && k != KRB_L) continue;
+                const int cell = fac_sec.cached(Section::T_VOH, e, false, &Section::make_voh);
+                if (!B.cells[cell].persist) { B.cells[cell].persist = true; fac_sec.vops.push_back({VOP_PERSIST, 0, -1, cell, -1, 0}); }
+                coef_voh[e] = cell;
+            }
+            step_sec.carry = &carry;
+            step_sec.coef_voh = &coef_voh;
+        }
         for (int k = 0; k < n; k++) {
             int Y = step_sec.sum_cell(rhs_srcs(plan, S.row_order[k]));
             for (size_t t = 0; t < S.Lpat[k].size(); t++) step_sec.op(KOP_FNMA, Y, Lcell[k][t], yhat[S.Lpat[k][t]]);
             step_sec.op(KOP_MUL, Y, Y, invd[k]);
             yhat[k] = Y;
         }
-        emit_back(step_sec);
+        emit_back(step_sec, carry_mode ? &carry : nullptr);
     }
 
     // ---- allocation ----
@@ -679,8 +808,11 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
         }
     }
     int max_slot = -1;
+    std::vector<double> pool_values;
+    evaluate_pool(plan, plan.circuit, plan.h_comp, pool_values);
     auto run_alloc = [&](Section &sec, Program &prog, bool pinned_valid) -> bool {
         Allocator A(B.cells, Scap, first_free, plan.n_planes, pinned_valid);
+        A.pool_values = &pool_values;
         if (!A.run(sec.vops, err)) return false;
         prog.ops.swap(A.out.ops);
         prog.n_ops = A.out.n_ops;

@@ -82,12 +82,55 @@ template <> struct Sc<true> {
 // diode.rs:42-70
 __device__ __forceinline__ double diode_limit(double vd, double vcrit) { return fmin(fmax(vd, -vcrit), vcrit); }
 
+// ---- shared-memory scratch access with 32-bit addresses (no generic-pointer arithmetic in the interpreter loop) ----
+template <bool CPLX> struct ScrIO;
+template <> struct ScrIO<false> {
+    static __device__ __forceinline__ double ld(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+};
+template <> struct ScrIO<true> {
+    static __device__ __forceinline__ double2 ld(uint32_t a) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory"); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory"); }
+};
+
+// asynchronous global -> shared copies straight into a scratch slot (LDGSTS); completion via KOP_WAIT
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <bool CPLX> __device__ __forceinline__ void async_real_to_slot(uint32_t saddr, const double *g) {
+    cp_async8(saddr, g);
+    if (CPLX) asm volatile("st.shared.f64 [%0], %1;" ::"r"(saddr + 8u), "d"(0.0) : "memory");   // (v, 0)
+}
+
+__device__ __forceinline__ double vm_rcp_seed(double x) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r; }
+// 1/x to ~1 ulp: r0 (1 + e + e^2) with e = 1 - x r0 (MUFU seed error ~2^-20 -> e^3 < 2^-60); pivots are not bit-pinned
+__device__ __forceinline__ double vm_fast_rcp(double x) {
+    const double r0 = vm_rcp_seed(x);
+    const double e = fma(-x, r0, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r0, t, r0);
+}
+template <bool CPLX> struct VmRcp;
+template <> struct VmRcp<false> {
+    static __device__ __forceinline__ double rcp(double a, bool &bad) { bad = !(fabs(a) > 0.0) || !isfinite(a); return vm_fast_rcp(a); }
+};
+template <> struct VmRcp<true> {
+    static __device__ __forceinline__ double2 rcp(double2 a, bool &bad) {
+        const double ns = fma(a.x, a.x, a.y * a.y);
+        bad = !(ns > 0.0) || !isfinite(ns);
+        const double r = vm_fast_rcp(ns);
+        return make_double2(a.x * r, -a.y * r);
+    }
+};
+
 template <bool CPLX, int TPB>
 __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
+    typedef ScrIO<CPLX> IO;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *scr = reinterpret_cast<T *>(smem_raw) + threadIdx.x;   // slot s lives at scr[s * TPB]
+    constexpr uint32_t SLOT_SHIFT = (CPLX ? 4 : 3) + (TPB == 32 ? 5 : TPB == 64 ? 6 : 7);   // log2(TPB * sizeof(T))
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + threadIdx.x * (uint32_t)sizeof(T);   // slot s at sbase + (s << SLOT_SHIFT)
     const unsigned lane_id = threadIdx.x & 31u;
     const long long lane = (long long)blockIdx.x * TPB + threadIdx.x;
     const long long L = p.L;
@@ -112,37 +155,46 @@ __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
                 const double *Xguess = (iter == 0 && !p.guess_empty_at_iter0) ? Xprev : reinterpret_cast<const double *>(Xcur);
                 const double *Bs = p.Bstep + ((size_t)row * 2 + (iter > 0 ? 1 : 0)) * (size_t)p.n_wave;
                 bool notconv = false;
-                // ---- run one program ----
+                // ---- run one program: 32-op chunks, one coalesced load per chunk (prefetched one chunk ahead), ops broadcast
+                // by shuffle; the next op's words are fetched while the current one executes ----
                 int pc = 0;
                 uint2 cur = prog[lane_id];
                 bool running = true;
                 while (running) {
                     const uint2 nxt = prog[pc + 32 + lane_id];   // programs are padded with 64 END ops
+                    uint32_t w0 = __shfl_sync(0xffffffffu, cur.x, 0);
+                    uint32_t imm = __shfl_sync(0xffffffffu, cur.y, 0);
+                    int t = 0;
 #pragma unroll 1
-                    for (int t = 0; t < 32; ++t) {
-                        const uint32_t w0 = __shfl_sync(0xffffffffu, cur.x, t);
-                        const uint32_t imm = __shfl_sync(0xffffffffu, cur.y, t);
+                    while (t < 32) {
+                        const int tn = t < 31 ? t + 1 : 31;
+                        const uint32_t nw0 = __shfl_sync(0xffffffffu, cur.x, tn);     // next op (or the inline constant of an LDK)
+                        const uint32_t nimm = __shfl_sync(0xffffffffu, cur.y, tn);
                         const uint32_t opc = w0 & 0xffu;
-                        if (opc == KOP_END) { running = false; break; }
-                        T *pd = scr + ((w0 >> 8) & 0xffu) * TPB;
-                        const T *pa = scr + ((w0 >> 16) & 0xffu) * TPB;
+                        const uint32_t ad = sbase + (((w0 >> 8) & 0xffu) << SLOT_SHIFT);
+                        const uint32_t aa = sbase + (((w0 >> 16) & 0xffu) << SLOT_SHIFT);
                         const uint32_t bf = w0 >> 24;
-                        const T *pb = scr + bf * TPB;
-                        switch (opc) {
-                        case KOP_LDB: *pd = S::from_real(__ldg(Bc + imm)); break;
-                        case KOP_LDBS: *pd = S::from_real(__ldg(Bs + imm)); break;
-                        case KOP_LDI: *pd = S::from_real(IN[(size_t)imm * L]); break;
-                        case KOP_LDG: *pd = G[(size_t)imm * L]; break;
-                        case KOP_STG: G[(size_t)imm * L] = *pa; break;
+                        const uint32_t ab = sbase + (bf << SLOT_SHIFT);
+                        int step = 1;
+                        if (opc == KOP_FNMA) IO::st(ad, S::fnma(IO::ld(ad), IO::ld(aa), IO::ld(ab)));
+                        else if (opc == KOP_LDK) { IO::st(ad, S::from_real(__hiloint2double((int)nimm, (int)nw0))); step = 2; }
+                        else if (opc == KOP_MUL) IO::st(ad, S::mul(IO::ld(aa), IO::ld(ab)));
+                        else if (opc == KOP_ADD) IO::st(ad, S::add(IO::ld(aa), IO::ld(ab)));
+                        else if (opc == KOP_STG) G[(size_t)imm * L] = IO::ld(aa);
+                        else if (opc == KOP_LDG) { if (CPLX) cp_async16(ad, G + (size_t)imm * L); else cp_async8(ad, G + (size_t)imm * L); }
+                        else if (opc == KOP_WAIT) cp_async_wait_all();
+                        else if (opc == KOP_END) { running = false; break; }
+                        else switch (opc) {
+                        case KOP_LDB: IO::st(ad, S::from_real(__ldg(Bc + imm))); break;
+                        case KOP_LDBS: async_real_to_slot<CPLX>(ad, Bs + imm); break;
+                        case KOP_LDI: async_real_to_slot<CPLX>(ad, IN + (size_t)imm * L); break;
                         case KOP_LDX: {
-                            double v;
-                            if (bf & 1u) v = guess_empty ? ((bf & 2u) ? 0.5 : 0.0) : Xguess[(size_t)imm * L];
-                            else v = Xprev[(size_t)imm * L];
-                            *pd = S::from_real(v);
+                            if ((bf & 1u) && guess_empty) IO::st(ad, S::from_real((bf & 2u) ? 0.5 : 0.0));   // empty solution map defaults
+                            else async_real_to_slot<CPLX>(ad, ((bf & 1u) ? Xguess : Xprev) + (size_t)imm * L);
                             break;
                         }
                         case KOP_XOUT: {
-                            const T v = *pa;
+                            const T v = IO::ld(aa);
                             if (!S::finite(v)) status |= KRB_LANE_NONFINITE;
                             if (!CPLX && p.nonlinear && !guess_empty && !(bf & 4u)) {
                                 const double nv = S::re(v);
@@ -155,39 +207,39 @@ __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
                             if (lane_active) Xcur[(size_t)imm * L] = v;
                             break;
                         }
-                        case KOP_ZERO: *pd = S::zero(); break;
-                        case KOP_MOV: *pd = *pa; break;
-                        case KOP_NEG: *pd = S::neg(*pa); break;
-                        case KOP_ADD: *pd = S::add(*pa, *pb); break;
-                        case KOP_SUB: *pd = S::sub(*pa, *pb); break;
-                        case KOP_MUL: *pd = S::mul(*pa, *pb); break;
-                        case KOP_FNMA: *pd = S::fnma(*pd, *pa, *pb); break;
+                        case KOP_ZERO: IO::st(ad, S::zero()); break;
+                        case KOP_MOV: IO::st(ad, IO::ld(aa)); break;
+                        case KOP_NEG: IO::st(ad, S::neg(IO::ld(aa))); break;
+                        case KOP_SUB: IO::st(ad, S::sub(IO::ld(aa), IO::ld(ab))); break;
                         case KOP_RCP: {
                             bool bad;
-                            *pd = S::rcp(*pa, bad);
+                            IO::st(ad, VmRcp<CPLX>::rcp(IO::ld(aa), bad));
                             if (bad) status |= KRB_LANE_ZERO_PIVOT;
                             break;
                         }
-                        case KOP_INV: *pd = S::from_real(__ddiv_rn(1.0, S::re(*pa))); break;
-                        case KOP_DIVR: *pd = S::from_real(__ddiv_rn(S::re(*pa), S::re(*pb))); break;
-                        case KOP_MULJ: *pd = S::mulj(*pa); break;
+                        case KOP_INV: IO::st(ad, S::from_real(__ddiv_rn(1.0, S::re(IO::ld(aa))))); break;
+                        case KOP_DIVR: IO::st(ad, S::from_real(__ddiv_rn(S::re(IO::ld(aa)), S::re(IO::ld(ab))))); break;
+                        case KOP_MULJ: IO::st(ad, S::mulj(IO::ld(aa))); break;
                         case KOP_DIOG: {   // (is/(n Vt)) * exp(vlim/(n Vt))
-                            const double vd = S::re(*pa);
+                            const double vd = S::re(IO::ld(aa));
                             const double vl = diode_limit(vd, __ldg(Bc + imm + 3));
-                            *pd = S::from_real(__ldg(Bc + imm) * exp(vl / __ldg(Bc + imm + 1)));
+                            IO::st(ad, S::from_real(__ldg(Bc + imm) * exp(vl / __ldg(Bc + imm + 1))));
                             break;
                         }
                         case KOP_DIOI: {   // is*(exp(vlim/(n Vt)) - 1) - g*vd
-                            const double vd = S::re(*pa);
+                            const double vd = S::re(IO::ld(aa));
                             const double vl = diode_limit(vd, __ldg(Bc + imm + 3));
                             const double ex = exp(vl / __ldg(Bc + imm + 1));
                             const double g = __ldg(Bc + imm) * ex;
                             const double id = __ldg(Bc + imm + 2) * (ex - 1.0);
-                            *pd = S::from_real(__dsub_rn(id, __dmul_rn(g, vd)));
+                            IO::st(ad, S::from_real(__dsub_rn(id, __dmul_rn(g, vd))));
                             break;
                         }
-                        default: break;
+                        default: break;   // KOP_NOP
                         }
+                        t += step;
+                        if (step == 1) { w0 = nw0; imm = nimm; }
+                        else if (t < 32) { w0 = __shfl_sync(0xffffffffu, cur.x, t); imm = __shfl_sync(0xffffffffu, cur.y, t); }
                     }
                     cur = nxt;
                     pc += 32;

@@ -35,7 +35,10 @@ enum KrbOp : uint32_t {
     KOP_MULJ = 18,  // scr[d] = (0, re(scr[a]))            (stamp: admittance (0, 2*pi*f*C), stampable.rs:379-382)
     KOP_DIOG = 19,  // scr[d] = diode conductance at vd = scr[a]; B[imm..imm+3] = {is/(n*Vt), n*Vt, is, vcrit}  (diode.rs:42-48)
     KOP_DIOI = 20,  // scr[d] = diode equivalent current at vd = scr[a]                                          (diode.rs:50-61)
-    KOP_COUNT = 21
+    KOP_LDK = 21,   // scr[d] = the f64 constant stored in the NEXT op slot (both words); that slot is skipped.  Never at chunk position 31.
+    KOP_NOP = 22,   // padding
+    KOP_WAIT = 23,  // wait for the asynchronous loads (LDI/LDG/LDX/LDBS are issued as cp.async straight into the scratch slot)
+    KOP_COUNT = 24
 };
 
 static inline uint32_t krb_op_w0(uint32_t opc, uint32_t d, uint32_t a, uint32_t b) { return opc | (d << 8) | (a << 16) | (b << 24); }

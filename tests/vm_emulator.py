@@ -10,7 +10,7 @@ import numpy as np
 
 from krets_b200 import _lib
 
-(END, LDB, LDBS, LDI, LDG, STG, LDX, XOUT, ZERO, MOV, NEG, ADD, SUB, MUL, FNMA, RCP, INV, DIVR, MULJ, DIOG, DIOI) = range(21)
+(END, LDB, LDBS, LDI, LDG, STG, LDX, XOUT, ZERO, MOV, NEG, ADD, SUB, MUL, FNMA, RCP, INV, DIVR, MULJ, DIOG, DIOI, LDK, NOP, WAIT) = range(24)
 ZERO_PIVOT, NOT_CONVERGED, NONFINITE = 1, 2, 4
 
 
@@ -56,17 +56,44 @@ class Emulator:
         self.status = np.zeros(lanes, dtype=np.int32)
         self.iters = np.zeros(lanes, dtype=np.int32)
         self.stats = dict(ldg=0, stg=0, ops=0)
+        self.pending = set()      # scratch slots with an asynchronous load in flight (must not be touched before WAIT)
 
     def run_prog(self, prog, IN, X, row, it, guess_empty, guess, prev, active):
         scr, G = self.scr, self.G
         notconv = np.zeros(self.L, dtype=bool)
         with np.errstate(all="ignore"):
-            for w0, imm in prog:
-                w0 = int(w0); imm = int(imm)
+            pcount = len(prog)
+            pci = 0
+            while pci < pcount:
+                w0, imm = int(prog[pci][0]), int(prog[pci][1])
+                pci += 1
                 opc, d, a, b = w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, (w0 >> 24) & 0xFF
                 self.stats["ops"] += 1
+                if opc in (ADD, SUB, MUL, FNMA, DIVR):
+                    touched = {d, a, b}
+                elif opc in (MOV, NEG, RCP, INV, MULJ, DIOG, DIOI):
+                    touched = {d, a}
+                elif opc in (STG, XOUT):
+                    touched = {a}
+                elif opc in (LDB, LDBS, LDI, LDG, LDX, ZERO, LDK):
+                    touched = {d}
+                else:
+                    touched = set()
+                assert not (touched & self.pending), f"op {opc} touches a slot with an async load in flight (missing WAIT)"
+                if opc in (LDBS, LDI, LDG) or (opc == LDX and not ((b & 1) and guess_empty)):
+                    self.pending.add(d)
                 if opc == END:
+                    assert not self.pending, "program ended with async loads in flight"
                     break
+                elif opc == LDK:
+                    assert (pci - 1) % 32 != 31, "LDK must not sit at the end of a 32-op chunk"
+                    bits = np.array([int(prog[pci][0]) | (int(prog[pci][1]) << 32)], dtype=np.uint64)
+                    pci += 1
+                    scr[d] = np.full(self.L, bits.view(np.float64)[0], dtype=self.dtype)
+                elif opc == NOP:
+                    pass
+                elif opc == WAIT:
+                    self.pending.clear()
                 elif opc == LDB:
                     scr[d] = np.full(self.L, self.pool[imm], dtype=self.dtype)
                 elif opc == LDBS:
