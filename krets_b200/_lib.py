@@ -113,6 +113,8 @@ _DEBUG_SYMBOLS = {
     "krb_plan_integrator": (_i32, [_vp]),
     "krb_plan_chain_size": (_i64, [_vp]),
     "krb_plan_get_chain": (_i32, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), _pi32]),
+    "krb_plan_front_array": (_i64, [_vp, _i32, _pi32]),
+    "krb_plan_front_info": (_i32, [_vp, C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -19,7 +19,9 @@ from ._lib import KrbConfig, KrbIO, KrbOverrides, KrbPlanInfo, KrbPlanOpts
 MODE_DC, MODE_AC, MODE_TRAN = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 LAYOUT_POINT_MAJOR, LAYOUT_LANE_INTERLEAVED = 0, 1
+EXEC_FUSED, EXEC_STAGED, EXEC_LANE_VM = 0, 1, 2   # krb_plan_opts.exec (STAGED = the supernodal front executor)
 LANE_ZERO_PIVOT, LANE_NOT_CONVERGED, LANE_NONFINITE = 1, 2, 4
+KIND_R, KIND_C, KIND_L, KIND_V, KIND_I, KIND_D, KIND_NMOS = range(7)   # krb_element.kind (elements.rs:45-55 order)
 
 _ERR_NAMES = {
     1: "InvalidArgument", 3: "ElementNotFound", 4: "InvalidElementFormat", 5: "MaximumIterationsExceeded",
@@ -294,7 +296,7 @@ class Plan:
 
     def __init__(self, circuit: Circuit, mode: int, *, sweep_element: int = -1, varied=(), time_step: float = 0.0,
                  nominal_frequency: float = 0.0, scratch_slots: int = 0, threads_per_block: int = 0, force_lane_vm: bool = False,
-                 integrator: int = 0):
+                 integrator: int = 0, executor: int | None = None):
         L = _lib.lib()
         self.circuit, self.mode = circuit, mode
         self.varied = list(varied)
@@ -309,7 +311,7 @@ class Plan:
         o.nominal_frequency = nominal_frequency
         o.scratch_slots = scratch_slots
         o.threads_per_block = threads_per_block
-        o.exec = 2 if force_lane_vm else 0
+        o.exec = executor if executor is not None else (EXEC_LANE_VM if force_lane_vm else EXEC_FUSED)
         o.integrator = integrator
         self._varied_arr = (C.c_int32 * max(len(self.varied), 1))(*self.varied)
         o.n_varied = len(self.varied)
@@ -338,6 +340,24 @@ class Plan:
             self._kc = None
 
     # -- introspection --
+    def front_tables(self) -> dict:
+        """Tables of the front executor (debug introspection; tests run them through a numpy multifrontal emulator)."""
+        L = _lib.lib()
+        names = ["piv0", "idx_ptr", "idx", "parent", "child_ptr", "child", "rel", "level_ptr", "level_fronts", "asm_ptr", "asm_ent", "asm_pos"]
+        out = {}
+        for which, name in enumerate(names):
+            size = L.krb_plan_front_array(self._h, which, None)
+            if size < 0:
+                raise KretsError(1, "plan does not use the front executor")
+            a = np.zeros(max(size, 1), dtype=np.int32)
+            L.krb_plan_front_array(self._h, which, a.ctypes.data_as(C.POINTER(C.c_int32)))
+            out[name] = a[:size]
+        info = (C.c_int64 * 8)()
+        _check_krb(L.krb_plan_front_info(self._h, info))
+        for k, name in enumerate(["n_fronts", "n_levels", "max_m", "max_p", "lu_size", "cb_size", "cbv_size", "flops"]):
+            out[name] = int(info[k])
+        return out
+
     def pattern(self):
         colptr = np.zeros(self.n + 1, dtype=np.int32)
         rowidx = np.zeros(max(self.info.nnz, 1), dtype=np.int32)

@@ -67,7 +67,7 @@ int32_t krb_analyze(const krb_circuit *c, int32_t mode, const krb_plan_opts *opt
         o = *opts;
     }
     if (o.n_varied < 0 || (o.n_varied > 0 && !o.varied_elements)) { set_error("krb_analyze: varied_elements missing"); return KRB_ERR_INVALID_ARGUMENT; }
-    if (o.exec != KRB_EXEC_FUSED && o.exec != KRB_EXEC_LANE_VM) { set_error("KRB_EXEC_STAGED is not implemented in this build"); return KRB_ERR_UNSUPPORTED; }
+    if (o.exec != KRB_EXEC_FUSED && o.exec != KRB_EXEC_LANE_VM && o.exec != KRB_EXEC_STAGED) { set_error("unknown krb_plan_opts.exec"); return KRB_ERR_INVALID_ARGUMENT; }
     krb_plan *p = new (std::nothrow) krb_plan();
     if (!p) return KRB_ERR_OUT_OF_MEMORY;
     std::string err;
@@ -85,6 +85,7 @@ int32_t krb_analyze(const krb_circuit *c, int32_t mode, const krb_plan_opts *opt
 void krb_plan_destroy(krb_plan *p) {
     if (!p) return;
     device_state_free(p->p.dev);
+    front_device_free(p->p.fdev);
     delete p;
 }
 
@@ -103,7 +104,7 @@ int32_t krb_plan_get_info(const krb_plan *p, krb_plan_info *info) {
     info->flops_per_point = P.flops_per_point;
     info->hbm_bytes_per_point = P.hbm_bytes_per_point;
     info->alg_bytes_per_point = P.alg_bytes_per_point;
-    info->executor = P.use_chain ? 1 : 0;
+    info->executor = P.use_front ? 2 : P.use_chain ? 1 : 0;
     info->reserved = 0;
     return KRB_OK;
 }
@@ -159,6 +160,24 @@ int32_t krb_plan_get_chain(const krb_plan *p, uint32_t *rowinfo /*n+1*/, uint64_
     if (rowinfo) std::memcpy(rowinfo, ch.rowinfo.data(), ch.rowinfo.size() * 4);
     if (stream) std::memcpy(stream, ch.stream.data(), ch.stream.size() * 8);
     if (unknown_of_row) std::memcpy(unknown_of_row, ch.unknown_of_row.data(), ch.unknown_of_row.size() * sizeof(int));
+    return KRB_OK;
+}
+/* front executor tables: which = 0 piv0, 1 idx_ptr, 2 idx, 3 parent, 4 child_ptr, 5 child, 6 rel, 7 level_ptr, 8 level_fronts,
+ * 9 asm_ptr, 10 asm_ent, 11 asm_pos; returns the length (copies when out != NULL) or -1 */
+int64_t krb_plan_front_array(const krb_plan *p, int32_t which, int32_t *out) {
+    if (!p || !p->p.use_front) return -1;
+    const FrontPlan &f = p->p.front;
+    const std::vector<int> *v[] = {&f.piv0, &f.idx_ptr, &f.idx, &f.parent, &f.child_ptr, &f.child, &f.rel, &f.level_ptr, &f.level_fronts,
+                                   &f.asm_ptr, &f.asm_ent, &f.asm_pos};
+    if (which < 0 || which >= 12) return -1;
+    if (out && !v[which]->empty()) std::memcpy(out, v[which]->data(), v[which]->size() * sizeof(int));
+    return (int64_t)v[which]->size();
+}
+/* out[0..7] = n_fronts, n_levels, max_m, max_p, lu_size, cb_size, cbv_size, flops */
+int32_t krb_plan_front_info(const krb_plan *p, int64_t *out) {
+    if (!p || !p->p.use_front || !out) return KRB_ERR_INVALID_ARGUMENT;
+    const FrontPlan &f = p->p.front;
+    out[0] = f.n_fronts; out[1] = f.n_levels; out[2] = f.max_m; out[3] = f.max_p; out[4] = f.lu_size; out[5] = f.cb_size; out[6] = f.cbv_size; out[7] = f.flops;
     return KRB_OK;
 }
 int32_t krb_plan_integrator(const krb_plan *p) { return p ? p->p.opts.integrator : -1; }

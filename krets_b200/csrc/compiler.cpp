@@ -624,8 +624,8 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
     if (!weighted_matching(plan.pattern, mag, match_row)) { err = "matrix is structurally singular"; return KRB_ERR_DECOMPOSITION_FAILED; }
     // Band-friendly candidates first (netlist order, reverse Cuthill-McKee both ways): ladders and lines come out with
     // lower bandwidth 1 / upper bandwidth 2 and no fill, which the native chain executor needs; otherwise minimum degree.
+    bool banded = false;
     {
-        bool banded = false;
         std::vector<int> cand(n);
         for (int i = 0; i < n; i++) cand[i] = i;
         if (band_ok(plan.pattern, match_row, cand)) { order = cand; banded = true; }
@@ -639,7 +639,14 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
         }
         if (!banded) minimum_degree(plan.pattern, match_row, order);
     }
-    symbolic_lu(plan.pattern, match_row, order, plan.sym);
+    // ---- executor selection: the one-thread-per-lane executors unroll the whole elimination into a lane program, which is
+    // right for ladders, filters and small networks; meshes go to the supernodal front executor (front_kernels.cuh) ----
+    bool use_front = (plan.opts.exec == KRB_EXEC_STAGED);
+    if (use_front && c.nonlinear) { err = "the front executor (KRB_EXEC_STAGED) handles linear circuits only"; return KRB_ERR_UNSUPPORTED; }
+    if (!use_front) {
+        symbolic_lu(plan.pattern, match_row, order, plan.sym);
+        if (plan.opts.exec == KRB_EXEC_FUSED && !banded && !c.nonlinear && plan.sym.flops > 250000) use_front = true;
+    }
     const Symbolic &S = plan.sym;
 
     // ---- per-lane inputs ----
@@ -660,6 +667,31 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
         if (B.input_of_elem[e] >= 0) { plan.input_of_varied.push_back(B.input_of_elem[e]); continue; }
         B.input_of_elem[e] = plan.n_inputs++;
         plan.input_of_varied.push_back(B.input_of_elem[e]);
+    }
+
+    if (use_front) {
+        build_front_plan(plan.pattern, match_row, order, plan.front);
+        const FrontPlan &fp = plan.front;
+        plan.sym = Symbolic();
+        plan.sym.n = n;
+        plan.sym.row_order = fp.row_order;
+        plan.sym.col_order = fp.col_order;
+        plan.sym.nnz_lu = fp.nnz_lu;
+        plan.sym.flops = fp.flops;
+        plan.front_input_of_elem = B.input_of_elem;
+        plan.wave_elems.clear();
+        for (const RhsContrib &rc : plan.stamps.rhs)
+            if (rc.s.kind == S_WAVE && std::find(plan.wave_elems.begin(), plan.wave_elems.end(), rc.s.elem) == plan.wave_elems.end()) plan.wave_elems.push_back(rc.s.elem);
+        plan.use_front = true;
+        plan.use_chain = false;
+        plan.has_step_sections = false;
+        const int64_t sz = plan.is_complex ? 16 : 8;
+        plan.flops_per_point = fp.flops * (plan.is_complex ? 4 : 1);
+        plan.alg_bytes_per_point = 8 * (int64_t)std::max(1, plan.n_inputs) + sz * (4 * fp.nnz_lu + 3 * (int64_t)n);
+        // what the kernels move per point: stamp A out + in, factor blocks out, contribution blocks out + in, solve reads the factor once
+        plan.hbm_bytes_per_point = 8 * (int64_t)std::max(1, plan.n_inputs) + sz * (2 * (int64_t)plan.pattern.nnz + 2 * fp.lu_size + 2 * fp.cb_size + 4 * (int64_t)n);
+        plan.vm_hbm_bytes_per_point = 0;
+        return KRB_OK;
     }
 
     // ---- emission ----

@@ -1,0 +1,438 @@
+// Runtime of the front executor (front_kernels.cuh): device tables of a FrontPlan, per-level launch lists, lane chunking
+// by device memory, and the analysis drivers (one-shot DC/AC solves, transient stepping with factors kept in HBM).
+// No CPU fallback: without a CUDA device every entry point returns KRB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "front_kernels.cuh"
+#include "plan.hpp"
+#include "runtime.hpp"
+
+namespace krb {
+
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) {                                                                               \
+            set_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);                    \
+            return (_e == cudaErrorMemoryAllocation) ? KRB_ERR_OUT_OF_MEMORY : KRB_ERR_CUDA;                   \
+        }                                                                                                      \
+    } while (0)
+
+namespace {
+struct FBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return KRB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        CUDA_TRY(cudaMalloc(&p, std::max<size_t>(need, 16)));
+        bytes = need;
+        return KRB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+struct FrontLaunch { int first, count; dim3 block; size_t smem; };
+}  // namespace
+
+struct FrontDevice {
+    bool uploaded = false;
+    FrontDesc *fronts = nullptr;
+    int *list = nullptr, *idx_unknown = nullptr, *rel = nullptr, *child = nullptr, *asm_ent = nullptr, *asm_pos = nullptr, *col_order = nullptr;
+    FrontElem *elems = nullptr;
+    FrontTerm *mat_terms = nullptr, *rhs_terms = nullptr;
+    int *mat_ptr = nullptr, *rhs_ptr = nullptr, *state_elems = nullptr;
+    std::vector<std::vector<FrontLaunch>> factor_launches, solve_launches;   // per level
+    long long fw_size = 0;
+    int smem_cap = 0;
+    FBuf IN, EV, A, LU, CB, FW, CBV, BP, ST, XS, status, Bstep;
+    std::vector<double> bstep_host;
+    int bstep_rows = -1;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    size_t events_used = 0;
+};
+
+static double front_sum_event_ms(void *obj) {
+    FrontDevice *d = (FrontDevice *)obj;
+    if (!d || d->events_used == 0) return -1.0;
+    double total = 0.0;
+    for (size_t i = 0; i < d->events_used; i++) {
+        if (cudaEventSynchronize(d->events[i].second) != cudaSuccess) return -1.0;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, d->events[i].first, d->events[i].second) != cudaSuccess) return -1.0;
+        total += ms;
+    }
+    return total;
+}
+
+void front_device_free(FrontDevice *d) {
+    if (!d) return;
+    retire_last_timer(d);
+    void *ptrs[] = {d->fronts, d->list, d->idx_unknown, d->rel, d->child, d->asm_ent, d->asm_pos, d->col_order, d->elems,
+                    d->mat_terms, d->rhs_terms, d->mat_ptr, d->rhs_ptr, d->state_elems};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep};
+    for (FBuf *b : bufs) b->release();
+    for (auto &e : d->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    delete d;
+}
+
+template <typename V>
+static int up(const std::vector<V> &v, V **out) {
+    CUDA_TRY(cudaMalloc((void **)out, std::max<size_t>(v.size(), 1) * sizeof(V)));
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice));
+    return KRB_OK;
+}
+
+static int upload_front(Plan &plan) {
+    if (!plan.fdev) plan.fdev = new FrontDevice();
+    FrontDevice &D = *plan.fdev;
+    if (D.uploaded) return KRB_OK;
+    const FrontPlan &fp = plan.front;
+    const size_t ts = plan.is_complex ? 16 : 8;
+    int dev = 0, optin = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    D.smem_cap = std::min(optin, 224 * 1024);
+    int m_smem = 1;
+    while ((size_t)(m_smem + 1) * (m_smem + 1) * ts <= (size_t)D.smem_cap) m_smem++;
+    if (const char *e = getenv("KRB_FRONT_SMEM_M")) m_smem = std::max(1, std::min(m_smem, atoi(e)));
+    const int nf = fp.n_fronts;
+    std::vector<FrontDesc> desc(nf);
+    D.fw_size = 0;
+    auto msize = [&](int f) { return (fp.piv0[f + 1] - fp.piv0[f]) + (fp.idx_ptr[f + 1] - fp.idx_ptr[f]); };
+    for (int f = 0; f < nf; f++) {
+        FrontDesc &d = desc[f];
+        d.p = fp.piv0[f + 1] - fp.piv0[f];
+        d.q = fp.idx_ptr[f + 1] - fp.idx_ptr[f];
+        d.piv0 = fp.piv0[f];
+        d.idx_off = fp.idx_ptr[f];
+        d.child_begin = fp.child_ptr[f]; d.child_end = fp.child_ptr[f + 1];
+        d.asm_begin = fp.asm_ptr[f]; d.asm_end = fp.asm_ptr[f + 1];
+        d.lu_off = fp.lu_off[f]; d.cb_off = fp.cb_off[f];
+        d.cbv_off = (int)fp.cbv_off[f]; d.pad = 0;
+        const long long m = d.p + d.q;
+        if (m > m_smem) { d.fw_off = D.fw_size; D.fw_size += ((m * m + 1) / 2) * 2; }
+        else d.fw_off = -1;
+    }
+    // launch lists: each level's fronts are sorted by size (largest first); cut them into size classes
+    D.factor_launches.assign(fp.n_levels, {});
+    D.solve_launches.assign(fp.n_levels, {});
+    for (int l = 0; l < fp.n_levels; l++) {
+        const int b = fp.level_ptr[l], e = fp.level_ptr[l + 1];
+        auto fclass = [&](int m) { return m > m_smem ? 0 : m > 96 ? 1 : m > 48 ? 2 : m > 16 ? 3 : 4; };
+        auto sclass = [&](int m) { return m > 128 ? 0 : m > 32 ? 1 : 2; };
+        for (int i = b; i < e;) {
+            const int m0 = msize(fp.level_fronts[i]);
+            const int c = fclass(m0);
+            int j = i;
+            while (j < e && fclass(msize(fp.level_fronts[j])) == c) j++;
+            FrontLaunch L;
+            L.first = i; L.count = j - i;
+            L.block = c <= 2 ? dim3(32, 16) : c == 3 ? dim3(32, 4) : dim3(16, 4);
+            L.smem = c == 0 ? std::min<size_t>((size_t)D.smem_cap, (size_t)2 * m0 * 16 * ts) : (size_t)m0 * m0 * ts;
+            D.factor_launches[l].push_back(L);
+            i = j;
+        }
+        for (int i = b; i < e;) {
+            const int m0 = msize(fp.level_fronts[i]);
+            const int c = sclass(m0);
+            int j = i;
+            while (j < e && sclass(msize(fp.level_fronts[j])) == c) j++;
+            FrontLaunch L;
+            L.first = i; L.count = j - i;
+            const int nt = c == 0 ? 256 : c == 1 ? 128 : 32;
+            L.block = dim3(nt);
+            L.smem = ((size_t)2 * m0 + nt) * ts;
+            D.solve_launches[l].push_back(L);
+            i = j;
+        }
+    }
+    int rc;
+    if ((rc = up(desc, &D.fronts))) return rc;
+    if ((rc = up(fp.level_fronts, &D.list))) return rc;
+    std::vector<int> idx_unknown(fp.idx.size());
+    for (size_t i = 0; i < fp.idx.size(); i++) idx_unknown[i] = fp.col_order[fp.idx[i]];
+    if ((rc = up(idx_unknown, &D.idx_unknown))) return rc;
+    if ((rc = up(fp.rel, &D.rel))) return rc;
+    if ((rc = up(fp.child, &D.child))) return rc;
+    if ((rc = up(fp.asm_ent, &D.asm_ent))) return rc;
+    if ((rc = up(fp.asm_pos, &D.asm_pos))) return rc;
+    if ((rc = up(fp.col_order, &D.col_order))) return rc;
+    // element table and stamp terms
+    const Circuit &c = plan.circuit;
+    std::vector<FrontElem> elems(c.el.size());
+    for (size_t e = 0; e < c.el.size(); e++) {
+        FrontElem &fe = elems[e];
+        fe.value = c.el[e].value; fe.ac_amp = c.el[e].ac_amplitude;
+        fe.ip = c.el[e].ip; fe.im = c.el[e].im; fe.ic = c.el[e].ic;
+        fe.in_plane = plan.front_input_of_elem.empty() ? -1 : plan.front_input_of_elem[e];
+        fe.wave_col = -1; fe.state_idx = -1;
+    }
+    for (size_t k = 0; k < plan.wave_elems.size(); k++) elems[plan.wave_elems[k]].wave_col = (int)k;
+    for (size_t j = 0; j < plan.state_elems.size(); j++) elems[plan.state_elems[j]].state_idx = (int)j;
+    if ((rc = up(elems, &D.elems))) return rc;
+    std::vector<FrontTerm> mt, rt;
+    std::vector<int> mp(plan.pattern.nnz + 1, 0), rp(plan.circuit.n + 1, 0);
+    for (int q = 0; q < plan.pattern.nnz; q++) {
+        for (int ci : plan.pattern.contribs[q]) { const Src &s = plan.stamps.mat[ci].s; mt.push_back({s.elem, (int)s.kind | (s.neg ? 0x100 : 0)}); }
+        mp[q + 1] = (int)mt.size();
+    }
+    for (int k = 0; k < plan.circuit.n; k++) {
+        for (int ri : plan.pattern.rhs_contribs[fp.row_order[k]]) { const Src &s = plan.stamps.rhs[ri].s; rt.push_back({s.elem, (int)s.kind | (s.neg ? 0x100 : 0)}); }
+        rp[k + 1] = (int)rt.size();
+    }
+    if ((rc = up(mt, &D.mat_terms))) return rc;
+    if ((rc = up(rt, &D.rhs_terms))) return rc;
+    if ((rc = up(mp, &D.mat_ptr))) return rc;
+    if ((rc = up(rp, &D.rhs_ptr))) return rc;
+    if ((rc = up(plan.state_elems, &D.state_elems))) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    D.uploaded = true;
+    return KRB_OK;
+}
+
+namespace {
+struct Bufs { void *A, *LU, *CB, *FW, *CBV, *BP; int *status; };
+}
+
+static FrontParams make_params(const Plan &plan, const Bufs &b, void *X, long long x_lane_stride, long long x_row_off) {
+    const FrontDevice &D = *plan.fdev;
+    const FrontPlan &fp = plan.front;
+    FrontParams P{};
+    P.fronts = D.fronts; P.list = D.list; P.idx_pos = nullptr; P.idx_unknown = D.idx_unknown; P.rel = D.rel; P.child = D.child;
+    P.asm_ent = D.asm_ent; P.asm_pos = D.asm_pos; P.col_order = D.col_order;
+    P.A = b.A; P.LU = b.LU; P.CB = b.CB; P.FW = b.FW; P.CBV = b.CBV; P.BP = b.BP;
+    P.a_stride = plan.pattern.nnz; P.lu_stride = fp.lu_size; P.cb_stride = fp.cb_size; P.fw_stride = D.fw_size; P.cbv_stride = fp.cbv_size;
+    P.n = fp.n; P.status = b.status;
+    P.X = X; P.x_lane_stride = x_lane_stride; P.x_row_off = x_row_off;
+    return P;
+}
+
+static int front_factor(const Plan &plan, FrontParams P, long long lanes, cudaStream_t st) {
+    const FrontDevice &D = *plan.fdev;
+    const size_t ts = plan.is_complex ? 16 : 8;
+    for (size_t l = 0; l < D.factor_launches.size(); l++)
+        for (const FrontLaunch &L : D.factor_launches[l]) {
+            FrontParams Q = P;
+            Q.list = D.list + L.first;
+            Q.smem_elems = (int)(L.smem / ts);
+            dim3 grid((unsigned)L.count, (unsigned)lanes);
+            if (plan.is_complex) krb_front_factor<true><<<grid, L.block, L.smem, st>>>(Q);
+            else krb_front_factor<false><<<grid, L.block, L.smem, st>>>(Q);
+            add_launches(1);
+        }
+    CUDA_TRY(cudaGetLastError());
+    return KRB_OK;
+}
+
+static int front_solve(const Plan &plan, FrontParams P, long long lanes, cudaStream_t st) {
+    const FrontDevice &D = *plan.fdev;
+    const int nl = (int)D.solve_launches.size();
+    for (int l = 0; l < nl; l++)
+        for (const FrontLaunch &L : D.solve_launches[l]) {
+            FrontParams Q = P;
+            Q.list = D.list + L.first;
+            dim3 grid((unsigned)L.count, (unsigned)lanes);
+            if (plan.is_complex) krb_front_forward<true><<<grid, L.block, L.smem, st>>>(Q);
+            else krb_front_forward<false><<<grid, L.block, L.smem, st>>>(Q);
+            add_launches(1);
+        }
+    for (int l = nl - 1; l >= 0; l--)
+        for (const FrontLaunch &L : D.solve_launches[l]) {
+            FrontParams Q = P;
+            Q.list = D.list + L.first;
+            dim3 grid((unsigned)L.count, (unsigned)lanes);
+            if (plan.is_complex) krb_front_backward<true><<<grid, L.block, L.smem, st>>>(Q);
+            else krb_front_backward<false><<<grid, L.block, L.smem, st>>>(Q);
+            add_launches(1);
+        }
+    CUDA_TRY(cudaGetLastError());
+    return KRB_OK;
+}
+
+int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
+    if (device_count() <= 0) { set_error("no CUDA device: krets_b200 has no CPU fallback"); return KRB_ERR_NO_DEVICE; }
+    Plan &P0 = *plan_first;
+    Plan *PS = plan_steps;
+    if (PS && !PS->use_front) { set_error("transient: plan_dc uses the front executor but plan_tran does not (analyse both with KRB_EXEC_STAGED)"); return KRB_ERR_UNSUPPORTED; }
+    if (a.layout != KRB_LAYOUT_POINT_MAJOR) { set_error("the front executor delivers point-major results only"); return KRB_ERR_UNSUPPORTED; }
+    if (a.op_solution && P0.circuit.nonlinear) { set_error("the front executor handles linear circuits only"); return KRB_ERR_UNSUPPORTED; }
+    int rc;
+    if ((rc = upload_front(P0))) return rc;
+    if (PS && (rc = upload_front(*PS))) return rc;
+    if (PS && PS->n_inputs != P0.n_inputs) { set_error("plan_dc and plan_tran must be analysed with the same varied elements"); return KRB_ERR_INVALID_ARGUMENT; }
+    FrontDevice &D = *P0.fdev;
+    cudaStream_t st = (cudaStream_t)a.stream;
+    const bool cplx = P0.is_complex;
+    const size_t ts = cplx ? 16 : 8;
+    const int n = P0.circuit.n, rows = a.rows;
+    const int n_elems = (int)P0.circuit.el.size();
+    const int n_state = PS ? (int)PS->state_elems.size() : 0;
+    if (n == 0 || a.lanes <= 0) return KRB_OK;
+    const bool out_dev = (a.memory == KRB_MEM_DEVICE);
+
+    if (PS) {   // per-step source table, as in the lane-VM runtime (the reference evaluates sources one step late)
+        FrontDevice &DS = *PS->fdev;
+        if (DS.bstep_rows != rows) {
+            const int nw = (int)PS->wave_elems.size();
+            const double h = PS->opts.time_step;
+            DS.bstep_host.assign((size_t)rows * 2 * std::max(nw, 1), 0.0);
+            for (int r = 1; r < rows; r++)
+                for (int k = 0; k < nw; k++) {
+                    const krb_element &el = PS->circuit.el[PS->wave_elems[k]];
+                    DS.bstep_host[((size_t)r * 2 + 0) * nw + k] = transient_value_at(el, (double)(PS->opts.integrator == KRB_INTEGRATOR_BE_KRETS ? r - 1 : r) * h);
+                    DS.bstep_host[((size_t)r * 2 + 1) * nw + k] = transient_value_at(el, (double)r * h);
+                }
+            if ((rc = DS.Bstep.ensure(DS.bstep_host.size() * 8))) return rc;
+            CUDA_TRY(cudaMemcpy(DS.Bstep.p, DS.bstep_host.data(), DS.bstep_host.size() * 8, cudaMemcpyHostToDevice));
+            DS.bstep_rows = rows;
+        }
+    }
+
+    // ---- chunking by device memory ----
+    auto mx = [&](auto f) { return PS ? std::max(f(P0), f(*PS)) : f(P0); };
+    const size_t lu_e = (size_t)mx([](const Plan &p) { return p.front.lu_size; });
+    const size_t cb_e = (size_t)mx([](const Plan &p) { return p.front.cb_size; });
+    const size_t cbv_e = (size_t)mx([](const Plan &p) { return p.front.cbv_size; });
+    const size_t fw_e = (size_t)mx([](const Plan &p) { return p.fdev->fw_size; });
+    const size_t a_e = (size_t)mx([](const Plan &p) { return (long long)p.pattern.nnz; });
+    const size_t per_lane = (lu_e + cb_e + cbv_e + fw_e + a_e + (size_t)n) * ts + (size_t)n_elems * 8 + (size_t)P0.n_inputs * 8 + (size_t)n_state * 8 +
+                            (out_dev ? 0 : (size_t)rows * n * ts) + 64;
+    long long chunk = a.chunk_lanes > 0 ? a.chunk_lanes : 1024;
+    chunk = std::min<long long>(chunk, a.lanes);
+    chunk = std::min<long long>(chunk, 65535);
+    {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t reusable = D.LU.bytes + D.CB.bytes + D.FW.bytes + D.CBV.bytes + D.A.bytes + D.BP.bytes + D.EV.bytes + D.XS.bytes + D.IN.bytes + D.ST.bytes;
+        const long long max_chunk = (long long)(((free_b + reusable) * 0.85) / (double)per_lane);
+        if (max_chunk < 1) { set_error("not enough device memory for one lane of this plan"); return KRB_ERR_OUT_OF_MEMORY; }
+        chunk = std::min(chunk, max_chunk);
+    }
+    if ((rc = D.IN.ensure(std::max<size_t>((size_t)P0.n_inputs, 1) * chunk * 8))) return rc;
+    if ((rc = D.EV.ensure(std::max<size_t>((size_t)n_elems, 1) * chunk * 8))) return rc;
+    if ((rc = D.A.ensure(a_e * chunk * ts))) return rc;
+    if ((rc = D.LU.ensure(lu_e * chunk * ts))) return rc;
+    if ((rc = D.CB.ensure(std::max<size_t>(cb_e, 1) * chunk * ts))) return rc;
+    if ((rc = D.FW.ensure(std::max<size_t>(fw_e, 1) * chunk * ts))) return rc;
+    if ((rc = D.CBV.ensure(std::max<size_t>(cbv_e, 1) * chunk * ts))) return rc;
+    if ((rc = D.BP.ensure((size_t)n * chunk * ts))) return rc;
+    if ((rc = D.ST.ensure(std::max<size_t>((size_t)n_state, 1) * chunk * 8))) return rc;
+    if ((rc = D.status.ensure((size_t)chunk * 4))) return rc;
+    if (!out_dev && (rc = D.XS.ensure((size_t)rows * n * chunk * ts))) return rc;
+
+    D.events_used = 0;
+    set_last_timer(front_sum_event_ms, &D);
+    const long long xls = (long long)rows * n;   // lane stride of the result rows
+    for (long long lane0 = 0; lane0 < a.lanes; lane0 += chunk) {
+        const long long lanes = std::min<long long>(chunk, a.lanes - lane0);
+        double *IN = (double *)D.IN.p;
+        for (int k = 0; k < P0.n_inputs; k++) {
+            const double *src = nullptr;
+            if (k == P0.input_sweep || k == P0.input_freq) src = a.lane_param;
+            else {
+                int vk = -1;
+                for (size_t q = 0; q < P0.input_of_varied.size(); q++) if (P0.input_of_varied[q] == k) { vk = (int)q; break; }
+                if (vk < 0 || !a.varied_values) { set_error("missing per-lane values for a varied element"); return KRB_ERR_INVALID_ARGUMENT; }
+                src = a.varied_values + (size_t)vk * a.lanes;
+            }
+            CUDA_TRY(cudaMemcpyAsync(IN + (size_t)k * lanes, src + lane0, (size_t)lanes * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY(cudaMemsetAsync(D.status.p, 0, (size_t)lanes * 4, st));
+        if (n_state) CUDA_TRY(cudaMemsetAsync(D.ST.p, 0, (size_t)n_state * lanes * 8, st));   // i_C(0) = 0
+        void *X = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * xls * ts) : D.XS.p;
+
+        if (D.events_used == D.events.size()) {
+            cudaEvent_t x, y;
+            CUDA_TRY(cudaEventCreate(&x));
+            CUDA_TRY(cudaEventCreate(&y));
+            D.events.push_back({x, y});
+        }
+        cudaEvent_t e0 = D.events[D.events_used].first, e1 = D.events[D.events_used].second;
+        D.events_used++;
+        CUDA_TRY(cudaEventRecord(e0, st));
+
+        Bufs bufs{D.A.p, D.LU.p, D.CB.p, D.FW.p, D.CBV.p, D.BP.p, (int *)D.status.p};
+        auto stamp_params = [&](const Plan &pl) {
+            const FrontDevice &DD = *pl.fdev;
+            FrontStampParams s{};
+            s.elems = DD.elems; s.n_elems = n_elems; s.IN = IN; s.L = lanes; s.EV = (double *)D.EV.p;
+            s.input_freq = pl.input_freq; s.h_comp = pl.h_comp; s.x_lane_stride = xls;
+            s.ST = (double *)D.ST.p; s.n_state = n_state;
+            return s;
+        };
+        {   // per-lane element values
+            FrontStampParams s = stamp_params(P0);
+            krb_front_expand<<<dim3((unsigned)((n_elems + 255) / 256), (unsigned)lanes), 256, 0, st>>>(s);
+            add_launches(1);
+        }
+        auto stamp_and_factor = [&](const Plan &pl) -> int {
+            FrontStampParams s = stamp_params(pl);
+            s.terms = pl.fdev->mat_terms; s.term_ptr = pl.fdev->mat_ptr; s.count = pl.pattern.nnz; s.OUT = D.A.p;
+            dim3 grid((unsigned)((s.count + 255) / 256), (unsigned)lanes);
+            if (pl.is_complex) krb_front_stamp<true><<<grid, 256, 0, st>>>(s);
+            else krb_front_stamp<false><<<grid, 256, 0, st>>>(s);
+            add_launches(1);
+            return front_factor(pl, make_params(pl, bufs, X, xls, 0), lanes, st);
+        };
+        auto rhs_and_solve = [&](const Plan &pl, int row) -> int {
+            FrontStampParams s = stamp_params(pl);
+            s.terms = pl.fdev->rhs_terms; s.term_ptr = pl.fdev->rhs_ptr; s.count = n; s.OUT = D.BP.p;
+            s.Bstep = (const double *)pl.fdev->Bstep.p; s.n_wave = (int)pl.wave_elems.size(); s.row = row;
+            s.Xprev = row > 0 ? (const double *)X + (size_t)(row - 1) * n : nullptr;
+            dim3 grid((unsigned)((n + 255) / 256), (unsigned)lanes);
+            if (pl.is_complex) krb_front_rhs<true><<<grid, 256, 0, st>>>(s);
+            else krb_front_rhs<false><<<grid, 256, 0, st>>>(s);
+            add_launches(1);
+            return front_solve(pl, make_params(pl, bufs, X, xls, (long long)row * n), lanes, st);
+        };
+        if ((rc = stamp_and_factor(P0))) return rc;
+        if ((rc = rhs_and_solve(P0, 0))) return rc;
+        if (PS && rows > 1) {
+            if ((rc = stamp_and_factor(*PS))) return rc;
+            for (int r = 1; r < rows; r++) {
+                if ((rc = rhs_and_solve(*PS, r))) return rc;
+                if (n_state) {
+                    FrontTrapParams t{};
+                    t.elems = PS->fdev->elems; t.state_elems = PS->fdev->state_elems; t.n_state = n_state; t.n_elems = n_elems;
+                    t.EV = (const double *)D.EV.p; t.h_comp = PS->h_comp;
+                    t.Xnew = (const double *)X + (size_t)r * n; t.Xprev = (const double *)X + (size_t)(r - 1) * n; t.x_lane_stride = xls;
+                    t.ST = (double *)D.ST.p;
+                    krb_front_trap_state<<<dim3((unsigned)((n_state + 255) / 256), (unsigned)lanes), 256, 0, st>>>(t);
+                    add_launches(1);
+                }
+            }
+        }
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaGetLastError());
+        // ---- delivery ----
+        if (!out_dev) {
+            CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * xls * ts, D.XS.p, (size_t)lanes * xls * ts, cudaMemcpyDeviceToHost, st));
+            if (a.lane_status) CUDA_TRY(cudaMemcpyAsync(a.lane_status + lane0, D.status.p, (size_t)lanes * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        } else if (a.lane_status) {
+            CUDA_TRY(cudaMemcpyAsync(a.lane_status + lane0, D.status.p, (size_t)lanes * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        if (a.iterations) {
+            // linear circuits: one Newton iteration (op.rs:33-82 with an empty first guess converges on the second pass only for
+            // nonlinear elements; the reference returns after iteration 1 for linear circuits)
+            std::vector<int> ones((size_t)lanes, 1);
+            CUDA_TRY(cudaMemcpyAsync(a.iterations + lane0, ones.data(), (size_t)lanes * 4, out_dev ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    return KRB_OK;
+}
+
+}  // namespace krb

@@ -1,0 +1,413 @@
+// sm_100a kernels of the front executor: batched supernodal multifrontal LU over independent solve lanes, for circuits
+// whose factor is far too large for the one-thread-per-lane executors (RLC meshes: n ~ 1e5, nnz(L+U) ~ 1e7 per lane).
+//
+// Replaces, per lane, faer's sp_lu() + solve() (op.rs:48-58, dc.rs:81-90, ac.rs:67-95, transient.rs:74-83) on the
+// shared static pattern.  Parallelism: grid = (fronts of one tree level, lanes); one CTA factorises one dense front of
+// one lane.  Layout: lane-major — every lane owns a contiguous factor store, inside it fronts are laid out in level order
+// and each front's L block is column-major, so a CTA streams its front with unit stride.
+//
+//   krb_front_expand   per-lane element values EV[lane][element] (Monte-Carlo inputs or nominal)
+//   krb_front_stamp    (a) stamps the CSC value array A[lane][entry] in stamp order (== sum_triplets, solver.rs:59-70)
+//   krb_front_rhs      right-hand side in pivot order incl. the companion-model history terms (stampable.rs:470-505, 806-815)
+//   krb_front_factor   (b) assemble (stamps + children's contribution blocks), dense partial LU, write L/U panels + contribution block
+//                      - fronts that fit in shared memory: right-looking rank-1 updates on the staged block
+//                      - larger fronts: blocked (panel in shared memory, 4x2 register tiles on the trailing block in L2/HBM)
+//   krb_front_forward  (c) level-scheduled forward substitution  (leaves -> root)
+//   krb_front_backward (c) level-scheduled backward substitution (root -> leaves), delivers x point-major
+//   krb_front_trap_state  trapezoidal capacitor currents carried between steps
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plan.hpp"
+#include "scalar.cuh"
+
+namespace krb {
+
+struct FrontDesc {            // one per front, 64 B
+    int p, q, piv0, idx_off;  // idx_off: into idx_unknown / idx_pos / rel
+    int child_begin, child_end, asm_begin, asm_end;
+    long long lu_off, cb_off, fw_off;   // fw_off < 0: the front is staged in shared memory
+    int cbv_off, pad;
+};
+struct FrontElem {            // one per circuit element, 40 B
+    double value, ac_amp;
+    int ip, im, ic, in_plane; // in_plane >= 0: per-lane value from input plane
+    int wave_col, state_idx;  // column of the per-step source table; trapezoidal state column
+};
+struct FrontTerm { int elem; int kind; };   // kind = SrcKind | (neg << 8)
+
+struct FrontParams {
+    const FrontDesc *fronts;
+    const int *list;          // fronts of this launch
+    const int *idx_pos, *idx_unknown, *rel, *child, *asm_ent, *asm_pos, *col_order;
+    const void *A;            // [lanes][a_stride]
+    void *LU, *CB, *FW, *CBV, *BP;   // per-lane stores
+    long long a_stride, lu_stride, cb_stride, fw_stride, cbv_stride;
+    int n;
+    int smem_elems;           // capacity of the dynamic shared memory in elements of T
+    int *status;
+    void *X;                  // result rows, point-major: X[lane * x_lane_stride + x_row_off + unknown]
+    long long x_lane_stride, x_row_off;
+};
+
+struct FrontStampParams {
+    const FrontElem *elems;
+    const FrontTerm *terms;
+    const int *term_ptr;      // CSR: matrix entry (stamp) or pivot position (rhs) -> terms
+    int count;                // entries / positions
+    int n_elems;
+    const double *IN;         // [n_inputs][L] lane-interleaved inputs
+    long long L;
+    double *EV;               // [lanes][n_elems]
+    void *OUT;                // A[lanes][count] or BP[lanes][count]
+    int input_freq;
+    double h_comp;
+    const double *Bstep;      // [rows][2][n_wave]
+    int n_wave, row;
+    const double *Xprev;      // previous result row (real): Xprev[lane * x_lane_stride + unknown]
+    long long x_lane_stride;
+    double *ST;               // [lanes][n_state] trapezoidal state
+    int n_state;
+};
+
+__global__ void krb_front_expand(const FrontStampParams p) {
+    const long long lane = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_elems) return;
+    const FrontElem el = p.elems[e];
+    p.EV[lane * p.n_elems + e] = el.in_plane >= 0 ? p.IN[(size_t)el.in_plane * p.L + lane] : el.value;
+}
+
+template <bool CPLX>
+__global__ void krb_front_stamp(const FrontStampParams p) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const long long lane = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.count) return;
+    const double *ev = p.EV + lane * p.n_elems;
+    T acc = S::zero();
+    const int t0 = p.term_ptr[e], t1 = p.term_ptr[e + 1];
+    for (int t = t0; t < t1; t++) {
+        const FrontTerm tm = p.terms[t];
+        const double v = ev[tm.elem];
+        T c;
+        switch (tm.kind & 0xff) {
+        case S_ONE: c = S::from_real(1.0); break;
+        case S_G: c = S::from_real(__ddiv_rn(1.0, v)); break;                       // stampable.rs:232
+        case S_VAL: c = S::from_real(v); break;
+        case S_VOH: c = S::from_real(__ddiv_rn(v, p.h_comp)); break;                // stampable.rs:449, 781
+        case S_JWV: {                                                                // (0, 2.0*PI*f*value)  stampable.rs:379-382
+            const double w = __dmul_rn(2.0 * 3.14159265358979323846264338327950288, p.IN[(size_t)p.input_freq * p.L + lane]);
+            c = S::mulj(S::from_real(__dmul_rn(w, v)));
+            break;
+        }
+        default: c = S::zero(); break;
+        }
+        if (tm.kind & 0x100) c = S::neg(c);
+        acc = (t == t0) ? c : S::add(acc, c);
+    }
+    reinterpret_cast<T *>(p.OUT)[lane * p.count + e] = acc;
+}
+
+template <bool CPLX>
+__global__ void krb_front_rhs(const FrontStampParams p) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const long long lane = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.count) return;
+    const double *ev = p.EV + lane * p.n_elems;
+    const double *xp = p.Xprev ? p.Xprev + lane * p.x_lane_stride : nullptr;
+    T acc = S::zero();
+    const int t0 = p.term_ptr[k], t1 = p.term_ptr[k + 1];
+    for (int t = t0; t < t1; t++) {
+        const FrontTerm tm = p.terms[t];
+        const FrontElem el = p.elems[tm.elem];
+        const double v = ev[tm.elem];
+        double c = 0.0;
+        switch (tm.kind & 0xff) {
+        case S_VAL: c = v; break;                                                    // stampable.rs:567, 1017
+        case S_ACAMP: c = el.ac_amp; break;                                          // :1031
+        case S_WAVE: c = p.Bstep[((size_t)p.row * 2) * p.n_wave + el.wave_col]; break;   // :1043-1048 (table built on the host)
+        case S_CAP_HIST: {                                                           // (C/h) * (v+_prev - v-_prev)   :480-493
+            const double coef = __ddiv_rn(v, p.h_comp);
+            double dv;
+            if (el.ip >= 0 && el.im >= 0) dv = __dsub_rn(xp[el.ip], xp[el.im]);
+            else if (el.ip >= 0) dv = xp[el.ip];
+            else dv = -xp[el.im];
+            c = __dmul_rn(coef, dv);
+            break;
+        }
+        case S_IND_HIST: c = __dmul_rn(__ddiv_rn(v, p.h_comp), xp[el.ic]); break;  // (L/h) * i_prev   :806-812
+        case S_CAP_IPREV: c = p.ST[lane * p.n_state + el.state_idx]; break;
+        case S_IND_VPREV:
+            if (el.ip >= 0 && el.im >= 0) c = __dsub_rn(xp[el.ip], xp[el.im]);
+            else if (el.ip >= 0) c = xp[el.ip];
+            else if (el.im >= 0) c = -xp[el.im];
+            break;
+        default: break;
+        }
+        if (tm.kind & 0x100) c = -c;
+        acc = (t == t0) ? S::from_real(c) : S::add(acc, S::from_real(c));
+    }
+    reinterpret_cast<T *>(p.OUT)[lane * p.count + k] = acc;
+}
+
+// i_n = (2C/h) * ((v+ - v-)_n - (v+ - v-)_{n-1}) - i_{n-1}
+struct FrontTrapParams {
+    const FrontElem *elems;
+    const int *state_elems;
+    int n_state, n_elems;
+    const double *EV;
+    double h_comp;
+    const double *Xnew, *Xprev;
+    long long x_lane_stride;
+    double *ST;
+};
+__global__ void krb_front_trap_state(const FrontTrapParams p) {
+    const long long lane = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.n_state) return;
+    const int e = p.state_elems[j];
+    const FrontElem el = p.elems[e];
+    const double g = __ddiv_rn(p.EV[lane * p.n_elems + e], p.h_comp);
+    const double *xn = p.Xnew + lane * p.x_lane_stride, *xo = p.Xprev + lane * p.x_lane_stride;
+    double vn, vp;
+    if (el.ip >= 0 && el.im >= 0) { vn = __dsub_rn(xn[el.ip], xn[el.im]); vp = __dsub_rn(xo[el.ip], xo[el.im]); }
+    else if (el.ip >= 0) { vn = xn[el.ip]; vp = xo[el.ip]; }
+    else if (el.im >= 0) { vn = -xn[el.im]; vp = -xo[el.im]; }
+    else return;
+    double *st = p.ST + lane * p.n_state + j;
+    *st = __dsub_rn(__dmul_rn(g, __dsub_rn(vn, vp)), *st);
+}
+
+// ---- (b) numeric factorisation of one front ---------------------------------------------------------------------
+// blockDim = (TX, TY); TX consecutive threads walk a column (unit stride), TY columns at a time.
+template <bool CPLX>
+__global__ void krb_front_factor(const FrontParams P) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    extern __shared__ __align__(16) unsigned char front_smem[];
+    T *sm = reinterpret_cast<T *>(front_smem);
+    const int f = P.list[blockIdx.x];
+    const long long lane = blockIdx.y;
+    const FrontDesc d = P.fronts[f];
+    const int p = d.p, q = d.q, m = p + q;
+    const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+    const int tid = ty * TX + tx, NT = TX * TY;
+    const bool in_smem = d.fw_off < 0;
+    T *F = in_smem ? sm : reinterpret_cast<T *>(P.FW) + lane * P.fw_stride + d.fw_off;
+    bool bad = false;
+
+    // ---- assemble: zero, stamped entries, children's contribution blocks (extend-add, children in ascending order) ----
+    for (int t = tid; t < m * m; t += NT) F[t] = S::zero();
+    __syncthreads();
+    {
+        const T *A = reinterpret_cast<const T *>(P.A) + lane * P.a_stride;
+        for (int t = d.asm_begin + tid; t < d.asm_end; t += NT) F[P.asm_pos[t]] = A[P.asm_ent[t]];
+    }
+    __syncthreads();
+    for (int ci = d.child_begin; ci < d.child_end; ci++) {
+        const FrontDesc c = P.fronts[P.child[ci]];
+        const int qc = c.q;
+        const T *CBc = reinterpret_cast<const T *>(P.CB) + lane * P.cb_stride + c.cb_off;
+        const int *rel = P.rel + c.idx_off;
+        for (int j = ty; j < qc; j += TY) {
+            const int rj = rel[j] * m;
+            for (int i = tx; i < qc; i += TX) { T *dst = F + rel[i] + rj; *dst = S::add(*dst, CBc[i + (size_t)qc * j]); }
+        }
+        __syncthreads();
+    }
+
+    if (in_smem) {
+        // ---- right-looking elimination on the staged block ----
+        for (int k = 0; k < p; k++) {
+            bool b1;
+            const T rp = S::rcp(F[k + m * k], b1);
+            bad |= b1;
+            for (int i = k + 1 + tid; i < m; i += NT) F[i + m * k] = S::mul(F[i + m * k], rp);
+            __syncthreads();
+            for (int i = k + 1 + tx; i < m; i += TX) {
+                const T l = F[i + m * k];
+                for (int j = k + 1 + ty; j < m; j += TY) F[i + m * j] = S::fnma(F[i + m * j], l, F[k + m * j]);
+            }
+            __syncthreads();
+        }
+    } else {
+        // ---- blocked elimination: panel (L columns + U rows) staged in shared memory, trailing block updated in place ----
+        int NB = P.smem_elems / (2 * m);
+        NB = NB > 16 ? 16 : NB;
+        for (int kb = 0; kb < p; kb += NB) {
+            const int nb = (p - kb) < NB ? (p - kb) : NB;
+            const int mk = m - kb, tw = mk - nb;
+            T *Lp = sm;                       // mk x nb, column-major
+            T *Up = sm + (size_t)mk * nb;     // nb x tw, Up[k + nb * j]
+            for (int k = ty; k < nb; k += TY)
+                for (int i = tx; i < mk; i += TX) Lp[i + mk * k] = F[(kb + i) + (size_t)m * (kb + k)];
+            for (int j = tid; j < tw; j += NT)
+                for (int k = 0; k < nb; k++) Up[k + nb * j] = F[(kb + k) + (size_t)m * (kb + nb + j)];
+            __syncthreads();
+            for (int k = 0; k < nb; k++) {
+                bool b1;
+                const T rp = S::rcp(Lp[k + mk * k], b1);
+                bad |= b1;
+                for (int i = k + 1 + tid; i < mk; i += NT) Lp[i + mk * k] = S::mul(Lp[i + mk * k], rp);
+                __syncthreads();
+                for (int j = k + 1 + ty; j < nb; j += TY) {                 // remaining panel columns
+                    const T u = Lp[k + mk * j];
+                    for (int i = k + 1 + tx; i < mk; i += TX) Lp[i + mk * j] = S::fnma(Lp[i + mk * j], Lp[i + mk * k], u);
+                }
+                for (int j = tid; j < tw; j += NT) {                        // remaining panel rows of U
+                    const T u = Up[k + nb * j];
+                    for (int r = k + 1; r < nb; r++) Up[r + nb * j] = S::fnma(Up[r + nb * j], Lp[r + mk * k], u);
+                }
+                __syncthreads();
+            }
+            // panels back to the front (final L and U values)
+            for (int k = ty; k < nb; k += TY)
+                for (int i = tx; i < mk; i += TX) F[(kb + i) + (size_t)m * (kb + k)] = Lp[i + mk * k];
+            for (int j = tid; j < tw; j += NT)
+                for (int k = 0; k < nb; k++) F[(kb + k) + (size_t)m * (kb + nb + j)] = Up[k + nb * j];
+            // trailing update, 4 x 2 register tiles
+            const int base = kb + nb;
+            for (int j0 = 0; j0 < tw; j0 += 2 * TY)
+                for (int i0 = 0; i0 < tw; i0 += 4 * TX) {
+                    T acc[4][2];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) { acc[a][0] = S::zero(); acc[a][1] = S::zero(); }
+                    int ii[4], jj[2];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) ii[a] = i0 + tx + a * TX;
+#pragma unroll
+                    for (int b = 0; b < 2; b++) jj[b] = j0 + ty + b * TY;
+                    for (int k = 0; k < nb; k++) {
+                        T l[4], u[2];
+#pragma unroll
+                        for (int a = 0; a < 4; a++) l[a] = ii[a] < tw ? Lp[nb + ii[a] + mk * k] : S::zero();
+#pragma unroll
+                        for (int b = 0; b < 2; b++) u[b] = jj[b] < tw ? Up[k + nb * jj[b]] : S::zero();
+#pragma unroll
+                        for (int a = 0; a < 4; a++) {
+                            acc[a][0] = S::fnma(acc[a][0], l[a], u[0]);
+                            acc[a][1] = S::fnma(acc[a][1], l[a], u[1]);
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < 2; b++)
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+                            if (ii[a] < tw && jj[b] < tw) {
+                                T *dst = F + (base + ii[a]) + (size_t)m * (base + jj[b]);
+                                *dst = S::add(*dst, acc[a][b]);
+                            }
+                }
+            __syncthreads();
+        }
+    }
+
+    // ---- write out: L block (m x p, reciprocal pivots on the diagonal), U12 (p x q), contribution block (q x q) ----
+    T *LUf = reinterpret_cast<T *>(P.LU) + lane * P.lu_stride + d.lu_off;
+    for (int k = ty; k < p; k += TY)
+        for (int i = tx; i < m; i += TX) {
+            T v = F[i + (size_t)m * k];
+            if (i == k) { bool b1; v = S::rcp(v, b1); }
+            LUf[i + (size_t)m * k] = v;
+        }
+    T *U12 = LUf + (size_t)m * p;
+    for (int j = ty; j < q; j += TY)
+        for (int k = tx; k < p; k += TX) U12[k + (size_t)p * j] = F[k + (size_t)m * (p + j)];
+    T *CBf = reinterpret_cast<T *>(P.CB) + lane * P.cb_stride + d.cb_off;
+    for (int j = ty; j < q; j += TY)
+        for (int i = tx; i < q; i += TX) CBf[i + (size_t)q * j] = F[(p + i) + (size_t)m * (p + j)];
+    if (bad && tid == 0 && P.status) atomicOr(P.status + lane, KRB_LANE_ZERO_PIVOT);
+}
+
+// ---- (c) forward substitution of one front: y_piv = L11^-1 (b_piv + children), contribution = rest - L21 y_piv -------
+template <bool CPLX>
+__global__ void krb_front_forward(const FrontParams P) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    extern __shared__ __align__(16) unsigned char front_smem[];
+    T *w = reinterpret_cast<T *>(front_smem);
+    const int f = P.list[blockIdx.x];
+    const long long lane = blockIdx.y;
+    const FrontDesc d = P.fronts[f];
+    const int p = d.p, q = d.q, m = p + q;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    T *BP = reinterpret_cast<T *>(P.BP) + lane * P.n;
+    T *CBV = reinterpret_cast<T *>(P.CBV) + lane * P.cbv_stride;
+    for (int i = tid; i < m; i += NT) w[i] = i < p ? BP[d.piv0 + i] : S::zero();
+    __syncthreads();
+    for (int ci = d.child_begin; ci < d.child_end; ci++) {
+        const FrontDesc c = P.fronts[P.child[ci]];
+        const int *rel = P.rel + c.idx_off;
+        for (int i = tid; i < c.q; i += NT) { T *dst = w + rel[i]; *dst = S::add(*dst, CBV[c.cbv_off + i]); }
+        __syncthreads();
+    }
+    const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
+    // unit-lower triangular solve on the pivot block
+    for (int k = 0; k + 1 < p; k++) {
+        const T wk = w[k];
+        for (int i = k + 1 + tid; i < p; i += NT) w[i] = S::fnma(w[i], L[i + (size_t)m * k], wk);
+        __syncthreads();
+    }
+    // rows below the pivot block: w[p + i] -= L21[i, :] . y
+    for (int i = p + tid; i < m; i += NT) {
+        T acc = w[i];
+        for (int k = 0; k < p; k++) acc = S::fnma(acc, L[i + (size_t)m * k], w[k]);
+        CBV[d.cbv_off + (i - p)] = acc;
+    }
+    for (int k = tid; k < p; k += NT) BP[d.piv0 + k] = w[k];
+}
+
+// ---- (c) backward substitution of one front: x_piv = U11^-1 (y_piv - U12 x_update) ----------------------------------
+template <bool CPLX>
+__global__ void krb_front_backward(const FrontParams P) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    extern __shared__ __align__(16) unsigned char front_smem[];
+    T *w = reinterpret_cast<T *>(front_smem);      // [0,p): running right-hand side, [p, m): x at the update positions
+    const int f = P.list[blockIdx.x];
+    const long long lane = blockIdx.y;
+    const FrontDesc d = P.fronts[f];
+    const int p = d.p, q = d.q, m = p + q;
+    T *xs = w + m;                                 // [p] solved pivots
+    T *red = xs + p;                               // [NT] partial sums
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const T *BP = reinterpret_cast<const T *>(P.BP) + lane * P.n;
+    T *X = reinterpret_cast<T *>(P.X) + lane * P.x_lane_stride + P.x_row_off;
+    for (int i = tid; i < m; i += NT) w[i] = i < p ? BP[d.piv0 + i] : X[P.idx_unknown[d.idx_off + (i - p)]];
+    __syncthreads();
+    const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
+    const T *U12 = L + (size_t)m * p;
+    if (q > 0) {
+        // w[k] -= sum_j U12[k, j] x_j : G thread groups split the columns, partial sums reduced in a fixed order
+        const int G = NT / p > 0 ? NT / p : 1;
+        for (int k0 = 0; k0 < p; k0 += NT) {
+            const int k = k0 + (tid % (p < NT ? p : NT)), g = tid / (p < NT ? p : NT);
+            T acc = S::zero();
+            const bool act = k < p && g < G;
+            if (act) for (int j = g; j < q; j += G) acc = S::fnma(acc, U12[k + (size_t)p * j], w[p + j]);
+            red[tid] = acc;
+            __syncthreads();
+            if (act && g == 0) {
+                T s = w[k];
+                const int stride = p < NT ? p : NT;
+                for (int gg = 0; gg < G; gg++) s = S::add(s, red[(k - k0) + gg * stride]);
+                w[k] = s;
+            }
+            __syncthreads();
+        }
+    }
+    for (int k = p - 1; k >= 0; k--) {
+        const T xk = S::mul(w[k], L[k + (size_t)m * k]);   // diagonal holds the reciprocal pivot
+        if (tid == 0) xs[k] = xk;
+        for (int i = tid; i < k; i += NT) w[i] = S::fnma(w[i], L[i + (size_t)m * k], xk);
+        __syncthreads();
+    }
+    for (int k = tid; k < p; k += NT) X[P.col_order[d.piv0 + k]] = xs[k];
+}
+
+}  // namespace krb

@@ -88,6 +88,7 @@ struct Program {
 };
 
 struct DeviceState;
+struct FrontDevice;
 
 // "chain" executor tables (chain_kernel.cuh): the permuted matrix is tridiagonal, so each pivot row is described by a
 // short run of stamp terms for its sub-diagonal, diagonal, super-diagonal and right-hand side.
@@ -103,6 +104,30 @@ struct ChainPlan {
     std::vector<uint32_t> runs;          // (count << 1) | is_fixed: consecutive rows of the same record type
     bool identity_order = false;         // unknown_of_row[k] == k: results can be delivered point-major straight from the kernel
 };
+
+// "front" executor tables (front_kernels.cuh): supernodal multifrontal LU on the symmetrised pattern of the permuted
+// matrix, for circuits whose factor is far too large for one thread per lane (meshes).  Everything is
+// in *position space*: position k is pivot k of the final elimination order (equation row_order[k], unknown col_order[k]).
+struct FrontPlan {
+    bool valid = false;
+    int n = 0, n_fronts = 0, n_levels = 0, max_m = 0, max_p = 0;
+    std::vector<int> row_order, col_order;
+    std::vector<int> piv0;                 // [n_fronts + 1] front f owns pivots [piv0[f], piv0[f+1])
+    std::vector<int> idx_ptr, idx;         // update index list of each front (positions, ascending); q = idx_ptr[f+1]-idx_ptr[f]
+    std::vector<int> parent;               // parent front or -1
+    std::vector<int> child_ptr, child;     // children, ascending
+    std::vector<int> rel_ptr, rel;         // per front (as a child): local index inside the parent's front of each update position
+    std::vector<int> level_ptr, level_fronts;   // fronts grouped by level (leaves first), largest front first inside a level
+    std::vector<int> asm_ptr, asm_ent, asm_pos; // stamped entries assembled into each front: CSC entry id, local r + m * c
+    std::vector<int64_t> lu_off;           // factor block of front f in the per-lane factor store: m x p column-major (L incl. the
+                                           // pivot block, reciprocal pivots on its diagonal), then the p x q block U12 column-major
+    std::vector<int64_t> cb_off;           // q x q contribution block in the per-lane workspace
+    std::vector<int64_t> cbv_off;          // q contribution vector (forward substitution)
+    int64_t lu_size = 0, cb_size = 0, cbv_size = 0;
+    int64_t nnz_lu = 0;                    // stored factor entries incl. explicit zeros of relaxed supernodes (= lu_size)
+    int64_t flops = 0;                     // factor + one solve, real flops of the real-valued problem
+};
+void build_front_plan(const Pattern &p, const std::vector<int> &match_row, const std::vector<int> &order, FrontPlan &fp);
 
 struct Plan {
     Circuit circuit;
@@ -128,6 +153,10 @@ struct Plan {
     ChainPlan chain;                    // filled when the structure allows the native chain executor
     bool use_chain = false;             // executor selected for krb_solve_* (chain.valid and not forced to the lane VM)
     int64_t vm_hbm_bytes_per_point = 0;
+    FrontPlan front;                    // filled when the front executor is selected
+    bool use_front = false;
+    FrontDevice *fdev = nullptr;        // device tables of the front executor (front_exec.cu)
+    std::vector<int> front_input_of_elem;   // element -> per-lane input plane or -1
 };
 
 // full pipeline; returns KRB_* status and fills `err`

@@ -30,6 +30,7 @@ const char *get_error() { return g_err.c_str(); }
 
 static std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
+void add_launches(long long k) { g_launches += k; }
 
 #define CUDA_TRY(expr)                                                                                         \
     do {                                                                                                       \
@@ -82,8 +83,13 @@ struct DeviceState {
 
 DeviceState *device_state_new() { return new DeviceState(); }
 
-static DeviceState *g_last_timed = nullptr;
+static double (*g_last_fn)(void *) = nullptr;
+static void *g_last_obj = nullptr;
 static double g_last_ms = -1.0;   // kept when the plan that owned the events is destroyed
+void set_last_timer(double (*fn)(void *), void *obj) { g_last_fn = fn; g_last_obj = obj; }
+void retire_last_timer(void *obj) {
+    if (g_last_obj == obj && g_last_fn) { g_last_ms = g_last_fn(obj); g_last_fn = nullptr; g_last_obj = nullptr; }
+}
 static double sum_event_ms(DeviceState *d) {
     if (!d || d->events_used == 0) return -1.0;
     double total = 0.0;
@@ -95,11 +101,12 @@ static double sum_event_ms(DeviceState *d) {
     }
     return total;
 }
-double last_kernel_ms() { return g_last_timed ? sum_event_ms(g_last_timed) : g_last_ms; }
+static double sum_event_ms_thunk(void *d) { return sum_event_ms((DeviceState *)d); }
+double last_kernel_ms() { return g_last_fn ? g_last_fn(g_last_obj) : g_last_ms; }
 
 void device_state_free(DeviceState *d) {
     if (!d) return;
-    if (g_last_timed == d) { g_last_ms = sum_event_ms(d); g_last_timed = nullptr; }
+    retire_last_timer(d);
     for (int i = 0; i < 3; i++) if (d->sec[i]) cudaFree(d->sec[i]);
     if (d->chain_rowinfo) cudaFree(d->chain_rowinfo);
     if (d->chain_stream) cudaFree(d->chain_stream);
@@ -212,6 +219,8 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if (device_count() <= 0) { set_error("no CUDA device: krets_b200 has no CPU fallback"); return KRB_ERR_NO_DEVICE; }
     Plan &P0 = *plan_first;
     Plan *PS = plan_steps;
+    if (P0.use_front) return run_front(plan_first, plan_steps, a);
+    if (PS && PS->use_front) { set_error("transient: plan_tran uses the front executor but plan_dc does not (analyse both with KRB_EXEC_STAGED)"); return KRB_ERR_UNSUPPORTED; }
     if (!P0.dev) P0.dev = device_state_new();
     if (PS && !PS->dev) PS->dev = device_state_new();
     DeviceState &D0 = *P0.dev;
@@ -284,7 +293,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if (PS) PS->dev->chunk_lanes = std::max(PS->dev->chunk_lanes, chunk);
 
     D0.events_used = 0;
-    g_last_timed = &D0;
+    set_last_timer(sum_event_ms_thunk, &D0);
     auto next_events = [&](cudaEvent_t &e0, cudaEvent_t &e1) -> int {
         if (D0.events_used == D0.events.size()) {
             cudaEvent_t x, y;

@@ -28,6 +28,13 @@ int device_count();
 long long launch_count();
 double last_kernel_ms();
 void device_state_free(DeviceState *d);
+void front_device_free(FrontDevice *d);
+void add_launches(long long k);
+// krb_last_kernel_ms(): the most recent call registers how its device time is read back (events are resolved lazily so that
+// device-memory calls never synchronise); an object that is destroyed first retires its timer and the value is kept
+void set_last_timer(double (*fn)(void *), void *obj);
+void retire_last_timer(void *obj);
+int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a);
 // plan_steps != nullptr: transient (plan_first = DC plan for row 0, plan_steps = TRAN plan for rows 1..)
 int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a);
 
