@@ -50,7 +50,7 @@ struct FrontDevice {
     std::vector<std::vector<FrontLaunch>> factor_launches, solve_launches;   // per level
     long long fw_size = 0;
     int smem_cap = 0;
-    FBuf IN, EV, A, LU, CB, FW, CBV, BP, ST, XS, status, Bstep;
+    FBuf IN, EV, A, LU, CB, FW, CBV, BP, ST, XS, status, Bstep, IPIV;
     std::vector<double> bstep_host;
     int bstep_rows = -1;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -76,7 +76,7 @@ void front_device_free(FrontDevice *d) {
     void *ptrs[] = {d->fronts, d->list, d->idx_unknown, d->rel, d->child, d->asm_ent, d->asm_pos, d->col_order, d->elems,
                     d->mat_terms, d->rhs_terms, d->mat_ptr, d->rhs_ptr, d->state_elems};
     for (void *p : ptrs) if (p) cudaFree(p);
-    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep};
+    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV};
     for (FBuf *b : bufs) b->release();
     for (auto &e : d->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete d;
@@ -135,7 +135,7 @@ static int upload_front(Plan &plan) {
             FrontLaunch L;
             L.first = i; L.count = j - i;
             L.block = c <= 2 ? dim3(32, 16) : c == 3 ? dim3(32, 4) : dim3(16, 4);
-            L.smem = c == 0 ? std::min<size_t>((size_t)D.smem_cap, (size_t)2 * m0 * 16 * ts) : (size_t)m0 * m0 * ts;
+            L.smem = c == 0 ? std::min<size_t>((size_t)D.smem_cap, ((size_t)2 * m0 * 16 + m0) * ts) : (size_t)m0 * m0 * ts;
             D.factor_launches[l].push_back(L);
             i = j;
         }
@@ -203,7 +203,7 @@ static int upload_front(Plan &plan) {
 }
 
 namespace {
-struct Bufs { void *A, *LU, *CB, *FW, *CBV, *BP; int *status; };
+struct Bufs { void *A, *LU, *CB, *FW, *CBV, *BP; int *status, *ipiv; };
 }
 
 static FrontParams make_params(const Plan &plan, const Bufs &b, void *X, long long x_lane_stride, long long x_row_off) {
@@ -214,7 +214,7 @@ static FrontParams make_params(const Plan &plan, const Bufs &b, void *X, long lo
     P.asm_ent = D.asm_ent; P.asm_pos = D.asm_pos; P.col_order = D.col_order;
     P.A = b.A; P.LU = b.LU; P.CB = b.CB; P.FW = b.FW; P.CBV = b.CBV; P.BP = b.BP;
     P.a_stride = plan.pattern.nnz; P.lu_stride = fp.lu_size; P.cb_stride = fp.cb_size; P.fw_stride = D.fw_size; P.cbv_stride = fp.cbv_size;
-    P.n = fp.n; P.status = b.status;
+    P.n = fp.n; P.status = b.status; P.IPIV = b.ipiv;
     P.X = X; P.x_lane_stride = x_lane_stride; P.x_row_off = x_row_off;
     return P;
 }
@@ -307,7 +307,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const size_t cbv_e = (size_t)mx([](const Plan &p) { return p.front.cbv_size; });
     const size_t fw_e = (size_t)mx([](const Plan &p) { return p.fdev->fw_size; });
     const size_t a_e = (size_t)mx([](const Plan &p) { return (long long)p.pattern.nnz; });
-    const size_t per_lane = (lu_e + cb_e + cbv_e + fw_e + a_e + (size_t)n) * ts + (size_t)n_elems * 8 + (size_t)P0.n_inputs * 8 + (size_t)n_state * 8 +
+    const size_t per_lane = (lu_e + cb_e + cbv_e + fw_e + a_e + (size_t)n) * ts + (size_t)n_elems * 8 + (size_t)P0.n_inputs * 8 + (size_t)n_state * 8 + (size_t)n * 4 +
                             (out_dev ? 0 : (size_t)rows * n * ts) + 64;
     long long chunk = a.chunk_lanes > 0 ? a.chunk_lanes : 1024;
     chunk = std::min<long long>(chunk, a.lanes);
@@ -330,6 +330,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if ((rc = D.BP.ensure((size_t)n * chunk * ts))) return rc;
     if ((rc = D.ST.ensure(std::max<size_t>((size_t)n_state, 1) * chunk * 8))) return rc;
     if ((rc = D.status.ensure((size_t)chunk * 4))) return rc;
+    if ((rc = D.IPIV.ensure((size_t)n * chunk * 4))) return rc;
     if (!out_dev && (rc = D.XS.ensure((size_t)rows * n * chunk * ts))) return rc;
 
     D.events_used = 0;
@@ -363,7 +364,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         D.events_used++;
         CUDA_TRY(cudaEventRecord(e0, st));
 
-        Bufs bufs{D.A.p, D.LU.p, D.CB.p, D.FW.p, D.CBV.p, D.BP.p, (int *)D.status.p};
+        Bufs bufs{D.A.p, D.LU.p, D.CB.p, D.FW.p, D.CBV.p, D.BP.p, (int *)D.status.p, (int *)D.IPIV.p};
         auto stamp_params = [&](const Plan &pl) {
             const FrontDevice &DD = *pl.fdev;
             FrontStampParams s{};

@@ -47,6 +47,7 @@ struct FrontParams {
     int n;
     int smem_elems;           // capacity of the dynamic shared memory in elements of T
     int *status;
+    int *IPIV;                // [lanes][n] row chosen for pivot k inside its front (local row index; == k when no swap)
     void *X;                  // result rows, point-major: X[lane * x_lane_stride + x_row_off + unknown]
     long long x_lane_stride, x_row_off;
 };
@@ -183,6 +184,37 @@ __global__ void krb_front_trap_state(const FrontTrapParams p) {
     *st = __dsub_rn(__dmul_rn(g, __dsub_rn(vn, vp)), *st);
 }
 
+// Threshold partial pivoting inside the fully-summed block of a front (rows k..p-1 of column k): the static pivot is kept
+// unless another fully-summed row is more than 8x larger (or the static pivot is zero / non-finite).  Per lane, like the
+// reference's faer LU picks pivots per factorisation; rows outside the front are never touched, so the symbolic plan holds.
+template <bool CPLX> struct FrontAbs;
+template <> struct FrontAbs<false> { static __device__ __forceinline__ double mag(double v) { return fabs(v); } static constexpr double THRESH = 8.0; };
+template <> struct FrontAbs<true> { static __device__ __forceinline__ double mag(double2 v) { return fma(v.x, v.x, v.y * v.y); } static constexpr double THRESH = 64.0; };
+
+// warp 0 scans col[k+1 .. p) (unit stride) and publishes the chosen row in *s_ip
+template <bool CPLX, typename T>
+__device__ __forceinline__ void front_pivot_search(const T *col, int k, int p, int tid, int *s_ip) {
+    if (tid < 32) {
+        double best = -1.0;
+        int bi = k;
+        for (int i = k + 1 + tid; i < p; i += 32) {
+            const double a = FrontAbs<CPLX>::mag(col[i]);
+            if (a > best) { best = a; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (tid == 0) {
+            const double d = FrontAbs<CPLX>::mag(col[k]);
+            const bool keep = isfinite(d) && d > 0.0 && !(best > FrontAbs<CPLX>::THRESH * d);
+            *s_ip = keep ? k : bi;
+        }
+    }
+}
+
 // ---- (b) numeric factorisation of one front ---------------------------------------------------------------------
 // blockDim = (TX, TY); TX consecutive threads walk a column (unit stride), TY columns at a time.
 template <bool CPLX>
@@ -200,6 +232,9 @@ __global__ void krb_front_factor(const FrontParams P) {
     const bool in_smem = d.fw_off < 0;
     T *F = in_smem ? sm : reinterpret_cast<T *>(P.FW) + lane * P.fw_stride + d.fw_off;
     bool bad = false;
+    __shared__ int s_ip;
+    __shared__ int s_pv[16];
+    int *ipiv = P.IPIV + lane * P.n + d.piv0;
 
     // ---- assemble: zero, stamped entries, children's contribution blocks (extend-add, children in ascending order) ----
     for (int t = tid; t < m * m; t += NT) F[t] = S::zero();
@@ -224,6 +259,16 @@ __global__ void krb_front_factor(const FrontParams P) {
     if (in_smem) {
         // ---- right-looking elimination on the staged block ----
         for (int k = 0; k < p; k++) {
+            if (k + 1 < p) {
+                front_pivot_search<CPLX>(F + m * k, k, p, tid, &s_ip);
+                __syncthreads();
+                const int ip = s_ip;
+                if (ip != k) {
+                    for (int j = tid; j < m; j += NT) { const T t = F[k + m * j]; F[k + m * j] = F[ip + m * j]; F[ip + m * j] = t; }
+                }
+                if (tid == 0) ipiv[k] = ip;
+                __syncthreads();
+            } else if (tid == 0) ipiv[k] = k;
             bool b1;
             const T rp = S::rcp(F[k + m * k], b1);
             bad |= b1;
@@ -237,19 +282,37 @@ __global__ void krb_front_factor(const FrontParams P) {
         }
     } else {
         // ---- blocked elimination: panel (L columns + U rows) staged in shared memory, trailing block updated in place ----
-        int NB = P.smem_elems / (2 * m);
+        int NB = (P.smem_elems - m) / (2 * m);
         NB = NB > 16 ? 16 : NB;
         for (int kb = 0; kb < p; kb += NB) {
             const int nb = (p - kb) < NB ? (p - kb) : NB;
             const int mk = m - kb, tw = mk - nb;
             T *Lp = sm;                       // mk x nb, column-major
-            T *Up = sm + (size_t)mk * nb;     // nb x tw, Up[k + nb * j]
+            const int ldu = nb | 1;           // odd leading dimension: one thread per column without bank conflicts
+            T *Up = sm + (size_t)mk * nb;     // nb x tw, Up[k + ldu * j]
             for (int k = ty; k < nb; k += TY)
                 for (int i = tx; i < mk; i += TX) Lp[i + mk * k] = F[(kb + i) + (size_t)m * (kb + k)];
             for (int j = tid; j < tw; j += NT)
-                for (int k = 0; k < nb; k++) Up[k + nb * j] = F[(kb + k) + (size_t)m * (kb + nb + j)];
+                for (int k = 0; k < nb; k++) Up[k + ldu * j] = F[(kb + k) + (size_t)m * (kb + nb + j)];
             __syncthreads();
+            // panel factorisation (LAPACK getrf order): interchanges are applied to the panel columns and to the finished L
+            // columns on the left at once; the columns right of the panel get them afterwards, before their U rows are formed
             for (int k = 0; k < nb; k++) {
+                int ip = k;
+                if (kb + k + 1 < p) {
+                    front_pivot_search<CPLX>(Lp + mk * k, k, p - kb, tid, &s_ip);
+                    __syncthreads();
+                    ip = s_ip;
+                    if (ip != k) {
+                        for (int j = tid; j < nb; j += NT) { const T t = Lp[k + mk * j]; Lp[k + mk * j] = Lp[ip + mk * j]; Lp[ip + mk * j] = t; }
+                        for (int j = tid; j < kb; j += NT) {
+                            T *a = F + (kb + k) + (size_t)m * j, *b = F + (kb + ip) + (size_t)m * j;
+                            const T t = *a; *a = *b; *b = t;
+                        }
+                    }
+                }
+                if (tid == 0) { ipiv[kb + k] = ip + kb; s_pv[k] = ip; }
+                __syncthreads();
                 bool b1;
                 const T rp = S::rcp(Lp[k + mk * k], b1);
                 bad |= b1;
@@ -259,17 +322,29 @@ __global__ void krb_front_factor(const FrontParams P) {
                     const T u = Lp[k + mk * j];
                     for (int i = k + 1 + tx; i < mk; i += TX) Lp[i + mk * j] = S::fnma(Lp[i + mk * j], Lp[i + mk * k], u);
                 }
-                for (int j = tid; j < tw; j += NT) {                        // remaining panel rows of U
-                    const T u = Up[k + nb * j];
-                    for (int r = k + 1; r < nb; r++) Up[r + nb * j] = S::fnma(Up[r + nb * j], Lp[r + mk * k], u);
-                }
                 __syncthreads();
+            }
+            // columns right of the panel, one thread per column: interchanges in order, then U12 = L11^-1 A12 (unit lower)
+            for (int j = tid; j < tw; j += NT) {
+                T *uc = Up + ldu * j;
+                for (int k = 0; k < nb; k++) {
+                    const int ip = s_pv[k];
+                    if (ip != k) {
+                        T *other = ip < nb ? uc + ip : F + (kb + ip) + (size_t)m * (kb + nb + j);
+                        const T t = uc[k]; uc[k] = *other; *other = t;
+                    }
+                }
+                for (int k = 0; k < nb; k++) {
+                    const T u = uc[k];
+                    for (int r = k + 1; r < nb; r++) uc[r] = S::fnma(uc[r], Lp[r + mk * k], u);
+                }
             }
             // panels back to the front (final L and U values)
             for (int k = ty; k < nb; k += TY)
                 for (int i = tx; i < mk; i += TX) F[(kb + i) + (size_t)m * (kb + k)] = Lp[i + mk * k];
             for (int j = tid; j < tw; j += NT)
-                for (int k = 0; k < nb; k++) F[(kb + k) + (size_t)m * (kb + nb + j)] = Up[k + nb * j];
+                for (int k = 0; k < nb; k++) F[(kb + k) + (size_t)m * (kb + nb + j)] = Up[k + ldu * j];
+            __syncthreads();
             // trailing update, 4 x 2 register tiles
             const int base = kb + nb;
             for (int j0 = 0; j0 < tw; j0 += 2 * TY)
@@ -287,7 +362,7 @@ __global__ void krb_front_factor(const FrontParams P) {
 #pragma unroll
                         for (int a = 0; a < 4; a++) l[a] = ii[a] < tw ? Lp[nb + ii[a] + mk * k] : S::zero();
 #pragma unroll
-                        for (int b = 0; b < 2; b++) u[b] = jj[b] < tw ? Up[k + nb * jj[b]] : S::zero();
+                        for (int b = 0; b < 2; b++) u[b] = jj[b] < tw ? Up[k + ldu * jj[b]] : S::zero();
 #pragma unroll
                         for (int a = 0; a < 4; a++) {
                             acc[a][0] = S::fnma(acc[a][0], l[a], u[0]);
@@ -345,6 +420,16 @@ __global__ void krb_front_forward(const FrontParams P) {
         const int *rel = P.rel + c.idx_off;
         for (int i = tid; i < c.q; i += NT) { T *dst = w + rel[i]; *dst = S::add(*dst, CBV[c.cbv_off + i]); }
         __syncthreads();
+    }
+    {   // the lane's row interchanges inside the pivot block (usually none)
+        const int *ipiv = P.IPIV + lane * P.n + d.piv0;
+        int moved = 0;
+        for (int k = tid; k < p; k += NT) moved |= (ipiv[k] != k);
+        if (__syncthreads_or(moved)) {
+            if (tid == 0)
+                for (int k = 0; k < p; k++) { const int ip = ipiv[k]; if (ip != k) { const T t = w[k]; w[k] = w[ip]; w[ip] = t; } }
+            __syncthreads();
+        }
     }
     const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
     // unit-lower triangular solve on the pivot block

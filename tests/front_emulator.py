@@ -32,6 +32,13 @@ def factor_and_solve(ft: dict, row_order, col_order, A_vals, b, dtype=np.float64
             F[np.ix_(r, r)] += CB[c]
             w[r] += CBV[c]
         for k in range(p):
+            if k + 1 < p:                       # threshold partial pivoting inside the fully-summed block (front_pivot_search)
+                cand = np.abs(F[k + 1:p, k])
+                i = k + 1 + int(np.argmax(cand))
+                d = abs(F[k, k])
+                if not (np.isfinite(d) and d > 0.0 and not (cand.max() > 8.0 * d)):
+                    F[[k, i], :] = F[[i, k], :]
+                    w[[k, i]] = w[[i, k]]
             F[k + 1:, k] /= F[k, k]
             F[k + 1:, k + 1:] -= np.outer(F[k + 1:, k], F[k, k + 1:])
         Lblk[f], U12[f], CB[f] = F[:, :p].copy(), F[:p, p:].copy(), F[p:, p:].copy()

@@ -59,6 +59,22 @@ def test_front_plan_emulated(oracle, shape, transient, mode):
     assert plan.info.nnz_lu == ft["lu_size"] or plan.info.nnz_lu <= ft["lu_size"]
 
 
+def test_front_plan_nominal_dc_needs_in_front_pivoting(oracle):
+    """DC mesh with identical element values: inductors are shorts (no branch diagonal, stampable.rs:688-701) and a static
+    pivot cancels exactly; the per-lane threshold pivoting inside the fully-summed block recovers full accuracy."""
+    text = netgen.rlc_mesh(40, 40, transient=True)
+    circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    plan = kb.Plan(circuit, api.MODE_DC, executor=api.EXEC_STAGED)
+    ocp, ori, vals = oc.stamp_matrix("dc", 0.0)
+    ro, co = plan.pivot_order()
+    b = np.zeros(circuit.n)
+    b[circuit.index_map["I(I1)"]] = 1e-3
+    with np.errstate(all="ignore"):
+        x = fe.factor_and_solve(plan.front_tables(), ro, co, vals, b)
+    xr = spl.splu(sp.csc_matrix((vals, ori, ocp), shape=(circuit.n, circuit.n))).solve(b)
+    assert np.max(np.abs(x - xr)) <= 1e-10 * np.max(np.abs(xr))
+
+
 def test_front_executor_selection():
     small = kb.parse_circuit_description(netgen.rlc_mesh(4, 4))
     assert kb.Plan(small, api.MODE_AC).info.executor == 0                      # small fill: per-lane program

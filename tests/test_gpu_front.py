@@ -114,6 +114,25 @@ def test_front_blocked_path_matches(oracle, monkeypatch):
     assert_close(out[0], oc.solve_op(), what="blocked path OP")
 
 
+@pytest.mark.parametrize("smem_m", [None, 24])
+def test_front_nominal_dc_pivots_inside_fronts(oracle, monkeypatch, smem_m):
+    """Identical element values + inductor shorts: a static pivot cancels exactly (CPU tier shows it); the kernels' per-lane
+    threshold pivoting inside the fully-summed block must recover it, on the shared-memory and on the blocked path."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    if smem_m:
+        monkeypatch.setenv("KRB_FRONT_SMEM_M", str(smem_m))
+    text = netgen.rlc_mesh(40, 40, transient=True)
+    circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    out, status = kb.Plan(circuit, api.MODE_DC, executor=api.EXEC_STAGED).solve_op(1)
+    assert not status.any()
+    colptr, rowidx, v = oc.stamp_matrix("dc", 0.0)
+    A = sp.csc_matrix((v, rowidx, colptr), shape=(circuit.n, circuit.n))
+    b = np.zeros(circuit.n)
+    b[circuit.index_map["I(I1)"]] = 1e-3
+    assert_close(out[0], spl.splu(A).solve(b), rtol=1e-8, what="40x40 nominal DC vs SuperLU")
+
+
 def test_front_zero_pivot_is_reported():
     text = netgen.rlc_mesh(5, 6, transient=True)
     circuit = kb.parse_circuit_description(text)
