@@ -97,7 +97,9 @@ enum { KRB_INTEGRATOR_BE_KRETS = 0,   /* backward Euler incl. the reference's on
        KRB_INTEGRATOR_BE = 2 };       /* backward Euler with sources evaluated at t_n (no lag; not reference behaviour) */
 enum { KRB_EXEC_FUSED = 0,            /* default: stamp+factor+solve fused per lane; the executor is chosen from the plan's
                                          structure (native chain kernel for tridiagonal-after-permutation plans, lane VM otherwise) */
-       KRB_EXEC_STAGED = 1,           /* stamp, factor, solve as separate launches through HBM value arrays (not implemented yet) */
+       KRB_EXEC_STAGED = 1,           /* front executor: stamp, supernodal multifrontal factor and level-scheduled solves as separate
+                                         launches over per-lane factor stores in HBM (meshes; linear circuits).  Also chosen by
+                                         KRB_EXEC_FUSED when the fill is too large for a per-lane program */
        KRB_EXEC_LANE_VM = 2 };        /* force the general lane-program interpreter */
 
 typedef struct krb_plan_opts {
@@ -106,7 +108,8 @@ typedef struct krb_plan_opts {
     int32_t integrator;               /* KRB_INTEGRATOR_* (TRAN) */
     int32_t scratch_slots;            /* per-lane on-chip scratch capacity (0 = default) */
     double time_step;                 /* h (TRAN) */
-    double nominal_frequency;         /* AC: frequency at which the static pivot plan is chosen (0 = 1 kHz) */
+    double nominal_frequency;         /* AC: frequency at which the static pivot plan is chosen (0 = 1 kHz); for the front
+                                         executor use the LOWEST frequency of the sweep (smallest |jwL| branch diagonals) */
     int32_t sweep_element;            /* DC: element ordinal whose value is the per-lane sweep value, or -1 */
     int32_t n_varied;                 /* Monte-Carlo: number of elements whose value is a per-lane input */
     const int32_t *varied_elements;   /* [n_varied] element ordinals (R/C/L/V/I) */
@@ -135,7 +138,7 @@ typedef struct krb_plan_info {
     int64_t flops_per_point;  /* real flops of factor+solve for one lane (complex counted x4/x2) */
     int64_t hbm_bytes_per_point;   /* bytes the lane program itself moves through HBM per point (model) */
     int64_t alg_bytes_per_point;   /* P + s*(4*nnz_lu + 3*n) */
-    int32_t executor;              /* 0 lane VM, 1 chain kernel */
+    int32_t executor;              /* 0 lane VM, 1 chain kernel, 2 front executor */
     int32_t reserved;
 } krb_plan_info;
 

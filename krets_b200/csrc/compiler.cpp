@@ -10,6 +10,7 @@
 // (farthest-next-use) eviction, rematerialises constants/inputs instead of spilling them, and spills the rest to
 // HBM value planes in production order (so the fused back substitution re-reads them as a reverse stream).
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -646,6 +647,13 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
     if (!use_front) {
         symbolic_lu(plan.pattern, match_row, order, plan.sym);
         if (plan.opts.exec == KRB_EXEC_FUSED && !banded && !c.nonlinear && plan.sym.flops > 250000) use_front = true;
+    }
+    if (use_front) {
+        // the fronts pivot dynamically, so prefer diagonal static pivots (structural symmetry => far less fill), then reorder
+        double bonus = 6.9;   // ln(1e3): growth per pivot stays <= 1e3 at the nominal point (AC: plan at the lowest frequency of the sweep)
+        if (const char *e = getenv("KRB_FRONT_DIAG_BONUS")) bonus = atof(e);
+        if (!weighted_matching(plan.pattern, mag, match_row, bonus)) { err = "matrix is structurally singular"; return KRB_ERR_DECOMPOSITION_FAILED; }
+        minimum_degree(plan.pattern, match_row, order);
     }
     const Symbolic &S = plan.sym;
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -37,7 +38,7 @@ struct FBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
-struct FrontLaunch { int first, count; dim3 block; size_t smem; };
+struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int slot_elems; };
 }  // namespace
 
 struct FrontDevice {
@@ -47,10 +48,12 @@ struct FrontDevice {
     FrontElem *elems = nullptr;
     FrontTerm *mat_terms = nullptr, *rhs_terms = nullptr;
     int *mat_ptr = nullptr, *rhs_ptr = nullptr, *state_elems = nullptr;
+    int *res_ptr = nullptr, *res_ent = nullptr, *res_col = nullptr;
+    int refine_steps = 0;
     std::vector<std::vector<FrontLaunch>> factor_launches, solve_launches;   // per level
     long long fw_size = 0;
     int smem_cap = 0;
-    FBuf IN, EV, A, LU, CB, FW, CBV, BP, ST, XS, status, Bstep, IPIV;
+    FBuf IN, EV, A, LU, CB, FW, CBV, BP, ST, XS, status, Bstep, IPIV, DX;
     std::vector<double> bstep_host;
     int bstep_rows = -1;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -74,9 +77,9 @@ void front_device_free(FrontDevice *d) {
     if (!d) return;
     retire_last_timer(d);
     void *ptrs[] = {d->fronts, d->list, d->idx_unknown, d->rel, d->child, d->asm_ent, d->asm_pos, d->col_order, d->elems,
-                    d->mat_terms, d->rhs_terms, d->mat_ptr, d->rhs_ptr, d->state_elems};
+                    d->mat_terms, d->rhs_terms, d->mat_ptr, d->rhs_ptr, d->state_elems, d->res_ptr, d->res_ent, d->res_col};
     for (void *p : ptrs) if (p) cudaFree(p);
-    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV};
+    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV, &d->DX};
     for (FBuf *b : bufs) b->release();
     for (auto &e : d->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete d;
@@ -100,7 +103,7 @@ static int upload_front(Plan &plan) {
     CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     D.smem_cap = std::min(optin, 224 * 1024);
     int m_smem = 1;
-    while ((size_t)(m_smem + 1) * (m_smem + 1) * ts <= (size_t)D.smem_cap) m_smem++;
+    while ((size_t)(m_smem + 1) * ((m_smem + 1) | 1) * ts <= (size_t)D.smem_cap) m_smem++;
     if (const char *e = getenv("KRB_FRONT_SMEM_M")) m_smem = std::max(1, std::min(m_smem, atoi(e)));
     const int nf = fp.n_fronts;
     std::vector<FrontDesc> desc(nf);
@@ -134,8 +137,9 @@ static int upload_front(Plan &plan) {
             while (j < e && fclass(msize(fp.level_fronts[j])) == c) j++;
             FrontLaunch L;
             L.first = i; L.count = j - i;
-            L.block = c <= 2 ? dim3(32, 16) : c == 3 ? dim3(32, 4) : dim3(16, 4);
-            L.smem = c == 0 ? std::min<size_t>((size_t)D.smem_cap, ((size_t)2 * m0 * 16 + m0) * ts) : (size_t)m0 * m0 * ts;
+            L.block = c <= 1 ? dim3(32, 16) : c == 2 ? dim3(16, 16) : c == 3 ? dim3(16, 8) : dim3(8, 8);
+            L.smem = c == 0 ? std::min<size_t>((size_t)D.smem_cap, ((size_t)2 * m0 * 16 + m0) * ts) : (size_t)m0 * (m0 | 1) * ts;
+            L.warp = false; L.slot_elems = 0;
             D.factor_launches[l].push_back(L);
             i = j;
         }
@@ -147,8 +151,10 @@ static int upload_front(Plan &plan) {
             FrontLaunch L;
             L.first = i; L.count = j - i;
             const int nt = c == 0 ? 256 : c == 1 ? 128 : 32;
-            L.block = dim3(nt);
-            L.smem = ((size_t)2 * m0 + nt) * ts;
+            L.warp = (c == 2);
+            L.slot_elems = m0 + nt;
+            L.block = L.warp ? dim3(32, 8) : dim3(nt);
+            L.smem = (size_t)L.slot_elems * ts * (L.warp ? 8 : 1);
             D.solve_launches[l].push_back(L);
             i = j;
         }
@@ -192,12 +198,30 @@ static int upload_front(Plan &plan) {
     if ((rc = up(mp, &D.mat_ptr))) return rc;
     if ((rc = up(rp, &D.rhs_ptr))) return rc;
     if ((rc = up(plan.state_elems, &D.state_elems))) return rc;
+    {   // rows of the permuted matrix for the refinement residual
+        const Pattern &pt = plan.pattern;
+        std::vector<int> pos_of_row(pt.n), rptr(pt.n + 1, 0), rent(pt.nnz), rcol(pt.nnz);
+        for (int k = 0; k < pt.n; k++) pos_of_row[fp.row_order[k]] = k;
+        for (int e = 0; e < pt.nnz; e++) rptr[pos_of_row[pt.rowidx[e]] + 1]++;
+        for (int k = 0; k < pt.n; k++) rptr[k + 1] += rptr[k];
+        std::vector<int> fill(rptr.begin(), rptr.end() - 1);
+        for (int col = 0; col < pt.n; col++)
+            for (int e = pt.colptr[col]; e < pt.colptr[col + 1]; e++) { const int t = fill[pos_of_row[pt.rowidx[e]]]++; rent[t] = e; rcol[t] = col; }
+        if ((rc = up(rptr, &D.res_ptr))) return rc;
+        if ((rc = up(rent, &D.res_ent))) return rc;
+        if ((rc = up(rcol, &D.res_col))) return rc;
+    }
+    // AC plans pick static pivots at one nominal frequency but serve lanes decades away from it: two refinement steps on the
+    // stamped matrix restore full accuracy there (each costs one residual + one pair of triangular solves).  Transient and DC
+    // plans are solved at the point they were planned for.
+    D.refine_steps = plan.mode == KRB_MODE_AC ? 2 : 0;
+    if (const char *e = getenv("KRB_FRONT_REFINE")) D.refine_steps = std::max(0, atoi(e));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
-    CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
-    CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
-    CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
-    CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     D.uploaded = true;
     return KRB_OK;
 }
@@ -227,6 +251,7 @@ static int front_factor(const Plan &plan, FrontParams P, long long lanes, cudaSt
             FrontParams Q = P;
             Q.list = D.list + L.first;
             Q.smem_elems = (int)(L.smem / ts);
+            Q.lanes = lanes;
             dim3 grid((unsigned)L.count, (unsigned)lanes);
             if (plan.is_complex) krb_front_factor<true><<<grid, L.block, L.smem, st>>>(Q);
             else krb_front_factor<false><<<grid, L.block, L.smem, st>>>(Q);
@@ -236,6 +261,24 @@ static int front_factor(const Plan &plan, FrontParams P, long long lanes, cudaSt
     return KRB_OK;
 }
 
+template <bool FWD>
+static void launch_solve(const Plan &plan, const FrontLaunch &L, FrontParams Q, long long lanes, cudaStream_t st) {
+    const size_t ts = plan.is_complex ? 16 : 8;
+    Q.lanes = lanes;
+    if (L.warp) {
+        Q.smem_elems = L.slot_elems;
+        dim3 grid((unsigned)L.count, (unsigned)((lanes + L.block.y - 1) / L.block.y));
+        if (plan.is_complex) { if (FWD) krb_front_forward<true, true><<<grid, L.block, L.smem, st>>>(Q); else krb_front_backward<true, true><<<grid, L.block, L.smem, st>>>(Q); }
+        else { if (FWD) krb_front_forward<false, true><<<grid, L.block, L.smem, st>>>(Q); else krb_front_backward<false, true><<<grid, L.block, L.smem, st>>>(Q); }
+    } else {
+        Q.smem_elems = (int)(L.smem / ts);
+        dim3 grid((unsigned)L.count, (unsigned)lanes);
+        if (plan.is_complex) { if (FWD) krb_front_forward<true, false><<<grid, L.block, L.smem, st>>>(Q); else krb_front_backward<true, false><<<grid, L.block, L.smem, st>>>(Q); }
+        else { if (FWD) krb_front_forward<false, false><<<grid, L.block, L.smem, st>>>(Q); else krb_front_backward<false, false><<<grid, L.block, L.smem, st>>>(Q); }
+    }
+    add_launches(1);
+}
+
 static int front_solve(const Plan &plan, FrontParams P, long long lanes, cudaStream_t st) {
     const FrontDevice &D = *plan.fdev;
     const int nl = (int)D.solve_launches.size();
@@ -243,19 +286,13 @@ static int front_solve(const Plan &plan, FrontParams P, long long lanes, cudaStr
         for (const FrontLaunch &L : D.solve_launches[l]) {
             FrontParams Q = P;
             Q.list = D.list + L.first;
-            dim3 grid((unsigned)L.count, (unsigned)lanes);
-            if (plan.is_complex) krb_front_forward<true><<<grid, L.block, L.smem, st>>>(Q);
-            else krb_front_forward<false><<<grid, L.block, L.smem, st>>>(Q);
-            add_launches(1);
+            launch_solve<true>(plan, L, Q, lanes, st);
         }
     for (int l = nl - 1; l >= 0; l--)
         for (const FrontLaunch &L : D.solve_launches[l]) {
             FrontParams Q = P;
             Q.list = D.list + L.first;
-            dim3 grid((unsigned)L.count, (unsigned)lanes);
-            if (plan.is_complex) krb_front_backward<true><<<grid, L.block, L.smem, st>>>(Q);
-            else krb_front_backward<false><<<grid, L.block, L.smem, st>>>(Q);
-            add_launches(1);
+            launch_solve<false>(plan, L, Q, lanes, st);
         }
     CUDA_TRY(cudaGetLastError());
     return KRB_OK;
@@ -307,7 +344,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const size_t cbv_e = (size_t)mx([](const Plan &p) { return p.front.cbv_size; });
     const size_t fw_e = (size_t)mx([](const Plan &p) { return p.fdev->fw_size; });
     const size_t a_e = (size_t)mx([](const Plan &p) { return (long long)p.pattern.nnz; });
-    const size_t per_lane = (lu_e + cb_e + cbv_e + fw_e + a_e + (size_t)n) * ts + (size_t)n_elems * 8 + (size_t)P0.n_inputs * 8 + (size_t)n_state * 8 + (size_t)n * 4 +
+    const size_t per_lane = (lu_e + cb_e + cbv_e + fw_e + a_e + (size_t)n) * ts + (size_t)n_elems * 8 + (size_t)P0.n_inputs * 8 + (size_t)n_state * 8 + (size_t)n * 4 + (size_t)n * ts +
                             (out_dev ? 0 : (size_t)rows * n * ts) + 64;
     long long chunk = a.chunk_lanes > 0 ? a.chunk_lanes : 1024;
     chunk = std::min<long long>(chunk, a.lanes);
@@ -331,6 +368,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if ((rc = D.ST.ensure(std::max<size_t>((size_t)n_state, 1) * chunk * 8))) return rc;
     if ((rc = D.status.ensure((size_t)chunk * 4))) return rc;
     if ((rc = D.IPIV.ensure((size_t)n * chunk * 4))) return rc;
+    if ((P0.fdev->refine_steps > 0 || (PS && PS->fdev->refine_steps > 0)) && (rc = D.DX.ensure((size_t)n * chunk * ts))) return rc;
     if (!out_dev && (rc = D.XS.ensure((size_t)rows * n * chunk * ts))) return rc;
 
     D.events_used = 0;
@@ -339,16 +377,23 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     for (long long lane0 = 0; lane0 < a.lanes; lane0 += chunk) {
         const long long lanes = std::min<long long>(chunk, a.lanes - lane0);
         double *IN = (double *)D.IN.p;
-        for (int k = 0; k < P0.n_inputs; k++) {
-            const double *src = nullptr;
-            if (k == P0.input_sweep || k == P0.input_freq) src = a.lane_param;
-            else {
-                int vk = -1;
-                for (size_t q = 0; q < P0.input_of_varied.size(); q++) if (P0.input_of_varied[q] == k) { vk = (int)q; break; }
-                if (vk < 0 || !a.varied_values) { set_error("missing per-lane values for a varied element"); return KRB_ERR_INVALID_ARGUMENT; }
-                src = a.varied_values + (size_t)vk * a.lanes;
-            }
-            CUDA_TRY(cudaMemcpyAsync(IN + (size_t)k * lanes, src + lane0, (size_t)lanes * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        {   // input planes IN[k][lanes]: the sweep value / frequency plane, then (normally) one contiguous run of Monte-Carlo planes
+            const cudaMemcpyKind kind = out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+            const int nv = (int)P0.input_of_varied.size();
+            if (nv > 0 && !a.varied_values) { set_error("missing per-lane values for a varied element"); return KRB_ERR_INVALID_ARGUMENT; }
+            if (P0.input_sweep >= 0) CUDA_TRY(cudaMemcpyAsync(IN + (size_t)P0.input_sweep * lanes, a.lane_param + lane0, (size_t)lanes * 8, kind, st));
+            if (P0.input_freq >= 0) CUDA_TRY(cudaMemcpyAsync(IN + (size_t)P0.input_freq * lanes, a.lane_param + lane0, (size_t)lanes * 8, kind, st));
+            bool run = nv > 0;
+            for (int q = 1; q < nv && run; q++) run = P0.input_of_varied[q] == P0.input_of_varied[0] + q;
+            if (run)
+                CUDA_TRY(cudaMemcpy2DAsync(IN + (size_t)P0.input_of_varied[0] * lanes, (size_t)lanes * 8, a.varied_values + lane0, (size_t)a.lanes * 8,
+                                           (size_t)lanes * 8, (size_t)nv, kind, st));
+            else
+                for (int q = 0; q < nv; q++) {
+                    const int k = P0.input_of_varied[q];
+                    if (k == P0.input_sweep) continue;   // the swept source's plane is the sweep value
+                    CUDA_TRY(cudaMemcpyAsync(IN + (size_t)k * lanes, a.varied_values + (size_t)q * a.lanes + lane0, (size_t)lanes * 8, kind, st));
+                }
         }
         CUDA_TRY(cudaMemsetAsync(D.status.p, 0, (size_t)lanes * 4, st));
         if (n_state) CUDA_TRY(cudaMemsetAsync(D.ST.p, 0, (size_t)n_state * lanes * 8, st));   // i_C(0) = 0
@@ -396,14 +441,44 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             if (pl.is_complex) krb_front_rhs<true><<<grid, 256, 0, st>>>(s);
             else krb_front_rhs<false><<<grid, 256, 0, st>>>(s);
             add_launches(1);
-            return front_solve(pl, make_params(pl, bufs, X, xls, (long long)row * n), lanes, st);
+            int rc2 = front_solve(pl, make_params(pl, bufs, X, xls, (long long)row * n), lanes, st);
+            for (int it = 0; it < pl.fdev->refine_steps && !rc2; it++) {
+                if (pl.is_complex) krb_front_rhs<true><<<grid, 256, 0, st>>>(s);
+                else krb_front_rhs<false><<<grid, 256, 0, st>>>(s);
+                FrontRefineParams r{};
+                r.res_ptr = pl.fdev->res_ptr; r.res_ent = pl.fdev->res_ent; r.res_col = pl.fdev->res_col;
+                r.A = D.A.p; r.a_stride = pl.pattern.nnz; r.BP = D.BP.p; r.X = X; r.x_lane_stride = xls; r.x_row_off = (long long)row * n;
+                r.DX = D.DX.p; r.n = n;
+                if (pl.is_complex) krb_front_residual<true><<<grid, 256, 0, st>>>(r);
+                else krb_front_residual<false><<<grid, 256, 0, st>>>(r);
+                rc2 = front_solve(pl, make_params(pl, bufs, D.DX.p, n, 0), lanes, st);
+                if (pl.is_complex) krb_front_axpy<true><<<grid, 256, 0, st>>>(r);
+                else krb_front_axpy<false><<<grid, 256, 0, st>>>(r);
+                add_launches(3);
+            }
+            return rc2;
         };
+        // KRB_FRONT_DEBUG=1: per-phase device times of the first chunk on stderr (synchronises; profiling aid only)
+        const bool dbg = getenv("KRB_FRONT_DEBUG") != nullptr && lane0 == 0;
+        std::vector<std::pair<const char *, cudaEvent_t>> marks;
+        auto mark = [&](const char *name) {
+            if (!dbg) return;
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            marks.push_back({name, e});
+        };
+        mark("start");
         if ((rc = stamp_and_factor(P0))) return rc;
+        mark("stamp+factor (first plan)");
         if ((rc = rhs_and_solve(P0, 0))) return rc;
+        mark("rhs+solve row 0");
         if (PS && rows > 1) {
             if ((rc = stamp_and_factor(*PS))) return rc;
+            mark("stamp+factor (step plan)");
             for (int r = 1; r < rows; r++) {
                 if ((rc = rhs_and_solve(*PS, r))) return rc;
+                if (r <= 2) mark("rhs+solve step");
                 if (n_state) {
                     FrontTrapParams t{};
                     t.elems = PS->fdev->elems; t.state_elems = PS->fdev->state_elems; t.n_state = n_state; t.n_elems = n_elems;
@@ -417,6 +492,16 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         }
         CUDA_TRY(cudaEventRecord(e1, st));
         CUDA_TRY(cudaGetLastError());
+        if (dbg) {
+            mark("end");
+            cudaStreamSynchronize(st);
+            for (size_t i = 1; i < marks.size(); i++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+                fprintf(stderr, "[krb front] lanes %lld  %-28s %9.3f ms\n", lanes, marks[i].first, ms);
+            }
+            for (auto &mk : marks) cudaEventDestroy(mk.second);
+        }
         // ---- delivery ----
         if (!out_dev) {
             CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * xls * ts, D.XS.p, (size_t)lanes * xls * ts, cudaMemcpyDeviceToHost, st));

@@ -47,6 +47,7 @@ struct FrontParams {
     int n;
     int smem_elems;           // capacity of the dynamic shared memory in elements of T
     int *status;
+    long long lanes;          // lanes of this launch (WARP-mode kernels bound-check their lane)
     int *IPIV;                // [lanes][n] row chosen for pivot k inside its front (local row index; == k when no swap)
     void *X;                  // result rows, point-major: X[lane * x_lane_stride + x_row_off + unknown]
     long long x_lane_stride, x_row_off;
@@ -217,8 +218,15 @@ __device__ __forceinline__ void front_pivot_search(const T *col, int k, int p, i
 
 // ---- (b) numeric factorisation of one front ---------------------------------------------------------------------
 // blockDim = (TX, TY); TX consecutive threads walk a column (unit stride), TY columns at a time.
+//
+// One algorithm for every front size (right-looking, blocked, LAPACK getrf order):
+//   for each panel of nb pivot columns:  factor the panel (threshold pivoting inside the fully-summed rows, rank-1 updates
+//   inside the panel only)  ->  interchanges + U12 = L11^-1 A12 on the columns right of it (one thread per column)  ->
+//   rank-nb update of the trailing block with 4 x 4 register tiles (each trailing element is read and written once per panel).
+// Fronts that fit are staged in shared memory whole (odd leading dimension: conflict-free column-per-thread access); larger
+// fronts live in the per-lane workspace (L2/HBM) and only the panel's L columns and U rows are copied to shared memory.
 template <bool CPLX>
-__global__ void krb_front_factor(const FrontParams P) {
+__global__ void __launch_bounds__(512) krb_front_factor(const FrontParams P) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
     extern __shared__ __align__(16) unsigned char front_smem[];
@@ -231,17 +239,22 @@ __global__ void krb_front_factor(const FrontParams P) {
     const int tid = ty * TX + tx, NT = TX * TY;
     const bool in_smem = d.fw_off < 0;
     T *F = in_smem ? sm : reinterpret_cast<T *>(P.FW) + lane * P.fw_stride + d.fw_off;
+    const int ldf = in_smem ? (m | 1) : m;          // F(i, j) = F[i + ldf * j]
     bool bad = false;
     __shared__ int s_ip;
     __shared__ int s_pv[16];
     int *ipiv = P.IPIV + lane * P.n + d.piv0;
 
     // ---- assemble: zero, stamped entries, children's contribution blocks (extend-add, children in ascending order) ----
-    for (int t = tid; t < m * m; t += NT) F[t] = S::zero();
+    for (int j = ty; j < m; j += TY)
+        for (int i = tx; i < m; i += TX) F[i + (size_t)ldf * j] = S::zero();
     __syncthreads();
     {
         const T *A = reinterpret_cast<const T *>(P.A) + lane * P.a_stride;
-        for (int t = d.asm_begin + tid; t < d.asm_end; t += NT) F[P.asm_pos[t]] = A[P.asm_ent[t]];
+        for (int t = d.asm_begin + tid; t < d.asm_end; t += NT) {
+            const int pos = P.asm_pos[t], c = pos / m, r = pos - c * m;
+            F[r + (size_t)ldf * c] = A[P.asm_ent[t]];
+        }
     }
     __syncthreads();
     for (int ci = d.child_begin; ci < d.child_end; ci++) {
@@ -250,249 +263,313 @@ __global__ void krb_front_factor(const FrontParams P) {
         const T *CBc = reinterpret_cast<const T *>(P.CB) + lane * P.cb_stride + c.cb_off;
         const int *rel = P.rel + c.idx_off;
         for (int j = ty; j < qc; j += TY) {
-            const int rj = rel[j] * m;
+            const size_t rj = (size_t)rel[j] * ldf;
             for (int i = tx; i < qc; i += TX) { T *dst = F + rel[i] + rj; *dst = S::add(*dst, CBc[i + (size_t)qc * j]); }
         }
         __syncthreads();
     }
 
-    if (in_smem) {
-        // ---- right-looking elimination on the staged block ----
-        for (int k = 0; k < p; k++) {
-            if (k + 1 < p) {
-                front_pivot_search<CPLX>(F + m * k, k, p, tid, &s_ip);
-                __syncthreads();
-                const int ip = s_ip;
-                if (ip != k) {
-                    for (int j = tid; j < m; j += NT) { const T t = F[k + m * j]; F[k + m * j] = F[ip + m * j]; F[ip + m * j] = t; }
-                }
-                if (tid == 0) ipiv[k] = ip;
-                __syncthreads();
-            } else if (tid == 0) ipiv[k] = k;
-            bool b1;
-            const T rp = S::rcp(F[k + m * k], b1);
-            bad |= b1;
-            for (int i = k + 1 + tid; i < m; i += NT) F[i + m * k] = S::mul(F[i + m * k], rp);
-            __syncthreads();
-            for (int i = k + 1 + tx; i < m; i += TX) {
-                const T l = F[i + m * k];
-                for (int j = k + 1 + ty; j < m; j += TY) F[i + m * j] = S::fnma(F[i + m * j], l, F[k + m * j]);
-            }
-            __syncthreads();
-        }
-    } else {
-        // ---- blocked elimination: panel (L columns + U rows) staged in shared memory, trailing block updated in place ----
-        int NB = (P.smem_elems - m) / (2 * m);
-        NB = NB > 16 ? 16 : NB;
-        for (int kb = 0; kb < p; kb += NB) {
-            const int nb = (p - kb) < NB ? (p - kb) : NB;
-            const int mk = m - kb, tw = mk - nb;
-            T *Lp = sm;                       // mk x nb, column-major
-            const int ldu = nb | 1;           // odd leading dimension: one thread per column without bank conflicts
-            T *Up = sm + (size_t)mk * nb;     // nb x tw, Up[k + ldu * j]
+    // ---- blocked elimination ----
+    int NB;
+    if (in_smem) NB = CPLX ? 4 : 8;
+    else { NB = (P.smem_elems - m) / (2 * m); NB = NB > 16 ? 16 : NB; }
+    for (int kb = 0; kb < p; kb += NB) {
+        const int nb = (p - kb) < NB ? (p - kb) : NB;
+        const int mk = m - kb, tw = mk - nb;
+        // panel views: Lp(i, k) = Lp[i + ldl * k] (mk x nb), Up(k, j) = Up[k + ldu * j] (nb x tw)
+        T *Lp, *Up;
+        int ldl, ldu;
+        if (in_smem) { Lp = F + kb + (size_t)ldf * kb; ldl = ldf; Up = F + kb + (size_t)ldf * (kb + nb); ldu = ldf; }
+        else {
+            Lp = sm; ldl = mk; Up = sm + (size_t)mk * nb; ldu = nb | 1;
             for (int k = ty; k < nb; k += TY)
-                for (int i = tx; i < mk; i += TX) Lp[i + mk * k] = F[(kb + i) + (size_t)m * (kb + k)];
+                for (int i = tx; i < mk; i += TX) Lp[i + ldl * k] = F[(kb + i) + (size_t)m * (kb + k)];
             for (int j = tid; j < tw; j += NT)
                 for (int k = 0; k < nb; k++) Up[k + ldu * j] = F[(kb + k) + (size_t)m * (kb + nb + j)];
             __syncthreads();
-            // panel factorisation (LAPACK getrf order): interchanges are applied to the panel columns and to the finished L
-            // columns on the left at once; the columns right of the panel get them afterwards, before their U rows are formed
-            for (int k = 0; k < nb; k++) {
-                int ip = k;
-                if (kb + k + 1 < p) {
-                    front_pivot_search<CPLX>(Lp + mk * k, k, p - kb, tid, &s_ip);
-                    __syncthreads();
-                    ip = s_ip;
-                    if (ip != k) {
-                        for (int j = tid; j < nb; j += NT) { const T t = Lp[k + mk * j]; Lp[k + mk * j] = Lp[ip + mk * j]; Lp[ip + mk * j] = t; }
-                        for (int j = tid; j < kb; j += NT) {
-                            T *a = F + (kb + k) + (size_t)m * j, *b = F + (kb + ip) + (size_t)m * j;
-                            const T t = *a; *a = *b; *b = t;
-                        }
+        }
+        // panel factorisation: interchanges are applied to the panel columns and to the finished L columns on the left at
+        // once; the columns right of the panel get them below, before their U rows are formed
+        for (int k = 0; k < nb; k++) {
+            int ip = k;
+            if (kb + k + 1 < p) {
+                front_pivot_search<CPLX>(Lp + (size_t)ldl * k, k, p - kb, tid, &s_ip);
+                __syncthreads();
+                ip = s_ip;
+                if (ip != k) {
+                    for (int j = tid; j < nb; j += NT) { const T t = Lp[k + ldl * j]; Lp[k + ldl * j] = Lp[ip + ldl * j]; Lp[ip + ldl * j] = t; }
+                    for (int j = tid; j < kb; j += NT) {
+                        T *a = F + (kb + k) + (size_t)ldf * j, *b = F + (kb + ip) + (size_t)ldf * j;
+                        const T t = *a; *a = *b; *b = t;
                     }
                 }
-                if (tid == 0) { ipiv[kb + k] = ip + kb; s_pv[k] = ip; }
-                __syncthreads();
-                bool b1;
-                const T rp = S::rcp(Lp[k + mk * k], b1);
-                bad |= b1;
-                for (int i = k + 1 + tid; i < mk; i += NT) Lp[i + mk * k] = S::mul(Lp[i + mk * k], rp);
-                __syncthreads();
-                for (int j = k + 1 + ty; j < nb; j += TY) {                 // remaining panel columns
-                    const T u = Lp[k + mk * j];
-                    for (int i = k + 1 + tx; i < mk; i += TX) Lp[i + mk * j] = S::fnma(Lp[i + mk * j], Lp[i + mk * k], u);
-                }
-                __syncthreads();
             }
-            // columns right of the panel, one thread per column: interchanges in order, then U12 = L11^-1 A12 (unit lower)
-            for (int j = tid; j < tw; j += NT) {
-                T *uc = Up + ldu * j;
-                for (int k = 0; k < nb; k++) {
-                    const int ip = s_pv[k];
-                    if (ip != k) {
-                        T *other = ip < nb ? uc + ip : F + (kb + ip) + (size_t)m * (kb + nb + j);
-                        const T t = uc[k]; uc[k] = *other; *other = t;
-                    }
-                }
-                for (int k = 0; k < nb; k++) {
-                    const T u = uc[k];
-                    for (int r = k + 1; r < nb; r++) uc[r] = S::fnma(uc[r], Lp[r + mk * k], u);
-                }
-            }
-            // panels back to the front (final L and U values)
-            for (int k = ty; k < nb; k += TY)
-                for (int i = tx; i < mk; i += TX) F[(kb + i) + (size_t)m * (kb + k)] = Lp[i + mk * k];
-            for (int j = tid; j < tw; j += NT)
-                for (int k = 0; k < nb; k++) F[(kb + k) + (size_t)m * (kb + nb + j)] = Up[k + ldu * j];
+            if (tid == 0) { ipiv[kb + k] = ip + kb; s_pv[k] = ip; }
             __syncthreads();
-            // trailing update, 4 x 2 register tiles
-            const int base = kb + nb;
-            for (int j0 = 0; j0 < tw; j0 += 2 * TY)
-                for (int i0 = 0; i0 < tw; i0 += 4 * TX) {
-                    T acc[4][2];
-#pragma unroll
-                    for (int a = 0; a < 4; a++) { acc[a][0] = S::zero(); acc[a][1] = S::zero(); }
-                    int ii[4], jj[2];
-#pragma unroll
-                    for (int a = 0; a < 4; a++) ii[a] = i0 + tx + a * TX;
-#pragma unroll
-                    for (int b = 0; b < 2; b++) jj[b] = j0 + ty + b * TY;
-                    for (int k = 0; k < nb; k++) {
-                        T l[4], u[2];
-#pragma unroll
-                        for (int a = 0; a < 4; a++) l[a] = ii[a] < tw ? Lp[nb + ii[a] + mk * k] : S::zero();
-#pragma unroll
-                        for (int b = 0; b < 2; b++) u[b] = jj[b] < tw ? Up[k + ldu * jj[b]] : S::zero();
-#pragma unroll
-                        for (int a = 0; a < 4; a++) {
-                            acc[a][0] = S::fnma(acc[a][0], l[a], u[0]);
-                            acc[a][1] = S::fnma(acc[a][1], l[a], u[1]);
-                        }
-                    }
-#pragma unroll
-                    for (int b = 0; b < 2; b++)
-#pragma unroll
-                        for (int a = 0; a < 4; a++)
-                            if (ii[a] < tw && jj[b] < tw) {
-                                T *dst = F + (base + ii[a]) + (size_t)m * (base + jj[b]);
-                                *dst = S::add(*dst, acc[a][b]);
-                            }
-                }
+            bool b1;
+            const T rp = S::rcp(Lp[k + ldl * k], b1);
+            bad |= b1;
+            for (int i = k + 1 + tid; i < mk; i += NT) Lp[i + ldl * k] = S::mul(Lp[i + ldl * k], rp);
+            __syncthreads();
+            for (int j = k + 1 + ty; j < nb; j += TY) {
+                const T u = Lp[k + ldl * j];
+                for (int i = k + 1 + tx; i < mk; i += TX) Lp[i + ldl * j] = S::fnma(Lp[i + ldl * j], Lp[i + ldl * k], u);
+            }
             __syncthreads();
         }
+        // columns right of the panel, one thread per column: interchanges in order, then U12 = L11^-1 A12 (unit lower)
+        for (int j = tid; j < tw; j += NT) {
+            T *uc = Up + (size_t)ldu * j;
+            for (int k = 0; k < nb; k++) {
+                const int ip = s_pv[k];
+                if (ip != k) {
+                    T *other = (in_smem || ip < nb) ? uc + ip : F + (kb + ip) + (size_t)m * (kb + nb + j);
+                    const T t = uc[k]; uc[k] = *other; *other = t;
+                }
+            }
+            for (int k = 0; k < nb; k++) {
+                const T u = uc[k];
+                for (int r = k + 1; r < nb; r++) uc[r] = S::fnma(uc[r], Lp[r + ldl * k], u);
+            }
+        }
+        if (!in_smem) {   // panels back to the front (final L and U values)
+            for (int k = ty; k < nb; k += TY)
+                for (int i = tx; i < mk; i += TX) F[(kb + i) + (size_t)m * (kb + k)] = Lp[i + ldl * k];
+            for (int j = tid; j < tw; j += NT)
+                for (int k = 0; k < nb; k++) F[(kb + k) + (size_t)m * (kb + nb + j)] = Up[k + ldu * j];
+        }
+        __syncthreads();
+        // trailing block C(i, j) -= sum_k Lp(nb + i, k) Up(k, j), 4 x 4 register tiles, C loaded before the k loop
+        {
+            T *C = F + (kb + nb) + (size_t)ldf * (kb + nb);
+            const T *Lt = Lp + nb;
+            for (int j0 = 0; j0 < tw; j0 += 4 * TY)
+                for (int i0 = 0; i0 < tw; i0 += 4 * TX) {
+                    int ii[4], jj[4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) { ii[a] = i0 + tx + a * TX; jj[a] = j0 + ty + a * TY; }
+                    if (ii[0] >= tw || jj[0] >= tw) continue;
+                    T c[4][4];
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+#pragma unroll
+                        for (int a = 0; a < 4; a++) c[a][b] = (ii[a] < tw && jj[b] < tw) ? C[ii[a] + (size_t)ldf * jj[b]] : S::zero();
+                    // clamp the indices of partial tiles (their results are discarded) so the inner loop is branch-free
+                    int il[4], jl[4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) { il[a] = ii[a] < tw ? ii[a] : ii[0]; jl[a] = jj[a] < tw ? jj[a] : jj[0]; }
+                    for (int k = 0; k < nb; k++) {
+                        T l[4], u[4];
+#pragma unroll
+                        for (int a = 0; a < 4; a++) { l[a] = Lt[il[a] + (size_t)ldl * k]; u[a] = Up[k + (size_t)ldu * jl[a]]; }
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+#pragma unroll
+                            for (int a = 0; a < 4; a++) c[a][b] = S::fnma(c[a][b], l[a], u[b]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+                            if (ii[a] < tw && jj[b] < tw) C[ii[a] + (size_t)ldf * jj[b]] = c[a][b];
+                }
+        }
+        __syncthreads();
     }
 
     // ---- write out: L block (m x p, reciprocal pivots on the diagonal), U12 (p x q), contribution block (q x q) ----
     T *LUf = reinterpret_cast<T *>(P.LU) + lane * P.lu_stride + d.lu_off;
     for (int k = ty; k < p; k += TY)
         for (int i = tx; i < m; i += TX) {
-            T v = F[i + (size_t)m * k];
+            T v = F[i + (size_t)ldf * k];
             if (i == k) { bool b1; v = S::rcp(v, b1); }
             LUf[i + (size_t)m * k] = v;
         }
     T *U12 = LUf + (size_t)m * p;
     for (int j = ty; j < q; j += TY)
-        for (int k = tx; k < p; k += TX) U12[k + (size_t)p * j] = F[k + (size_t)m * (p + j)];
+        for (int k = tx; k < p; k += TX) U12[k + (size_t)p * j] = F[k + (size_t)ldf * (p + j)];
     T *CBf = reinterpret_cast<T *>(P.CB) + lane * P.cb_stride + d.cb_off;
     for (int j = ty; j < q; j += TY)
-        for (int i = tx; i < q; i += TX) CBf[i + (size_t)q * j] = F[(p + i) + (size_t)m * (p + j)];
+        for (int i = tx; i < q; i += TX) CBf[i + (size_t)q * j] = F[(p + i) + (size_t)ldf * (p + j)];
     if (bad && tid == 0 && P.status) atomicOr(P.status + lane, KRB_LANE_ZERO_PIVOT);
 }
 
-// ---- (c) forward substitution of one front: y_piv = L11^-1 (b_piv + children), contribution = rest - L21 y_piv -------
+// ---- iterative refinement: r = b - A x on the stamped values, in pivot order; x += correction ------------------------
+struct FrontRefineParams {
+    const int *res_ptr, *res_ent, *res_col;   // CSR of the permuted matrix: position k -> (CSC entry id, unknown)
+    const void *A;
+    long long a_stride;
+    void *BP;                                  // in: b (pivot order), out: residual
+    const void *X;                             // current solution, X[lane * x_lane_stride + x_row_off + unknown]
+    long long x_lane_stride, x_row_off;
+    void *DX;                                  // correction, DX[lane * n + unknown]
+    int n;
+};
 template <bool CPLX>
+__global__ void krb_front_residual(const FrontRefineParams p) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const long long lane = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.n) return;
+    const T *A = reinterpret_cast<const T *>(p.A) + lane * p.a_stride;
+    const T *X = reinterpret_cast<const T *>(p.X) + lane * p.x_lane_stride + p.x_row_off;
+    T *bp = reinterpret_cast<T *>(p.BP) + lane * p.n + k;
+    T acc = *bp;
+    for (int t = p.res_ptr[k]; t < p.res_ptr[k + 1]; t++) acc = S::fnma(acc, A[p.res_ent[t]], X[p.res_col[t]]);
+    *bp = acc;
+}
+template <bool CPLX>
+__global__ void krb_front_axpy(const FrontRefineParams p) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const long long lane = blockIdx.y;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= p.n) return;
+    T *x = const_cast<T *>(reinterpret_cast<const T *>(p.X)) + lane * p.x_lane_stride + p.x_row_off + u;
+    *x = S::add(*x, reinterpret_cast<const T *>(p.DX)[lane * p.n + u]);
+}
+
+// ---- (c) triangular solves ------------------------------------------------------------------------------------------
+// Two launch shapes: CTA per (front, lane) for large fronts, and WARP mode (blockDim = (32, W)) where every warp owns its own
+// (front, lane) pair and synchronises with __syncwarp only — the lowest tree levels hold thousands of tiny fronts per lane.
+// Both walk the pivot block in panels of 32 columns: the 32 x 32 diagonal block is solved by one warp with shuffles (all its
+// L/U entries are loaded up front), the rows outside it are updated by one thread per row, so every factor entry is read
+// exactly once, with unit stride, and never behind a dependent chain.
+template <bool WARP> __device__ __forceinline__ void front_sync() { if (WARP) __syncwarp(); else __syncthreads(); }
+template <bool WARP> __device__ __forceinline__ int front_any(int pred) { return WARP ? __any_sync(0xffffffffu, pred) : __syncthreads_or(pred); }
+__device__ __forceinline__ double front_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double2 front_shfl(double2 v, int src) { return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
+
+// forward: y_piv = L11^-1 P (b_piv + children), contribution = rest - L21 y_piv
+template <bool CPLX, bool WARP>
 __global__ void krb_front_forward(const FrontParams P) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
     extern __shared__ __align__(16) unsigned char front_smem[];
-    T *w = reinterpret_cast<T *>(front_smem);
+    const long long lane = WARP ? (long long)blockIdx.y * blockDim.y + threadIdx.y : (long long)blockIdx.y;
+    if (WARP && lane >= P.lanes) return;
+    T *w = reinterpret_cast<T *>(front_smem) + (WARP ? (size_t)threadIdx.y * P.smem_elems : 0);
     const int f = P.list[blockIdx.x];
-    const long long lane = blockIdx.y;
     const FrontDesc d = P.fronts[f];
     const int p = d.p, q = d.q, m = p + q;
     const int tid = threadIdx.x, NT = blockDim.x;
     T *BP = reinterpret_cast<T *>(P.BP) + lane * P.n;
     T *CBV = reinterpret_cast<T *>(P.CBV) + lane * P.cbv_stride;
     for (int i = tid; i < m; i += NT) w[i] = i < p ? BP[d.piv0 + i] : S::zero();
-    __syncthreads();
+    front_sync<WARP>();
     for (int ci = d.child_begin; ci < d.child_end; ci++) {
         const FrontDesc c = P.fronts[P.child[ci]];
         const int *rel = P.rel + c.idx_off;
         for (int i = tid; i < c.q; i += NT) { T *dst = w + rel[i]; *dst = S::add(*dst, CBV[c.cbv_off + i]); }
-        __syncthreads();
+        front_sync<WARP>();
     }
     {   // the lane's row interchanges inside the pivot block (usually none)
         const int *ipiv = P.IPIV + lane * P.n + d.piv0;
         int moved = 0;
         for (int k = tid; k < p; k += NT) moved |= (ipiv[k] != k);
-        if (__syncthreads_or(moved)) {
+        if (front_any<WARP>(moved)) {
             if (tid == 0)
                 for (int k = 0; k < p; k++) { const int ip = ipiv[k]; if (ip != k) { const T t = w[k]; w[k] = w[ip]; w[ip] = t; } }
-            __syncthreads();
+            front_sync<WARP>();
         }
     }
     const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
-    // unit-lower triangular solve on the pivot block
-    for (int k = 0; k + 1 < p; k++) {
-        const T wk = w[k];
-        for (int i = k + 1 + tid; i < p; i += NT) w[i] = S::fnma(w[i], L[i + (size_t)m * k], wk);
-        __syncthreads();
+    for (int kb = 0; kb < p; kb += 32) {
+        const int nbk = (p - kb) < 32 ? (p - kb) : 32;
+        if (tid < 32) {
+            // unit-lower diagonal block: lane t owns row kb + t; its entries left of the diagonal are loaded first
+            T lrow[32];
+            const T *Lr = L + (kb + tid) + (size_t)m * kb;
+#pragma unroll
+            for (int k = 0; k < 32; k++) lrow[k] = (k < tid && tid < nbk) ? Lr[(size_t)m * k] : S::zero();
+            T val = tid < nbk ? w[kb + tid] : S::zero();
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                const T yk = front_shfl(val, k);
+                if (k < tid) val = S::fnma(val, lrow[k], yk);
+            }
+            if (tid < nbk) w[kb + tid] = val;
+        }
+        front_sync<WARP>();
+        for (int i = kb + nbk + tid; i < m; i += NT) {
+            T acc = w[i];
+            const T *Lr = L + i + (size_t)m * kb;
+            for (int k = 0; k < nbk; k++) acc = S::fnma(acc, Lr[(size_t)m * k], w[kb + k]);
+            w[i] = acc;
+        }
+        front_sync<WARP>();
     }
-    // rows below the pivot block: w[p + i] -= L21[i, :] . y
-    for (int i = p + tid; i < m; i += NT) {
-        T acc = w[i];
-        for (int k = 0; k < p; k++) acc = S::fnma(acc, L[i + (size_t)m * k], w[k]);
-        CBV[d.cbv_off + (i - p)] = acc;
-    }
+    for (int i = tid; i < q; i += NT) CBV[d.cbv_off + i] = w[p + i];
     for (int k = tid; k < p; k += NT) BP[d.piv0 + k] = w[k];
 }
 
-// ---- (c) backward substitution of one front: x_piv = U11^-1 (y_piv - U12 x_update) ----------------------------------
-template <bool CPLX>
+// backward: x_piv = U11^-1 (y_piv - U12 x_update), delivered point-major in unknown order
+template <bool CPLX, bool WARP>
 __global__ void krb_front_backward(const FrontParams P) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
     extern __shared__ __align__(16) unsigned char front_smem[];
-    T *w = reinterpret_cast<T *>(front_smem);      // [0,p): running right-hand side, [p, m): x at the update positions
+    const long long lane = WARP ? (long long)blockIdx.y * blockDim.y + threadIdx.y : (long long)blockIdx.y;
+    if (WARP && lane >= P.lanes) return;
+    T *w = reinterpret_cast<T *>(front_smem) + (WARP ? (size_t)threadIdx.y * P.smem_elems : 0);   // [0,p): rhs -> x, [p,m): x at the update positions
     const int f = P.list[blockIdx.x];
-    const long long lane = blockIdx.y;
     const FrontDesc d = P.fronts[f];
     const int p = d.p, q = d.q, m = p + q;
-    T *xs = w + m;                                 // [p] solved pivots
-    T *red = xs + p;                               // [NT] partial sums
+    T *red = w + m;                                // [NT] partial sums
     const int tid = threadIdx.x, NT = blockDim.x;
     const T *BP = reinterpret_cast<const T *>(P.BP) + lane * P.n;
     T *X = reinterpret_cast<T *>(P.X) + lane * P.x_lane_stride + P.x_row_off;
     for (int i = tid; i < m; i += NT) w[i] = i < p ? BP[d.piv0 + i] : X[P.idx_unknown[d.idx_off + (i - p)]];
-    __syncthreads();
+    front_sync<WARP>();
     const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
     const T *U12 = L + (size_t)m * p;
     if (q > 0) {
         // w[k] -= sum_j U12[k, j] x_j : G thread groups split the columns, partial sums reduced in a fixed order
+        const int stride = p < NT ? p : NT;
         const int G = NT / p > 0 ? NT / p : 1;
         for (int k0 = 0; k0 < p; k0 += NT) {
-            const int k = k0 + (tid % (p < NT ? p : NT)), g = tid / (p < NT ? p : NT);
+            const int k = k0 + (tid % stride), g = tid / stride;
             T acc = S::zero();
             const bool act = k < p && g < G;
             if (act) for (int j = g; j < q; j += G) acc = S::fnma(acc, U12[k + (size_t)p * j], w[p + j]);
             red[tid] = acc;
-            __syncthreads();
+            front_sync<WARP>();
             if (act && g == 0) {
                 T s = w[k];
-                const int stride = p < NT ? p : NT;
                 for (int gg = 0; gg < G; gg++) s = S::add(s, red[(k - k0) + gg * stride]);
                 w[k] = s;
             }
-            __syncthreads();
+            front_sync<WARP>();
         }
     }
-    for (int k = p - 1; k >= 0; k--) {
-        const T xk = S::mul(w[k], L[k + (size_t)m * k]);   // diagonal holds the reciprocal pivot
-        if (tid == 0) xs[k] = xk;
-        for (int i = tid; i < k; i += NT) w[i] = S::fnma(w[i], L[i + (size_t)m * k], xk);
-        __syncthreads();
+    for (int kb = ((p - 1) / 32) * 32; kb >= 0; kb -= 32) {
+        const int nbk = (p - kb) < 32 ? (p - kb) : 32;
+        if (tid < 32) {
+            // upper-triangular diagonal block (reciprocal pivots on the diagonal): lane t owns row kb + t
+            T urow[32];
+            const T *Ur = L + (kb + tid) + (size_t)m * kb;
+#pragma unroll
+            for (int k = 0; k < 32; k++) urow[k] = (k >= tid && k < nbk) ? Ur[(size_t)m * k] : S::zero();
+            T val = tid < nbk ? w[kb + tid] : S::zero();
+#pragma unroll
+            for (int k = 31; k >= 0; k--) {
+                if (k == tid) val = S::mul(val, urow[k]);        // x_k = rhs_k / pivot_k
+                const T xk = front_shfl(val, k);
+                if (k > tid) val = S::fnma(val, urow[k], xk);
+            }
+            if (tid < nbk) w[kb + tid] = val;
+        }
+        front_sync<WARP>();
+        for (int i = tid; i < kb; i += NT) {
+            T acc = w[i];
+            const T *Ur = L + i + (size_t)m * kb;
+            for (int k = 0; k < nbk; k++) acc = S::fnma(acc, Ur[(size_t)m * k], w[kb + k]);
+            w[i] = acc;
+        }
+        front_sync<WARP>();
     }
-    for (int k = tid; k < p; k += NT) X[P.col_order[d.piv0 + k]] = xs[k];
+    for (int k = tid; k < p; k += NT) X[P.col_order[d.piv0 + k]] = w[k];
 }
 
 }  // namespace krb

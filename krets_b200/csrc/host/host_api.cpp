@@ -210,6 +210,16 @@ int32_t krh_solver_solve_ac(krh_solver *s, int32_t sweep_kind, uint32_t points, 
             auto h = std::make_unique<PlanHolder>();
             rc = krb_analyze(s->kc, KRB_MODE_AC, &o, &h->p);
             if (rc) return fail_krb(rc);
+            krb_plan_info pi;
+            if (krb_plan_get_info(h->p, &pi) == KRB_OK && pi.executor == 2 && freqs.front() < o.nominal_frequency) {
+                // front executor: static pivots prefer the diagonal where it is within 1e3 of the column maximum at the nominal
+                // frequency; the inductor branch diagonal -j*w*L (stampable.rs:715) is smallest at the lowest frequency, so plan there
+                krb_plan_destroy(h->p);
+                h->p = nullptr;
+                o.nominal_frequency = freqs.front();
+                rc = krb_analyze(s->kc, KRB_MODE_AC, &o, &h->p);
+                if (rc) return fail_krb(rc);
+            }
             s->ac_plan = std::move(h);
         }
         std::vector<int32_t> st(freqs.size(), 0);

@@ -60,7 +60,10 @@ void nominal_magnitudes(const Circuit &c, const Stamps &s, const Pattern &p, int
 // ---- static pivot plan ----------------------------------------------------------------------------------
 // maximum-product transversal: match_row[col] = row used as the pivot equation of unknown `col`; false if
 // structurally singular
-bool weighted_matching(const Pattern &p, const std::vector<double> &mag, std::vector<int> &match_row);
+// diag_bonus (natural-log units): a diagonal entry is treated as if it were exp(diag_bonus) times larger.  The front executor
+// pivots dynamically inside its fronts, so it prefers the structurally symmetric (diagonal) matching, which keeps the fill of
+// the symmetrised pattern low; the one-thread-per-lane executors use 0 (pure maximum product).
+bool weighted_matching(const Pattern &p, const std::vector<double> &mag, std::vector<int> &match_row, double diag_bonus = 0.0);
 // minimum-degree ordering of the symmetrised, row-permuted pattern; returns order[k] = unknown eliminated k-th
 void minimum_degree(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order);
 void rcm_order(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order);

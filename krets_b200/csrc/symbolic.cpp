@@ -19,7 +19,7 @@ namespace krb {
 // Maximum-product transversal (Duff & Koster MC64 job 5 formulation): minimise sum of
 // c_ij = log(max_i |a_ij|) - log |a_ij| over perfect matchings, by successive shortest augmenting paths with
 // row/column potentials (reduced costs stay >= 0, matched edges stay tight).
-bool weighted_matching(const Pattern &p, const std::vector<double> &mag, std::vector<int> &match_row) {
+bool weighted_matching(const Pattern &p, const std::vector<double> &mag, std::vector<int> &match_row, double diag_bonus) {
     const int n = p.n;
     const double ZERO_COST = 80.0;   // numerically-zero but structurally present entries: last resort
     std::vector<double> cost(p.nnz);
@@ -28,6 +28,9 @@ bool weighted_matching(const Pattern &p, const std::vector<double> &mag, std::ve
         for (int q = p.colptr[j]; q < p.colptr[j + 1]; q++) cmax = std::max(cmax, mag[q]);
         for (int q = p.colptr[j]; q < p.colptr[j + 1]; q++)
             cost[q] = (mag[q] > 0.0 && cmax > 0.0) ? std::log(cmax) - std::log(mag[q]) : ZERO_COST;
+        if (diag_bonus > 0.0)
+            for (int q = p.colptr[j]; q < p.colptr[j + 1]; q++)
+                if (p.rowidx[q] == j && cost[q] < ZERO_COST) cost[q] = std::max(0.0, cost[q] - diag_bonus);
     }
     std::vector<double> u(n, 0.0), v(n, 0.0);
     std::vector<int> row_mate(n, -1);   // row -> column
