@@ -53,7 +53,7 @@ struct FrontDevice {
     std::vector<std::vector<FrontLaunch>> factor_launches, solve_launches;   // per level
     long long fw_size = 0;
     int smem_cap = 0;
-    FBuf IN, EV, A, LU, CB, FW, CBV, BP, ST, XS, status, Bstep, IPIV, DX;
+    FBuf IN, EV, A, LU, LU0, CB, FW, CBV, BP, ST, XS, status, Bstep, IPIV, DX;
     std::vector<double> bstep_host;
     int bstep_rows = -1;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -79,7 +79,7 @@ void front_device_free(FrontDevice *d) {
     void *ptrs[] = {d->fronts, d->list, d->idx_unknown, d->rel, d->child, d->asm_ent, d->asm_pos, d->col_order, d->elems,
                     d->mat_terms, d->rhs_terms, d->mat_ptr, d->rhs_ptr, d->state_elems, d->res_ptr, d->res_ent, d->res_col};
     for (void *p : ptrs) if (p) cudaFree(p);
-    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV, &d->DX};
+    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV, &d->DX, &d->LU0};
     for (FBuf *b : bufs) b->release();
     for (auto &e : d->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete d;
@@ -216,8 +216,8 @@ static int upload_front(Plan &plan) {
     // plans are solved at the point they were planned for.
     D.refine_steps = plan.mode == KRB_MODE_AC ? 2 : 0;
     if (const char *e = getenv("KRB_FRONT_REFINE")) D.refine_steps = std::max(0, atoi(e));
-    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
-    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
@@ -253,8 +253,9 @@ static int front_factor(const Plan &plan, FrontParams P, long long lanes, cudaSt
             Q.smem_elems = (int)(L.smem / ts);
             Q.lanes = lanes;
             dim3 grid((unsigned)L.count, (unsigned)lanes);
-            if (plan.is_complex) krb_front_factor<true><<<grid, L.block, L.smem, st>>>(Q);
-            else krb_front_factor<false><<<grid, L.block, L.smem, st>>>(Q);
+            const bool small = L.block.x * L.block.y <= 128;
+            if (plan.is_complex) { if (small) krb_front_factor<true, 2><<<grid, L.block, L.smem, st>>>(Q); else krb_front_factor<true, 4><<<grid, L.block, L.smem, st>>>(Q); }
+            else { if (small) krb_front_factor<false, 2><<<grid, L.block, L.smem, st>>>(Q); else krb_front_factor<false, 4><<<grid, L.block, L.smem, st>>>(Q); }
             add_launches(1);
         }
     CUDA_TRY(cudaGetLastError());
@@ -338,37 +339,52 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     }
 
     // ---- chunking by device memory ----
-    auto mx = [&](auto f) { return PS ? std::max(f(P0), f(*PS)) : f(P0); };
-    const size_t lu_e = (size_t)mx([](const Plan &p) { return p.front.lu_size; });
-    const size_t cb_e = (size_t)mx([](const Plan &p) { return p.front.cb_size; });
-    const size_t cbv_e = (size_t)mx([](const Plan &p) { return p.front.cbv_size; });
-    const size_t fw_e = (size_t)mx([](const Plan &p) { return p.fdev->fw_size; });
-    const size_t a_e = (size_t)mx([](const Plan &p) { return (long long)p.pattern.nnz; });
-    const size_t per_lane = (lu_e + cb_e + cbv_e + fw_e + a_e + (size_t)n) * ts + (size_t)n_elems * 8 + (size_t)P0.n_inputs * 8 + (size_t)n_state * 8 + (size_t)n * 4 + (size_t)n * ts +
-                            (out_dev ? 0 : (size_t)rows * n * ts) + 64;
-    long long chunk = a.chunk_lanes > 0 ? a.chunk_lanes : 1024;
+    // persistent per lane of a chunk: inputs, element values, stamped values A, the factor store of the plan that is solved
+    // repeatedly (LU), vectors; workspace per lane of a factor window: contribution blocks, out-of-shared-memory fronts, and for a
+    // transient the operating-point plan's own factor store (needed for row 0 only).
+    Plan &PM = PS ? *PS : P0;                      // plan whose factors stay resident
+    const size_t a_e = (size_t)std::max<long long>(P0.pattern.nnz, PS ? PS->pattern.nnz : 0);
+    const size_t cbv_e = (size_t)std::max<long long>(P0.front.cbv_size, PS ? PS->front.cbv_size : 0);
+    const size_t lu_e = (size_t)PM.front.lu_size;
+    const size_t lu0_e = PS ? (size_t)P0.front.lu_size : 0;
+    const size_t cb_e = (size_t)std::max<long long>(P0.front.cb_size, PS ? PS->front.cb_size : 0);
+    const size_t fw_e = (size_t)std::max<long long>(P0.fdev->fw_size, PS ? PS->fdev->fw_size : 0);
+    const bool refine = P0.fdev->refine_steps > 0 || (PS && PS->fdev->refine_steps > 0);
+    const size_t persist = (lu_e + a_e + cbv_e + (size_t)n * (refine ? 2 : 1)) * ts + (size_t)n_elems * 8 + (size_t)P0.n_inputs * 8 + (size_t)n_state * 8 +
+                           (size_t)n * 4 + (out_dev ? 0 : (size_t)rows * n * ts) + 64;
+    const size_t work = (cb_e + fw_e + lu0_e) * ts + 64;
+    long long chunk = a.chunk_lanes > 0 ? a.chunk_lanes : 2048;
     chunk = std::min<long long>(chunk, a.lanes);
     chunk = std::min<long long>(chunk, 65535);
+    long long window = 256;
+    if (const char *e = getenv("KRB_FRONT_WINDOW")) window = std::max(1, atoi(e));
+    window = std::min(window, chunk);
     {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const size_t reusable = D.LU.bytes + D.CB.bytes + D.FW.bytes + D.CBV.bytes + D.A.bytes + D.BP.bytes + D.EV.bytes + D.XS.bytes + D.IN.bytes + D.ST.bytes;
-        const long long max_chunk = (long long)(((free_b + reusable) * 0.85) / (double)per_lane);
-        if (max_chunk < 1) { set_error("not enough device memory for one lane of this plan"); return KRB_ERR_OUT_OF_MEMORY; }
-        chunk = std::min(chunk, max_chunk);
+        size_t reusable = 0;
+        FBuf *all[] = {&D.IN, &D.EV, &D.A, &D.LU, &D.LU0, &D.CB, &D.FW, &D.CBV, &D.BP, &D.ST, &D.XS, &D.IPIV, &D.DX};
+        for (FBuf *bf : all) reusable += bf->bytes;
+        const double avail = (double)(free_b + reusable) * 0.88;
+        if (avail < (double)(persist + work)) { set_error("not enough device memory for one lane of this plan"); return KRB_ERR_OUT_OF_MEMORY; }
+        window = std::min<long long>(window, std::max<long long>(1, (long long)(avail * 0.5 / (double)work)));
+        const long long max_chunk = (long long)((avail - (double)window * (double)work) / (double)persist);
+        chunk = std::max<long long>(1, std::min(chunk, max_chunk));
+        window = std::min(window, chunk);
     }
     if ((rc = D.IN.ensure(std::max<size_t>((size_t)P0.n_inputs, 1) * chunk * 8))) return rc;
     if ((rc = D.EV.ensure(std::max<size_t>((size_t)n_elems, 1) * chunk * 8))) return rc;
     if ((rc = D.A.ensure(a_e * chunk * ts))) return rc;
     if ((rc = D.LU.ensure(lu_e * chunk * ts))) return rc;
-    if ((rc = D.CB.ensure(std::max<size_t>(cb_e, 1) * chunk * ts))) return rc;
-    if ((rc = D.FW.ensure(std::max<size_t>(fw_e, 1) * chunk * ts))) return rc;
+    if (PS && (rc = D.LU0.ensure(lu0_e * window * ts))) return rc;
+    if ((rc = D.CB.ensure(std::max<size_t>(cb_e, 1) * window * ts))) return rc;
+    if ((rc = D.FW.ensure(std::max<size_t>(fw_e, 1) * window * ts))) return rc;
     if ((rc = D.CBV.ensure(std::max<size_t>(cbv_e, 1) * chunk * ts))) return rc;
     if ((rc = D.BP.ensure((size_t)n * chunk * ts))) return rc;
     if ((rc = D.ST.ensure(std::max<size_t>((size_t)n_state, 1) * chunk * 8))) return rc;
     if ((rc = D.status.ensure((size_t)chunk * 4))) return rc;
     if ((rc = D.IPIV.ensure((size_t)n * chunk * 4))) return rc;
-    if ((P0.fdev->refine_steps > 0 || (PS && PS->fdev->refine_steps > 0)) && (rc = D.DX.ensure((size_t)n * chunk * ts))) return rc;
+    if (refine && (rc = D.DX.ensure((size_t)n * chunk * ts))) return rc;
     if (!out_dev && (rc = D.XS.ensure((size_t)rows * n * chunk * ts))) return rc;
 
     D.events_used = 0;
@@ -397,7 +413,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         }
         CUDA_TRY(cudaMemsetAsync(D.status.p, 0, (size_t)lanes * 4, st));
         if (n_state) CUDA_TRY(cudaMemsetAsync(D.ST.p, 0, (size_t)n_state * lanes * 8, st));   // i_C(0) = 0
-        void *X = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * xls * ts) : D.XS.p;
+        char *X = out_dev ? (char *)a.x_out + (size_t)lane0 * xls * ts : (char *)D.XS.p;
 
         if (D.events_used == D.events.size()) {
             cudaEvent_t x, y;
@@ -409,49 +425,63 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         D.events_used++;
         CUDA_TRY(cudaEventRecord(e0, st));
 
-        Bufs bufs{D.A.p, D.LU.p, D.CB.p, D.FW.p, D.CBV.p, D.BP.p, (int *)D.status.p, (int *)D.IPIV.p};
-        auto stamp_params = [&](const Plan &pl) {
+        // a lane window [s0, s0 + sl) of the chunk: persistent stores are addressed from s0, workspace from 0
+        auto bufs_for = [&](const Plan &pl, void *lu_base, bool lu_windowed, long long s0) {
+            Bufs b{};
+            b.A = (char *)D.A.p + (size_t)s0 * pl.pattern.nnz * ts;
+            b.LU = (char *)lu_base + (lu_windowed ? 0 : (size_t)s0 * pl.front.lu_size * ts);
+            b.CB = D.CB.p; b.FW = D.FW.p;
+            b.CBV = (char *)D.CBV.p + (size_t)s0 * pl.front.cbv_size * ts;
+            b.BP = (char *)D.BP.p + (size_t)s0 * n * ts;
+            b.status = (int *)D.status.p + s0;
+            b.ipiv = (int *)D.IPIV.p + (size_t)s0 * n;
+            return b;
+        };
+        auto stamp_params = [&](const Plan &pl, long long s0) {
             const FrontDevice &DD = *pl.fdev;
             FrontStampParams s{};
-            s.elems = DD.elems; s.n_elems = n_elems; s.IN = IN; s.L = lanes; s.EV = (double *)D.EV.p;
+            s.elems = DD.elems; s.n_elems = n_elems; s.IN = IN + s0; s.L = lanes; s.EV = (double *)D.EV.p + (size_t)s0 * n_elems;
             s.input_freq = pl.input_freq; s.h_comp = pl.h_comp; s.x_lane_stride = xls;
-            s.ST = (double *)D.ST.p; s.n_state = n_state;
+            s.ST = (double *)D.ST.p + (size_t)s0 * n_state; s.n_state = n_state;
             return s;
         };
         {   // per-lane element values
-            FrontStampParams s = stamp_params(P0);
+            FrontStampParams s = stamp_params(P0, 0);
             krb_front_expand<<<dim3((unsigned)((n_elems + 255) / 256), (unsigned)lanes), 256, 0, st>>>(s);
             add_launches(1);
         }
-        auto stamp_and_factor = [&](const Plan &pl) -> int {
-            FrontStampParams s = stamp_params(pl);
-            s.terms = pl.fdev->mat_terms; s.term_ptr = pl.fdev->mat_ptr; s.count = pl.pattern.nnz; s.OUT = D.A.p;
-            dim3 grid((unsigned)((s.count + 255) / 256), (unsigned)lanes);
+        auto stamp_and_factor = [&](const Plan &pl, void *lu_base, bool lu_windowed, long long s0, long long sl) -> int {
+            FrontStampParams s = stamp_params(pl, s0);
+            s.terms = pl.fdev->mat_terms; s.term_ptr = pl.fdev->mat_ptr; s.count = pl.pattern.nnz;
+            s.OUT = (char *)D.A.p + (size_t)s0 * pl.pattern.nnz * ts;
+            dim3 grid((unsigned)((s.count + 255) / 256), (unsigned)sl);
             if (pl.is_complex) krb_front_stamp<true><<<grid, 256, 0, st>>>(s);
             else krb_front_stamp<false><<<grid, 256, 0, st>>>(s);
             add_launches(1);
-            return front_factor(pl, make_params(pl, bufs, X, xls, 0), lanes, st);
+            return front_factor(pl, make_params(pl, bufs_for(pl, lu_base, lu_windowed, s0), X + (size_t)s0 * xls * ts, xls, 0), sl, st);
         };
-        auto rhs_and_solve = [&](const Plan &pl, int row) -> int {
-            FrontStampParams s = stamp_params(pl);
-            s.terms = pl.fdev->rhs_terms; s.term_ptr = pl.fdev->rhs_ptr; s.count = n; s.OUT = D.BP.p;
+        auto rhs_and_solve = [&](const Plan &pl, void *lu_base, bool lu_windowed, long long s0, long long sl, int row) -> int {
+            char *Xw = X + (size_t)s0 * xls * ts;
+            const Bufs bufs = bufs_for(pl, lu_base, lu_windowed, s0);
+            FrontStampParams s = stamp_params(pl, s0);
+            s.terms = pl.fdev->rhs_terms; s.term_ptr = pl.fdev->rhs_ptr; s.count = n; s.OUT = bufs.BP;
             s.Bstep = (const double *)pl.fdev->Bstep.p; s.n_wave = (int)pl.wave_elems.size(); s.row = row;
-            s.Xprev = row > 0 ? (const double *)X + (size_t)(row - 1) * n : nullptr;
-            dim3 grid((unsigned)((n + 255) / 256), (unsigned)lanes);
+            s.Xprev = row > 0 ? (const double *)Xw + (size_t)(row - 1) * n : nullptr;
+            dim3 grid((unsigned)((n + 255) / 256), (unsigned)sl);
             if (pl.is_complex) krb_front_rhs<true><<<grid, 256, 0, st>>>(s);
             else krb_front_rhs<false><<<grid, 256, 0, st>>>(s);
             add_launches(1);
-            int rc2 = front_solve(pl, make_params(pl, bufs, X, xls, (long long)row * n), lanes, st);
+            int rc2 = front_solve(pl, make_params(pl, bufs, Xw, xls, (long long)row * n), sl, st);
             for (int it = 0; it < pl.fdev->refine_steps && !rc2; it++) {
                 if (pl.is_complex) krb_front_rhs<true><<<grid, 256, 0, st>>>(s);
                 else krb_front_rhs<false><<<grid, 256, 0, st>>>(s);
                 FrontRefineParams r{};
                 r.res_ptr = pl.fdev->res_ptr; r.res_ent = pl.fdev->res_ent; r.res_col = pl.fdev->res_col;
-                r.A = D.A.p; r.a_stride = pl.pattern.nnz; r.BP = D.BP.p; r.X = X; r.x_lane_stride = xls; r.x_row_off = (long long)row * n;
-                r.DX = D.DX.p; r.n = n;
+                r.A = bufs.A; r.a_stride = pl.pattern.nnz; r.BP = bufs.BP; r.X = Xw; r.x_lane_stride = xls; r.x_row_off = (long long)row * n;
+                r.DX = (char *)D.DX.p + (size_t)s0 * n * ts; r.n = n;
                 if (pl.is_complex) krb_front_residual<true><<<grid, 256, 0, st>>>(r);
                 else krb_front_residual<false><<<grid, 256, 0, st>>>(r);
-                rc2 = front_solve(pl, make_params(pl, bufs, D.DX.p, n, 0), lanes, st);
+                rc2 = front_solve(pl, make_params(pl, bufs, r.DX, n, 0), sl, st);
                 if (pl.is_complex) krb_front_axpy<true><<<grid, 256, 0, st>>>(r);
                 else krb_front_axpy<false><<<grid, 256, 0, st>>>(r);
                 add_launches(3);
@@ -469,24 +499,41 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             marks.push_back({name, e});
         };
         mark("start");
-        if ((rc = stamp_and_factor(P0))) return rc;
-        mark("stamp+factor (first plan)");
-        if ((rc = rhs_and_solve(P0, 0))) return rc;
-        mark("rhs+solve row 0");
-        if (PS && rows > 1) {
-            if ((rc = stamp_and_factor(*PS))) return rc;
-            mark("stamp+factor (step plan)");
-            for (int r = 1; r < rows; r++) {
-                if ((rc = rhs_and_solve(*PS, r))) return rc;
-                if (r <= 2) mark("rhs+solve step");
-                if (n_state) {
-                    FrontTrapParams t{};
-                    t.elems = PS->fdev->elems; t.state_elems = PS->fdev->state_elems; t.n_state = n_state; t.n_elems = n_elems;
-                    t.EV = (const double *)D.EV.p; t.h_comp = PS->h_comp;
-                    t.Xnew = (const double *)X + (size_t)r * n; t.Xprev = (const double *)X + (size_t)(r - 1) * n; t.x_lane_stride = xls;
-                    t.ST = (double *)D.ST.p;
-                    krb_front_trap_state<<<dim3((unsigned)((n_state + 255) / 256), (unsigned)lanes), 256, 0, st>>>(t);
-                    add_launches(1);
+        if (!PS) {
+            // one-shot solves (DC sweep / OP lanes / AC): factor window by window, each window solved while its factors are hot
+            for (long long s0 = 0; s0 < lanes; s0 += window) {
+                const long long sl = std::min(window, lanes - s0);
+                if ((rc = stamp_and_factor(P0, D.LU.p, false, s0, sl))) return rc;
+                if ((rc = rhs_and_solve(P0, D.LU.p, false, s0, sl, 0))) return rc;
+            }
+            mark("stamp+factor+solve");
+        } else {
+            // transient: operating point (row 0) through the DC plan window by window, then the step plan's factors are built
+            // window by window into the resident store, then every step solves the whole chunk at once
+            for (long long s0 = 0; s0 < lanes; s0 += window) {
+                const long long sl = std::min(window, lanes - s0);
+                if ((rc = stamp_and_factor(P0, D.LU0.p, true, s0, sl))) return rc;
+                if ((rc = rhs_and_solve(P0, D.LU0.p, true, s0, sl, 0))) return rc;
+            }
+            mark("operating point (stamp+factor+solve)");
+            if (rows > 1) {
+                for (long long s0 = 0; s0 < lanes; s0 += window) {
+                    const long long sl = std::min(window, lanes - s0);
+                    if ((rc = stamp_and_factor(*PS, D.LU.p, false, s0, sl))) return rc;
+                }
+                mark("stamp+factor (step plan)");
+                for (int r = 1; r < rows; r++) {
+                    if ((rc = rhs_and_solve(*PS, D.LU.p, false, 0, lanes, r))) return rc;
+                    if (r <= 2) mark("rhs+solve step");
+                    if (n_state) {
+                        FrontTrapParams t{};
+                        t.elems = PS->fdev->elems; t.state_elems = PS->fdev->state_elems; t.n_state = n_state; t.n_elems = n_elems;
+                        t.EV = (const double *)D.EV.p; t.h_comp = PS->h_comp;
+                        t.Xnew = (const double *)X + (size_t)r * n; t.Xprev = (const double *)X + (size_t)(r - 1) * n; t.x_lane_stride = xls;
+                        t.ST = (double *)D.ST.p;
+                        krb_front_trap_state<<<dim3((unsigned)((n_state + 255) / 256), (unsigned)lanes), 256, 0, st>>>(t);
+                        add_launches(1);
+                    }
                 }
             }
         }

@@ -225,8 +225,8 @@ __device__ __forceinline__ void front_pivot_search(const T *col, int k, int p, i
 //   rank-nb update of the trailing block with 4 x 4 register tiles (each trailing element is read and written once per panel).
 // Fronts that fit are staged in shared memory whole (odd leading dimension: conflict-free column-per-thread access); larger
 // fronts live in the per-lane workspace (L2/HBM) and only the panel's L columns and U rows are copied to shared memory.
-template <bool CPLX>
-__global__ void __launch_bounds__(512) krb_front_factor(const FrontParams P) {
+template <bool CPLX, int R>   // R x R register tiles in the trailing update: 4 for the large classes, 2 (more resident CTAs) for small fronts
+__global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_factor(const FrontParams P) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
     extern __shared__ __align__(16) unsigned char front_smem[];
@@ -339,38 +339,38 @@ __global__ void __launch_bounds__(512) krb_front_factor(const FrontParams P) {
                 for (int k = 0; k < nb; k++) F[(kb + k) + (size_t)m * (kb + nb + j)] = Up[k + ldu * j];
         }
         __syncthreads();
-        // trailing block C(i, j) -= sum_k Lp(nb + i, k) Up(k, j), 4 x 4 register tiles, C loaded before the k loop
+        // trailing block C(i, j) -= sum_k Lp(nb + i, k) Up(k, j), R x R register tiles, C loaded before the k loop
         {
             T *C = F + (kb + nb) + (size_t)ldf * (kb + nb);
             const T *Lt = Lp + nb;
-            for (int j0 = 0; j0 < tw; j0 += 4 * TY)
-                for (int i0 = 0; i0 < tw; i0 += 4 * TX) {
-                    int ii[4], jj[4];
+            for (int j0 = 0; j0 < tw; j0 += R * TY)
+                for (int i0 = 0; i0 < tw; i0 += R * TX) {
+                    int ii[R], jj[R];
 #pragma unroll
-                    for (int a = 0; a < 4; a++) { ii[a] = i0 + tx + a * TX; jj[a] = j0 + ty + a * TY; }
+                    for (int a = 0; a < R; a++) { ii[a] = i0 + tx + a * TX; jj[a] = j0 + ty + a * TY; }
                     if (ii[0] >= tw || jj[0] >= tw) continue;
-                    T c[4][4];
+                    T c[R][R];
 #pragma unroll
-                    for (int b = 0; b < 4; b++)
+                    for (int b = 0; b < R; b++)
 #pragma unroll
-                        for (int a = 0; a < 4; a++) c[a][b] = (ii[a] < tw && jj[b] < tw) ? C[ii[a] + (size_t)ldf * jj[b]] : S::zero();
+                        for (int a = 0; a < R; a++) c[a][b] = (ii[a] < tw && jj[b] < tw) ? C[ii[a] + (size_t)ldf * jj[b]] : S::zero();
                     // clamp the indices of partial tiles (their results are discarded) so the inner loop is branch-free
-                    int il[4], jl[4];
+                    int il[R], jl[R];
 #pragma unroll
-                    for (int a = 0; a < 4; a++) { il[a] = ii[a] < tw ? ii[a] : ii[0]; jl[a] = jj[a] < tw ? jj[a] : jj[0]; }
+                    for (int a = 0; a < R; a++) { il[a] = ii[a] < tw ? ii[a] : ii[0]; jl[a] = jj[a] < tw ? jj[a] : jj[0]; }
                     for (int k = 0; k < nb; k++) {
-                        T l[4], u[4];
+                        T l[R], u[R];
 #pragma unroll
-                        for (int a = 0; a < 4; a++) { l[a] = Lt[il[a] + (size_t)ldl * k]; u[a] = Up[k + (size_t)ldu * jl[a]]; }
+                        for (int a = 0; a < R; a++) { l[a] = Lt[il[a] + (size_t)ldl * k]; u[a] = Up[k + (size_t)ldu * jl[a]]; }
 #pragma unroll
-                        for (int b = 0; b < 4; b++)
+                        for (int b = 0; b < R; b++)
 #pragma unroll
-                            for (int a = 0; a < 4; a++) c[a][b] = S::fnma(c[a][b], l[a], u[b]);
+                            for (int a = 0; a < R; a++) c[a][b] = S::fnma(c[a][b], l[a], u[b]);
                     }
 #pragma unroll
-                    for (int b = 0; b < 4; b++)
+                    for (int b = 0; b < R; b++)
 #pragma unroll
-                        for (int a = 0; a < 4; a++)
+                        for (int a = 0; a < R; a++)
                             if (ii[a] < tw && jj[b] < tw) C[ii[a] + (size_t)ldf * jj[b]] = c[a][b];
                 }
         }
@@ -479,15 +479,17 @@ __global__ void krb_front_forward(const FrontParams P) {
         const int nbk = (p - kb) < 32 ? (p - kb) : 32;
         if (tid < 32) {
             // unit-lower diagonal block: lane t owns row kb + t; its entries left of the diagonal are loaded first
-            T lrow[32];
             const T *Lr = L + (kb + tid) + (size_t)m * kb;
-#pragma unroll
-            for (int k = 0; k < 32; k++) lrow[k] = (k < tid && tid < nbk) ? Lr[(size_t)m * k] : S::zero();
             T val = tid < nbk ? w[kb + tid] : S::zero();
+            for (int k0 = 0; k0 < nbk; k0 += 8) {
+                T lrow[8];
 #pragma unroll
-            for (int k = 0; k < 32; k++) {
-                const T yk = front_shfl(val, k);
-                if (k < tid) val = S::fnma(val, lrow[k], yk);
+                for (int k = 0; k < 8; k++) lrow[k] = (k0 + k < tid && tid < nbk) ? Lr[(size_t)m * (k0 + k)] : S::zero();
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const T yk = front_shfl(val, k0 + k);
+                    if (k0 + k < tid) val = S::fnma(val, lrow[k], yk);
+                }
             }
             if (tid < nbk) w[kb + tid] = val;
         }
@@ -495,7 +497,15 @@ __global__ void krb_front_forward(const FrontParams P) {
         for (int i = kb + nbk + tid; i < m; i += NT) {
             T acc = w[i];
             const T *Lr = L + i + (size_t)m * kb;
-            for (int k = 0; k < nbk; k++) acc = S::fnma(acc, Lr[(size_t)m * k], w[kb + k]);
+            int k0 = 0;
+            for (; k0 + 8 <= nbk; k0 += 8) {   // 8 loads in flight before the dependent chain
+                T lv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) lv[k] = Lr[(size_t)m * (k0 + k)];
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc = S::fnma(acc, lv[k], w[kb + k0 + k]);
+            }
+            for (; k0 < nbk; k0++) acc = S::fnma(acc, Lr[(size_t)m * k0], w[kb + k0]);
             w[i] = acc;
         }
         front_sync<WARP>();
@@ -547,16 +557,18 @@ __global__ void krb_front_backward(const FrontParams P) {
         const int nbk = (p - kb) < 32 ? (p - kb) : 32;
         if (tid < 32) {
             // upper-triangular diagonal block (reciprocal pivots on the diagonal): lane t owns row kb + t
-            T urow[32];
             const T *Ur = L + (kb + tid) + (size_t)m * kb;
-#pragma unroll
-            for (int k = 0; k < 32; k++) urow[k] = (k >= tid && k < nbk) ? Ur[(size_t)m * k] : S::zero();
             T val = tid < nbk ? w[kb + tid] : S::zero();
+            for (int k0 = ((nbk - 1) / 8) * 8; k0 >= 0; k0 -= 8) {
+                T urow[8];
 #pragma unroll
-            for (int k = 31; k >= 0; k--) {
-                if (k == tid) val = S::mul(val, urow[k]);        // x_k = rhs_k / pivot_k
-                const T xk = front_shfl(val, k);
-                if (k > tid) val = S::fnma(val, urow[k], xk);
+                for (int k = 0; k < 8; k++) urow[k] = (k0 + k >= tid && k0 + k < nbk) ? Ur[(size_t)m * (k0 + k)] : S::zero();
+#pragma unroll
+                for (int k = 7; k >= 0; k--) {
+                    if (k0 + k == tid) val = S::mul(val, urow[k]);        // x_k = rhs_k / pivot_k
+                    const T xk = front_shfl(val, k0 + k);
+                    if (k0 + k > tid) val = S::fnma(val, urow[k], xk);
+                }
             }
             if (tid < nbk) w[kb + tid] = val;
         }
@@ -564,7 +576,15 @@ __global__ void krb_front_backward(const FrontParams P) {
         for (int i = tid; i < kb; i += NT) {
             T acc = w[i];
             const T *Ur = L + i + (size_t)m * kb;
-            for (int k = 0; k < nbk; k++) acc = S::fnma(acc, Ur[(size_t)m * k], w[kb + k]);
+            int k0 = 0;
+            for (; k0 + 8 <= nbk; k0 += 8) {
+                T uv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) uv[k] = Ur[(size_t)m * (k0 + k)];
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc = S::fnma(acc, uv[k], w[kb + k0 + k]);
+            }
+            for (; k0 < nbk; k0++) acc = S::fnma(acc, Ur[(size_t)m * k0], w[kb + k0]);
             w[i] = acc;
         }
         front_sync<WARP>();

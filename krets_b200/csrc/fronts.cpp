@@ -7,6 +7,7 @@
 // to the parent as a contribution block.  Fronts of one level of the tree are independent and are factorised by one launch.
 #include <algorithm>
 #include <cassert>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "plan.hpp"
@@ -102,6 +103,8 @@ void build_front_plan(const Pattern &P, const std::vector<int> &match_row, const
     std::vector<int> sn_parent(ns, -1);
     for (int s = 0; s < ns; s++) { const int pk = parent[sn_last[s]]; sn_parent[s] = pk >= 0 ? sn_of[pk] : -1; }
     // ---- relaxed amalgamation (CHOLMOD-style thresholds): merge a child into its parent when the explicit zeros stay small ----
+    int relax_p = 16;
+    if (const char *e = getenv("KRB_FRONT_RELAX")) relax_p = std::max(1, atoi(e));
     struct SN { std::vector<int> piv; int q; int64_t zeros; bool alive; std::vector<int> kids; };
     std::vector<SN> sn(ns);
     for (int s = 0; s < ns; s++) {
@@ -129,10 +132,12 @@ void build_front_plan(const Pattern &P, const std::vector<int> &match_row, const
             const int64_t size_tot = stored(p_new, me.q);
             const double frac = size_tot > 0 ? (double)z_tot / (double)size_tot : 0.0;
             bool merge = false;
+            // every front costs a CTA (or warp) with a fixed chain of dependent global accesses, so small fronts are merged
+            // generously; larger ones only when the explicit zeros stay a small fraction of the stored block
             if (z_new == 0) merge = true;
-            else if (p_new <= 4) merge = true;
-            else if (p_new <= 16) merge = frac < 0.8;
-            else if (p_new <= 48) merge = frac < 0.1;
+            else if (p_new <= relax_p / 4) merge = true;
+            else if (p_new <= relax_p) merge = frac < 0.8;
+            else if (p_new <= 3 * relax_p) merge = frac < 0.1;
             else merge = frac < 0.05;
             if (merge) {
                 merged_piv.push_back(ch.piv);

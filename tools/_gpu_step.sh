@@ -1,3 +1,4 @@
-python -m pytest tests/test_gpu_front.py -x -q 2>&1 | tail -15
+python -m pytest tests/test_gpu_front.py -x -q 2>&1 | tail -3
 export KRB_FRONT_DEBUG=1
-python tools/measure_mesh.py --grid 224 --lanes 128 --steps 4 --modes tran,ac --reps 1 2>&1 | tail -16
+python tools/measure_mesh.py --grid 224 --lanes 768 --steps 4 --modes tran --reps 1 2>&1 | tail -7
+python tools/measure_mesh.py --grid 224 --lanes 512 --modes ac --reps 1 2>&1 | tail -3
