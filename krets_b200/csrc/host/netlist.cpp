@@ -151,12 +151,177 @@ int parse_value(const std::string &token, double &out) {
     return 0;
 }
 
+
+namespace {
+// x<name> n1 n2 ... <definition>   (subcircuit.rs:147-172)
+struct SubcktInstance { std::string instance_name, definition_name; std::vector<std::string> nodes; };
+struct DefElement { bool is_instance = false; ParsedElement e; SubcktInstance inst; };
+struct SubcktDefinition { std::vector<std::string> pins; std::vector<DefElement> elements; };
+
+// One element line.  Returns PARSE_OK / PARSE_ERROR / PARSE_UNSUPPORTED.
+int parse_element_line(const std::string &line, DefElement &de) {
+    ParsedElement &e = de.e;
+    // element line: the reference tries R, C, L, V, I, D, BJT, NMOS, subckt in that order (elements.rs:45-55);
+    // each alternative is keyed by its leading tag, so dispatching on it is equivalent
+    e.pod.ip = e.pod.im = e.pod.ic = -1;
+    e.pod.n = 1.0; e.pod.is = 1e-12;
+    Cursor c(line);
+    const char c0 = (char)std::toupper((unsigned char)line[0]);
+    bool ok = false;
+    auto rcli = [&](int kind, char letter) {
+        ++c.i;
+        e.identifier = std::string(1, letter);
+        e.pod.kind = kind;
+        return two_node_head(c, e) && c.space1() && c.value(e.pod.value);
+    };
+    if (c0 == 'R') ok = rcli(KRB_R, 'R');
+    else if (c0 == 'C') {
+        ok = rcli(KRB_C, 'C');
+        if (ok) { Cursor t = c; if (t.space1() && t.tag_no_case("G2")) e.pod.flags |= KRB_ELEM_FLAG_G2; }   // capacitor.rs:31
+    } else if (c0 == 'L') ok = rcli(KRB_L, 'L');
+    else if (c0 == 'I') ok = rcli(KRB_I, 'I');
+    else if (c0 == 'V') {                                                        // voltage_source.rs:188-235
+        ++c.i;
+        e.identifier = "V";
+        e.pod.kind = KRB_V;
+        ok = two_node_head(c, e);
+        if (ok) {
+            double dc = 0.0, v;
+            { Cursor t = c; if (t.space1() && t.nom_double(v)) { dc = v; c.i = t.i; } }
+            for (;;) {
+                Cursor t = c;
+                if (!t.space1()) break;
+                Cursor k = t;
+                if (k.tag_no_case("dc") && k.space1() && k.nom_double(v)) { dc = v; c.i = k.i; continue; }
+                k.i = t.i;
+                if (k.tag_no_case("ac") && k.space1() && k.nom_double(v)) { e.pod.ac_amplitude = v; c.i = k.i; continue; }
+                k.i = t.i;
+                double w[7] = {0, 0, 0, 0, 0, 0, 0};
+                if (k.tag_no_case("pulse") && paren_values(k, w, 7)) { e.pod.waveform = KRB_WAVE_PULSE; std::copy(w, w + 7, e.pod.wave); c.i = k.i; continue; }
+                k.i = t.i;
+                if (k.tag_no_case("sin") && paren_values(k, w, 6)) {
+                    // a later SIN does not displace an earlier PULSE: transient_value_at prefers pulse (voltage_source.rs:245-249)
+                    if (e.pod.waveform != KRB_WAVE_PULSE) { e.pod.waveform = KRB_WAVE_SIN; std::copy(w, w + 6, e.pod.wave); }
+                    c.i = k.i;
+                    continue;
+                }
+                break;
+            }
+            e.pod.value = dc;
+        }
+    } else if (c0 == 'D') {                                                      // diode.rs:74-92
+        ++c.i;
+        e.identifier = "D";
+        e.pod.kind = KRB_D;
+        ok = two_node_head(c, e);
+        e.model_name = "default";
+        if (ok) { Cursor t = c; std::string m; if (t.space1() && t.ident(m)) e.model_name = m; }
+    } else if (c0 == 'M' && line.size() > 1 && std::toupper((unsigned char)line[1]) == 'N') {   // nmosfet.rs:113-166
+        c.i = 2;
+        e.identifier = "M";
+        e.pod.kind = KRB_NMOS;
+        std::string name, bulk;
+        ok = c.ident(name) && c.space1() && c.ident(e.nodes[0]) && c.space1() && c.ident(e.nodes[1]) && c.space1() && c.ident(e.nodes[2]) &&
+             c.space1() && c.ident(bulk) && c.space1() && c.ident(e.model_name);
+        e.identifier += name;
+    } else if (c0 == 'X') {                                                      // subcircuit.rs:147-172
+        ++c.i;
+        SubcktInstance &si = de.inst;
+        if (!c.ident(si.instance_name)) return PARSE_ERROR;
+        std::vector<std::string> toks;
+        for (;;) { Cursor t = c; std::string tok; if (!t.space1() || !t.ident(tok)) break; toks.push_back(tok); c.i = t.i; }
+        if (toks.empty()) return PARSE_ERROR;
+        si.definition_name = toks.back();
+        toks.pop_back();
+        si.nodes = toks;
+        de.is_instance = true;
+        return PARSE_OK;
+    } else if (c0 == 'Q') {
+        return PARSE_UNSUPPORTED;                                                  // BJT: todo!() in the reference's stamps
+    }
+    return ok ? PARSE_OK : PARSE_ERROR;
+}
+
+// subcircuit.rs:85-116: map the nodes through the pin list (internal nodes get "<instance>_" in front — including a "0"
+// that is not a pin, as in the reference) and prefix the element name
+void map_sub_element(DefElement &de, const std::unordered_map<std::string, std::string> &port_to_node, const std::string &parent) {
+    auto map_node = [&](std::string &node) {
+        auto it = port_to_node.find(node);
+        node = it != port_to_node.end() ? it->second : parent + "_" + node;
+    };
+    if (de.is_instance) {
+        for (auto &nd : de.inst.nodes) map_node(nd);
+        de.inst.instance_name = parent + "_" + de.inst.instance_name;
+    } else {
+        const int nn = de.e.pod.kind == KRB_NMOS ? 3 : 2;
+        for (int k = 0; k < nn; k++) map_node(de.e.nodes[k]);
+        de.e.identifier = de.e.identifier.substr(0, 1) + parent + "_" + de.e.identifier.substr(1);   // identifier = letter + name
+    }
+}
+
+// subcircuit.rs:33-82
+int instantiate(const SubcktInstance &inst, const std::unordered_map<std::string, SubcktDefinition> &defs, std::vector<ParsedElement> &out,
+                std::string &err, int depth) {
+    if (depth > 64) { err = "subcircuit nesting deeper than 64 levels (recursive definition?)"; return PARSE_ERROR; }
+    auto it = defs.find(inst.definition_name);
+    if (it == defs.end()) { err = "Undefined subcircuit definition: " + inst.definition_name; return PARSE_ERROR; }
+    const SubcktDefinition &def = it->second;
+    if (inst.nodes.size() != def.pins.size()) {
+        err = "Node/port mismatch for instance " + inst.instance_name + ": expected " + std::to_string(def.pins.size()) + ", got " + std::to_string(inst.nodes.size());
+        return PARSE_ERROR;
+    }
+    std::unordered_map<std::string, std::string> port_to_node;
+    for (size_t k = 0; k < def.pins.size(); k++) port_to_node[def.pins[k]] = inst.nodes[k];   // later duplicates win, as HashMap::collect
+    for (const DefElement &sub : def.elements) {
+        DefElement mapped = sub;
+        map_sub_element(mapped, port_to_node, inst.instance_name);
+        if (mapped.is_instance) {
+            const int rc = instantiate(mapped.inst, defs, out, err, depth + 1);
+            if (rc) return rc;
+        } else out.push_back(mapped.e);
+    }
+    return PARSE_OK;
+}
+}  // namespace
+
 int parse_circuit_description(const std::string &text, ParsedCircuit &out, std::string &err) {
     out = ParsedCircuit();
     std::unordered_map<std::string, ModelCard> models;
     bool in_control = false, in_subckt = false;
     size_t pos = 0;
     int lineno = 0;
+    // ---- pre-pass: subcircuit definitions (subcircuit.rs:174-218) ----
+    std::unordered_map<std::string, SubcktDefinition> subckts;
+    {
+        std::string current;
+        bool inside = false;
+        size_t q = 0;
+        while (q < text.size()) {
+            size_t eol = text.find('\n', q);
+            const std::string line = trim(text.substr(q, eol == std::string::npos ? std::string::npos : eol - q));
+            q = eol == std::string::npos ? text.size() : eol + 1;
+            if (line.empty() || line[0] == '%' || line[0] == '*') continue;
+            if (starts_with_nc(line, ".subckt")) {
+                Cursor c(line);
+                c.i = 7;
+                std::string name;
+                if (!c.space1() || !c.ident(name)) { err = "Failed to parse subcircuit header: " + line; return PARSE_ERROR; }
+                SubcktDefinition def;
+                for (;;) { Cursor t = c; std::string pin; if (!t.space1() || !t.ident(pin)) break; def.pins.push_back(pin); c.i = t.i; }
+                subckts[name] = def;
+                current = name;
+                inside = true;
+                continue;
+            }
+            if (starts_with_nc(line, ".ends")) { inside = false; current.clear(); continue; }
+            if (inside) {
+                DefElement de;
+                const int prc = parse_element_line(line, de);
+                if (prc) { err = "Failed to parse subcircuit element in '" + current + "': " + line; return prc; }
+                subckts[current].elements.push_back(de);
+            }
+        }
+    }
     auto fail = [&](int code, const std::string &line) {
         err = "Parse error on line " + std::to_string(lineno) + ": " + line;
         return code;
@@ -206,75 +371,14 @@ int parse_circuit_description(const std::string &text, ParsedCircuit &out, std::
             models[name] = m;
             continue;
         }
-        // element line: the reference tries R, C, L, V, I, D, BJT, NMOS, subckt in that order (elements.rs:45-55);
-        // each alternative is keyed by its leading tag, so dispatching on it is equivalent
-        ParsedElement e;
-        e.pod.ip = e.pod.im = e.pod.ic = -1;
-        e.pod.n = 1.0; e.pod.is = 1e-12;
-        Cursor c(line);
-        const char c0 = (char)std::toupper((unsigned char)line[0]);
-        bool ok = false;
-        auto rcli = [&](int kind, char letter) {
-            ++c.i;
-            e.identifier = std::string(1, letter);
-            e.pod.kind = kind;
-            return two_node_head(c, e) && c.space1() && c.value(e.pod.value);
-        };
-        if (c0 == 'R') ok = rcli(KRB_R, 'R');
-        else if (c0 == 'C') {
-            ok = rcli(KRB_C, 'C');
-            if (ok) { Cursor t = c; if (t.space1() && t.tag_no_case("G2")) e.pod.flags |= KRB_ELEM_FLAG_G2; }   // capacitor.rs:31
-        } else if (c0 == 'L') ok = rcli(KRB_L, 'L');
-        else if (c0 == 'I') ok = rcli(KRB_I, 'I');
-        else if (c0 == 'V') {                                                        // voltage_source.rs:188-235
-            ++c.i;
-            e.identifier = "V";
-            e.pod.kind = KRB_V;
-            ok = two_node_head(c, e);
-            if (ok) {
-                double dc = 0.0, v;
-                { Cursor t = c; if (t.space1() && t.nom_double(v)) { dc = v; c.i = t.i; } }
-                for (;;) {
-                    Cursor t = c;
-                    if (!t.space1()) break;
-                    Cursor k = t;
-                    if (k.tag_no_case("dc") && k.space1() && k.nom_double(v)) { dc = v; c.i = k.i; continue; }
-                    k.i = t.i;
-                    if (k.tag_no_case("ac") && k.space1() && k.nom_double(v)) { e.pod.ac_amplitude = v; c.i = k.i; continue; }
-                    k.i = t.i;
-                    double w[7] = {0, 0, 0, 0, 0, 0, 0};
-                    if (k.tag_no_case("pulse") && paren_values(k, w, 7)) { e.pod.waveform = KRB_WAVE_PULSE; std::copy(w, w + 7, e.pod.wave); c.i = k.i; continue; }
-                    k.i = t.i;
-                    if (k.tag_no_case("sin") && paren_values(k, w, 6)) {
-                        // a later SIN does not displace an earlier PULSE: transient_value_at prefers pulse (voltage_source.rs:245-249)
-                        if (e.pod.waveform != KRB_WAVE_PULSE) { e.pod.waveform = KRB_WAVE_SIN; std::copy(w, w + 6, e.pod.wave); }
-                        c.i = k.i;
-                        continue;
-                    }
-                    break;
-                }
-                e.pod.value = dc;
-            }
-        } else if (c0 == 'D') {                                                      // diode.rs:74-92
-            ++c.i;
-            e.identifier = "D";
-            e.pod.kind = KRB_D;
-            ok = two_node_head(c, e);
-            e.model_name = "default";
-            if (ok) { Cursor t = c; std::string m; if (t.space1() && t.ident(m)) e.model_name = m; }
-        } else if (c0 == 'M' && line.size() > 1 && std::toupper((unsigned char)line[1]) == 'N') {   // nmosfet.rs:113-166
-            c.i = 2;
-            e.identifier = "M";
-            e.pod.kind = KRB_NMOS;
-            std::string name, bulk;
-            ok = c.ident(name) && c.space1() && c.ident(e.nodes[0]) && c.space1() && c.ident(e.nodes[1]) && c.space1() && c.ident(e.nodes[2]) &&
-                 c.space1() && c.ident(bulk) && c.space1() && c.ident(e.model_name);
-            e.identifier += name;
-        } else if (c0 == 'Q' || c0 == 'X') {
-            return fail(PARSE_UNSUPPORTED, line);
-        }
-        if (!ok) return fail(PARSE_ERROR, line);
-        out.elements.push_back(e);
+        DefElement de;
+        const int prc = parse_element_line(line, de);
+        if (prc) return fail(prc, line);
+        if (de.is_instance) {                                                          // parser.rs:93-98
+            std::string ierr;
+            const int irc = instantiate(de.inst, subckts, out.elements, ierr, 0);
+            if (irc) { err = ierr; return irc; }
+        } else out.elements.push_back(de.e);
     }
     // ---- index map: parser.rs:105-125 ----
     std::unordered_set<std::string> seen_nodes;

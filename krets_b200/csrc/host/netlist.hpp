@@ -1,6 +1,6 @@
 // Host-side front end (the role krets-parser plays for the solver): netlist text -> element table + MNA index map.
 // Only what the solver hot path needs: R/C/L/V/I/D/MN element lines, .model D/NMOS,
-// comment / .control / .subckt skipping, the index assignment of parser.rs:105-125, and the AC frequency grids of
+// comment / .control skipping, .subckt definitions and instance flattening (subcircuit.rs), the index assignment of parser.rs:105-125, and the AC frequency grids of
 // analyses.rs:80-158.
 #pragma once
 #include <cstdint>
@@ -16,7 +16,7 @@ enum ParseStatus {
     PARSE_OK = 0,
     PARSE_ERROR = 30,          // krets_parser::Error::ParseError / InvalidFormat
     PARSE_EMPTY_NETLIST = 31,  // krets_parser::Error::EmptyNetlist
-    PARSE_UNSUPPORTED = 32,    // BJT / subcircuit instances: outside the restated subset
+    PARSE_UNSUPPORTED = 32,    // BJT: outside the restated subset (the reference's stamps are todo!())
     PARSE_MISSING_MODEL = 33,  // reference: todo!() at parser.rs:138,146
     PARSE_IO = 34
 };

@@ -350,3 +350,108 @@ def test_program_transient_extensions(oracle, golden, integ):
         X[:1, : kc.n] = Emulator(pdc, 1, rows=1).run(np.zeros((0, 1)))
         X = em.run(np.zeros((0, 1)), X=X, row_begin=1, guess_empty_at_iter0=False, pseudo_time=True)
         assert_close(X[:, : kc.n, 0], ref, rtol=1e-7 if key == "rectifier" else 1e-9, what=f"{key} integrator {integ}")
+
+
+# ---- f3: subcircuit flattening (krets-parser/src/elements/subcircuit.rs:33-116, parser.rs:93-98) ---------------------
+SUBCKT_FIXTURE = """* circuits/voltage_divider/subckt/voltage_divider.cir
+xdiv1 10 7 0 vdivide
+.subckt vdivide 1 2 3
+r1 1 2 10K
+r2 2 3 5K
+.ends
+
+V1 1 0 dc 10
+.control
+op
+.endc
+"""
+SUBCKT_NESTED = """* crates/krets-parser/tests/test_parse_netlist.rs:78-102
+xdiv1 10 7 0 vdivide
+
+.subckt vdivide 1 2 3
+xr1 1 2 myresistor
+xr2 2 3 myresistor
+.ends
+
+.subckt myresistor plus minus
+r0 plus minus 1k
+.ends
+"""
+
+
+def _flatten_reference_way(text):
+    """Python restatement of SubcircuitInstance::instantiate + map_sub_element for two-terminal elements (test oracle)."""
+    defs, cur, top, control = {}, None, [], False
+    for raw in text.splitlines():
+        line = raw.strip()
+        if not line or line[0] in "%*":
+            continue
+        low = line.lower()
+        if low.startswith(".control") or low.startswith(".endc"):
+            control = low.startswith(".control")
+            continue
+        if control:
+            continue
+        if low.startswith(".subckt"):
+            tok = line.split()
+            cur = tok[1]
+            defs[cur] = (tok[2:], [])
+        elif low.startswith(".ends"):
+            cur = None
+        elif cur is not None:
+            defs[cur][1].append(line.split())
+        elif not low.startswith("."):
+            top.append(line.split())
+
+    def inst(name, nodes, dname):
+        pins, elems = defs[dname]
+        assert len(pins) == len(nodes)
+        m = dict(zip(pins, nodes))
+        out = []
+        for tok in elems:
+            if tok[0][0] in "xX":
+                out += inst(name + "_" + tok[0][1:], [m.get(t, name + "_" + t) for t in tok[1:-1]], tok[-1])
+            else:
+                out.append((tok[0][0].upper() + name + "_" + tok[0][1:], m.get(tok[1], name + "_" + tok[1]), m.get(tok[2], name + "_" + tok[2])))
+        return out
+
+    flat = []
+    for tok in top:
+        if tok[0][0] in "xX":
+            flat += inst(tok[0][1:], tok[1:-1], tok[-1])
+        else:
+            flat.append((tok[0][0].upper() + tok[0][1:], tok[1], tok[2]))
+    return flat
+
+
+@pytest.mark.parametrize("text,count", [(SUBCKT_FIXTURE, 3), (SUBCKT_NESTED, 2)])
+def test_subckt_flattening_matches_reference_rules(text, count):
+    circuit = kb.parse_circuit_description(text)
+    L = _lib.lib()
+    idents = [L.krh_circuit_element_identifier(circuit._h, e).decode() for e in range(circuit.num_elements)]
+    expect = _flatten_reference_way(text)
+    assert circuit.num_elements == count == len(expect)
+    assert idents == [e[0] for e in expect]
+    # index map: parser.rs:105-125 applied to the flattened element list
+    names, seen = [], set()
+    for ident, plus, minus in expect:
+        if ident[0] in "VLI":
+            names.append(f"I({ident})")
+        for node in (plus, minus):
+            if node not in seen:
+                seen.add(node)
+                if node != "0":
+                    names.append(f"V({node})")
+    assert circuit.names == names
+    for e, (ident, plus, minus) in enumerate(expect):
+        el = circuit.element(e)
+        assert el.ip == circuit.index_map.get(f"V({plus})", -1) and el.im == circuit.index_map.get(f"V({minus})", -1)
+
+
+def test_subckt_internal_ground_is_prefixed_and_errors():
+    # a "0" inside a definition that is not a pin becomes "<instance>_0" (map_sub_element, subcircuit.rs:96-103)
+    c = kb.parse_circuit_description("V1 in 0 1\nxa in out cell\n.subckt cell a b\nr1 a b 1k\nr2 b 0 2k\n.ends\n")
+    assert c.names == ["I(V1)", "V(in)", "V(out)", "V(a_0)"]
+    for bad in ("xa 1 2 nodef\nR1 1 0 1\n", "xa 1 cell\n.subckt cell a b\nr1 a b 1\n.ends\n", "xa 1 2 cell\n.subckt cell a b\nq1 a b c\n.ends\n"):
+        with pytest.raises(kb.KretsError):
+            kb.parse_circuit_description(bad)
