@@ -875,6 +875,34 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
     plan.alg_bytes_per_point = 8 * (int64_t)std::max(1, plan.n_inputs) + s * (4 * S.nnz_lu + 3 * (int64_t)n);
     plan.vm_hbm_bytes_per_point = plan.hbm_bytes_per_point;
     plan.use_chain = plan.chain.valid && plan.opts.exec != KRB_EXEC_LANE_VM;
+    // small linear transient plans are stepped by the native dense kernel (dense_tran_kernel.cuh) instead of the interpreter
+    plan.dense = DensePlan();
+    if (split && plan.opts.exec == KRB_EXEC_FUSED && n >= 1 && n <= 8 && plan.state_elems.size() <= 8 && plan.wave_elems.size() <= 4) {
+        DensePlan &dp = plan.dense;
+        std::vector<int> pos_of_col(n), pos_of_row(n);
+        for (int k = 0; k < n; k++) { pos_of_col[S.col_order[k]] = k; pos_of_row[S.row_order[k]] = k; }
+        auto pos = [&](int u) { return u >= 0 ? pos_of_col[u] : -1; };
+        dp.elems.resize(c.el.size());
+        for (size_t e = 0; e < c.el.size(); e++) {
+            DensePlan::Elem &de = dp.elems[e];
+            de.value = c.el[e].value; de.in_plane = B.input_of_elem[e];
+            de.pp = pos(c.el[e].ip); de.pm = pos(c.el[e].im); de.pc = pos(c.el[e].ic);
+            de.wave_col = -1; de.state_idx = -1;
+        }
+        for (size_t k = 0; k < plan.wave_elems.size(); k++) dp.elems[plan.wave_elems[k]].wave_col = (int)k;
+        for (size_t j = 0; j < plan.state_elems.size(); j++) dp.elems[plan.state_elems[j]].state_idx = (int)j;
+        bool ok = true;
+        for (const MatContrib &mc : plan.stamps.mat) {
+            if (mc.s.kind != S_ONE && mc.s.kind != S_G && mc.s.kind != S_VAL && mc.s.kind != S_VOH) ok = false;
+            dp.mat_terms.push_back({pos_of_row[mc.row], pos_of_col[mc.col], (int)mc.s.kind | (mc.s.neg ? 0x100 : 0), mc.s.elem});
+        }
+        for (const RhsContrib &rc : plan.stamps.rhs) {
+            const SrcKind kd = rc.s.kind;
+            if (kd != S_VAL && kd != S_WAVE && kd != S_CAP_HIST && kd != S_IND_HIST && kd != S_CAP_IPREV && kd != S_IND_VPREV) ok = false;
+            dp.rhs_terms.push_back({pos_of_row[rc.row], 0, (int)kd | (rc.s.neg ? 0x100 : 0), rc.s.elem});
+        }
+        dp.valid = ok;
+    }
     if (plan.use_chain) plan.hbm_bytes_per_point = s * (5 * (int64_t)n + 2 * plan.chain.n_u2) + 8 * (int64_t)plan.n_inputs;   // 2n(+) out, back, n results
     return KRB_OK;
 }

@@ -1,0 +1,199 @@
+// sm_100a kernel for the transient stepping of SMALL linear circuits (n <= 8): BASELINE config 4 is dual_rc_ladder, n = 4,
+// 10^4 steps x 16 384 Monte-Carlo lanes.  With so few lanes (512 warps on 592 warp schedulers) the run time is the length of
+// the dependent chain per step, so the per-step work must be native code, not interpreted lane-program ops:
+//
+//   once per lane : stamp the dense companion matrix (stampable.rs:442-468, 780-792, 972-980 ...), LU with the plan's static
+//                   pivots; turn the right-hand-side stamps (:470-505, :806-815, :1043-1048) into dense coefficient rows
+//                   b = H1 + Hx x_prev + Hs state + Hw sources(t)
+//   every step    : b (FMA rows), forward / backward substitution fully unrolled over compile-time N with the unknowns in
+//                   registers, trapezoidal capacitor currents, one coalesced store per unknown into the lane-interleaved
+//                   result planes X[row][unknown][lane] (the layout krb_pack_point_major delivers from).
+//
+// Coefficients live in per-thread shared-memory columns C[idx][tid] (conflict-free, static offsets after unrolling).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plan.hpp"
+
+namespace krb {
+
+struct DenseElem { double value; int in_plane, pp, pm, pc, wave_col, state_idx; };   // pp/pm/pc: pivot positions of V(plus), V(minus), I(ident) or -1
+struct DenseTerm { int k, l, kind, elem; };                                         // matrix: position (k, l); rhs: row k (l unused); kind = SrcKind | neg << 8
+
+struct DenseTranParams {
+    const DenseElem *elems;
+    const DenseTerm *mat_terms, *rhs_terms;
+    int n_mat, n_rhs;
+    const int *state_elems;      // [ns] element ordinals carrying a trapezoidal state
+    const int *col_order;        // position -> unknown
+    int n, ns, nw, width;        // width = n + ns result columns per row
+    const double *IN;            // [n_inputs][L]
+    const double *Bstep;         // [rows][2][nw] source table (iteration-0 entries are used: linear circuit)
+    double *X;                   // [rows][width][L]; with OUT set only row 0 (the operating point) is read from it
+    double *OUT;                 // optional: point-major delivery x[lane][row][unknown] straight from the kernel
+    long long out_lanes;         // lanes that own storage in OUT
+    long long L;
+    int rows;
+    double h_comp;
+    int *status;
+};
+
+// N unknowns, NSP / NWP = padded counts of trapezoidal state columns and source-table columns (zero coefficients beyond
+// ns / nw), all compile-time so that the step loop is straight-line code.  For N <= 4 every coefficient is copied from the
+// shared-memory columns into registers before the loop: a step is then ~60 instructions of FMA chain.
+template <int N, int NSP, int NWP, int TPB>
+__global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
+    extern __shared__ double dense_smem[];
+    const int tid = threadIdx.x;
+    const long long lane = (long long)blockIdx.x * TPB + tid;
+    const long long L = p.L;
+    const int ns = p.ns, nw = p.nw;
+    // per-thread columns: A[N*N] | Hx[N*N] | H1[N] | Hs[N*NSP] | Hw[N*NWP] | Gx[NSP*N]
+    constexpr int O_A = 0, O_HX = N * N, O_H1 = 2 * N * N, O_HS = O_H1 + N, O_HW = O_HS + N * NSP, O_GX = O_HW + N * NWP, TOTAL = O_GX + NSP * N;
+    double *C = dense_smem + tid;
+    for (int i = 0; i < TOTAL; i++) C[(size_t)i * TPB] = 0.0;
+    auto value_of = [&](const DenseElem &el) { return el.in_plane >= 0 ? p.IN[(size_t)el.in_plane * L + lane] : el.value; };
+
+    // ---- companion matrix in pivot order, summed in stamp order (== sum_triplets, solver.rs:59-70) ----
+    for (int t = 0; t < p.n_mat; t++) {
+        const DenseTerm tm = p.mat_terms[t];
+        const DenseElem el = p.elems[tm.elem];
+        const double v = value_of(el);
+        double c = 0.0;
+        switch (tm.kind & 0xff) {
+        case S_ONE: c = 1.0; break;
+        case S_G: c = __ddiv_rn(1.0, v); break;
+        case S_VAL: c = v; break;
+        case S_VOH: c = __ddiv_rn(v, p.h_comp); break;
+        default: break;
+        }
+        if (tm.kind & 0x100) c = -c;
+        C[(size_t)(O_A + tm.k * N + tm.l) * TPB] += c;
+    }
+    // ---- right-hand side as coefficient rows: b = H1 + Hx x_prev + Hs state + Hw sources(t) ----
+    for (int t = 0; t < p.n_rhs; t++) {
+        const DenseTerm tm = p.rhs_terms[t];
+        const DenseElem el = p.elems[tm.elem];
+        const double v = value_of(el);
+        const double sg = (tm.kind & 0x100) ? -1.0 : 1.0;
+        const int k = tm.k;
+        switch (tm.kind & 0xff) {
+        case S_VAL: C[(size_t)(O_H1 + k) * TPB] += sg * v; break;
+        case S_WAVE: C[(size_t)(O_HW + k * NWP + el.wave_col) * TPB] += sg; break;
+        case S_CAP_HIST: {                                   // (C/h) (v+_prev - v-_prev)
+            const double c = sg * __ddiv_rn(v, p.h_comp);
+            if (el.pp >= 0) C[(size_t)(O_HX + k * N + el.pp) * TPB] += c;
+            if (el.pm >= 0) C[(size_t)(O_HX + k * N + el.pm) * TPB] -= c;
+            break;
+        }
+        case S_IND_HIST: if (el.pc >= 0) C[(size_t)(O_HX + k * N + el.pc) * TPB] += sg * __ddiv_rn(v, p.h_comp); break;   // (L/h) i_prev
+        case S_CAP_IPREV: C[(size_t)(O_HS + k * NSP + el.state_idx) * TPB] += sg; break;
+        case S_IND_VPREV:
+            if (el.pp >= 0) C[(size_t)(O_HX + k * N + el.pp) * TPB] += sg;
+            if (el.pm >= 0) C[(size_t)(O_HX + k * N + el.pm) * TPB] -= sg;
+            break;
+        default: break;
+        }
+    }
+    // trapezoidal capacitor currents: i_n = (2C/h) ((v+ - v-)_n - (v+ - v-)_{n-1}) - i_{n-1}
+    for (int j = 0; j < ns; j++) {
+        const DenseElem el = p.elems[p.state_elems[j]];
+        const double g = __ddiv_rn(value_of(el), p.h_comp);
+        if (el.pp >= 0) C[(size_t)(O_GX + j * N + el.pp) * TPB] += g;
+        if (el.pm >= 0) C[(size_t)(O_GX + j * N + el.pm) * TPB] -= g;
+    }
+    // ---- LU with the static pivots (unit lower, reciprocal pivots on the diagonal) ----
+    bool bad = false, nonfinite = false;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        const double d = C[(size_t)(O_A + k * N + k) * TPB];
+        bad |= !(fabs(d) > 0.0) || !isfinite(d);
+        const double r = 1.0 / d;
+        C[(size_t)(O_A + k * N + k) * TPB] = r;
+#pragma unroll
+        for (int i = k + 1; i < N; i++) {
+            const double l = C[(size_t)(O_A + i * N + k) * TPB] * r;
+            C[(size_t)(O_A + i * N + k) * TPB] = l;
+#pragma unroll
+            for (int j = k + 1; j < N; j++)
+                C[(size_t)(O_A + i * N + j) * TPB] = fma(-l, C[(size_t)(O_A + k * N + j) * TPB], C[(size_t)(O_A + i * N + j) * TPB]);
+        }
+    }
+    constexpr bool REGS = (N <= 4);
+    double rc[REGS ? TOTAL : 1];
+    if (REGS) {
+#pragma unroll
+        for (int i = 0; i < TOTAL; i++) rc[REGS ? i : 0] = C[(size_t)i * TPB];
+    }
+#define KRB_DC(i) (REGS ? rc[REGS ? (i) : 0] : C[(size_t)(i) * TPB])
+    double x[N], st[NSP > 0 ? NSP : 1];
+    double *xp[N];                                                                           // store cursors, one per unknown
+    const bool direct = p.OUT != nullptr;
+    if (direct && lane >= p.out_lanes) return;                                               // padding lanes own no output
+#pragma unroll
+    for (int l = 0; l < N; l++) {
+        const int u = p.col_order[l];
+        x[l] = p.X[(size_t)u * L + lane];                                                    // row 0: the operating point
+        xp[l] = direct ? p.OUT + (size_t)lane * p.rows * p.n + u : p.X + (size_t)u * L + lane;
+        if (direct) *xp[l] = x[l];
+    }
+#pragma unroll
+    for (int j = 0; j < NSP; j++) st[j] = j < ns ? p.X[(size_t)(p.n + j) * L + lane] : 0.0;   // i_C(0)
+    const size_t row_stride = direct ? (size_t)p.n : (size_t)p.width * L;
+    double wv[NWP];
+#pragma unroll
+    for (int j = 0; j < NWP; j++) wv[j] = (j < nw && p.rows > 1) ? __ldg(p.Bstep + (size_t)2 * nw + j) : 0.0;
+
+    for (int row = 1; row < p.rows; row++) {
+        double wn[NWP];                                        // next step's sources: their load latency hides behind this step
+#pragma unroll
+        for (int j = 0; j < NWP; j++) wn[j] = (j < nw && row + 1 < p.rows) ? __ldg(p.Bstep + (size_t)(row + 1) * 2 * nw + j) : 0.0;
+        double b[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            double acc = KRB_DC(O_H1 + k);
+#pragma unroll
+            for (int l = 0; l < N; l++) acc = fma(KRB_DC(O_HX + k * N + l), x[l], acc);
+#pragma unroll
+            for (int j = 0; j < NSP; j++) acc = fma(KRB_DC(O_HS + k * NSP + j), st[j], acc);
+#pragma unroll
+            for (int j = 0; j < NWP; j++) acc = fma(KRB_DC(O_HW + k * NWP + j), wv[j], acc);
+            b[k] = acc;
+        }
+#pragma unroll
+        for (int k = 1; k < N; k++)
+#pragma unroll
+            for (int l = 0; l < k; l++) b[k] = fma(-KRB_DC(O_A + k * N + l), b[l], b[k]);
+        double xn[N];
+#pragma unroll
+        for (int k = N - 1; k >= 0; k--) {
+            double acc = b[k];
+#pragma unroll
+            for (int l = k + 1; l < N; l++) acc = fma(-KRB_DC(O_A + k * N + l), xn[l], acc);
+            xn[k] = acc * KRB_DC(O_A + k * N + k);
+        }
+#pragma unroll
+        for (int j = 0; j < NSP; j++) {
+            double acc = -st[j];
+#pragma unroll
+            for (int l = 0; l < N; l++) acc = fma(KRB_DC(O_GX + j * N + l), xn[l] - x[l], acc);
+            st[j] = acc;
+        }
+        double chk = 0.0;
+#pragma unroll
+        for (int l = 0; l < N; l++) {
+            xp[l] += row_stride;
+            *xp[l] = xn[l];
+            x[l] = xn[l];
+            chk += xn[l] * 0.0;                                // NaN iff any unknown is inf / NaN
+        }
+        nonfinite |= (chk != 0.0);
+#pragma unroll
+        for (int j = 0; j < NWP; j++) wv[j] = wn[j];
+    }
+#undef KRB_DC
+    if (bad || nonfinite) p.status[lane] |= (bad ? KRB_LANE_ZERO_PIVOT : 0) | (nonfinite ? KRB_LANE_NONFINITE : 0);
+}
+
+}  // namespace krb

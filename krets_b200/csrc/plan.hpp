@@ -132,6 +132,15 @@ struct FrontPlan {
 };
 void build_front_plan(const Pattern &p, const std::vector<int> &match_row, const std::vector<int> &order, FrontPlan &fp);
 
+// "dense transient" executor tables (dense_tran_kernel.cuh): small linear circuits (n <= 8) stepped natively
+struct DensePlan {
+    bool valid = false;
+    struct Elem { double value; int in_plane, pp, pm, pc, wave_col, state_idx; };
+    struct Term { int k, l, kind, elem; };
+    std::vector<Elem> elems;
+    std::vector<Term> mat_terms, rhs_terms;
+};
+
 struct Plan {
     Circuit circuit;
     DeviceState *dev = nullptr;        // device-side buffers, created lazily by the runtime
@@ -156,6 +165,7 @@ struct Plan {
     ChainPlan chain;                    // filled when the structure allows the native chain executor
     bool use_chain = false;             // executor selected for krb_solve_* (chain.valid and not forced to the lane VM)
     int64_t vm_hbm_bytes_per_point = 0;
+    DensePlan dense;                    // linear transient plans of small circuits: native stepping kernel
     FrontPlan front;                    // filled when the front executor is selected
     bool use_front = false;
     FrontDevice *fdev = nullptr;        // device tables of the front executor (front_exec.cu)

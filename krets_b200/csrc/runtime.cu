@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "chain_kernel.cuh"
+#include "dense_tran_kernel.cuh"
 #include "plan.hpp"
 #include "runtime.hpp"
 #include "vm_kernel.cuh"
@@ -69,6 +70,9 @@ struct DeviceState {
     int *chain_unknown = nullptr;
     int *chain_u2_rows = nullptr;
     uint32_t *chain_runs = nullptr;
+    DenseElem *dense_elems = nullptr;    // dense transient executor tables
+    DenseTerm *dense_mat = nullptr, *dense_rhs = nullptr;
+    int *dense_state = nullptr, *dense_col_order = nullptr;
     double *B = nullptr;                 // static constant pool (uploaded once: the plan owns a fixed copy of the circuit)
     Buf Bstep, IN, G, XOP, status, iters;
     Buf X[2], packed[2];                 // double-buffered for host delivery
@@ -114,6 +118,11 @@ void device_state_free(DeviceState *d) {
     if (d->chain_u2_rows) cudaFree(d->chain_u2_rows);
     if (d->chain_runs) cudaFree(d->chain_runs);
     if (d->B) cudaFree(d->B);
+    if (d->dense_elems) cudaFree(d->dense_elems);
+    if (d->dense_mat) cudaFree(d->dense_mat);
+    if (d->dense_rhs) cudaFree(d->dense_rhs);
+    if (d->dense_state) cudaFree(d->dense_state);
+    if (d->dense_col_order) cudaFree(d->dense_col_order);
     d->Bstep.release(); d->IN.release(); d->G.release(); d->XOP.release(); d->status.release(); d->iters.release();
     for (int i = 0; i < 2; i++) {
         d->X[i].release(); d->packed[i].release();
@@ -150,6 +159,14 @@ static int upload_plan(Plan &plan, DeviceState &d) {
         if ((rc = upload_vec(plan.chain.unknown_of_row, &d.chain_unknown))) return rc;
         if ((rc = upload_vec(plan.chain.u2_rows, &d.chain_u2_rows))) return rc;
         if ((rc = upload_vec(plan.chain.runs, &d.chain_runs))) return rc;
+    }
+    if (plan.dense.valid) {
+        static_assert(sizeof(DenseElem) == sizeof(DensePlan::Elem) && sizeof(DenseTerm) == sizeof(DensePlan::Term), "dense table layouts");
+        if ((rc = upload_vec(plan.dense.elems, (DensePlan::Elem **)&d.dense_elems))) return rc;
+        if ((rc = upload_vec(plan.dense.mat_terms, (DensePlan::Term **)&d.dense_mat))) return rc;
+        if ((rc = upload_vec(plan.dense.rhs_terms, (DensePlan::Term **)&d.dense_rhs))) return rc;
+        if ((rc = upload_vec(plan.state_elems, &d.dense_state))) return rc;
+        if ((rc = upload_vec(plan.sym.col_order, &d.dense_col_order))) return rc;
     }
     std::vector<double> pool;
     evaluate_pool(plan, plan.circuit, plan.h_comp, pool);
@@ -209,6 +226,43 @@ static int launch_chain(bool cplx, int tpb, bool direct, const ChainParams &p, l
     return direct ? launch_chain_d<true>(cplx, tpb, p, Lpad, st) : launch_chain_d<false>(cplx, tpb, p, Lpad, st);
 }
 
+template <int N, int NSP, int NWP>
+static int launch_dense_t(const DenseTranParams &p, long long Lpad, cudaStream_t st) {
+    constexpr int TPB = 32;
+    const size_t per_thread = (size_t)2 * N * N + N + (size_t)N * NSP + (size_t)N * NWP + (size_t)NSP * N;
+    const size_t smem = per_thread * TPB * 8;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(krb_dense_tran<N, NSP, NWP, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        configured = std::max<size_t>(smem, 48 * 1024);
+    }
+    krb_dense_tran<N, NSP, NWP, TPB><<<(unsigned)(Lpad / TPB), TPB, smem, st>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return KRB_OK;
+}
+template <int N>
+static int launch_dense_n(const DenseTranParams &p, long long Lpad, cudaStream_t st) {
+    // padded state / source counts: {0, 4, 8} x {1, 4}
+    const int nsp = p.ns == 0 ? 0 : p.ns <= 4 ? 4 : 8, nwp = p.nw <= 1 ? 1 : 4;
+    if (nsp == 0) return nwp == 1 ? launch_dense_t<N, 0, 1>(p, Lpad, st) : launch_dense_t<N, 0, 4>(p, Lpad, st);
+    if (nsp == 4) return nwp == 1 ? launch_dense_t<N, 4, 1>(p, Lpad, st) : launch_dense_t<N, 4, 4>(p, Lpad, st);
+    return nwp == 1 ? launch_dense_t<N, 8, 1>(p, Lpad, st) : launch_dense_t<N, 8, 4>(p, Lpad, st);
+}
+static int launch_dense(const DenseTranParams &p, long long Lpad, cudaStream_t st) {
+    switch (p.n) {
+    case 1: return launch_dense_n<1>(p, Lpad, st);
+    case 2: return launch_dense_n<2>(p, Lpad, st);
+    case 3: return launch_dense_n<3>(p, Lpad, st);
+    case 4: return launch_dense_n<4>(p, Lpad, st);
+    case 5: return launch_dense_n<5>(p, Lpad, st);
+    case 6: return launch_dense_n<6>(p, Lpad, st);
+    case 7: return launch_dense_n<7>(p, Lpad, st);
+    case 8: return launch_dense_n<8>(p, Lpad, st);
+    default: set_error("dense transient executor: n out of range"); return KRB_ERR_INTERNAL;
+    }
+}
+
 static int pick_tpb(const Plan &plan) {
     const int t = plan.opts.threads_per_block;
     if (t == 32 || t == 64 || t == 128) return t;
@@ -240,6 +294,9 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const bool out_dev = (a.memory == KRB_MEM_DEVICE);
     // the chain kernel can write point-major results itself when pivot row k is unknown k (no X staging, no pack kernel)
     const bool direct = chain && P0.chain.identity_order && a.layout == KRB_LAYOUT_POINT_MAJOR && rows == 1;
+    // the dense transient kernel delivers point-major rows itself: only the operating-point row is staged in planes
+    const bool dense_direct = PS && rows > 1 && PS->dense.valid && a.layout == KRB_LAYOUT_POINT_MAJOR && getenv("KRB_NO_DENSE_TRAN") == nullptr;
+    const int plane_rows = dense_direct ? 1 : rows;
 
     // ---- per-step source table (transient) ----
     if (PS) {
@@ -264,7 +321,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     // ---- chunking: bound the per-call device footprint ----
     const int planes0 = chain ? 2 * n + P0.chain.n_u2 : P0.n_planes, planesS = PS ? PS->n_planes : 0;
     const int nbuf = out_dev ? 1 : 2;
-    const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)rows * width * ts * (out_dev ? 1 : 4) +
+    const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)plane_rows * width * ts * (out_dev ? 1 : 2) + (out_dev ? 0 : (size_t)rows * width * ts * 2) +
                             (size_t)P0.n_inputs * 8 + (a.op_solution ? (size_t)n * 8 : 0) + 16;
     long long want = a.chunk_lanes > 0 ? a.chunk_lanes : (out_dev ? 65536 : 16384);
     want = std::min<long long>(want, ((a.lanes + tpb - 1) / tpb) * tpb);
@@ -283,7 +340,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if ((rc = D0.G.ensure(std::max<size_t>((size_t)planes0, 1) * chunk * ts))) return rc;
     if (PS && (rc = PS->dev->G.ensure(std::max<size_t>((size_t)planesS, 1) * chunk * ts))) return rc;
     for (int b = 0; b < nbuf; b++) {
-        if (!direct && (rc = D0.X[b].ensure((size_t)rows * width * chunk * ts))) return rc;
+        if (!direct && (rc = D0.X[b].ensure((size_t)plane_rows * width * chunk * ts))) return rc;
         if (!out_dev && (rc = D0.packed[b].ensure((size_t)rows * n * chunk * ts))) return rc;
     }
     if ((rc = D0.status.ensure((size_t)chunk * 4 * 2))) return rc;
@@ -378,7 +435,20 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             p.status = status_d; p.iters = iters_d;
             if (width > n) CUDA_TRY(cudaMemsetAsync((char *)D0.X[b].p + (size_t)n * Lpad * ts, 0, (size_t)(width - n) * Lpad * ts, st));   // i_C(0) = 0
             if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st))) return rc;
-            if (PS && rows > 1) {
+            if (PS && rows > 1 && PS->dense.valid && getenv("KRB_NO_DENSE_TRAN") == nullptr) {
+                // small linear circuit: native stepping kernel (row 0 = the operating point just written by the DC plan)
+                DeviceState &DS = *PS->dev;
+                DenseTranParams q{};
+                q.elems = DS.dense_elems; q.mat_terms = DS.dense_mat; q.rhs_terms = DS.dense_rhs;
+                q.n_mat = (int)PS->dense.mat_terms.size(); q.n_rhs = (int)PS->dense.rhs_terms.size();
+                q.state_elems = DS.dense_state; q.col_order = DS.dense_col_order;
+                q.n = n; q.ns = (int)PS->state_elems.size(); q.nw = (int)PS->wave_elems.size(); q.width = width;
+                q.IN = IN; q.Bstep = (const double *)DS.Bstep.p; q.X = (double *)D0.X[b].p; q.L = Lpad; q.rows = rows;
+                q.h_comp = PS->h_comp; q.status = status_d;
+                q.OUT = dense_direct ? (out_dev ? (double *)a.x_out + (size_t)lane0 * (size_t)rows * n : (double *)D0.packed[b].p) : nullptr;
+                q.out_lanes = lanes;
+                if ((rc = launch_dense(q, Lpad, st))) return rc;
+            } else if (PS && rows > 1) {
                 DeviceState &DS = *PS->dev;
                 VmParams q = p;
                 q.sec0 = DS.sec[0]; q.sec1 = DS.sec[1]; q.sec2 = DS.sec[2];
@@ -399,7 +469,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         // ---- delivery ----
         const size_t per_point = (size_t)rows * n;
         if (out_dev) {
-            if (direct) {
+            if (direct || dense_direct) {
                 // already delivered by the kernel
             } else if (a.layout == KRB_LAYOUT_POINT_MAJOR) {
                 void *dst = (char *)a.x_out + (size_t)lane0 * per_point * ts;
@@ -417,7 +487,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             if (a.iterations) CUDA_TRY(cudaMemcpyAsync(a.iterations + lane0, iters_d, (size_t)lanes * 4, cudaMemcpyDeviceToDevice, st));
         } else {
             cudaStream_t cs = D0.copy_stream;
-            if (a.layout == KRB_LAYOUT_POINT_MAJOR && !direct) {
+            if (a.layout == KRB_LAYOUT_POINT_MAJOR && !direct && !dense_direct) {
                 dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)rows), block(32, 8);
                 if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)D0.packed[b].p, rows, n, width, Lpad, lanes);
                 else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)D0.packed[b].p, rows, n, width, Lpad, lanes);

@@ -431,3 +431,53 @@ def test_op_with_subcircuits(oracle):
     assert_close(sol.array[0], oc.solve_op(), what="subcircuit OP")
     x = dict(zip(circuit.names, sol.array[0]))
     assert abs(x["V(7)"] - 10.0 * 5.0 / 15.0) < 1e-12 and abs(x["V(top_0)"] - x["V(7)"]) < 1e-12
+
+
+# ---- dense transient executor (n <= 8, linear): native stepping kernel vs the lane VM vs the oracle ------------------------
+@pytest.mark.parametrize("integ", [api.INTEGRATOR_BE_KRETS, api.INTEGRATOR_TRAP, api.INTEGRATOR_BE])
+def test_dense_transient_kernel_matches_lane_vm_and_oracle(oracle, golden, integ, monkeypatch):
+    import torch
+    circuit, oc = both(oracle, golden, "dual_rc_ladder")
+    names = ["R1", "R2", "C1", "C2"]
+    varied = [circuit.element_index(nm) for nm in names]
+    lanes, h, steps = 70, 5e-6, 400
+    vals = np.array([[circuit.element_value(e) * netgen.mc_factor(l, j, 4) for l in range(lanes)] for j, e in enumerate(varied)])
+    pdc = kb.Plan(circuit, api.MODE_DC, varied=varied)
+    ptr = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=h, integrator=integ)
+    out_dense, st = ptr.solve_transient(pdc, steps, lanes, varied_values=vals)                       # host buffers
+    assert not st.any()
+    dv = torch.from_numpy(vals).cuda()
+    out_dev, st_dev = ptr.solve_transient(pdc, steps, lanes, varied_values=dv)                       # device buffers, direct delivery
+    assert not st_dev.any().item() and np.array_equal(out_dev.cpu().numpy(), out_dense)
+    out_li, _ = ptr.solve_transient(pdc, steps, lanes, varied_values=vals, layout=api.LAYOUT_LANE_INTERLEAVED)
+    assert np.array_equal(np.transpose(out_li, (2, 0, 1)), out_dense)
+    monkeypatch.setenv("KRB_NO_DENSE_TRAN", "1")
+    pdc2 = kb.Plan(circuit, api.MODE_DC, varied=varied)
+    ptr2 = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=h, integrator=integ)
+    out_vm, st2 = ptr2.solve_transient(pdc2, steps, lanes, varied_values=vals)
+    assert not st2.any()
+    assert_close(out_dense, out_vm, rtol=1e-10, what="dense kernel vs lane VM")
+    for lane in (0, 1, lanes - 1):
+        for j, e in enumerate(varied):
+            oc.set_element_value(e, vals[j, lane])
+        _, ref = oc.solve_tran(h, steps * h, integrator=integ)
+        assert_close(out_dense[lane], ref, rtol=1e-9, what=f"dense transient integrator {integ} lane {lane}")
+
+
+def test_config4_full_size_properties(golden):
+    """BASELINE config 4 at full size (10^4 steps x 16 384 Monte-Carlo lanes): lane 0 is the nominal circuit, every lane settles to
+    the source's final value (RC ladder: V(out) -> V(in)), and the result is finite everywhere."""
+    import torch
+    circuit = kb.parse_circuit_description(golden["netlists"]["dual_rc_ladder"])
+    varied = [circuit.element_index(nm) for nm in ["R1", "R2", "C1", "C2"]]
+    lanes, steps = 16384, 10000
+    vals = np.array([[circuit.element_value(e) * netgen.mc_factor(l, j, 4) for l in range(lanes)] for j, e in enumerate(varied)])
+    pdc = kb.Plan(circuit, api.MODE_DC, varied=varied)
+    ptr = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=5e-6)
+    out, st = ptr.solve_transient(pdc, steps, lanes, varied_values=torch.from_numpy(vals).cuda())
+    assert not st.any().item() and bool(torch.isfinite(out).all().item())
+    nominal, _ = ptr.solve_transient(pdc, steps, 1, varied_values=torch.from_numpy(vals[:, :1].copy()).cuda())
+    assert torch.equal(out[0], nominal[0])
+    vin, vout = circuit.index_map["V(in)"], circuit.index_map["V(out)"]
+    final = out[:, -1, :]
+    assert float((final[:, vout] - final[:, vin]).abs().max().item()) < 1e-6 * float(final[:, vin].abs().max().item())

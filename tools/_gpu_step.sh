@@ -1,5 +1,2 @@
-set -x
-M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__occupancy_limit_registers,launch__occupancy_limit_shared_mem,launch__occupancy_limit_warps,launch__occupancy_limit_blocks,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,smsp__inst_executed.sum,lts__t_sector_hit_rate.pct,launch__grid_size,launch__block_size,launch__shared_mem_per_block_dynamic"
-timeout 900 ncu --metrics $M --clock-control none -k regex:krb_front_ -c 330 --csv --log-file gpurun_out/front_metrics_r1.csv python tools/measure_mesh.py --grid 224 --lanes 128 --modes ac --reps 1 > gpurun_out/front_metrics.log 2>&1
-tail -1 gpurun_out/front_metrics.log
-ls -la gpurun_out/
+python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+python tools/measure_configs.py 2>&1 | tail -2

@@ -78,7 +78,8 @@ def main():
                 "spill_planes": int(ptrap.info.spill_planes)})
     out.append({"config": 4, "what": f"dual_rc_ladder transient BE_KRETS, {nsteps} steps x {lanes} MC lanes (n=4, f64)", "ms": ms,
                 "points_per_s": pts / (ms * 1e-3), "executor": ptr.info.executor, "scratch_slots": int(ptr.info.scratch_slots),
-                "spill_planes": int(ptr.info.spill_planes), "note": "lane VM, factor values pinned on chip; latency bound (512 warps on 592 schedulers)"})
+                "spill_planes": int(ptr.info.spill_planes), "kernel_ms": kb.last_kernel_ms(),
+                "note": "steps by krb_dense_tran<4> (native, unknowns in registers) unless KRB_NO_DENSE_TRAN is set (lane VM)"})
     for o in out:
         print(json.dumps(o))
 
