@@ -465,8 +465,9 @@ def test_dense_transient_kernel_matches_lane_vm_and_oracle(oracle, golden, integ
 
 
 def test_config4_full_size_properties(golden):
-    """BASELINE config 4 at full size (10^4 steps x 16 384 Monte-Carlo lanes): lane 0 is the nominal circuit, every lane settles to
-    the source's final value (RC ladder: V(out) -> V(in)), and the result is finite everywhere."""
+    """BASELINE config 4 at full size (10^4 steps x 16 384 Monte-Carlo lanes): lane 0 is the nominal circuit; every lane is a
+    passive RC ladder driven by a 0 -> 1 V step, so V(out) rises monotonically (backward Euler is monotone here), stays below
+    V(in) = 1 V and is within 2 % of it after 50 ms (tau ~ 10 ms +- 10 %); the result is finite everywhere."""
     import torch
     circuit = kb.parse_circuit_description(golden["netlists"]["dual_rc_ladder"])
     varied = [circuit.element_index(nm) for nm in ["R1", "R2", "C1", "C2"]]
@@ -480,4 +481,7 @@ def test_config4_full_size_properties(golden):
     assert torch.equal(out[0], nominal[0])
     vin, vout = circuit.index_map["V(in)"], circuit.index_map["V(out)"]
     final = out[:, -1, :]
-    assert float((final[:, vout] - final[:, vin]).abs().max().item()) < 1e-6 * float(final[:, vin].abs().max().item())
+    assert float((final[:, vin] - 1.0).abs().max().item()) < 1e-12
+    gap = final[:, vin] - final[:, vout]
+    assert float(gap.min().item()) > 0.0 and float(gap.max().item()) < 0.02
+    assert float((out[:, 1:, vout] - out[:, :-1, vout]).min().item()) >= -1e-13
