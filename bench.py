@@ -143,6 +143,142 @@ def run_reference(args):
     }))
 
 
+def run_other_workload(args):
+    """BASELINE configs 3, 4 and 5 under the same contract (device-resident, CUDA events, max over ranks, weak scaling: every
+    rank runs the same number of lanes on its own GPU, no data-path collective).  The headline stays config 2."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import netgen
+    import krets_b200 as kb
+    from krets_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, K = max(args.warmup, 3), args.steps
+    peak, peak_src = measured_peaks()
+    wl = args.workload
+    with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
+        golden = json.load(f)
+
+    def mc(circuit, varied, lanes, lane0):
+        """values[k][lane] = nominal * (0.95 + 0.10 u), u = (splitmix64(seed + n_elements*lane + element) >> 11) * 2^-53; lane 0 nominal
+        (same rule as tests/netgen.mc_factor, vectorised)."""
+        lane = np.arange(lane0, lane0 + lanes, dtype=np.uint64)[None, :]
+        e = np.asarray(varied, dtype=np.uint64)[:, None]
+        with np.errstate(over="ignore"):
+            x = np.uint64(0x6B72657473) + np.uint64(circuit.num_elements) * lane + e + np.uint64(0x9E3779B97F4A7C15)
+            z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+        f = 0.95 + 0.10 * ((z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53)
+        f[:, (lane[0] == 0)] = 1.0
+        nominal = np.array([circuit.element_value(int(k)) for k in varied])[:, None]
+        return nominal * f
+
+    extra = {}
+    if wl == "rc_ac":
+        circuit = kb.parse_circuit_description(netgen.rc_ladder(LADDER_N))
+        plan = kb.Plan(circuit, api.MODE_AC, nominal_frequency=1.0)
+        allf = kb.generate_frequencies("Decade", 125000, 1.0, 1e8)
+        lanes = args.lanes if args.lanes != LANES_PER_GPU else 131072
+        sel = torch.from_numpy(allf[(rank * lanes) % len(allf):][:lanes].copy()).cuda()
+        lanes = int(sel.shape[0])
+        out = torch.empty((lanes, circuit.n), dtype=torch.complex128, device="cuda")
+        step = lambda: plan.solve_ac(sel, out=out)
+        points, dtype, s = lanes, "c64", 16
+        what = f"resistor_ladder_5000-class RC ladder AC sweep, {lanes} of {len(allf)} log-spaced frequencies per GPU (complex f64)"
+        bytes_pt, bytes_what = int(plan.info.alg_bytes_per_point), "P + s*(4*nnz_lu + 3*n), SURVEY 8(d)"
+        kernel = "krb_chain_kernel<c64>"
+    elif wl == "dual_rc_tran":
+        circuit = kb.parse_circuit_description(golden["netlists"]["dual_rc_ladder"])
+        varied = [circuit.element_index(nm) for nm in ["R1", "R2", "C1", "C2"]]
+        lanes = args.lanes if args.lanes != LANES_PER_GPU else 16384
+        nsteps = args.tran_steps or 10000
+        vals = torch.from_numpy(np.array([[circuit.element_value(e) * netgen.mc_factor(l, j, 4) for l in range(rank * lanes, (rank + 1) * lanes)]
+                                          for j, e in enumerate(varied)])).cuda()
+        pdc = kb.Plan(circuit, api.MODE_DC, varied=varied)
+        plan = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=5e-6, integrator=api.INTEGRATOR_TRAP)
+        out = torch.empty((lanes, nsteps + 1, circuit.n), dtype=torch.float64, device="cuda")
+        step = lambda: plan.solve_transient(pdc, nsteps, lanes, varied_values=vals, out=out)
+        points, dtype, s = lanes * nsteps, "f64", 8
+        what = f"circuits/dual_rc_ladder transient, {nsteps} trapezoidal steps x {lanes} Monte-Carlo R/C variants per GPU"
+        bytes_pt, bytes_what = s * (int(plan.info.nnz_lu) + 3 * circuit.n), "B_step = s*(nnz_lu + 3*n), SURVEY 8(d); the kernel keeps factors on chip and only writes s*n per point"
+        extra["floor_bytes_per_point"] = s * circuit.n
+        kernel = "krb_dense_tran<4>"
+    else:
+        transient = wl == "mesh_tran"
+        g = args.mesh_grid
+        circuit = kb.parse_circuit_description(netgen.rlc_mesh(g, g, transient=transient))
+        kinds = [circuit.element(e).kind for e in range(circuit.num_elements)]
+        varied = [e for e, k in enumerate(kinds) if k in (api.KIND_R, api.KIND_C, api.KIND_L)]
+        lanes = args.lanes if args.lanes != LANES_PER_GPU else (512 if transient else 256)
+        vals = torch.from_numpy(mc(circuit, varied, lanes, rank * lanes)).cuda()
+        if transient:
+            nsteps = args.tran_steps or 32
+            pdc = kb.Plan(circuit, api.MODE_DC, varied=varied, executor=api.EXEC_STAGED)
+            plan = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=1e-9, integrator=api.INTEGRATOR_TRAP, executor=api.EXEC_STAGED)
+            out = torch.empty((lanes, nsteps + 1, circuit.n), dtype=torch.float64, device="cuda")
+            step = lambda: plan.solve_transient(pdc, nsteps, lanes, varied_values=vals, out=out)
+            points, dtype, s = lanes * (nsteps + 1), "f64", 8
+            what = f"synthetic {g}x{g} RLC mesh (n={circuit.n}) transient Monte-Carlo: {lanes} lanes per GPU x ({nsteps} trapezoidal steps + operating point)"
+            bytes_pt, bytes_what = s * (int(plan.info.nnz_lu) + 3 * circuit.n), "B_step = s*(nnz_lu + 3*n) per solved time point, SURVEY 8(d)"
+        else:
+            plan = kb.Plan(circuit, api.MODE_AC, varied=varied, nominal_frequency=1e4, executor=api.EXEC_STAGED)
+            freqs = torch.logspace(4, 8, lanes, dtype=torch.float64, device="cuda")
+            out = torch.empty((lanes, circuit.n), dtype=torch.complex128, device="cuda")
+            step = lambda: plan.solve_ac(freqs, varied_values=vals, out=out)
+            points, dtype, s = lanes, "c64", 16
+            what = f"synthetic {g}x{g} RLC mesh (n={circuit.n}) AC Monte-Carlo: {lanes} lanes per GPU, 10 kHz..100 MHz"
+            bytes_pt, bytes_what = int(plan.info.alg_bytes_per_point), "P + s*(4*nnz_lu + 3*n), SURVEY 8(d)"
+        kernel = "krb_front_factor / krb_front_forward / krb_front_backward"
+        extra["nnz_lu"] = int(plan.info.nnz_lu)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        _, status = step()
+    barrier()
+    launches0 = kb.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(K):
+            step()
+        ev1.record()
+        barrier()
+    launches = kb.kernel_launch_count() - launches0
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = points * world * K / (ms * 1e-3)
+    if rank == 0:
+        achieved = bytes_pt * points * K / (ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                "config": {"workload": what, "n_unknowns": circuit.n, "lanes_per_gpu": lanes, "sharding": f"independent lanes, {world} rank(s), no data-path collective",
+                           "l2": "per-step working set >> 126 MB L2; no explicit flush", **extra},
+                "clocks": clocks.summary(), "e2e": None, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": kernel, "bytes_per_point": bytes_pt, "bytes_model": bytes_what, "peak_source": peak_src,
+                             "note": "whole-step time (all kernels of the step), not a single kernel's duration"},
+                "lanes_with_status": int((status != 0).sum().item())}
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,9 +289,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--force-vm", action="store_true", help="profiling: run the workload on the general lane VM instead of the chain executor")
+    ap.add_argument("--workload", default="ladder_dc", choices=["ladder_dc", "rc_ac", "dual_rc_tran", "mesh_tran", "mesh_ac"],
+                    help="ladder_dc = BASELINE config 2 (the headline, default); rc_ac = config 3, dual_rc_tran = config 4, mesh_* = config 5")
+    ap.add_argument("--mesh-grid", type=int, default=224)
+    ap.add_argument("--tran-steps", type=int, default=0, help="time steps per lane for the transient workloads (0 = workload default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "ladder_dc":
+        return run_other_workload(args)
 
     import numpy as np
     import torch
