@@ -1,3 +1,4 @@
-python __graft_entry__.py smoke 2>&1 | tail -2
-python bench.py --steps 5 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_r1j.log; cut -c1-400 gpurun_out/bench_r1j.log
-for w in rc_ac dual_rc_tran mesh_ac mesh_tran; do python bench.py --workload $w --steps 3 --warmup 3 2>&1 | tail -1 | tee -a gpurun_out/bench_workloads_r1.jsonl | cut -c1-700; done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1k.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_bench_k.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:krb_chain -s 3 -c 1 -o gpurun_out/prof_chain_r1k python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full_k.log 2>&1
+ncu -i gpurun_out/prof_chain_r1k.ncu-rep --page raw --csv > gpurun_out/prof_chain_r1k_raw.csv
+ls -la gpurun_out/prof_chain_r1k.ncu-rep
