@@ -129,7 +129,7 @@ static int upload_front(Plan &plan) {
     for (int l = 0; l < fp.n_levels; l++) {
         const int b = fp.level_ptr[l], e = fp.level_ptr[l + 1];
         auto fclass = [&](int m) { return m > m_smem ? 0 : m > 96 ? 1 : m > 48 ? 2 : m > 16 ? 3 : 4; };
-        auto sclass = [&](int m) { return m > 128 ? 0 : m > 32 ? 1 : 2; };
+        auto sclass = [&](int m) { return m > 192 ? 0 : m > 64 ? 1 : 2; };
         for (int i = b; i < e;) {
             const int m0 = msize(fp.level_fronts[i]);
             const int c = fclass(m0);
@@ -153,8 +153,8 @@ static int upload_front(Plan &plan) {
             const int nt = c == 0 ? 256 : c == 1 ? 128 : 32;
             L.warp = (c == 2);
             L.slot_elems = m0 + nt;
-            L.block = L.warp ? dim3(32, 8) : dim3(nt);
-            L.smem = (size_t)L.slot_elems * ts * (L.warp ? 8 : 1);
+            L.block = L.warp ? dim3(32, 16) : dim3(nt);      // WARP mode: 16 independent (front, lane) pairs per CTA, 64 warps per SM
+            L.smem = (size_t)L.slot_elems * ts * (L.warp ? 16 : 1);
             D.solve_launches[l].push_back(L);
             i = j;
         }
