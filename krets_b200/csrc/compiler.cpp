@@ -654,6 +654,36 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
         if (const char *e = getenv("KRB_FRONT_DIAG_BONUS")) bonus = atof(e);
         if (!weighted_matching(plan.pattern, mag, match_row, bonus)) { err = "matrix is structurally singular"; return KRB_ERR_DECOMPOSITION_FAILED; }
         minimum_degree(plan.pattern, match_row, order);
+        // DC: inductors are 0 V branches whose own equation has no diagonal (stampable.rs:688-701), like V sources (:972-980).  A
+        // row matching makes the pattern unsymmetric and the symmetrised fill grows 2.7x on a mesh.  Instead keep every row in
+        // place and eliminate each such branch current right after one of its terminal nodes (2x2-pivot compression of KKT-like
+        // systems): the node's elimination fills the missing diagonal, and the fronts pivot dynamically should it come out small.
+        if (mode == KRB_MODE_DC && getenv("KRB_FRONT_NO_PAIRING") == nullptr) {
+            const Pattern &pt = plan.pattern;
+            std::vector<char> has_diag(n, 0), taken(n, 0);
+            auto has_entry = [&](int row, int col) {
+                auto b = pt.rowidx.begin() + pt.colptr[col], e = pt.rowidx.begin() + pt.colptr[col + 1];
+                return std::binary_search(b, e, row);
+            };
+            for (int u = 0; u < n; u++) has_diag[u] = has_entry(u, u) && mag[(int)(std::lower_bound(pt.rowidx.begin() + pt.colptr[u], pt.rowidx.begin() + pt.colptr[u + 1], u) - pt.rowidx.begin())] > 0.0;
+            std::vector<int> leader_of(n, -1);
+            bool ok = true, any = false;
+            for (int u = 0; u < n && ok; u++) {
+                if (has_diag[u]) continue;
+                any = true;
+                int pick = -1;
+                for (int q = pt.colptr[u]; q < pt.colptr[u + 1] && pick < 0; q++) {
+                    const int v = pt.rowidx[q];               // A[v, u] != 0
+                    if (v != u && has_diag[v] && !taken[v] && has_entry(u, v)) pick = v;
+                }
+                if (pick < 0) ok = false;
+                else { leader_of[u] = pick; taken[pick] = 1; }
+            }
+            if (ok && any) {
+                for (int j = 0; j < n; j++) match_row[j] = j;
+                minimum_degree_paired(plan.pattern, leader_of, order);
+            }
+        }
     }
     const Symbolic &S = plan.sym;
 

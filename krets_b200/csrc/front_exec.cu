@@ -354,6 +354,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
                            (size_t)n * 4 + (out_dev ? 0 : (size_t)rows * n * ts) + 64;
     const size_t work = (cb_e + fw_e + lu0_e) * ts + 64;
     long long chunk = a.chunk_lanes > 0 ? a.chunk_lanes : 2048;
+    if (const char *e = getenv("KRB_FRONT_CHUNK")) chunk = std::max(1, atoi(e));   // tests: force several chunks
     chunk = std::min<long long>(chunk, a.lanes);
     chunk = std::min<long long>(chunk, 65535);
     long long window = 256;

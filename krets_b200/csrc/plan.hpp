@@ -66,6 +66,8 @@ void nominal_magnitudes(const Circuit &c, const Stamps &s, const Pattern &p, int
 bool weighted_matching(const Pattern &p, const std::vector<double> &mag, std::vector<int> &match_row, double diag_bonus = 0.0);
 // minimum-degree ordering of the symmetrised, row-permuted pattern; returns order[k] = unknown eliminated k-th
 void minimum_degree(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order);
+// identity row matching; leader_of[u] >= 0: unknown u (structurally zero diagonal) is eliminated right after unknown leader_of[u]
+void minimum_degree_paired(const Pattern &p, const std::vector<int> &leader_of, std::vector<int> &order);
 void rcm_order(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order);
 bool band_ok(const Pattern &p, const std::vector<int> &match_row, const std::vector<int> &order);
 

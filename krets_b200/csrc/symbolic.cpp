@@ -106,17 +106,9 @@ bool weighted_matching(const Pattern &p, const std::vector<double> &mag, std::ve
 
 // Exact minimum degree on the elimination graph of B + B^T, B = row-permuted A (row j of B = equation matched to
 // unknown j).  Ties broken by lowest index.  Ladders/trees come out leaf-first with zero fill.
-void minimum_degree(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order) {
-    const int n = p.n;
-    std::vector<int> col_of_row(n, -1);
-    for (int j = 0; j < n; j++) col_of_row[match_row[j]] = j;
-    std::vector<std::vector<int>> adj(n);
-    for (int l = 0; l < n; l++)
-        for (int q = p.colptr[l]; q < p.colptr[l + 1]; q++) {
-            const int j = col_of_row[p.rowidx[q]];
-            if (j != l) { adj[j].push_back(l); adj[l].push_back(j); }
-        }
-    for (auto &a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+// exact minimum degree on an explicit (symmetric, sorted, duplicate-free) adjacency; ties broken by lowest index
+static void minimum_degree_graph(std::vector<std::vector<int>> &adj, std::vector<int> &order) {
+    const int n = (int)adj.size();
     // A path graph (every ladder / transmission line) is eliminated end to end: zero fill, and the permuted matrix is
     // tridiagonal, which the native chain executor relies on.  (Minimum degree gives the same fill but may alternate ends.)
     {
@@ -163,6 +155,52 @@ void minimum_degree(const Pattern &p, const std::vector<int> &match_row, std::ve
             pq.insert({deg[w], w});
         }
         std::vector<int>().swap(adj[v]);
+    }
+}
+
+
+void minimum_degree(const Pattern &p, const std::vector<int> &match_row, std::vector<int> &order) {
+    const int n = p.n;
+    std::vector<int> col_of_row(n, -1);
+    for (int j = 0; j < n; j++) col_of_row[match_row[j]] = j;
+    std::vector<std::vector<int>> adj(n);
+    for (int l = 0; l < n; l++)
+        for (int q = p.colptr[l]; q < p.colptr[l + 1]; q++) {
+            const int j = col_of_row[p.rowidx[q]];
+            if (j != l) { adj[j].push_back(l); adj[l].push_back(j); }
+        }
+    for (auto &a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+    minimum_degree_graph(adj, order);
+}
+
+// Constrained variant for the front executor: unknown `follower[k]` (a branch current whose own equation has a structurally
+// zero diagonal: V sources stampable.rs:972-980, inductors in DC :688-701) is merged with `leader[k]` (one of its terminal
+// nodes) into one vertex of the ordering graph and eliminated right after it, when the node's elimination has filled the
+// missing diagonal.  Rows stay in place (identity matching), so the pattern stays structurally symmetric.
+void minimum_degree_paired(const Pattern &p, const std::vector<int> &leader_of, std::vector<int> &order) {
+    const int n = p.n;
+    std::vector<int> rep(n), cid(n, -1);
+    for (int u = 0; u < n; u++) rep[u] = leader_of[u] >= 0 ? leader_of[u] : u;
+    int nc = 0;
+    for (int u = 0; u < n; u++) if (rep[u] == u) cid[u] = nc++;
+    std::vector<std::vector<int>> adj(nc);
+    for (int col = 0; col < n; col++)
+        for (int q = p.colptr[col]; q < p.colptr[col + 1]; q++) {
+            const int a = cid[rep[p.rowidx[q]]], b = cid[rep[col]];
+            if (a != b) { adj[a].push_back(b); adj[b].push_back(a); }
+        }
+    for (auto &a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+    std::vector<int> corder;
+    minimum_degree_graph(adj, corder);
+    std::vector<std::vector<int>> followers(n);
+    for (int u = 0; u < n; u++) if (rep[u] != u) followers[rep[u]].push_back(u);
+    std::vector<int> unknown_of_cid(nc);
+    for (int u = 0; u < n; u++) if (cid[u] >= 0) unknown_of_cid[cid[u]] = u;
+    order.clear();
+    for (int c : corder) {
+        const int u = unknown_of_cid[c];
+        order.push_back(u);
+        for (int f : followers[u]) order.push_back(f);
     }
 }
 

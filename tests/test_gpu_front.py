@@ -133,6 +133,33 @@ def test_front_nominal_dc_pivots_inside_fronts(oracle, monkeypatch, smem_m):
     assert_close(out[0], spl.splu(A).solve(b), rtol=1e-8, what="40x40 nominal DC vs SuperLU")
 
 
+def test_front_chunks_and_windows(oracle, monkeypatch):
+    """Lane chunks (resident factor stores) and factor windows (workspace) that do not divide the lane count."""
+    monkeypatch.setenv("KRB_FRONT_CHUNK", "3")
+    monkeypatch.setenv("KRB_FRONT_WINDOW", "2")
+    text = netgen.rlc_mesh(6, 7, transient=True)
+    circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    lanes, h, steps = 7, 2e-7, 40
+    varied, vals = mc_values(circuit, oc, lanes)
+    plan_dc = kb.Plan(circuit, api.MODE_DC, varied=varied, executor=api.EXEC_STAGED)
+    plan_tr = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=h, integrator=api.INTEGRATOR_TRAP, executor=api.EXEC_STAGED)
+    out, status = plan_tr.solve_transient(plan_dc, steps, lanes, varied_values=vals)
+    assert not status.any()
+    import torch
+    out_d, status_d = plan_tr.solve_transient(plan_dc, steps, lanes, varied_values=torch.from_numpy(vals).cuda())
+    assert np.array_equal(out_d.cpu().numpy(), out) and not status_d.any().item()
+    for lane in (0, 2, 3, 6):
+        _, ref = oracle_lane(oc, varied, vals, lane, lambda: oc.solve_tran(h, steps * h, integrator=api.INTEGRATOR_TRAP))
+        assert_close(out[lane], ref, rtol=1e-8, what=f"chunked transient lane {lane}")
+    text = netgen.rlc_mesh(6, 7, transient=False)
+    circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    freqs = kb.generate_frequencies("Decade", 1, 1e3, 1e9)
+    out, status = kb.Plan(circuit, api.MODE_AC, nominal_frequency=1e3, executor=api.EXEC_STAGED).solve_ac(freqs)
+    _, ref = oc.solve_ac(freqs)
+    assert not status.any() and len(freqs) == 7
+    assert_close(out, ref, what="chunked AC")
+
+
 def test_front_zero_pivot_is_reported():
     text = netgen.rlc_mesh(5, 6, transient=True)
     circuit = kb.parse_circuit_description(text)
