@@ -260,7 +260,7 @@ int32_t krb_solve_transient(krb_plan *plan_dc, krb_plan *plan_tran, const krb_co
 }
 
 const char *krb_last_error_string(void) { return get_error(); }
-const char *krb_version(void) { return "krets_b200 0.1 (sm_100a lane-VM backend)"; }
+const char *krb_version(void) { return "krets_b200 0.2 (sm_100a: chain, lane-VM, dense-transient and front executors)"; }
 int32_t krb_device_count(void) { return device_count(); }
 int64_t krb_kernel_launch_count(void) { return launch_count(); }
 double krb_last_kernel_ms(void) { return last_kernel_ms(); }

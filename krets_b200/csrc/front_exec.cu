@@ -234,7 +234,7 @@ static FrontParams make_params(const Plan &plan, const Bufs &b, void *X, long lo
     const FrontDevice &D = *plan.fdev;
     const FrontPlan &fp = plan.front;
     FrontParams P{};
-    P.fronts = D.fronts; P.list = D.list; P.idx_pos = nullptr; P.idx_unknown = D.idx_unknown; P.rel = D.rel; P.child = D.child;
+    P.fronts = D.fronts; P.list = D.list; P.idx_unknown = D.idx_unknown; P.rel = D.rel; P.child = D.child;
     P.asm_ent = D.asm_ent; P.asm_pos = D.asm_pos; P.col_order = D.col_order;
     P.A = b.A; P.LU = b.LU; P.CB = b.CB; P.FW = b.FW; P.CBV = b.CBV; P.BP = b.BP;
     P.a_stride = plan.pattern.nnz; P.lu_stride = fp.lu_size; P.cb_stride = fp.cb_size; P.fw_stride = D.fw_size; P.cbv_stride = fp.cbv_size;

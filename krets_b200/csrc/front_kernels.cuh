@@ -25,7 +25,7 @@
 namespace krb {
 
 struct FrontDesc {            // one per front, 64 B
-    int p, q, piv0, idx_off;  // idx_off: into idx_unknown / idx_pos / rel
+    int p, q, piv0, idx_off;  // idx_off: into idx_unknown / rel
     int child_begin, child_end, asm_begin, asm_end;
     long long lu_off, cb_off, fw_off;   // fw_off < 0: the front is staged in shared memory
     int cbv_off, pad;
@@ -40,7 +40,7 @@ struct FrontTerm { int elem; int kind; };   // kind = SrcKind | (neg << 8)
 struct FrontParams {
     const FrontDesc *fronts;
     const int *list;          // fronts of this launch
-    const int *idx_pos, *idx_unknown, *rel, *child, *asm_ent, *asm_pos, *col_order;
+    const int *idx_unknown, *rel, *child, *asm_ent, *asm_pos, *col_order;
     const void *A;            // [lanes][a_stride]
     void *LU, *CB, *FW, *CBV, *BP;   // per-lane stores
     long long a_stride, lu_stride, cb_stride, fw_stride, cbv_stride;
