@@ -48,6 +48,7 @@ struct FrontDevice {
     FrontElem *elems = nullptr;
     FrontTerm *mat_terms = nullptr, *rhs_terms = nullptr;
     int *mat_ptr = nullptr, *rhs_ptr = nullptr, *state_elems = nullptr;
+    FrontChild *childrec = nullptr;
     int *res_ptr = nullptr, *res_ent = nullptr, *res_col = nullptr;
     int refine_steps = 0;
     std::vector<std::vector<FrontLaunch>> factor_launches, solve_launches;   // per level
@@ -77,7 +78,7 @@ void front_device_free(FrontDevice *d) {
     if (!d) return;
     retire_last_timer(d);
     void *ptrs[] = {d->fronts, d->list, d->idx_unknown, d->rel, d->child, d->asm_ent, d->asm_pos, d->col_order, d->elems,
-                    d->mat_terms, d->rhs_terms, d->mat_ptr, d->rhs_ptr, d->state_elems, d->res_ptr, d->res_ent, d->res_col};
+                    d->mat_terms, d->rhs_terms, d->mat_ptr, d->rhs_ptr, d->state_elems, d->res_ptr, d->res_ent, d->res_col, d->childrec};
     for (void *p : ptrs) if (p) cudaFree(p);
     FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV, &d->DX, &d->LU0};
     for (FBuf *b : bufs) b->release();
@@ -167,6 +168,15 @@ static int upload_front(Plan &plan) {
     if ((rc = up(idx_unknown, &D.idx_unknown))) return rc;
     if ((rc = up(fp.rel, &D.rel))) return rc;
     if ((rc = up(fp.child, &D.child))) return rc;
+    {
+        std::vector<FrontChild> cr(fp.child.size());
+        for (size_t i = 0; i < fp.child.size(); i++) {
+            const int c = fp.child[i];
+            cr[i].q = fp.idx_ptr[c + 1] - fp.idx_ptr[c]; cr[i].idx_off = fp.idx_ptr[c]; cr[i].cbv_off = (int)fp.cbv_off[c]; cr[i].pad = 0;
+            cr[i].cb_off = fp.cb_off[c]; cr[i].pad2 = 0;
+        }
+        if ((rc = up(cr, &D.childrec))) return rc;
+    }
     if ((rc = up(fp.asm_ent, &D.asm_ent))) return rc;
     if ((rc = up(fp.asm_pos, &D.asm_pos))) return rc;
     if ((rc = up(fp.col_order, &D.col_order))) return rc;
@@ -234,7 +244,7 @@ static FrontParams make_params(const Plan &plan, const Bufs &b, void *X, long lo
     const FrontDevice &D = *plan.fdev;
     const FrontPlan &fp = plan.front;
     FrontParams P{};
-    P.fronts = D.fronts; P.list = D.list; P.idx_unknown = D.idx_unknown; P.rel = D.rel; P.child = D.child;
+    P.fronts = D.fronts; P.list = D.list; P.idx_unknown = D.idx_unknown; P.rel = D.rel; P.child = D.child; P.childrec = D.childrec;
     P.asm_ent = D.asm_ent; P.asm_pos = D.asm_pos; P.col_order = D.col_order;
     P.A = b.A; P.LU = b.LU; P.CB = b.CB; P.FW = b.FW; P.CBV = b.CBV; P.BP = b.BP;
     P.a_stride = plan.pattern.nnz; P.lu_stride = fp.lu_size; P.cb_stride = fp.cb_size; P.fw_stride = D.fw_size; P.cbv_stride = fp.cbv_size;

@@ -30,6 +30,10 @@ struct FrontDesc {            // one per front, 64 B
     long long lu_off, cb_off, fw_off;   // fw_off < 0: the front is staged in shared memory
     int cbv_off, pad;
 };
+struct FrontChild {           // one per tree edge, indexed like the child list: what a parent needs from the child, 32 B
+    int q, idx_off, cbv_off, pad;
+    long long cb_off, pad2;
+};
 struct FrontElem {            // one per circuit element, 40 B
     double value, ac_amp;
     int ip, im, ic, in_plane; // in_plane >= 0: per-lane value from input plane
@@ -41,6 +45,7 @@ struct FrontParams {
     const FrontDesc *fronts;
     const int *list;          // fronts of this launch
     const int *idx_unknown, *rel, *child, *asm_ent, *asm_pos, *col_order;
+    const FrontChild *childrec;
     const void *A;            // [lanes][a_stride]
     void *LU, *CB, *FW, *CBV, *BP;   // per-lane stores
     long long a_stride, lu_stride, cb_stride, fw_stride, cbv_stride;
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
     }
     __syncthreads();
     for (int ci = d.child_begin; ci < d.child_end; ci++) {
-        const FrontDesc c = P.fronts[P.child[ci]];
+        const FrontChild c = P.childrec[ci];
         const int qc = c.q;
         const T *CBc = reinterpret_cast<const T *>(P.CB) + lane * P.cb_stride + c.cb_off;
         const int *rel = P.rel + c.idx_off;
@@ -436,6 +441,14 @@ __global__ void krb_front_axpy(const FrontRefineParams p) {
 // Both walk the pivot block in panels of 32 columns: the 32 x 32 diagonal block is solved by one warp with shuffles (all its
 // L/U entries are loaded up front), the rows outside it are updated by one thread per row, so every factor entry is read
 // exactly once, with unit stride, and never behind a dependent chain.
+// non-blocking L2 prefetch of the first lines of a block (at most 32 lines per thread pass: small fronts completely, large ones
+// their first panels)
+__device__ __forceinline__ void front_prefetch(const void *base, size_t bytes, int tid, int nt) {
+    const char *b = reinterpret_cast<const char *>(base);
+    const size_t lines = (bytes + 127) / 128;
+    const size_t cap = lines < (size_t)nt * 2 ? lines : (size_t)nt * 2;
+    for (size_t i = tid; i < cap; i += nt) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + i * 128));
+}
 template <bool WARP> __device__ __forceinline__ void front_sync() { if (WARP) __syncwarp(); else __syncthreads(); }
 template <bool WARP> __device__ __forceinline__ int front_any(int pred) { return WARP ? __any_sync(0xffffffffu, pred) : __syncthreads_or(pred); }
 __device__ __forceinline__ double front_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -456,10 +469,12 @@ __global__ void krb_front_forward(const FrontParams P) {
     const int tid = threadIdx.x, NT = blockDim.x;
     T *BP = reinterpret_cast<T *>(P.BP) + lane * P.n;
     T *CBV = reinterpret_cast<T *>(P.CBV) + lane * P.cbv_stride;
+    const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
+    front_prefetch(L, (size_t)m * p * sizeof(T), tid, NT);      // the factor block streams in while the children are gathered
     for (int i = tid; i < m; i += NT) w[i] = i < p ? BP[d.piv0 + i] : S::zero();
     front_sync<WARP>();
     for (int ci = d.child_begin; ci < d.child_end; ci++) {
-        const FrontDesc c = P.fronts[P.child[ci]];
+        const FrontChild c = P.childrec[ci];
         const int *rel = P.rel + c.idx_off;
         for (int i = tid; i < c.q; i += NT) { T *dst = w + rel[i]; *dst = S::add(*dst, CBV[c.cbv_off + i]); }
         front_sync<WARP>();
@@ -474,7 +489,6 @@ __global__ void krb_front_forward(const FrontParams P) {
             front_sync<WARP>();
         }
     }
-    const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
     for (int kb = 0; kb < p; kb += 32) {
         const int nbk = (p - kb) < 32 ? (p - kb) : 32;
         if (tid < 32) {
@@ -530,9 +544,10 @@ __global__ void krb_front_backward(const FrontParams P) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const T *BP = reinterpret_cast<const T *>(P.BP) + lane * P.n;
     T *X = reinterpret_cast<T *>(P.X) + lane * P.x_lane_stride + P.x_row_off;
+    const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
+    front_prefetch(L, ((size_t)m * p + (size_t)p * q) * sizeof(T), tid, NT);
     for (int i = tid; i < m; i += NT) w[i] = i < p ? BP[d.piv0 + i] : X[P.idx_unknown[d.idx_off + (i - p)]];
     front_sync<WARP>();
-    const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
     const T *U12 = L + (size_t)m * p;
     if (q > 0) {
         // w[k] -= sum_j U12[k, j] x_j : G thread groups split the columns, partial sums reduced in a fixed order
