@@ -367,11 +367,163 @@ static void set_err(int *err, int code, char *msg, int len, const char *fmt, int
     if (msg && len > 0) snprintf(msg, len, fmt, line, text);
 }
 
+/* ---- subcircuits: krets-parser/src/elements/subcircuit.rs ------------------------------------------------------- */
+#define KO_MAX_PINS 32
+typedef struct { char instance_name[KO_NAME], definition_name[KO_NAME]; char nodes[KO_MAX_PINS][KO_NAME]; int nn; } ko_inst;
+typedef struct { int is_instance; ko_elem e; ko_inst x; } ko_defelem;
+typedef struct { char name[KO_NAME]; char pins[KO_MAX_PINS][KO_NAME]; int npins; ko_defelem *el; int nel; } ko_subckt;
+
+/* parse_subckt_instance, subcircuit.rs:147-172: x<name> n1 n2 ... <definition> */
+static int parse_instance(const char *line, ko_inst *x) {
+    const char *p = line + 1;
+    char toks[KO_MAX_PINS + 1][KO_NAME];
+    int nt = 0;
+    if (!(p = ident1(p, x->instance_name))) return 0;
+    for (;;) {
+        const char *q = space1(p);
+        if (!q) break;
+        char tok[KO_NAME];
+        const char *r = ident1(q, tok);
+        if (!r) break;
+        if (nt > KO_MAX_PINS) return 0;
+        strcpy(toks[nt++], tok);
+        p = r;
+    }
+    if (nt == 0) return 0;
+    strcpy(x->definition_name, toks[nt - 1]);
+    x->nn = nt - 1;
+    for (int i = 0; i < x->nn; i++) strcpy(x->nodes[i], toks[i]);
+    return 1;
+}
+
+/* one element line (elements.rs:45-55: alt(R, C, L, V, I, D, BJT, NMOS, subckt), each keyed by its leading tag) */
+static int parse_element_line(const char *s, ko_defelem *de, int *code) {
+    memset(de, 0, sizeof(*de));
+    ko_elem *e = &de->e;
+    e->ip = e->im = e->ic = -1;
+    char c0 = (char)toupper((unsigned char)s[0]);
+    *code = KO_ERR_PARSE;
+    if (c0 == 'R') return parse_rcli(s, e, KO_R, 'R');
+    if (c0 == 'C') return parse_rcli(s, e, KO_C, 'C');
+    if (c0 == 'L') return parse_rcli(s, e, KO_L, 'L');
+    if (c0 == 'V') return parse_vsource(s, e);
+    if (c0 == 'I') return parse_rcli(s, e, KO_I, 'I');
+    if (c0 == 'D') return parse_diode(s, e);
+    if (c0 == 'M' && toupper((unsigned char)s[1]) == 'N') return parse_nmos(s, e);
+    if (c0 == 'X') { de->is_instance = 1; return parse_instance(s, &de->x); }
+    if (c0 == 'Q') { *code = KO_ERR_UNSUPPORTED; return 0; }
+    return 0;
+}
+
+static void push_elem(ko_circuit *c, const ko_elem *e) {
+    if (c->ne == c->ecap) { c->ecap = c->ecap ? 2 * c->ecap : 64; c->e = (ko_elem *)realloc(c->e, sizeof(ko_elem) * c->ecap); }
+    c->e[c->ne++] = *e;
+}
+
+/* map_sub_element, subcircuit.rs:85-116: pins map to the instance's nodes, every other node (a "0" that is not a pin included)
+ * and the element name get "<instance>_" in front */
+static int map_node(char *node, const ko_subckt *def, const ko_inst *x) {
+    for (int k = def->npins - 1; k >= 0; k--)            /* HashMap::collect: a repeated pin keeps its last node */
+        if (!strcmp(def->pins[k], node)) { strcpy(node, x->nodes[k]); return 1; }
+    char tmp[2 * KO_NAME + 2];
+    snprintf(tmp, sizeof(tmp), "%s_%s", x->instance_name, node);
+    if (strlen(tmp) >= KO_NAME) return 0;
+    strcpy(node, tmp);
+    return 1;
+}
+
+/* SubcircuitInstance::instantiate, subcircuit.rs:33-82 */
+static int instantiate(ko_circuit *c, const ko_inst *x, const ko_subckt *defs, int ndefs, int depth) {
+    if (depth > 64) return 0;
+    const ko_subckt *def = NULL;
+    for (int i = 0; i < ndefs; i++) if (!strcmp(defs[i].name, x->definition_name)) def = &defs[i];   /* later definitions replace earlier ones */
+    if (!def || def->npins != x->nn) return 0;
+    for (int i = 0; i < def->nel; i++) {
+        ko_defelem m = def->el[i];
+        char tmp[2 * KO_NAME + 2];
+        if (m.is_instance) {
+            for (int k = 0; k < m.x.nn; k++) if (!map_node(m.x.nodes[k], def, x)) return 0;
+            snprintf(tmp, sizeof(tmp), "%s_%s", x->instance_name, m.x.instance_name);
+            if (strlen(tmp) >= KO_NAME) return 0;
+            strcpy(m.x.instance_name, tmp);
+            if (!instantiate(c, &m.x, defs, ndefs, depth + 1)) return 0;
+        } else {
+            if (!map_node(m.e.plus, def, x) || !map_node(m.e.minus, def, x)) return 0;
+            if (m.e.kind == KO_NMOS && !map_node(m.e.third, def, x)) return 0;
+            snprintf(tmp, sizeof(tmp), "%s_%s", x->instance_name, m.e.name);
+            if (strlen(tmp) >= KO_NAME) return 0;
+            strcpy(m.e.name, tmp);
+            snprintf(m.e.ident, sizeof(m.e.ident), "%c%s", m.e.ident[0], m.e.name);                   /* identifier = letter + name */
+            push_elem(c, &m.e);
+        }
+    }
+    return 1;
+}
+
+/* parse_subcircuits, subcircuit.rs:174-218 (pre-pass over the whole text) */
+static int parse_subcircuits(const char *text, ko_subckt **out, int *nout) {
+    ko_subckt *defs = NULL;
+    int nd = 0, cur = -1;
+    const char *p = text;
+    while (*p) {
+        const char *eol = strchr(p, '\n');
+        size_t len = eol ? (size_t)(eol - p) : strlen(p);
+        char *buf = (char *)malloc(len + 1);
+        memcpy(buf, p, len); buf[len] = 0;
+        p = eol ? eol + 1 : p + len;
+        char *s = buf;
+        while (*s && isspace((unsigned char)*s)) s++;
+        char *t = s + strlen(s);
+        while (t > s && isspace((unsigned char)t[-1])) *--t = 0;
+        int ok = 1;
+        if (!*s || *s == '%' || *s == '*') { free(buf); continue; }
+        if (starts_with_nc(s, ".subckt")) {
+            ko_subckt d; memset(&d, 0, sizeof(d));
+            const char *q = space1(s + 7);
+            q = q ? ident1(q, d.name) : NULL;
+            if (!q) ok = 0;
+            while (ok) {
+                const char *r = space1(q);
+                char pin[KO_NAME];
+                if (!r || !(r = ident1(r, pin))) break;
+                if (d.npins == KO_MAX_PINS) { ok = 0; break; }
+                strcpy(d.pins[d.npins++], pin);
+                q = r;
+            }
+            if (ok) {
+                defs = (ko_subckt *)realloc(defs, sizeof(ko_subckt) * (nd + 1));
+                defs[nd] = d;
+                cur = nd++;
+            }
+        } else if (starts_with_nc(s, ".ends")) cur = -1;
+        else if (cur >= 0) {
+            ko_defelem de;
+            int code;
+            if (!parse_element_line(s, &de, &code)) ok = 0;
+            else {
+                defs[cur].el = (ko_defelem *)realloc(defs[cur].el, sizeof(ko_defelem) * (defs[cur].nel + 1));
+                defs[cur].el[defs[cur].nel++] = de;
+            }
+        }
+        free(buf);
+        if (!ok) { for (int i = 0; i < nd; i++) free(defs[i].el); free(defs); return 0; }
+    }
+    *out = defs; *nout = nd;
+    return 1;
+}
+
 /* parser.rs:27-154 */
 ko_circuit *ko_parse(const char *text, int *err, char *errmsg, int errmsg_len) {
     ko_circuit *c = (ko_circuit *)calloc(1, sizeof(*c));
     if (err) *err = KO_OK;
     int in_control = 0, in_subckt = 0, lineno = 0;
+    ko_subckt *defs = NULL;
+    int ndefs = 0;
+    if (!parse_subcircuits(text, &defs, &ndefs)) {
+        set_err(err, KO_ERR_PARSE, errmsg, errmsg_len, "Failed to parse a subcircuit definition%.0d%s", 0, "");
+        ko_free(c);
+        return NULL;
+    }
     const char *p = text;
     while (*p) {
         const char *eol = strchr(p, '\n');
@@ -409,26 +561,23 @@ ko_circuit *ko_parse(const char *text, int *err, char *errmsg, int errmsg_len) {
             goto next;
         }
         {
-            ko_elem e; memset(&e, 0, sizeof(e));
-            e.ip = e.im = e.ic = -1;
-            char c0 = (char)toupper((unsigned char)s[0]);
-            /* elements.rs:45-55: alt(R, C, L, V, I, D, BJT, NMOS, subckt) — each keyed by its leading tag */
-            if (c0 == 'R') ok = parse_rcli(s, &e, KO_R, 'R');
-            else if (c0 == 'C') ok = parse_rcli(s, &e, KO_C, 'C');
-            else if (c0 == 'L') ok = parse_rcli(s, &e, KO_L, 'L');
-            else if (c0 == 'V') ok = parse_vsource(s, &e);
-            else if (c0 == 'I') ok = parse_rcli(s, &e, KO_I, 'I');
-            else if (c0 == 'D') ok = parse_diode(s, &e);
-            else if (c0 == 'M' && toupper((unsigned char)s[1]) == 'N') ok = parse_nmos(s, &e);
-            else if (c0 == 'Q' || c0 == 'X') { ok = 0; code = KO_ERR_UNSUPPORTED; }
-            else ok = 0;
-            if (!ok) { set_err(err, code, errmsg, errmsg_len, "Parse error on line %d: %s", lineno, s); free(buf); ko_free(c); return NULL; }
-            if (c->ne == c->ecap) { c->ecap = c->ecap ? 2 * c->ecap : 64; c->e = (ko_elem *)realloc(c->e, sizeof(ko_elem) * c->ecap); }
-            c->e[c->ne++] = e;
+            ko_defelem de;
+            ok = parse_element_line(s, &de, &code);
+            if (ok && de.is_instance) ok = instantiate(c, &de.x, defs, ndefs, 0);      /* parser.rs:93-98 */
+            else if (ok) push_elem(c, &de.e);
+            if (!ok) {
+                set_err(err, code, errmsg, errmsg_len, "Parse error on line %d: %s", lineno, s);
+                free(buf); ko_free(c);
+                for (int i = 0; i < ndefs; i++) free(defs[i].el);
+                free(defs);
+                return NULL;
+            }
         }
     next:
         free(buf);
     }
+    for (int i = 0; i < ndefs; i++) free(defs[i].el);
+    free(defs);
     /* index map, parser.rs:105-125: group-2 current first, then unseen non-ground nodes in nodes() order */
     {
         /* `nodes` HashSet<String>: reuse a second string set via a scratch circuit map */

@@ -424,7 +424,8 @@ def test_op_with_subcircuits(oracle):
             "xtop 7 out stage\n.subckt stage a b\nxr a mid res\nxs mid b res\nr9 b 0 4k\n.ends\n.subckt res p m\nr0 p m 1k\n.ends\n")
     flat = ("Rdiv1_1 10 7 10K\nRdiv1_2 7 0 5K\nV1 10 0 dc 10\nRtop_r_0 7 top_mid 1k\nRtop_s_0 top_mid out 1k\nRtop_9 out top_0 4k\n")
     circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(flat)
-    assert circuit.names == oc.names
+    assert circuit.names == oc.names == oracle.Circuit(text).names          # the oracle flattens subcircuits too
+    assert_close(oracle.Circuit(text).solve_op(), oc.solve_op(), what="oracle: flattened by the parser vs by hand")
     sol = kb.Solver(circuit).solve(kb.Analysis.Op())
     # "top_0": a ground inside a definition that is not a pin is an ordinary internal node (reference behaviour), so the
     # second stage floats at V(7) — the oracle on the hand-flattened netlist agrees

@@ -425,8 +425,13 @@ def _flatten_reference_way(text):
 
 
 @pytest.mark.parametrize("text,count", [(SUBCKT_FIXTURE, 3), (SUBCKT_NESTED, 2)])
-def test_subckt_flattening_matches_reference_rules(text, count):
+def test_subckt_flattening_matches_reference_rules(oracle, text, count):
     circuit = kb.parse_circuit_description(text)
+    oc = oracle.Circuit(text)                      # the C oracle restates subcircuit.rs independently of the host front end
+    assert circuit.names == oc.names and circuit.num_elements == oc.num_elements
+    for e in range(circuit.num_elements):
+        el = circuit.element(e)
+        assert (el.ip, el.im, el.ic) == oc.element_indices(e) and circuit.identifiers[e] == oc.element_ident(e)
     L = _lib.lib()
     idents = [L.krh_circuit_element_identifier(circuit._h, e).decode() for e in range(circuit.num_elements)]
     expect = _flatten_reference_way(text)
