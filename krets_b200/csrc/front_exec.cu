@@ -139,7 +139,7 @@ static int upload_front(Plan &plan) {
             FrontLaunch L;
             L.first = i; L.count = j - i;
             L.block = c <= 1 ? dim3(32, 16) : c == 2 ? dim3(16, 16) : c == 3 ? dim3(16, 8) : dim3(8, 8);
-            L.smem = c == 0 ? std::min<size_t>((size_t)D.smem_cap, ((size_t)2 * m0 * 16 + m0) * ts) : (size_t)m0 * (m0 | 1) * ts;
+            L.smem = c == 0 ? std::min<size_t>((size_t)D.smem_cap, ((size_t)2 * m0 * 32 + m0) * ts) : (size_t)m0 * (m0 | 1) * ts;
             L.warp = false; L.slot_elems = 0;
             D.factor_launches[l].push_back(L);
             i = j;
@@ -249,6 +249,7 @@ static FrontParams make_params(const Plan &plan, const Bufs &b, void *X, long lo
     P.A = b.A; P.LU = b.LU; P.CB = b.CB; P.FW = b.FW; P.CBV = b.CBV; P.BP = b.BP;
     P.a_stride = plan.pattern.nnz; P.lu_stride = fp.lu_size; P.cb_stride = fp.cb_size; P.fw_stride = D.fw_size; P.cbv_stride = fp.cbv_size;
     P.n = fp.n; P.status = b.status; P.IPIV = b.ipiv;
+    P.use_dmma = getenv("KRB_FRONT_NO_DMMA") == nullptr ? 1 : 0;
     P.X = X; P.x_lane_stride = x_lane_stride; P.x_row_off = x_row_off;
     return P;
 }

@@ -51,6 +51,7 @@ struct FrontParams {
     long long a_stride, lu_stride, cb_stride, fw_stride, cbv_stride;
     int n;
     int smem_elems;           // capacity of the dynamic shared memory in elements of T
+    int use_dmma;             // real f64, 512-thread classes: trailing update on the FP64 tensor cores
     int *status;
     long long lanes;          // lanes of this launch (WARP-mode kernels bound-check their lane)
     int *IPIV;                // [lanes][n] row chosen for pivot k inside its front (local row index; == k when no swap)
@@ -222,6 +223,63 @@ __device__ __forceinline__ void front_pivot_search(const T *col, int k, int p, i
 }
 
 // ---- (b) numeric factorisation of one front ---------------------------------------------------------------------
+// ---- FP64 tensor-core (DMMA) trailing update ---------------------------------------------------------------------------
+// The rank-nb update C -= L U of a large front is the one genuinely dense contraction on this path.  With FMA register tiles it
+// is bound by operand delivery (8 shared-memory loads per 16 FMAs per thread); mma.sync.m8n8k4.f64 needs one A and one B value
+// per thread for 8 FMAs' worth of work and a quarter of the issue slots.  Fragment layout (PTX ISA, m8n8k4 .f64): g = lane >> 2,
+// t = lane & 3; A[g][t], B[t][g], C[g][2t + {0, 1}].  16 warps as 4 x 4, each warp owns a 32 x 16 block of C (4 x 2 MMA tiles).
+__device__ __forceinline__ void front_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// C(i, j) -= sum_{k < K} Lt(i, k) Up(k, j), i < rows, j < cols; blockDim must be (32, 16)
+__device__ __forceinline__ void front_dmma_update(double *C, int ldc, int rows, int cols, const double *Lt, int ldl, const double *Up, int ldu, int K,
+                                                  int lane, int warp) {
+    const int g = lane >> 2, t = lane & 3, wr = warp & 3, wc = warp >> 2;
+    for (int j0 = 0; j0 < cols; j0 += 64)
+        for (int i0 = 0; i0 < rows; i0 += 128) {
+            const int rbase = i0 + wr * 32, cbase = j0 + wc * 16;
+            if (rbase >= rows || cbase >= cols) continue;                 // whole warp leaves together
+            double c[4][2][2];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const int r = rbase + a * 8 + g, cc = cbase + b * 8 + 2 * t + i;
+                        c[a][b][i] = (r < rows && cc < cols) ? C[r + (size_t)ldc * cc] : 0.0;
+                    }
+            int ra[4], cb[2];                                             // clamped fragment coordinates (results of padding discarded)
+#pragma unroll
+            for (int a = 0; a < 4; a++) { const int r = rbase + a * 8 + g; ra[a] = r < rows ? r : rows - 1; }
+#pragma unroll
+            for (int b = 0; b < 2; b++) { const int cc = cbase + b * 8 + g; cb[b] = cc < cols ? cc : cols - 1; }
+            for (int k0 = 0; k0 < K; k0 += 4) {
+                const int kk = k0 + t;
+                const bool kv = kk < K;
+                const int kc = kv ? kk : K - 1;
+                double af[4], bf[2];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { const double v = Lt[ra[a] + (size_t)ldl * kc]; af[a] = kv ? -v : 0.0; }
+#pragma unroll
+                for (int b = 0; b < 2; b++) { const double v = Up[kc + (size_t)ldu * cb[b]]; bf[b] = kv ? v : 0.0; }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++) front_dmma(c[a][b][0], c[a][b][1], af[a], bf[b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const int r = rbase + a * 8 + g, cc = cbase + b * 8 + 2 * t + i;
+                        if (r < rows && cc < cols) C[r + (size_t)ldc * cc] = c[a][b][i];
+                    }
+        }
+}
+
 // blockDim = (TX, TY); TX consecutive threads walk a column (unit stride), TY columns at a time.
 //
 // One algorithm for every front size (right-looking, blocked, LAPACK getrf order):
@@ -246,8 +304,9 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
     T *F = in_smem ? sm : reinterpret_cast<T *>(P.FW) + lane * P.fw_stride + d.fw_off;
     const int ldf = in_smem ? (m | 1) : m;          // F(i, j) = F[i + ldf * j]
     bool bad = false;
+    const bool use_dmma = (TX == 32 && TY == 16 && P.use_dmma);
     __shared__ int s_ip;
-    __shared__ int s_pv[16];
+    __shared__ int s_pv[32];
     int *ipiv = P.IPIV + lane * P.n + d.piv0;
 
     // ---- assemble: zero, stamped entries, children's contribution blocks (extend-add, children in ascending order) ----
@@ -277,7 +336,7 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
     // ---- blocked elimination ----
     int NB;
     if (in_smem) NB = CPLX ? 4 : 8;
-    else { NB = (P.smem_elems - m) / (2 * m); NB = NB > 16 ? 16 : NB; }
+    else { NB = (P.smem_elems - m) / (2 * m); NB = NB > 32 ? 32 : NB; }   // wide panels: the trailing block streams through L2/HBM once per panel
     for (int kb = 0; kb < p; kb += NB) {
         const int nb = (p - kb) < NB ? (p - kb) : NB;
         const int mk = m - kb, tw = mk - nb;
@@ -344,8 +403,12 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
                 for (int k = 0; k < nb; k++) F[(kb + k) + (size_t)m * (kb + nb + j)] = Up[k + ldu * j];
         }
         __syncthreads();
-        // trailing block C(i, j) -= sum_k Lp(nb + i, k) Up(k, j), R x R register tiles, C loaded before the k loop
-        {
+        // trailing block C(i, j) -= sum_k Lp(nb + i, k) Up(k, j): FP64 tensor cores for the large real classes, else R x R register
+        // tiles with C loaded before the k loop
+        if (!CPLX && R == 4 && use_dmma) {
+            front_dmma_update(reinterpret_cast<double *>(F) + (kb + nb) + (size_t)ldf * (kb + nb), ldf, tw, tw, reinterpret_cast<const double *>(Lp) + nb, ldl,
+                              reinterpret_cast<const double *>(Up), ldu, nb, tx, ty);
+        } else {
             T *C = F + (kb + nb) + (size_t)ldf * (kb + nb);
             const T *Lt = Lp + nb;
             for (int j0 = 0; j0 < tw; j0 += R * TY)
