@@ -1088,6 +1088,76 @@ static int dc_range(ko_circuit *c, const ko_config *cfg, int ei, double start, d
     return rc;
 }
 
+/* cpu_best_effort: what a tuned CPU implementation of the same path does for a LINEAR circuit — the stamped
+ * pattern, the triplet -> CSC slot map and all buffers are built once; every point re-stamps the values (same push order, so the
+ * per-entry sums are bit-identical to sum_triplets), scatters them into the fixed CSC, runs the numeric LU and solves.  Points are
+ * split over `nthreads` OpenMP threads.  A reported baseline, not the reference's work structure (that is ko_solve_dc). */
+int ko_solve_dc_best_effort(ko_circuit *c, const char *element, double start, double step, int num, double *out, int nthreads) {
+    int ei = ko_element_index(c, element);
+    if (ei < 0) return KO_ERR_ELEMENT_NOT_FOUND;
+    if (c->e[ei].kind != KO_V && c->e[ei].kind != KO_I) return KO_ERR_INVALID_ELEMENT_FORMAT;
+    if (ko_is_nonlinear(c)) return KO_ERR_UNSUPPORTED;
+    const int n = c->n;
+    ko_map none = { NULL, 0, 0.0 };
+    /* one-time analysis */
+    ko_trip g0, b0, gs;
+    trip_init(&g0, 0); trip_init(&b0, 0);
+    int rc = assemble(c, MODE_DC, &none, NULL, 0.0, &g0, &b0);
+    if (rc) { trip_free(&g0); trip_free(&b0); return rc; }
+    sum_triplets(&g0, n, &gs);
+    const int nnz = gs.n;
+    int *Ap = (int *)malloc(sizeof(int) * (n + 1)), *Ai = (int *)malloc(sizeof(int) * (nnz + 1));
+    double *A0 = (double *)malloc(sizeof(double) * (nnz + 1));
+    build_csc(&gs, n, Ap, Ai, A0, NULL);
+    int *slot = (int *)malloc(sizeof(int) * (g0.n + 1));
+    for (int t = 0; t < g0.n; t++) {
+        int lo = Ap[g0.c[t]], hi = Ap[g0.c[t] + 1] - 1;
+        while (lo < hi) { int mid = (lo + hi) / 2; if (Ai[mid] < g0.r[t]) lo = mid + 1; else hi = mid; }
+        slot[t] = lo;
+    }
+    const int ntrip = g0.n;
+    trip_free(&g0); trip_free(&b0); trip_free(&gs); free(A0);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+#endif
+    {
+        int tid = 0, nt = 1;
+#ifdef _OPENMP
+        tid = omp_get_thread_num(); nt = omp_get_num_threads();
+#endif
+        int i0 = (int)((int64_t)num * tid / nt), i1 = (int)((int64_t)num * (tid + 1) / nt);
+        ko_circuit *d = clone_circuit_shallow(c);
+        ko_trip g, b;
+        trip_init(&g, 0); trip_init(&b, 0);
+        double *Ax = (double *)malloc(sizeof(double) * (nnz + 1)), *rhs = (double *)malloc(sizeof(double) * (n ? n : 1));
+        int r = KO_OK;
+        for (int i = i0; i < i1 && !r; i++) {
+            d->e[ei].value = start + ((double)i * step);
+            g.n = 0; b.n = 0;
+            r = assemble(d, MODE_DC, &none, NULL, 0.0, &g, &b);
+            if (!r && g.n != ntrip) r = KO_ERR_UNSUPPORTED;   /* stamp structure changed between points: not a linear sweep */
+            if (r) break;
+            memset(Ax, 0, sizeof(double) * nnz);
+            for (int t = 0; t < ntrip; t++) Ax[slot[t]] += g.re[t];
+            memset(rhs, 0, sizeof(double) * n);
+            for (int t = 0; t < b.n; t++) rhs[b.r[t]] += b.re[t];
+            ko_lu_r f;
+            if (ko_lu_factor_r(n, Ap, Ai, Ax, &f)) { r = KO_ERR_DECOMPOSITION; break; }
+            ko_lu_solve_r(&f, rhs, out + (size_t)i * n);
+            ko_lu_free_r(&f);
+        }
+        trip_free(&g); trip_free(&b); free(Ax); free(rhs); free_clone(d);
+        if (r) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+            rc = r;
+        }
+    }
+    free(Ap); free(Ai); free(slot);
+    return rc;
+}
+
 int ko_solve_dc(ko_circuit *c, const ko_config *cfg, const char *element, double start, double stop, double step, double *out,
                 int cap_points, int *npoints, int warm_start, int nthreads) {
     int ei = ko_element_index(c, element);

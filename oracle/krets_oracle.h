@@ -83,6 +83,8 @@ int ko_solve_op(const ko_circuit *c, const ko_config *cfg, double *x, int *itera
  * lane-parallel product, identical for linear circuits).  nthreads>1 splits points over threads
  * (only valid when results do not depend on the warm start, i.e. linear circuits or warm_start=0). */
 int ko_dc_num_steps(double start, double stop, double step);
+/* SURVEY 8(d) cpu_best_effort: analysis once, per point re-stamp + numeric LU + solve, OpenMP over points; linear circuits */
+int ko_solve_dc_best_effort(ko_circuit *c, const char *element, double start, double step, int num, double *out, int nthreads);
 int ko_solve_dc(ko_circuit *c, const ko_config *cfg, const char *element, double start, double stop, double step,
                 double *out, int cap_points, int *npoints, int warm_start, int nthreads);
 

@@ -75,6 +75,8 @@ def lib():
         L.ko_transient_value_at.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.ko_solve_op.argtypes = [C.c_void_p, C.POINTER(_Config), dp, ip]
         L.ko_dc_num_steps.argtypes = [C.c_double, C.c_double, C.c_double]
+        L.ko_solve_dc_best_effort.restype = C.c_int
+        L.ko_solve_dc_best_effort.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int]
         L.ko_solve_dc.argtypes = [C.c_void_p, C.POINTER(_Config), C.c_char_p, C.c_double, C.c_double, C.c_double,
                                   dp, C.c_int, ip, C.c_int, C.c_int]
         L.ko_solve_ac.argtypes = [C.c_void_p, C.POINTER(_Config), dp, C.c_int, dp, ip, C.c_int]
@@ -208,6 +210,15 @@ class Circuit:
                                1 if warm_start else 0, nthreads)
         if rc:
             raise OracleError(rc, "dc")
+        return out[:, : self.n]
+
+    def solve_dc_best_effort(self, element: str, start: float, stop: float, step: float, nthreads=1):
+        """SURVEY 8(d) cpu_best_effort: one-time analysis, per point re-stamp + numeric LU + solve (linear circuits)."""
+        num = lib().ko_dc_num_steps(start, stop, step)
+        out = np.zeros((num, max(self.n, 1)), dtype=np.float64)
+        rc = lib().ko_solve_dc_best_effort(self._h, element.encode(), start, step, num, _dp(out), nthreads)
+        if rc:
+            raise OracleError(rc, "dc best effort")
         return out[:, : self.n]
 
     def solve_ac(self, freqs, cfg=None, nthreads=1):

@@ -228,3 +228,13 @@ def test_lu_vs_scipy(oracle):
     b[c.index_map["I(I1)"]] = 1e-3
     ref = spla.splu(A).solve(b)
     np.testing.assert_allclose(c.solve_op(), ref, rtol=1e-9, atol=1e-14)
+
+
+def test_cpu_best_effort_mode_is_bit_identical(oracle):
+    """the tuned CPU mode (analysis once, re-stamp + numeric LU per point) sums every entry in the same order as
+    sum_triplets, so it must reproduce the faithful restatement bit for bit."""
+    import netgen
+    oc = oracle.Circuit(netgen.resistor_ladder(300))
+    a = oc.solve_dc("V1", 0.0, 63 * 2.0 ** -6, 2.0 ** -6)
+    b = oc.solve_dc_best_effort("V1", 0.0, 63 * 2.0 ** -6, 2.0 ** -6, nthreads=3)
+    assert a.shape == b.shape == (64, 301) and np.array_equal(a, b)
