@@ -42,19 +42,56 @@ def workload_config(n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled every ~2 ms from a thread
+    (the timed region of the default run is only tens of ms); nvidia-smi is the fallback when pynvml is unavailable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.mx, self.reasons, self._stop, self._t, self.source = index, [], [], set(), threading.Event(), None, None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index) if bus is None else None
+            if self._h is None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self._h = h
+                        break
+                if self._h is None:
+                    self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nv = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._h = None
+            self.source = "nvidia-smi"
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self._h is not None:
+                    nv = self._nv
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                    self._stop.wait(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                    r = [c.strip() for c in out.split(",")]
+                    self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:
                 pass
             self._stop.wait(0.2)
@@ -69,18 +106,9 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.source}
 
 
 def measured_peaks():
