@@ -162,6 +162,22 @@ int32_t krb_plan_get_chain(const krb_plan *p, uint32_t *rowinfo /*n+1*/, uint64_
     if (unknown_of_row) std::memcpy(unknown_of_row, ch.unknown_of_row.data(), ch.unknown_of_row.size() * sizeof(int));
     return KRB_OK;
 }
+/* block-partitioned chain kernel tables (tests emulate the kernel on CPU): info = {valid, T, M, n_dict}; rows 2*T*M words; dict 4|8 words each */
+int32_t krb_plan_chain_block_info(const krb_plan *p, int32_t *info /*4*/, double *nominal_diff) {
+    if (!p || !p->p.chain.valid || !info) return KRB_ERR_INVALID_ARGUMENT;
+    const ChainPlan::Block &b = p->p.chain.block;
+    info[0] = b.valid ? 1 : 0; info[1] = b.T; info[2] = b.M; info[3] = b.n_dict;
+    if (nominal_diff) *nominal_diff = b.nominal_diff;
+    if (!b.valid) set_error(b.why_not);
+    return KRB_OK;
+}
+int32_t krb_plan_get_chain_block(const krb_plan *p, uint32_t *rows, uint64_t *dict) {
+    if (!p || !p->p.chain.valid || !p->p.chain.block.valid) return KRB_ERR_INVALID_ARGUMENT;
+    const ChainPlan::Block &b = p->p.chain.block;
+    if (rows) std::memcpy(rows, b.rows.data(), b.rows.size() * 4);
+    if (dict) std::memcpy(dict, b.dict.data(), b.dict.size() * 8);
+    return KRB_OK;
+}
 /* front executor tables: which = 0 piv0, 1 idx_ptr, 2 idx, 3 parent, 4 child_ptr, 5 child, 6 rel, 7 level_ptr, 8 level_fronts,
  * 9 asm_ptr, 10 asm_ent, 11 asm_pos; returns the length (copies when out != NULL) or -1 */
 int64_t krb_plan_front_array(const krb_plan *p, int32_t which, int32_t *out) {

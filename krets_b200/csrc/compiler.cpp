@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cmath>
+#include <complex>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -486,6 +487,203 @@ std::vector<Src> rhs_srcs(const Plan &p, int row) {
     return v;
 }
 
+// ---- block-partitioned chain tables (chain_block_kernel.cuh) ---------------------------------------------------------
+// One CTA of T threads solves one lane: thread t owns pivot rows [t*M, (t+1)*M); the last row of each block is a
+// separator.  Interior rows are eliminated inside the thread (left boundary carried as a fill column), the T separator
+// equations form a tridiagonal system solved by parallel cyclic reduction, interiors follow by substitution.  Nothing
+// but the inputs and the n results touches HBM.  Applicability is decided here, on the host:
+//   * n <= T*M for one of the compiled (T, M) shapes;
+//   * a row with a second super-diagonal must sit at local index <= M-3 of its block, at most one per block;
+//   * the partitioned elimination, run at the nominal inputs, must agree with the sequential one to 5e-10 (scaled) —
+//     the interior blocks are factorised without their left neighbour, which is only safe when they are well conditioned
+//     on their own (ladders, RC lines: diagonally dominant); anything else keeps the sequential chain kernel.
+typedef std::complex<double> cd;
+static void chain_rows_nominal(const Plan &plan, const std::vector<uint32_t> &row_off, const std::vector<double> &nom, double w,
+                               std::vector<cd> e[5]) {
+    const ChainPlan &ch = plan.chain;
+    const int n = plan.sym.n;
+    const bool cplx = plan.is_complex;
+    auto dval = [&](size_t word) { double v; std::memcpy(&v, &ch.stream[word], 8); return v; };
+    for (int g = 0; g < 5; g++) e[g].assign(n, cd(0.0, 0.0));
+    for (int k = 0; k < n; k++) {
+        const size_t w0 = (size_t)row_off[k] * 2;
+        if (ch.rowinfo[k] & 1u) {
+            e[0][k] = cd(dval(w0 + 0), cplx ? w * dval(w0 + 4) : 0.0);
+            e[1][k] = cd(dval(w0 + 1), cplx ? w * dval(w0 + 5) : 0.0);
+            e[2][k] = cd(dval(w0 + 2), cplx ? w * dval(w0 + 6) : 0.0);
+            e[4][k] = cd(dval(w0 + 3), 0.0);
+        } else {
+            const int nt = (int)(ch.rowinfo[k] >> 8);
+            for (int t = 0; t < nt; t++) {
+                const uint64_t mw = ch.stream[w0 + 2 * t];
+                const uint32_t meta = (uint32_t)mw, plane = (uint32_t)(mw >> 32);
+                const double K = dval(w0 + 2 * t + 1);
+                cd v(0.0, 0.0);
+                switch ((meta >> 4) & 0xfu) {
+                case 0: v = cd(K, 0.0); break;
+                case 1: v = cd(nom[plane], 0.0); break;
+                case 2: v = cd(1.0 / nom[plane], 0.0); break;
+                case 3: v = cd(nom[plane] / K, 0.0); break;
+                case 4: v = cd(0.0, w * K); break;
+                default: v = cd(0.0, w * nom[plane]); break;
+                }
+                if (meta & (1u << 8)) v = -v;
+                e[meta & 7u][k] += v;
+            }
+        }
+    }
+}
+
+static void build_chain_block(Plan &plan, const std::vector<uint32_t> &row_off, const std::vector<int> &input_of_elem) {
+    ChainPlan &ch = plan.chain;
+    ChainPlan::Block &bk = ch.block;
+    bk = ChainPlan::Block();
+    const int n = plan.sym.n;
+    const bool cplx = plan.is_complex;
+    const char *env = getenv("KRB_CHAIN_BLOCK");          // "0": never, "1": also for small systems (tests)
+    if (env && env[0] == '0') { bk.why_not = "disabled by KRB_CHAIN_BLOCK=0"; return; }
+    const bool force_small = env && env[0] == '1';
+    if (n < 512 && !force_small) { bk.why_not = "n < 512: the sequential chain kernel is used"; return; }
+    const int T = cplx ? 512 : 256, mstep = cplx ? 2 : 4, mmax = cplx ? 10 : 20;
+    // smallest compiled M that holds the system and keeps every row with a second super-diagonal at local index <= M-3,
+    // at most one per block
+    int M = 0;
+    for (int m = mstep; m <= mmax && !M; m += mstep) {
+        if ((int64_t)T * m < n) continue;
+        bool fits = true;
+        int last_block = -1;
+        for (int k : ch.u2_rows) {
+            if (k % m > m - 3 || k / m == last_block) { fits = false; break; }
+            last_block = k / m;
+        }
+        if (fits) M = m;
+    }
+    if (!M) { bk.why_not = "no compiled (T, M) shape holds the system with its second-super-diagonal rows inside a block"; return; }
+    // ---- nominal numeric check: sequential vs partitioned elimination ----
+    std::vector<double> nom(std::max(plan.n_inputs, 1), 1.0);
+    const double fnom = plan.opts.nominal_frequency > 0.0 ? plan.opts.nominal_frequency : 1000.0;
+    for (size_t el = 0; el < input_of_elem.size(); el++) if (input_of_elem[el] >= 0) nom[input_of_elem[el]] = plan.circuit.el[el].value;
+    if (plan.input_freq >= 0) nom[plan.input_freq] = fnom;
+    if (plan.input_sweep >= 0 && nom[plan.input_sweep] == 0.0) nom[plan.input_sweep] = 1.0;   // a zero source would hide the right-hand side
+    const double w = (2.0 * 3.14159265358979323846264338327950288) * fnom;
+    std::vector<cd> e[5];
+    chain_rows_nominal(plan, row_off, nom, w, e);
+    const int np = T * M;
+    for (int g = 0; g < 5; g++) e[g].resize(np, cd(0.0, 0.0));
+    for (int k = n; k < np; k++) e[1][k] = cd(1.0, 0.0);
+    const cd zero(0.0, 0.0);
+    // sequential reference (what krb_chain_kernel computes)
+    std::vector<cd> xs(np), u(np), u2(np), y(np);
+    {
+        cd pu = zero, pu2 = zero, py = zero;
+        for (int k = 0; k < np; k++) {
+            const cd wk = e[1][k] - e[0][k] * pu, s1 = e[2][k] - e[0][k] * pu2, yk = e[4][k] - e[0][k] * py;
+            pu = s1 / wk; pu2 = e[3][k] / wk; py = yk / wk;
+            u[k] = pu; u2[k] = pu2; y[k] = py;
+        }
+        for (int k = np - 1; k >= 0; k--) xs[k] = y[k] - (k + 1 < np ? u[k] * xs[k + 1] : zero) - (k + 2 < np ? u2[k] * xs[k + 2] : zero);
+    }
+    // partitioned
+    std::vector<cd> xb(np), l(np), p(np), r(np), q(np);
+    std::vector<cd> A(T), B(T), Cc(T), D(T);
+    bool ok = true;
+    auto pivot_ok = [&](cd wk, cd a, cd b) {   // wk = a - b: finite, non-zero, no catastrophic cancellation
+        const double m = std::max(std::abs(a), std::abs(b));
+        return std::isfinite(wk.real()) && std::isfinite(wk.imag()) && std::abs(wk) > 1e-9 * m && std::abs(wk) > 0.0;
+    };
+    for (int t = 0; t < T && ok; t++) {
+        const int a = t * M;
+        for (int j = 0; j < M - 1; j++) {
+            const int k = a + j;
+            cd wk, s1, yk, lk;
+            if (j == 0) { wk = e[1][k]; s1 = e[2][k]; yk = e[4][k]; lk = e[0][k]; ok = ok && pivot_ok(wk, wk, zero); }
+            else {
+                wk = e[1][k] - e[0][k] * u[k - 1]; s1 = e[2][k] - e[0][k] * u2[k - 1]; yk = e[4][k] - e[0][k] * y[k - 1]; lk = -e[0][k] * l[k - 1];
+                ok = ok && pivot_ok(wk, e[1][k], e[0][k] * u[k - 1]);
+            }
+            u[k] = s1 / wk; u2[k] = e[3][k] / wk; y[k] = yk / wk; l[k] = lk / wk;
+        }
+        const int sp = a + M - 1;
+        A[t] = -e[0][sp] * l[sp - 1]; B[t] = e[1][sp] - e[0][sp] * u[sp - 1]; D[t] = e[4][sp] - e[0][sp] * y[sp - 1];
+        p[sp] = zero; r[sp] = cd(-1.0, 0.0); q[sp] = zero;
+        for (int j = M - 2; j >= 0; j--) {
+            const int k = a + j;
+            const cd p2 = j + 2 <= M - 1 ? p[k + 2] : zero, r2 = j + 2 <= M - 1 ? r[k + 2] : zero, q2 = j + 2 <= M - 1 ? q[k + 2] : zero;
+            p[k] = y[k] - u[k] * p[k + 1] - u2[k] * p2;
+            r[k] = -u[k] * r[k + 1] - u2[k] * r2;
+            q[k] = l[k] - u[k] * q[k + 1] - u2[k] * q2;
+        }
+    }
+    if (ok) {
+        for (int t = 0; t < T; t++) {
+            const cd ss = e[2][t * M + M - 1];
+            const cd pn = t + 1 < T ? p[(t + 1) * M] : zero, rn = t + 1 < T ? r[(t + 1) * M] : zero, qn = t + 1 < T ? q[(t + 1) * M] : zero;
+            const cd b0 = B[t];
+            B[t] = b0 - ss * qn; Cc[t] = -ss * rn; D[t] = D[t] - ss * pn;
+            ok = ok && pivot_ok(B[t], b0, ss * qn);
+        }
+        // parallel cyclic reduction, rows normalised to a unit diagonal
+        std::vector<cd> a1(T), c1(T), d1(T), a2(T), c2(T), d2(T);
+        for (int t = 0; t < T; t++) { a1[t] = A[t] / B[t]; c1[t] = Cc[t] / B[t]; d1[t] = D[t] / B[t]; }
+        for (int s = 1; s < T && ok; s *= 2) {
+            for (int t = 0; t < T; t++) {
+                const cd am = t >= s ? a1[t - s] : zero, cm = t >= s ? c1[t - s] : zero, dm = t >= s ? d1[t - s] : zero;
+                const cd ap = t + s < T ? a1[t + s] : zero, cp = t + s < T ? c1[t + s] : zero, dp = t + s < T ? d1[t + s] : zero;
+                const cd sub_ = a1[t] * cm + c1[t] * ap;
+                const cd b2 = cd(1.0, 0.0) - sub_;
+                ok = ok && pivot_ok(b2, cd(1.0, 0.0), sub_);
+                a2[t] = -a1[t] * am / b2; c2[t] = -c1[t] * cp / b2; d2[t] = (d1[t] - a1[t] * dm - c1[t] * dp) / b2;
+            }
+            a1.swap(a2); c1.swap(c2); d1.swap(d2);
+        }
+        for (int t = 0; t < T; t++) {
+            const cd st = d1[t], sm = t > 0 ? d1[t - 1] : zero;
+            for (int j = 0; j < M - 1; j++) { const int k = t * M + j; xb[k] = p[k] - r[k] * st - q[k] * sm; }
+            xb[t * M + M - 1] = st;
+        }
+    }
+    if (!ok) { bk.why_not = "partitioned elimination meets a weak pivot at the nominal inputs"; return; }
+    double scale = 0.0, diff = 0.0;
+    for (int k = 0; k < n; k++) scale = std::max(scale, std::abs(xs[k]));
+    for (int k = 0; k < n; k++) {
+        const double den = std::max(std::abs(xs[k]), 1e-6 * scale);
+        if (den > 0.0) diff = std::max(diff, std::abs(xb[k] - xs[k]) / den);
+        if (!std::isfinite(std::abs(xb[k]))) diff = INFINITY;
+    }
+    bk.nominal_diff = diff;
+    if (!(diff <= 5e-10)) { bk.why_not = "partitioned and sequential elimination differ by more than 5e-10 at the nominal inputs"; return; }
+
+    // ---- tables ----
+    const int fw = cplx ? 8 : 4;                                  // words per FIXED record
+    std::map<std::vector<uint64_t>, uint32_t> index;
+    auto intern = [&](const std::vector<uint64_t> &rec) {
+        auto it = index.find(rec);
+        if (it != index.end()) return it->second;
+        const uint32_t id = (uint32_t)index.size();
+        index.emplace(rec, id);
+        bk.dict.insert(bk.dict.end(), rec.begin(), rec.end());
+        return id;
+    };
+    std::vector<uint64_t> pad_rec(fw, 0);
+    { const double one = 1.0; std::memcpy(&pad_rec[1], &one, 8); }
+    bk.rows.assign((size_t)2 * T * M, 0u);
+    for (int t = 0; t < T; t++)
+        for (int j = 0; j < M; j++) {
+            const int k = t * M + j;
+            uint32_t w0, w1 = 0;
+            if (k >= n) w0 = (intern(pad_rec) << 1) | 1u;
+            else if (ch.rowinfo[k] & 1u) {
+                std::vector<uint64_t> rec(ch.stream.begin() + (size_t)row_off[k] * 2, ch.stream.begin() + (size_t)row_off[k] * 2 + fw);
+                w0 = (intern(rec) << 1) | 1u;
+            } else { w0 = row_off[k] << 1; w1 = ch.rowinfo[k] & ~1u; }
+            bk.rows[((size_t)j * T + t) * 2 + 0] = w0;
+            bk.rows[((size_t)j * T + t) * 2 + 1] = w1;
+        }
+    bk.n_dict = (int)index.size();
+    bk.T = T; bk.M = M;
+    bk.valid = true;
+}
+
 // ---- chain executor tables ------------------------------------------------------------------------------------
 // Applicable when the circuit is linear, the solve is one-shot (DC / AC) and the permuted matrix has lower bandwidth
 // <= 1 and upper bandwidth <= 2:  Lpat[k] in {k-1},  Upat[k] in {k+1, k+2}.
@@ -534,7 +732,9 @@ void build_chain_plan(Plan &plan, const std::vector<int> &input_of_elem) {
     auto dbits = [](double v) { uint64_t b; std::memcpy(&b, &v, 8); return b; };
     const bool cplx = plan.is_complex;
     int n_u2 = 0, n_fixed = 0;
+    std::vector<uint32_t> row_off(n);                             // 16-byte unit offset of each row's record / term run
     for (int k = 0; k < n; k++) {
+        row_off[k] = (uint32_t)(ch.stream.size() / 2);
         std::vector<ChainTerm> row;
         if (!S.Lpat[k].empty() && !emit_terms(entry_srcs(plan, S.Lent[k][0]), 0u, row)) return;
         if (!emit_terms(entry_srcs(plan, S.Dent[k]), 1u, row)) return;
@@ -590,6 +790,7 @@ void build_chain_plan(Plan &plan, const std::vector<int> &input_of_elem) {
     ch.n_u2 = n_u2;
     ch.n_fixed = n_fixed;
     ch.valid = true;
+    build_chain_block(plan, row_off, input_of_elem);
 }
 
 }  // namespace
@@ -934,6 +1135,7 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
         dp.valid = ok;
     }
     if (plan.use_chain) plan.hbm_bytes_per_point = s * (5 * (int64_t)n + 2 * plan.chain.n_u2) + 8 * (int64_t)plan.n_inputs;   // 2n(+) out, back, n results
+    if (plan.use_chain && plan.chain.block.valid) plan.hbm_bytes_per_point = s * (int64_t)n + 8 * (int64_t)plan.n_inputs;   // block kernel: inputs in, n results out
     return KRB_OK;
 }
 

@@ -108,6 +108,17 @@ struct ChainPlan {
     std::vector<int> u2_rows;            // rows owning a u2 plane, ascending
     std::vector<uint32_t> runs;          // (count << 1) | is_fixed: consecutive rows of the same record type
     bool identity_order = false;         // unknown_of_row[k] == k: results can be delivered point-major straight from the kernel
+    // ---- block-partitioned kernel (chain_block_kernel.cuh): one CTA of T threads per lane, M consecutive pivot rows per thread ----
+    struct Block {
+        bool valid = false;
+        int T = 0, M = 0;                // n <= T * M; rows >= n are identity padding
+        std::vector<uint32_t> rows;      // [M][T][2]: word 0 = FIXED ? (dictionary index << 1) | 1 : (stream unit offset << 1);
+                                         //            word 1 = (#terms << 8) | (HAS_U2 ? 2 : 0)
+        std::vector<uint64_t> dict;      // unique FIXED records, 4 (real) / 8 (complex) words each, same layout as in `stream`
+        int n_dict = 0;
+        double nominal_diff = 0.0;       // max scaled |x_block - x_sequential| at the nominal inputs (host check, must be <= 5e-10)
+        std::string why_not;             // reason the block kernel is not applicable (diagnostics)
+    } block;
 };
 
 // "front" executor tables (front_kernels.cuh): supernodal multifrontal LU on the symmetrised pattern of the permuted

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "chain_kernel.cuh"
+#include "chain_block_kernel.cuh"
 #include "dense_tran_kernel.cuh"
 #include "plan.hpp"
 #include "runtime.hpp"
@@ -70,6 +71,8 @@ struct DeviceState {
     int *chain_unknown = nullptr;
     int *chain_u2_rows = nullptr;
     uint32_t *chain_runs = nullptr;
+    uint2 *block_rows = nullptr;         // block-partitioned chain kernel tables
+    uint4 *block_dict = nullptr;
     DenseElem *dense_elems = nullptr;    // dense transient executor tables
     DenseTerm *dense_mat = nullptr, *dense_rhs = nullptr;
     int *dense_state = nullptr, *dense_col_order = nullptr;
@@ -117,6 +120,8 @@ void device_state_free(DeviceState *d) {
     if (d->chain_unknown) cudaFree(d->chain_unknown);
     if (d->chain_u2_rows) cudaFree(d->chain_u2_rows);
     if (d->chain_runs) cudaFree(d->chain_runs);
+    if (d->block_rows) cudaFree(d->block_rows);
+    if (d->block_dict) cudaFree(d->block_dict);
     if (d->B) cudaFree(d->B);
     if (d->dense_elems) cudaFree(d->dense_elems);
     if (d->dense_mat) cudaFree(d->dense_mat);
@@ -159,6 +164,10 @@ static int upload_plan(Plan &plan, DeviceState &d) {
         if ((rc = upload_vec(plan.chain.unknown_of_row, &d.chain_unknown))) return rc;
         if ((rc = upload_vec(plan.chain.u2_rows, &d.chain_u2_rows))) return rc;
         if ((rc = upload_vec(plan.chain.runs, &d.chain_runs))) return rc;
+        if (plan.chain.block.valid) {
+            if ((rc = upload_vec(plan.chain.block.rows, (uint32_t **)&d.block_rows))) return rc;
+            if ((rc = upload_vec(plan.chain.block.dict, (uint64_t **)&d.block_dict))) return rc;
+        }
     }
     if (plan.dense.valid) {
         static_assert(sizeof(DenseElem) == sizeof(DensePlan::Elem) && sizeof(DenseTerm) == sizeof(DensePlan::Term), "dense table layouts");
@@ -224,6 +233,49 @@ static int launch_chain_d(bool cplx, int tpb, const ChainParams &p, long long Lp
 }
 static int launch_chain(bool cplx, int tpb, bool direct, const ChainParams &p, long long Lpad, cudaStream_t st) {
     return direct ? launch_chain_d<true>(cplx, tpb, p, Lpad, st) : launch_chain_d<false>(cplx, tpb, p, Lpad, st);
+}
+
+// block-partitioned chain kernel: persistent CTAs (one lane at a time each), grid = resident CTAs of the device
+template <bool CPLX, int T, int M>
+static int launch_chain_block_t(const ChainBlockParams &p, cudaStream_t st) {
+    typedef typename ChainSc<CPLX>::T V;
+    const size_t smem = ((size_t)T * (M + 1) + (size_t)6 * T) * sizeof(V);
+    static int resident = 0;
+    if (!resident) {
+        CUDA_TRY(cudaFuncSetAttribute(krb_chain_block_kernel<CPLX, T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0, sms = 0, per_sm = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krb_chain_block_kernel<CPLX, T, M>, T, smem));
+        if (per_sm < 1) { set_error("block chain kernel does not fit on an SM"); return KRB_ERR_INTERNAL; }
+        resident = sms * per_sm;
+    }
+    const unsigned grid = (unsigned)std::min<long long>(p.lanes, resident);
+    krb_chain_block_kernel<CPLX, T, M><<<grid, T, smem, st>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return KRB_OK;
+}
+static int launch_chain_block(bool cplx, int M, const ChainBlockParams &p, cudaStream_t st) {
+    if (cplx) {
+        switch (M) {
+        case 2: return launch_chain_block_t<true, 512, 2>(p, st);
+        case 4: return launch_chain_block_t<true, 512, 4>(p, st);
+        case 6: return launch_chain_block_t<true, 512, 6>(p, st);
+        case 8: return launch_chain_block_t<true, 512, 8>(p, st);
+        case 10: return launch_chain_block_t<true, 512, 10>(p, st);
+        }
+    } else {
+        switch (M) {
+        case 4: return launch_chain_block_t<false, 256, 4>(p, st);
+        case 8: return launch_chain_block_t<false, 256, 8>(p, st);
+        case 12: return launch_chain_block_t<false, 256, 12>(p, st);
+        case 16: return launch_chain_block_t<false, 256, 16>(p, st);
+        case 20: return launch_chain_block_t<false, 256, 20>(p, st);
+        }
+    }
+    set_error("block chain kernel: no compiled shape for this plan");
+    return KRB_ERR_INTERNAL;
 }
 
 template <int N, int NSP, int NWP>
@@ -293,7 +345,10 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const int width = n + (PS ? (int)PS->state_elems.size() : 0);   // result-row columns incl. trapezoidal state
     const bool out_dev = (a.memory == KRB_MEM_DEVICE);
     // the chain kernel can write point-major results itself when pivot row k is unknown k (no X staging, no pack kernel)
-    const bool direct = chain && P0.chain.identity_order && a.layout == KRB_LAYOUT_POINT_MAJOR && rows == 1;
+    // block-partitioned chain kernel: one CTA per lane, results delivered point-major from shared memory (any pivot order),
+    // no factor planes in HBM.  KRB_CHAIN_SEQ=1 keeps the sequential kernel (tests, A/B measurements).
+    const bool block = chain && P0.chain.block.valid && a.layout == KRB_LAYOUT_POINT_MAJOR && rows == 1 && getenv("KRB_CHAIN_SEQ") == nullptr;
+    const bool direct = block || (chain && P0.chain.identity_order && a.layout == KRB_LAYOUT_POINT_MAJOR && rows == 1);
     // the dense transient kernel delivers point-major rows itself: only the operating-point row is staged in planes
     const bool dense_direct = PS && rows > 1 && PS->dense.valid && a.layout == KRB_LAYOUT_POINT_MAJOR && getenv("KRB_NO_DENSE_TRAN") == nullptr;
     const int plane_rows = dense_direct ? 1 : rows;
@@ -319,7 +374,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     }
 
     // ---- chunking: bound the per-call device footprint ----
-    const int planes0 = chain ? 2 * n + P0.chain.n_u2 : P0.n_planes, planesS = PS ? PS->n_planes : 0;
+    const int planes0 = block ? 0 : chain ? 2 * n + P0.chain.n_u2 : P0.n_planes, planesS = PS ? PS->n_planes : 0;
     const int nbuf = out_dev ? 1 : 2;
     const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)plane_rows * width * ts * (out_dev ? 1 : 2) + (out_dev ? 0 : (size_t)rows * width * ts * 2) +
                             (size_t)P0.n_inputs * 8 + (a.op_solution ? (size_t)n * 8 : 0) + 16;
@@ -410,7 +465,14 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         cudaEvent_t e0, e1;
         if ((rc = next_events(e0, e1))) return rc;
         CUDA_TRY(cudaEventRecord(e0, st));
-        if (chain) {
+        if (block) {
+            ChainBlockParams c{};
+            c.rows = D0.block_rows; c.dict = D0.block_dict; c.stream = D0.chain_stream;
+            c.unknown_of_row = P0.chain.identity_order ? nullptr : D0.chain_unknown;
+            c.IN = IN; c.lanes = lanes; c.L = Lpad; c.n = n; c.input_freq = P0.input_freq; c.status = status_d;
+            c.OUT = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p;
+            if ((rc = launch_chain_block(cplx, P0.chain.block.M, c, st))) return rc;
+        } else if (chain) {
             ChainParams c{};
             c.rowinfo = D0.chain_rowinfo; c.stream = D0.chain_stream; c.unknown_of_row = D0.chain_unknown; c.IN = IN;
             c.UY = D0.G.p; c.X = D0.X[b].p; c.n = n; c.input_freq = P0.input_freq; c.n_u2 = P0.chain.n_u2; c.L = Lpad; c.status = status_d;

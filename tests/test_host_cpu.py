@@ -316,6 +316,88 @@ def test_chain_terms_ac_and_monte_carlo(oracle, golden):
         assert_close(X[:, l], oc.solve_ac([f[l]])[1][0], what=f"chain MC lane {l}")
 
 
+# ---- block-partitioned chain kernel tables (chain_block_kernel.cuh) ------------------------------------------------
+def test_chain_block_tables_ladder_5000(oracle):
+    """BASELINE config 2 shape: T = 256 threads x M = 20 rows; the numpy restatement of the kernel against the oracle."""
+    from vm_emulator import run_chain_block, run_chain, chain_block_info
+    text = netgen.resistor_ladder(5000)
+    kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    plan = kb.Plan(kc, api.MODE_DC, sweep_element=0)
+    valid, T, M, n_dict, diff, why = chain_block_info(plan)
+    assert valid and (T, M) == (256, 20), why
+    assert n_dict <= 6 and diff <= 5e-10            # a ladder has a handful of distinct row records
+    assert plan.info.hbm_bytes_per_point == 8 * 5001 + 8     # inputs in, n results out: SURVEY 8(d)'s fused floor
+    vals = np.array([-1.5, 0.25, 3.0])
+    X, status = run_chain_block(plan, vals[None, :], False)
+    assert not status.any()
+    assert_close(X.T, np.array([oc_solve_dc_point(oc, v) for v in vals]), what="block chain DC")
+    Xs, _ = run_chain(plan, vals[None, :], False)
+    assert_close(X, Xs, rtol=5e-10, what="block vs sequential chain")
+
+
+def oc_solve_dc_point(oc, v):
+    return oc.solve_dc("V1", v, v, 1.0)[0]
+
+
+def test_chain_block_tables_rc_ladder_ac(oracle):
+    """BASELINE config 3 shape (complex): T = 512 x M = 10, frequencies across eight decades."""
+    from vm_emulator import run_chain_block, chain_block_info
+    text = netgen.rc_ladder(5000)
+    kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    plan = kb.Plan(kc, api.MODE_AC, nominal_frequency=1e4)
+    valid, T, M, _, _, why = chain_block_info(plan)
+    assert valid and (T, M) == (512, 10), why
+    freqs = np.array([1.0, 1e3, 1e6, 1e8])
+    X, status = run_chain_block(plan, freqs[None, :], True)
+    assert not status.any()
+    assert_close(X.T, oc.solve_ac(freqs)[1], what="block chain AC")
+
+
+def test_chain_block_small_forced_monte_carlo_and_order(oracle, monkeypatch):
+    """KRB_CHAIN_BLOCK=1 admits small systems (mostly padding rows): Monte-Carlo term runs on every row, a pivot order that is
+    not the unknown order, and the default (n < 512 keeps the sequential kernel)."""
+    from vm_emulator import run_chain_block, run_chain, chain_block_info
+    text = netgen.rc_ladder(40)
+    kc = kb.parse_circuit_description(text)
+    assert not chain_block_info(kb.Plan(kc, api.MODE_AC))[0]
+    monkeypatch.setenv("KRB_CHAIN_BLOCK", "1")
+    varied = [kc.element_index(f"R{k}") for k in range(1, 41)] + [kc.element_index(f"C{k}") for k in (2, 7, 40)]
+    lanes = 3
+    rng = np.random.default_rng(5)
+    vals = np.array([[kc.element_value(e) * (0.9 + 0.2 * rng.random()) for _ in range(lanes)] for e in varied])
+    plan = kb.Plan(kc, api.MODE_AC, varied=varied)
+    valid, T, M, _, _, why = chain_block_info(plan)
+    assert valid and (T, M) == (512, 4), why
+    _, fi, iov = input_layout(plan)
+    IN = np.zeros((plan.info.n_inputs, lanes))
+    f = np.array([10.0, 1e4, 1e7])
+    IN[fi] = f
+    for k, pl in enumerate(iov):
+        IN[pl] = vals[k]
+    X, status = run_chain_block(plan, IN, True)
+    assert not status.any()
+    for l in range(lanes):
+        oc = oracle.Circuit(text)
+        for k, e in enumerate(varied):
+            oc.set_element_value(e, vals[k, l])
+        assert_close(X[:, l], oc.solve_ac([f[l]])[1][0], what=f"block chain MC lane {l}")
+    # resistors listed from the grounded end, source last: unknown order is the reverse of the elimination order
+    lines = [f"R{k} n{k} n{k + 1} 1k" for k in range(30, 0, -1)] + ["R31 n31 0 1k", "V1 n1 0 2"]
+    text = "\n".join(lines) + "\n"
+    kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    plan = kb.Plan(kc, api.MODE_DC, sweep_element=kc.element_index("V1"))
+    if plan.info.executor == 1 and chain_block_info(plan)[0]:
+        vals = np.array([0.5, 2.0])
+        X, _ = run_chain_block(plan, vals[None, :], False)
+        for l, v in enumerate(vals):
+            assert_close(X[:, l], oc.solve_dc("V1", v, v, 1.0)[0], what="block chain, permuted order")
+        Xs, _ = run_chain(plan, vals[None, :], False)
+        assert_close(X, Xs, rtol=1e-11, what="block vs sequential, permuted order")
+    # KRB_CHAIN_BLOCK=0 switches the tables off
+    monkeypatch.setenv("KRB_CHAIN_BLOCK", "0")
+    assert not chain_block_info(kb.Plan(kb.parse_circuit_description(netgen.resistor_ladder(5000)), api.MODE_DC, sweep_element=0))[0]
+
+
 # ---- trapezoidal / lag-free integrators (north-star extension; not reference behaviour) ---------------------------
 def test_trapezoidal_oracle_vs_closed_form(oracle):
     """The non-reference integrators of the oracle are validated against the closed-form RC response to a sine source:

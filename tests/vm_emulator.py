@@ -273,3 +273,128 @@ def run_chain(plan, IN, cplx):
     assert 2 * i == nw - 2200, "record stream must end with the prefetch padding"
     run_chain.last_fixed_rows = n_fixed
     return X, status
+
+
+# ---- block-partitioned chain kernel (chain_block_kernel.cuh) ------------------------------------------------------
+def chain_block_info(plan):
+    """(valid, T, M, n_dict, nominal_diff, why_not) of the plan's block-partitioned chain tables."""
+    L_ = _lib.lib()
+    L_.krb_plan_chain_block_info.restype = C.c_int32
+    L_.krb_plan_chain_block_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    info = (C.c_int32 * 4)()
+    nd = C.c_double(0.0)
+    rc = L_.krb_plan_chain_block_info(plan._h, info, C.byref(nd))
+    assert rc == 0, "plan has no chain tables"
+    why = "" if info[0] else L_.krb_last_error_string().decode()
+    return bool(info[0]), int(info[1]), int(info[2]), int(info[3]), float(nd.value), why
+
+
+def run_chain_block(plan, IN, cplx):
+    """numpy restatement of krb_chain_block_kernel: Wang partition (T blocks of M rows) + parallel cyclic reduction on the
+    separators.  IN [n_inputs][L] -> X [n][L] (unknown order), status [L]."""
+    L_ = _lib.lib()
+    valid, T, M, n_dict, _, why = chain_block_info(plan)
+    assert valid, f"block tables not valid: {why}"
+    L_.krb_plan_get_chain_block.restype = C.c_int32
+    L_.krb_plan_get_chain_block.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    n = plan.n
+    fw = 8 if cplx else 4
+    rows = np.zeros(2 * T * M, dtype=np.uint32)
+    dict_w = np.zeros(max(n_dict * fw, 1), dtype=np.uint64)
+    assert L_.krb_plan_get_chain_block(plan._h, rows.ctypes.data_as(C.POINTER(C.c_uint32)), dict_w.ctypes.data_as(C.POINTER(C.c_uint64))) == 0
+    rows = rows.reshape(M, T, 2)
+    dict_d = dict_w.view(np.float64)
+    nw = int(L_.krb_plan_chain_size(plan._h))
+    words = np.zeros(nw, dtype=np.uint64)
+    unk = np.zeros(n, dtype=np.int32)
+    L_.krb_plan_get_chain(plan._h, None, words.ctypes.data_as(C.POINTER(C.c_uint64)), unk.ctypes.data_as(C.POINTER(C.c_int32)))
+    dwords = words.view(np.float64)
+    lanes = IN.shape[1]
+    _, freq, _ = input_layout(plan)
+    w = (2.0 * np.pi) * IN[freq] if (cplx and freq >= 0) else np.zeros(lanes)
+    dt = np.complex128 if cplx else np.float64
+    E = np.zeros((5, T, M, lanes), dtype=dt)          # sub, diag, sup1, sup2, rhs of row t*M + j
+    has_u2 = np.zeros((T, M), dtype=bool)
+    for t in range(T):
+        for j in range(M):
+            w0, w1 = int(rows[j, t, 0]), int(rows[j, t, 1])
+            if w0 & 1:
+                d = dict_d[(w0 >> 1) * fw: (w0 >> 1) * fw + fw]
+                if cplx:
+                    E[0, t, j] = d[0] + 1j * (w * d[4]); E[1, t, j] = d[1] + 1j * (w * d[5]); E[2, t, j] = d[2] + 1j * (w * d[6]); E[4, t, j] = d[3]
+                else:
+                    E[0, t, j] = d[0]; E[1, t, j] = d[1]; E[2, t, j] = d[2]; E[4, t, j] = d[3]
+            else:
+                i, nt = w0 >> 1, w1 >> 8
+                has_u2[t, j] = bool(w1 & 2)
+                assert t * M + j < n
+                for q in range(nt):
+                    mw = int(words[2 * (i + q)])
+                    meta, plane, K = mw & 0xFFFFFFFF, mw >> 32, float(dwords[2 * (i + q) + 1])
+                    kind = (meta >> 4) & 0xF
+                    if kind == 0: v = np.full(lanes, K, dtype=dt)
+                    elif kind == 1: v = IN[plane].astype(dt)
+                    elif kind == 2: v = (1.0 / IN[plane]).astype(dt)
+                    elif kind == 3: v = (IN[plane] / K).astype(dt)
+                    elif kind == 4: v = 1j * (w * K)
+                    elif kind == 5: v = 1j * (w * IN[plane])
+                    else: raise ValueError(kind)
+                    if meta & (1 << 8):
+                        v = -v
+                    E[meta & 7, t, j] = E[meta & 7, t, j] + v
+    for t in range(T):                                 # layout rules the kernel relies on
+        js = np.nonzero(has_u2[t])[0]
+        assert len(js) <= 1 and all(j <= M - 3 for j in js), "u2 row next to a block boundary / two per block"
+    assert not np.any(E[3][~has_u2] != 0)
+    sub, diag, sup, sup2, rhs = E
+    status = np.zeros(lanes, dtype=np.int32)
+    with np.errstate(all="ignore"):
+        u = np.zeros((T, M - 1, lanes), dtype=dt); u2 = np.zeros_like(u); y = np.zeros_like(u); l = np.zeros_like(u)
+        for j in range(M - 1):
+            if j == 0:
+                wk, s1, yk, lk = diag[:, 0], sup[:, 0], rhs[:, 0], sub[:, 0]
+            else:
+                wk = diag[:, j] - sub[:, j] * u[:, j - 1]
+                s1 = sup[:, j] - sub[:, j] * u2[:, j - 1]
+                yk = rhs[:, j] - sub[:, j] * y[:, j - 1]
+                lk = -sub[:, j] * l[:, j - 1]
+            inv = 1.0 / wk
+            status[~np.isfinite(inv).all(axis=0)] |= ZERO_PIVOT
+            u[:, j], u2[:, j], y[:, j], l[:, j] = s1 * inv, sup2[:, j] * inv, yk * inv, lk * inv
+        A = -sub[:, M - 1] * l[:, M - 2]
+        Bp = diag[:, M - 1] - sub[:, M - 1] * u[:, M - 2]
+        Dp = rhs[:, M - 1] - sub[:, M - 1] * y[:, M - 2]
+        p = np.zeros((T, M + 1, lanes), dtype=dt); r = np.zeros_like(p); q = np.zeros_like(p)
+        r[:, M - 1] = -1.0
+        for j in range(M - 2, -1, -1):
+            p[:, j] = y[:, j] - u[:, j] * p[:, j + 1] - u2[:, j] * p[:, j + 2]
+            r[:, j] = -u[:, j] * r[:, j + 1] - u2[:, j] * r[:, j + 2]
+            q[:, j] = l[:, j] - u[:, j] * q[:, j + 1] - u2[:, j] * q[:, j + 2]
+        def nxt(v):
+            o = np.zeros_like(v); o[:-1] = v[1:]; return o
+        ss = sup[:, M - 1]
+        Bq = Bp - ss * nxt(q[:, 0]); Cq = -ss * nxt(r[:, 0]); Dq = Dp - ss * nxt(p[:, 0])
+        inv = 1.0 / Bq
+        status[~np.isfinite(inv).all(axis=0)] |= ZERO_PIVOT
+        a, c, d = A * inv, Cq * inv, Dq * inv
+        s = 1
+        while s < T:
+            def sh(v, k):
+                o = np.zeros_like(v)
+                if k > 0: o[k:] = v[:-k]
+                else: o[:k] = v[-k:]
+                return o
+            am, cm, dm, ap, cp, dp = sh(a, s), sh(c, s), sh(d, s), sh(a, -s), sh(c, -s), sh(d, -s)
+            inv = 1.0 / (1.0 - a * cm - c * ap)
+            status[~np.isfinite(inv).all(axis=0)] |= ZERO_PIVOT
+            a, c, d = (-a * am) * inv, (-c * cp) * inv, (d - a * dm - c * dp) * inv
+            s *= 2
+        sprev = np.zeros_like(d); sprev[1:] = d[:-1]
+        x = p[:, :M] - r[:, :M] * d[:, None] - q[:, :M] * sprev[:, None]
+        x[:, M - 1] = d
+    xr = x.reshape(T * M, lanes)
+    assert not np.any(xr[n:] != 0), "padding rows must stay zero"
+    X = np.zeros((n, lanes), dtype=dt)
+    X[unk] = xr[:n]
+    status[~np.isfinite(d).all(axis=0)] |= NONFINITE
+    return X, status
