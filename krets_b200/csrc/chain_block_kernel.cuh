@@ -20,32 +20,38 @@
 namespace krb {
 
 struct ChainBlockParams {
-    const uint2 *rows;           // [M][T]: .x = FIXED ? (dict index << 1) | 1 : (stream unit offset << 1); .y = (#terms << 8) | HAS_U2
+    const uint2 *rows;           // [M][T]: .x = FIXED ? (dict index << 1) | 1 : (stream unit offset << 1); .y = BR_* fields
     const uint4 *dict;           // unique FIXED records (2 units real / 4 units complex)
     const uint4 *stream;         // GENERIC term runs (the sequential kernel's record stream)
     const int *unknown_of_row;   // nullptr when pivot row k delivers unknown k
+    const int *gen_rows;         // shared-dictionary mode: the GENERIC pivot rows in slot order (n_gen entries)
     const double *IN;            // [n_inputs][L]
     void *OUT;                   // point-major x_out[lane][unknown]
     long long lanes;
     long long L;                 // lane stride of the input planes
     int n;
     int input_freq;
+    int n_dict;                  // unique FIXED records
+    int n_gen;                   // GENERIC rows (shared-dictionary mode: n_dict + n_gen <= KRB_BLOCK_DMAX)
     int *status;
 };
 
-// exponent field all-zero (0 / denormal) or all-one (inf / nan): integer pipe only
-__device__ __forceinline__ bool bad_pivot(double w) {
-    const uint32_t hi = (uint32_t)__double2hiint(w);
-    return ((hi & 0x7ff00000u) - 0x00100000u) >= 0x7fe00000u;
-}
+// row word .y: bit 1 HAS_U2, bits 2..15 #terms, bits 16..31 slot of a GENERIC row (shared-dictionary mode)
+enum : uint32_t { BR_HAS_U2 = 2u, BR_NT_SHIFT = 2, BR_NT_MASK = 0x3fffu, BR_SLOT_SHIFT = 16 };
+constexpr int KRB_BLOCK_DMAX = 256;   // entries of the shared-memory dictionary (unique FIXED records + GENERIC rows)
+
+// Pivot health on the integer pipe: key(w) = (exponent field) - 1 as an unsigned number is >= 0x7fe00000 exactly when the
+// exponent field is all-zero (0 / denormal) or all-one (inf / nan); a thread keeps the running maximum of its pivots' keys.
+__device__ __forceinline__ uint32_t pivot_key(double w) { return ((uint32_t)__double2hiint(w) & 0x7ff00000u) - 0x00100000u; }
+constexpr uint32_t KRB_BAD_PIVOT_KEY = 0x7fe00000u;
 
 template <bool CPLX> struct BlockSc;
 template <> struct BlockSc<false> {
     typedef double T;
     // reciprocal of the pivot to ~1 ulp, returned as (r0, t):  q / w = fma(q*r0, t, q*r0)
     struct Inv { double r0, t; };
-    static __device__ __forceinline__ Inv inv(double w, bool &bad) {
-        bad = bad_pivot(w);
+    static __device__ __forceinline__ Inv inv(double w, uint32_t &worst) {
+        worst = max(worst, pivot_key(w));
         const double r0 = rcp_seed(w);
         const double e = fma(-w, r0, 1.0);
         return Inv{r0, fma(e, e, e)};
@@ -57,9 +63,9 @@ template <> struct BlockSc<false> {
 template <> struct BlockSc<true> {
     typedef double2 T;
     struct Inv { double2 c; };    // conj(w) / |w|^2
-    static __device__ __forceinline__ Inv inv(double2 w, bool &bad) {
+    static __device__ __forceinline__ Inv inv(double2 w, uint32_t &worst) {
         const double ns = fma(w.x, w.x, w.y * w.y);
-        bad = bad_pivot(ns);
+        worst = max(worst, pivot_key(ns));
         const double r = fast_rcp(ns);
         return Inv{make_double2(w.x * r, -w.y * r)};
     }
@@ -68,7 +74,50 @@ template <> struct BlockSc<true> {
     static __device__ __forceinline__ double2 one() { return make_double2(1.0, 0.0); }
 };
 
-template <bool CPLX, int T, int M>
+// One GENERIC row: ordered term run, same decoding and summation order as chain_kernel.cuh (bit-identical stamps).
+template <bool CPLX>
+__device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, int nt, const double *__restrict__ IN, long long L, double w,
+                                                 long long prefetch_ahead, typename ChainSc<CPLX>::T &e0, typename ChainSc<CPLX>::T &e1,
+                                                 typename ChainSc<CPLX>::T &e2, typename ChainSc<CPLX>::T &e3, typename ChainSc<CPLX>::T &e4) {
+    typedef ChainSc<CPLX> S;
+    typedef typename S::T V;
+    e0 = S::zero(); e1 = S::zero(); e2 = S::zero(); e3 = S::zero(); e4 = S::zero();
+    for (int q = 0; q < nt; ++q) {
+        const uint4 cur = __ldg(dp + q);
+        const double K = u4hi(cur);
+        const uint32_t kind = (cur.x >> 4) & 0xfu;
+        double re = 0.0, im = 0.0;
+        if (kind == CK_CONST) re = K;
+        else if (kind == CK_JW_K) im = __dmul_rn(w, K);
+        else {
+            const double *src = IN + (size_t)cur.y * L;
+            const double v = __ldg(src);
+            if (prefetch_ahead > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + prefetch_ahead));
+            if (kind == CK_IN) re = v;
+            else if (kind == CK_INV_IN) re = __ddiv_rn(1.0, v);
+            else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
+            else im = __dmul_rn(w, v);
+        }
+        if (cur.x & CT_NEG) { re = -re; im = -im; }
+        const uint32_t tgt = cur.x & 7u;
+        // the target differs from thread to thread: select the accumulator, add once, select back
+        V acc = tgt == CT_SUB ? e0 : tgt == CT_DIAG ? e1 : tgt == CT_SUP1 ? e2 : tgt == CT_SUP2 ? e3 : e4;
+        S::add(acc, re, im);
+        e0 = tgt == CT_SUB ? acc : e0;
+        e1 = tgt == CT_DIAG ? acc : e1;
+        e2 = tgt == CT_SUP1 ? acc : e2;
+        e3 = tgt == CT_SUP2 ? acc : e3;
+        e4 = tgt >= CT_RHS ? acc : e4;
+    }
+}
+
+// SD (shared dictionary): the plan's unique FIXED records and its GENERIC rows together fit KRB_BLOCK_DMAX entries (ladders,
+// RC lines, swept sources: a handful).  Every row then reads its stamped (sub, diag, sup, rhs) from a shared-memory entry:
+// FIXED entries are lane-invariant (real) or refreshed per lane with the lane's w (complex: (re, w*K) is formed once per
+// entry instead of once per row), GENERIC entries are evaluated per lane by one thread each — for the NEXT lane, between
+// the first barrier and the end of the current one, so the main loop is branch-free and no warp waits for a term run.
+// !SD: FIXED rows read the global dictionary (L1), warps owning GENERIC rows decode them inline (Monte-Carlo plans).
+template <bool CPLX, int T, int M, bool SD>
 __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const ChainBlockParams p) {
     typedef ChainSc<CPLX> S;
     typedef BlockSc<CPLX> B;
@@ -76,35 +125,143 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
     constexpr int MI = M - 1;               // interior rows per thread
     constexpr int XS = M + 1;               // stride of a thread's shared-memory column (odd: conflict-free)
     constexpr int FIX_UNITS = CPLX ? 4 : 2;
+    constexpr int NW = T / 32;
     extern __shared__ __align__(16) unsigned char krb_block_smem[];
     V *xq = reinterpret_cast<V *>(krb_block_smem);   // [T][XS]: l^_j -> q_j -> x_j
     V *red = xq + T * XS;                              // [2][3][T]: cyclic-reduction rows (a, c, d), double-buffered
     V *fst = red + 3 * T;                              // [3][T]: (p, r, q) of each block's first row; aliases buffer 1
+    V *sd = red + 6 * T;                               // SD: [KRB_BLOCK_DMAX][4] stamped (sub, diag, sup, rhs) per entry
+    V *pe3 = sd + 4 * KRB_BLOCK_DMAX;                  // SD: [KRB_BLOCK_DMAX] second super-diagonal of a GENERIC entry
     const int t = threadIdx.x;
     V *mycol = xq + t * XS;
     const long long L = p.L;
     const int n = p.n;
 
+    // The rows a thread owns do not depend on the lane: dictionary / entry indices are packed two per register once.
+    uint32_t pk[(M + 1) / 2];
+    bool my_generic = false;
+    int ju = -1, gu = 0;                     // SD: local index / entry of this block's row with a second super-diagonal
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        const uint2 rw = __ldg(p.rows + j * T + t);
+        uint32_t idx = rw.x >> 1;
+        if (!(rw.x & 1u)) {
+            my_generic = true;
+            if (SD) {
+                idx = (uint32_t)p.n_dict + (rw.y >> BR_SLOT_SHIFT);
+                if (rw.y & BR_HAS_U2) { ju = j; gu = (int)idx; }
+            }
+        }
+        if (j & 1) pk[j >> 1] |= idx << 16; else pk[j >> 1] = idx & 0xffffu;
+    }
+    const bool warp_generic = __any_sync(0xffffffffu, my_generic);
+    const bool warp_u2 = __any_sync(0xffffffffu, ju >= 0);
+    (void)warp_generic; (void)warp_u2; (void)gu; (void)sd; (void)pe3;
+
+    // SD: (re)build the entries for `lane`; entry d is handled by thread (d % NW) * 32 + d / NW, i.e. spread over the warps
+    auto refresh = [&](long long lane, double w, long long ahead) {
+        const int n_entries = p.n_dict + p.n_gen;
+        for (int d = (t & 31) * NW + (t >> 5); d < n_entries; d += T) {
+            if (d < p.n_dict) {
+                if (CPLX) {
+                    const uint4 *g = p.dict + (size_t)d * FIX_UNITS;
+                    const uint4 c0 = __ldg(g), c1 = __ldg(g + 1), c2 = __ldg(g + 2), c3 = __ldg(g + 3);
+                    sd[4 * d + 0] = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
+                    sd[4 * d + 1] = S::make(u4hi(c0), __dmul_rn(w, u4hi(c2)));
+                    sd[4 * d + 2] = S::make(u4lo(c1), __dmul_rn(w, u4lo(c3)));
+                    sd[4 * d + 3] = S::make(u4hi(c1), 0.0);
+                }
+            } else {
+                const int row = __ldg(p.gen_rows + (d - p.n_dict));
+                const uint2 rw = __ldg(p.rows + (row % M) * T + row / M);
+                V e0, e1, e2, e3, e4;
+                block_eval_terms<CPLX>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), p.IN + lane, L, w, ahead, e0, e1, e2, e3, e4);
+                sd[4 * d + 0] = e0; sd[4 * d + 1] = e1; sd[4 * d + 2] = e2; sd[4 * d + 3] = e4;
+                pe3[d] = e3;
+            }
+        }
+    };
+    const double TWO_PI = 2.0 * 3.14159265358979323846264338327950288;
+    if (SD) {
+        if (!CPLX)
+            for (int d = t; d < p.n_dict; d += T) {
+                const uint4 *g = p.dict + (size_t)d * FIX_UNITS;
+                const uint4 c0 = __ldg(g), c1 = __ldg(g + 1);
+                sd[4 * d + 0] = S::make(u4lo(c0), 0.0); sd[4 * d + 1] = S::make(u4hi(c0), 0.0);
+                sd[4 * d + 2] = S::make(u4lo(c1), 0.0); sd[4 * d + 3] = S::make(u4hi(c1), 0.0);
+            }
+        if ((long long)blockIdx.x < p.lanes) {
+            double w0 = 0.0;
+            if (CPLX && p.input_freq >= 0) w0 = __dmul_rn(TWO_PI, __ldg(p.IN + blockIdx.x + (size_t)p.input_freq * L));
+            refresh(blockIdx.x, w0, (long long)blockIdx.x + gridDim.x < p.lanes ? (long long)gridDim.x : 0);
+        }
+        __syncthreads();
+    }
+
     for (long long lane = blockIdx.x; lane < p.lanes; lane += gridDim.x) {
         const double *__restrict__ IN = p.IN + lane;
-        double w = 0.0;                              // (2.0 * PI) * f, rounded once as the reference does
-        if (CPLX && p.input_freq >= 0) w = __dmul_rn(2.0 * 3.14159265358979323846264338327950288, __ldg(IN + (size_t)p.input_freq * L));
-        bool bad = false;
+        const long long next = lane + gridDim.x;
+        double w = 0.0, f_next = 1.0;                // w = (2.0 * PI) * f, rounded once as the reference does
+        if (CPLX && p.input_freq >= 0) {
+            if (!SD) w = __dmul_rn(TWO_PI, __ldg(IN + (size_t)p.input_freq * L));
+            else if (next < p.lanes) f_next = __ldg(p.IN + next + (size_t)p.input_freq * L);   // consumed after the first barrier
+        }
+        uint32_t worst = 0;                          // running maximum of the pivots' keys (pivot_key)
         V u[MI], y[MI];
         V lprev = S::zero(), pu2 = S::zero(), u2v = S::zero();
-        bool pu2_live = false;
-        int ju = -1;                                 // local index of this block's row with a second super-diagonal
         V sepA = S::zero(), sepB = S::zero(), sepD = S::zero(), sepS = S::zero();
 
         // ---- 1. stamp + top-down elimination of the interior rows; separator row partially reduced ----
+        // one interior row:  w_k = diag - sub u^_{k-1},  u^ = sup1'/w_k,  y^ = (rhs - sub y^_{k-1})/w_k,  l^ = -sub l^_{k-1}/w_k
+        auto interior = [&](int j, V e0, V e1, V s1, V e4) {
+            V wk, yk, lk;
+            if (j == 0) { wk = e1; yk = e4; lk = e0; }
+            else {
+                wk = S::fnma(e1, e0, u[j > 0 ? j - 1 : 0]);
+                yk = S::fnma(e4, e0, y[j > 0 ? j - 1 : 0]);
+                lk = B::neg(S::mul(e0, lprev));
+            }
+            const typename B::Inv iv = B::inv(wk, worst);
+            u[j] = B::div(s1, iv);
+            y[j] = B::div(yk, iv);
+            lprev = B::div(lk, iv);
+            mycol[j] = lprev;
+            return iv;
+        };
+        // separator row: sub * x_{last interior} substituted from the forward-eliminated last interior row
+        auto separator = [&](V e0, V e1, V e2, V e4) {
+            sepA = B::neg(S::mul(e0, lprev));
+            sepB = S::fnma(e1, e0, u[MI - 1]);
+            sepD = S::fnma(e4, e0, y[MI - 1]);
+            sepS = e2;
+        };
+        if (SD) {
+            if (!warp_u2) {
 #pragma unroll
-        for (int j = 0; j < M; ++j) {
-            const uint2 rw = __ldg(p.rows + j * T + t);
-            V e0, e1, e2, e3 = S::zero(), e4;
-            bool has_u2 = false;
-            if (rw.x & 1u) {
-                const uint4 *d = p.dict + (size_t)(rw.x >> 1) * FIX_UNITS;
+                for (int j = 0; j < M; ++j) {
+                    const V *e = sd + 4 * ((pk[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+                    if (j < MI) interior(j, e[0], e[1], e[2], e[3]);
+                    else separator(e[0], e[1], e[2], e[3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const V *e = sd + 4 * ((pk[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+                    if (j < MI) {
+                        V s1 = e[2];
+                        if (j > 0 && j - 1 == ju) s1 = S::fnma(s1, e[0], pu2);     // fill from the row above's second super-diagonal
+                        const typename B::Inv iv = interior(j, e[0], e[1], s1, e[3]);
+                        if (j == ju) { pu2 = B::div(pe3[gu], iv); u2v = pu2; }
+                    } else separator(e[0], e[1], e[2], e[3]);
+                }
+            }
+        } else if (!warp_generic) {
+            // every row of this warp is a FIXED record: branch-free, the record loads of later rows overlap the recurrence
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const uint4 *d = p.dict + (size_t)((pk[j >> 1] >> ((j & 1) * 16)) & 0xffffu) * FIX_UNITS;
                 const uint4 c0 = __ldg(d), c1 = __ldg(d + 1);
+                V e0, e1, e2, e4;
                 if (CPLX) {
                     const uint4 c2 = __ldg(d + 2), c3 = __ldg(d + 3);
                     e0 = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
@@ -114,71 +271,47 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
                 } else {
                     e0 = S::make(u4lo(c0), 0.0); e1 = S::make(u4hi(c0), 0.0); e2 = S::make(u4lo(c1), 0.0); e4 = S::make(u4hi(c1), 0.0);
                 }
-            } else {
-                // GENERIC row: ordered term run (same decoding and summation order as chain_kernel.cuh)
-                const uint4 *dp = p.stream + (rw.x >> 1);
-                const int nt = (int)(rw.y >> RI_NTERMS_SHIFT);
-                has_u2 = (rw.y & RI_HAS_U2) != 0;
-                e0 = S::zero(); e1 = S::zero(); e2 = S::zero(); e4 = S::zero();
-                for (int q = 0; q < nt; ++q) {
-                    const uint4 cur = __ldg(dp + q);
-                    const double K = u4hi(cur);
-                    const uint32_t kind = (cur.x >> 4) & 0xfu;
-                    double re = 0.0, im = 0.0;
-                    if (kind == CK_CONST) re = K;
-                    else if (kind == CK_JW_K) im = __dmul_rn(w, K);
-                    else {
-                        const double v = __ldg(IN + (size_t)cur.y * L);
-                        if (kind == CK_IN) re = v;
-                        else if (kind == CK_INV_IN) re = __ddiv_rn(1.0, v);
-                        else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
-                        else im = __dmul_rn(w, v);
-                    }
-                    if (cur.x & CT_NEG) { re = -re; im = -im; }
-                    const uint32_t tgt = cur.x & 7u;
-                    // the target differs from thread to thread: select the accumulator, add once, select back
-                    V acc = tgt == CT_SUB ? e0 : tgt == CT_DIAG ? e1 : tgt == CT_SUP1 ? e2 : tgt == CT_SUP2 ? e3 : e4;
-                    S::add(acc, re, im);
-                    e0 = tgt == CT_SUB ? acc : e0;
-                    e1 = tgt == CT_DIAG ? acc : e1;
-                    e2 = tgt == CT_SUP1 ? acc : e2;
-                    e3 = tgt == CT_SUP2 ? acc : e3;
-                    e4 = tgt >= CT_RHS ? acc : e4;
-                }
+                if (j < MI) interior(j, e0, e1, e2, e4);
+                else separator(e0, e1, e2, e4);
             }
-            if (j < MI) {
-                V wk, s1, yk, lk;
-                if (j == 0) { wk = e1; s1 = e2; yk = e4; lk = e0; }
-                else {
-                    wk = S::fnma(e1, e0, u[j - 1]);
-                    s1 = pu2_live ? S::fnma(e2, e0, pu2) : e2;
-                    yk = S::fnma(e4, e0, y[j - 1]);
-                    lk = B::neg(S::mul(e0, lprev));
+        } else {
+            // general path: GENERIC rows decoded inline (Monte-Carlo plans: every row of the warp is one)
+            bool pu2_live = false;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const uint2 rw = __ldg(p.rows + j * T + t);
+                V e0, e1, e2, e3 = S::zero(), e4;
+                bool has_u2 = false;
+                if (rw.x & 1u) {
+                    const uint4 *d = p.dict + (size_t)(rw.x >> 1) * FIX_UNITS;
+                    const uint4 c0 = __ldg(d), c1 = __ldg(d + 1);
+                    if (CPLX) {
+                        const uint4 c2 = __ldg(d + 2), c3 = __ldg(d + 3);
+                        e0 = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
+                        e1 = S::make(u4hi(c0), __dmul_rn(w, u4hi(c2)));
+                        e2 = S::make(u4lo(c1), __dmul_rn(w, u4lo(c3)));
+                        e4 = S::make(u4hi(c1), 0.0);
+                    } else {
+                        e0 = S::make(u4lo(c0), 0.0); e1 = S::make(u4hi(c0), 0.0); e2 = S::make(u4lo(c1), 0.0); e4 = S::make(u4hi(c1), 0.0);
+                    }
+                } else {
+                    has_u2 = (rw.y & BR_HAS_U2) != 0;
+                    block_eval_terms<CPLX>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), IN, L, w, 0, e0, e1, e2, e3, e4);
                 }
-                bool b1;
-                const typename B::Inv iv = B::inv(wk, b1);
-                bad = bad || b1;
-                u[j] = B::div(s1, iv);
-                y[j] = B::div(yk, iv);
-                lprev = B::div(lk, iv);
-                mycol[j] = lprev;
-                pu2_live = has_u2;
-                if (has_u2) { pu2 = B::div(e3, iv); u2v = pu2; ju = j; }
-            } else {
-                // separator row: sub * x_{last interior} substituted from the forward-eliminated last interior row
-                sepA = B::neg(S::mul(e0, lprev));
-                sepB = S::fnma(e1, e0, u[MI - 1]);
-                sepD = S::fnma(e4, e0, y[MI - 1]);
-                sepS = e2;
+                if (j < MI) {
+                    const V s1 = (j > 0 && pu2_live) ? S::fnma(e2, e0, pu2) : e2;
+                    const typename B::Inv iv = interior(j, e0, e1, s1, e4);
+                    pu2_live = has_u2;
+                    if (has_u2) { pu2 = B::div(e3, iv); u2v = pu2; ju = j; }
+                } else separator(e0, e1, e2, e4);
             }
         }
 
         // ---- 2. bottom-up: x_j = p_j - r_j s_t - q_j s_{t-1}  (p in y[], r in u[], q in the shared column) ----
         {
             // last interior row: the virtual separator row below it is (p, r, q) = (0, -1, 0)
-            V qn = mycol[MI - 1];                     // q_{M-2} = l^_{M-2}
-            // p_{M-2} = y^, r_{M-2} = u^: already in place
-            if (__any_sync(0xffffffffu, ju >= 0)) {
+            V qn = lprev;                             // q_{M-2} = l^_{M-2}; p_{M-2} = y^, r_{M-2} = u^ are already in place
+            if (SD ? warp_u2 : __any_sync(0xffffffffu, ju >= 0)) {
                 V p2 = S::zero(), r2 = B::neg(B::one()), q2 = S::zero();   // row j+2 (starts at the virtual separator)
 #pragma unroll
                 for (int j = MI - 2; j >= 0; --j) {
@@ -204,6 +337,8 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             fst[t] = y[0]; fst[T + t] = u[0]; fst[2 * T + t] = qn;
         }
         __syncthreads();
+        // SD: nobody reads the entries any more for this lane: build the next lane's
+        if (SD && next < p.lanes) refresh(next, CPLX ? __dmul_rn(TWO_PI, f_next) : 0.0, next + gridDim.x < p.lanes ? (long long)gridDim.x : 0);
 
         // ---- 3. separator system: A s_{t-1} + B s_t + C s_{t+1} = D, parallel cyclic reduction ----
         V a, c, d;
@@ -213,9 +348,7 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             const V bb = S::fnma(sepB, sepS, qn);
             const V cc = B::neg(S::mul(sepS, rn));
             const V dd = S::fnma(sepD, sepS, pn);
-            bool b1;
-            const typename B::Inv iv = B::inv(bb, b1);
-            bad = bad || b1;
+            const typename B::Inv iv = B::inv(bb, worst);
             a = B::div(sepA, iv); c = B::div(cc, iv); d = B::div(dd, iv);
         }
         red[t] = a; red[T + t] = c; red[2 * T + t] = d;
@@ -232,9 +365,7 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             const V a2 = B::neg(S::mul(a, am));
             const V c2 = B::neg(S::mul(c, cp));
             const V d2 = S::fnma(S::fnma(d, a, dm), c, dq);
-            bool b1;
-            const typename B::Inv iv = B::inv(b2, b1);
-            bad = bad || b1;
+            const typename B::Inv iv = B::inv(b2, worst);
             a = B::div(a2, iv); c = B::div(c2, iv); d = B::div(d2, iv);
             dst[t] = a; dst[T + t] = c; dst[2 * T + t] = d;
             __syncthreads();
@@ -247,15 +378,24 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
 #pragma unroll
         for (int j = 0; j < MI; ++j) mycol[j] = S::fnma(S::fnma(y[j], u[j], st), mycol[j], sm);
         mycol[MI] = st;
-        int status = bad ? KRB_LANE_ZERO_PIVOT : 0;
+        int status = worst >= KRB_BAD_PIVOT_KEY ? KRB_LANE_ZERO_PIVOT : 0;
         if (!S::finite(st)) status |= KRB_LANE_NONFINITE;
         if (status && p.status) atomicOr(p.status + lane, status);
         __syncthreads();
         V *__restrict__ out = reinterpret_cast<V *>(p.OUT) + (size_t)lane * (size_t)n;
+        // pivot row i lives at xq[(i / M) * XS + i % M] = xq[i + i / M]
         if (p.unknown_of_row == nullptr) {
-            for (int i = t; i < n; i += T) __stcs(out + i, xq[(i / M) * XS + (i % M)]);
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                const int i = t + k * T;
+                if (i < n) __stcs(out + i, xq[i + i / M]);
+            }
         } else {
-            for (int i = t; i < n; i += T) __stcs(out + __ldg(p.unknown_of_row + i), xq[(i / M) * XS + (i % M)]);
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                const int i = t + k * T;
+                if (i < n) __stcs(out + __ldg(p.unknown_of_row + i), xq[i + i / M]);
+            }
         }
         __syncthreads();                              // the columns and the reduction buffers are reused by the next lane
     }

@@ -667,6 +667,12 @@ static void build_chain_block(Plan &plan, const std::vector<uint32_t> &row_off, 
     std::vector<uint64_t> pad_rec(fw, 0);
     { const double one = 1.0; std::memcpy(&pad_rec[1], &one, 8); }
     bk.rows.assign((size_t)2 * T * M, 0u);
+    bk.gen_rows.clear();
+    for (int k = 0; k < n; k++)
+        if (!(ch.rowinfo[k] & 1u)) {
+            if ((ch.rowinfo[k] >> 8) > 0x3fffu) { bk = ChainPlan::Block(); bk.why_not = "a row has more than 16383 stamp terms"; return; }
+            bk.gen_rows.push_back(k);
+        }
     for (int t = 0; t < T; t++)
         for (int j = 0; j < M; j++) {
             const int k = t * M + j;
@@ -675,11 +681,19 @@ static void build_chain_block(Plan &plan, const std::vector<uint32_t> &row_off, 
             else if (ch.rowinfo[k] & 1u) {
                 std::vector<uint64_t> rec(ch.stream.begin() + (size_t)row_off[k] * 2, ch.stream.begin() + (size_t)row_off[k] * 2 + fw);
                 w0 = (intern(rec) << 1) | 1u;
-            } else { w0 = row_off[k] << 1; w1 = ch.rowinfo[k] & ~1u; }
+            } else {
+                // word 1: bit 1 HAS_U2, bits 2..15 #terms, bits 16..31 slot (rank among the GENERIC rows, when it fits)
+                const uint32_t slot = (uint32_t)(std::lower_bound(bk.gen_rows.begin(), bk.gen_rows.end(), k) - bk.gen_rows.begin());
+                w0 = row_off[k] << 1;
+                w1 = (ch.rowinfo[k] & 2u) | ((ch.rowinfo[k] >> 8) << 2) | ((slot & 0xffffu) << 16);
+            }
             bk.rows[((size_t)j * T + t) * 2 + 0] = w0;
             bk.rows[((size_t)j * T + t) * 2 + 1] = w1;
         }
     bk.n_dict = (int)index.size();
+    if (bk.n_dict > 0xffff) { bk = ChainPlan::Block(); bk.why_not = "dictionary index does not fit 16 bits"; return; }
+    // shared-dictionary mode of the kernel: unique FIXED records + GENERIC rows fit the on-chip table
+    bk.shared_dict = bk.n_dict + (int)bk.gen_rows.size() <= 256 && getenv("KRB_CHAIN_BLOCK_NO_SD") == nullptr;
     bk.T = T; bk.M = M;
     bk.valid = true;
 }

@@ -113,9 +113,11 @@ struct ChainPlan {
         bool valid = false;
         int T = 0, M = 0;                // n <= T * M; rows >= n are identity padding
         std::vector<uint32_t> rows;      // [M][T][2]: word 0 = FIXED ? (dictionary index << 1) | 1 : (stream unit offset << 1);
-                                         //            word 1 = (#terms << 8) | (HAS_U2 ? 2 : 0)
+                                         //            word 1 = (HAS_U2 ? 2 : 0) | #terms << 2 | slot << 16
         std::vector<uint64_t> dict;      // unique FIXED records, 4 (real) / 8 (complex) words each, same layout as in `stream`
         int n_dict = 0;
+        std::vector<int> gen_rows;       // GENERIC pivot rows, ascending (slot order)
+        bool shared_dict = false;        // n_dict + #GENERIC rows <= 256: the kernel keeps every row's stamped values in a shared-memory table
         double nominal_diff = 0.0;       // max scaled |x_block - x_sequential| at the nominal inputs (host check, must be <= 5e-10)
         std::string why_not;             // reason the block kernel is not applicable (diagnostics)
     } block;

@@ -73,6 +73,7 @@ struct DeviceState {
     uint32_t *chain_runs = nullptr;
     uint2 *block_rows = nullptr;         // block-partitioned chain kernel tables
     uint4 *block_dict = nullptr;
+    int *block_gen = nullptr;
     DenseElem *dense_elems = nullptr;    // dense transient executor tables
     DenseTerm *dense_mat = nullptr, *dense_rhs = nullptr;
     int *dense_state = nullptr, *dense_col_order = nullptr;
@@ -122,6 +123,7 @@ void device_state_free(DeviceState *d) {
     if (d->chain_runs) cudaFree(d->chain_runs);
     if (d->block_rows) cudaFree(d->block_rows);
     if (d->block_dict) cudaFree(d->block_dict);
+    if (d->block_gen) cudaFree(d->block_gen);
     if (d->B) cudaFree(d->B);
     if (d->dense_elems) cudaFree(d->dense_elems);
     if (d->dense_mat) cudaFree(d->dense_mat);
@@ -167,6 +169,7 @@ static int upload_plan(Plan &plan, DeviceState &d) {
         if (plan.chain.block.valid) {
             if ((rc = upload_vec(plan.chain.block.rows, (uint32_t **)&d.block_rows))) return rc;
             if ((rc = upload_vec(plan.chain.block.dict, (uint64_t **)&d.block_dict))) return rc;
+            if ((rc = upload_vec(plan.chain.block.gen_rows, &d.block_gen))) return rc;
         }
     }
     if (plan.dense.valid) {
@@ -236,46 +239,50 @@ static int launch_chain(bool cplx, int tpb, bool direct, const ChainParams &p, l
 }
 
 // block-partitioned chain kernel: persistent CTAs (one lane at a time each), grid = resident CTAs of the device
-template <bool CPLX, int T, int M>
+template <bool CPLX, int T, int M, bool SD>
 static int launch_chain_block_t(const ChainBlockParams &p, cudaStream_t st) {
     typedef typename ChainSc<CPLX>::T V;
-    const size_t smem = ((size_t)T * (M + 1) + (size_t)6 * T) * sizeof(V);
+    const size_t smem = ((size_t)T * (M + 1) + (size_t)6 * T + (SD ? (size_t)5 * KRB_BLOCK_DMAX : 0)) * sizeof(V);
     static int resident = 0;
     if (!resident) {
-        CUDA_TRY(cudaFuncSetAttribute(krb_chain_block_kernel<CPLX, T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(krb_chain_block_kernel<CPLX, T, M, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0, sms = 0, per_sm = 0;
         CUDA_TRY(cudaGetDevice(&dev));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krb_chain_block_kernel<CPLX, T, M>, T, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krb_chain_block_kernel<CPLX, T, M, SD>, T, smem));
         if (per_sm < 1) { set_error("block chain kernel does not fit on an SM"); return KRB_ERR_INTERNAL; }
         resident = sms * per_sm;
     }
     const unsigned grid = (unsigned)std::min<long long>(p.lanes, resident);
-    krb_chain_block_kernel<CPLX, T, M><<<grid, T, smem, st>>>(p);
+    krb_chain_block_kernel<CPLX, T, M, SD><<<grid, T, smem, st>>>(p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return KRB_OK;
 }
-static int launch_chain_block(bool cplx, int M, const ChainBlockParams &p, cudaStream_t st) {
+template <bool SD>
+static int launch_chain_block_s(bool cplx, int M, const ChainBlockParams &p, cudaStream_t st) {
     if (cplx) {
         switch (M) {
-        case 2: return launch_chain_block_t<true, 512, 2>(p, st);
-        case 4: return launch_chain_block_t<true, 512, 4>(p, st);
-        case 6: return launch_chain_block_t<true, 512, 6>(p, st);
-        case 8: return launch_chain_block_t<true, 512, 8>(p, st);
-        case 10: return launch_chain_block_t<true, 512, 10>(p, st);
+        case 2: return launch_chain_block_t<true, 512, 2, SD>(p, st);
+        case 4: return launch_chain_block_t<true, 512, 4, SD>(p, st);
+        case 6: return launch_chain_block_t<true, 512, 6, SD>(p, st);
+        case 8: return launch_chain_block_t<true, 512, 8, SD>(p, st);
+        case 10: return launch_chain_block_t<true, 512, 10, SD>(p, st);
         }
     } else {
         switch (M) {
-        case 4: return launch_chain_block_t<false, 256, 4>(p, st);
-        case 8: return launch_chain_block_t<false, 256, 8>(p, st);
-        case 12: return launch_chain_block_t<false, 256, 12>(p, st);
-        case 16: return launch_chain_block_t<false, 256, 16>(p, st);
-        case 20: return launch_chain_block_t<false, 256, 20>(p, st);
+        case 4: return launch_chain_block_t<false, 256, 4, SD>(p, st);
+        case 8: return launch_chain_block_t<false, 256, 8, SD>(p, st);
+        case 12: return launch_chain_block_t<false, 256, 12, SD>(p, st);
+        case 16: return launch_chain_block_t<false, 256, 16, SD>(p, st);
+        case 20: return launch_chain_block_t<false, 256, 20, SD>(p, st);
         }
     }
     set_error("block chain kernel: no compiled shape for this plan");
     return KRB_ERR_INTERNAL;
+}
+static int launch_chain_block(bool cplx, int M, bool shared_dict, const ChainBlockParams &p, cudaStream_t st) {
+    return shared_dict ? launch_chain_block_s<true>(cplx, M, p, st) : launch_chain_block_s<false>(cplx, M, p, st);
 }
 
 template <int N, int NSP, int NWP>
@@ -470,8 +477,9 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             c.rows = D0.block_rows; c.dict = D0.block_dict; c.stream = D0.chain_stream;
             c.unknown_of_row = P0.chain.identity_order ? nullptr : D0.chain_unknown;
             c.IN = IN; c.lanes = lanes; c.L = Lpad; c.n = n; c.input_freq = P0.input_freq; c.status = status_d;
+            c.gen_rows = D0.block_gen; c.n_dict = P0.chain.block.n_dict; c.n_gen = (int)P0.chain.block.gen_rows.size();
             c.OUT = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p;
-            if ((rc = launch_chain_block(cplx, P0.chain.block.M, c, st))) return rc;
+            if ((rc = launch_chain_block(cplx, P0.chain.block.M, P0.chain.block.shared_dict, c, st))) return rc;
         } else if (chain) {
             ChainParams c{};
             c.rowinfo = D0.chain_rowinfo; c.stream = D0.chain_stream; c.unknown_of_row = D0.chain_unknown; c.IN = IN;

@@ -315,6 +315,7 @@ def run_chain_block(plan, IN, cplx):
     dt = np.complex128 if cplx else np.float64
     E = np.zeros((5, T, M, lanes), dtype=dt)          # sub, diag, sup1, sup2, rhs of row t*M + j
     has_u2 = np.zeros((T, M), dtype=bool)
+    slots = []
     for t in range(T):
         for j in range(M):
             w0, w1 = int(rows[j, t, 0]), int(rows[j, t, 1])
@@ -325,8 +326,9 @@ def run_chain_block(plan, IN, cplx):
                 else:
                     E[0, t, j] = d[0]; E[1, t, j] = d[1]; E[2, t, j] = d[2]; E[4, t, j] = d[3]
             else:
-                i, nt = w0 >> 1, w1 >> 8
+                i, nt = w0 >> 1, (w1 >> 2) & 0x3FFF           # word 1: bit 1 HAS_U2, bits 2..15 #terms, bits 16.. slot
                 has_u2[t, j] = bool(w1 & 2)
+                slots.append((t * M + j, w1 >> 16))
                 assert t * M + j < n
                 for q in range(nt):
                     mw = int(words[2 * (i + q)])
@@ -342,6 +344,8 @@ def run_chain_block(plan, IN, cplx):
                     if meta & (1 << 8):
                         v = -v
                     E[meta & 7, t, j] = E[meta & 7, t, j] + v
+    if len(slots) < 65536:                             # slot = rank among the GENERIC rows (shared-dictionary mode)
+        assert [sl for _, sl in sorted(slots)] == list(range(len(slots)))
     for t in range(T):                                 # layout rules the kernel relies on
         js = np.nonzero(has_u2[t])[0]
         assert len(js) <= 1 and all(j <= M - 3 for j in js), "u2 row next to a block boundary / two per block"
