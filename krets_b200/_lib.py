@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkrets_b200.so")
+# KRETS_B200_LIB: profiling knob — load another build of the same library (tools/build_variant.sh), never a fallback
+LIB_PATH = os.environ.get("KRETS_B200_LIB") or os.path.join(_HERE, "libkrets_b200.so")
 
 
 class KrbElement(C.Structure):          # krb_element

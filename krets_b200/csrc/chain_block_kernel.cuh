@@ -17,6 +17,26 @@
 #pragma once
 #include "chain_kernel.cuh"
 
+#ifndef KRB_BX_L1PF
+#define KRB_BX_L1PF 0       // next lane's inputs are prefetched into L1 (0: L2) by the thread that will read them
+#endif
+#ifndef KRB_BX_CR
+#define KRB_BX_CR 1         // separator system: one cyclic-reduction level, then PCR on T/2 rows by half the warps
+                            // (1: complex plans only — measured: c64 -13 %, f64 +4 %; 2: always; 0: never)
+#endif
+#ifndef KRB_BX_PIPE1
+#define KRB_BX_PIPE1 1      // experiment: dictionary entries fetched exactly one row ahead
+#endif
+#ifndef KRB_BX_UNIFORM
+#define KRB_BX_UNIFORM 1    // warps whose threads each stamp all their rows from one entry read it once per lane
+#endif
+#ifndef KRB_BX_FWDACC
+#define KRB_BX_FWDACC 1     // (p, r, q) of a block's first row accumulated top-down inside step 1 (no bottom-up pass)
+#endif
+#ifndef KRB_BX_RECUR
+#define KRB_BX_RECUR 1      // step 2 carries (p, r, q) of the first row as scalars, step 4 is a back substitution
+#endif
+
 namespace krb {
 
 struct ChainBlockParams {
@@ -59,6 +79,7 @@ template <> struct BlockSc<false> {
     static __device__ __forceinline__ double div(double a, const Inv &i) { const double a0 = a * i.r0; return fma(a0, i.t, a0); }
     static __device__ __forceinline__ double neg(double a) { return -a; }
     static __device__ __forceinline__ double one() { return 1.0; }
+    static __device__ __forceinline__ double shfl_up1(double a) { return __shfl_up_sync(0xffffffffu, a, 1); }
 };
 template <> struct BlockSc<true> {
     typedef double2 T;
@@ -72,6 +93,9 @@ template <> struct BlockSc<true> {
     static __device__ __forceinline__ double2 div(double2 a, const Inv &i) { return ChainSc<true>::mul(a, i.c); }
     static __device__ __forceinline__ double2 neg(double2 a) { return make_double2(-a.x, -a.y); }
     static __device__ __forceinline__ double2 one() { return make_double2(1.0, 0.0); }
+    static __device__ __forceinline__ double2 shfl_up1(double2 a) {
+        return make_double2(__shfl_up_sync(0xffffffffu, a.x, 1), __shfl_up_sync(0xffffffffu, a.y, 1));
+    }
 };
 
 // One GENERIC row: ordered term run, same decoding and summation order as chain_kernel.cuh (bit-identical stamps).
@@ -92,7 +116,11 @@ __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, i
         else {
             const double *src = IN + (size_t)cur.y * L;
             const double v = __ldg(src);
+#if KRB_BX_L1PF
+            if (prefetch_ahead > 0) prefetch_l1(src + prefetch_ahead);   // the same thread reads it one lane later
+#else
             if (prefetch_ahead > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + prefetch_ahead));
+#endif
             if (kind == CK_IN) re = v;
             else if (kind == CK_INV_IN) re = __ddiv_rn(1.0, v);
             else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
@@ -138,7 +166,9 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
     const int n = p.n;
 
     // The rows a thread owns do not depend on the lane: dictionary / entry indices are packed two per register once.
-    uint32_t pk[(M + 1) / 2];
+    constexpr int PKW = SD ? 8 : 16;         // SD: entry indices < KRB_BLOCK_DMAX = 256, four per register
+    constexpr int PKN = 32 / PKW;
+    uint32_t pk[(M + PKN - 1) / PKN];
     bool my_generic = false;
     int ju = -1, gu = 0;                     // SD: local index / entry of this block's row with a second super-diagonal
 #pragma unroll
@@ -152,33 +182,42 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
                 if (rw.y & BR_HAS_U2) { ju = j; gu = (int)idx; }
             }
         }
-        if (j & 1) pk[j >> 1] |= idx << 16; else pk[j >> 1] = idx & 0xffffu;
+        if (j % PKN) pk[j / PKN] |= (idx & ((1u << PKW) - 1u)) << ((j % PKN) * PKW); else pk[j / PKN] = idx & ((1u << PKW) - 1u);
     }
     const bool warp_generic = __any_sync(0xffffffffu, my_generic);
     const bool warp_u2 = __any_sync(0xffffffffu, ju >= 0);
+    // SD: every thread of the warp stamps its M rows from ONE entry (the periodic interior of a ladder / line): the entry is
+    // read once per lane instead of once per row
+    bool one_entry = SD;
+#pragma unroll
+    for (int j = 1; j < M; ++j)
+        one_entry = one_entry && ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u)) == (pk[0] & ((1u << PKW) - 1u));
+    const bool warp_one_entry = KRB_BX_UNIFORM && SD && !warp_u2 && __all_sync(0xffffffffu, one_entry);
     (void)warp_generic; (void)warp_u2; (void)gu; (void)sd; (void)pe3;
 
-    // SD: (re)build the entries for `lane`; entry d is handled by thread (d % NW) * 32 + d / NW, i.e. spread over the warps
+    // SD: (re)build the entries for `lane`.  KRB_BLOCK_DMAX <= T, so a thread owns at most one entry: entry d belongs to
+    // thread (d % NW) * 32 + d / NW (spread over the warps).  What the owner needs is looked up again for every lane (from an
+    // opaque copy of t, two L1 hits for a GENERIC entry): kept across the lane loop it would cost five registers of the
+    // elimination's budget, i.e. local-memory traffic in every thread.
+    static_assert(KRB_BLOCK_DMAX <= 256 && KRB_BLOCK_DMAX <= T, "one dictionary entry per thread, 8-bit entry indices");
     auto refresh = [&](long long lane, double w, long long ahead) {
-        const int n_entries = p.n_dict + p.n_gen;
-        for (int d = (t & 31) * NW + (t >> 5); d < n_entries; d += T) {
-            if (d < p.n_dict) {
-                if (CPLX) {
-                    const uint4 *g = p.dict + (size_t)d * FIX_UNITS;
-                    const uint4 c0 = __ldg(g), c1 = __ldg(g + 1), c2 = __ldg(g + 2), c3 = __ldg(g + 3);
-                    sd[4 * d + 0] = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
-                    sd[4 * d + 1] = S::make(u4hi(c0), __dmul_rn(w, u4hi(c2)));
-                    sd[4 * d + 2] = S::make(u4lo(c1), __dmul_rn(w, u4lo(c3)));
-                    sd[4 * d + 3] = S::make(u4hi(c1), 0.0);
-                }
-            } else {
-                const int row = __ldg(p.gen_rows + (d - p.n_dict));
-                const uint2 rw = __ldg(p.rows + (row % M) * T + row / M);
-                V e0, e1, e2, e3, e4;
-                block_eval_terms<CPLX>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), p.IN + lane, L, w, ahead, e0, e1, e2, e3, e4);
-                sd[4 * d + 0] = e0; sd[4 * d + 1] = e1; sd[4 * d + 2] = e2; sd[4 * d + 3] = e4;
-                pe3[d] = e3;
-            }
+        int tt = t;
+        asm volatile("" : "+r"(tt));
+        const int my_entry = (tt & 31) * NW + (tt >> 5);
+        if (CPLX && my_entry < p.n_dict) {
+            const uint4 *g = p.dict + (size_t)my_entry * FIX_UNITS;
+            const uint4 c0 = __ldg(g), c1 = __ldg(g + 1), c2 = __ldg(g + 2), c3 = __ldg(g + 3);
+            sd[4 * my_entry + 0] = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
+            sd[4 * my_entry + 1] = S::make(u4hi(c0), __dmul_rn(w, u4hi(c2)));
+            sd[4 * my_entry + 2] = S::make(u4lo(c1), __dmul_rn(w, u4lo(c3)));
+            sd[4 * my_entry + 3] = S::make(u4hi(c1), 0.0);
+        } else if (my_entry >= p.n_dict && my_entry < p.n_dict + p.n_gen) {
+            const int row = __ldg(p.gen_rows + (my_entry - p.n_dict));
+            const uint2 rw = __ldg(p.rows + (row % M) * T + row / M);
+            V e0, e1, e2, e3, e4;
+            block_eval_terms<CPLX>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), p.IN + lane, L, w, ahead, e0, e1, e2, e3, e4);
+            sd[4 * my_entry + 0] = e0; sd[4 * my_entry + 1] = e1; sd[4 * my_entry + 2] = e2; sd[4 * my_entry + 3] = e4;
+            pe3[my_entry] = e3;
         }
     };
     const double TWO_PI = 2.0 * 3.14159265358979323846264338327950288;
@@ -206,6 +245,9 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             if (!SD) w = __dmul_rn(TWO_PI, __ldg(IN + (size_t)p.input_freq * L));
             else if (next < p.lanes) f_next = __ldg(p.IN + next + (size_t)p.input_freq * L);   // consumed after the first barrier
         }
+        // keep what is derived from the packed indices (20 shared-memory addresses) inside the loop: hoisted, it is spilled
+#pragma unroll
+        for (int i = 0; i < (M + PKN - 1) / PKN; ++i) asm volatile("" : "+r"(pk[i]));
         uint32_t worst = 0;                          // running maximum of the pivots' keys (pivot_key)
         V u[MI], y[MI];
         V lprev = S::zero(), pu2 = S::zero(), u2v = S::zero();
@@ -213,6 +255,12 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
 
         // ---- 1. stamp + top-down elimination of the interior rows; separator row partially reduced ----
         // one interior row:  w_k = diag - sub u^_{k-1},  u^ = sup1'/w_k,  y^ = (rhs - sub y^_{k-1})/w_k,  l^ = -sub l^_{k-1}/w_k
+#if KRB_BX_FWDACC
+        V accP = S::zero(), accQ = S::zero(), fA = B::one(), fAprev = B::one(), fB = S::zero();
+#define KRB_FB_UPDATE fB = B::neg(S::mul(fAprev, pu2));
+#else
+#define KRB_FB_UPDATE
+#endif
         auto interior = [&](int j, V e0, V e1, V s1, V e4) {
             V wk, yk, lk;
             if (j == 0) { wk = e1; yk = e4; lk = e0; }
@@ -226,6 +274,17 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             y[j] = B::div(yk, iv);
             lprev = B::div(lk, iv);
             mycol[j] = lprev;
+#if KRB_BX_FWDACC
+            // x_0 = accP - accQ s_{t-1} + fA x_j + fB x_{j+1}: substitute row j  (what step 2 would compute bottom-up)
+            if (j == 0) { accP = y[0]; accQ = lprev; fAprev = B::one(); fA = B::neg(u[0]); }
+            else {
+                accP = S::fnma(accP, B::neg(fA), y[j]);
+                accQ = S::fnma(accQ, B::neg(fA), lprev);
+                fAprev = fA;
+                fA = S::fnma(fB, fA, u[j]);
+            }
+            fB = S::zero();
+#endif
             return iv;
         };
         // separator row: sub * x_{last interior} substituted from the forward-eliminated last interior row
@@ -236,30 +295,74 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             sepS = e2;
         };
         if (SD) {
-            if (!warp_u2) {
+            if (warp_one_entry) {
+                const V *e = sd + 4 * (pk[0] & ((1u << PKW) - 1u));
+                const V c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
-                    const V *e = sd + 4 * ((pk[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+                    if (j < MI) interior(j, c0, c1, c2, c3);
+                    else separator(c0, c1, c2, c3);
+                }
+            } else if (!warp_u2) {
+#if KRB_BX_PIPE1
+                // entries fetched exactly one row ahead (the fence keeps the compiler from hoisting more of them: each costs
+                // 4 values of the register budget that u^ / y^ need)
+                auto entry = [&](int j) { return sd + 4 * ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u)); };
+                const V *e = entry(0);
+                V c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    V n0 = c0, n1 = c1, n2 = c2, n3 = c3;
+                    if (j + 1 < M) { e = entry(j + 1); n0 = e[0]; n1 = e[1]; n2 = e[2]; n3 = e[3]; }
+                    asm volatile("" ::: "memory");
+                    if (j < MI) interior(j, c0, c1, c2, c3);
+                    else separator(c0, c1, c2, c3);
+                    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+                }
+#else
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const V *e = sd + 4 * ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u));
                     if (j < MI) interior(j, e[0], e[1], e[2], e[3]);
                     else separator(e[0], e[1], e[2], e[3]);
                 }
+#endif
             } else {
+#if KRB_BX_PIPE1
+                auto entry = [&](int j) { return sd + 4 * ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u)); };
+                const V *e = entry(0);
+                V c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
-                    const V *e = sd + 4 * ((pk[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+                    V n0 = c0, n1 = c1, n2 = c2, n3 = c3;
+                    if (j + 1 < M) { e = entry(j + 1); n0 = e[0]; n1 = e[1]; n2 = e[2]; n3 = e[3]; }
+                    asm volatile("" ::: "memory");
+                    if (j < MI) {
+                        V s1 = c2;
+                        if (j > 0 && j - 1 == ju) s1 = S::fnma(s1, c0, pu2);       // fill from the row above's second super-diagonal
+                        const typename B::Inv iv = interior(j, c0, c1, s1, c3);
+                        if (j == ju) { pu2 = B::div(pe3[gu], iv); u2v = pu2; KRB_FB_UPDATE }
+                    } else separator(c0, c1, c2, c3);
+                    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+                }
+#else
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const V *e = sd + 4 * ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u));
                     if (j < MI) {
                         V s1 = e[2];
                         if (j > 0 && j - 1 == ju) s1 = S::fnma(s1, e[0], pu2);     // fill from the row above's second super-diagonal
                         const typename B::Inv iv = interior(j, e[0], e[1], s1, e[3]);
-                        if (j == ju) { pu2 = B::div(pe3[gu], iv); u2v = pu2; }
+                        if (j == ju) { pu2 = B::div(pe3[gu], iv); u2v = pu2; KRB_FB_UPDATE }
                     } else separator(e[0], e[1], e[2], e[3]);
                 }
+#endif
             }
         } else if (!warp_generic) {
             // every row of this warp is a FIXED record: branch-free, the record loads of later rows overlap the recurrence
 #pragma unroll
             for (int j = 0; j < M; ++j) {
-                const uint4 *d = p.dict + (size_t)((pk[j >> 1] >> ((j & 1) * 16)) & 0xffffu) * FIX_UNITS;
+                const uint4 *d = p.dict + (size_t)((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u)) * FIX_UNITS;
                 const uint4 c0 = __ldg(d), c1 = __ldg(d + 1);
                 V e0, e1, e2, e4;
                 if (CPLX) {
@@ -302,12 +405,44 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
                     const V s1 = (j > 0 && pu2_live) ? S::fnma(e2, e0, pu2) : e2;
                     const typename B::Inv iv = interior(j, e0, e1, s1, e4);
                     pu2_live = has_u2;
-                    if (has_u2) { pu2 = B::div(e3, iv); u2v = pu2; ju = j; }
+                    if (has_u2) { pu2 = B::div(e3, iv); u2v = pu2; ju = j; KRB_FB_UPDATE }
                 } else separator(e0, e1, e2, e4);
             }
         }
 
         // ---- 2. bottom-up: x_j = p_j - r_j s_t - q_j s_{t-1}  (p in y[], r in u[], q in the shared column) ----
+#if KRB_BX_FWDACC
+        // (p, r, q) of the block's first row were accumulated top-down inside step 1: nothing to do bottom-up
+        fst[t] = accP; fst[T + t] = B::neg(fA); fst[2 * T + t] = accQ;
+#elif KRB_BX_RECUR
+        // Only the block's FIRST row is needed by the separator system: (p, r, q) are carried as scalars, nothing is written
+        // back (y^, u^ stay in registers and l^ in the shared column for the back substitution of step 4).
+        {
+            V pn = y[MI - 1], rn = u[MI - 1], qn = lprev;          // last interior row: x = y^ - u^ s_t - l^ s_{t-1}
+            if (SD ? warp_u2 : __any_sync(0xffffffffu, ju >= 0)) {
+                V p2 = S::zero(), r2 = B::neg(B::one()), q2 = S::zero();   // row j+2 (starts at the virtual separator)
+#pragma unroll
+                for (int j = MI - 2; j >= 0; --j) {
+                    const V uj = u[j];
+                    V pj = S::fnma(y[j], uj, pn);
+                    V rj = B::neg(S::mul(uj, rn));
+                    V qj = S::fnma(mycol[j], uj, qn);
+                    if (j == ju) { pj = S::fnma(pj, u2v, p2); rj = S::fnma(rj, u2v, r2); qj = S::fnma(qj, u2v, q2); }
+                    p2 = pn; r2 = rn; q2 = qn;
+                    pn = pj; rn = rj; qn = qj;
+                }
+            } else {
+#pragma unroll
+                for (int j = MI - 2; j >= 0; --j) {
+                    const V uj = u[j];
+                    pn = S::fnma(y[j], uj, pn);
+                    rn = B::neg(S::mul(uj, rn));
+                    qn = S::fnma(mycol[j], uj, qn);
+                }
+            }
+            fst[t] = pn; fst[T + t] = rn; fst[2 * T + t] = qn;
+        }
+#else
         {
             // last interior row: the virtual separator row below it is (p, r, q) = (0, -1, 0)
             V qn = lprev;                             // q_{M-2} = l^_{M-2}; p_{M-2} = y^, r_{M-2} = u^ are already in place
@@ -336,6 +471,7 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             }
             fst[t] = y[0]; fst[T + t] = u[0]; fst[2 * T + t] = qn;
         }
+#endif
         __syncthreads();
         // SD: nobody reads the entries any more for this lane: build the next lane's
         if (SD && next < p.lanes) refresh(next, CPLX ? __dmul_rn(TWO_PI, f_next) : 0.0, next + gridDim.x < p.lanes ? (long long)gridDim.x : 0);
@@ -351,6 +487,60 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             const typename B::Inv iv = B::inv(bb, worst);
             a = B::div(sepA, iv); c = B::div(cc, iv); d = B::div(dd, iv);
         }
+        V st, sm;
+        if constexpr (KRB_BX_CR == 2 || (KRB_BX_CR == 1 && CPLX)) {
+        // One level of cyclic reduction, then parallel cyclic reduction on the odd rows only: the T/2 threads of the lower
+        // warps own compact row t' = (2t'+1); rows are stored de-interleaved by parity so that every access stays unit-stride.
+        // Half the warps sit out the log2(T/2) reduction steps (the other resident CTA gets their issue slots) and the
+        // shared-memory traffic of the separator system drops by ~45 %.
+        constexpr int TH = T / 2;
+        V *ini = red;                                  // [parity][a, c, d][TH]; the odd part's `a` row later holds the solution
+        V *sol = ini + 3 * TH;
+        const int hk = t >> 1, par = t & 1;
+        ini[(par * 3 + 0) * TH + hk] = a; ini[(par * 3 + 1) * TH + hk] = c; ini[(par * 3 + 2) * TH + hk] = d;
+        __syncthreads();
+        auto reduce_row = [&](V am, V cm, V dm, V ap, V cp, V dq, bool need_ac) {
+            const V b2 = S::fnma(S::fnma(B::one(), a, cm), c, ap);
+            const V d2 = S::fnma(S::fnma(d, a, dm), c, dq);
+            const typename B::Inv iv = B::inv(b2, worst);
+            if (need_ac) {
+                const V a2 = B::neg(S::mul(a, am));
+                const V c2 = B::neg(S::mul(c, cp));
+                a = B::div(a2, iv); c = B::div(c2, iv);
+            }
+            d = B::div(d2, iv);
+        };
+        V *pa = red + 3 * T, *pb = pa + 3 * TH;        // double-buffered [a, c, d][TH] of the reduced system (pa aliases fst)
+        if (t < TH) {
+            a = ini[3 * TH + t]; c = ini[4 * TH + t]; d = ini[5 * TH + t];             // row 2t+1
+            V ap = S::zero(), cp = S::zero(), dq = S::zero();
+            if (t + 1 < TH) { ap = ini[t + 1]; cp = ini[TH + t + 1]; dq = ini[2 * TH + t + 1]; }   // row 2t+2
+            reduce_row(ini[t], ini[TH + t], ini[2 * TH + t], ap, cp, dq, true);        // row 2t
+            pa[t] = a; pa[TH + t] = c; pa[2 * TH + t] = d;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 1; s < TH; s <<= 1) {
+            if (t < TH) {
+                V am = S::zero(), cm = S::zero(), dm = S::zero(), ap = S::zero(), cp = S::zero(), dq = S::zero();
+                if (t >= s) { am = pa[t - s]; cm = pa[TH + t - s]; dm = pa[2 * TH + t - s]; }
+                if (t + s < TH) { ap = pa[t + s]; cp = pa[TH + t + s]; dq = pa[2 * TH + t + s]; }
+                reduce_row(am, cm, dm, ap, cp, dq, 2 * s < TH);
+                if (2 * s < TH) { pb[t] = a; pb[TH + t] = c; pb[2 * TH + t] = d; }
+                else sol[t] = d;                                                       // x of row 2t+1
+            }
+            __syncthreads();
+            V *sw = pa; pa = pb; pb = sw;
+        }
+        // even rows by substitution from their own (a, c, d); a thread's left separator: odd rows get it from the lane below
+        st = sol[hk];
+        {
+            const V xl = (par == 0 && hk > 0) ? sol[hk - 1] : S::zero();
+            if (par == 0) st = S::fnma(S::fnma(ini[2 * TH + hk], ini[hk], xl), ini[TH + hk], st);
+            const V below = B::shfl_up1(st);
+            sm = par ? below : xl;
+        }
+        } else {
         red[t] = a; red[T + t] = c; red[2 * T + t] = d;
         __syncthreads();
         int cur = 0;
@@ -371,29 +561,56 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             __syncthreads();
             cur ^= 1;
         }
-        const V st = d;
-        const V sm = t > 0 ? (red + cur * 3 * T)[2 * T + t - 1] : S::zero();
+        st = d;
+        sm = t > 0 ? (red + cur * 3 * T)[2 * T + t - 1] : S::zero();
+        }
 
         // ---- 4. interiors, staged in the shared column, then coalesced point-major delivery ----
+#if KRB_BX_RECUR
+        // back substitution  x_j = (y^_j - l^_j s_{t-1}) - u^_j x_{j+1} (- u2^_j x_{j+2}),  x_{M-1} = s_t
+        {
+            V xn = st;
+            if (SD ? warp_u2 : __any_sync(0xffffffffu, ju >= 0)) {
+                V x2 = st;
+#pragma unroll
+                for (int j = MI - 1; j >= 0; --j) {
+                    V xj = S::fnma(S::fnma(y[j], mycol[j], sm), u[j], xn);
+                    if (j == ju) xj = S::fnma(xj, u2v, x2);
+                    mycol[j] = xj;
+                    x2 = xn; xn = xj;
+                }
+            } else {
+#pragma unroll
+                for (int j = MI - 1; j >= 0; --j) {
+                    xn = S::fnma(S::fnma(y[j], mycol[j], sm), u[j], xn);
+                    mycol[j] = xn;
+                }
+            }
+        }
+#else
 #pragma unroll
         for (int j = 0; j < MI; ++j) mycol[j] = S::fnma(S::fnma(y[j], u[j], st), mycol[j], sm);
+#endif
         mycol[MI] = st;
         int status = worst >= KRB_BAD_PIVOT_KEY ? KRB_LANE_ZERO_PIVOT : 0;
         if (!S::finite(st)) status |= KRB_LANE_NONFINITE;
         if (status && p.status) atomicOr(p.status + lane, status);
         __syncthreads();
         V *__restrict__ out = reinterpret_cast<V *>(p.OUT) + (size_t)lane * (size_t)n;
-        // pivot row i lives at xq[(i / M) * XS + i % M] = xq[i + i / M]
+        // pivot row i lives at xq[(i / M) * XS + i % M] = xq[i + i / M].  The M offsets do not depend on the lane, but hoisted
+        // out of the lane loop they cost M registers (spilled: M local loads per lane); an opaque copy of t keeps them here.
+        int tt = t;
+        asm volatile("" : "+r"(tt));
         if (p.unknown_of_row == nullptr) {
 #pragma unroll
             for (int k = 0; k < M; ++k) {
-                const int i = t + k * T;
+                const int i = tt + k * T;
                 if (i < n) __stcs(out + i, xq[i + i / M]);
             }
         } else {
 #pragma unroll
             for (int k = 0; k < M; ++k) {
-                const int i = t + k * T;
+                const int i = tt + k * T;
                 if (i < n) __stcs(out + __ldg(p.unknown_of_row + i), xq[i + i / M]);
             }
         }

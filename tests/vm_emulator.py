@@ -290,8 +290,8 @@ def chain_block_info(plan):
 
 
 def run_chain_block(plan, IN, cplx):
-    """numpy restatement of krb_chain_block_kernel: Wang partition (T blocks of M rows) + parallel cyclic reduction on the
-    separators.  IN [n_inputs][L] -> X [n][L] (unknown order), status [L]."""
+    """numpy restatement of krb_chain_block_kernel: Wang partition (T blocks of M rows), one cyclic-reduction level + parallel
+    cyclic reduction on the odd separators, interiors by back substitution.  IN [n_inputs][L] -> X [n][L] (unknown order), status [L]."""
     L_ = _lib.lib()
     valid, T, M, n_dict, _, why = chain_block_info(plan)
     assert valid, f"block tables not valid: {why}"
@@ -374,28 +374,54 @@ def run_chain_block(plan, IN, cplx):
             p[:, j] = y[:, j] - u[:, j] * p[:, j + 1] - u2[:, j] * p[:, j + 2]
             r[:, j] = -u[:, j] * r[:, j + 1] - u2[:, j] * r[:, j + 2]
             q[:, j] = l[:, j] - u[:, j] * q[:, j + 1] - u2[:, j] * q[:, j + 2]
+        # the kernel accumulates the first row's relation x_0 = P - R s_t - Q s_{t-1} top-down (x_0 = accP - accQ s_{t-1}
+        # + fA x_j + fB x_{j+1}, row j substituted); the bottom-up recurrences above are the independent check
+        accP = np.zeros((T, lanes), dtype=dt); accQ = np.zeros_like(accP); fA = np.ones_like(accP); fB = np.zeros_like(accP)
+        for j in range(M - 1):
+            accP = accP + fA * y[:, j]
+            accQ = accQ + fA * l[:, j]
+            fA, fB = fB - fA * u[:, j], -fA * u2[:, j]
+        assert not np.any(fB != 0)
+        scale = max(1e-300, float(np.abs(p[:, 0]).max()), float(np.abs(q[:, 0]).max()), float(np.abs(r[:, 0]).max()))
+        assert np.abs(accP - p[:, 0]).max() <= 1e-9 * scale and np.abs(accQ - q[:, 0]).max() <= 1e-9 * scale and np.abs(-fA - r[:, 0]).max() <= 1e-9 * scale
         def nxt(v):
             o = np.zeros_like(v); o[:-1] = v[1:]; return o
         ss = sup[:, M - 1]
-        Bq = Bp - ss * nxt(q[:, 0]); Cq = -ss * nxt(r[:, 0]); Dq = Dp - ss * nxt(p[:, 0])
+        Bq = Bp - ss * nxt(accQ); Cq = -ss * nxt(-fA); Dq = Dp - ss * nxt(accP)
         inv = 1.0 / Bq
         status[~np.isfinite(inv).all(axis=0)] |= ZERO_PIVOT
         a, c, d = A * inv, Cq * inv, Dq * inv
-        s = 1
-        while s < T:
-            def sh(v, k):
-                o = np.zeros_like(v)
-                if k > 0: o[k:] = v[:-k]
-                else: o[:k] = v[-k:]
-                return o
-            am, cm, dm, ap, cp, dp = sh(a, s), sh(c, s), sh(d, s), sh(a, -s), sh(c, -s), sh(d, -s)
+        def sh(v, k):
+            o = np.zeros_like(v)
+            if k > 0: o[k:] = v[:-k]
+            else: o[:k] = v[-k:]
+            return o
+        def reduce(a, c, d, am, cm, dm, ap, cp, dp):
             inv = 1.0 / (1.0 - a * cm - c * ap)
             status[~np.isfinite(inv).all(axis=0)] |= ZERO_PIVOT
-            a, c, d = (-a * am) * inv, (-c * cp) * inv, (d - a * dm - c * dp) * inv
+            return (-a * am) * inv, (-c * cp) * inv, (d - a * dm - c * dp) * inv
+        # one cyclic-reduction level: the odd rows 2k+1 absorb rows 2k and 2k+2 ...
+        ae, ce, de = a[0::2], c[0::2], d[0::2]
+        a1, c1, d1 = reduce(a[1::2], c[1::2], d[1::2], ae, ce, de, sh(ae, -1), sh(ce, -1), sh(de, -1))
+        # ... parallel cyclic reduction on the T/2 odd rows ...
+        s = 1
+        while s < T // 2:
+            a1, c1, d1 = reduce(a1, c1, d1, sh(a1, s), sh(c1, s), sh(d1, s), sh(a1, -s), sh(c1, -s), sh(d1, -s))
             s *= 2
+        # ... even rows by substitution
+        sep = np.zeros_like(d)
+        sep[1::2] = d1
+        sep[0::2] = de - ae * sh(d1, 1) - ce * d1
+        d = sep
         sprev = np.zeros_like(d); sprev[1:] = d[:-1]
-        x = p[:, :M] - r[:, :M] * d[:, None] - q[:, :M] * sprev[:, None]
+        # interiors: back substitution x_j = (y^_j - l^_j s_{t-1}) - u^_j x_{j+1} - u2^_j x_{j+2}, x_{M-1} = s_t
+        x = np.zeros((T, M + 1, lanes), dtype=dt)
         x[:, M - 1] = d
+        x[:, M] = 0.0
+        for j in range(M - 2, -1, -1):
+            x2 = x[:, j + 2] if j + 2 <= M - 1 else 0.0
+            x[:, j] = (y[:, j] - l[:, j] * sprev) - u[:, j] * x[:, j + 1] - u2[:, j] * x2
+        x = x[:, :M]
     xr = x.reshape(T * M, lanes)
     assert not np.any(xr[n:] != 0), "padding rows must stay zero"
     X = np.zeros((n, lanes), dtype=dt)
