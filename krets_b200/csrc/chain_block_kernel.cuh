@@ -4,38 +4,24 @@
 //
 //   thread t owns pivot rows [t*M, (t+1)*M): M-1 interior rows and one separator (the block's last row)
 //   1. stamp + eliminate the interior rows top-down inside the thread; the coupling to the previous block's separator is
-//      carried as a fill column l^ (Wang's partition method):   x_j + u^_j x_{j+1} (+ u2^_j x_{j+2}) + l^_j s_{t-1} = y^_j
-//   2. eliminate bottom-up:                                     x_j = p_j - r_j s_t - q_j s_{t-1}
-//   3. the separator rows, with x_{first of block t+1} substituted, form a T x T tridiagonal system in s_0..s_{T-1}:
-//      parallel cyclic reduction in shared memory (log2 T steps)
-//   4. interiors by substitution, rows staged in shared memory and written point-major with full-width coalesced stores.
+//      carried as a fill column l^ (Wang's partition method):   x_j + u^_j x_{j+1} (+ u2^_j x_{j+2}) + l^_j s_{t-1} = y^_j.
+//      The relation of the block's FIRST row to its two separators,  x_0 = P - R s_t - Q s_{t-1},  is accumulated in the same
+//      sweep (x_0 = accP - accQ s_{t-1} + fA x_j + fB x_{j+1}, row j substituted as soon as it is eliminated): no bottom-up pass
+//   2. the separator rows, with x_{first of block t+1} substituted, form a T x T tridiagonal system in s_0..s_{T-1}:
+//      one level of cyclic reduction (odd rows absorb the even ones), parallel cyclic reduction on the T/2 odd rows by the
+//      lower half of the warps (log2(T/2) steps in shared memory), even rows by substitution
+//   3. interiors by back substitution  x_j = (y^_j - l^_j s_{t-1}) - u^_j x_{j+1} (- u2^_j x_{j+2}),  staged in the shared
+//      column and written point-major with full-width coalesced stores.
 //
-// u^ / y^ (later r / p) live in registers, l^ (later q, then x) in a per-thread shared-memory column with an odd stride.
+// u^ / y^ live in registers, l^ (then x) in a per-thread shared-memory column with an odd stride.  Register budget: 2 (M-1)
+// values of u^ / y^ leave ~50 of the 128 registers (2 CTAs / SM) for everything else, so lane-invariant address arithmetic is
+// deliberately kept INSIDE the lane loop (opaque copies of t / the packed entry indices): hoisted, it was spilled and every
+// lane paid ~90 local-memory accesses per thread (ncu: 33.6 M -> 1.8 M local loads per 65 536-lane launch, -18 % run time).
 // Stamped values are bit-identical to chain_kernel.cuh (same records, same summation order); the elimination order differs,
 // so unknowns agree with the sequential kernel to ~M ulp-amplifications (host check in compiler.cpp::build_chain_block
 // admits a plan only if both orders agree to 5e-10 at the nominal inputs; SURVEY §8(c): values are held to 1e-9).
 #pragma once
 #include "chain_kernel.cuh"
-
-#ifndef KRB_BX_L1PF
-#define KRB_BX_L1PF 0       // next lane's inputs are prefetched into L1 (0: L2) by the thread that will read them
-#endif
-#ifndef KRB_BX_CR
-#define KRB_BX_CR 1         // separator system: one cyclic-reduction level, then PCR on T/2 rows by half the warps
-                            // (1: complex plans only — measured: c64 -13 %, f64 +4 %; 2: always; 0: never)
-#endif
-#ifndef KRB_BX_PIPE1
-#define KRB_BX_PIPE1 1      // experiment: dictionary entries fetched exactly one row ahead
-#endif
-#ifndef KRB_BX_UNIFORM
-#define KRB_BX_UNIFORM 1    // warps whose threads each stamp all their rows from one entry read it once per lane
-#endif
-#ifndef KRB_BX_FWDACC
-#define KRB_BX_FWDACC 1     // (p, r, q) of a block's first row accumulated top-down inside step 1 (no bottom-up pass)
-#endif
-#ifndef KRB_BX_RECUR
-#define KRB_BX_RECUR 1      // step 2 carries (p, r, q) of the first row as scalars, step 4 is a back substitution
-#endif
 
 namespace krb {
 
@@ -116,11 +102,7 @@ __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, i
         else {
             const double *src = IN + (size_t)cur.y * L;
             const double v = __ldg(src);
-#if KRB_BX_L1PF
-            if (prefetch_ahead > 0) prefetch_l1(src + prefetch_ahead);   // the same thread reads it one lane later
-#else
             if (prefetch_ahead > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + prefetch_ahead));
-#endif
             if (kind == CK_IN) re = v;
             else if (kind == CK_INV_IN) re = __ddiv_rn(1.0, v);
             else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
@@ -155,9 +137,9 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
     constexpr int FIX_UNITS = CPLX ? 4 : 2;
     constexpr int NW = T / 32;
     extern __shared__ __align__(16) unsigned char krb_block_smem[];
-    V *xq = reinterpret_cast<V *>(krb_block_smem);   // [T][XS]: l^_j -> q_j -> x_j
-    V *red = xq + T * XS;                              // [2][3][T]: cyclic-reduction rows (a, c, d), double-buffered
-    V *fst = red + 3 * T;                              // [3][T]: (p, r, q) of each block's first row; aliases buffer 1
+    V *xq = reinterpret_cast<V *>(krb_block_smem);   // [T][XS]: l^_j -> x_j
+    V *red = xq + T * XS;                              // [2][3][T]: separator rows (a, c, d) by parity, then the reduced system
+    V *fst = red + 3 * T;                              // [3][T]: (P, R, Q) of each block's first row; aliases the reduced system
     V *sd = red + 6 * T;                               // SD: [KRB_BLOCK_DMAX][4] stamped (sub, diag, sup, rhs) per entry
     V *pe3 = sd + 4 * KRB_BLOCK_DMAX;                  // SD: [KRB_BLOCK_DMAX] second super-diagonal of a GENERIC entry
     const int t = threadIdx.x;
@@ -186,14 +168,15 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
     }
     const bool warp_generic = __any_sync(0xffffffffu, my_generic);
     const bool warp_u2 = __any_sync(0xffffffffu, ju >= 0);
+    const uint32_t u2mask = __reduce_or_sync(0xffffffffu, ju >= 0 ? 1u << ju : 0u);   // SD: local indices of the warp's u2 rows
     // SD: every thread of the warp stamps its M rows from ONE entry (the periodic interior of a ladder / line): the entry is
     // read once per lane instead of once per row
     bool one_entry = SD;
 #pragma unroll
     for (int j = 1; j < M; ++j)
         one_entry = one_entry && ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u)) == (pk[0] & ((1u << PKW) - 1u));
-    const bool warp_one_entry = KRB_BX_UNIFORM && SD && !warp_u2 && __all_sync(0xffffffffu, one_entry);
-    (void)warp_generic; (void)warp_u2; (void)gu; (void)sd; (void)pe3;
+    const bool warp_one_entry = SD && !warp_u2 && __all_sync(0xffffffffu, one_entry);
+    (void)warp_generic; (void)warp_u2; (void)u2mask; (void)gu; (void)sd; (void)pe3;
 
     // SD: (re)build the entries for `lane`.  KRB_BLOCK_DMAX <= T, so a thread owns at most one entry: entry d belongs to
     // thread (d % NW) * 32 + d / NW (spread over the warps).  What the owner needs is looked up again for every lane (from an
@@ -255,12 +238,7 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
 
         // ---- 1. stamp + top-down elimination of the interior rows; separator row partially reduced ----
         // one interior row:  w_k = diag - sub u^_{k-1},  u^ = sup1'/w_k,  y^ = (rhs - sub y^_{k-1})/w_k,  l^ = -sub l^_{k-1}/w_k
-#if KRB_BX_FWDACC
         V accP = S::zero(), accQ = S::zero(), fA = B::one(), fAprev = B::one(), fB = S::zero();
-#define KRB_FB_UPDATE fB = B::neg(S::mul(fAprev, pu2));
-#else
-#define KRB_FB_UPDATE
-#endif
         auto interior = [&](int j, V e0, V e1, V s1, V e4) {
             V wk, yk, lk;
             if (j == 0) { wk = e1; yk = e4; lk = e0; }
@@ -274,8 +252,7 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             y[j] = B::div(yk, iv);
             lprev = B::div(lk, iv);
             mycol[j] = lprev;
-#if KRB_BX_FWDACC
-            // x_0 = accP - accQ s_{t-1} + fA x_j + fB x_{j+1}: substitute row j  (what step 2 would compute bottom-up)
+            // x_0 = accP - accQ s_{t-1} + fA x_j + fB x_{j+1}: substitute row j (replaces a bottom-up pass over the block)
             if (j == 0) { accP = y[0]; accQ = lprev; fAprev = B::one(); fA = B::neg(u[0]); }
             else {
                 accP = S::fnma(accP, B::neg(fA), y[j]);
@@ -284,7 +261,6 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
                 fA = S::fnma(fB, fA, u[j]);
             }
             fB = S::zero();
-#endif
             return iv;
         };
         // separator row: sub * x_{last interior} substituted from the forward-eliminated last interior row
@@ -303,32 +279,11 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
                     if (j < MI) interior(j, c0, c1, c2, c3);
                     else separator(c0, c1, c2, c3);
                 }
-            } else if (!warp_u2) {
-#if KRB_BX_PIPE1
-                // entries fetched exactly one row ahead (the fence keeps the compiler from hoisting more of them: each costs
-                // 4 values of the register budget that u^ / y^ need)
-                auto entry = [&](int j) { return sd + 4 * ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u)); };
-                const V *e = entry(0);
-                V c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    V n0 = c0, n1 = c1, n2 = c2, n3 = c3;
-                    if (j + 1 < M) { e = entry(j + 1); n0 = e[0]; n1 = e[1]; n2 = e[2]; n3 = e[3]; }
-                    asm volatile("" ::: "memory");
-                    if (j < MI) interior(j, c0, c1, c2, c3);
-                    else separator(c0, c1, c2, c3);
-                    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-                }
-#else
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    const V *e = sd + 4 * ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u));
-                    if (j < MI) interior(j, e[0], e[1], e[2], e[3]);
-                    else separator(e[0], e[1], e[2], e[3]);
-                }
-#endif
             } else {
-#if KRB_BX_PIPE1
+                // entries fetched exactly one row ahead (the fence keeps the compiler from hoisting more of them: each costs
+                // 4 values of the register budget that u^ / y^ need).  Rows with a second super-diagonal (at most one per
+                // thread) are found through the warp's mask of their local indices: a warp-uniform test per row, the
+                // per-thread comparison only on the one or two rows where some thread of the warp needs it.
                 auto entry = [&](int j) { return sd + 4 * ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u)); };
                 const V *e = entry(0);
                 V c0 = e[0], c1 = e[1], c2 = e[2], c3 = e[3];
@@ -339,24 +294,16 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
                     asm volatile("" ::: "memory");
                     if (j < MI) {
                         V s1 = c2;
-                        if (j > 0 && j - 1 == ju) s1 = S::fnma(s1, c0, pu2);       // fill from the row above's second super-diagonal
+                        if (j > 0 && ((u2mask >> (j - 1)) & 1u)) {
+                            if (j - 1 == ju) s1 = S::fnma(s1, c0, pu2);            // fill from the row above's second super-diagonal
+                        }
                         const typename B::Inv iv = interior(j, c0, c1, s1, c3);
-                        if (j == ju) { pu2 = B::div(pe3[gu], iv); u2v = pu2; KRB_FB_UPDATE }
+                        if ((u2mask >> j) & 1u) {
+                            if (j == ju) { pu2 = B::div(pe3[gu], iv); u2v = pu2; fB = B::neg(S::mul(fAprev, pu2)); }
+                        }
                     } else separator(c0, c1, c2, c3);
                     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
                 }
-#else
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    const V *e = sd + 4 * ((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u));
-                    if (j < MI) {
-                        V s1 = e[2];
-                        if (j > 0 && j - 1 == ju) s1 = S::fnma(s1, e[0], pu2);     // fill from the row above's second super-diagonal
-                        const typename B::Inv iv = interior(j, e[0], e[1], s1, e[3]);
-                        if (j == ju) { pu2 = B::div(pe3[gu], iv); u2v = pu2; KRB_FB_UPDATE }
-                    } else separator(e[0], e[1], e[2], e[3]);
-                }
-#endif
             }
         } else if (!warp_generic) {
             // every row of this warp is a FIXED record: branch-free, the record loads of later rows overlap the recurrence
@@ -405,78 +352,18 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
                     const V s1 = (j > 0 && pu2_live) ? S::fnma(e2, e0, pu2) : e2;
                     const typename B::Inv iv = interior(j, e0, e1, s1, e4);
                     pu2_live = has_u2;
-                    if (has_u2) { pu2 = B::div(e3, iv); u2v = pu2; ju = j; KRB_FB_UPDATE }
+                    if (has_u2) { pu2 = B::div(e3, iv); u2v = pu2; ju = j; fB = B::neg(S::mul(fAprev, pu2)); }
                 } else separator(e0, e1, e2, e4);
             }
         }
 
-        // ---- 2. bottom-up: x_j = p_j - r_j s_t - q_j s_{t-1}  (p in y[], r in u[], q in the shared column) ----
-#if KRB_BX_FWDACC
-        // (p, r, q) of the block's first row were accumulated top-down inside step 1: nothing to do bottom-up
+        // (P, R, Q) of the block's first row were accumulated top-down inside step 1: there is no bottom-up pass
         fst[t] = accP; fst[T + t] = B::neg(fA); fst[2 * T + t] = accQ;
-#elif KRB_BX_RECUR
-        // Only the block's FIRST row is needed by the separator system: (p, r, q) are carried as scalars, nothing is written
-        // back (y^, u^ stay in registers and l^ in the shared column for the back substitution of step 4).
-        {
-            V pn = y[MI - 1], rn = u[MI - 1], qn = lprev;          // last interior row: x = y^ - u^ s_t - l^ s_{t-1}
-            if (SD ? warp_u2 : __any_sync(0xffffffffu, ju >= 0)) {
-                V p2 = S::zero(), r2 = B::neg(B::one()), q2 = S::zero();   // row j+2 (starts at the virtual separator)
-#pragma unroll
-                for (int j = MI - 2; j >= 0; --j) {
-                    const V uj = u[j];
-                    V pj = S::fnma(y[j], uj, pn);
-                    V rj = B::neg(S::mul(uj, rn));
-                    V qj = S::fnma(mycol[j], uj, qn);
-                    if (j == ju) { pj = S::fnma(pj, u2v, p2); rj = S::fnma(rj, u2v, r2); qj = S::fnma(qj, u2v, q2); }
-                    p2 = pn; r2 = rn; q2 = qn;
-                    pn = pj; rn = rj; qn = qj;
-                }
-            } else {
-#pragma unroll
-                for (int j = MI - 2; j >= 0; --j) {
-                    const V uj = u[j];
-                    pn = S::fnma(y[j], uj, pn);
-                    rn = B::neg(S::mul(uj, rn));
-                    qn = S::fnma(mycol[j], uj, qn);
-                }
-            }
-            fst[t] = pn; fst[T + t] = rn; fst[2 * T + t] = qn;
-        }
-#else
-        {
-            // last interior row: the virtual separator row below it is (p, r, q) = (0, -1, 0)
-            V qn = lprev;                             // q_{M-2} = l^_{M-2}; p_{M-2} = y^, r_{M-2} = u^ are already in place
-            if (SD ? warp_u2 : __any_sync(0xffffffffu, ju >= 0)) {
-                V p2 = S::zero(), r2 = B::neg(B::one()), q2 = S::zero();   // row j+2 (starts at the virtual separator)
-#pragma unroll
-                for (int j = MI - 2; j >= 0; --j) {
-                    const V uj = u[j];
-                    V pj = S::fnma(y[j], uj, y[j + 1]);
-                    V rj = B::neg(S::mul(uj, u[j + 1]));
-                    V qj = S::fnma(mycol[j], uj, qn);
-                    if (j == ju) { pj = S::fnma(pj, u2v, p2); rj = S::fnma(rj, u2v, r2); qj = S::fnma(qj, u2v, q2); }
-                    p2 = y[j + 1]; r2 = u[j + 1]; q2 = qn;
-                    y[j] = pj; u[j] = rj; qn = qj;
-                    mycol[j] = qj;
-                }
-            } else {
-#pragma unroll
-                for (int j = MI - 2; j >= 0; --j) {
-                    const V uj = u[j];
-                    y[j] = S::fnma(y[j], uj, y[j + 1]);
-                    u[j] = B::neg(S::mul(uj, u[j + 1]));
-                    qn = S::fnma(mycol[j], uj, qn);
-                    mycol[j] = qn;
-                }
-            }
-            fst[t] = y[0]; fst[T + t] = u[0]; fst[2 * T + t] = qn;
-        }
-#endif
         __syncthreads();
         // SD: nobody reads the entries any more for this lane: build the next lane's
         if (SD && next < p.lanes) refresh(next, CPLX ? __dmul_rn(TWO_PI, f_next) : 0.0, next + gridDim.x < p.lanes ? (long long)gridDim.x : 0);
 
-        // ---- 3. separator system: A s_{t-1} + B s_t + C s_{t+1} = D, parallel cyclic reduction ----
+        // ---- 2. separator system: A s_{t-1} + B s_t + C s_{t+1} = D ----
         V a, c, d;
         {
             V pn = S::zero(), rn = S::zero(), qn = S::zero();
@@ -488,7 +375,6 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             a = B::div(sepA, iv); c = B::div(cc, iv); d = B::div(dd, iv);
         }
         V st, sm;
-        if constexpr (KRB_BX_CR == 2 || (KRB_BX_CR == 1 && CPLX)) {
         // One level of cyclic reduction, then parallel cyclic reduction on the odd rows only: the T/2 threads of the lower
         // warps own compact row t' = (2t'+1); rows are stored de-interleaved by parity so that every access stays unit-stride.
         // Half the warps sit out the log2(T/2) reduction steps (the other resident CTA gets their issue slots) and the
@@ -540,57 +426,22 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             const V below = B::shfl_up1(st);
             sm = par ? below : xl;
         }
-        } else {
-        red[t] = a; red[T + t] = c; red[2 * T + t] = d;
-        __syncthreads();
-        int cur = 0;
-#pragma unroll
-        for (int s = 1; s < T; s <<= 1) {
-            const V *src = red + cur * 3 * T;
-            V *dst = red + (cur ^ 1) * 3 * T;
-            V am = S::zero(), cm = S::zero(), dm = S::zero(), ap = S::zero(), cp = S::zero(), dq = S::zero();
-            if (t >= s) { am = src[t - s]; cm = src[T + t - s]; dm = src[2 * T + t - s]; }
-            if (t + s < T) { ap = src[t + s]; cp = src[T + t + s]; dq = src[2 * T + t + s]; }
-            const V b2 = S::fnma(S::fnma(B::one(), a, cm), c, ap);
-            const V a2 = B::neg(S::mul(a, am));
-            const V c2 = B::neg(S::mul(c, cp));
-            const V d2 = S::fnma(S::fnma(d, a, dm), c, dq);
-            const typename B::Inv iv = B::inv(b2, worst);
-            a = B::div(a2, iv); c = B::div(c2, iv); d = B::div(d2, iv);
-            dst[t] = a; dst[T + t] = c; dst[2 * T + t] = d;
-            __syncthreads();
-            cur ^= 1;
-        }
-        st = d;
-        sm = t > 0 ? (red + cur * 3 * T)[2 * T + t - 1] : S::zero();
-        }
 
-        // ---- 4. interiors, staged in the shared column, then coalesced point-major delivery ----
-#if KRB_BX_RECUR
+        // ---- 3. interiors, staged in the shared column, then coalesced point-major delivery ----
         // back substitution  x_j = (y^_j - l^_j s_{t-1}) - u^_j x_{j+1} (- u2^_j x_{j+2}),  x_{M-1} = s_t
         {
-            V xn = st;
-            if (SD ? warp_u2 : __any_sync(0xffffffffu, ju >= 0)) {
-                V x2 = st;
+            V xn = st, x2 = st;
+            const uint32_t m4 = SD ? u2mask : __reduce_or_sync(0xffffffffu, ju >= 0 ? 1u << ju : 0u);
 #pragma unroll
-                for (int j = MI - 1; j >= 0; --j) {
-                    V xj = S::fnma(S::fnma(y[j], mycol[j], sm), u[j], xn);
+            for (int j = MI - 1; j >= 0; --j) {
+                V xj = S::fnma(S::fnma(y[j], mycol[j], sm), u[j], xn);
+                if ((m4 >> j) & 1u) {
                     if (j == ju) xj = S::fnma(xj, u2v, x2);
-                    mycol[j] = xj;
-                    x2 = xn; xn = xj;
                 }
-            } else {
-#pragma unroll
-                for (int j = MI - 1; j >= 0; --j) {
-                    xn = S::fnma(S::fnma(y[j], mycol[j], sm), u[j], xn);
-                    mycol[j] = xn;
-                }
+                mycol[j] = xj;
+                x2 = xn; xn = xj;
             }
         }
-#else
-#pragma unroll
-        for (int j = 0; j < MI; ++j) mycol[j] = S::fnma(S::fnma(y[j], u[j], st), mycol[j], sm);
-#endif
         mycol[MI] = st;
         int status = worst >= KRB_BAD_PIVOT_KEY ? KRB_LANE_ZERO_PIVOT : 0;
         if (!S::finite(st)) status |= KRB_LANE_NONFINITE;
@@ -601,6 +452,8 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
         // out of the lane loop they cost M registers (spilled: M local loads per lane); an opaque copy of t keeps them here.
         int tt = t;
         asm volatile("" : "+r"(tt));
+        // (issuing the M shared-memory loads ahead of their stores, all at once or in groups, was measured slower: the burst
+        // throttles the MIO queue that the other resident CTA's elimination needs)
         if (p.unknown_of_row == nullptr) {
 #pragma unroll
             for (int k = 0; k < M; ++k) {

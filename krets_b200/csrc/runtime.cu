@@ -253,7 +253,8 @@ static int launch_chain_block_t(const ChainBlockParams &p, cudaStream_t st) {
         if (per_sm < 1) { set_error("block chain kernel does not fit on an SM"); return KRB_ERR_INTERNAL; }
         resident = sms * per_sm;
     }
-    const unsigned grid = (unsigned)std::min<long long>(p.lanes, resident);
+    static const char *grid_env = getenv("KRB_BLOCK_GRID");             // profiling: CTAs to launch instead of all resident ones
+    const unsigned grid = (unsigned)std::min<long long>(p.lanes, grid_env && atoi(grid_env) > 0 ? atoi(grid_env) : resident);
     krb_chain_block_kernel<CPLX, T, M, SD><<<grid, T, smem, st>>>(p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
