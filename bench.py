@@ -490,6 +490,7 @@ def main():
                          "kernel_ms": kernel_ms, "alg_bytes_per_point": alg, "peak_source": peak_src,
                          "model_hbm_bytes_per_point": int(info.hbm_bytes_per_point),
                          "fused_floor_bytes_per_point": floor_bytes,
+                         "frac_of_nominal_8TBps": achieved / 8000.0,
                          "moved_GBps": real, "moved_frac_of_peak": real / peak,
                          "note": "achieved uses the 3-pass algorithmic bytes of SURVEY §8(d) (P + s*(4*nnz_lu + 3*n)); the fused kernel moves "
                                  "model_hbm_bytes_per_point (= ncu traffic / lanes), so frac exceeds 1; moved_GBps / moved_frac_of_peak is what "

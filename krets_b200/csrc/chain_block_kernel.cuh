@@ -8,8 +8,9 @@
 //      The relation of the block's FIRST row to its two separators,  x_0 = P - R s_t - Q s_{t-1},  is accumulated in the same
 //      sweep (x_0 = accP - accQ s_{t-1} + fA x_j + fB x_{j+1}, row j substituted as soon as it is eliminated): no bottom-up pass
 //   2. the separator rows, with x_{first of block t+1} substituted, form a T x T tridiagonal system in s_0..s_{T-1}:
-//      one level of cyclic reduction (odd rows absorb the even ones), parallel cyclic reduction on the T/2 odd rows by the
-//      lower half of the warps (log2(T/2) steps in shared memory), even rows by substitution
+//      two levels of cyclic reduction (odd rows absorb the even ones, rows kept de-interleaved by parity so that every
+//      access is unit-stride), parallel cyclic reduction on the remaining T/4 rows by a quarter of the warps (log2(T/4)
+//      steps in shared memory), eliminated rows by substitution
 //   3. interiors by back substitution  x_j = (y^_j - l^_j s_{t-1}) - u^_j x_{j+1} (- u2^_j x_{j+2}),  staged in the shared
 //      column and written point-major with full-width coalesced stores.
 //
@@ -22,6 +23,10 @@
 // admits a plan only if both orders agree to 5e-10 at the nominal inputs; SURVEY §8(c): values are held to 1e-9).
 #pragma once
 #include "chain_kernel.cuh"
+
+#ifndef KRB_BX_CRL
+#define KRB_BX_CRL 2        // cyclic-reduction levels before the parallel cyclic reduction of the separator system (1 or 2)
+#endif
 
 namespace krb {
 
@@ -375,10 +380,11 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             a = B::div(sepA, iv); c = B::div(cc, iv); d = B::div(dd, iv);
         }
         V st, sm;
-        // One level of cyclic reduction, then parallel cyclic reduction on the odd rows only: the T/2 threads of the lower
-        // warps own compact row t' = (2t'+1); rows are stored de-interleaved by parity so that every access stays unit-stride.
-        // Half the warps sit out the log2(T/2) reduction steps (the other resident CTA gets their issue slots) and the
-        // shared-memory traffic of the separator system drops by ~45 %.
+        // Cyclic reduction, then parallel cyclic reduction on the surviving odd rows only: the T/2 threads of the lower warps
+        // own compact row t' = (2t'+1); rows are stored de-interleaved by parity so that every access stays unit-stride.  The
+        // other warps sit out the reduction steps (the other resident CTA gets their issue slots); against PCR on all T rows
+        // the shared-memory traffic of the separator system drops by ~45 % (one level) / ~65 % (two levels); measured:
+        // one level -13 % (c64) / -5 % (f64) run time, the second another -4 % / -0.6 %.
         constexpr int TH = T / 2;
         V *ini = red;                                  // [parity][a, c, d][TH]; the odd part's `a` row later holds the solution
         V *sol = ini + 3 * TH;
@@ -396,6 +402,51 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             }
             d = B::div(d2, iv);
         };
+        if constexpr (KRB_BX_CRL == 2) {
+            // second level: the T/2 compact rows are reduced once more the same way, PCR runs on T/4 rows in a quarter of the warps
+            constexpr int TQ = T / 4;
+            V *ini2 = red + 3 * T;                     // [parity][a, c, d][TQ] (aliases fst); odd part's `a` row: level-2 solution
+            V *sol2 = ini2 + 3 * TQ;
+            V *pa = ini2 + 6 * TQ, *pb = pa + 3 * TQ;  // double-buffered [a, c, d][TQ]
+            if (t < TH) {
+                a = ini[3 * TH + t]; c = ini[4 * TH + t]; d = ini[5 * TH + t];         // row 2t+1
+                V ap = S::zero(), cp = S::zero(), dq = S::zero();
+                if (t + 1 < TH) { ap = ini[t + 1]; cp = ini[TH + t + 1]; dq = ini[2 * TH + t + 1]; }   // row 2t+2
+                reduce_row(ini[t], ini[TH + t], ini[2 * TH + t], ap, cp, dq, true);    // row 2t
+                ini2[(par * 3 + 0) * TQ + hk] = a; ini2[(par * 3 + 1) * TQ + hk] = c; ini2[(par * 3 + 2) * TQ + hk] = d;
+            }
+            __syncthreads();
+            if (t < TQ) {
+                a = ini2[3 * TQ + t]; c = ini2[4 * TQ + t]; d = ini2[5 * TQ + t];      // compact row 2t+1
+                V ap = S::zero(), cp = S::zero(), dq = S::zero();
+                if (t + 1 < TQ) { ap = ini2[t + 1]; cp = ini2[TQ + t + 1]; dq = ini2[2 * TQ + t + 1]; }
+                reduce_row(ini2[t], ini2[TQ + t], ini2[2 * TQ + t], ap, cp, dq, true);
+                pa[t] = a; pa[TQ + t] = c; pa[2 * TQ + t] = d;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 1; s < TQ; s <<= 1) {
+                if (t < TQ) {
+                    V am = S::zero(), cm = S::zero(), dm = S::zero(), ap = S::zero(), cp = S::zero(), dq = S::zero();
+                    if (t >= s) { am = pa[t - s]; cm = pa[TQ + t - s]; dm = pa[2 * TQ + t - s]; }
+                    if (t + s < TQ) { ap = pa[t + s]; cp = pa[TQ + t + s]; dq = pa[2 * TQ + t + s]; }
+                    reduce_row(am, cm, dm, ap, cp, dq, 2 * s < TQ);
+                    if (2 * s < TQ) { pb[t] = a; pb[TQ + t] = c; pb[2 * TQ + t] = d; }
+                    else sol2[t] = d;
+                }
+                __syncthreads();
+                V *sw = pa; pa = pb; pb = sw;
+            }
+            if (t < TH) {                               // compact rows: odd ones are solved, even ones by substitution
+                V x1 = sol2[hk];
+                if (par == 0) {
+                    const V xl2 = hk > 0 ? sol2[hk - 1] : S::zero();
+                    x1 = S::fnma(S::fnma(ini2[2 * TQ + hk], ini2[hk], xl2), ini2[TQ + hk], x1);
+                }
+                sol[t] = x1;
+            }
+            __syncthreads();
+        } else {
         V *pa = red + 3 * T, *pb = pa + 3 * TH;        // double-buffered [a, c, d][TH] of the reduced system (pa aliases fst)
         if (t < TH) {
             a = ini[3 * TH + t]; c = ini[4 * TH + t]; d = ini[5 * TH + t];             // row 2t+1
@@ -417,6 +468,7 @@ __global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const 
             }
             __syncthreads();
             V *sw = pa; pa = pb; pb = sw;
+        }
         }
         // even rows by substitution from their own (a, c, d); a thread's left separator: odd rows get it from the lane below
         st = sol[hk];
