@@ -235,7 +235,8 @@ def run_other_workload(args):
 
     extra = {}
     if wl == "rc_ac":
-        circuit = kb.parse_circuit_description(netgen.rc_ladder(LADDER_N))
+        ladder_n = int(os.environ.get("KRB_BENCH_LADDER_N", LADDER_N))      # profiling: other ladder lengths
+        circuit = kb.parse_circuit_description(netgen.rc_ladder(ladder_n))
         plan = kb.Plan(circuit, api.MODE_AC, nominal_frequency=1.0)
         allf = kb.generate_frequencies("Decade", 125000, 1.0, 1e8)
         lanes = args.lanes if args.lanes != LANES_PER_GPU else 131072

@@ -133,7 +133,7 @@ __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, i
 // the first barrier and the end of the current one, so the main loop is branch-free and no warp waits for a term run.
 // !SD: FIXED rows read the global dictionary (L1), warps owning GENERIC rows decode them inline (Monte-Carlo plans).
 template <bool CPLX, int T, int M, bool SD>
-__global__ void __launch_bounds__(T, CPLX ? 1 : 2) krb_chain_block_kernel(const ChainBlockParams p) {
+__global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(const ChainBlockParams p) {
     typedef ChainSc<CPLX> S;
     typedef BlockSc<CPLX> B;
     typedef typename S::T V;

@@ -544,7 +544,9 @@ static void build_chain_block(Plan &plan, const std::vector<uint32_t> &row_off, 
     if (env && env[0] == '0') { bk.why_not = "disabled by KRB_CHAIN_BLOCK=0"; return; }
     const bool force_small = env && env[0] == '1';
     if (n < 512 && !force_small) { bk.why_not = "n < 512: the sequential chain kernel is used"; return; }
-    const int T = cplx ? 512 : 256, mstep = cplx ? 2 : 4, mmax = cplx ? 10 : 20;
+    // KRB_CHAIN_BLOCK_CT256 (profiling): complex plans on 256-thread CTAs, two resident per SM (systems up to 2560 rows)
+    const bool ct256 = cplx && getenv("KRB_CHAIN_BLOCK_CT256") != nullptr;
+    const int T = cplx && !ct256 ? 512 : 256, mstep = cplx ? 2 : 4, mmax = cplx ? 10 : 20;
     // smallest compiled M that holds the system and keeps every row with a second super-diagonal at local index <= M-3,
     // at most one per block
     int M = 0;

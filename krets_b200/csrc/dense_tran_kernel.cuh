@@ -37,6 +37,8 @@ struct DenseTranParams {
     int rows;
     double h_comp;
     int *status;
+    int propagate;               // 1: steps apply the per-lane propagator G = A^-1 [H1 | Hx | Hs | Hw] (N independent FMA rows);
+                                 // 0: forward / backward substitution with the LU factors every step (KRB_DENSE_TRAN_LU=1)
 };
 
 // N unknowns, NSP / NWP = padded counts of trapezoidal state columns and source-table columns (zero coefficients beyond
@@ -120,24 +122,92 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
                 C[(size_t)(O_A + i * N + j) * TPB] = fma(-l, C[(size_t)(O_A + k * N + j) * TPB], C[(size_t)(O_A + i * N + j) * TPB]);
         }
     }
+    // ---- propagator: with A constant over the steps, x_n = A^-1 b = G z, z = (1, x_prev, state, sources).  The columns of
+    // [H1 | Hx | Hs | Hw] are solved once, in place; a step is then N independent dot products (two accumulators each) instead
+    // of a forward and a backward substitution whose ~3N dependent FP64 operations set the run time at one warp per scheduler.
+    const bool prop = p.propagate != 0;
+    if (prop) {
+        auto solve_col = [&](int base, int stride) {
+            double v[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) v[k] = C[(size_t)(base + k * stride) * TPB];
+#pragma unroll
+            for (int k = 1; k < N; k++)
+#pragma unroll
+                for (int l = 0; l < k; l++) v[k] = fma(-C[(size_t)(O_A + k * N + l) * TPB], v[l], v[k]);
+#pragma unroll
+            for (int k = N - 1; k >= 0; k--) {
+                double acc = v[k];
+#pragma unroll
+                for (int l = k + 1; l < N; l++) acc = fma(-C[(size_t)(O_A + k * N + l) * TPB], v[l], acc);
+                v[k] = acc * C[(size_t)(O_A + k * N + k) * TPB];
+            }
+#pragma unroll
+            for (int k = 0; k < N; k++) C[(size_t)(base + k * stride) * TPB] = v[k];
+        };
+        solve_col(O_H1, 1);
+#pragma unroll
+        for (int l = 0; l < N; l++) solve_col(O_HX + l, N);
+#pragma unroll
+        for (int j = 0; j < NSP; j++) solve_col(O_HS + j, NSP);
+#pragma unroll
+        for (int j = 0; j < NWP; j++) solve_col(O_HW + j, NWP);
+    }
     constexpr bool REGS = (N <= 4);
+    const bool direct = p.OUT != nullptr;
+    if (direct && lane >= p.out_lanes) return;                                               // padding lanes own no output
+    // Point-major delivery with the propagator (N = 2, 4): the rows and columns of G are permuted into UNKNOWN order while they
+    // are copied to registers, so that a solved point is one 128 / 256-bit store per lane instead of N scalar ones: lanes are
+    // rows * n values apart, every scalar store of a warp touches 32 sectors, and that store path - not the arithmetic - is
+    // what bounds this kernel (config 4: 4 x 8 B stores per lane and step -> one 32 B store).
+    constexpr bool VEC = REGS && (N == 2 || N == 4);
+    const bool ordered = VEC && prop && direct && ((reinterpret_cast<uintptr_t>(p.OUT) & (N * 8 - 1)) == 0);
     double rc[REGS ? TOTAL : 1];
     if (REGS) {
+        if (ordered) {
+            int pos[N];                                                                      // pivot position of unknown u
 #pragma unroll
-        for (int i = 0; i < TOTAL; i++) rc[REGS ? i : 0] = C[(size_t)i * TPB];
+            for (int l = 0; l < N; l++) {
+                const int u = p.col_order[l];
+#pragma unroll
+                for (int v = 0; v < N; v++) if (v == u) pos[v] = l;
+            }
+#pragma unroll
+            for (int u = 0; u < N; u++) {
+                const int l = pos[u];
+                rc[REGS ? O_H1 + u : 0] = C[(size_t)(O_H1 + l) * TPB];
+#pragma unroll
+                for (int v = 0; v < N; v++) rc[REGS ? O_HX + u * N + v : 0] = C[(size_t)(O_HX + l * N + pos[v]) * TPB];
+#pragma unroll
+                for (int j = 0; j < NSP; j++) rc[REGS ? O_HS + u * NSP + j : 0] = C[(size_t)(O_HS + l * NSP + j) * TPB];
+#pragma unroll
+                for (int j = 0; j < NWP; j++) rc[REGS ? O_HW + u * NWP + j : 0] = C[(size_t)(O_HW + l * NWP + j) * TPB];
+            }
+#pragma unroll
+            for (int j = 0; j < NSP; j++)
+#pragma unroll
+                for (int v = 0; v < N; v++) rc[REGS ? O_GX + j * N + v : 0] = C[(size_t)(O_GX + j * N + pos[v]) * TPB];
+        } else {
+#pragma unroll
+            for (int i = 0; i < TOTAL; i++) rc[REGS ? i : 0] = C[(size_t)i * TPB];
+        }
     }
 #define KRB_DC(i) (REGS ? rc[REGS ? (i) : 0] : C[(size_t)(i) * TPB])
     double x[N], st[NSP > 0 ? NSP : 1];
     double *xp[N];                                                                           // store cursors, one per unknown
-    const bool direct = p.OUT != nullptr;
-    if (direct && lane >= p.out_lanes) return;                                               // padding lanes own no output
+    double *pv = direct ? p.OUT + (size_t)lane * p.rows * p.n : nullptr;                     // ordered: cursor of the whole point
+    auto store_point = [&](double *dst, const double *v) {
+        if (N == 4) asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v[0]), "d"(v[N > 1 ? 1 : 0]), "d"(v[N > 2 ? 2 : 0]), "d"(v[N > 3 ? 3 : 0]) : "memory");
+        else asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(v[0]), "d"(v[N > 1 ? 1 : 0]) : "memory");
+    };
 #pragma unroll
     for (int l = 0; l < N; l++) {
-        const int u = p.col_order[l];
+        const int u = ordered ? l : p.col_order[l];
         x[l] = p.X[(size_t)u * L + lane];                                                    // row 0: the operating point
         xp[l] = direct ? p.OUT + (size_t)lane * p.rows * p.n + u : p.X + (size_t)u * L + lane;
-        if (direct) *xp[l] = x[l];
+        if (direct && !ordered) *xp[l] = x[l];
     }
+    if (ordered) store_point(pv, x);
 #pragma unroll
     for (int j = 0; j < NSP; j++) st[j] = j < ns ? p.X[(size_t)(p.n + j) * L + lane] : 0.0;   // i_C(0)
     const size_t row_stride = direct ? (size_t)p.n : (size_t)p.width * L;
@@ -149,42 +219,64 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
         double wn[NWP];                                        // next step's sources: their load latency hides behind this step
 #pragma unroll
         for (int j = 0; j < NWP; j++) wn[j] = (j < nw && row + 1 < p.rows) ? __ldg(p.Bstep + (size_t)(row + 1) * 2 * nw + j) : 0.0;
-        double b[N];
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            double acc = KRB_DC(O_H1 + k);
-#pragma unroll
-            for (int l = 0; l < N; l++) acc = fma(KRB_DC(O_HX + k * N + l), x[l], acc);
-#pragma unroll
-            for (int j = 0; j < NSP; j++) acc = fma(KRB_DC(O_HS + k * NSP + j), st[j], acc);
-#pragma unroll
-            for (int j = 0; j < NWP; j++) acc = fma(KRB_DC(O_HW + k * NWP + j), wv[j], acc);
-            b[k] = acc;
-        }
-#pragma unroll
-        for (int k = 1; k < N; k++)
-#pragma unroll
-            for (int l = 0; l < k; l++) b[k] = fma(-KRB_DC(O_A + k * N + l), b[l], b[k]);
         double xn[N];
+        if (prop) {
 #pragma unroll
-        for (int k = N - 1; k >= 0; k--) {
-            double acc = b[k];
+            for (int k = 0; k < N; k++) {
+                double a0 = KRB_DC(O_H1 + k), a1 = 0.0;            // two accumulators: half the dependent chain
 #pragma unroll
-            for (int l = k + 1; l < N; l++) acc = fma(-KRB_DC(O_A + k * N + l), xn[l], acc);
-            xn[k] = acc * KRB_DC(O_A + k * N + k);
+                for (int l = 0; l < N; l++) {
+                    if (l & 1) a1 = fma(KRB_DC(O_HX + k * N + l), x[l], a1); else a0 = fma(KRB_DC(O_HX + k * N + l), x[l], a0);
+                }
+#pragma unroll
+                for (int j = 0; j < NSP; j++) {
+                    if ((N + j) & 1) a1 = fma(KRB_DC(O_HS + k * NSP + j), st[j], a1); else a0 = fma(KRB_DC(O_HS + k * NSP + j), st[j], a0);
+                }
+#pragma unroll
+                for (int j = 0; j < NWP; j++) {
+                    if ((N + NSP + j) & 1) a1 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a1); else a0 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a0);
+                }
+                xn[k] = a0 + a1;
+            }
+        } else {
+            double b[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                double acc = KRB_DC(O_H1 + k);
+#pragma unroll
+                for (int l = 0; l < N; l++) acc = fma(KRB_DC(O_HX + k * N + l), x[l], acc);
+#pragma unroll
+                for (int j = 0; j < NSP; j++) acc = fma(KRB_DC(O_HS + k * NSP + j), st[j], acc);
+#pragma unroll
+                for (int j = 0; j < NWP; j++) acc = fma(KRB_DC(O_HW + k * NWP + j), wv[j], acc);
+                b[k] = acc;
+            }
+#pragma unroll
+            for (int k = 1; k < N; k++)
+#pragma unroll
+                for (int l = 0; l < k; l++) b[k] = fma(-KRB_DC(O_A + k * N + l), b[l], b[k]);
+#pragma unroll
+            for (int k = N - 1; k >= 0; k--) {
+                double acc = b[k];
+#pragma unroll
+                for (int l = k + 1; l < N; l++) acc = fma(-KRB_DC(O_A + k * N + l), xn[l], acc);
+                xn[k] = acc * KRB_DC(O_A + k * N + k);
+            }
         }
 #pragma unroll
         for (int j = 0; j < NSP; j++) {
-            double acc = -st[j];
+            double a0 = -st[j], a1 = 0.0;
 #pragma unroll
-            for (int l = 0; l < N; l++) acc = fma(KRB_DC(O_GX + j * N + l), xn[l] - x[l], acc);
-            st[j] = acc;
+            for (int l = 0; l < N; l++) {
+                if (prop && (l & 1)) a1 = fma(KRB_DC(O_GX + j * N + l), xn[l] - x[l], a1); else a0 = fma(KRB_DC(O_GX + j * N + l), xn[l] - x[l], a0);
+            }
+            st[j] = prop ? a0 + a1 : a0;
         }
         double chk = 0.0;
+        if (ordered) { pv += N; store_point(pv, xn); }
 #pragma unroll
         for (int l = 0; l < N; l++) {
-            xp[l] += row_stride;
-            *xp[l] = xn[l];
+            if (!ordered) { xp[l] += row_stride; *xp[l] = xn[l]; }
             x[l] = xn[l];
             chk += xn[l] * 0.0;                                // NaN iff any unknown is inf / NaN
         }

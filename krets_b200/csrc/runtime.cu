@@ -261,8 +261,16 @@ static int launch_chain_block_t(const ChainBlockParams &p, cudaStream_t st) {
     return KRB_OK;
 }
 template <bool SD>
-static int launch_chain_block_s(bool cplx, int M, const ChainBlockParams &p, cudaStream_t st) {
-    if (cplx) {
+static int launch_chain_block_s(bool cplx, int T, int M, const ChainBlockParams &p, cudaStream_t st) {
+    if (cplx && T == 256) {            // profiling shape (KRB_CHAIN_BLOCK_CT256 at analysis time)
+        switch (M) {
+        case 2: return launch_chain_block_t<true, 256, 2, SD>(p, st);
+        case 4: return launch_chain_block_t<true, 256, 4, SD>(p, st);
+        case 6: return launch_chain_block_t<true, 256, 6, SD>(p, st);
+        case 8: return launch_chain_block_t<true, 256, 8, SD>(p, st);
+        case 10: return launch_chain_block_t<true, 256, 10, SD>(p, st);
+        }
+    } else if (cplx) {
         switch (M) {
         case 2: return launch_chain_block_t<true, 512, 2, SD>(p, st);
         case 4: return launch_chain_block_t<true, 512, 4, SD>(p, st);
@@ -282,8 +290,8 @@ static int launch_chain_block_s(bool cplx, int M, const ChainBlockParams &p, cud
     set_error("block chain kernel: no compiled shape for this plan");
     return KRB_ERR_INTERNAL;
 }
-static int launch_chain_block(bool cplx, int M, bool shared_dict, const ChainBlockParams &p, cudaStream_t st) {
-    return shared_dict ? launch_chain_block_s<true>(cplx, M, p, st) : launch_chain_block_s<false>(cplx, M, p, st);
+static int launch_chain_block(bool cplx, int T, int M, bool shared_dict, const ChainBlockParams &p, cudaStream_t st) {
+    return shared_dict ? launch_chain_block_s<true>(cplx, T, M, p, st) : launch_chain_block_s<false>(cplx, T, M, p, st);
 }
 
 template <int N, int NSP, int NWP>
@@ -480,7 +488,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             c.IN = IN; c.lanes = lanes; c.L = Lpad; c.n = n; c.input_freq = P0.input_freq; c.status = status_d;
             c.gen_rows = D0.block_gen; c.n_dict = P0.chain.block.n_dict; c.n_gen = (int)P0.chain.block.gen_rows.size();
             c.OUT = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p;
-            if ((rc = launch_chain_block(cplx, P0.chain.block.M, P0.chain.block.shared_dict, c, st))) return rc;
+            if ((rc = launch_chain_block(cplx, P0.chain.block.T, P0.chain.block.M, P0.chain.block.shared_dict, c, st))) return rc;
         } else if (chain) {
             ChainParams c{};
             c.rowinfo = D0.chain_rowinfo; c.stream = D0.chain_stream; c.unknown_of_row = D0.chain_unknown; c.IN = IN;
@@ -516,6 +524,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
                 q.n = n; q.ns = (int)PS->state_elems.size(); q.nw = (int)PS->wave_elems.size(); q.width = width;
                 q.IN = IN; q.Bstep = (const double *)DS.Bstep.p; q.X = (double *)D0.X[b].p; q.L = Lpad; q.rows = rows;
                 q.h_comp = PS->h_comp; q.status = status_d;
+                q.propagate = getenv("KRB_DENSE_TRAN_LU") == nullptr;      // default: per-lane propagator steps
                 q.OUT = dense_direct ? (out_dev ? (double *)a.x_out + (size_t)lane0 * (size_t)rows * n : (double *)D0.packed[b].p) : nullptr;
                 q.out_lanes = lanes;
                 if ((rc = launch_dense(q, Lpad, st))) return rc;

@@ -53,12 +53,15 @@ def test_block_vs_sequential_and_oracle_dc(oracle, monkeypatch, nodes, shape):
         assert_close(a[l], _dc_point(oc, v[l]), what=f"block chain DC lane {l}")
 
 
-@pytest.mark.parametrize("nodes,shape", [(5000, (512, 10)), (2500, (512, 6))])
+@pytest.mark.parametrize("nodes,shape", [(5000, (512, 10)), (2500, (512, 6)), (2500, (256, 10))])
 def test_block_vs_sequential_and_oracle_ac(oracle, monkeypatch, nodes, shape):
     import torch
     text = netgen.rc_ladder(nodes)
     circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    if shape[0] == 256:                              # profiling shape: complex plans on 256-thread CTAs, two per SM
+        monkeypatch.setenv("KRB_CHAIN_BLOCK_CT256", "1")
     plan = kb.Plan(circuit, api.MODE_AC, nominal_frequency=1e4)
+    monkeypatch.delenv("KRB_CHAIN_BLOCK_CT256", raising=False)
     valid, T, M, _, _, why = chain_block_info(plan)
     assert valid and (T, M) == shape, why
     freqs = np.logspace(0, 8, 411)

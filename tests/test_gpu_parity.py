@@ -452,6 +452,11 @@ def test_dense_transient_kernel_matches_lane_vm_and_oracle(oracle, golden, integ
     assert not st_dev.any().item() and np.array_equal(out_dev.cpu().numpy(), out_dense)
     out_li, _ = ptr.solve_transient(pdc, steps, lanes, varied_values=vals, layout=api.LAYOUT_LANE_INTERLEAVED)
     assert np.array_equal(np.transpose(out_li, (2, 0, 1)), out_dense)
+    monkeypatch.setenv("KRB_DENSE_TRAN_LU", "1")           # forward / backward substitution every step instead of the propagator
+    out_lu, st_lu = ptr.solve_transient(pdc, steps, lanes, varied_values=vals)
+    monkeypatch.delenv("KRB_DENSE_TRAN_LU")
+    assert not st_lu.any()
+    assert_close(out_dense, out_lu, rtol=1e-10, what="dense kernel: propagator steps vs LU steps")
     monkeypatch.setenv("KRB_NO_DENSE_TRAN", "1")
     pdc2 = kb.Plan(circuit, api.MODE_DC, varied=varied)
     ptr2 = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=h, integrator=integ)
