@@ -5,9 +5,18 @@
 //   once per lane : stamp the dense companion matrix (stampable.rs:442-468, 780-792, 972-980 ...), LU with the plan's static
 //                   pivots; turn the right-hand-side stamps (:470-505, :806-815, :1043-1048) into dense coefficient rows
 //                   b = H1 + Hx x_prev + Hs state + Hw sources(t)
-//   every step    : b (FMA rows), forward / backward substitution fully unrolled over compile-time N with the unknowns in
-//                   registers, trapezoidal capacitor currents, one coalesced store per unknown into the lane-interleaved
-//                   result planes X[row][unknown][lane] (the layout krb_pack_point_major delivers from).
+//   every step    : propagator mode (default): A is constant over the steps, so x_n = A^-1 b = G z with z = (1, x_prev, state,
+//                   sources) and G = A^-1 [H1 | Hx | Hs | Hw] solved once per lane with the LU factors: a step is N independent
+//                   dot products (two accumulators each) - no forward / backward substitution in the loop.  G is permuted
+//                   into UNKNOWN order on its way to registers, so that a solved point leaves as ONE 256-bit (N = 4) or
+//                   128-bit (N = 2) store per lane: lanes are rows * n values apart, a scalar store of a warp touches 32
+//                   sectors, and that store path was what bounded the kernel (config 4: 4.7 -> 2.5 ms from the store alone).
+//                   The source table is staged through shared memory in chunks of 32 steps.  Measured on B200 (tools/
+//                   microbench/fp64_lat.cu): DFMA dependent latency 8 cycles, one warp issues a DFMA every 2 cycles.
+//                   KRB_DENSE_TRAN_LU=1: forward / backward substitution with the LU factors every step (the work
+//                   structure of transient.rs:43-112), scalar stores; the GPU tests hold both against the oracle.
+//                   Then trapezoidal capacitor currents; without direct delivery one coalesced store per unknown into the
+//                   lane-interleaved result planes X[row][unknown][lane] (the layout krb_pack_point_major delivers from).
 //
 // Coefficients live in per-thread shared-memory columns C[idx][tid] (conflict-free, static offsets after unrolling).
 #pragma once
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
     }
     constexpr bool REGS = (N <= 4);
     const bool direct = p.OUT != nullptr;
-    if (direct && lane >= p.out_lanes) return;                                               // padding lanes own no output
+    const bool owns_out = !direct || lane < p.out_lanes;                                     // padding lanes compute but own no output
     // Point-major delivery with the propagator (N = 2, 4): the rows and columns of G are permuted into UNKNOWN order while they
     // are copied to registers, so that a solved point is one 128 / 256-bit store per lane instead of N scalar ones: lanes are
     // rows * n values apart, every scalar store of a warp touches 32 sectors, and that store path - not the arithmetic - is
@@ -205,36 +214,62 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
         const int u = ordered ? l : p.col_order[l];
         x[l] = p.X[(size_t)u * L + lane];                                                    // row 0: the operating point
         xp[l] = direct ? p.OUT + (size_t)lane * p.rows * p.n + u : p.X + (size_t)u * L + lane;
-        if (direct && !ordered) *xp[l] = x[l];
+        if (direct && !ordered && owns_out) *xp[l] = x[l];
     }
-    if (ordered) store_point(pv, x);
+    if (ordered && owns_out) store_point(pv, x);
 #pragma unroll
     for (int j = 0; j < NSP; j++) st[j] = j < ns ? p.X[(size_t)(p.n + j) * L + lane] : 0.0;   // i_C(0)
     const size_t row_stride = direct ? (size_t)p.n : (size_t)p.width * L;
-    double wv[NWP];
+    // The source table is the same for every lane: the warp (TPB == 32: one warp per block) stages it through shared memory in
+    // chunks of 32 steps, the next chunk loaded into registers while the current one is consumed (one L2 latency per 32 steps
+    // and off the critical path, instead of one exposed global load per step).
+    static_assert(TPB == 32, "source-table staging assumes one warp per block");
+    double *ws = dense_smem + (size_t)TOTAL * TPB;             // [2][32][NWP]
+    auto fetch_chunk = [&](int c, double *dst) {               // thread tid fetches the sources of step c * 32 + tid
+        const int r = c * 32 + tid;
 #pragma unroll
-    for (int j = 0; j < NWP; j++) wv[j] = (j < nw && p.rows > 1) ? __ldg(p.Bstep + (size_t)2 * nw + j) : 0.0;
+        for (int j = 0; j < NWP; j++) dst[j] = (j < nw && r < p.rows) ? __ldg(p.Bstep + (size_t)r * 2 * nw + j) : 0.0;
+    };
+    {
+        double w0[NWP];
+        fetch_chunk(0, w0);
+#pragma unroll
+        for (int j = 0; j < NWP; j++) ws[tid * NWP + j] = w0[j];
+        __syncwarp();
+    }
+    double wnext[NWP];
+    fetch_chunk(1, wnext);
 
     for (int row = 1; row < p.rows; row++) {
-        double wn[NWP];                                        // next step's sources: their load latency hides behind this step
+        if ((row & 31) == 0) {                                 // publish the chunk fetched during the previous 32 steps, fetch the next
+            double *dstc = ws + (size_t)((row >> 5) & 1) * 32 * NWP;
 #pragma unroll
-        for (int j = 0; j < NWP; j++) wn[j] = (j < nw && row + 1 < p.rows) ? __ldg(p.Bstep + (size_t)(row + 1) * 2 * nw + j) : 0.0;
+            for (int j = 0; j < NWP; j++) dstc[tid * NWP + j] = wnext[j];
+            __syncwarp();
+            fetch_chunk((row >> 5) + 1, wnext);
+        }
+        // (reading the NEXT step's sources here, one step ahead, and unrolling two steps were both measured slower)
+        double wv[NWP];
+#pragma unroll
+        for (int j = 0; j < NWP; j++) wv[j] = ws[(size_t)((row >> 5) & 1) * 32 * NWP + (row & 31) * NWP + j];
         double xn[N];
         if (prop) {
 #pragma unroll
             for (int k = 0; k < N; k++) {
-                double a0 = KRB_DC(O_H1 + k), a1 = 0.0;            // two accumulators: half the dependent chain
+                // two accumulators; sources and x_prev first, the state terms last: the state is what the previous step
+                // delivers last, so the step-to-step critical path is state -> 1 FMA -> add -> x_n -> state update
+                double a0 = KRB_DC(O_H1 + k), a1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NWP; j++) {
+                    if (j & 1) a0 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a0); else a1 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a1);
+                }
 #pragma unroll
                 for (int l = 0; l < N; l++) {
                     if (l & 1) a1 = fma(KRB_DC(O_HX + k * N + l), x[l], a1); else a0 = fma(KRB_DC(O_HX + k * N + l), x[l], a0);
                 }
 #pragma unroll
                 for (int j = 0; j < NSP; j++) {
-                    if ((N + j) & 1) a1 = fma(KRB_DC(O_HS + k * NSP + j), st[j], a1); else a0 = fma(KRB_DC(O_HS + k * NSP + j), st[j], a0);
-                }
-#pragma unroll
-                for (int j = 0; j < NWP; j++) {
-                    if ((N + NSP + j) & 1) a1 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a1); else a0 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a0);
+                    if (j & 1) a1 = fma(KRB_DC(O_HS + k * NSP + j), st[j], a1); else a0 = fma(KRB_DC(O_HS + k * NSP + j), st[j], a0);
                 }
                 xn[k] = a0 + a1;
             }
@@ -272,17 +307,19 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
             }
             st[j] = prop ? a0 + a1 : a0;
         }
-        double chk = 0.0;
-        if (ordered) { pv += N; store_point(pv, xn); }
+        if (ordered) { pv += N; if (owns_out) store_point(pv, xn); }
+        double chk[N];                                         // NaN iff any unknown is inf / NaN; pairwise, not a chain of N
 #pragma unroll
         for (int l = 0; l < N; l++) {
-            if (!ordered) { xp[l] += row_stride; *xp[l] = xn[l]; }
+            if (!ordered) { xp[l] += row_stride; if (owns_out) *xp[l] = xn[l]; }
             x[l] = xn[l];
-            chk += xn[l] * 0.0;                                // NaN iff any unknown is inf / NaN
+            chk[l] = xn[l] * 0.0;
         }
-        nonfinite |= (chk != 0.0);
 #pragma unroll
-        for (int j = 0; j < NWP; j++) wv[j] = wn[j];
+        for (int w = 1; w < N; w <<= 1)
+#pragma unroll
+            for (int l = 0; l + w < N; l += 2 * w) chk[l] += chk[l + w];
+        nonfinite |= (chk[0] != 0.0);
     }
 #undef KRB_DC
     if (bad || nonfinite) p.status[lane] |= (bad ? KRB_LANE_ZERO_PIVOT : 0) | (nonfinite ? KRB_LANE_NONFINITE : 0);

@@ -298,7 +298,7 @@ template <int N, int NSP, int NWP>
 static int launch_dense_t(const DenseTranParams &p, long long Lpad, cudaStream_t st) {
     constexpr int TPB = 32;
     const size_t per_thread = (size_t)2 * N * N + N + (size_t)N * NSP + (size_t)N * NWP + (size_t)NSP * N;
-    const size_t smem = per_thread * TPB * 8;
+    const size_t smem = per_thread * TPB * 8 + (size_t)2 * 32 * NWP * 8;      // coefficient columns + the staged source table
     static size_t configured = 0;
     if (smem > configured) {
         CUDA_TRY(cudaFuncSetAttribute(krb_dense_tran<N, NSP, NWP, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
@@ -311,9 +311,10 @@ static int launch_dense_t(const DenseTranParams &p, long long Lpad, cudaStream_t
 }
 template <int N>
 static int launch_dense_n(const DenseTranParams &p, long long Lpad, cudaStream_t st) {
-    // padded state / source counts: {0, 4, 8} x {1, 4}
-    const int nsp = p.ns == 0 ? 0 : p.ns <= 4 ? 4 : 8, nwp = p.nw <= 1 ? 1 : 4;
+    // padded state / source counts: {0, 2, 4, 8} x {1, 4}
+    const int nsp = p.ns == 0 ? 0 : p.ns <= 2 ? 2 : p.ns <= 4 ? 4 : 8, nwp = p.nw <= 1 ? 1 : 4;
     if (nsp == 0) return nwp == 1 ? launch_dense_t<N, 0, 1>(p, Lpad, st) : launch_dense_t<N, 0, 4>(p, Lpad, st);
+    if (nsp == 2) return nwp == 1 ? launch_dense_t<N, 2, 1>(p, Lpad, st) : launch_dense_t<N, 2, 4>(p, Lpad, st);
     if (nsp == 4) return nwp == 1 ? launch_dense_t<N, 4, 1>(p, Lpad, st) : launch_dense_t<N, 4, 4>(p, Lpad, st);
     return nwp == 1 ? launch_dense_t<N, 8, 1>(p, Lpad, st) : launch_dense_t<N, 8, 4>(p, Lpad, st);
 }
