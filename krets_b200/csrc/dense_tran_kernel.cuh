@@ -256,13 +256,9 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
         if (prop) {
 #pragma unroll
             for (int k = 0; k < N; k++) {
-                // two accumulators; sources and x_prev first, the state terms last: the state is what the previous step
-                // delivers last, so the step-to-step critical path is state -> 1 FMA -> add -> x_n -> state update
+                // two accumulators; x_prev and the state first (both in registers when the step starts), the source terms
+                // last: their shared-memory load was issued at the top of the step and completes behind the other terms
                 double a0 = KRB_DC(O_H1 + k), a1 = 0.0;
-#pragma unroll
-                for (int j = 0; j < NWP; j++) {
-                    if (j & 1) a0 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a0); else a1 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a1);
-                }
 #pragma unroll
                 for (int l = 0; l < N; l++) {
                     if (l & 1) a1 = fma(KRB_DC(O_HX + k * N + l), x[l], a1); else a0 = fma(KRB_DC(O_HX + k * N + l), x[l], a0);
@@ -270,6 +266,10 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
 #pragma unroll
                 for (int j = 0; j < NSP; j++) {
                     if (j & 1) a1 = fma(KRB_DC(O_HS + k * NSP + j), st[j], a1); else a0 = fma(KRB_DC(O_HS + k * NSP + j), st[j], a0);
+                }
+#pragma unroll
+                for (int j = 0; j < NWP; j++) {
+                    if (j & 1) a0 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a0); else a1 = fma(KRB_DC(O_HW + k * NWP + j), wv[j], a1);
                 }
                 xn[k] = a0 + a1;
             }
@@ -308,18 +308,19 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
             st[j] = prop ? a0 + a1 : a0;
         }
         if (ordered) { pv += N; if (owns_out) store_point(pv, xn); }
-        double chk[N];                                         // NaN iff any unknown is inf / NaN; pairwise, not a chain of N
 #pragma unroll
         for (int l = 0; l < N; l++) {
             if (!ordered) { xp[l] += row_stride; if (owns_out) *xp[l] = xn[l]; }
             x[l] = xn[l];
-            chk[l] = xn[l] * 0.0;
         }
+        // a linear recurrence never comes back from inf / NaN (inf - inf, 0 * inf = NaN): testing every 32nd step and the last
+        // one finds every lane that overflowed at any step
+        if ((row & 31) == 31 || row + 1 == p.rows) {
+            double chk = 0.0;
 #pragma unroll
-        for (int w = 1; w < N; w <<= 1)
-#pragma unroll
-            for (int l = 0; l + w < N; l += 2 * w) chk[l] += chk[l + w];
-        nonfinite |= (chk[0] != 0.0);
+            for (int l = 0; l < N; l++) chk += xn[l] * 0.0;    // NaN iff any unknown is inf / NaN
+            nonfinite |= (chk != 0.0);
+        }
     }
 #undef KRB_DC
     if (bad || nonfinite) p.status[lane] |= (bad ? KRB_LANE_ZERO_PIVOT : 0) | (nonfinite ? KRB_LANE_NONFINITE : 0);
