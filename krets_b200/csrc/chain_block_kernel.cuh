@@ -484,9 +484,13 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
         {
             V xn = st, x2 = st;
             const uint32_t m4 = SD ? u2mask : __reduce_or_sync(0xffffffffu, ju >= 0 ? 1u << ju : 0u);
+            V lj = mycol[MI - 1];                     // l^ of row j - 1 is loaded while row j is computed (c64: -2.5 %)
 #pragma unroll
             for (int j = MI - 1; j >= 0; --j) {
-                V xj = S::fnma(S::fnma(y[j], mycol[j], sm), u[j], xn);
+                V ln = lj;
+                if (j > 0) ln = mycol[j - 1];
+                V xj = S::fnma(S::fnma(y[j], lj, sm), u[j], xn);
+                lj = ln;
                 if ((m4 >> j) & 1u) {
                     if (j == ju) xj = S::fnma(xj, u2v, x2);
                 }
@@ -504,13 +508,17 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
         // out of the lane loop they cost M registers (spilled: M local loads per lane); an opaque copy of t keeps them here.
         int tt = t;
         asm volatile("" : "+r"(tt));
-        // (issuing the M shared-memory loads ahead of their stores, all at once or in groups, was measured slower: the burst
-        // throttles the MIO queue that the other resident CTA's elimination needs)
+        // (issuing ALL M shared-memory loads ahead of their stores, or groups of 2-10, was measured slower: the burst throttles
+        // the MIO queue that the other resident CTA's elimination needs; one element ahead is the sweet spot)
         if (p.unknown_of_row == nullptr) {
+            V cur = xq[tt + tt / M];                 // element k + 1 is loaded before element k is stored (f64: -2 %)
 #pragma unroll
             for (int k = 0; k < M; ++k) {
-                const int i = tt + k * T;
-                if (i < n) __stcs(out + i, xq[i + i / M]);
+                const int i = tt + k * T, i1 = i + T;
+                V nxt = cur;
+                if (k + 1 < M) nxt = xq[i1 + i1 / M];
+                if (i < n) __stcs(out + i, cur);
+                cur = nxt;
             }
         } else {
 #pragma unroll
