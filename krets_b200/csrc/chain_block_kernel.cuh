@@ -24,10 +24,6 @@
 #pragma once
 #include "chain_kernel.cuh"
 
-#ifndef KRB_BX_CRL
-#define KRB_BX_CRL 2        // cyclic-reduction levels before the parallel cyclic reduction of the separator system (1 or 2)
-#endif
-
 namespace krb {
 
 struct ChainBlockParams {
@@ -183,31 +179,42 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
     const bool warp_one_entry = SD && !warp_u2 && __all_sync(0xffffffffu, one_entry);
     (void)warp_generic; (void)warp_u2; (void)u2mask; (void)gu; (void)sd; (void)pe3;
 
-    // SD: (re)build the entries for `lane`.  KRB_BLOCK_DMAX <= T, so a thread owns at most one entry: entry d belongs to
-    // thread (d % NW) * 32 + d / NW (spread over the warps).  What the owner needs is looked up again for every lane (from an
-    // opaque copy of t, two L1 hits for a GENERIC entry): kept across the lane loop it would cost five registers of the
+    // SD: (re)build the entries for `lane`.  The owners are the threads of the UPPER half of the warps - the ones that sit out the
+    // reduction of the separator system (step 2) - so that the global loads of a GENERIC entry (term run + per-lane inputs, two
+    // to four dependent L2 round trips) run beside that reduction instead of in front of it, where every other warp of the CTA
+    // waited for the owner (ncu, c64: 11.7 % of all warp samples at the barrier behind it).  Owner s = t - T/2 takes entries
+    // e(s), e(s) + T/2, ... with e(s) = (s % 32) * (NW/2) + s / 32 (spread over the upper warps).  What an owner needs is looked
+    // up again for every lane (from an opaque copy of t): kept across the lane loop it would cost registers of the
     // elimination's budget, i.e. local-memory traffic in every thread.
-    static_assert(KRB_BLOCK_DMAX <= 256 && KRB_BLOCK_DMAX <= T, "one dictionary entry per thread, 8-bit entry indices");
+    static_assert(KRB_BLOCK_DMAX <= 256, "8-bit entry indices");
+    constexpr int TH = T / 2, TQ = T / 4;
     auto refresh = [&](long long lane, double w, long long ahead) {
         int tt = t;
         asm volatile("" : "+r"(tt));
-        const int my_entry = (tt & 31) * NW + (tt >> 5);
-        if (CPLX && my_entry < p.n_dict) {
-            const uint4 *g = p.dict + (size_t)my_entry * FIX_UNITS;
-            const uint4 c0 = __ldg(g), c1 = __ldg(g + 1), c2 = __ldg(g + 2), c3 = __ldg(g + 3);
-            sd[4 * my_entry + 0] = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
-            sd[4 * my_entry + 1] = S::make(u4hi(c0), __dmul_rn(w, u4hi(c2)));
-            sd[4 * my_entry + 2] = S::make(u4lo(c1), __dmul_rn(w, u4lo(c3)));
-            sd[4 * my_entry + 3] = S::make(u4hi(c1), 0.0);
-        } else if (my_entry >= p.n_dict && my_entry < p.n_dict + p.n_gen) {
-            const int row = __ldg(p.gen_rows + (my_entry - p.n_dict));
-            const uint2 rw = __ldg(p.rows + (row % M) * T + row / M);
-            V e0, e1, e2, e3, e4;
-            block_eval_terms<CPLX>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), p.IN + lane, L, w, ahead, e0, e1, e2, e3, e4);
-            sd[4 * my_entry + 0] = e0; sd[4 * my_entry + 1] = e1; sd[4 * my_entry + 2] = e2; sd[4 * my_entry + 3] = e4;
-            pe3[my_entry] = e3;
+        if (tt < TH) return;
+        tt -= TH;
+        for (int my_entry = (tt & 31) * (NW / 2) + (tt >> 5); my_entry < p.n_dict + p.n_gen; my_entry += TH) {
+            if (my_entry < p.n_dict) {
+                if (CPLX) {
+                    const uint4 *g = p.dict + (size_t)my_entry * FIX_UNITS;
+                    const uint4 c0 = __ldg(g), c1 = __ldg(g + 1), c2 = __ldg(g + 2), c3 = __ldg(g + 3);
+                    sd[4 * my_entry + 0] = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
+                    sd[4 * my_entry + 1] = S::make(u4hi(c0), __dmul_rn(w, u4hi(c2)));
+                    sd[4 * my_entry + 2] = S::make(u4lo(c1), __dmul_rn(w, u4lo(c3)));
+                    sd[4 * my_entry + 3] = S::make(u4hi(c1), 0.0);
+                }
+            } else {
+                const int row = __ldg(p.gen_rows + (my_entry - p.n_dict));
+                const uint2 rw = __ldg(p.rows + (row % M) * T + row / M);
+                V e0, e1, e2, e3, e4;
+                block_eval_terms<CPLX>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), p.IN + lane, L, w, ahead, e0, e1, e2, e3, e4);
+                sd[4 * my_entry + 0] = e0; sd[4 * my_entry + 1] = e1; sd[4 * my_entry + 2] = e2; sd[4 * my_entry + 3] = e4;
+                pe3[my_entry] = e3;
+            }
         }
     };
+    // barriers among the lower warps only (ids 1, 2): the warps that have nothing to reduce do not take part
+    auto bar_lower = [](int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); };
     const double TWO_PI = 2.0 * 3.14159265358979323846264338327950288;
     if (SD) {
         if (!CPLX)
@@ -365,8 +372,6 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
         // (P, R, Q) of the block's first row were accumulated top-down inside step 1: there is no bottom-up pass
         fst[t] = accP; fst[T + t] = B::neg(fA); fst[2 * T + t] = accQ;
         __syncthreads();
-        // SD: nobody reads the entries any more for this lane: build the next lane's
-        if (SD && next < p.lanes) refresh(next, CPLX ? __dmul_rn(TWO_PI, f_next) : 0.0, next + gridDim.x < p.lanes ? (long long)gridDim.x : 0);
 
         // ---- 2. separator system: A s_{t-1} + B s_t + C s_{t+1} = D ----
         V a, c, d;
@@ -380,12 +385,12 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
             a = B::div(sepA, iv); c = B::div(cc, iv); d = B::div(dd, iv);
         }
         V st, sm;
-        // Cyclic reduction, then parallel cyclic reduction on the surviving odd rows only: the T/2 threads of the lower warps
-        // own compact row t' = (2t'+1); rows are stored de-interleaved by parity so that every access stays unit-stride.  The
-        // other warps sit out the reduction steps (the other resident CTA gets their issue slots); against PCR on all T rows
-        // the shared-memory traffic of the separator system drops by ~45 % (one level) / ~65 % (two levels); measured:
-        // one level -13 % (c64) / -5 % (f64) run time, the second another -4 % / -0.6 %.
-        constexpr int TH = T / 2;
+        // Two levels of cyclic reduction, then parallel cyclic reduction on the surviving rows only: the T/2 threads of the lower
+        // warps own compact row t' = (2t'+1), the lowest T/4 the rows that survive the second level; rows are stored
+        // de-interleaved by parity so that every access stays unit-stride.  Against PCR on all T rows the shared-memory traffic of
+        // the separator system drops by ~65 % (measured: one level -13 % (c64) / -5 % (f64) run time, the second another -4 % /
+        // -0.6 %).  The upper warps rebuild the dictionary entries for the next lane meanwhile (nobody reads them any more for this
+        // lane) and meet the others at the barrier in front of step 3.
         V *ini = red;                                  // [parity][a, c, d][TH]; the odd part's `a` row later holds the solution
         V *sol = ini + 3 * TH;
         const int hk = t >> 1, par = t & 1;
@@ -402,74 +407,48 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
             }
             d = B::div(d2, iv);
         };
-        if constexpr (KRB_BX_CRL == 2) {
-            // second level: the T/2 compact rows are reduced once more the same way, PCR runs on T/4 rows in a quarter of the warps
-            constexpr int TQ = T / 4;
+        if (t >= TH) {
+            if (SD && next < p.lanes) refresh(next, CPLX ? __dmul_rn(TWO_PI, f_next) : 0.0, next + gridDim.x < p.lanes ? (long long)gridDim.x : 0);
+        } else {
             V *ini2 = red + 3 * T;                     // [parity][a, c, d][TQ] (aliases fst); odd part's `a` row: level-2 solution
             V *sol2 = ini2 + 3 * TQ;
             V *pa = ini2 + 6 * TQ, *pb = pa + 3 * TQ;  // double-buffered [a, c, d][TQ]
-            if (t < TH) {
+            {
                 a = ini[3 * TH + t]; c = ini[4 * TH + t]; d = ini[5 * TH + t];         // row 2t+1
                 V ap = S::zero(), cp = S::zero(), dq = S::zero();
                 if (t + 1 < TH) { ap = ini[t + 1]; cp = ini[TH + t + 1]; dq = ini[2 * TH + t + 1]; }   // row 2t+2
                 reduce_row(ini[t], ini[TH + t], ini[2 * TH + t], ap, cp, dq, true);    // row 2t
                 ini2[(par * 3 + 0) * TQ + hk] = a; ini2[(par * 3 + 1) * TQ + hk] = c; ini2[(par * 3 + 2) * TQ + hk] = d;
             }
-            __syncthreads();
+            bar_lower(1, TH);
             if (t < TQ) {
                 a = ini2[3 * TQ + t]; c = ini2[4 * TQ + t]; d = ini2[5 * TQ + t];      // compact row 2t+1
                 V ap = S::zero(), cp = S::zero(), dq = S::zero();
                 if (t + 1 < TQ) { ap = ini2[t + 1]; cp = ini2[TQ + t + 1]; dq = ini2[2 * TQ + t + 1]; }
                 reduce_row(ini2[t], ini2[TQ + t], ini2[2 * TQ + t], ap, cp, dq, true);
                 pa[t] = a; pa[TQ + t] = c; pa[2 * TQ + t] = d;
-            }
-            __syncthreads();
+                bar_lower(2, TQ);
 #pragma unroll
-            for (int s = 1; s < TQ; s <<= 1) {
-                if (t < TQ) {
-                    V am = S::zero(), cm = S::zero(), dm = S::zero(), ap = S::zero(), cp = S::zero(), dq = S::zero();
+                for (int s = 1; s < TQ; s <<= 1) {
+                    V am = S::zero(), cm = S::zero(), dm = S::zero(), ap2 = S::zero(), cp2 = S::zero(), dq2 = S::zero();
                     if (t >= s) { am = pa[t - s]; cm = pa[TQ + t - s]; dm = pa[2 * TQ + t - s]; }
-                    if (t + s < TQ) { ap = pa[t + s]; cp = pa[TQ + t + s]; dq = pa[2 * TQ + t + s]; }
-                    reduce_row(am, cm, dm, ap, cp, dq, 2 * s < TQ);
+                    if (t + s < TQ) { ap2 = pa[t + s]; cp2 = pa[TQ + t + s]; dq2 = pa[2 * TQ + t + s]; }
+                    reduce_row(am, cm, dm, ap2, cp2, dq2, 2 * s < TQ);
                     if (2 * s < TQ) { pb[t] = a; pb[TQ + t] = c; pb[2 * TQ + t] = d; }
                     else sol2[t] = d;
+                    bar_lower(2, TQ);
+                    V *sw = pa; pa = pb; pb = sw;
                 }
-                __syncthreads();
-                V *sw = pa; pa = pb; pb = sw;
             }
-            if (t < TH) {                               // compact rows: odd ones are solved, even ones by substitution
-                V x1 = sol2[hk];
-                if (par == 0) {
-                    const V xl2 = hk > 0 ? sol2[hk - 1] : S::zero();
-                    x1 = S::fnma(S::fnma(ini2[2 * TQ + hk], ini2[hk], xl2), ini2[TQ + hk], x1);
-                }
-                sol[t] = x1;
+            bar_lower(1, TH);                           // the level-2 solution is visible to the T/2 compact rows
+            V x1 = sol2[hk];                            // compact rows: odd ones are solved, even ones by substitution
+            if (par == 0) {
+                const V xl2 = hk > 0 ? sol2[hk - 1] : S::zero();
+                x1 = S::fnma(S::fnma(ini2[2 * TQ + hk], ini2[hk], xl2), ini2[TQ + hk], x1);
             }
-            __syncthreads();
-        } else {
-        V *pa = red + 3 * T, *pb = pa + 3 * TH;        // double-buffered [a, c, d][TH] of the reduced system (pa aliases fst)
-        if (t < TH) {
-            a = ini[3 * TH + t]; c = ini[4 * TH + t]; d = ini[5 * TH + t];             // row 2t+1
-            V ap = S::zero(), cp = S::zero(), dq = S::zero();
-            if (t + 1 < TH) { ap = ini[t + 1]; cp = ini[TH + t + 1]; dq = ini[2 * TH + t + 1]; }   // row 2t+2
-            reduce_row(ini[t], ini[TH + t], ini[2 * TH + t], ap, cp, dq, true);        // row 2t
-            pa[t] = a; pa[TH + t] = c; pa[2 * TH + t] = d;
+            sol[t] = x1;
         }
         __syncthreads();
-#pragma unroll
-        for (int s = 1; s < TH; s <<= 1) {
-            if (t < TH) {
-                V am = S::zero(), cm = S::zero(), dm = S::zero(), ap = S::zero(), cp = S::zero(), dq = S::zero();
-                if (t >= s) { am = pa[t - s]; cm = pa[TH + t - s]; dm = pa[2 * TH + t - s]; }
-                if (t + s < TH) { ap = pa[t + s]; cp = pa[TH + t + s]; dq = pa[2 * TH + t + s]; }
-                reduce_row(am, cm, dm, ap, cp, dq, 2 * s < TH);
-                if (2 * s < TH) { pb[t] = a; pb[TH + t] = c; pb[2 * TH + t] = d; }
-                else sol[t] = d;                                                       // x of row 2t+1
-            }
-            __syncthreads();
-            V *sw = pa; pa = pb; pb = sw;
-        }
-        }
         // even rows by substitution from their own (a, c, d); a thread's left separator: odd rows get it from the lane below
         st = sol[hk];
         {
