@@ -134,3 +134,30 @@ def test_block_small_forced_monte_carlo_order_and_status(oracle, monkeypatch):
     out, status = plan.solve_op(2, varied_values=vv)
     assert status[0] == 0 and (status[1] & api.LANE_ZERO_PIVOT)
     assert_close(out[0], oracle.Circuit(text).solve_op(), what="healthy lane next to a singular one")
+
+
+def test_block_shared_dictionary_many_generic_entries(oracle, monkeypatch):
+    """~200 GENERIC entries in shared-dictionary mode on the 256-thread shape: more entries than the T/2 owner threads of the
+    upper warps, so an owner rebuilds several entries per lane (chain_block_kernel.cuh: refresh)."""
+    monkeypatch.setenv("KRB_CHAIN_BLOCK", "1")
+    nodes = 200
+    text = netgen.resistor_ladder(nodes)
+    circuit = kb.parse_circuit_description(text)
+    varied = [circuit.element_index(f"R{k}") for k in range(1, nodes + 1)]
+    lanes = 333                                      # more lanes than resident CTAs
+    rng = np.random.default_rng(5)
+    vals = np.array([[circuit.element_value(e) * (0.9 + 0.2 * rng.random()) for _ in range(lanes)] for e in varied])
+    plan = kb.Plan(circuit, api.MODE_DC, varied=varied)
+    valid, T, M, n_dict, _, why = chain_block_info(plan)
+    assert plan.info.executor == 1 and valid and T == 256, why
+    out, status = plan.solve_op(lanes, varied_values=np.ascontiguousarray(vals))
+    assert not status.any()
+    monkeypatch.setenv("KRB_CHAIN_SEQ", "1")
+    seq, _ = plan.solve_op(lanes, varied_values=np.ascontiguousarray(vals))
+    monkeypatch.delenv("KRB_CHAIN_SEQ")
+    assert_close(out, seq, rtol=5e-10, what="block vs sequential chain kernel, 200 generic entries")
+    for l in (0, 150, lanes - 1):
+        oc = oracle.Circuit(text)
+        for k, e in enumerate(varied):
+            oc.set_element_value(e, vals[k, l])
+        assert_close(out[l], oc.solve_op(), what=f"block chain, 200 generic entries, lane {l}")
