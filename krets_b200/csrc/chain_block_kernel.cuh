@@ -125,8 +125,9 @@ __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, i
 // SD (shared dictionary): the plan's unique FIXED records and its GENERIC rows together fit KRB_BLOCK_DMAX entries (ladders,
 // RC lines, swept sources: a handful).  Every row then reads its stamped (sub, diag, sup, rhs) from a shared-memory entry:
 // FIXED entries are lane-invariant (real) or refreshed per lane with the lane's w (complex: (re, w*K) is formed once per
-// entry instead of once per row), GENERIC entries are evaluated per lane by one thread each — for the NEXT lane, between
-// the first barrier and the end of the current one, so the main loop is branch-free and no warp waits for a term run.
+// entry instead of once per row), GENERIC entries are evaluated per lane by one thread each — for the NEXT lane, by threads of
+// the upper-half warps while the lower warps reduce the separator system, so the main loop is branch-free and no warp waits
+// for a term run.
 // !SD: FIXED rows read the global dictionary (L1), warps owning GENERIC rows decode them inline (Monte-Carlo plans).
 template <bool CPLX, int T, int M, bool SD>
 __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(const ChainBlockParams p) {
