@@ -111,6 +111,19 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned result buffers it allocates
+    (first touch) sit on that NUMA node: with several ranks the end-to-end path is bound by host-memory / PCIe-root traffic, and
+    remote-node buffers halve it.  Best effort: any failure leaves the default placement."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -366,6 +379,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     distributed = world > 1
+    cpus = bind_to_gpu_numa_node(local_rank) if distributed else None
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert kb.device_count() > 0, "bench needs a CUDA device (no CPU fallback)"
@@ -441,7 +455,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": lanes * world * Ke / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": lanes * 8,
                "d2h_bytes_per_step": lanes * n * 8 + lanes * 4, "steps": Ke,
-               "note": "krb_solve_dc_sweep with KRB_MEM_HOST pinned buffers; D2H of all 5001 unknowns of every point is inside the timed region"}
+               "note": "krb_solve_dc_sweep with KRB_MEM_HOST pinned buffers; D2H of all 5001 unknowns of every point is inside the timed region",
+               "host_cpus_rank0": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)} CPUs local to the GPU, NVML)" if cpus else "default placement")}
         assert np.array_equal(ho[lanes - 1], out[lanes - 1].cpu().numpy())
 
     # ---- final gather of result shards over NVLink (outside the timed region; reported separately) ----
