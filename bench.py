@@ -6,8 +6,15 @@ Workload at every N: BASELINE config 2 — resistor_ladder_5000 (n = 5001, nnz =
 batch: every lane is stamped, refactorised and solved and all 5001 unknowns of every point are delivered point-major.
 
   value  : device-resident throughput (inputs and outputs in HBM), CUDA events, max over ranks
-  e2e    : same metric through the C ABI with pinned HOST buffers (H2D of the sweep values, D2H of every result)
-  roofline: lane-program kernel (krb_lane_vm) against the measured HBM peak, algorithmic bytes per SURVEY.md §8(d)
+  e2e    : same metric through the C ABI with pinned HOST buffers (H2D of the sweep values, D2H of every result), beside the box's
+           bare pinned-D2H ceiling measured in the same run (e2e.link_ceiling_GBps)
+  roofline: the block-partitioned chain kernel (krb_chain_block_kernel, one CTA per lane) against the measured HBM peak.
+           frac = the bytes that must cross HBM (P + s*n per point: inputs in, results out — the kernel keeps the factorisation
+           on chip) / kernel time / peak; frac_alg_model = the same time against SURVEY.md §8(d)'s 3-pass contract bytes
+           (exceeds 1 for a fused kernel: a model figure, not a bus fraction)
+  parity_spot_check: 64 random lanes of the timed output against the CPU oracle (+ linearity), computed after the timed region
+  other_configs: BASELINE configs 3, 4 (trapezoidal and reference backward Euler), 5 (mesh AC / transient) and the ladder with all
+           5000 resistors per-lane, measured in the same run under the same rules, each with its own roofline block
   cpu_baseline / --impl reference: the CPU oracle (restated krets semantics; the krets binary cannot be built here)
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -29,6 +36,8 @@ LANES_PER_GPU = 65536
 STEP = 2.0 ** -16
 METRIC = "solved sweep points/sec (batched sparse LU)"
 UNIT = "points/s"
+ALL_WORKLOADS = ["ladder_dc", "rc_ac", "dual_rc_tran", "dual_rc_tran_be", "mesh_tran", "mesh_ac", "ladder_mc"]
+OTHER_WORKLOADS = ["rc_ac", "ladder_mc", "dual_rc_tran", "dual_rc_tran_be", "mesh_ac", "mesh_tran"]   # other_configs of the default line
 
 
 def workload_config(n_gpus):
@@ -36,7 +45,7 @@ def workload_config(n_gpus):
         "workload": "circuits/resistor_ladder_5000 DC sweep of V1 over 65,536 points per GPU (real f64 batched LU)",
         "n_unknowns": LADDER_N + 1, "nnz": 3 * LADDER_N, "lanes_per_gpu": LANES_PER_GPU, "lanes_total": LANES_PER_GPU * n_gpus,
         "sharding": f"independent lanes, {n_gpus} rank(s), no data-path collective",
-        "l2": "per-step working set (2.6 GB results + spilled U/y planes) >> 126 MB L2; no explicit flush",
+        "l2": "per-step working set (2.6 GB of results per step, inputs 0.5 MB) >> 126 MB L2; no explicit flush",
         "result_layout": "point-major x[lane][unknown] (one vector per solved point, as the reference returns)",
     }
 
@@ -207,143 +216,296 @@ def run_reference(args):
     }))
 
 
-def run_other_workload(args):
-    """BASELINE configs 3, 4 and 5 under the same contract (device-resident, CUDA events, max over ranks, weak scaling: every
-    rank runs the same number of lanes on its own GPU, no data-path collective).  The headline stays config 2."""
+
+# ---- workloads (BASELINE.json configs 2-5 + the per-lane stamping workload VERDICT r1 asked for) -----------------------------
+def mc_matrix(circuit, varied, lanes, lane0):
+    """values[k][lane] = nominal * (0.95 + 0.10 u), u = (splitmix64(seed + n_elements*lane + element) >> 11) * 2^-53; lane 0 nominal
+    (same rule as tests/netgen.mc_factor, vectorised)."""
+    import numpy as np
+    lane = np.arange(lane0, lane0 + lanes, dtype=np.uint64)[None, :]
+    e = np.asarray(varied, dtype=np.uint64)[:, None]
+    with np.errstate(over="ignore"):
+        x = np.uint64(0x6B72657473) + np.uint64(circuit.num_elements) * lane + e + np.uint64(0x9E3779B97F4A7C15)
+        z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    f = 0.95 + 0.10 * ((z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53)
+    f[:, (lane[0] == 0)] = 1.0
+    nominal = np.array([circuit.element_value(int(k)) for k in varied])[:, None]
+    return nominal * f
+
+
+class Workload:
+    """One bench workload: `step()` = one pass of the hot path over one batch resident in HBM.
+    bytes: `alg` = SURVEY 8(d) contract figure per point; `moved` = bytes that must cross HBM per point for this executor
+    (inputs + results for the fused kernels; the factor-store model for the front executor) — roofline.frac is on `moved`."""
+    def __init__(self, **kw):
+        self.extra = {}
+        self.kernel_is_step = False      # True: roofline time = whole step (several kernels), else the lane kernel's own duration
+        self.__dict__.update(kw)
+
+
+def make_workload(name, args, rank):
     import numpy as np
     import torch
-    import torch.distributed as dist
-
     import netgen
     import krets_b200 as kb
     from krets_b200 import api
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    distributed = world > 1
-    if distributed:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    W, K = max(args.warmup, 3), args.steps
-    peak, peak_src = measured_peaks()
-    wl = args.workload
     with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
         golden = json.load(f)
+    dflt = args.lanes == LANES_PER_GPU
+    if name == "ladder_dc":          # BASELINE config 2: the headline
+        circuit = kb.parse_circuit_description(netgen.resistor_ladder(LADDER_N))
+        plan = kb.Plan(circuit, api.MODE_DC, sweep_element=circuit.element_index("V1"), force_lane_vm=args.force_vm)
+        lanes, n = args.lanes, circuit.n
+        vals = (torch.arange(lanes, dtype=torch.float64, device="cuda") + float(rank * lanes)) * STEP
+        out = torch.empty((lanes, n), dtype=torch.float64, device="cuda")
+        shape = chain_block_shape(plan)
+        kname = ("krb_lane_vm<f64>" if plan.info.executor != 1 else f"krb_chain_block_kernel<f64, {shape[0]}, {shape[1]}, SD>" if shape else "krb_chain_kernel<f64>")
 
-    def mc(circuit, varied, lanes, lane0):
-        """values[k][lane] = nominal * (0.95 + 0.10 u), u = (splitmix64(seed + n_elements*lane + element) >> 11) * 2^-53; lane 0 nominal
-        (same rule as tests/netgen.mc_factor, vectorised)."""
-        lane = np.arange(lane0, lane0 + lanes, dtype=np.uint64)[None, :]
-        e = np.asarray(varied, dtype=np.uint64)[:, None]
-        with np.errstate(over="ignore"):
-            x = np.uint64(0x6B72657473) + np.uint64(circuit.num_elements) * lane + e + np.uint64(0x9E3779B97F4A7C15)
-            z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-            z = z ^ (z >> np.uint64(31))
-        f = 0.95 + 0.10 * ((z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53)
-        f[:, (lane[0] == 0)] = 1.0
-        nominal = np.array([circuit.element_value(int(k)) for k in varied])[:, None]
-        return nominal * f
+        def check(k=64):
+            from oracle import oracle
+            oc = oracle.Circuit(netgen.resistor_ladder(LADDER_N))
+            idx = np.random.default_rng(2).choice(lanes, size=min(k, lanes), replace=False)
+            host, v = out[torch.from_numpy(idx).cuda()].cpu().numpy(), vals.cpu().numpy()
+            return {"lanes_checked": int(len(idx)), "max_rel_err_vs_oracle": max(_rel_err(host[i], oc.solve_dc("V1", float(v[l]), float(v[l]), 1.0)[0]) for i, l in enumerate(idx))}
+        return Workload(name=name, config=2, plan=plan, circuit=circuit, lanes=lanes, points=lanes, dtype="f64", s=8, out=out,
+                        step=lambda: plan.solve_dc_sweep(vals, out=out), vals=vals, kernel=kname + " (stamp + LDU refactor + forward/back substitution fused per lane)",
+                        what=workload_config(1)["workload"], alg=int(plan.info.alg_bytes_per_point), moved=8 + 8 * n if shape else int(plan.info.hbm_bytes_per_point),
+                        moved_what="P + s*n: the sweep value in, n results out (SURVEY 8(d) fused floor B_floor)" if shape else "plan model: spilled factor planes + results",
+                        traffic_key="krb_chain_block_kernel_dc_config2_bytes_per_launch" if shape and dflt else None, check=check)
+    if name == "ladder_mc":          # north-star (a): per-lane stamping of device values at size — every resistor is a per-lane input
+        circuit = kb.parse_circuit_description(netgen.resistor_ladder(LADDER_N))
+        varied = [circuit.element_index(f"R{k}") for k in range(1, LADDER_N + 1)]
+        plan = kb.Plan(circuit, api.MODE_DC, varied=varied)
+        lanes, n = (32768 if dflt else args.lanes), circuit.n
+        host_vals = mc_matrix(circuit, varied, lanes, rank * lanes)
+        vals = torch.from_numpy(host_vals).cuda()
+        out = torch.empty((lanes, n), dtype=torch.float64, device="cuda")
+        shape = chain_block_shape(plan)
 
-    extra = {}
-    if wl == "rc_ac":
+        def check(k=4):
+            from oracle import oracle
+            idx = np.random.default_rng(3).choice(lanes, size=min(k, lanes), replace=False)
+            host, worst = out[torch.from_numpy(idx).cuda()].cpu().numpy(), 0.0
+            for i, l in enumerate(idx):
+                oc = oracle.Circuit(netgen.resistor_ladder(LADDER_N))
+                for kk, e in enumerate(varied):
+                    oc.set_element_value(e, host_vals[kk, l])
+                worst = max(worst, _rel_err(host[i], oc.solve_op()))
+            return {"lanes_checked": int(len(idx)), "max_rel_err_vs_oracle": worst}
+        return Workload(name=name, config="2-mc", plan=plan, circuit=circuit, lanes=lanes, points=lanes, dtype="f64", s=8, out=out,
+                        step=lambda: plan.solve_op(lanes, varied_values=vals, out=out),
+                        kernel=(f"krb_chain_block_kernel<f64, {shape[0]}, {shape[1]}, !SD> (every row's stamps decoded from per-lane inputs)" if shape else "krb_chain_kernel<f64>"),
+                        what=f"resistor_ladder_5000 operating point, {lanes} Monte-Carlo lanes per GPU with ALL 5000 resistors per-lane (+-5 %): 40 KB of element values stamped per lane",
+                        alg=int(plan.info.alg_bytes_per_point), moved=8 * len(varied) + 8 * n,
+                        moved_what="P + s*n: 5000 per-lane resistor values in, n results out", traffic_key=None, check=check)
+    if name == "rc_ac":              # BASELINE config 3
         ladder_n = int(os.environ.get("KRB_BENCH_LADDER_N", LADDER_N))      # profiling: other ladder lengths
         circuit = kb.parse_circuit_description(netgen.rc_ladder(ladder_n))
         plan = kb.Plan(circuit, api.MODE_AC, nominal_frequency=1.0)
         allf = kb.generate_frequencies("Decade", 125000, 1.0, 1e8)
-        lanes = args.lanes if args.lanes != LANES_PER_GPU else 131072
-        sel = torch.from_numpy(allf[(rank * lanes) % len(allf):][:lanes].copy()).cuda()
-        lanes = int(sel.shape[0])
-        out = torch.empty((lanes, circuit.n), dtype=torch.complex128, device="cuda")
-        step = lambda: plan.solve_ac(sel, out=out)
-        points, dtype, s = lanes, "c64", 16
-        what = f"resistor_ladder_5000-class RC ladder AC sweep, {lanes} of {len(allf)} log-spaced frequencies per GPU (complex f64)"
-        bytes_pt, bytes_what = int(plan.info.alg_bytes_per_point), "P + s*(4*nnz_lu + 3*n), SURVEY 8(d)"
+        lanes = 131072 if dflt else args.lanes
+        sel_host = allf[(rank * lanes) % len(allf):][:lanes].copy()
+        sel = torch.from_numpy(sel_host).cuda()
+        lanes, n = int(sel.shape[0]), circuit.n
+        out = torch.empty((lanes, n), dtype=torch.complex128, device="cuda")
         shape = chain_block_shape(plan)
-        kernel = f"krb_chain_block_kernel<c64, {shape[0]}, {shape[1]}>" if shape else "krb_chain_kernel<c64>"
-        extra["model_hbm_bytes_per_point"] = int(plan.info.hbm_bytes_per_point)
-    elif wl == "dual_rc_tran":
-        circuit = kb.parse_circuit_description(golden["netlists"]["dual_rc_ladder"])
-        varied = [circuit.element_index(nm) for nm in ["R1", "R2", "C1", "C2"]]
-        lanes = args.lanes if args.lanes != LANES_PER_GPU else 16384
+
+        def check(k=16):
+            from oracle import oracle
+            oc = oracle.Circuit(netgen.rc_ladder(ladder_n))
+            idx = np.sort(np.random.default_rng(4).choice(lanes, size=min(k, lanes), replace=False))
+            host = out[torch.from_numpy(idx).cuda()].cpu().numpy()
+            _, ref = oc.solve_ac(sel_host[idx], nthreads=min(os.cpu_count() or 1, 8))
+            return {"lanes_checked": int(len(idx)), "max_rel_err_vs_oracle": max(_rel_err(host[i], ref[i]) for i in range(len(idx)))}
+        return Workload(name=name, config=3, plan=plan, circuit=circuit, lanes=lanes, points=lanes, dtype="c64", s=16, out=out,
+                        step=lambda: plan.solve_ac(sel, out=out),
+                        kernel=(f"krb_chain_block_kernel<c64, {shape[0]}, {shape[1]}, SD>" if shape else "krb_chain_kernel<c64>"),
+                        what=f"resistor_ladder_5000-class RC ladder AC sweep, {lanes} of {len(allf)} log-spaced frequencies per GPU (complex f64); the full sweep is {len(allf)} lanes = {len(allf) * n * 16 / 1e9:.0f} GB of results",
+                        alg=int(plan.info.alg_bytes_per_point), moved=8 + 16 * n if shape else int(plan.info.hbm_bytes_per_point),
+                        moved_what="P + s*n: the frequency in, n complex results out",
+                        traffic_key="krb_chain_block_kernel_ac_config3_131072_lanes_bytes_per_launch" if shape and dflt and ladder_n == LADDER_N else None, check=check)
+    if name in ("dual_rc_tran", "dual_rc_tran_be"):     # BASELINE config 4: trapezoidal (as written) and the reference's backward Euler
+        integ = api.INTEGRATOR_TRAP if name == "dual_rc_tran" else api.INTEGRATOR_BE_KRETS
+        text = golden["netlists"]["dual_rc_ladder"]
+        circuit = kb.parse_circuit_description(text)
+        names = ["R1", "R2", "C1", "C2"]
+        varied = [circuit.element_index(nm) for nm in names]
+        lanes = 16384 if dflt else args.lanes
         nsteps = args.tran_steps or 10000
-        vals = torch.from_numpy(np.array([[circuit.element_value(e) * netgen.mc_factor(l, j, 4) for l in range(rank * lanes, (rank + 1) * lanes)]
-                                          for j, e in enumerate(varied)])).cuda()
+        host_vals = np.array([[circuit.element_value(e) * netgen.mc_factor(l, j, 4) for l in range(rank * lanes, (rank + 1) * lanes)] for j, e in enumerate(varied)])
+        vals = torch.from_numpy(host_vals).cuda()
         pdc = kb.Plan(circuit, api.MODE_DC, varied=varied)
-        plan = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=5e-6, integrator=api.INTEGRATOR_TRAP)
+        plan = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=5e-6, integrator=integ)
         out = torch.empty((lanes, nsteps + 1, circuit.n), dtype=torch.float64, device="cuda")
-        step = lambda: plan.solve_transient(pdc, nsteps, lanes, varied_values=vals, out=out)
-        points, dtype, s = lanes * nsteps, "f64", 8
-        what = f"circuits/dual_rc_ladder transient, {nsteps} trapezoidal steps x {lanes} Monte-Carlo R/C variants per GPU"
-        bytes_pt, bytes_what = s * (int(plan.info.nnz_lu) + 3 * circuit.n), "B_step = s*(nnz_lu + 3*n), SURVEY 8(d); the kernel keeps factors on chip and only writes s*n per point"
-        extra["floor_bytes_per_point"] = s * circuit.n
-        kernel = "krb_dense_tran<4>"
-    else:
-        transient = wl == "mesh_tran"
+
+        def check(k=2):
+            from oracle import oracle
+            idx = np.random.default_rng(5).choice(lanes, size=min(k, lanes), replace=False)
+            worst = 0.0
+            for l in idx:
+                oc = oracle.Circuit(text)
+                for j, nm in enumerate(names):
+                    oc.set_element_value(oc.element_index(nm), host_vals[j, l])
+                _, ref = oc.solve_tran(5e-6, nsteps * 5e-6, integrator=integ)
+                worst = max(worst, _rel_err(out[int(l)].cpu().numpy(), ref))
+            return {"lanes_checked": int(len(idx)), "rows_per_lane": nsteps + 1, "max_rel_err_vs_oracle": worst}
+        return Workload(name=name, config=4, plan=plan, circuit=circuit, lanes=lanes, points=lanes * nsteps, dtype="f64", s=8, out=out,
+                        step=lambda: plan.solve_transient(pdc, nsteps, lanes, varied_values=vals, out=out),
+                        kernel="krb_dense_tran<4> (per-lane propagator steps, factors on chip)",
+                        what=f"circuits/dual_rc_ladder transient, {nsteps} {'trapezoidal' if integ == api.INTEGRATOR_TRAP else 'backward-Euler (reference: transient.rs:43-112, incl. its source lag)'} steps x {lanes} Monte-Carlo R/C variants per GPU",
+                        alg=8 * (int(plan.info.nnz_lu) + 3 * circuit.n), alg_what="B_step = s*(nnz_lu + 3*n), SURVEY 8(d)",
+                        moved=8 * circuit.n, moved_what="s*n: one result row per solved point (factors and state stay on chip)",
+                        traffic_key="krb_dense_tran_config4_bytes_per_launch" if dflt and not args.tran_steps else None, check=check)
+    if name in ("mesh_ac", "mesh_tran"):                # BASELINE config 5
+        transient = name == "mesh_tran"
         g = args.mesh_grid
-        circuit = kb.parse_circuit_description(netgen.rlc_mesh(g, g, transient=transient))
+        text = netgen.rlc_mesh(g, g, transient=transient)
+        circuit = kb.parse_circuit_description(text)
         kinds = [circuit.element(e).kind for e in range(circuit.num_elements)]
         varied = [e for e, k in enumerate(kinds) if k in (api.KIND_R, api.KIND_C, api.KIND_L)]
-        lanes = args.lanes if args.lanes != LANES_PER_GPU else (512 if transient else 256)
-        vals = torch.from_numpy(mc(circuit, varied, lanes, rank * lanes)).cuda()
+        lanes = (512 if transient else 256) if dflt else args.lanes
+        host_vals = mc_matrix(circuit, varied, lanes, rank * lanes)
+        vals = torch.from_numpy(host_vals).cuda()
+        n = circuit.n
         if transient:
             nsteps = args.tran_steps or 32
             pdc = kb.Plan(circuit, api.MODE_DC, varied=varied, executor=api.EXEC_STAGED)
             plan = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=1e-9, integrator=api.INTEGRATOR_TRAP, executor=api.EXEC_STAGED)
-            out = torch.empty((lanes, nsteps + 1, circuit.n), dtype=torch.float64, device="cuda")
+            out = torch.empty((lanes, nsteps + 1, n), dtype=torch.float64, device="cuda")
             step = lambda: plan.solve_transient(pdc, nsteps, lanes, varied_values=vals, out=out)
             points, dtype, s = lanes * (nsteps + 1), "f64", 8
-            what = f"synthetic {g}x{g} RLC mesh (n={circuit.n}) transient Monte-Carlo: {lanes} lanes per GPU x ({nsteps} trapezoidal steps + operating point)"
-            bytes_pt, bytes_what = s * (int(plan.info.nnz_lu) + 3 * circuit.n), "B_step = s*(nnz_lu + 3*n) per solved time point, SURVEY 8(d)"
+            what = f"synthetic {g}x{g} RLC mesh (n={n}) transient Monte-Carlo: {lanes} lanes per GPU x ({nsteps} trapezoidal steps + operating point)"
+            alg, alg_what = s * (int(plan.info.nnz_lu) + 3 * n), "B_step = s*(nnz_lu + 3*n) per solved time point, SURVEY 8(d)"
+
+            def check(k=1):
+                return _mesh_check(text, varied, host_vals, out, 0, "tran", 1e-9, nsteps)
         else:
             plan = kb.Plan(circuit, api.MODE_AC, varied=varied, nominal_frequency=1e4, executor=api.EXEC_STAGED)
             freqs = torch.logspace(4, 8, lanes, dtype=torch.float64, device="cuda")
-            out = torch.empty((lanes, circuit.n), dtype=torch.complex128, device="cuda")
+            out = torch.empty((lanes, n), dtype=torch.complex128, device="cuda")
             step = lambda: plan.solve_ac(freqs, varied_values=vals, out=out)
             points, dtype, s = lanes, "c64", 16
-            what = f"synthetic {g}x{g} RLC mesh (n={circuit.n}) AC Monte-Carlo: {lanes} lanes per GPU, 10 kHz..100 MHz"
-            bytes_pt, bytes_what = int(plan.info.alg_bytes_per_point), "P + s*(4*nnz_lu + 3*n), SURVEY 8(d)"
-        kernel = "krb_front_factor / krb_front_forward / krb_front_backward"
-        extra["nnz_lu"] = int(plan.info.nnz_lu)
+            what = f"synthetic {g}x{g} RLC mesh (n={n}) AC Monte-Carlo: {lanes} lanes per GPU, 10 kHz..100 MHz"
+            alg, alg_what = int(plan.info.alg_bytes_per_point), "P + s*(4*nnz_lu + 3*n), SURVEY 8(d)"
 
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
+            def check(k=1):
+                return _mesh_check(text, varied, host_vals, out, lanes // 2, "ac", float(freqs[lanes // 2].item()), 0)
+        w = Workload(name=name, config=5, plan=plan, circuit=circuit, lanes=lanes, points=points, dtype=dtype, s=s, out=out, step=step,
+                     kernel="krb_front_factor / krb_front_forward / krb_front_backward (supernodal multifrontal LU, level-scheduled)",
+                     what=what, alg=alg, alg_what=alg_what, moved=alg,
+                     moved_what="the contract bytes themselves: the factor store does not fit on chip, so stamp -> factor -> solve streams it through HBM",
+                     traffic_key=None, check=check)
+        w.kernel_is_step = True
+        w.extra["nnz_lu"] = int(plan.info.nnz_lu)
+        w.heavy = True
+        return w
+    raise ValueError(name)
 
+
+def _rel_err(a, b):
+    """tests/helpers.rel_err: max |a-b| / max(|b|, 1e-6 ||b||_inf) (north-star tolerance 1e-9)."""
+    import numpy as np
+    a, b = np.asarray(a), np.asarray(b)
+    top = float(np.max(np.abs(b))) if b.size else 0.0
+    scale = np.maximum(np.abs(b), 1e-6 * top if top > 0 else 1e-300)
+    return float(np.max(np.abs(a - b) / scale)) if b.size else 0.0
+
+
+def _mesh_check(text, varied, host_vals, out, lane, mode, w, nsteps):
+    """config 5 is far beyond the oracle's natural-order LU: residual on the ORACLE-stamped matrix + SuperLU on the same matrix
+    (tests/mesh_reference.py), one lane."""
+    import numpy as np
+    import scipy.sparse.linalg as spl
+    import mesh_reference as mr
+    from oracle import oracle
+    oc = oracle.Circuit(text)
+    tab = mr.ElementTable(oc)
+    for k, e in enumerate(varied):
+        oc.set_element_value(e, host_vals[k, lane])
+    x = out[lane].cpu().numpy()
+    if mode == "ac":
+        A, b = mr.csc(oc, "ac", w), mr.ac_rhs(oc, tab, tab.values(oc))
+        return {"lanes_checked": 1, "residual_on_oracle_matrix": float(np.max(np.abs(A @ x - b)) / np.max(np.abs(b))),
+                "max_rel_err_vs_superlu_on_oracle_matrix": _rel_err(x, spl.splu(A).solve(b))}
+    rows = min(nsteps, 4)
+    ref = mr.trap_rows(oc, tab, w, rows)
+    return {"lanes_checked": 1, "rows_checked": rows + 1, "max_rel_err_vs_superlu_stepping_on_oracle_matrices": _rel_err(x[: rows + 1], ref)}
+
+
+def time_workload(w, W, K, ctx):
+    """W warm-up steps, then exactly K timed steps between barrier + synchronize, CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import krets_b200 as kb
     for _ in range(W):
-        _, status = step()
-    barrier()
+        _, status = w.step()
+    ctx["barrier"]()
     launches0 = kb.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
+    with ClockSampler(ctx["local_rank"]) as clocks:
+        ctx["barrier"]()
         ev0.record()
         for _ in range(K):
-            step()
+            w.step()
         ev1.record()
-        barrier()
+        ctx["barrier"]()
     launches = kb.kernel_launch_count() - launches0
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    if distributed:
+    ms = ev0.elapsed_time(ev1)
+    # lane-kernel duration, measured live with CUDA events on the launch stream inside the library (separate pass so that the
+    # event reads do not perturb the timed loop above)
+    kernel_ms = 0.0
+    reps = 1 if getattr(w, "heavy", False) else K
+    for _ in range(reps):
+        w.step()
+        kernel_ms += kb.last_kernel_ms()
+    kernel_ms /= reps
+    t = torch.tensor([ms, kernel_ms], dtype=torch.float64, device="cuda")
+    if ctx["distributed"]:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = points * world * K / (ms * 1e-3)
-    if rank == 0:
-        achieved = bytes_pt * points * K / (ms * 1e-3) / 1e9
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-                "config": {"workload": what, "n_unknowns": circuit.n, "lanes_per_gpu": lanes, "sharding": f"independent lanes, {world} rank(s), no data-path collective",
-                           "l2": "per-step working set >> 126 MB L2; no explicit flush", **extra},
-                "clocks": clocks.summary(), "e2e": None, "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "kernel": kernel, "bytes_per_point": bytes_pt, "bytes_model": bytes_what, "peak_source": peak_src,
-                             "note": "whole-step time (all kernels of the step), not a single kernel's duration"},
-                "lanes_with_status": int((status != 0).sum().item())}
-        print(json.dumps(line))
-    if distributed:
-        dist.destroy_process_group()
+    ms_max, kernel_ms = float(t[0].item()), float(t[1].item())
+    world = ctx["world"]
+    peak, peak_src = measured_peaks()
+    t_roof = (ms_max / K if w.kernel_is_step else kernel_ms) * 1e-3
+    moved_GBps = w.moved * w.points / t_roof / 1e9
+    alg_GBps = w.alg * w.points / t_roof / 1e9
+    traffic = ncu_traffic(w.traffic_key) if w.traffic_key else None
+    res = {
+        "workload": w.what, "baseline_config": w.config, "dtype": w.dtype, "n_unknowns": w.circuit.n, "lanes_per_gpu": w.lanes,
+        "value": w.points * world * K / (ms_max * 1e-3), "unit": UNIT, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "gpu_launches": int(launches),
+        "lanes_with_status": int((status != 0).sum().item()),
+        "roofline": {"bound": "hbm", "achieved": moved_GBps, "peak": peak, "unit": "GB/s", "frac": moved_GBps / peak, "traffic": traffic,
+                     "kernel": w.kernel, "kernel_ms": kernel_ms, "timed": "whole step (all kernels of the step)" if w.kernel_is_step else "the lane kernel alone, CUDA events on its stream",
+                     "bytes_per_point": w.moved, "bytes_model": w.moved_what, "peak_source": peak_src,
+                     "frac_of_nominal_8TBps": moved_GBps / 8000.0,
+                     "alg_bytes_per_point": w.alg, "alg_bytes_model": getattr(w, "alg_what", "P + s*(4*nnz_lu + 3*n), SURVEY 8(d)"),
+                     "frac_alg_model": alg_GBps / peak,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, round-2 capture (profiles/traffic.json)" if traffic else None},
+        **w.extra,
+    }
+    return res, clocks.summary()
+
+
+def link_ceiling(ctx, nbytes=1 << 30, reps=3):
+    """Bare pinned cudaMemcpyAsync D2H on every rank at once: the box's ceiling for delivering results to the host."""
+    import torch
+    import torch.distributed as dist
+    src = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst.copy_(src, non_blocking=True)
+    ctx["barrier"]()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if ctx["distributed"]:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del src, dst
+    return nbytes * reps * ctx["world"] / float(t.item()) / 1e9
 
 
 def main():
@@ -355,24 +517,22 @@ def main():
     ap.add_argument("--lanes", type=int, default=LANES_PER_GPU)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_configs block (BASELINE configs 3-5 + the Monte-Carlo ladder)")
     ap.add_argument("--force-vm", action="store_true", help="profiling: run the workload on the general lane VM instead of the chain executor")
-    ap.add_argument("--workload", default="ladder_dc", choices=["ladder_dc", "rc_ac", "dual_rc_tran", "mesh_tran", "mesh_ac"],
-                    help="ladder_dc = BASELINE config 2 (the headline, default); rc_ac = config 3, dual_rc_tran = config 4, mesh_* = config 5")
+    ap.add_argument("--workload", default="ladder_dc", choices=ALL_WORKLOADS,
+                    help="ladder_dc = BASELINE config 2 (the headline, default); rc_ac = config 3, dual_rc_tran(_be) = config 4, mesh_* = config 5, "
+                         "ladder_mc = ladder 5000 with every resistor per-lane")
     ap.add_argument("--mesh-grid", type=int, default=224)
     ap.add_argument("--tran-steps", type=int, default=0, help="time steps per lane for the transient workloads (0 = workload default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload != "ladder_dc":
-        return run_other_workload(args)
 
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    import netgen
     import krets_b200 as kb
-    from krets_b200 import api
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -383,60 +543,28 @@ def main():
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert kb.device_count() > 0, "bench needs a CUDA device (no CPU fallback)"
-    W = max(args.warmup, 3)
-    K = args.steps
-    lanes = args.lanes
-
-    circuit = kb.parse_circuit_description(netgen.resistor_ladder(LADDER_N))
-    plan = kb.Plan(circuit, api.MODE_DC, sweep_element=circuit.element_index("V1"), force_lane_vm=args.force_vm)
-    info = plan.info
-    n = info.n
-    vals = (torch.arange(lanes, dtype=torch.float64, device="cuda") + float(rank * lanes)) * STEP
-    out = torch.empty((lanes, n), dtype=torch.float64, device="cuda")
+    W, K = max(args.warmup, 3), args.steps
 
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
+    ctx = {"world": world, "rank": rank, "local_rank": local_rank, "distributed": distributed, "barrier": barrier}
 
-    def step():
-        plan.solve_dc_sweep(vals, out=out)
+    # ---- the main line: device-resident throughput of the selected workload ----
+    w = make_workload(args.workload, args, rank)
+    info = w.plan.info
+    main_res, clocks = time_workload(w, W, K, ctx)
+    lanes, n = w.lanes, w.circuit.n
+    parity = w.check() if rank == 0 else None
+    if w.name == "ladder_dc" and rank == 0:      # also the size-independent property: x(lane) = v_lane * x(1 V)
+        ref = w.out[lanes - 1] / w.vals[lanes - 1]
+        parity["linearity_max_rel_err"] = float(((w.out[lanes // 2] - ref * w.vals[lanes // 2]).abs().max() / ref.abs().max()).item())
 
-    # ---- device-resident throughput ----
-    for _ in range(W):
-        step()
-    barrier()
-    launches0 = kb.kernel_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = 0.0
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        ev0.record()
-        for _ in range(K):
-            step()
-        ev1.record()
-        barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = kb.kernel_launch_count() - launches0
-    # lane-program kernel duration, measured live with CUDA events on the launch stream (separate pass so that the event
-    # reads do not perturb the timed loop above)
-    for _ in range(K):
-        step()
-        kernel_ms += kb.last_kernel_ms()
-    kernel_ms /= K
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = lanes * world * K / (ms_max * 1e-3)
-
-    # ---- parity spot check inside the bench (linearity against lane 65535) ----
-    ref = out[lanes - 1] / vals[lanes - 1]
-    lin_err = float(((out[lanes // 2] - ref * vals[lanes // 2]).abs().max() / ref.abs().max()).item())
-
-    # ---- end to end through the C ABI with pinned host buffers ----
+    # ---- end to end through the C ABI with pinned host buffers (headline workload only) ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and w.name == "ladder_dc":
+        out, vals, plan = w.out, w.vals, w.plan
         h_vals = torch.empty(lanes, dtype=torch.float64).pin_memory()
         h_vals.copy_(vals.cpu())
         h_out = torch.empty((lanes, n), dtype=torch.float64).pin_memory()
@@ -453,15 +581,21 @@ def main():
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if distributed:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": lanes * world * Ke / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": lanes * 8,
-               "d2h_bytes_per_step": lanes * n * 8 + lanes * 4, "steps": Ke,
+        d2h = lanes * n * 8 + lanes * 4
+        e2e = {"value": lanes * world * Ke / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": lanes * 8, "d2h_bytes_per_step": d2h, "steps": Ke,
                "note": "krb_solve_dc_sweep with KRB_MEM_HOST pinned buffers; D2H of all 5001 unknowns of every point is inside the timed region",
                "host_cpus_rank0": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)} CPUs local to the GPU, NVML)" if cpus else "default placement")}
         assert np.array_equal(ho[lanes - 1], out[lanes - 1].cpu().numpy())
+        del h_out, ho
+        e2e["d2h_GBps"] = d2h * world * Ke / float(t.item()) / 1e9
+        e2e["link_ceiling_GBps"] = link_ceiling(ctx)
+        e2e["frac_of_link_ceiling"] = e2e["d2h_GBps"] / e2e["link_ceiling_GBps"]
+        e2e["link_ceiling_note"] = f"bare pinned cudaMemcpyAsync D2H of 1 GiB x 3 on all {world} rank(s) at once, aggregate"
 
     # ---- final gather of result shards over NVLink (outside the timed region; reported separately) ----
     gather = None
-    if distributed:
+    if distributed and w.name == "ladder_dc":
+        out = w.out
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         bufs = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
@@ -477,47 +611,49 @@ def main():
         nbytes = out.numel() * 8 * (world - 1)
         gather = {"collective": "ncclGather of x shards to rank 0", "ms": float(gms.item()), "bytes_inbound_rank0": nbytes,
                   "GBps": nbytes / (float(gms.item()) * 1e-3) / 1e9,
-                  "value_with_gather": lanes * world / ((ms_max / K + float(gms.item())) * 1e-3)}
+                  "value_with_gather": lanes * world / ((main_res["ms_per_step"] + float(gms.item())) * 1e-3)}
         del bufs
 
+    # ---- the other BASELINE configs, measured in the same run under the same rules ----
+    others = []
+    if not args.no_others and w.name == "ladder_dc" and lanes == LANES_PER_GPU:
+        del w
+        torch.cuda.empty_cache()
+        for name in OTHER_WORKLOADS:
+            try:
+                ow = make_workload(name, args, rank)
+                heavy = getattr(ow, "heavy", False)
+                res, _ = time_workload(ow, 1 if heavy else 3, 2 if heavy else max(3, min(K, 10)), ctx)
+                if rank == 0:
+                    res["parity_spot_check"] = ow.check()
+                res["name"] = name
+                others.append(res)
+            except Exception as ex:   # a failing side workload must not lose the headline line
+                others.append({"name": name, "error": f"{type(ex).__name__}: {ex}"})
+            ow = None
+            torch.cuda.empty_cache()
+
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        alg = int(info.alg_bytes_per_point)
-        achieved = alg * lanes / (kernel_ms * 1e-3) / 1e9
-        floor_bytes = 8 + 8 * n
-        shape = chain_block_shape(plan)
-        if info.executor != 1:
-            kname, tkey = "krb_lane_vm<f64>", None
-        elif shape:
-            kname, tkey = f"krb_chain_block_kernel<f64, {shape[0]}, {shape[1]}>", "krb_chain_block_kernel_dc_config2_bytes_per_launch"
-        else:
-            kname, tkey = "krb_chain_kernel<f64>", "krb_chain_kernel_dc_config2_bytes_per_launch"
-        traffic = ncu_traffic(tkey) if tkey and lanes == LANES_PER_GPU else None
-        real = int(info.hbm_bytes_per_point) * lanes / (kernel_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world),
-            "clocks": clocks.summary(),
-            "e2e": e2e,
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": kname + " (stamp + LDU refactor + forward/back substitution fused per lane)",
-                         "kernel_ms": kernel_ms, "alg_bytes_per_point": alg, "peak_source": peak_src,
-                         "model_hbm_bytes_per_point": int(info.hbm_bytes_per_point),
-                         "fused_floor_bytes_per_point": floor_bytes,
-                         "frac_of_nominal_8TBps": achieved / 8000.0,
-                         "moved_GBps": real, "moved_frac_of_peak": real / peak,
-                         "note": "achieved uses the 3-pass algorithmic bytes of SURVEY §8(d) (P + s*(4*nnz_lu + 3*n)); the fused kernel moves "
-                                 "model_hbm_bytes_per_point (= ncu traffic / lanes), so frac exceeds 1; moved_GBps / moved_frac_of_peak is what "
-                                 "actually crosses HBM per second — see DESIGN.md §5.1"},
-            "plan": {"executor": "chain" if info.executor == 1 else "lane_vm", "nnz_lu": int(info.nnz_lu), "scratch_slots": int(info.scratch_slots), "spill_planes": int(info.spill_planes),
-                     "program_ops": int(info.program_ops)},
-            "parity_spot_check": {"linearity_max_rel_err": lin_err},
+            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": main_res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": main_res["dtype"], "data": "synthetic",
+            "config": workload_config(world) if (args.workload == "ladder_dc" and lanes == LANES_PER_GPU) else
+                      {"workload": main_res["workload"], "n_unknowns": n, "nnz": int(info.nnz), "lanes_per_gpu": lanes, "lanes_total": lanes * world,
+                       "sharding": f"independent lanes, {world} rank(s), no data-path collective",
+                       "l2": f"per-step working set ({main_res['roofline']['bytes_per_point'] * main_res['lanes_per_gpu'] / 1e9:.2f} GB of inputs + results per step) >> 126 MB L2; no explicit flush",
+                       "result_layout": "point-major x[lane][unknown] (one vector per solved point, as the reference returns)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
+            "plan": {"executor": {0: "lane_vm", 1: "chain", 2: "front"}[int(info.executor)], "nnz_lu": int(info.nnz_lu), "flops_per_point": int(info.flops_per_point)},
+            "parity_spot_check": parity, "lanes_with_status": main_res["lanes_with_status"],
         }
+        for k in ("nnz_lu",):
+            if k in main_res:
+                line["config"][k] = main_res[k]
         if gather:
             line["gather"] = gather
-        if world == 1 and not args.no_cpu:
+        if others:
+            line["other_configs"] = others
+        if world == 1 and not args.no_cpu and args.workload == "ladder_dc":
             from oracle import oracle
             oracle.build()
             threads = os.cpu_count() or 1

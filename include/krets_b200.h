@@ -49,8 +49,16 @@ enum {
     KRB_LANE_OK = 0,
     KRB_LANE_ZERO_PIVOT = 1,            /* a static pivot was exactly zero or non-finite (-> DecompositionFailed) */
     KRB_LANE_NOT_CONVERGED = 2,         /* NR hit maximum_iterations (-> MaximumIterationsExceeded) */
-    KRB_LANE_NONFINITE = 4              /* a delivered unknown is inf/nan */
+    KRB_LANE_NONFINITE = 4,             /* a delivered unknown is inf/nan */
+    KRB_LANE_INACCURATE = 8             /* pivot growth: a scaled factor entry (u^ = u/pivot, or a front's multiplier l/pivot) reached
+                                           2^24 on this lane, i.e. the STATIC pivot cancelled >= 24 bits against its row — where the
+                                           reference's faer LU (op.rs:50, ac.rs:70) would have exchanged rows.  The lane's unknowns may
+                                           have lost >= 7 of 16 digits (error ~ eps * growth >= 1e-9, the parity contract).  The host
+                                           mirror re-solves such lanes on the front executor (pivoting inside fronts + refinement).
+                                           Linear circuits only: over Newton iterates a diode conductance spans tens of decades, so the
+                                           measure says nothing there and the convergence check (solver.rs:76-104) is the guard */
 };
+#define KRB_GROWTH_LIMIT_LOG2 24
 
 /* ---- circuit (flattened krets_parser::circuit::Circuit, circuit.rs:7-20) ------------------------------ */
 /* element kinds; same order as the reference's parser `alt`, elements.rs:45-55 */
@@ -114,7 +122,11 @@ typedef struct krb_plan_opts {
     int32_t n_varied;                 /* Monte-Carlo: number of elements whose value is a per-lane input */
     const int32_t *varied_elements;   /* [n_varied] element ordinals (R/C/L/V/I) */
     int32_t threads_per_block;        /* 0 = default */
-    int32_t reserved;
+    int32_t refine_steps;             /* front executor: 0 = default (AC plans: 2 steps of iterative refinement on the stamped matrix,
+                                         DC/TRAN: none); k > 0 = k steps, followed by a componentwise backward-error check of every
+                                         delivered row (|b - A x| <= 2^-40 (|A||x| + |b|)) that sets or CLEARS KRB_LANE_INACCURATE —
+                                         the a-posteriori answer replaces the a-priori growth flag.  Used by the host mirror's
+                                         pivoting fallback */
 } krb_plan_opts;
 
 void krb_default_plan_opts(krb_plan_opts *o);

@@ -12,6 +12,7 @@ pub const KRB_ERR_UNSUPPORTED: i32 = 7;
 pub const KRB_LANE_ZERO_PIVOT: i32 = 1;
 pub const KRB_LANE_NOT_CONVERGED: i32 = 2;
 pub const KRB_LANE_NONFINITE: i32 = 4;
+pub const KRB_LANE_INACCURATE: i32 = 8;
 
 pub const KRB_R: i32 = 0;
 pub const KRB_C: i32 = 1;
@@ -70,7 +71,7 @@ pub struct krb_plan_opts {
     pub n_varied: i32,
     pub varied_elements: *const i32,
     pub threads_per_block: i32,
-    pub reserved: i32,
+    pub refine_steps: i32,
 }
 
 #[repr(C)]

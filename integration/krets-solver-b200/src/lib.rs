@@ -65,6 +65,11 @@ fn first_failed_lane(status: &[i32], max_iter: usize) -> Result<()> {
         if s & KRB_LANE_NOT_CONVERGED != 0 {
             return Err(Error::MaximumIterationsExceeded(max_iter)); // op.rs:79-81
         }
+        // inf/nan rows and lanes whose static pivots lost accuracy (and that the caller did not re-solve on a
+        // KRB_EXEC_STAGED plan with refine_steps > 0, as the C++ host mirror does) are not returned as successes
+        if s & (KRB_LANE_NONFINITE | KRB_LANE_INACCURATE) != 0 {
+            return Err(Error::DecompositionFailed);
+        }
     }
     Ok(())
 }

@@ -28,7 +28,7 @@ class KrbPlanOpts(C.Structure):         # krb_plan_opts
     _fields_ = [("struct_size", C.c_int32), ("exec", C.c_int32), ("integrator", C.c_int32), ("scratch_slots", C.c_int32),
                 ("time_step", C.c_double), ("nominal_frequency", C.c_double), ("sweep_element", C.c_int32),
                 ("n_varied", C.c_int32), ("varied_elements", C.POINTER(C.c_int32)), ("threads_per_block", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("refine_steps", C.c_int32)]
 
 
 class KrbPlanInfo(C.Structure):         # krb_plan_info

@@ -20,7 +20,7 @@ MODE_DC, MODE_AC, MODE_TRAN = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 LAYOUT_POINT_MAJOR, LAYOUT_LANE_INTERLEAVED = 0, 1
 EXEC_FUSED, EXEC_STAGED, EXEC_LANE_VM = 0, 1, 2   # krb_plan_opts.exec (STAGED = the supernodal front executor)
-LANE_ZERO_PIVOT, LANE_NOT_CONVERGED, LANE_NONFINITE = 1, 2, 4
+LANE_ZERO_PIVOT, LANE_NOT_CONVERGED, LANE_NONFINITE, LANE_INACCURATE = 1, 2, 4, 8
 KIND_R, KIND_C, KIND_L, KIND_V, KIND_I, KIND_D, KIND_NMOS = range(7)   # krb_element.kind (elements.rs:45-55 order)
 
 _ERR_NAMES = {
@@ -291,12 +291,40 @@ def _ptr(x):
     return C.c_void_p(x.ctypes.data)
 
 
+def _f64_in(x, shape, name):
+    """A lane-sized INPUT of the C ABI as packed float64: host arrays are converted (np.ascontiguousarray), device tensors must
+    already be contiguous float64 (no silent device copies); the shape is checked either way."""
+    if x is None:
+        return None
+    if _is_device(x):
+        import torch
+        if x.dtype != torch.float64 or not x.is_contiguous():
+            raise ValueError(f"{name}: CUDA tensors must be contiguous float64 (got {x.dtype}, contiguous={x.is_contiguous()})")
+    else:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+    if shape is not None and tuple(x.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(x.shape)}")
+    return x
+
+
+def _check_out(x, shape, complex_, name="out"):
+    """A caller-provided OUTPUT buffer is written in place: it must be contiguous, of the right dtype and shape."""
+    if _is_device(x):
+        import torch
+        ok = x.dtype == (torch.complex128 if complex_ else torch.float64) and x.is_contiguous()
+    else:
+        ok = isinstance(x, np.ndarray) and x.dtype == (np.complex128 if complex_ else np.float64) and x.flags["C_CONTIGUOUS"]
+    if not ok or tuple(x.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected a contiguous {'complex128' if complex_ else 'float64'} array of shape {tuple(shape)}")
+    return x
+
+
 class Plan:
     """One-time symbolic analysis of a circuit for one stamp mode (krb_analyze) + lane-batch solves (krb_solve_*)."""
 
     def __init__(self, circuit: Circuit, mode: int, *, sweep_element: int = -1, varied=(), time_step: float = 0.0,
                  nominal_frequency: float = 0.0, scratch_slots: int = 0, threads_per_block: int = 0, force_lane_vm: bool = False,
-                 integrator: int = 0, executor: int | None = None):
+                 integrator: int = 0, executor: int | None = None, refine_steps: int = 0):
         L = _lib.lib()
         self.circuit, self.mode = circuit, mode
         self.varied = list(varied)
@@ -313,6 +341,7 @@ class Plan:
         o.threads_per_block = threads_per_block
         o.exec = executor if executor is not None else (EXEC_LANE_VM if force_lane_vm else EXEC_FUSED)
         o.integrator = integrator
+        o.refine_steps = refine_steps     # front executor: k > 0 = k refinement steps + backward-error check (krets_b200.h)
         self._varied_arr = (C.c_int32 * max(len(self.varied), 1))(*self.varied)
         o.n_varied = len(self.varied)
         o.varied_elements = C.cast(self._varied_arr, C.POINTER(C.c_int32))
@@ -404,7 +433,8 @@ class Plan:
     def solve_op(self, lanes: int = 1, varied_values=None, out=None, cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR,
                  return_iterations=False):
         cfg = cfg or SolverConfig()
-        out = out if out is not None else np.zeros((lanes, self.n), dtype=np.float64)
+        varied_values = _f64_in(varied_values, (len(self.varied), lanes) if self.varied else None, "varied_values")
+        out = _check_out(out, _shape(layout, lanes, 1, self.n), False) if out is not None else _like_out(varied_values, _shape(layout, lanes, 1, self.n), False)
         status = _like_int(out, lanes)
         iters = _like_int(out, lanes) if return_iterations else None
         ov, _keep = self._ov(varied_values)
@@ -415,8 +445,12 @@ class Plan:
 
     def solve_dc_sweep(self, sweep_values, varied_values=None, out=None, cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR):
         cfg = cfg or SolverConfig()
+        sweep_values = _f64_in(sweep_values, None, "sweep_values")
+        if sweep_values.ndim != 1:
+            raise ValueError("sweep_values: expected a 1-D array of per-lane source values")
         lanes = int(sweep_values.shape[0])
-        out = out if out is not None else _like_out(sweep_values, (lanes, self.n), False)
+        varied_values = _f64_in(varied_values, (len(self.varied), lanes) if self.varied else None, "varied_values")
+        out = _check_out(out, _shape(layout, lanes, 1, self.n), False) if out is not None else _like_out(sweep_values, _shape(layout, lanes, 1, self.n), False)
         status = _like_int(out, lanes)
         ov, _keep = self._ov(varied_values)
         io = self._io([sweep_values, out, varied_values], layout)
@@ -427,13 +461,23 @@ class Plan:
     def solve_ac(self, frequencies, varied_values=None, op_solution=None, out=None, cfg: SolverConfig | None = None,
                  layout=LAYOUT_POINT_MAJOR):
         cfg = cfg or SolverConfig()
+        frequencies = _f64_in(frequencies, None, "frequencies")
+        if frequencies.ndim != 1:
+            raise ValueError("frequencies: expected a 1-D array")
         lanes = int(frequencies.shape[0])
-        out = out if out is not None else _like_out(frequencies, (lanes, self.n), True)
+        varied_values = _f64_in(varied_values, (len(self.varied), lanes) if self.varied else None, "varied_values")
+        out = _check_out(out, _shape(layout, lanes, 1, self.n), True) if out is not None else _like_out(frequencies, _shape(layout, lanes, 1, self.n), True)
         status = _like_int(out, lanes)
         ov, _keep = self._ov(varied_values)
         lanes_op = 0
         if op_solution is not None:
-            lanes_op = 1 if op_solution.ndim == 1 else int(op_solution.shape[0])
+            op_solution = _f64_in(op_solution, None, "op_solution")
+            if op_solution.ndim == 1 and op_solution.shape[0] == self.n:
+                lanes_op = 1
+            elif op_solution.ndim == 2 and tuple(op_solution.shape) == (lanes, self.n):
+                lanes_op = lanes
+            else:
+                raise ValueError(f"op_solution: expected shape ({self.n},) or ({lanes}, {self.n})")
         io = self._io([frequencies, out, varied_values, op_solution], layout)
         _check_krb(_lib.lib().krb_solve_ac(self._h, C.byref(cfg.c), _ptr(frequencies), lanes, C.byref(ov) if ov else None,
                                            _ptr(op_solution), lanes_op, _ptr(out), _ptr(status), C.byref(io)))
@@ -443,15 +487,23 @@ class Plan:
                         cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR):
         """self must be a MODE_TRAN plan; plan_dc the MODE_DC plan of the same circuit (row 0 = OP, transient.rs:21)."""
         cfg = cfg or SolverConfig()
+        varied_values = _f64_in(varied_values, (len(self.varied), lanes) if self.varied else None, "varied_values")
+        shape = (lanes, n_steps + 1, self.n) if layout == LAYOUT_POINT_MAJOR else (n_steps + 1, self.n, lanes)
         if out is None:
-            shape = (lanes, n_steps + 1, self.n) if layout == LAYOUT_POINT_MAJOR else (n_steps + 1, self.n, lanes)
             out = _like_out(varied_values, shape, False) if varied_values is not None else np.zeros(shape, dtype=np.float64)
+        else:
+            _check_out(out, shape, False)
         status = _like_int(out, lanes)
         ov, _keep = self._ov(varied_values)
         io = self._io([out, varied_values], layout)
         _check_krb(_lib.lib().krb_solve_transient(plan_dc._h, self._h, C.byref(cfg.c), n_steps, lanes, C.byref(ov) if ov else None,
                                                   _ptr(out), _ptr(status), C.byref(io)))
         return out, status
+
+
+def _shape(layout, lanes, rows, n):
+    """result shape of a one-row analysis: x[lane][unknown] point-major, x[unknown][lane] lane-interleaved"""
+    return (lanes, n) if layout == LAYOUT_POINT_MAJOR else (n, lanes)
 
 
 def _like_out(ref, shape, complex_):

@@ -72,6 +72,9 @@ int32_t krb_analyze(const krb_circuit *c, int32_t mode, const krb_plan_opts *opt
     if (!p) return KRB_ERR_OUT_OF_MEMORY;
     std::string err;
     int rc;
+    NvtxRange nvtx_analyze(mode == KRB_MODE_DC ? "krb_analyze (DC): stamps, pivot plan, symbolic LU, executor tables"
+                           : mode == KRB_MODE_AC ? "krb_analyze (AC): stamps, pivot plan, symbolic LU, executor tables"
+                                                 : "krb_analyze (TRAN): stamps, pivot plan, symbolic LU, executor tables");
     try {
         rc = analyze(c->c, mode, o, p->p, err);
     } catch (const std::exception &ex) {

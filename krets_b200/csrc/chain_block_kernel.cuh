@@ -47,8 +47,13 @@ struct ChainBlockParams {
 enum : uint32_t { BR_HAS_U2 = 2u, BR_NT_SHIFT = 2, BR_NT_MASK = 0x3fffu, BR_SLOT_SHIFT = 16 };
 constexpr int KRB_BLOCK_DMAX = 256;   // entries of the shared-memory dictionary (unique FIXED records + GENERIC rows)
 
-// Pivot health on the integer pipe: key(w) = (exponent field) - 1 as an unsigned number is >= 0x7fe00000 exactly when the
-// exponent field is all-zero (0 / denormal) or all-one (inf / nan); a thread keeps the running maximum of its pivots' keys.
+// Pivot health on the integer pipe.  The lane keeps ONE running maximum, of growth_key(u^) = the high word of |u^| = |sup / pivot|
+// (complex: of the larger component):
+//   * a pivot that is zero, denormal, inf or nan makes u^ non-finite (rcp.approx.ftz -> inf/0 -> nan in the correction step), i.e.
+//     key >= 0x7ff00000                                               -> KRB_LANE_ZERO_PIVOT (the reference: DecompositionFailed)
+//   * |u^| >= 2^KRB_GROWTH_LIMIT_LOG2: the static pivot cancelled that many bits against its row, where faer's per-factorisation
+//     partial pivoting (op.rs:50) would have exchanged rows           -> KRB_LANE_INACCURATE
+// Pivots whose quotients are not all kept (the separator system's last PCR step) are tested directly (pivot_key).
 __device__ __forceinline__ uint32_t pivot_key(double w) { return ((uint32_t)__double2hiint(w) & 0x7ff00000u) - 0x00100000u; }
 constexpr uint32_t KRB_BAD_PIVOT_KEY = 0x7fe00000u;
 
@@ -57,8 +62,8 @@ template <> struct BlockSc<false> {
     typedef double T;
     // reciprocal of the pivot to ~1 ulp, returned as (r0, t):  q / w = fma(q*r0, t, q*r0)
     struct Inv { double r0, t; };
-    static __device__ __forceinline__ Inv inv(double w, uint32_t &worst) {
-        worst = max(worst, pivot_key(w));
+    static __device__ __forceinline__ uint32_t bad_pivot(double w) { return pivot_key(w) >= KRB_BAD_PIVOT_KEY ? KRB_NONFINITE_KEY : 0u; }
+    static __device__ __forceinline__ Inv inv(double w) {
         const double r0 = rcp_seed(w);
         const double e = fma(-w, r0, 1.0);
         return Inv{r0, fma(e, e, e)};
@@ -71,9 +76,9 @@ template <> struct BlockSc<false> {
 template <> struct BlockSc<true> {
     typedef double2 T;
     struct Inv { double2 c; };    // conj(w) / |w|^2
-    static __device__ __forceinline__ Inv inv(double2 w, uint32_t &worst) {
+    static __device__ __forceinline__ uint32_t bad_pivot(double2 w) { return pivot_key(fma(w.x, w.x, w.y * w.y)) >= KRB_BAD_PIVOT_KEY ? KRB_NONFINITE_KEY : 0u; }
+    static __device__ __forceinline__ Inv inv(double2 w) {
         const double ns = fma(w.x, w.x, w.y * w.y);
-        worst = max(worst, pivot_key(ns));
         const double r = fast_rcp(ns);
         return Inv{make_double2(w.x * r, -w.y * r)};
     }
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
         // keep what is derived from the packed indices (20 shared-memory addresses) inside the loop: hoisted, it is spilled
 #pragma unroll
         for (int i = 0; i < (M + PKN - 1) / PKN; ++i) asm volatile("" : "+r"(pk[i]));
-        uint32_t worst = 0;                          // running maximum of the pivots' keys (pivot_key)
+        uint32_t grow = 0;                           // running maximum of growth_key(u^) (see pivot_key / growth_key above)
         V u[MI], y[MI];
         V lprev = S::zero(), pu2 = S::zero(), u2v = S::zero();
         V sepA = S::zero(), sepB = S::zero(), sepD = S::zero(), sepS = S::zero();
@@ -260,8 +265,9 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
                 yk = S::fnma(e4, e0, y[j > 0 ? j - 1 : 0]);
                 lk = B::neg(S::mul(e0, lprev));
             }
-            const typename B::Inv iv = B::inv(wk, worst);
+            const typename B::Inv iv = B::inv(wk);
             u[j] = B::div(s1, iv);
+            grow = max(grow, growth_key(u[j]));
             y[j] = B::div(yk, iv);
             lprev = B::div(lk, iv);
             mycol[j] = lprev;
@@ -382,8 +388,9 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
             const V bb = S::fnma(sepB, sepS, qn);
             const V cc = B::neg(S::mul(sepS, rn));
             const V dd = S::fnma(sepD, sepS, pn);
-            const typename B::Inv iv = B::inv(bb, worst);
+            const typename B::Inv iv = B::inv(bb);
             a = B::div(sepA, iv); c = B::div(cc, iv); d = B::div(dd, iv);
+            grow = max(grow, max(growth_key(a), growth_key(c)));
         }
         V st, sm;
         // Two levels of cyclic reduction, then parallel cyclic reduction on the surviving rows only: the T/2 threads of the lower
@@ -400,11 +407,13 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
         auto reduce_row = [&](V am, V cm, V dm, V ap, V cp, V dq, bool need_ac) {
             const V b2 = S::fnma(S::fnma(B::one(), a, cm), c, ap);
             const V d2 = S::fnma(S::fnma(d, a, dm), c, dq);
-            const typename B::Inv iv = B::inv(b2, worst);
+            const typename B::Inv iv = B::inv(b2);
+            if (!need_ac) grow = max(grow, B::bad_pivot(b2));
             if (need_ac) {
                 const V a2 = B::neg(S::mul(a, am));
                 const V c2 = B::neg(S::mul(c, cp));
                 a = B::div(a2, iv); c = B::div(c2, iv);
+                grow = max(grow, max(growth_key(a), growth_key(c)));
             }
             d = B::div(d2, iv);
         };
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
             }
         }
         mycol[MI] = st;
-        int status = worst >= KRB_BAD_PIVOT_KEY ? KRB_LANE_ZERO_PIVOT : 0;
+        int status = grow >= KRB_NONFINITE_KEY ? KRB_LANE_ZERO_PIVOT : grow >= KRB_GROWTH_KEY ? KRB_LANE_INACCURATE : 0;
         if (!S::finite(st)) status |= KRB_LANE_NONFINITE;
         if (status && p.status) atomicOr(p.status + lane, status);
         __syncthreads();

@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "../../include/krets_b200.h"
+#include "scalar.cuh"
 
 namespace krb {
 
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(TPB, (TPB == 32 ? 14 : TPB == 64 ? 7 : 3)) krb
     T *__restrict__ UY = reinterpret_cast<T *>(p.UY) + lane;
     T *__restrict__ X = reinterpret_cast<T *>(p.X) + lane;
     int status = 0;
+    uint32_t grow = 0;                                // running maximum of growth_key(u^)
 
     double w = 0.0;                                   // (2.0 * PI) * f, rounded once as the reference does
     if (CPLX && p.input_freq >= 0) w = __dmul_rn(2.0 * 3.14159265358979323846264338327950288, IN[(size_t)p.input_freq * L]);
@@ -147,10 +149,11 @@ __global__ void __launch_bounds__(TPB, (TPB == 32 ? 14 : TPB == 64 ? 7 : 3)) krb
         const T s1 = S::fnma(e2, e0, pu2);            // sup1'   = sup1 - sub * u^_{k-1,k+1}
         const T yk = S::fnma(e4, e0, py);             // y_k     = rhs  - sub * y^_{k-1}
         if (S::scale3(wk, s1, e3, yk, pu1, pu2, py)) status |= KRB_LANE_ZERO_PIVOT;
+        grow = max(grow, growth_key(pu1));
         __stcs(up, pu1);
         __stcs(up + L, py);
         up += up_step;
-        if (has_u2) { __stcs(&UY[(size_t)(2 * n + r2) * L], pu2); ++r2; }
+        if (has_u2) { __stcs(&UY[(size_t)(2 * n + r2) * L], pu2); ++r2; grow = max(grow, growth_key(pu2)); }
     };
     int k = 0;
     const int n_runs = (p.debug & 4) ? 0 : p.n_runs;
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(TPB, (TPB == 32 ? 14 : TPB == 64 ? 7 : 3)) krb
     }
     if (DIRECT && fill > 0) flush_tile();
     if (!S::finite(x1)) status |= KRB_LANE_NONFINITE;   // non-finite values propagate down the recurrence to x_0
+    if (grow >= KRB_GROWTH_KEY && grow < KRB_NONFINITE_KEY) status |= KRB_LANE_INACCURATE;
     if (p.status) p.status[lane] |= status;
 }
 

@@ -981,7 +981,7 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
             Ucell[k].clear();
             for (size_t t = 0; t < Up.size(); t++) {
                 const int u = W[Up[t]];
-                sec.op(KOP_MUL, u, u, inv);
+                sec.op(KOP_MULG, u, u, inv);        // u^ = u / pivot, growth-tracked (KRB_LANE_INACCURATE)
                 Ucell[k].push_back(u);
                 if (persist) { B.cells[u].persist = true; sec.vops.push_back({VOP_PERSIST, 0, -1, u, -1, 0}); }
             }

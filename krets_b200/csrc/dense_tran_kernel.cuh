@@ -21,6 +21,8 @@
 // Coefficients live in per-thread shared-memory columns C[idx][tid] (conflict-free, static offsets after unrolling).
 #pragma once
 #include <cuda_runtime.h>
+
+#include "scalar.cuh"
 #include <stdint.h>
 
 #include "plan.hpp"
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
     }
     // ---- LU with the static pivots (unit lower, reciprocal pivots on the diagonal) ----
     bool bad = false, nonfinite = false;
+    uint32_t grow = 0;   // pivot growth: largest multiplier |l| = |a_ik / pivot| (scalar.cuh: growth_key, KRB_LANE_INACCURATE)
 #pragma unroll
     for (int k = 0; k < N; k++) {
         const double d = C[(size_t)(O_A + k * N + k) * TPB];
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
 #pragma unroll
         for (int i = k + 1; i < N; i++) {
             const double l = C[(size_t)(O_A + i * N + k) * TPB] * r;
+            grow = max(grow, growth_key(l));
             C[(size_t)(O_A + i * N + k) * TPB] = l;
 #pragma unroll
             for (int j = k + 1; j < N; j++)
@@ -323,7 +327,8 @@ __global__ void __launch_bounds__(TPB) krb_dense_tran(const DenseTranParams p) {
         }
     }
 #undef KRB_DC
-    if (bad || nonfinite) p.status[lane] |= (bad ? KRB_LANE_ZERO_PIVOT : 0) | (nonfinite ? KRB_LANE_NONFINITE : 0);
+    const bool inacc = grow >= KRB_GROWTH_KEY && grow < KRB_NONFINITE_KEY;
+    if (bad || nonfinite || inacc) p.status[lane] |= (bad ? KRB_LANE_ZERO_PIVOT : 0) | (nonfinite ? KRB_LANE_NONFINITE : 0) | (inacc ? KRB_LANE_INACCURATE : 0);
 }
 
 }  // namespace krb

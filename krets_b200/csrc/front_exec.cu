@@ -43,6 +43,7 @@ struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int s
 
 struct FrontDevice {
     bool uploaded = false;
+    int device = -1;          // device of the tables and buffers (a plan stays on the device of its first solve)
     FrontDesc *fronts = nullptr;
     int *list = nullptr, *idx_unknown = nullptr, *rel = nullptr, *child = nullptr, *asm_ent = nullptr, *asm_pos = nullptr, *col_order = nullptr;
     FrontElem *elems = nullptr;
@@ -51,10 +52,11 @@ struct FrontDevice {
     FrontChild *childrec = nullptr;
     int *res_ptr = nullptr, *res_ent = nullptr, *res_col = nullptr;
     int refine_steps = 0;
+    bool verify = false;      // krb_plan_opts.refine_steps > 0: backward-error check after the refinement sets / clears KRB_LANE_INACCURATE
     std::vector<std::vector<FrontLaunch>> factor_launches, solve_launches;   // per level
     long long fw_size = 0;
     int smem_cap = 0;
-    FBuf IN, EV, A, LU, LU0, CB, FW, CBV, BP, ST, XS, status, Bstep, IPIV, DX;
+    FBuf IN, EV, A, LU, LU0, CB, FW, CBV, BP, ST, XS, status, Bstep, IPIV, DX, ERR;
     std::vector<double> bstep_host;
     int bstep_rows = -1;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -80,7 +82,7 @@ void front_device_free(FrontDevice *d) {
     void *ptrs[] = {d->fronts, d->list, d->idx_unknown, d->rel, d->child, d->asm_ent, d->asm_pos, d->col_order, d->elems,
                     d->mat_terms, d->rhs_terms, d->mat_ptr, d->rhs_ptr, d->state_elems, d->res_ptr, d->res_ent, d->res_col, d->childrec};
     for (void *p : ptrs) if (p) cudaFree(p);
-    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV, &d->DX, &d->LU0};
+    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV, &d->DX, &d->LU0, &d->ERR};
     for (FBuf *b : bufs) b->release();
     for (auto &e : d->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete d;
@@ -225,6 +227,7 @@ static int upload_front(Plan &plan) {
     // stamped matrix restore full accuracy there (each costs one residual + one pair of triangular solves).  Transient and DC
     // plans are solved at the point they were planned for.
     D.refine_steps = plan.mode == KRB_MODE_AC ? 2 : 0;
+    if (plan.opts.refine_steps > 0) { D.refine_steps = plan.opts.refine_steps; D.verify = true; }   // the host mirror's pivoting fallback
     if (const char *e = getenv("KRB_FRONT_REFINE")) D.refine_steps = std::max(0, atoi(e));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
@@ -322,6 +325,16 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if (PS && (rc = upload_front(*PS))) return rc;
     if (PS && PS->n_inputs != P0.n_inputs) { set_error("plan_dc and plan_tran must be analysed with the same varied elements"); return KRB_ERR_INVALID_ARGUMENT; }
     FrontDevice &D = *P0.fdev;
+    {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (D.device < 0) D.device = dev;
+        if (PS && PS->fdev->device < 0) PS->fdev->device = dev;
+        if (D.device != dev || (PS && PS->fdev->device != dev)) {
+            set_error("this plan was first used on another CUDA device; analyse one plan per device");
+            return KRB_ERR_INVALID_ARGUMENT;
+        }
+    }
     cudaStream_t st = (cudaStream_t)a.stream;
     const bool cplx = P0.is_complex;
     const size_t ts = cplx ? 16 : 8;
@@ -361,6 +374,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const size_t cb_e = (size_t)std::max<long long>(P0.front.cb_size, PS ? PS->front.cb_size : 0);
     const size_t fw_e = (size_t)std::max<long long>(P0.fdev->fw_size, PS ? PS->fdev->fw_size : 0);
     const bool refine = P0.fdev->refine_steps > 0 || (PS && PS->fdev->refine_steps > 0);
+    const bool verify = P0.fdev->verify || (PS && PS->fdev->verify);
     const size_t persist = (lu_e + a_e + cbv_e + (size_t)n * (refine ? 2 : 1)) * ts + (size_t)n_elems * 8 + (size_t)P0.n_inputs * 8 + (size_t)n_state * 8 +
                            (size_t)n * 4 + (out_dev ? 0 : (size_t)rows * n * ts) + 64;
     const size_t work = (cb_e + fw_e + lu0_e) * ts + 64;
@@ -397,6 +411,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if ((rc = D.status.ensure((size_t)chunk * 4))) return rc;
     if ((rc = D.IPIV.ensure((size_t)n * chunk * 4))) return rc;
     if (refine && (rc = D.DX.ensure((size_t)n * chunk * ts))) return rc;
+    if (verify && (rc = D.ERR.ensure((size_t)chunk * 8))) return rc;
     if (!out_dev && (rc = D.XS.ensure((size_t)rows * n * chunk * ts))) return rc;
 
     D.events_used = 0;
@@ -413,6 +428,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             if (P0.input_freq >= 0) CUDA_TRY(cudaMemcpyAsync(IN + (size_t)P0.input_freq * lanes, a.lane_param + lane0, (size_t)lanes * 8, kind, st));
             bool run = nv > 0;
             for (int q = 1; q < nv && run; q++) run = P0.input_of_varied[q] == P0.input_of_varied[0] + q;
+            for (int q = 0; q < nv && run; q++) run = P0.input_of_varied[q] != P0.input_sweep;   // the swept source's plane is the sweep value (as runtime.cu)
             if (run)
                 CUDA_TRY(cudaMemcpy2DAsync(IN + (size_t)P0.input_of_varied[0] * lanes, (size_t)lanes * 8, a.varied_values + lane0, (size_t)a.lanes * 8,
                                            (size_t)lanes * 8, (size_t)nv, kind, st));
@@ -463,6 +479,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             add_launches(1);
         }
         auto stamp_and_factor = [&](const Plan &pl, void *lu_base, bool lu_windowed, long long s0, long long sl) -> int {
+            NvtxRange nvtx("krb front: stamp + multifrontal factor (one lane window)");
             FrontStampParams s = stamp_params(pl, s0);
             s.terms = pl.fdev->mat_terms; s.term_ptr = pl.fdev->mat_ptr; s.count = pl.pattern.nnz;
             s.OUT = (char *)D.A.p + (size_t)s0 * pl.pattern.nnz * ts;
@@ -473,6 +490,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             return front_factor(pl, make_params(pl, bufs_for(pl, lu_base, lu_windowed, s0), X + (size_t)s0 * xls * ts, xls, 0), sl, st);
         };
         auto rhs_and_solve = [&](const Plan &pl, void *lu_base, bool lu_windowed, long long s0, long long sl, int row) -> int {
+            NvtxRange nvtx("krb front: rhs + level-scheduled solves (+ refinement)");
             char *Xw = X + (size_t)s0 * xls * ts;
             const Bufs bufs = bufs_for(pl, lu_base, lu_windowed, s0);
             FrontStampParams s = stamp_params(pl, s0);
@@ -496,6 +514,21 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
                 rc2 = front_solve(pl, make_params(pl, bufs, r.DX, n, 0), sl, st);
                 if (pl.is_complex) krb_front_axpy<true><<<grid, 256, 0, st>>>(r);
                 else krb_front_axpy<false><<<grid, 256, 0, st>>>(r);
+                add_launches(3);
+            }
+            if (pl.fdev->verify && !rc2) {
+                // a-posteriori check of the delivered row: componentwise backward error <= 2^-40, else KRB_LANE_INACCURATE
+                unsigned long long *err = (unsigned long long *)D.ERR.p + s0;
+                CUDA_TRY(cudaMemsetAsync(err, 0, (size_t)sl * 8, st));
+                if (pl.is_complex) krb_front_rhs<true><<<grid, 256, 0, st>>>(s);
+                else krb_front_rhs<false><<<grid, 256, 0, st>>>(s);
+                FrontRefineParams r{};
+                r.res_ptr = pl.fdev->res_ptr; r.res_ent = pl.fdev->res_ent; r.res_col = pl.fdev->res_col;
+                r.A = bufs.A; r.a_stride = pl.pattern.nnz; r.BP = bufs.BP; r.X = Xw; r.x_lane_stride = xls; r.x_row_off = (long long)row * n;
+                r.DX = nullptr; r.n = n; r.err = err; r.status = bufs.status;
+                if (pl.is_complex) krb_front_residual<true><<<grid, 256, 0, st>>>(r);
+                else krb_front_residual<false><<<grid, 256, 0, st>>>(r);
+                krb_front_verify<<<(unsigned)((sl + 255) / 256), 256, 0, st>>>(err, bufs.status, sl, 9.094947017729282e-13);
                 add_launches(3);
             }
             return rc2;
@@ -562,6 +595,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             for (auto &mk : marks) cudaEventDestroy(mk.second);
         }
         // ---- delivery ----
+        NvtxRange nvtx_deliver("krb front: deliver");
         if (!out_dev) {
             CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * xls * ts, D.XS.p, (size_t)lanes * xls * ts, cudaMemcpyDeviceToHost, st));
             if (a.lane_status) CUDA_TRY(cudaMemcpyAsync(a.lane_status + lane0, D.status.p, (size_t)lanes * 4, cudaMemcpyDeviceToHost, st));

@@ -195,8 +195,16 @@ __global__ void krb_front_trap_state(const FrontTrapParams p) {
 // unless another fully-summed row is more than 8x larger (or the static pivot is zero / non-finite).  Per lane, like the
 // reference's faer LU picks pivots per factorisation; rows outside the front are never touched, so the symbolic plan holds.
 template <bool CPLX> struct FrontAbs;
-template <> struct FrontAbs<false> { static __device__ __forceinline__ double mag(double v) { return fabs(v); } static constexpr double THRESH = 8.0; };
-template <> struct FrontAbs<true> { static __device__ __forceinline__ double mag(double2 v) { return fma(v.x, v.x, v.y * v.y); } static constexpr double THRESH = 64.0; };
+template <> struct FrontAbs<false> {
+    static __device__ __forceinline__ double mag(double v) { return fabs(v); }
+    static __device__ __forceinline__ double abs1(double v) { return fabs(v); }
+    static constexpr double THRESH = 8.0;
+};
+template <> struct FrontAbs<true> {
+    static __device__ __forceinline__ double mag(double2 v) { return fma(v.x, v.x, v.y * v.y); }
+    static __device__ __forceinline__ double abs1(double2 v) { return fabs(v.x) + fabs(v.y); }
+    static constexpr double THRESH = 64.0;
+};
 
 // warp 0 scans col[k+1 .. p) (unit stride) and publishes the chosen row in *s_ip
 template <bool CPLX, typename T>
@@ -304,6 +312,7 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
     T *F = in_smem ? sm : reinterpret_cast<T *>(P.FW) + lane * P.fw_stride + d.fw_off;
     const int ldf = in_smem ? (m | 1) : m;          // F(i, j) = F[i + ldf * j]
     bool bad = false;
+    uint32_t grow = 0;   // largest multiplier |l_ik| = |a_ik / pivot| seen by this thread (scalar.cuh: growth_key)
     const bool use_dmma = (TX == 32 && TY == 16 && P.use_dmma);
     __shared__ int s_ip;
     __shared__ int s_pv[32];
@@ -373,7 +382,7 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
             bool b1;
             const T rp = S::rcp(Lp[k + ldl * k], b1);
             bad |= b1;
-            for (int i = k + 1 + tid; i < mk; i += NT) Lp[i + ldl * k] = S::mul(Lp[i + ldl * k], rp);
+            for (int i = k + 1 + tid; i < mk; i += NT) { const T l = S::mul(Lp[i + ldl * k], rp); Lp[i + ldl * k] = l; grow = max(grow, growth_key(l)); }
             __syncthreads();
             for (int j = k + 1 + ty; j < nb; j += TY) {
                 const T u = Lp[k + ldl * j];
@@ -460,6 +469,8 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
     for (int j = ty; j < q; j += TY)
         for (int i = tx; i < q; i += TX) CBf[i + (size_t)q * j] = F[(p + i) + (size_t)ldf * (p + j)];
     if (bad && tid == 0 && P.status) atomicOr(P.status + lane, KRB_LANE_ZERO_PIVOT);
+    // pivoting is restricted to the front's fully-summed rows: a multiplier of 2^24 or more means no acceptable pivot was among them
+    if (grow >= KRB_GROWTH_KEY && grow < KRB_NONFINITE_KEY && P.status) atomicOr(P.status + lane, KRB_LANE_INACCURATE);
 }
 
 // ---- iterative refinement: r = b - A x on the stamped values, in pivot order; x += correction ------------------------
@@ -472,6 +483,8 @@ struct FrontRefineParams {
     long long x_lane_stride, x_row_off;
     void *DX;                                  // correction, DX[lane * n + unknown]
     int n;
+    unsigned long long *err;                   // verify: per-lane max componentwise backward error (bits of a non-negative double), or nullptr
+    int *status;
 };
 template <bool CPLX>
 __global__ void krb_front_residual(const FrontRefineParams p) {
@@ -484,8 +497,29 @@ __global__ void krb_front_residual(const FrontRefineParams p) {
     const T *X = reinterpret_cast<const T *>(p.X) + lane * p.x_lane_stride + p.x_row_off;
     T *bp = reinterpret_cast<T *>(p.BP) + lane * p.n + k;
     T acc = *bp;
-    for (int t = p.res_ptr[k]; t < p.res_ptr[k + 1]; t++) acc = S::fnma(acc, A[p.res_ent[t]], X[p.res_col[t]]);
-    *bp = acc;
+    if (p.err == nullptr) {
+        for (int t = p.res_ptr[k]; t < p.res_ptr[k + 1]; t++) acc = S::fnma(acc, A[p.res_ent[t]], X[p.res_col[t]]);
+        *bp = acc;
+        return;
+    }
+    // verification pass: componentwise backward error of row k (Oettli-Prager),  |b - A x|_k / (|A| |x| + |b|)_k
+    double den = FrontAbs<CPLX>::abs1(acc);
+    for (int t = p.res_ptr[k]; t < p.res_ptr[k + 1]; t++) {
+        const T a = A[p.res_ent[t]], x = X[p.res_col[t]];
+        acc = S::fnma(acc, a, x);
+        den = fma(FrontAbs<CPLX>::abs1(a), FrontAbs<CPLX>::abs1(x), den);
+    }
+    const double r = FrontAbs<CPLX>::abs1(acc);
+    const double w = den > 0.0 ? r / den : (r > 0.0 ? 1.0 : 0.0);
+    atomicMax(p.err + lane, (unsigned long long)__double_as_longlong(w == w ? w : 1.0));
+}
+// sets / clears KRB_LANE_INACCURATE from the verified backward error: the a-posteriori answer replaces the a-priori growth flag
+__global__ void krb_front_verify(const unsigned long long *err, int *status, long long lanes, double tol) {
+    const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= lanes) return;
+    const double w = __longlong_as_double((long long)err[lane]);
+    if (w <= tol) status[lane] &= ~KRB_LANE_INACCURATE;
+    else status[lane] |= KRB_LANE_INACCURATE;
 }
 template <bool CPLX>
 __global__ void krb_front_axpy(const FrontRefineParams p) {

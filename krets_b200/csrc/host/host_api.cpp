@@ -1,6 +1,8 @@
 // Host mirror of the krets public API over the C ABI (include/krets_b200_host.h).
 #include <cmath>
 #include <cstring>
+#include <exception>
+#include <new>
 #include <fstream>
 #include <map>
 #include <memory>
@@ -22,14 +24,24 @@ struct PlanHolder {
     ~PlanHolder() { krb_plan_destroy(p); }
 };
 
+struct PlanKey {                        // one cached plan per (mode, executor request, sweep element, step, integrator)
+    int mode, exec, sweep_element, integrator;
+    double time_step;
+    bool operator<(const PlanKey &o) const {
+        if (mode != o.mode) return mode < o.mode;
+        if (exec != o.exec) return exec < o.exec;
+        if (sweep_element != o.sweep_element) return sweep_element < o.sweep_element;
+        if (integrator != o.integrator) return integrator < o.integrator;
+        return time_step < o.time_step;
+    }
+};
+
 struct krh_solver {                     // Solver { circuit, config }  solver.rs:17-20
     krh::ParsedCircuit pc;
     krb_config cfg;
     krb_circuit *kc = nullptr;
-    std::map<int, std::unique_ptr<PlanHolder>> dc_plans;      // keyed by sweep element (-1: none)
-    std::unique_ptr<PlanHolder> ac_plan;
-    std::map<std::pair<double, int>, std::unique_ptr<PlanHolder>> tran_plans; // keyed by (time step, integrator)
-    ~krh_solver() { dc_plans.clear(); ac_plan.reset(); tran_plans.clear(); krb_circuit_destroy(kc); }
+    std::map<PlanKey, std::unique_ptr<PlanHolder>> plans;
+    ~krh_solver() { plans.clear(); krb_circuit_destroy(kc); }
 };
 
 struct krh_result {
@@ -42,28 +54,64 @@ struct krh_result {
 static int fail(int code, const std::string &msg) { g_herr = msg; return code; }
 static int fail_krb(int code) { g_herr = krb_last_error_string(); return code; }
 
-static krb_plan *get_dc_plan(krh_solver *s, int sweep_element, int &rc) {
-    auto it = s->dc_plans.find(sweep_element);
-    if (it != s->dc_plans.end()) { rc = KRB_OK; return it->second->p; }
+// cached krb_analyze; `nominal_frequency` is only used when the plan is created (AC plans are keyed without it: one per solver)
+static krb_plan *get_plan(krh_solver *s, int mode, int exec, int sweep_element, double time_step, int integrator, double nominal_frequency, int &rc,
+                          int refine_steps = 0) {
+    const PlanKey key{mode, exec + 16 * refine_steps, sweep_element, integrator, time_step};
+    auto it = s->plans.find(key);
+    if (it != s->plans.end()) { rc = KRB_OK; return it->second->p; }
     krb_plan_opts o;
     krb_default_plan_opts(&o);
+    o.exec = exec;
     o.sweep_element = sweep_element;
+    o.time_step = time_step;
+    o.integrator = integrator;
+    o.nominal_frequency = nominal_frequency;
+    o.refine_steps = refine_steps;
     auto h = std::make_unique<PlanHolder>();
-    rc = krb_analyze(s->kc, KRB_MODE_DC, &o, &h->p);
+    rc = krb_analyze(s->kc, mode, &o, &h->p);
     if (rc) return nullptr;
     krb_plan *p = h->p;
-    s->dc_plans[sweep_element] = std::move(h);
+    s->plans[key] = std::move(h);
     return p;
 }
+static krb_plan *get_dc_plan(krh_solver *s, int sweep_element, int &rc, int exec = KRB_EXEC_FUSED, int refine_steps = 0) {
+    return get_plan(s, KRB_MODE_DC, exec, sweep_element, 0.0, 0, 0.0, rc, refine_steps);
+}
+// pivoting fallback: front executor (threshold pivoting inside the fronts, per lane) + 2 refinement steps + backward-error check
+static const int KRH_FALLBACK_REFINE = 2;
+static int plan_executor(const krb_plan *p) {
+    krb_plan_info pi;
+    return krb_plan_get_info(p, &pi) == KRB_OK ? pi.executor : -1;
+}
 
-// lane statuses -> the Err the reference would have returned at the first failing point
+// lane statuses -> the Err the reference would have returned at the first failing point.  The reference pivots per factorisation
+// (faer, op.rs:50): a lane that still carries KRB_LANE_INACCURATE after the pivoting fallback, or that delivered inf/nan, is
+// reported as a failed decomposition rather than returned as a success with wrong digits.
 static int status_to_error(const std::vector<int32_t> &st) {
     for (int32_t v : st) {
         if (v & KRB_LANE_ZERO_PIVOT) return fail(KRB_ERR_DECOMPOSITION_FAILED, "Decomposition failed");
         if (v & KRB_LANE_NOT_CONVERGED) return fail(KRB_ERR_MAX_ITERATIONS, "Maximum iterations exceeded");
+        if (v & KRB_LANE_NONFINITE) return fail(KRB_ERR_DECOMPOSITION_FAILED, "Decomposition failed (non-finite solution)");
+        if (v & KRB_LANE_INACCURATE) return fail(KRB_ERR_DECOMPOSITION_FAILED, "Decomposition failed (static pivot growth >= 2^24 and no pivoting fallback for this circuit)");
     }
     return KRB_OK;
 }
+static std::vector<int64_t> inaccurate_lanes(const std::vector<int32_t> &st) {
+    std::vector<int64_t> v;
+    for (size_t i = 0; i < st.size(); i++) if ((st[i] & KRB_LANE_INACCURATE) && !(st[i] & ~(KRB_LANE_INACCURATE))) v.push_back((int64_t)i);
+    return v;
+}
+static bool circuit_is_linear(const krh_solver *s) {
+    for (const krb_element &e : s->pc.pod) if (e.kind == KRB_D || e.kind == KRB_NMOS) return false;
+    return true;
+}
+// entry points must not let a C++ exception cross the C boundary (std::bad_alloc on absurd step counts)
+#define KRH_GUARD_BEGIN try {
+#define KRH_GUARD_END                                                                                    \
+    } catch (const std::bad_alloc &) { return fail(KRB_ERR_OUT_OF_MEMORY, "out of host memory"); }       \
+    catch (const std::exception &e) { return fail(KRB_ERR_INTERNAL, e.what()); }
+static const int64_t KRH_MAX_ROWS = 0x3fffffff;   // krb_solve_transient's own bound on n_steps
 
 extern "C" {
 
@@ -147,18 +195,28 @@ static int solve_op_vec(krh_solver *s, std::vector<double> &x) {
     std::vector<int32_t> st(1, 0);
     rc = krb_solve_op(p, &s->cfg, 1, nullptr, x.data(), nullptr, st.data(), nullptr);
     if (rc) return fail_krb(rc);
+    if (!inaccurate_lanes(st).empty() && circuit_is_linear(s)) {
+        // pivoting fallback: the front executor pivots inside its fronts per lane (front_kernels.cuh)
+        krb_plan *pf = get_dc_plan(s, -1, rc, KRB_EXEC_STAGED, KRH_FALLBACK_REFINE);
+        if (!pf) return fail_krb(rc);
+        st[0] = 0;
+        rc = krb_solve_op(pf, &s->cfg, 1, nullptr, x.data(), nullptr, st.data(), nullptr);
+        if (rc) return fail_krb(rc);
+    }
     x.resize(n);
     return status_to_error(st);
 }
 
 int32_t krh_solver_solve_op(krh_solver *s, krh_result **out) {
     if (!s || !out) return fail(KRB_ERR_INVALID_ARGUMENT, "null argument");
+    KRH_GUARD_BEGIN
     auto r = std::make_unique<krh_result>();
     int rc = solve_op_vec(s, r->data);
     if (rc) return rc;
     r->kind = KRH_RESULT_OP; r->rows = 1; r->n = (int)s->pc.unknown_names.size();
     *out = r.release();
     return KRB_OK;
+    KRH_GUARD_END
 }
 
 // dc.rs:14-124
@@ -170,7 +228,11 @@ int32_t krh_solver_solve_dc(krh_solver *s, const char *element, double start, do
     if (ei < 0) return fail(KRB_ERR_ELEMENT_NOT_FOUND, std::string("Element '") + element + "' not found in the netlist");
     const int kind = s->pc.pod[ei].kind;
     if (kind != KRB_V && kind != KRB_I) return fail(KRB_ERR_INVALID_ELEMENT_FORMAT, "DC sweep element must be a voltage or current source");   // dc.rs:30-38
+    if (!std::isfinite(start) || !std::isfinite(stop) || !std::isfinite(step_size) || step_size == 0.0)
+        return fail(KRB_ERR_INVALID_ARGUMENT, "DC sweep: start, stop and a non-zero step_size must be finite");
     const int num = krh_dc_num_steps(start, stop, step_size);                          // dc.rs:44-45
+    if ((int64_t)num > KRH_MAX_ROWS) return fail(KRB_ERR_INVALID_ARGUMENT, "DC sweep: too many sweep points");
+    KRH_GUARD_BEGIN
     int rc;
     krb_plan *p = get_dc_plan(s, ei, rc);
     if (!p) return fail_krb(rc);
@@ -184,14 +246,30 @@ int32_t krh_solver_solve_dc(krh_solver *s, const char *element, double start, do
     std::vector<int32_t> st(num, 0);
     rc = krb_solve_dc_sweep(p, &s->cfg, vals.data(), num, nullptr, r->data.data(), st.data(), nullptr);
     if (rc) return fail_krb(rc);
+    const std::vector<int64_t> redo = inaccurate_lanes(st);
+    if (!redo.empty() && circuit_is_linear(s)) {            // pivoting fallback for the flagged points only
+        krb_plan *pf = get_dc_plan(s, ei, rc, KRB_EXEC_STAGED, KRH_FALLBACK_REFINE);
+        if (!pf) return fail_krb(rc);
+        std::vector<double> v2(redo.size()), x2(redo.size() * (size_t)std::max(n, 1));
+        std::vector<int32_t> st2(redo.size(), 0);
+        for (size_t i = 0; i < redo.size(); i++) v2[i] = vals[redo[i]];
+        rc = krb_solve_dc_sweep(pf, &s->cfg, v2.data(), (int64_t)redo.size(), nullptr, x2.data(), st2.data(), nullptr);
+        if (rc) return fail_krb(rc);
+        for (size_t i = 0; i < redo.size(); i++) {
+            std::memcpy(&r->data[(size_t)redo[i] * n], &x2[i * (size_t)n], (size_t)n * 8);
+            st[redo[i]] = st2[i];
+        }
+    }
     if ((rc = status_to_error(st))) return rc;
     *out = r.release();
     return KRB_OK;
+    KRH_GUARD_END
 }
 
 // ac.rs:17-109
 int32_t krh_solver_solve_ac(krh_solver *s, int32_t sweep_kind, uint32_t points, double fstart, double fstop, krh_result **out) {
     if (!s || !out || sweep_kind < 0 || sweep_kind > 2) return fail(KRB_ERR_INVALID_ARGUMENT, "invalid argument");
+    KRH_GUARD_BEGIN
     std::vector<double> op;
     int rc = solve_op_vec(s, op);                                                     // ac.rs:25
     if (rc) return rc;
@@ -203,32 +281,37 @@ int32_t krh_solver_solve_ac(krh_solver *s, int32_t sweep_kind, uint32_t points, 
     r->axis = freqs;
     r->data.assign(freqs.size() * (size_t)std::max(n, 1) * 2, 0.0);
     if (!freqs.empty()) {
-        if (!s->ac_plan) {
-            krb_plan_opts o;
-            krb_default_plan_opts(&o);
-            o.nominal_frequency = std::sqrt(freqs.front() * freqs.back());
-            auto h = std::make_unique<PlanHolder>();
-            rc = krb_analyze(s->kc, KRB_MODE_AC, &o, &h->p);
-            if (rc) return fail_krb(rc);
-            krb_plan_info pi;
-            if (krb_plan_get_info(h->p, &pi) == KRB_OK && pi.executor == 2 && freqs.front() < o.nominal_frequency) {
-                // front executor: static pivots prefer the diagonal where it is within 1e3 of the column maximum at the nominal
-                // frequency; the inductor branch diagonal -j*w*L (stampable.rs:715) is smallest at the lowest frequency, so plan there
-                krb_plan_destroy(h->p);
-                h->p = nullptr;
-                o.nominal_frequency = freqs.front();
-                rc = krb_analyze(s->kc, KRB_MODE_AC, &o, &h->p);
-                if (rc) return fail_krb(rc);
-            }
-            s->ac_plan = std::move(h);
+        double fnom = std::sqrt(freqs.front() * freqs.back());
+        krb_plan *pa = get_plan(s, KRB_MODE_AC, KRB_EXEC_FUSED, -1, 0.0, 0, fnom, rc);
+        if (!pa) return fail_krb(rc);
+        if (plan_executor(pa) == 2 && freqs.front() < fnom) {
+            // front executor: static pivots prefer the diagonal where it is within 1e3 of the column maximum at the nominal
+            // frequency; the inductor branch diagonal -j*w*L (stampable.rs:715) is smallest at the lowest frequency, so plan there
+            pa = get_plan(s, KRB_MODE_AC, KRB_EXEC_STAGED, -1, 0.0, 0, freqs.front(), rc);
+            if (!pa) return fail_krb(rc);
         }
         std::vector<int32_t> st(freqs.size(), 0);
-        rc = krb_solve_ac(s->ac_plan->p, &s->cfg, freqs.data(), (int64_t)freqs.size(), nullptr, op.data(), 1, r->data.data(), st.data(), nullptr);
+        rc = krb_solve_ac(pa, &s->cfg, freqs.data(), (int64_t)freqs.size(), nullptr, op.data(), 1, r->data.data(), st.data(), nullptr);
         if (rc) return fail_krb(rc);
+        const std::vector<int64_t> redo = inaccurate_lanes(st);
+        if (!redo.empty() && circuit_is_linear(s)) {        // pivoting fallback for the flagged frequencies only
+            std::vector<double> f2(redo.size()), x2(redo.size() * (size_t)std::max(n, 1) * 2);
+            std::vector<int32_t> st2(redo.size(), 0);
+            for (size_t i = 0; i < redo.size(); i++) f2[i] = freqs[redo[i]];
+            krb_plan *pf = get_plan(s, KRB_MODE_AC, KRB_EXEC_STAGED, -1, 0.0, 0, f2.front(), rc, KRH_FALLBACK_REFINE);
+            if (!pf) return fail_krb(rc);
+            rc = krb_solve_ac(pf, &s->cfg, f2.data(), (int64_t)redo.size(), nullptr, op.data(), 1, x2.data(), st2.data(), nullptr);
+            if (rc) return fail_krb(rc);
+            for (size_t i = 0; i < redo.size(); i++) {
+                std::memcpy(&r->data[(size_t)redo[i] * n * 2], &x2[i * (size_t)n * 2], (size_t)n * 16);
+                st[redo[i]] = st2[i];
+            }
+        }
         if ((rc = status_to_error(st))) return rc;
     }
     *out = r.release();
     return KRB_OK;
+    KRH_GUARD_END
 }
 
 // transient.rs:14-114
@@ -237,21 +320,24 @@ int32_t krh_solver_solve_transient(krh_solver *s, double time_step, double stop_
 }
 int32_t krh_solver_solve_transient_with(krh_solver *s, double time_step, double stop_time, int32_t integrator, krh_result **out) {
     if (!s || !out) return fail(KRB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!std::isfinite(time_step) || !std::isfinite(stop_time) || !(time_step > 0.0))
+        return fail(KRB_ERR_INVALID_ARGUMENT, "transient: time_step must be positive and finite, stop_time finite");
     const int nsteps = krh_transient_num_steps(time_step, stop_time);                  // transient.rs:29
+    if ((int64_t)nsteps + 1 > KRH_MAX_ROWS) return fail(KRB_ERR_INVALID_ARGUMENT, "transient: too many time steps");
+    KRH_GUARD_BEGIN
     int rc;
+    // The DC and the step plan choose their executor independently (their patterns differ: capacitors are dropped and inductor
+    // branches have no diagonal in DC); the runtime needs both on the same side, so when exactly one of them selected the front
+    // executor the other one is analysed for it as well.
     krb_plan *pdc = get_dc_plan(s, -1, rc);
     if (!pdc) return fail_krb(rc);
-    const auto key = std::make_pair(time_step, (int)integrator);
-    auto it = s->tran_plans.find(key);
-    if (it == s->tran_plans.end()) {
-        krb_plan_opts o;
-        krb_default_plan_opts(&o);
-        o.time_step = time_step;
-        o.integrator = integrator;
-        auto h = std::make_unique<PlanHolder>();
-        rc = krb_analyze(s->kc, KRB_MODE_TRAN, &o, &h->p);
-        if (rc) return fail_krb(rc);
-        it = s->tran_plans.emplace(key, std::move(h)).first;
+    krb_plan *ptr = get_plan(s, KRB_MODE_TRAN, KRB_EXEC_FUSED, -1, time_step, integrator, 0.0, rc);
+    if (!ptr) return fail_krb(rc);
+    const bool fdc = plan_executor(pdc) == 2, ftr = plan_executor(ptr) == 2;
+    if (fdc != ftr) {
+        if (!fdc) pdc = get_dc_plan(s, -1, rc, KRB_EXEC_STAGED);
+        else ptr = get_plan(s, KRB_MODE_TRAN, KRB_EXEC_STAGED, -1, time_step, integrator, 0.0, rc);
+        if (!pdc || !ptr) return fail_krb(rc);
     }
     const int n = (int)s->pc.unknown_names.size();
     auto r = std::make_unique<krh_result>();
@@ -260,11 +346,21 @@ int32_t krh_solver_solve_transient_with(krh_solver *s, double time_step, double 
     r->axis.resize(nsteps + 1);
     for (int k = 0; k <= nsteps; k++) r->axis[k] = (double)k * time_step;             // transient.rs:24,44
     std::vector<int32_t> st(1, 0);
-    rc = krb_solve_transient(pdc, it->second->p, &s->cfg, nsteps, 1, nullptr, r->data.data(), st.data(), nullptr);
+    rc = krb_solve_transient(pdc, ptr, &s->cfg, nsteps, 1, nullptr, r->data.data(), st.data(), nullptr);
     if (rc) return fail_krb(rc);
+    if (!inaccurate_lanes(st).empty() && circuit_is_linear(s)) {       // pivoting fallback: both plans on the front executor
+        pdc = get_dc_plan(s, -1, rc, KRB_EXEC_STAGED, KRH_FALLBACK_REFINE);
+        if (!pdc) return fail_krb(rc);
+        ptr = get_plan(s, KRB_MODE_TRAN, KRB_EXEC_STAGED, -1, time_step, integrator, 0.0, rc, KRH_FALLBACK_REFINE);
+        if (!ptr) return fail_krb(rc);
+        st[0] = 0;
+        rc = krb_solve_transient(pdc, ptr, &s->cfg, nsteps, 1, nullptr, r->data.data(), st.data(), nullptr);
+        if (rc) return fail_krb(rc);
+    }
     if ((rc = status_to_error(st))) return rc;
     *out = r.release();
     return KRB_OK;
+    KRH_GUARD_END
 }
 
 int32_t krh_result_kind(const krh_result *r) { return r ? r->kind : -1; }

@@ -48,6 +48,14 @@ int device_count() {
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+// per-device caches of function attributes / occupancy (a process may drive several GPUs; the values are idempotent, so
+// concurrent first calls at worst repeat the query)
+constexpr int KRB_MAX_DEVICES = 64;
+static int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return dev >= 0 && dev < KRB_MAX_DEVICES ? dev : 0;
+}
 
 struct Buf {
     void *p = nullptr;
@@ -65,6 +73,7 @@ struct Buf {
 
 struct DeviceState {
     bool uploaded = false;
+    int device = -1;                     // the device the plan's buffers live on (set at first use; a plan stays on one device)
     uint2 *sec[3] = {nullptr, nullptr, nullptr};
     uint32_t *chain_rowinfo = nullptr;
     uint4 *chain_stream = nullptr;
@@ -195,7 +204,8 @@ static int upload_plan(Plan &plan, DeviceState &d) {
 template <bool CPLX, int TPB>
 static int launch_vm_t(const VmParams &p, long long Lpad, int n_slots, cudaStream_t st) {
     const size_t smem = (size_t)std::max(n_slots, 1) * TPB * (CPLX ? 16 : 8);
-    static size_t configured = 0;
+    static size_t configured_dev[KRB_MAX_DEVICES] = {};
+    size_t &configured = configured_dev[current_device_slot()];
     if (smem > configured) {
         CUDA_TRY(cudaFuncSetAttribute(krb_lane_vm<CPLX, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
         configured = std::max<size_t>(smem, 48 * 1024);
@@ -243,7 +253,8 @@ template <bool CPLX, int T, int M, bool SD>
 static int launch_chain_block_t(const ChainBlockParams &p, cudaStream_t st) {
     typedef typename ChainSc<CPLX>::T V;
     const size_t smem = ((size_t)T * (M + 1) + (size_t)6 * T + (SD ? (size_t)5 * KRB_BLOCK_DMAX : 0)) * sizeof(V);
-    static int resident = 0;
+    static int resident_dev[KRB_MAX_DEVICES] = {};
+    int &resident = resident_dev[current_device_slot()];
     if (!resident) {
         CUDA_TRY(cudaFuncSetAttribute(krb_chain_block_kernel<CPLX, T, M, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0, sms = 0, per_sm = 0;
@@ -299,7 +310,8 @@ static int launch_dense_t(const DenseTranParams &p, long long Lpad, cudaStream_t
     constexpr int TPB = 32;
     const size_t per_thread = (size_t)2 * N * N + N + (size_t)N * NSP + (size_t)N * NWP + (size_t)NSP * N;
     const size_t smem = per_thread * TPB * 8 + (size_t)2 * 32 * NWP * 8;      // coefficient columns + the staged source table
-    static size_t configured = 0;
+    static size_t configured_dev[KRB_MAX_DEVICES] = {};
+    size_t &configured = configured_dev[current_device_slot()];
     if (smem > configured) {
         CUDA_TRY(cudaFuncSetAttribute(krb_dense_tran<N, NSP, NWP, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
         configured = std::max<size_t>(smem, 48 * 1024);
@@ -347,6 +359,16 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if (!P0.dev) P0.dev = device_state_new();
     if (PS && !PS->dev) PS->dev = device_state_new();
     DeviceState &D0 = *P0.dev;
+    {   // a plan's device buffers are tied to the device of its first solve; one solve at a time per plan (include/krets_b200.h)
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (D0.device < 0) D0.device = dev;
+        if (PS && PS->dev->device < 0) PS->dev->device = dev;
+        if (D0.device != dev || (PS && PS->dev->device != dev)) {
+            set_error("this plan was first used on another CUDA device; analyse one plan per device");
+            return KRB_ERR_INVALID_ARGUMENT;
+        }
+    }
     cudaStream_t st = (cudaStream_t)a.stream;
     const bool cplx = P0.is_complex;
     const size_t ts = cplx ? 16 : 8;
@@ -447,6 +469,8 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         int *iters_d = a.iterations ? (int *)D0.iters.p + (size_t)b * chunk : nullptr;
         if (!out_dev && chunk_idx >= 2) CUDA_TRY(cudaStreamWaitEvent(st, D0.copy_done[b], 0));   // buffer set b is free again
         // ---- inputs ----
+        {
+        NvtxRange nvtx_inputs("krb lanes: inputs (sweep values / frequencies / Monte-Carlo planes)");
         for (int k = 0; k < P0.n_inputs; k++) {
             const double *src = nullptr;
             if (k == P0.input_sweep || k == P0.input_freq) src = a.lane_param;
@@ -477,8 +501,12 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             g_launches++;
         }
         CUDA_TRY(cudaMemsetAsync(status_d, 0, (size_t)Lpad * 4, st));
+        }
 
         // ---- compute ----
+        {
+        NvtxRange nvtx_compute(block ? "krb lanes: stamp + factor + solve (krb_chain_block_kernel)" : chain ? "krb lanes: stamp + factor + solve (krb_chain_kernel)"
+                                                                                                              : "krb lanes: stamp + factor + solve (krb_lane_vm / krb_dense_tran)");
         cudaEvent_t e0, e1;
         if ((rc = next_events(e0, e1))) return rc;
         CUDA_TRY(cudaEventRecord(e0, st));
@@ -546,8 +574,10 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             }
         }
         CUDA_TRY(cudaEventRecord(e1, st));
+        }
 
         // ---- delivery ----
+        NvtxRange nvtx_deliver("krb lanes: deliver (pack / D2H)");
         const size_t per_point = (size_t)rows * n;
         if (out_dev) {
             if (direct || dense_direct) {

@@ -1,10 +1,21 @@
 // Internal interface between the C ABI (api.cpp) and the CUDA runtime (runtime.cu).
 #pragma once
+#include <nvtx3/nvToolsExt.h>
+
 #include <string>
 
 #include "plan.hpp"
 
 namespace krb {
+
+// NVTX range per phase (analyze / inputs / stamp+factor+solve / deliver ...): header-only NVTX v3, a no-op unless a profiler
+// (nsys, ncu --nvtx) injects itself; ranges bracket the host-side enqueue of the phase's kernels and copies.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 struct RunArgs {
     krb_config cfg;

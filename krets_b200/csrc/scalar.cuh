@@ -1,10 +1,22 @@
 // Scalar arithmetic shared by the kernels: real f64 and complex f64 (num_complex-style products, as the reference's c64).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/krets_b200.h"
 
 namespace krb {
 
 struct c64 { double re, im; };
+
+// Pivot growth on the integer pipe: high word of |v| (complex: of the larger component).  A lane whose largest scaled factor entry
+// |u^| = |u / pivot| reaches 2^KRB_GROWTH_LIMIT_LOG2 gets KRB_LANE_INACCURATE (include/krets_b200.h): its static pivot cancelled that
+// many bits against its row, where faer's per-factorisation partial pivoting (op.rs:50) would have exchanged rows.
+__device__ __forceinline__ uint32_t growth_key(double v) { return (uint32_t)__double2hiint(v) & 0x7fffffffu; }
+__device__ __forceinline__ uint32_t growth_key(double2 v) { return max(growth_key(v.x), growth_key(v.y)); }
+constexpr uint32_t KRB_GROWTH_KEY = (uint32_t)(1023 + KRB_GROWTH_LIMIT_LOG2) << 20;
+constexpr uint32_t KRB_NONFINITE_KEY = 0x7ff00000u;
+
 
 template <bool CPLX> struct Sc;
 template <> struct Sc<false> {

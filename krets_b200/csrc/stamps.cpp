@@ -173,9 +173,13 @@ void nominal_magnitudes(const Circuit &c, const Stamps &s, const Pattern &p, int
             case S_VAL: vr = el.value; break;
             case S_VOH: vr = el.value / h; break;
             case S_JWV: vi = 2.0 * PI * fnom * el.value; break;
-            case S_DIODE_G: {   // the reference's empty-guess default: vd = 0.5 (diode.rs:26-36)
+            case S_DIODE_G: {
+                // the un-biased junction (vd = 0): g = Is / (n Vt) ~ 4e-11.  A diode conductance spans > 20 decades over the Newton
+                // iterates and the lanes (reverse bias: -> 0), so the STATIC pivot plan must not rest on one wherever a resistor,
+                // companion or source-coupling entry is available — the weighted matching then picks that entry, as faer's
+                // per-factorisation partial pivoting (op.rs:50) would on every iterate where the diode is off.
                 const double nvt = el.n * thermal_voltage();
-                vr = (el.is / nvt) * std::exp(0.5 / nvt);
+                vr = el.is / nvt;
                 break;
             }
             default: break;

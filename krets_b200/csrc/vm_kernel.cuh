@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
     const double *__restrict__ Bc = p.B;
     int status = 0;
     int it_used = 0;
+    uint32_t grow = 0;   // running maximum of growth_key(u^) over every factorisation of the lane (scalar.cuh)
 
     for (int row = p.row_begin; row < p.row_end; ++row) {
         T *Xcur = reinterpret_cast<T *>(p.X) + (size_t)row * (size_t)p.row_width * (size_t)L + lane;
@@ -176,6 +177,12 @@ __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
                             if (bad) status |= KRB_LANE_ZERO_PIVOT;
                             break;
                         }
+                        case KOP_MULG: {
+                            const T v = S::mul(IO::ld(aa), IO::ld(ab));
+                            IO::st(ad, v);
+                            grow = max(grow, growth_key(v));
+                            break;
+                        }
                         case KOP_INV: IO::st(ad, S::from_real(__ddiv_rn(1.0, S::re(IO::ld(aa))))); break;
                         case KOP_DIVR: IO::st(ad, S::from_real(__ddiv_rn(S::re(IO::ld(aa)), S::re(IO::ld(ab))))); break;
                         case KOP_MULJ: IO::st(ad, S::mulj(IO::ld(aa))); break;
@@ -218,6 +225,9 @@ __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
             }
         }
     }
+    // linear circuits only: a diode conductance spans tens of decades over the Newton iterates, so |u^| says nothing about a
+    // nonlinear lane; there the convergence check (solver.rs:76-104) on the next iterate is what guards the answer
+    if (!p.nonlinear && grow >= KRB_GROWTH_KEY && grow < KRB_NONFINITE_KEY) status |= KRB_LANE_INACCURATE;
     if (p.status) p.status[lane] |= status;
     if (p.iters) p.iters[lane] = it_used;
 }

@@ -38,7 +38,8 @@ enum KrbOp : uint32_t {
     KOP_LDK = 21,   // scr[d] = the f64 constant stored in the NEXT op slot (both words); that slot is skipped.  Never at chunk position 31.
     KOP_NOP = 22,   // padding
     KOP_WAIT = 23,  // wait for the asynchronous loads (LDI/LDG/LDX/LDBS are issued as cp.async straight into the scratch slot)
-    KOP_COUNT = 24
+    KOP_MULG = 24,  // scr[d] = scr[a] * scr[b], a scaled factor entry u^ = u * (1/pivot): also tracks the lane's pivot growth (KRB_LANE_INACCURATE)
+    KOP_COUNT = 25
 };
 
 static inline uint32_t krb_op_w0(uint32_t opc, uint32_t d, uint32_t a, uint32_t b) { return opc | (d << 8) | (a << 16) | (b << 24); }

@@ -1,0 +1,119 @@
+"""GPU tier: the per-lane accuracy flag KRB_LANE_INACCURATE (include/krets_b200.h) and the host mirror's pivoting fallback.
+
+The reference pivots per factorisation (faer sp_lu: op.rs:50, dc.rs:83, ac.rs:70); the kernels use one static pivot plan for
+every lane.  A lane whose scaled factor entries reach 2^24 (pivot cancelled >= 24 bits against its row) is flagged; the
+`Solver` mirror re-solves flagged points on the front executor with refinement and a backward-error check, so that what it
+returns still matches the oracle (partial pivoting) at 1e-9.
+"""
+import numpy as np
+import pytest
+
+import netgen
+from helpers import assert_close, rel_err
+
+import krets_b200 as kb
+from krets_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert kb.device_count() > 0, "GPU tier needs a CUDA device (the library has no CPU fallback)"
+
+
+def cancelling_ladder(n=40):
+    """Resistor ladder whose 10th pivot cancels in the natural elimination order although every stamped entry is healthy:
+    w_10 = g9 + g10 - g9^2 / w_9 with w_9 = (9/8) g  ->  g10 = -g/9 (1 - 9e-9): R10 = -9000.00008 leaves w_10 ~ 1e-12, |u^| ~ 1e8."""
+    lines = ["V1 1 0 1"]
+    for k in range(1, n):
+        lines.append(f"R{k} {k} {k + 1} {'-9000.00008' if k == 10 else '1000'}")
+    lines.append(f"R{n} {n} 0 1000")
+    return "\n".join(lines) + "\n"
+
+
+def test_growth_flag_per_lane_every_executor(oracle, monkeypatch):
+    """Monte-Carlo lanes of a healthy ladder; lane 1 carries the cancelling R10.  Every executor must flag lane 1 (or, where it
+    pivots per lane, deliver it accurately) and leave lane 0 untouched."""
+    text = netgen.resistor_ladder(40)
+    circuit = kb.parse_circuit_description(text)
+    e = [circuit.element_index("R10")]
+    vals = np.array([[1000.0, -9000.00008, 1000.0]])
+    refs = []
+    for l in range(3):
+        oc = oracle.Circuit(text)
+        oc.set_element_value(oc.element_index("R10"), vals[0, l])
+        refs.append(oc.solve_op())
+    cases = [("sequential chain kernel", {}, {}), ("block chain kernel", {"KRB_CHAIN_BLOCK": "1"}, {}),
+             ("lane VM", {}, {"force_lane_vm": True}), ("front executor", {}, {"executor": api.EXEC_STAGED})]
+    for name, env, kw in cases:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        plan = kb.Plan(circuit, api.MODE_DC, varied=e, **kw)
+        for k in env:
+            monkeypatch.delenv(k)
+        out, status = plan.solve_op(3, varied_values=vals)
+        assert status[0] == 0 and status[2] == 0, (name, status)
+        assert_close(out[0], refs[0], what=f"{name}: healthy lane 0")
+        assert_close(out[2], refs[2], what=f"{name}: healthy lane 2")
+        if name != "front executor":
+            assert status[1] == api.LANE_INACCURATE, (name, status)
+        else:   # pivots inside its fronts per lane: either it recovered the lane or it says so
+            assert (status[1] & api.LANE_INACCURATE) or rel_err(out[1], refs[1]) <= 1e-9, (name, status)
+
+
+def test_fallback_plan_refines_and_verifies(oracle):
+    """KRB_EXEC_STAGED with refine_steps = 2: refinement on the stamped matrix + backward-error check; the flag is the verified answer."""
+    text = netgen.resistor_ladder(40)
+    circuit = kb.parse_circuit_description(text)
+    e = [circuit.element_index("R10")]
+    vals = np.array([[1000.0, -9000.00008, 1000.0, -9000.0000008]])
+    plan = kb.Plan(circuit, api.MODE_DC, varied=e, executor=api.EXEC_STAGED, refine_steps=2)
+    out, status = plan.solve_op(4, varied_values=vals)
+    assert not status.any(), status
+    for l in range(4):
+        oc = oracle.Circuit(text)
+        oc.set_element_value(oc.element_index("R10"), vals[0, l])
+        assert_close(out[l], oc.solve_op(), what=f"refined front executor lane {l}")
+
+
+def test_solver_falls_back_to_pivoting(oracle):
+    """The nominal circuit itself cancels in the static order: the plain plan flags it, `Solver` still returns the oracle's answer
+    (OP, DC sweep, AC and transient all go through the same fallback)."""
+    text = cancelling_ladder()
+    circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    plan = kb.Plan(circuit, api.MODE_DC)
+    assert plan.info.executor == 1
+    _, status = plan.solve_op(1)
+    assert status[0] == api.LANE_INACCURATE
+    solver = kb.Solver(circuit)
+    assert_close(solver.solve(kb.Analysis.Op()).array[0], oc.solve_op(), what="Solver OP through the pivoting fallback")
+    res = solver.solve(kb.Analysis.Dc(kb.DcAnalysis("V1", 0.0, 2.0, 0.5)))
+    assert_close(res.array, oc.solve_dc("V1", 0.0, 2.0, 0.5), what="Solver DC sweep through the pivoting fallback")
+
+
+def test_nonfinite_rows_are_errors_in_the_solver_mirror():
+    """status_to_error: a lane that delivered inf/nan is a failed decomposition, not a success."""
+    circuit = kb.parse_circuit_description("V1 1 0 1\nR1 1 2 0\nR2 2 0 1k\n")   # g = 1/0
+    with pytest.raises(kb.KretsError) as ei:
+        kb.Solver(circuit).solve(kb.Analysis.Op())
+    assert ei.value.kind == "DecompositionFailed"
+
+
+def test_transient_executor_pair_is_made_consistent(oracle):
+    """26 x 26 RLC mesh: the DC plan stays on the lane VM while the step plan selects the front executor; the Solver
+    mirror re-analyses the other plan instead of failing with Unsupported."""
+    text = netgen.rlc_mesh(26, 26, transient=True)
+    circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    pdc = kb.Plan(circuit, api.MODE_DC)
+    ptr = kb.Plan(circuit, api.MODE_TRAN, time_step=1e-9)
+    assert (pdc.info.executor == 2) != (ptr.info.executor == 2), "premise: the two plans pick different executors at this size"
+    res = kb.Solver(circuit).solve(kb.Analysis.Transient(kb.TransientAnalysis(1e-9, 6e-9)))
+    assert res.array.shape == (7, circuit.n) and np.isfinite(res.array).all()
+    # row 0 is the operating point: residual on the oracle-stamped DC matrix
+    import scipy.sparse as sp
+    colptr, rowidx, v = oc.stamp_matrix("dc", 0.0)
+    A = sp.csc_matrix((v, rowidx, colptr), shape=(circuit.n, circuit.n))
+    b = np.zeros(circuit.n)
+    b[circuit.index_map["I(I1)"]] = 1e-3
+    assert np.max(np.abs(A @ res.array[0] - b)) < 1e-12

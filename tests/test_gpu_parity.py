@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import netgen
-from helpers import assert_close
+from helpers import assert_close, rel_err
 
 import krets_b200 as kb
 from krets_b200 import api
@@ -319,7 +319,12 @@ def test_config2_full_size_linearity(oracle):
 
 
 def test_config3_chunk_rc_ladder_5000(oracle):
-    """RC ladder 5000, one 8192-lane slice of the 1e6-point decade grid: sampled lanes vs the oracle + KCL residual on all."""
+    """RC ladder 5000 (BASELINE config 3), an 8192-lane slice spread over the whole 1e6-point decade grid: EVERY lane and every
+    unknown against the oracle (the oracle needs ~10-20 s on the box's host threads).
+    helpers.rel_err measures unknowns more than six orders below the lane's largest one against that floor: at high frequency the
+    ladder attenuates by hundreds of decades, so most of the 5001 unknowns of such a lane are compared absolutely (they underflow
+    towards zero in both solvers)."""
+    import os
     import torch
     text = netgen.rc_ladder(5000)
     circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
@@ -332,9 +337,13 @@ def test_config3_chunk_rc_ladder_5000(oracle):
     torch.cuda.synchronize()
     assert int(status.abs().max().item()) == 0
     host = out.cpu().numpy()
-    idx = [0, 1, 1000, 4095, 8191]
-    _, ref = oc.solve_ac(sel[idx])
-    assert_close(host[idx], ref, what="RC ladder 5000 sampled lanes")
+    _, ref = oc.solve_ac(sel, nthreads=os.cpu_count() or 1)
+    assert ref.shape == host.shape
+    worst = max(rel_err(host[l], ref[l]) for l in range(len(sel)))      # per lane: each lane has its own scale
+    assert worst <= 1e-9, f"RC ladder 5000, all {len(sel)} lanes: max relative error {worst:.3e}"
+    # the part of each lane that carries signal, compared purely relatively (no floor): unknowns within 1e-6 of the lane's maximum
+    big = np.abs(ref) >= 1e-6 * np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(host - ref)[big] / np.abs(ref)[big]) <= 1e-9
     # residual of the source row: V(1) = 1 for every lane (row I(V1): V(1) = ac amplitude)
     assert np.max(np.abs(host[:, circuit.index_map["V(1)"]] - 1.0)) < 1e-12
 

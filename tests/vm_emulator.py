@@ -10,8 +10,9 @@ import numpy as np
 
 from krets_b200 import _lib
 
-(END, LDB, LDBS, LDI, LDG, STG, LDX, XOUT, ZERO, MOV, NEG, ADD, SUB, MUL, FNMA, RCP, INV, DIVR, MULJ, DIOG, DIOI, LDK, NOP, WAIT) = range(24)
-ZERO_PIVOT, NOT_CONVERGED, NONFINITE = 1, 2, 4
+(END, LDB, LDBS, LDI, LDG, STG, LDX, XOUT, ZERO, MOV, NEG, ADD, SUB, MUL, FNMA, RCP, INV, DIVR, MULJ, DIOG, DIOI, LDK, NOP, WAIT, MULG) = range(25)
+ZERO_PIVOT, NOT_CONVERGED, NONFINITE, INACCURATE = 1, 2, 4, 8
+GROWTH_LIMIT = 2.0 ** 24   # KRB_GROWTH_LIMIT_LOG2
 
 
 def _plan_tables(plan, rows, h):
@@ -69,7 +70,7 @@ class Emulator:
                 pci += 1
                 opc, d, a, b = w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, (w0 >> 24) & 0xFF
                 self.stats["ops"] += 1
-                if opc in (ADD, SUB, MUL, FNMA, DIVR):
+                if opc in (ADD, SUB, MUL, MULG, FNMA, DIVR):
                     touched = {d, a, b}
                 elif opc in (MOV, NEG, RCP, INV, MULJ, DIOG, DIOI):
                     touched = {d, a}
@@ -132,6 +133,12 @@ class Emulator:
                     scr[d] = scr[a] - scr[b]
                 elif opc == MUL:
                     scr[d] = scr[a] * scr[b]
+                elif opc == MULG:                    # u^ = u / pivot: growth-tracked
+                    scr[d] = scr[a] * scr[b]
+                    v = scr[d]
+                    mag = np.maximum(np.abs(v.real), np.abs(v.imag)) if np.iscomplexobj(v) else np.abs(v)
+                    if not self.nonlinear:           # NR convergence, not pivot growth, guards nonlinear circuits (vm_kernel.cuh)
+                        self.status[np.isfinite(mag) & (mag >= GROWTH_LIMIT)] |= INACCURATE
                 elif opc == FNMA:
                     scr[d] = scr[d] - scr[a] * scr[b]
                 elif opc == RCP:
