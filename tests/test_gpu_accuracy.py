@@ -56,9 +56,10 @@ def test_growth_flag_per_lane_every_executor(oracle, monkeypatch):
         assert status[0] == 0 and status[2] == 0, (name, status)
         assert_close(out[0], refs[0], what=f"{name}: healthy lane 0")
         assert_close(out[2], refs[2], what=f"{name}: healthy lane 2")
-        if name != "front executor":
+        if name in ("sequential chain kernel", "lane VM"):      # the natural elimination order, where w_10 cancels
             assert status[1] == api.LANE_INACCURATE, (name, status)
-        else:   # pivots inside its fronts per lane: either it recovered the lane or it says so
+        else:   # other elimination orders (Wang partition inside the CTA; fronts with per-lane pivoting): the pivot may not
+            # cancel at all - either the lane is delivered accurately or it is flagged
             assert (status[1] & api.LANE_INACCURATE) or rel_err(out[1], refs[1]) <= 1e-9, (name, status)
 
 
