@@ -11,10 +11,13 @@
 //      two levels of cyclic reduction (odd rows absorb the even ones, rows kept de-interleaved by parity so that every
 //      access is unit-stride), parallel cyclic reduction on the remaining T/4 rows by a quarter of the warps (log2(T/4)
 //      steps in shared memory), eliminated rows by substitution
-//   3. interiors by back substitution  x_j = (y^_j - l^_j s_{t-1}) - u^_j x_{j+1} (- u2^_j x_{j+2}),  staged in the shared
-//      column and written point-major with full-width coalesced stores.
+//   3. interiors by back substitution  x_j = (y^_j - l^_j s_{t-1}) - u^_j x_{j+1} (- u2^_j x_{j+2}),  written to a second
+//      shared-memory buffer in pivot-row order — the lane's result vector, contiguous — and delivered by ONE bulk asynchronous
+//      copy (cp.async.bulk.global.shared::cta, the TMA engine) issued by thread 0: the CTA starts the next lane at once and the
+//      delivery costs no LDS / STG issue slots (ncu r2a: the per-thread delivery loop was 19 % of all warp samples and 23 % of
+//      the shared-memory wavefronts, 38 % of them bank conflicts of the padded column layout).
 //
-// u^ / y^ live in registers, l^ (then x) in a per-thread shared-memory column with an odd stride.  Register budget: 2 (M-1)
+// u^ / y^ live in registers, l^ in a per-thread shared-memory column with an odd stride (conflict-free), x in the result buffer.  Register budget: 2 (M-1)
 // values of u^ / y^ leave ~50 of the 128 registers (2 CTAs / SM) for everything else, so lane-invariant address arithmetic is
 // deliberately kept INSIDE the lane loop (opaque copies of t / the packed entry indices): hoisted, it was spilled and every
 // lane paid ~90 local-memory accesses per thread (ncu: 33.6 M -> 1.8 M local loads per 65 536-lane launch, -18 % run time).
@@ -39,13 +42,22 @@ struct ChainBlockParams {
     int n;
     int input_freq;
     int n_dict;                  // unique FIXED records
-    int n_gen;                   // GENERIC rows (shared-dictionary mode: n_dict + n_gen <= KRB_BLOCK_DMAX)
+    int n_gen;                   // GENERIC rows (shared-dictionary mode: n_dict + n_gen <= the kernel's dictionary capacity)
     int *status;
+    int bulk_store;              // deliver with cp.async.bulk (needs unknown_of_row == nullptr; complex: OUT 16-byte aligned)
+    const void *E;               // !SD: pre-stamped rows E[lane][M][T][4] = (sub, diag, sup, rhs) written by krb_block_stamp_rows
+    const void *U2;              // !SD: U2[lane][T] second super-diagonal of the (at most one) u2 row of each block
 };
 
 // row word .y: bit 1 HAS_U2, bits 2..15 #terms, bits 16..31 slot of a GENERIC row (shared-dictionary mode)
 enum : uint32_t { BR_HAS_U2 = 2u, BR_NT_SHIFT = 2, BR_NT_MASK = 0x3fffu, BR_SLOT_SHIFT = 16 };
-constexpr int KRB_BLOCK_DMAX = 256;   // entries of the shared-memory dictionary (unique FIXED records + GENERIC rows)
+constexpr int KRB_BLOCK_DMAX = 256;   // entries of the shared-memory dictionary (unique FIXED records + GENERIC rows), real plans
+constexpr int KRB_BLOCK_DMAX_CPLX = 64;   // complex plans: two 80 KB lane buffers leave room for 64 entries (227 KB per CTA)
+template <bool CPLX> struct BlockDmax { static constexpr int value = CPLX ? KRB_BLOCK_DMAX_CPLX : KRB_BLOCK_DMAX; };
+// shared-memory footprint in elements of V (runtime.cu sizes the launch with the same expression)
+template <bool CPLX, int T, int M, bool SD> constexpr size_t block_smem_elems() {
+    return (size_t)T * ((M & 1) ? M : M + 1) + ((size_t)T * M + 2) + (size_t)6 * T + 16 + (SD ? (size_t)5 * BlockDmax<CPLX>::value : 0);
+}
 
 // Pivot health on the integer pipe.  The lane keeps ONE running maximum, of growth_key(u^) = the high word of |u^| = |sup / pivot|
 // (complex: of the larger component):
@@ -127,6 +139,83 @@ __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, i
     }
 }
 
+// ---- pre-stamped rows for plans without a shared dictionary ---------------------------------------------------------------
+template <bool CPLX> struct BlockRec;
+template <> struct BlockRec<false> {
+    struct __align__(16) T { double v[4]; };          // (sub, diag, sup, rhs)
+    static __device__ __forceinline__ void load(const T *p, double &a, double &b, double &c, double &d) {
+        const double2 lo = __ldcs(reinterpret_cast<const double2 *>(p)), hi = __ldcs(reinterpret_cast<const double2 *>(p) + 1);
+        a = lo.x; b = lo.y; c = hi.x; d = hi.y;
+    }
+};
+template <> struct BlockRec<true> {
+    struct __align__(16) T { double2 v[4]; };
+    static __device__ __forceinline__ void load(const T *p, double2 &a, double2 &b, double2 &c, double2 &d) {
+        const double2 *q = reinterpret_cast<const double2 *>(p);
+        a = __ldcs(q); b = __ldcs(q + 1); c = __ldcs(q + 2); d = __ldcs(q + 3);
+    }
+};
+
+struct BlockStampParams {
+    const uint2 *rows;           // [M][T] row words (as ChainBlockParams::rows)
+    const uint4 *dict, *stream;
+    const double *IN;            // [n_inputs][L]
+    long long L, lanes;
+    int input_freq, slots;       // slots = T * M
+    int T;
+    void *E, *U2;
+};
+
+// (a) of the north star for Monte-Carlo chain plans: one thread stamps one pivot row of one lane — ordered term run, exact IEEE
+// divisions, same summation order as sum_triplets (solver.rs:59-70) — from the lane-interleaved inputs (a warp = 32 consecutive
+// lanes of one row: coalesced), and the tile is transposed through shared memory so that every lane receives 32 consecutive
+// records (1 / 2 KB) at once.  blockDim = (32, 8); grid = (slots / 32, ceil(lanes / 32)).
+template <bool CPLX>
+__global__ void __launch_bounds__(256) krb_block_stamp_rows(const BlockStampParams p) {
+    typedef ChainSc<CPLX> S;
+    typedef typename S::T V;
+    constexpr int FIX_UNITS = CPLX ? 4 : 2;
+    constexpr int RT = CPLX ? 16 : 32;               // rows per tile (shared memory: 4 * RT * 33 elements)
+    __shared__ V tile[RT * 4][33];
+    const int lx = threadIdx.x;
+    const long long lane0 = (long long)blockIdx.y * 32, lane = lane0 + lx;
+    const bool live = lane < p.lanes;
+    const double *__restrict__ IN = p.IN + (live ? lane : 0);
+    double w = 0.0;
+    if (CPLX && p.input_freq >= 0) w = __dmul_rn(2.0 * 3.14159265358979323846264338327950288, __ldg(IN + (size_t)p.input_freq * p.L));
+    const int slot0 = blockIdx.x * RT;
+    for (int r = threadIdx.y; r < RT; r += blockDim.y) {
+        const int slot = slot0 + r;                   // = j * T + t
+        const uint2 rw = __ldg(p.rows + slot);
+        V e0, e1, e2, e3 = S::zero(), e4;
+        if (rw.x & 1u) {
+            const uint4 *d = p.dict + (size_t)(rw.x >> 1) * FIX_UNITS;
+            const uint4 c0 = __ldg(d), c1 = __ldg(d + 1);
+            if (CPLX) {
+                const uint4 c2 = __ldg(d + 2), c3 = __ldg(d + 3);
+                e0 = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
+                e1 = S::make(u4hi(c0), __dmul_rn(w, u4hi(c2)));
+                e2 = S::make(u4lo(c1), __dmul_rn(w, u4lo(c3)));
+                e4 = S::make(u4hi(c1), 0.0);
+            } else {
+                e0 = S::make(u4lo(c0), 0.0); e1 = S::make(u4hi(c0), 0.0); e2 = S::make(u4lo(c1), 0.0); e4 = S::make(u4hi(c1), 0.0);
+            }
+        } else {
+            block_eval_terms<CPLX>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), IN, p.L, w, 0, e0, e1, e2, e3, e4);
+            if ((rw.y & BR_HAS_U2) && live) reinterpret_cast<V *>(p.U2)[(size_t)lane * p.T + slot % p.T] = e3;
+        }
+        tile[r * 4 + 0][lx] = e0; tile[r * 4 + 1][lx] = e1; tile[r * 4 + 2][lx] = e2; tile[r * 4 + 3][lx] = e4;
+    }
+    __syncthreads();
+    V *__restrict__ E = reinterpret_cast<V *>(p.E);
+    for (int ll = threadIdx.y; ll < 32; ll += blockDim.y) {
+        const long long ln = lane0 + ll;
+        if (ln >= p.lanes) break;
+        V *dst = E + ((size_t)ln * (size_t)p.slots + (size_t)slot0) * 4;
+        for (int q = lx; q < RT * 4; q += 32) __stcs(dst + q, tile[q][ll]);
+    }
+}
+
 // SD (shared dictionary): the plan's unique FIXED records and its GENERIC rows together fit KRB_BLOCK_DMAX entries (ladders,
 // RC lines, swept sources: a handful).  Every row then reads its stamped (sub, diag, sup, rhs) from a shared-memory entry:
 // FIXED entries are lane-invariant (real) or refreshed per lane with the lane's w (complex: (re, w*K) is formed once per
@@ -140,15 +229,18 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
     typedef BlockSc<CPLX> B;
     typedef typename S::T V;
     constexpr int MI = M - 1;               // interior rows per thread
-    constexpr int XS = M + 1;               // stride of a thread's shared-memory column (odd: conflict-free)
+    constexpr int XS = (M & 1) ? M : M + 1; // stride of a thread's l^ column (odd: conflict-free)
     constexpr int FIX_UNITS = CPLX ? 4 : 2;
     constexpr int NW = T / 32;
+    constexpr int DMAX = BlockDmax<CPLX>::value;
+    constexpr int RPAD = 8;                 // the odd-parity halves of the reduction buffers start 8 elements later: threads t, t+1 hit different banks
     extern __shared__ __align__(16) unsigned char krb_block_smem[];
-    V *xq = reinterpret_cast<V *>(krb_block_smem);   // [T][XS]: l^_j -> x_j
-    V *red = xq + T * XS;                              // [2][3][T]: separator rows (a, c, d) by parity, then the reduced system
-    V *fst = red + 3 * T;                              // [3][T]: (P, R, Q) of each block's first row; aliases the reduced system
-    V *sd = red + 6 * T;                               // SD: [KRB_BLOCK_DMAX][4] stamped (sub, diag, sup, rhs) per entry
-    V *pe3 = sd + 4 * KRB_BLOCK_DMAX;                  // SD: [KRB_BLOCK_DMAX] second super-diagonal of a GENERIC entry
+    V *xq = reinterpret_cast<V *>(krb_block_smem);   // [T][XS]: l^_j
+    V *xo = xq + T * XS;                               // [T * M + 2]: the lane's results in pivot-row order (+ one element of alignment shift)
+    V *red = xo + T * M + 2;                           // [2][3][T] + pads: separator rows (a, c, d) by parity, then the reduced system
+    V *fst = red + 3 * T + RPAD;                       // [3][T] + pad: (P, R, Q) of each block's first row; aliases the reduced system
+    V *sd = red + 6 * T + 2 * RPAD;                    // SD: [DMAX][4] stamped (sub, diag, sup, rhs) per entry
+    V *pe3 = sd + 4 * DMAX;                            // SD: [DMAX] second super-diagonal of a GENERIC entry
     const int t = threadIdx.x;
     V *mycol = xq + t * XS;
     const long long L = p.L;
@@ -166,16 +258,14 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
         uint32_t idx = rw.x >> 1;
         if (!(rw.x & 1u)) {
             my_generic = true;
-            if (SD) {
-                idx = (uint32_t)p.n_dict + (rw.y >> BR_SLOT_SHIFT);
-                if (rw.y & BR_HAS_U2) { ju = j; gu = (int)idx; }
-            }
+            if (SD) idx = (uint32_t)p.n_dict + (rw.y >> BR_SLOT_SHIFT);
+            if (rw.y & BR_HAS_U2) { ju = j; gu = (int)idx; }
         }
         if (j % PKN) pk[j / PKN] |= (idx & ((1u << PKW) - 1u)) << ((j % PKN) * PKW); else pk[j / PKN] = idx & ((1u << PKW) - 1u);
     }
     const bool warp_generic = __any_sync(0xffffffffu, my_generic);
     const bool warp_u2 = __any_sync(0xffffffffu, ju >= 0);
-    const uint32_t u2mask = __reduce_or_sync(0xffffffffu, ju >= 0 ? 1u << ju : 0u);   // SD: local indices of the warp's u2 rows
+    const uint32_t u2mask = __reduce_or_sync(0xffffffffu, ju >= 0 ? 1u << ju : 0u);   // local indices of the warp's u2 rows
     // SD: every thread of the warp stamps its M rows from ONE entry (the periodic interior of a ladder / line): the entry is
     // read once per lane instead of once per row
     bool one_entry = SD;
@@ -192,7 +282,7 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
     // e(s), e(s) + T/2, ... with e(s) = (s % 32) * (NW/2) + s / 32 (spread over the upper warps).  What an owner needs is looked
     // up again for every lane (from an opaque copy of t): kept across the lane loop it would cost registers of the
     // elimination's budget, i.e. local-memory traffic in every thread.
-    static_assert(KRB_BLOCK_DMAX <= 256, "8-bit entry indices");
+    static_assert(DMAX <= 256, "8-bit entry indices");
     constexpr int TH = T / 2, TQ = T / 4;
     auto refresh = [&](long long lane, double w, long long ahead) {
         int tt = t;
@@ -324,55 +414,41 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
                     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
                 }
             }
-        } else if (!warp_generic) {
-            // every row of this warp is a FIXED record: branch-free, the record loads of later rows overlap the recurrence
-#pragma unroll
-            for (int j = 0; j < M; ++j) {
-                const uint4 *d = p.dict + (size_t)((pk[j / PKN] >> ((j % PKN) * PKW)) & ((1u << PKW) - 1u)) * FIX_UNITS;
-                const uint4 c0 = __ldg(d), c1 = __ldg(d + 1);
-                V e0, e1, e2, e4;
-                if (CPLX) {
-                    const uint4 c2 = __ldg(d + 2), c3 = __ldg(d + 3);
-                    e0 = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
-                    e1 = S::make(u4hi(c0), __dmul_rn(w, u4hi(c2)));
-                    e2 = S::make(u4lo(c1), __dmul_rn(w, u4lo(c3)));
-                    e4 = S::make(u4hi(c1), 0.0);
-                } else {
-                    e0 = S::make(u4lo(c0), 0.0); e1 = S::make(u4hi(c0), 0.0); e2 = S::make(u4lo(c1), 0.0); e4 = S::make(u4hi(c1), 0.0);
-                }
-                if (j < MI) interior(j, e0, e1, e2, e4);
-                else separator(e0, e1, e2, e4);
-            }
         } else {
-            // general path: GENERIC rows decoded inline (Monte-Carlo plans: every row of the warp is one)
-            bool pu2_live = false;
+            // !SD (Monte-Carlo plans: most rows carry per-lane terms): the rows were stamped by krb_block_stamp_rows into
+            // E[lane][M][T][4] — thousands of term runs with IEEE divisions per lane belong in a thread-per-(row, lane) kernel with
+            // coalesced lane-interleaved inputs, not on this kernel's dependent chain.  A row is one 32-byte (real) / 64-byte
+            // (complex) record per thread, a warp reads 1 / 2 KB contiguous; records are fetched one row ahead and the next lane's
+            // block is prefetched into L2 (296 resident lanes x 172 KB fit it).
+            typedef typename BlockRec<CPLX>::T Rec;
+            int tt = t;
+            asm volatile("" : "+r"(tt));
+            const Rec *__restrict__ Eb = reinterpret_cast<const Rec *>(p.E) + (size_t)lane * (size_t)(T * M) + tt;
+            if (next < p.lanes) {
+                const char *nb = reinterpret_cast<const char *>(reinterpret_cast<const Rec *>(p.E) + (size_t)next * (size_t)(T * M));
+                constexpr int LINES = (int)(((size_t)T * M * sizeof(Rec) + 127) / 128);
+                for (int ln = tt; ln < LINES; ln += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)ln * 128));
+            }
+            V e3v = S::zero();
+            if (ju >= 0) e3v = __ldg(reinterpret_cast<const V *>(p.U2) + (size_t)lane * T + tt);
+            V c0, c1, c2, c3;
+            BlockRec<CPLX>::load(Eb, c0, c1, c2, c3);
 #pragma unroll
             for (int j = 0; j < M; ++j) {
-                const uint2 rw = __ldg(p.rows + j * T + t);
-                V e0, e1, e2, e3 = S::zero(), e4;
-                bool has_u2 = false;
-                if (rw.x & 1u) {
-                    const uint4 *d = p.dict + (size_t)(rw.x >> 1) * FIX_UNITS;
-                    const uint4 c0 = __ldg(d), c1 = __ldg(d + 1);
-                    if (CPLX) {
-                        const uint4 c2 = __ldg(d + 2), c3 = __ldg(d + 3);
-                        e0 = S::make(u4lo(c0), __dmul_rn(w, u4lo(c2)));
-                        e1 = S::make(u4hi(c0), __dmul_rn(w, u4hi(c2)));
-                        e2 = S::make(u4lo(c1), __dmul_rn(w, u4lo(c3)));
-                        e4 = S::make(u4hi(c1), 0.0);
-                    } else {
-                        e0 = S::make(u4lo(c0), 0.0); e1 = S::make(u4hi(c0), 0.0); e2 = S::make(u4lo(c1), 0.0); e4 = S::make(u4hi(c1), 0.0);
-                    }
-                } else {
-                    has_u2 = (rw.y & BR_HAS_U2) != 0;
-                    block_eval_terms<CPLX>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), IN, L, w, 0, e0, e1, e2, e3, e4);
-                }
+                V n0 = c0, n1 = c1, n2 = c2, n3 = c3;
+                if (j + 1 < M) BlockRec<CPLX>::load(Eb + (j + 1) * T, n0, n1, n2, n3);
+                asm volatile("" ::: "memory");
                 if (j < MI) {
-                    const V s1 = (j > 0 && pu2_live) ? S::fnma(e2, e0, pu2) : e2;
-                    const typename B::Inv iv = interior(j, e0, e1, s1, e4);
-                    pu2_live = has_u2;
-                    if (has_u2) { pu2 = B::div(e3, iv); u2v = pu2; ju = j; fB = B::neg(S::mul(fAprev, pu2)); }
-                } else separator(e0, e1, e2, e4);
+                    V s1 = c2;
+                    if (j > 0 && ((u2mask >> (j - 1)) & 1u)) {
+                        if (j - 1 == ju) s1 = S::fnma(s1, c0, pu2);            // fill from the row above's second super-diagonal
+                    }
+                    const typename B::Inv iv = interior(j, c0, c1, s1, c3);
+                    if ((u2mask >> j) & 1u) {
+                        if (j == ju) { pu2 = B::div(e3v, iv); u2v = pu2; fB = B::neg(S::mul(fAprev, pu2)); }
+                    }
+                } else separator(c0, c1, c2, c3);
+                c0 = n0; c1 = n1; c2 = n2; c3 = n3;
             }
         }
 
@@ -399,10 +475,11 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
         // the separator system drops by ~65 % (measured: one level -13 % (c64) / -5 % (f64) run time, the second another -4 % /
         // -0.6 %).  The upper warps rebuild the dictionary entries for the next lane meanwhile (nobody reads them any more for this
         // lane) and meet the others at the barrier in front of step 3.
-        V *ini = red;                                  // [parity][a, c, d][TH]; the odd part's `a` row later holds the solution
-        V *sol = ini + 3 * TH;
+        V *ini = red;                                  // [parity][a, c, d][TH] (odd half RPAD later); the odd part's `a` row later holds the solution
+        V *inio = ini + 3 * TH + RPAD;                 // the odd rows
+        V *sol = inio;
         const int hk = t >> 1, par = t & 1;
-        ini[(par * 3 + 0) * TH + hk] = a; ini[(par * 3 + 1) * TH + hk] = c; ini[(par * 3 + 2) * TH + hk] = d;
+        { V *w_ = par ? inio : ini; w_[hk] = a; w_[TH + hk] = c; w_[2 * TH + hk] = d; }
         __syncthreads();
         auto reduce_row = [&](V am, V cm, V dm, V ap, V cp, V dq, bool need_ac) {
             const V b2 = S::fnma(S::fnma(B::one(), a, cm), c, ap);
@@ -420,19 +497,20 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
         if (t >= TH) {
             if (SD && next < p.lanes) refresh(next, CPLX ? __dmul_rn(TWO_PI, f_next) : 0.0, next + gridDim.x < p.lanes ? (long long)gridDim.x : 0);
         } else {
-            V *ini2 = red + 3 * T;                     // [parity][a, c, d][TQ] (aliases fst); odd part's `a` row: level-2 solution
-            V *sol2 = ini2 + 3 * TQ;
-            V *pa = ini2 + 6 * TQ, *pb = pa + 3 * TQ;  // double-buffered [a, c, d][TQ]
+            V *ini2 = fst;                             // [parity][a, c, d][TQ] (aliases fst, odd half RPAD later); odd part's `a` row: level-2 solution
+            V *ini2o = ini2 + 3 * TQ + RPAD;
+            V *sol2 = ini2o;
+            V *pa = ini2o + 3 * TQ, *pb = pa + 3 * TQ; // double-buffered [a, c, d][TQ]
             {
-                a = ini[3 * TH + t]; c = ini[4 * TH + t]; d = ini[5 * TH + t];         // row 2t+1
+                a = inio[t]; c = inio[TH + t]; d = inio[2 * TH + t];                   // row 2t+1
                 V ap = S::zero(), cp = S::zero(), dq = S::zero();
                 if (t + 1 < TH) { ap = ini[t + 1]; cp = ini[TH + t + 1]; dq = ini[2 * TH + t + 1]; }   // row 2t+2
                 reduce_row(ini[t], ini[TH + t], ini[2 * TH + t], ap, cp, dq, true);    // row 2t
-                ini2[(par * 3 + 0) * TQ + hk] = a; ini2[(par * 3 + 1) * TQ + hk] = c; ini2[(par * 3 + 2) * TQ + hk] = d;
+                { V *w_ = par ? ini2o : ini2; w_[hk] = a; w_[TQ + hk] = c; w_[2 * TQ + hk] = d; }
             }
             bar_lower(1, TH);
             if (t < TQ) {
-                a = ini2[3 * TQ + t]; c = ini2[4 * TQ + t]; d = ini2[5 * TQ + t];      // compact row 2t+1
+                a = ini2o[t]; c = ini2o[TQ + t]; d = ini2o[2 * TQ + t];                // compact row 2t+1
                 V ap = S::zero(), cp = S::zero(), dq = S::zero();
                 if (t + 1 < TQ) { ap = ini2[t + 1]; cp = ini2[TQ + t + 1]; dq = ini2[2 * TQ + t + 1]; }
                 reduce_row(ini2[t], ini2[TQ + t], ini2[2 * TQ + t], ap, cp, dq, true);
@@ -457,6 +535,9 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
                 x1 = S::fnma(S::fnma(ini2[2 * TQ + hk], ini2[hk], xl2), ini2[TQ + hk], x1);
             }
             sol[t] = x1;
+            // KRB_BLOCK_WAIT_BULK: the previous lane's bulk copy has had a whole elimination + reduction to read xo; make sure of it
+            // before the barrier that lets every thread overwrite xo
+            if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         __syncthreads();
         // even rows by substitution from their own (a, c, d); a thread's left separator: odd rows get it from the lane below
@@ -468,11 +549,18 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
             sm = par ? below : xl;
         }
 
-        // ---- 3. interiors, staged in the shared column, then coalesced point-major delivery ----
+        // ---- 3. interiors into the result buffer, then ONE bulk asynchronous copy of the lane's vector ----
         // back substitution  x_j = (y^_j - l^_j s_{t-1}) - u^_j x_{j+1} (- u2^_j x_{j+2}),  x_{M-1} = s_t
+        V *__restrict__ out = reinterpret_cast<V *>(p.OUT) + (size_t)lane * (size_t)n;
+        // real: the lane's first byte may sit at 8 mod 16; the result buffer is shifted by one element then, so that shared and
+        // global addresses stay congruent mod 16 (bulk copies need 16-byte aligned addresses and sizes)
+        const int shift = CPLX ? 0 : (int)((reinterpret_cast<size_t>(out) >> 3) & 1);
         {
+            int tt = t;
+            asm volatile("" : "+r"(tt));
+            V *__restrict__ xcol = xo + shift + tt * M;
             V xn = st, x2 = st;
-            const uint32_t m4 = SD ? u2mask : __reduce_or_sync(0xffffffffu, ju >= 0 ? 1u << ju : 0u);
+            const uint32_t m4 = u2mask;
             V lj = mycol[MI - 1];                     // l^ of row j - 1 is loaded while row j is computed (c64: -2.5 %)
 #pragma unroll
             for (int j = MI - 1; j >= 0; --j) {
@@ -483,41 +571,55 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
                 if ((m4 >> j) & 1u) {
                     if (j == ju) xj = S::fnma(xj, u2v, x2);
                 }
-                mycol[j] = xj;
+                xcol[j] = xj;
                 x2 = xn; xn = xj;
             }
+            xcol[MI] = st;
         }
-        mycol[MI] = st;
         int status = grow >= KRB_NONFINITE_KEY ? KRB_LANE_ZERO_PIVOT : grow >= KRB_GROWTH_KEY ? KRB_LANE_INACCURATE : 0;
         if (!S::finite(st)) status |= KRB_LANE_NONFINITE;
         if (status && p.status) atomicOr(p.status + lane, status);
-        __syncthreads();
-        V *__restrict__ out = reinterpret_cast<V *>(p.OUT) + (size_t)lane * (size_t)n;
-        // pivot row i lives at xq[(i / M) * XS + i % M] = xq[i + i / M].  The M offsets do not depend on the lane, but hoisted
-        // out of the lane loop they cost M registers (spilled: M local loads per lane); an opaque copy of t keeps them here.
-        int tt = t;
-        asm volatile("" : "+r"(tt));
-        // (issuing ALL M shared-memory loads ahead of their stores, or groups of 2-10, was measured slower: the burst throttles
-        // the MIO queue that the other resident CTA's elimination needs; one element ahead is the sweet spot)
-        if (p.unknown_of_row == nullptr) {
-            V cur = xq[tt + tt / M];                 // element k + 1 is loaded before element k is stored (f64: -2 %)
-#pragma unroll
-            for (int k = 0; k < M; ++k) {
-                const int i = tt + k * T, i1 = i + T;
-                V nxt = cur;
-                if (k + 1 < M) nxt = xq[i1 + i1 / M];
-                if (i < n) __stcs(out + i, cur);
-                cur = nxt;
+        __syncthreads();                              // the whole vector is in xo
+        const V *__restrict__ xv = xo + shift;        // pivot row i at xv[i]
+        if (p.bulk_store) {
+            if (t == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+                const int head = shift;                                    // real, odd-aligned lane: element 0 by a plain store
+                const int cnt = n - head;
+                const int tail = CPLX ? 0 : (cnt & 1);                     // real: an odd count leaves one element for a plain store
+                if (head) __stcs(out, xv[0]);
+                if (tail) __stcs(out + (n - 1), xv[n - 1]);
+                const uint32_t bytes = (uint32_t)(cnt - tail) * (uint32_t)sizeof(V);
+                if (bytes) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(xv + head);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + head), "r"(src), "r"(bytes) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {
+            // per-thread delivery (permuted pivot order, or a caller's buffer the bulk copy cannot address): pivot row i is at xv[i],
+            // consecutive threads read consecutive elements (conflict-free) and store full-width runs
+            int tt = t;
+            asm volatile("" : "+r"(tt));
+            if (p.unknown_of_row == nullptr) {
 #pragma unroll
-            for (int k = 0; k < M; ++k) {
-                const int i = tt + k * T;
-                if (i < n) __stcs(out + __ldg(p.unknown_of_row + i), xq[i + i / M]);
+                for (int k = 0; k < M; ++k) {
+                    const int i = tt + k * T;
+                    if (i < n) __stcs(out + i, xv[i]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    const int i = tt + k * T;
+                    if (i < n) __stcs(out + __ldg(p.unknown_of_row + i), xv[i]);
+                }
             }
         }
-        __syncthreads();                              // the columns and the reduction buffers are reused by the next lane
+        // no barrier here: the next lane's elimination touches only the threads' own l^ columns; its separator buffers were last
+        // read before the barrier in front of step 3, and xo is rewritten only in the next lane's step 3, three barriers from now
+        // (a pending bulk copy is waited for just before that barrier, see KRB_BLOCK_WAIT_BULK)
     }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the copies that read it
 }
 
 }  // namespace krb

@@ -546,11 +546,13 @@ static void build_chain_block(Plan &plan, const std::vector<uint32_t> &row_off, 
     if (n < 512 && !force_small) { bk.why_not = "n < 512: the sequential chain kernel is used"; return; }
     // KRB_CHAIN_BLOCK_CT256 (profiling): complex plans on 256-thread CTAs, two resident per SM (systems up to 2560 rows)
     const bool ct256 = cplx && getenv("KRB_CHAIN_BLOCK_CT256") != nullptr;
-    const int T = cplx && !ct256 ? 512 : 256, mstep = cplx ? 2 : 4, mmax = cplx ? 10 : 20;
+    // compiled shapes: real M = 5, 9, ... 21 (odd: the lane's result vector is contiguous AND conflict-free in shared memory),
+    // complex M = 2, 4, ... 10
+    const int T = cplx && !ct256 ? 512 : 256, mfirst = cplx ? 2 : 5, mstep = cplx ? 2 : 4, mmax = cplx ? 10 : 21;
     // smallest compiled M that holds the system and keeps every row with a second super-diagonal at local index <= M-3,
     // at most one per block
     int M = 0;
-    for (int m = mstep; m <= mmax && !M; m += mstep) {
+    for (int m = mfirst; m <= mmax && !M; m += mstep) {
         if ((int64_t)T * m < n) continue;
         bool fits = true;
         int last_block = -1;
@@ -695,7 +697,7 @@ static void build_chain_block(Plan &plan, const std::vector<uint32_t> &row_off, 
     bk.n_dict = (int)index.size();
     if (bk.n_dict > 0xffff) { bk = ChainPlan::Block(); bk.why_not = "dictionary index does not fit 16 bits"; return; }
     // shared-dictionary mode of the kernel: unique FIXED records + GENERIC rows fit the on-chip table
-    bk.shared_dict = bk.n_dict + (int)bk.gen_rows.size() <= 256 && getenv("KRB_CHAIN_BLOCK_NO_SD") == nullptr;
+    bk.shared_dict = bk.n_dict + (int)bk.gen_rows.size() <= (cplx ? 64 : 256) && getenv("KRB_CHAIN_BLOCK_NO_SD") == nullptr;   // KRB_BLOCK_DMAX(_CPLX)
     bk.T = T; bk.M = M;
     bk.valid = true;
 }

@@ -252,7 +252,7 @@ static int launch_chain(bool cplx, int tpb, bool direct, const ChainParams &p, l
 template <bool CPLX, int T, int M, bool SD>
 static int launch_chain_block_t(const ChainBlockParams &p, cudaStream_t st) {
     typedef typename ChainSc<CPLX>::T V;
-    const size_t smem = ((size_t)T * (M + 1) + (size_t)6 * T + (SD ? (size_t)5 * KRB_BLOCK_DMAX : 0)) * sizeof(V);
+    const size_t smem = block_smem_elems<CPLX, T, M, SD>() * sizeof(V);
     static int resident_dev[KRB_MAX_DEVICES] = {};
     int &resident = resident_dev[current_device_slot()];
     if (!resident) {
@@ -290,12 +290,12 @@ static int launch_chain_block_s(bool cplx, int T, int M, const ChainBlockParams 
         case 10: return launch_chain_block_t<true, 512, 10, SD>(p, st);
         }
     } else {
-        switch (M) {
-        case 4: return launch_chain_block_t<false, 256, 4, SD>(p, st);
-        case 8: return launch_chain_block_t<false, 256, 8, SD>(p, st);
-        case 12: return launch_chain_block_t<false, 256, 12, SD>(p, st);
-        case 16: return launch_chain_block_t<false, 256, 16, SD>(p, st);
-        case 20: return launch_chain_block_t<false, 256, 20, SD>(p, st);
+        switch (M) {   // odd: a thread's column and the lane's contiguous result vector are both conflict-free
+        case 5: return launch_chain_block_t<false, 256, 5, SD>(p, st);
+        case 9: return launch_chain_block_t<false, 256, 9, SD>(p, st);
+        case 13: return launch_chain_block_t<false, 256, 13, SD>(p, st);
+        case 17: return launch_chain_block_t<false, 256, 17, SD>(p, st);
+        case 21: return launch_chain_block_t<false, 256, 21, SD>(p, st);
         }
     }
     set_error("block chain kernel: no compiled shape for this plan");
@@ -413,7 +413,9 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     }
 
     // ---- chunking: bound the per-call device footprint ----
-    const int planes0 = block ? 0 : chain ? 2 * n + P0.chain.n_u2 : P0.n_planes, planesS = PS ? PS->n_planes : 0;
+    // block kernel without a shared dictionary: pre-stamped rows E[lane][T*M][4] + U2[lane][T] live in the G buffer (counted in planes)
+    const bool block_stamped = block && !P0.chain.block.shared_dict;
+    const int planes0 = block ? (block_stamped ? P0.chain.block.T * (4 * P0.chain.block.M + 1) : 0) : chain ? 2 * n + P0.chain.n_u2 : P0.n_planes, planesS = PS ? PS->n_planes : 0;
     const int nbuf = out_dev ? 1 : 2;
     const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)plane_rows * width * ts * (out_dev ? 1 : 2) + (out_dev ? 0 : (size_t)rows * width * ts * 2) +
                             (size_t)P0.n_inputs * 8 + (a.op_solution ? (size_t)n * 8 : 0) + 16;
@@ -471,16 +473,28 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         // ---- inputs ----
         {
         NvtxRange nvtx_inputs("krb lanes: inputs (sweep values / frequencies / Monte-Carlo planes)");
-        for (int k = 0; k < P0.n_inputs; k++) {
-            const double *src = nullptr;
-            if (k == P0.input_sweep || k == P0.input_freq) src = a.lane_param;
-            else {
-                int vk = -1;
-                for (size_t q = 0; q < P0.input_of_varied.size(); q++) if (P0.input_of_varied[q] == k) { vk = (int)q; break; }
-                if (vk < 0 || !a.varied_values) { set_error("missing per-lane values for a varied element"); return KRB_ERR_INVALID_ARGUMENT; }
-                src = a.varied_values + (size_t)vk * a.lanes;
+        {
+            // Monte-Carlo planes normally occupy one contiguous run of input planes in the caller's order: one strided 2-D copy
+            // instead of one copy per plane (a ladder with every resistor per-lane has 5000 of them: 20 ms of launches per chunk)
+            const int nv = (int)P0.input_of_varied.size();
+            bool run = nv > 1 && a.varied_values != nullptr;
+            for (int q = 1; q < nv && run; q++) run = P0.input_of_varied[q] == P0.input_of_varied[0] + q;
+            for (int q = 0; q < nv && run; q++) run = P0.input_of_varied[q] != P0.input_sweep && P0.input_of_varied[q] != P0.input_freq;
+            if (run)
+                CUDA_TRY(cudaMemcpy2DAsync(IN + (size_t)P0.input_of_varied[0] * Lpad, (size_t)Lpad * 8, a.varied_values + lane0, (size_t)a.lanes * 8,
+                                           (size_t)lanes * 8, (size_t)nv, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+            for (int k = 0; k < P0.n_inputs; k++) {
+                const double *src = nullptr;
+                if (k == P0.input_sweep || k == P0.input_freq) src = a.lane_param;
+                else {
+                    if (run) continue;
+                    int vk = -1;
+                    for (size_t q = 0; q < P0.input_of_varied.size(); q++) if (P0.input_of_varied[q] == k) { vk = (int)q; break; }
+                    if (vk < 0 || !a.varied_values) { set_error("missing per-lane values for a varied element"); return KRB_ERR_INVALID_ARGUMENT; }
+                    src = a.varied_values + (size_t)vk * a.lanes;
+                }
+                CUDA_TRY(cudaMemcpyAsync(IN + (size_t)k * Lpad, src + lane0, (size_t)lanes * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
             }
-            CUDA_TRY(cudaMemcpyAsync(IN + (size_t)k * Lpad, src + lane0, (size_t)lanes * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         }
         if (Lpad > lanes && P0.n_inputs > 0) {
             const long long work = (long long)P0.n_inputs * (Lpad - lanes);
@@ -517,6 +531,24 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             c.IN = IN; c.lanes = lanes; c.L = Lpad; c.n = n; c.input_freq = P0.input_freq; c.status = status_d;
             c.gen_rows = D0.block_gen; c.n_dict = P0.chain.block.n_dict; c.n_gen = (int)P0.chain.block.gen_rows.size();
             c.OUT = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p;
+            // one bulk asynchronous copy per lane (TMA engine) when pivot row k is unknown k; complex results need a 16-byte aligned
+            // buffer (real ones are handled at any 8-byte alignment).  KRB_BLOCK_NO_BULK=1: per-thread stores (A/B measurements)
+            static const bool no_bulk = getenv("KRB_BLOCK_NO_BULK") != nullptr;
+            c.bulk_store = (P0.chain.identity_order && !no_bulk && (!cplx || ((size_t)c.OUT & 15u) == 0)) ? 1 : 0;
+            if (block_stamped) {
+                // (a) stamping as its own launch: thread per (pivot row, lane), coalesced inputs, records transposed to lane-major
+                const int T = P0.chain.block.T, M = P0.chain.block.M;
+                BlockStampParams sp{};
+                sp.rows = D0.block_rows; sp.dict = D0.block_dict; sp.stream = D0.chain_stream; sp.IN = IN; sp.L = Lpad; sp.lanes = lanes;
+                sp.input_freq = P0.input_freq; sp.slots = T * M; sp.T = T;
+                sp.E = D0.G.p; sp.U2 = (char *)D0.G.p + (size_t)chunk * (size_t)T * M * 4 * ts;
+                const dim3 grid((unsigned)(T * M / (cplx ? 16 : 32)), (unsigned)((lanes + 31) / 32)), blk(32, 8);
+                if (cplx) krb_block_stamp_rows<true><<<grid, blk, 0, st>>>(sp);
+                else krb_block_stamp_rows<false><<<grid, blk, 0, st>>>(sp);
+                g_launches++;
+                CUDA_TRY(cudaGetLastError());
+                c.E = sp.E; c.U2 = sp.U2;
+            }
             if ((rc = launch_chain_block(cplx, P0.chain.block.T, P0.chain.block.M, P0.chain.block.shared_dict, c, st))) return rc;
         } else if (chain) {
             ChainParams c{};

@@ -26,7 +26,7 @@ def _dc_point(oc, v):
     return oc.solve_dc("V1", v, v, 1.0)[0]
 
 
-@pytest.mark.parametrize("nodes,shape", [(5000, (256, 20)), (3000, (256, 12)), (700, (256, 4))])
+@pytest.mark.parametrize("nodes,shape", [(5000, (256, 21)), (3000, (256, 13)), (700, (256, 5))])
 def test_block_vs_sequential_and_oracle_dc(oracle, monkeypatch, nodes, shape):
     import torch
     text = netgen.resistor_ladder(nodes)
@@ -161,3 +161,44 @@ def test_block_shared_dictionary_many_generic_entries(oracle, monkeypatch):
         for k, e in enumerate(varied):
             oc.set_element_value(e, vals[k, l])
         assert_close(out[l], oc.solve_op(), what=f"block chain, 200 generic entries, lane {l}")
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_block_prestamped_rows_monte_carlo(oracle, cplx):
+    """Plans whose per-lane rows do not fit the shared dictionary (every element Monte-Carlo): the rows are stamped by
+    krb_block_stamp_rows (thread per (row, lane)) and streamed by the block kernel.  More lanes than resident CTAs, a lane count
+    that is not a multiple of the stamping tile, every lane against the oracle on a sample + block vs sequential kernel on all."""
+    import torch
+    nodes = 700
+    text = netgen.rc_ladder(nodes) if cplx else netgen.resistor_ladder(nodes)
+    circuit = kb.parse_circuit_description(text)
+    varied = [e for e in range(circuit.num_elements) if circuit.element(e).kind in (api.KIND_R, api.KIND_C)]
+    lanes = 1301
+    rng = np.random.default_rng(23)
+    vals = np.array([[circuit.element_value(e) * (0.95 + 0.1 * rng.random()) for _ in range(lanes)] for e in varied])
+    plan = kb.Plan(circuit, api.MODE_AC if cplx else api.MODE_DC, varied=varied, nominal_frequency=1e4)
+    valid, T, M, n_dict, _, why = chain_block_info(plan)
+    assert plan.info.executor == 1 and valid, why
+    v_dev = torch.from_numpy(vals).cuda()
+    if cplx:
+        freqs = np.logspace(1, 7, lanes)
+        out, status = plan.solve_ac(torch.from_numpy(freqs).cuda(), varied_values=v_dev)
+    else:
+        out, status = plan.solve_op(lanes, varied_values=v_dev)
+    torch.cuda.synchronize()
+    assert int(status.abs().max().item()) == 0
+    a = out.cpu().numpy()
+    import os
+    os.environ["KRB_CHAIN_SEQ"] = "1"
+    try:
+        seq = (plan.solve_ac(torch.from_numpy(freqs).cuda(), varied_values=v_dev) if cplx else plan.solve_op(lanes, varied_values=v_dev))[0].cpu().numpy()
+    finally:
+        del os.environ["KRB_CHAIN_SEQ"]
+    assert_close(a, seq, rtol=5e-10, what="pre-stamped block kernel vs sequential chain kernel")
+    assert not np.array_equal(a, seq)
+    for l in (0, 1, 650, lanes - 1):
+        oc = oracle.Circuit(text)
+        for k, e in enumerate(varied):
+            oc.set_element_value(e, vals[k, l])
+        ref = oc.solve_ac([freqs[l]])[1][0] if cplx else oc.solve_op()
+        assert_close(a[l], ref, what=f"pre-stamped block kernel lane {l}")

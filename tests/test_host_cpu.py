@@ -324,7 +324,7 @@ def test_chain_block_tables_ladder_5000(oracle):
     kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
     plan = kb.Plan(kc, api.MODE_DC, sweep_element=0)
     valid, T, M, n_dict, diff, why = chain_block_info(plan)
-    assert valid and (T, M) == (256, 20), why
+    assert valid and (T, M) == (256, 21), why
     assert n_dict <= 6 and diff <= 5e-10            # a ladder has a handful of distinct row records
     assert plan.info.hbm_bytes_per_point == 8 * 5001 + 8     # inputs in, n results out: SURVEY 8(d)'s fused floor
     vals = np.array([-1.5, 0.25, 3.0])
