@@ -69,18 +69,34 @@ template <bool CPLX, int T, int M, bool SD> constexpr size_t block_smem_elems() 
 __device__ __forceinline__ uint32_t pivot_key(double w) { return ((uint32_t)__double2hiint(w) & 0x7ff00000u) - 0x00100000u; }
 constexpr uint32_t KRB_BAD_PIVOT_KEY = 0x7fe00000u;
 
+#ifndef KRB_OLD_FULL_BARRIER
+#define KRB_BLOCK_ISSUER(NW) (((NW) / 2 - 1) * 32)
+#else
+#define KRB_BLOCK_ISSUER(NW) 0
+#endif
+
 template <bool CPLX> struct BlockSc;
 template <> struct BlockSc<false> {
     typedef double T;
     // reciprocal of the pivot to ~1 ulp, returned as (r0, t):  q / w = fma(q*r0, t, q*r0)
+#ifndef KRB_OLD_RCP8
+    struct Inv { double r; };     // the full reciprocal once (r0 (1 + e + e^2), ~1 ulp), quotients = a * r: 6 instead of 8 FP64 operations per row (r2g: -6.6 %)
+#else
     struct Inv { double r0, t; };
+#endif
     static __device__ __forceinline__ uint32_t bad_pivot(double w) { return pivot_key(w) >= KRB_BAD_PIVOT_KEY ? KRB_NONFINITE_KEY : 0u; }
     static __device__ __forceinline__ Inv inv(double w) {
         const double r0 = rcp_seed(w);
         const double e = fma(-w, r0, 1.0);
+#ifndef KRB_OLD_RCP8
+        return Inv{fma(r0, fma(e, e, e), r0)};
+    }
+    static __device__ __forceinline__ double div(double a, const Inv &i) { return a * i.r; }
+#else
         return Inv{r0, fma(e, e, e)};
     }
     static __device__ __forceinline__ double div(double a, const Inv &i) { const double a0 = a * i.r0; return fma(a0, i.t, a0); }
+#endif
     static __device__ __forceinline__ double neg(double a) { return -a; }
     static __device__ __forceinline__ double one() { return 1.0; }
     static __device__ __forceinline__ double shfl_up1(double a) { return __shfl_up_sync(0xffffffffu, a, 1); }
@@ -537,7 +553,7 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
             sol[t] = x1;
             // KRB_BLOCK_WAIT_BULK: the previous lane's bulk copy has had a whole elimination + reduction to read xo; make sure of it
             // before the barrier that lets every thread overwrite xo
-            if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (t == KRB_BLOCK_ISSUER(NW)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         __syncthreads();
         // even rows by substitution from their own (a, c, d); a thread's left separator: odd rows get it from the lane below
@@ -562,27 +578,52 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
             V xn = st, x2 = st;
             const uint32_t m4 = u2mask;
             V lj = mycol[MI - 1];                     // l^ of row j - 1 is loaded while row j is computed (c64: -2.5 %)
+#ifndef KRB_OLD_NO_BSPLIT
+            if (m4 == 0u) {                           // (r2g: -2.1 %) no row of this warp has a second super-diagonal: a test-free loop
 #pragma unroll
-            for (int j = MI - 1; j >= 0; --j) {
-                V ln = lj;
-                if (j > 0) ln = mycol[j - 1];
-                V xj = S::fnma(S::fnma(y[j], lj, sm), u[j], xn);
-                lj = ln;
-                if ((m4 >> j) & 1u) {
-                    if (j == ju) xj = S::fnma(xj, u2v, x2);
+                for (int j = MI - 1; j >= 0; --j) {
+                    V ln = lj;
+                    if (j > 0) ln = mycol[j - 1];
+                    const V xj = S::fnma(S::fnma(y[j], lj, sm), u[j], xn);
+                    lj = ln;
+                    xcol[j] = xj;
+                    xn = xj;
                 }
-                xcol[j] = xj;
-                x2 = xn; xn = xj;
+            } else
+#endif
+            {
+#pragma unroll
+                for (int j = MI - 1; j >= 0; --j) {
+                    V ln = lj;
+                    if (j > 0) ln = mycol[j - 1];
+                    V xj = S::fnma(S::fnma(y[j], lj, sm), u[j], xn);
+                    lj = ln;
+                    if ((m4 >> j) & 1u) {
+                        if (j == ju) xj = S::fnma(xj, u2v, x2);
+                    }
+                    xcol[j] = xj;
+                    x2 = xn; xn = xj;
+                }
             }
             xcol[MI] = st;
         }
         int status = grow >= KRB_NONFINITE_KEY ? KRB_LANE_ZERO_PIVOT : grow >= KRB_GROWTH_KEY ? KRB_LANE_INACCURATE : 0;
         if (!S::finite(st)) status |= KRB_LANE_NONFINITE;
         if (status && p.status) atomicOr(p.status + lane, status);
-        __syncthreads();                              // the whole vector is in xo
         const V *__restrict__ xv = xo + shift;        // pivot row i at xv[i]
+#ifndef KRB_OLD_FULL_BARRIER
+        // (r2g: -1 %) only the warp that issues the bulk copy waits for the vector; the others signal and start the next lane
+        constexpr int ISSUER = (NW / 2 - 1) * 32;     // a thread of a warp with periodic interior rows (the fast elimination path)
         if (p.bulk_store) {
-            if (t == 0) {
+            if ((t >> 5) == (ISSUER >> 5)) asm volatile("bar.sync 3, %0;" ::"r"(T) : "memory");
+            else asm volatile("bar.arrive 3, %0;" ::"r"(T) : "memory");
+        } else __syncthreads();
+#else
+        constexpr int ISSUER = 0;
+        __syncthreads();                              // the whole vector is in xo
+#endif
+        if (p.bulk_store) {
+            if (t == ISSUER) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
                 const int head = shift;                                    // real, odd-aligned lane: element 0 by a plain store
                 const int cnt = n - head;
@@ -619,7 +660,7 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
         // read before the barrier in front of step 3, and xo is rewritten only in the next lane's step 3, three barriers from now
         // (a pending bulk copy is waited for just before that barrier, see KRB_BLOCK_WAIT_BULK)
     }
-    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the copies that read it
+    if (t == KRB_BLOCK_ISSUER(NW)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the copies that read it
 }
 
 }  // namespace krb
