@@ -488,6 +488,62 @@ def time_workload(w, W, K, ctx):
     return res, clocks.summary()
 
 
+def strong_scaling_rc_ac(ctx):
+    """BASELINE config 3 as written: the WHOLE 10^6-frequency sweep of the RC ladder 5000, split over the ranks (strong scaling),
+    solved in 65 536-lane chunks.  `value`: results stay sharded (the default); `with_gather`: every chunk travels to rank 0 while the
+    next one is solved, gather inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    import netgen
+    import krets_b200 as kb
+    from krets_b200 import api
+    from krets_b200.sharding import solve_sharded_chunked, shard_bounds
+    world, rank = ctx["world"], ctx["rank"]
+    circuit = kb.parse_circuit_description(netgen.rc_ladder(LADDER_N))
+    plan = kb.Plan(circuit, api.MODE_AC, nominal_frequency=1.0)
+    allf = torch.from_numpy(kb.generate_frequencies("Decade", 125000, 1.0, 1e8)).cuda()
+    total, n, chunk = int(allf.shape[0]), circuit.n, 65536
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def solve_chunk(lo, hi, dst):
+        _, st = plan.solve_ac(allf[lo:hi], out=dst)
+        bad.add_((st != 0).sum())
+
+    def timed(gather_to, reps):
+        solve_sharded_chunked(total, solve_chunk, chunk_lanes=chunk, row_shape=(n,), dtype=torch.complex128, device="cuda", gather_to=gather_to)
+        ctx["barrier"]()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            lo, res = solve_sharded_chunked(total, solve_chunk, chunk_lanes=chunk, row_shape=(n,), dtype=torch.complex128, device="cuda", gather_to=gather_to)
+        e1.record()
+        ctx["barrier"]()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+        if ctx["distributed"]:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        v1 = None
+        if res is not None:
+            col = circuit.index_map["V(1)"]
+            v1 = float((res[:, col] - 1.0).abs().max().item())        # source row: V(1) = 1 on every lane
+        del res
+        torch.cuda.empty_cache()
+        return float(t.item()), v1
+    ms_sh, v1 = timed(None, 2)
+    out = {"name": "rc_ac_full_strong", "baseline_config": 3, "scaling": "strong", "dtype": "c64", "n_unknowns": n, "lanes_total": total,
+           "workload": f"resistor_ladder_5000-class RC ladder AC sweep, ALL {total} log-spaced frequencies split over {world} GPU(s) (strong scaling), {chunk}-lane chunks; {total * n * 16 / 1e9:.0f} GB of results",
+           "value": total / (ms_sh * 1e-3), "unit": UNIT, "ms_per_sweep": ms_sh, "results": "stay sharded on their GPUs (default)",
+           "max_abs_err_source_row": v1}
+    if world > 1:
+        ms_g, v1g = timed(0, 1)
+        lo, hi = shard_bounds(total, world, 0)
+        inbound = (total - (hi - lo)) * n * 16
+        out["with_gather"] = {"value": total / (ms_g * 1e-3), "unit": UNIT, "ms_per_sweep": ms_g, "bytes_inbound_rank0": inbound, "GBps_inbound": inbound / (ms_g * 1e-3) / 1e9,
+                              "collective": "chunked ncclSend/ncclRecv to rank 0, grouped per round, overlapped with the next chunk's solve, inside the timed region",
+                              "max_abs_err_source_row": v1g}
+    out["lanes_with_status"] = int(bad.item())
+    return out if rank == 0 else None
+
+
 def link_ceiling(ctx, nbytes=1 << 30, reps=3):
     """Bare pinned cudaMemcpyAsync D2H on every rank at once: the box's ceiling for delivering results to the host."""
     import torch
@@ -591,28 +647,55 @@ def main():
         e2e["link_ceiling_GBps"] = link_ceiling(ctx)
         e2e["frac_of_link_ceiling"] = e2e["d2h_GBps"] / e2e["link_ceiling_GBps"]
         e2e["link_ceiling_note"] = f"bare pinned cudaMemcpyAsync D2H of 1 GiB x 3 on all {world} rank(s) at once, aggregate"
+        # EXTENSION (labelled; the reference returns every unknown, ac.rs:97-105): the same call with krb_io.select = 8 unknowns —
+        # what a plotting front end reads.  Reported beside the full-delivery headline, never instead of it.
+        sel = [0, 1, 2, n // 4, n // 2, (3 * n) // 4, n - 2, n - 1]
+        h_sel = torch.empty((lanes, len(sel)), dtype=torch.float64).pin_memory()
+        hs = h_sel.numpy()
+        for _ in range(2):
+            plan.solve_dc_sweep(hv, out=hs, select=sel)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            plan.solve_dc_sweep(hv, out=hs, select=sel)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert np.array_equal(hs[lanes - 1], out[lanes - 1].cpu().numpy()[sel])
+        e2e["selected"] = {"value": lanes * world * Ke / float(t.item()), "unit": UNIT, "n_select": len(sel), "d2h_bytes_per_step": lanes * len(sel) * 8 + lanes * 4,
+                           "note": "EXTENSION, not reference behaviour: krb_io.select delivers 8 of the 5001 unknowns per point (host buffers, same call otherwise)"}
 
-    # ---- final gather of result shards over NVLink (outside the timed region; reported separately) ----
+    # ---- results gathered on rank 0: by default they stay sharded (`value` above: no data-path collective); here every
+    # chunk is sent to rank 0 over NVLink (ncclSend/ncclRecv, grouped per round) while the next chunk is being solved, and the
+    # whole thing - solve + gather - is inside the timed region ----
     gather = None
     if distributed and w.name == "ladder_dc":
-        out = w.out
+        from krets_b200.sharding import solve_sharded_chunked
+        plan = w.plan
+        total = lanes * world
+        all_vals = torch.arange(total, dtype=torch.float64, device="cuda") * STEP
+        chunk = 16384
+
+        def solve_chunk(lo, hi, dst):
+            plan.solve_dc_sweep(all_vals[lo:hi], out=dst)
+        solve_sharded_chunked(total, solve_chunk, chunk_lanes=chunk, row_shape=(n,), dtype=torch.float64, device="cuda", gather_to=0)   # warm-up: NCCL connections
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        bufs = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
-        warm = [torch.empty_like(out[:64]) for _ in range(world)] if rank == 0 else None
-        dist.gather(out[:64].contiguous(), warm, dst=0)          # NCCL connection setup is not part of the gather time
-        barrier()
         g0.record()
-        dist.gather(out, bufs, dst=0)
+        _, full = solve_sharded_chunked(total, solve_chunk, chunk_lanes=chunk, row_shape=(n,), dtype=torch.float64, device="cuda", gather_to=0)
         g1.record()
         barrier()
         gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        nbytes = out.numel() * 8 * (world - 1)
-        gather = {"collective": "ncclGather of x shards to rank 0", "ms": float(gms.item()), "bytes_inbound_rank0": nbytes,
-                  "GBps": nbytes / (float(gms.item()) * 1e-3) / 1e9,
-                  "value_with_gather": lanes * world / ((main_res["ms_per_step"] + float(gms.item())) * 1e-3)}
-        del bufs
+        nbytes = lanes * n * 8 * (world - 1)
+        if rank == 0:
+            assert torch.equal(full[:lanes], w.out)
+        gather = {"collective": f"chunked ncclSend/ncclRecv to rank 0 ({chunk}-lane chunks, grouped per round), overlapped with the solve of the next chunk; solve + gather timed together",
+                  "ms": float(gms.item()), "bytes_inbound_rank0": nbytes, "GBps_inbound": nbytes / (float(gms.item()) * 1e-3) / 1e9,
+                  "value_with_gather": total / (float(gms.item()) * 1e-3),
+                  "note": "the root's inbound NVLink port (<= 900 GB/s), not the solve, bounds a gathered sweep: results stay sharded by default"}
+        del full, all_vals
 
     # ---- the other BASELINE configs, measured in the same run under the same rules ----
     others = []
@@ -632,6 +715,15 @@ def main():
                 others.append({"name": name, "error": f"{type(ex).__name__}: {ex}"})
             ow = None
             torch.cuda.empty_cache()
+
+    if not args.no_others and args.workload == "ladder_dc" and lanes == LANES_PER_GPU:
+        try:
+            res = strong_scaling_rc_ac(ctx)
+            if res is not None:
+                others.append(res)
+        except Exception as ex:
+            others.append({"name": "rc_ac_full_strong", "error": f"{type(ex).__name__}: {ex}"})
+        torch.cuda.empty_cache()
 
     if rank == 0:
         line = {

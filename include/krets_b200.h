@@ -175,7 +175,15 @@ typedef struct krb_io {
     int32_t layout;                   /* KRB_LAYOUT_* of x_out */
     int32_t reserved;
     void *stream;                     /* cudaStream_t */
+    /* EXTENSION (not reference behaviour: ac.rs:97-105, dc.rs:92-97 and transient.rs:90-95 return every unknown of every point):
+     * result selection.  n_select > 0: only the unknowns select[0..n_select) (index-map indices, HOST pointer, copied by the call)
+     * are delivered and x_out holds n_select values per solved point instead of n (point-major layout only).  What a plotting
+     * front end (krets-gui) needs; cuts the device->host traffic of a sweep from n to n_select values per point. */
+    const int32_t *select;
+    int32_t n_select;
+    int32_t reserved2;
 } krb_io;
+#define KRB_IO_SIZE_V1 24             /* struct_size of the layout without the selection fields (still accepted) */
 void krb_default_io(krb_io *io);
 
 /* per-lane element values (Monte-Carlo): values[k][lane] is the value of plan.varied_elements[k] on that lane */

@@ -81,6 +81,9 @@ pub struct krb_io {
     pub layout: i32,
     pub reserved: i32,
     pub stream: *mut c_void,
+    pub select: *const i32, // extension: deliver only these unknowns (krets_b200.h)
+    pub n_select: i32,
+    pub reserved2: i32,
 }
 
 #[repr(C)]

@@ -40,7 +40,7 @@ class KrbPlanInfo(C.Structure):         # krb_plan_info
 
 class KrbIO(C.Structure):               # krb_io
     _fields_ = [("struct_size", C.c_int32), ("memory", C.c_int32), ("layout", C.c_int32), ("reserved", C.c_int32),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("select", C.POINTER(C.c_int32)), ("n_select", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class KrbOverrides(C.Structure):        # krb_overrides

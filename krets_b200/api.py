@@ -409,9 +409,13 @@ class Plan:
         return ops
 
     # -- solves --
-    def _io(self, arrays, layout):
+    def _io(self, arrays, layout, select=None):
         io = KrbIO()
         _lib.lib().krb_default_io(C.byref(io))
+        if select is not None:        # extension: deliver only these unknowns (index-map indices), krets_b200.h krb_io.select
+            self._sel = np.ascontiguousarray(select, dtype=np.int32)
+            io.select = self._sel.ctypes.data_as(C.POINTER(C.c_int32))
+            io.n_select = int(self._sel.size)
         dev = [_is_device(a) for a in arrays if a is not None]
         if any(dev) and not all(dev):
             raise ValueError("all lane-sized arrays of one call must be on the same side (host numpy or CUDA tensors)")
@@ -431,42 +435,45 @@ class Plan:
         return ov, values
 
     def solve_op(self, lanes: int = 1, varied_values=None, out=None, cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR,
-                 return_iterations=False):
+                 return_iterations=False, select=None):
         cfg = cfg or SolverConfig()
         varied_values = _f64_in(varied_values, (len(self.varied), lanes) if self.varied else None, "varied_values")
-        out = _check_out(out, _shape(layout, lanes, 1, self.n), False) if out is not None else _like_out(varied_values, _shape(layout, lanes, 1, self.n), False)
+        cols = self.n if select is None else len(select)
+        out = _check_out(out, _shape(layout, lanes, 1, cols), False) if out is not None else _like_out(varied_values, _shape(layout, lanes, 1, cols), False)
         status = _like_int(out, lanes)
         iters = _like_int(out, lanes) if return_iterations else None
         ov, _keep = self._ov(varied_values)
-        io = self._io([out, varied_values], layout)
+        io = self._io([out, varied_values], layout, select)
         _check_krb(_lib.lib().krb_solve_op(self._h, C.byref(cfg.c), lanes, C.byref(ov) if ov else None, _ptr(out), _ptr(iters),
                                            _ptr(status), C.byref(io)))
         return (out, status, iters) if return_iterations else (out, status)
 
-    def solve_dc_sweep(self, sweep_values, varied_values=None, out=None, cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR):
+    def solve_dc_sweep(self, sweep_values, varied_values=None, out=None, cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR, select=None):
         cfg = cfg or SolverConfig()
         sweep_values = _f64_in(sweep_values, None, "sweep_values")
         if sweep_values.ndim != 1:
             raise ValueError("sweep_values: expected a 1-D array of per-lane source values")
         lanes = int(sweep_values.shape[0])
         varied_values = _f64_in(varied_values, (len(self.varied), lanes) if self.varied else None, "varied_values")
-        out = _check_out(out, _shape(layout, lanes, 1, self.n), False) if out is not None else _like_out(sweep_values, _shape(layout, lanes, 1, self.n), False)
+        cols = self.n if select is None else len(select)
+        out = _check_out(out, _shape(layout, lanes, 1, cols), False) if out is not None else _like_out(sweep_values, _shape(layout, lanes, 1, cols), False)
         status = _like_int(out, lanes)
         ov, _keep = self._ov(varied_values)
-        io = self._io([sweep_values, out, varied_values], layout)
+        io = self._io([sweep_values, out, varied_values], layout, select)
         _check_krb(_lib.lib().krb_solve_dc_sweep(self._h, C.byref(cfg.c), _ptr(sweep_values), lanes, C.byref(ov) if ov else None,
                                                  _ptr(out), _ptr(status), C.byref(io)))
         return out, status
 
     def solve_ac(self, frequencies, varied_values=None, op_solution=None, out=None, cfg: SolverConfig | None = None,
-                 layout=LAYOUT_POINT_MAJOR):
+                 layout=LAYOUT_POINT_MAJOR, select=None):
         cfg = cfg or SolverConfig()
         frequencies = _f64_in(frequencies, None, "frequencies")
         if frequencies.ndim != 1:
             raise ValueError("frequencies: expected a 1-D array")
         lanes = int(frequencies.shape[0])
         varied_values = _f64_in(varied_values, (len(self.varied), lanes) if self.varied else None, "varied_values")
-        out = _check_out(out, _shape(layout, lanes, 1, self.n), True) if out is not None else _like_out(frequencies, _shape(layout, lanes, 1, self.n), True)
+        cols = self.n if select is None else len(select)
+        out = _check_out(out, _shape(layout, lanes, 1, cols), True) if out is not None else _like_out(frequencies, _shape(layout, lanes, 1, cols), True)
         status = _like_int(out, lanes)
         ov, _keep = self._ov(varied_values)
         lanes_op = 0
@@ -478,24 +485,25 @@ class Plan:
                 lanes_op = lanes
             else:
                 raise ValueError(f"op_solution: expected shape ({self.n},) or ({lanes}, {self.n})")
-        io = self._io([frequencies, out, varied_values, op_solution], layout)
+        io = self._io([frequencies, out, varied_values, op_solution], layout, select)
         _check_krb(_lib.lib().krb_solve_ac(self._h, C.byref(cfg.c), _ptr(frequencies), lanes, C.byref(ov) if ov else None,
                                            _ptr(op_solution), lanes_op, _ptr(out), _ptr(status), C.byref(io)))
         return out, status
 
     def solve_transient(self, plan_dc: "Plan", n_steps: int, lanes: int = 1, varied_values=None, out=None,
-                        cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR):
+                        cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR, select=None):
         """self must be a MODE_TRAN plan; plan_dc the MODE_DC plan of the same circuit (row 0 = OP, transient.rs:21)."""
         cfg = cfg or SolverConfig()
         varied_values = _f64_in(varied_values, (len(self.varied), lanes) if self.varied else None, "varied_values")
-        shape = (lanes, n_steps + 1, self.n) if layout == LAYOUT_POINT_MAJOR else (n_steps + 1, self.n, lanes)
+        cols = self.n if select is None else len(select)
+        shape = (lanes, n_steps + 1, cols) if layout == LAYOUT_POINT_MAJOR else (n_steps + 1, cols, lanes)
         if out is None:
             out = _like_out(varied_values, shape, False) if varied_values is not None else np.zeros(shape, dtype=np.float64)
         else:
             _check_out(out, shape, False)
         status = _like_int(out, lanes)
         ov, _keep = self._ov(varied_values)
-        io = self._io([out, varied_values], layout)
+        io = self._io([out, varied_values], layout, select)
         _check_krb(_lib.lib().krb_solve_transient(plan_dc._h, self._h, C.byref(cfg.c), n_steps, lanes, C.byref(ov) if ov else None,
                                                   _ptr(out), _ptr(status), C.byref(io)))
         return out, status

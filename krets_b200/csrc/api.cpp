@@ -206,9 +206,21 @@ int32_t krb_plan_has_step_sections(const krb_plan *p) { return p ? (p->p.has_ste
 static int check_io(const krb_io *io, krb_io &o) {
     krb_default_io(&o);
     if (io) {
-        if (io->struct_size != (int32_t)sizeof(krb_io)) { set_error("krb_io.struct_size mismatch"); return KRB_ERR_INVALID_ARGUMENT; }
-        o = *io;
+        if (io->struct_size == KRB_IO_SIZE_V1) std::memcpy(&o, io, KRB_IO_SIZE_V1);          // callers built against the first layout
+        else if (io->struct_size == (int32_t)sizeof(krb_io)) o = *io;
+        else { set_error("krb_io.struct_size mismatch"); return KRB_ERR_INVALID_ARGUMENT; }
+        o.struct_size = (int32_t)sizeof(krb_io);
     }
+    if (o.n_select < 0 || (o.n_select > 0 && !o.select)) { set_error("krb_io: n_select > 0 needs select"); return KRB_ERR_INVALID_ARGUMENT; }
+    if (o.n_select > 0 && o.layout != KRB_LAYOUT_POINT_MAJOR) { set_error("krb_io: result selection delivers point-major rows only"); return KRB_ERR_UNSUPPORTED; }
+    return KRB_OK;
+}
+static int set_select(const Plan &P, const krb_io &o, RunArgs &a) {
+    a.select = nullptr; a.n_select = 0;
+    if (o.n_select <= 0) return KRB_OK;
+    for (int k = 0; k < o.n_select; k++)
+        if (o.select[k] < 0 || o.select[k] >= P.circuit.n) { set_error("krb_io.select: unknown index out of range"); return KRB_ERR_INVALID_ARGUMENT; }
+    a.select = o.select; a.n_select = o.n_select;
     return KRB_OK;
 }
 static int check_ov(const Plan &P, const krb_overrides *ov, const double **vals) {
@@ -230,6 +242,7 @@ int32_t krb_solve_op(krb_plan *plan_dc, const krb_config *cfg, int64_t lanes, co
     if ((rc = check_ov(plan_dc->p, ov, &a.varied_values))) return rc;
     a.cfg = *cfg; a.lanes = lanes; a.rows = 1; a.x_out = x_out; a.lane_status = lane_status; a.iterations = iterations;
     a.memory = o.memory; a.layout = o.layout; a.stream = o.stream;
+    if ((rc = set_select(plan_dc->p, o, a))) return rc;
     return run_lanes(&plan_dc->p, nullptr, a);
 }
 
@@ -243,6 +256,7 @@ int32_t krb_solve_dc_sweep(krb_plan *plan_dc, const krb_config *cfg, const doubl
     if ((rc = check_ov(plan_dc->p, ov, &a.varied_values))) return rc;
     a.cfg = *cfg; a.lanes = lanes; a.rows = 1; a.lane_param = sweep_values; a.x_out = x_out; a.lane_status = lane_status;
     a.memory = o.memory; a.layout = o.layout; a.stream = o.stream;
+    if ((rc = set_select(plan_dc->p, o, a))) return rc;
     return run_lanes(&plan_dc->p, nullptr, a);
 }
 
@@ -258,6 +272,7 @@ int32_t krb_solve_ac(krb_plan *plan_ac, const krb_config *cfg, const double *fre
     a.cfg = *cfg; a.lanes = lanes; a.rows = 1; a.lane_param = frequencies; a.x_out = x_out; a.lane_status = lane_status;
     a.op_solution = plan_ac->p.circuit.nonlinear ? op_solution : nullptr; a.lanes_op = lanes_op;
     a.memory = o.memory; a.layout = o.layout; a.stream = o.stream;
+    if ((rc = set_select(plan_ac->p, o, a))) return rc;
     return run_lanes(&plan_ac->p, nullptr, a);
 }
 
@@ -275,6 +290,7 @@ int32_t krb_solve_transient(krb_plan *plan_dc, krb_plan *plan_tran, const krb_co
     if ((rc = check_ov(plan_tran->p, ov, &v2))) return rc;
     a.cfg = *cfg; a.lanes = lanes; a.rows = (int)n_steps + 1; a.x_out = x_out; a.lane_status = lane_status;
     a.memory = o.memory; a.layout = o.layout; a.stream = o.stream;
+    if ((rc = set_select(plan_dc->p, o, a))) return rc;
     return run_lanes(&plan_dc->p, &plan_tran->p, a);
 }
 

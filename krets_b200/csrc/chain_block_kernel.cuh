@@ -47,6 +47,8 @@ struct ChainBlockParams {
     int bulk_store;              // deliver with cp.async.bulk (needs unknown_of_row == nullptr; complex: OUT 16-byte aligned)
     const void *E;               // !SD: pre-stamped rows E[lane][M][T][4] = (sub, diag, sup, rhs) written by krb_block_stamp_rows
     const void *U2;              // !SD: U2[lane][T] second super-diagonal of the (at most one) u2 row of each block
+    const int *select;           // extension (krb_io.select): deliver only these unknowns, OUT = x_out[lane][n_select]; needs pivot row k == unknown k
+    int n_select;
 };
 
 // row word .y: bit 1 HAS_U2, bits 2..15 #terms, bits 16..31 slot of a GENERIC row (shared-dictionary mode)
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
 
         // ---- 3. interiors into the result buffer, then ONE bulk asynchronous copy of the lane's vector ----
         // back substitution  x_j = (y^_j - l^_j s_{t-1}) - u^_j x_{j+1} (- u2^_j x_{j+2}),  x_{M-1} = s_t
-        V *__restrict__ out = reinterpret_cast<V *>(p.OUT) + (size_t)lane * (size_t)n;
+        V *__restrict__ out = reinterpret_cast<V *>(p.OUT) + (size_t)lane * (size_t)(p.n_select > 0 ? p.n_select : n);
         // real: the lane's first byte may sit at 8 mod 16; the result buffer is shifted by one element then, so that shared and
         // global addresses stay congruent mod 16 (bulk copies need 16-byte aligned addresses and sizes)
         const int shift = CPLX ? 0 : (int)((reinterpret_cast<size_t>(out) >> 3) & 1);
@@ -637,6 +639,9 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+        } else if (p.n_select > 0) {
+            // extension: only the selected unknowns leave the chip
+            for (int i = t; i < p.n_select; i += T) __stcs(out + i, xv[__ldg(p.select + i)]);
         } else {
             // per-thread delivery (permuted pivot order, or a caller's buffer the bulk copy cannot address): pivot row i is at xv[i],
             // consecutive threads read consecutive elements (conflict-free) and store full-width runs

@@ -56,7 +56,7 @@ struct FrontDevice {
     std::vector<std::vector<FrontLaunch>> factor_launches, solve_launches;   // per level
     long long fw_size = 0;
     int smem_cap = 0;
-    FBuf IN, EV, A, LU, LU0, CB, FW, CBV, BP, ST, XS, status, Bstep, IPIV, DX, ERR;
+    FBuf IN, EV, A, LU, LU0, CB, FW, CBV, BP, ST, XS, status, Bstep, IPIV, DX, ERR, SEL, SELIDX;
     std::vector<double> bstep_host;
     int bstep_rows = -1;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -82,7 +82,7 @@ void front_device_free(FrontDevice *d) {
     void *ptrs[] = {d->fronts, d->list, d->idx_unknown, d->rel, d->child, d->asm_ent, d->asm_pos, d->col_order, d->elems,
                     d->mat_terms, d->rhs_terms, d->mat_ptr, d->rhs_ptr, d->state_elems, d->res_ptr, d->res_ent, d->res_col, d->childrec};
     for (void *p : ptrs) if (p) cudaFree(p);
-    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV, &d->DX, &d->LU0, &d->ERR};
+    FBuf *bufs[] = {&d->IN, &d->EV, &d->A, &d->LU, &d->CB, &d->FW, &d->CBV, &d->BP, &d->ST, &d->XS, &d->status, &d->Bstep, &d->IPIV, &d->DX, &d->LU0, &d->ERR, &d->SEL, &d->SELIDX};
     for (FBuf *b : bufs) b->release();
     for (auto &e : d->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete d;
@@ -343,6 +343,9 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const int n_state = PS ? (int)PS->state_elems.size() : 0;
     if (n == 0 || a.lanes <= 0) return KRB_OK;
     const bool out_dev = (a.memory == KRB_MEM_DEVICE);
+    const int nsel = a.n_select;               // extension (krb_io.select): full rows are solved into XS, a gather compacts them
+    const bool sel = nsel > 0;
+    const bool staged = !out_dev || sel;
 
     if (PS) {   // per-step source table, as in the lane-VM runtime (the reference evaluates sources one step late)
         FrontDevice &DS = *PS->fdev;
@@ -376,7 +379,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const bool refine = P0.fdev->refine_steps > 0 || (PS && PS->fdev->refine_steps > 0);
     const bool verify = P0.fdev->verify || (PS && PS->fdev->verify);
     const size_t persist = (lu_e + a_e + cbv_e + (size_t)n * (refine ? 2 : 1)) * ts + (size_t)n_elems * 8 + (size_t)P0.n_inputs * 8 + (size_t)n_state * 8 +
-                           (size_t)n * 4 + (out_dev ? 0 : (size_t)rows * n * ts) + 64;
+                           (size_t)n * 4 + (staged ? (size_t)rows * n * ts : 0) + (sel && !out_dev ? (size_t)rows * nsel * ts : 0) + 64;
     const size_t work = (cb_e + fw_e + lu0_e) * ts + 64;
     long long chunk = a.chunk_lanes > 0 ? a.chunk_lanes : 2048;
     if (const char *e = getenv("KRB_FRONT_CHUNK")) chunk = std::max(1, atoi(e));   // tests: force several chunks
@@ -412,7 +415,12 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if ((rc = D.IPIV.ensure((size_t)n * chunk * 4))) return rc;
     if (refine && (rc = D.DX.ensure((size_t)n * chunk * ts))) return rc;
     if (verify && (rc = D.ERR.ensure((size_t)chunk * 8))) return rc;
-    if (!out_dev && (rc = D.XS.ensure((size_t)rows * n * chunk * ts))) return rc;
+    if (staged && (rc = D.XS.ensure((size_t)rows * n * chunk * ts))) return rc;
+    if (sel && !out_dev && (rc = D.SEL.ensure((size_t)rows * nsel * chunk * ts))) return rc;
+    if (sel) {
+        if ((rc = D.SELIDX.ensure((size_t)nsel * 4))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(D.SELIDX.p, a.select, (size_t)nsel * 4, cudaMemcpyHostToDevice, st));
+    }
 
     D.events_used = 0;
     set_last_timer(front_sum_event_ms, &D);
@@ -441,7 +449,7 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         }
         CUDA_TRY(cudaMemsetAsync(D.status.p, 0, (size_t)lanes * 4, st));
         if (n_state) CUDA_TRY(cudaMemsetAsync(D.ST.p, 0, (size_t)n_state * lanes * 8, st));   // i_C(0) = 0
-        char *X = out_dev ? (char *)a.x_out + (size_t)lane0 * xls * ts : (char *)D.XS.p;
+        char *X = staged ? (char *)D.XS.p : (char *)a.x_out + (size_t)lane0 * xls * ts;
 
         if (D.events_used == D.events.size()) {
             cudaEvent_t x, y;
@@ -596,8 +604,17 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         }
         // ---- delivery ----
         NvtxRange nvtx_deliver("krb front: deliver");
+        const long long xls_out = (long long)rows * (sel ? nsel : n);
+        if (sel) {
+            void *dst = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * xls_out * ts) : D.SEL.p;
+            const long long points = lanes * rows, work = points * nsel;
+            if (cplx) krb_select_columns<double2><<<(unsigned)((work + 255) / 256), 256, 0, st>>>((const double2 *)D.XS.p, (double2 *)dst, (const int *)D.SELIDX.p, n, nsel, points);
+            else krb_select_columns<double><<<(unsigned)((work + 255) / 256), 256, 0, st>>>((const double *)D.XS.p, (double *)dst, (const int *)D.SELIDX.p, n, nsel, points);
+            add_launches(1);
+            CUDA_TRY(cudaGetLastError());
+        }
         if (!out_dev) {
-            CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * xls * ts, D.XS.p, (size_t)lanes * xls * ts, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * xls_out * ts, sel ? D.SEL.p : D.XS.p, (size_t)lanes * xls_out * ts, cudaMemcpyDeviceToHost, st));
             if (a.lane_status) CUDA_TRY(cudaMemcpyAsync(a.lane_status + lane0, D.status.p, (size_t)lanes * 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         } else if (a.lane_status) {

@@ -89,6 +89,7 @@ struct DeviceState {
     double *B = nullptr;                 // static constant pool (uploaded once: the plan owns a fixed copy of the circuit)
     Buf Bstep, IN, G, XOP, status, iters;
     Buf X[2], packed[2];                 // double-buffered for host delivery
+    Buf selbuf[2], select;               // result selection (krb_io.select): compacted rows, the device copy of the index list
     std::vector<double> bstep_host;
     int bstep_rows = -1;
     cudaStream_t copy_stream = nullptr;
@@ -139,9 +140,9 @@ void device_state_free(DeviceState *d) {
     if (d->dense_rhs) cudaFree(d->dense_rhs);
     if (d->dense_state) cudaFree(d->dense_state);
     if (d->dense_col_order) cudaFree(d->dense_col_order);
-    d->Bstep.release(); d->IN.release(); d->G.release(); d->XOP.release(); d->status.release(); d->iters.release();
+    d->Bstep.release(); d->IN.release(); d->G.release(); d->XOP.release(); d->status.release(); d->iters.release(); d->select.release();
     for (int i = 0; i < 2; i++) {
-        d->X[i].release(); d->packed[i].release();
+        d->X[i].release(); d->packed[i].release(); d->selbuf[i].release();
         if (d->compute_done[i]) cudaEventDestroy(d->compute_done[i]);
         if (d->copy_done[i]) cudaEventDestroy(d->copy_done[i]);
     }
@@ -383,10 +384,18 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const bool chain = P0.use_chain && !PS;
     const int width = n + (PS ? (int)PS->state_elems.size() : 0);   // result-row columns incl. trapezoidal state
     const bool out_dev = (a.memory == KRB_MEM_DEVICE);
+    if (a.n_select > 0 && a.layout != KRB_LAYOUT_POINT_MAJOR) { set_error("result selection delivers point-major rows only"); return KRB_ERR_UNSUPPORTED; }
     // the chain kernel can write point-major results itself when pivot row k is unknown k (no X staging, no pack kernel)
     // block-partitioned chain kernel: one CTA per lane, results delivered point-major from shared memory (any pivot order),
     // no factor planes in HBM.  KRB_CHAIN_SEQ=1 keeps the sequential kernel (tests, A/B measurements).
     const bool block = chain && P0.chain.block.valid && a.layout == KRB_LAYOUT_POINT_MAJOR && rows == 1 && getenv("KRB_CHAIN_SEQ") == nullptr;
+    // result selection (extension): the block kernel writes only the selected unknowns itself when pivot row k is unknown k; every
+    // other path delivers full rows into an internal buffer first and a gather kernel compacts them (device->host traffic shrinks
+    // either way, which is the point)
+    const int nsel = a.n_select;
+    const bool sel = nsel > 0;
+    const bool sel_in_kernel = sel && block && P0.chain.identity_order;
+    const bool sel_gather = sel && !sel_in_kernel;
     const bool direct = block || (chain && P0.chain.identity_order && a.layout == KRB_LAYOUT_POINT_MAJOR && rows == 1);
     // the dense transient kernel delivers point-major rows itself: only the operating-point row is staged in planes
     const bool dense_direct = PS && rows > 1 && PS->dense.valid && a.layout == KRB_LAYOUT_POINT_MAJOR && getenv("KRB_NO_DENSE_TRAN") == nullptr;
@@ -417,7 +426,8 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const bool block_stamped = block && !P0.chain.block.shared_dict;
     const int planes0 = block ? (block_stamped ? P0.chain.block.T * (4 * P0.chain.block.M + 1) : 0) : chain ? 2 * n + P0.chain.n_u2 : P0.n_planes, planesS = PS ? PS->n_planes : 0;
     const int nbuf = out_dev ? 1 : 2;
-    const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)plane_rows * width * ts * (out_dev ? 1 : 2) + (out_dev ? 0 : (size_t)rows * width * ts * 2) +
+    const bool staged = !out_dev || sel_gather;      // full rows are packed into packed[b] before they leave (host copy / gather)
+    const size_t per_lane = (size_t)(planes0 + planesS) * ts + (size_t)plane_rows * width * ts * (out_dev ? 1 : 2) + (staged ? (size_t)rows * width * ts * 2 : 0) +
                             (size_t)P0.n_inputs * 8 + (a.op_solution ? (size_t)n * 8 : 0) + 16;
     long long want = a.chunk_lanes > 0 ? a.chunk_lanes : (out_dev ? 65536 : 16384);
     want = std::min<long long>(want, ((a.lanes + tpb - 1) / tpb) * tpb);
@@ -437,7 +447,12 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if (PS && (rc = PS->dev->G.ensure(std::max<size_t>((size_t)planesS, 1) * chunk * ts))) return rc;
     for (int b = 0; b < nbuf; b++) {
         if (!direct && (rc = D0.X[b].ensure((size_t)plane_rows * width * chunk * ts))) return rc;
-        if (!out_dev && (rc = D0.packed[b].ensure((size_t)rows * n * chunk * ts))) return rc;
+        if (staged && !sel_in_kernel && (rc = D0.packed[b].ensure((size_t)rows * n * chunk * ts))) return rc;
+        if (sel && !out_dev && (rc = D0.selbuf[b].ensure((size_t)rows * nsel * chunk * ts))) return rc;
+    }
+    if (sel) {
+        if ((rc = D0.select.ensure((size_t)nsel * 4))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(D0.select.p, a.select, (size_t)nsel * 4, cudaMemcpyHostToDevice, (cudaStream_t)a.stream));
     }
     if ((rc = D0.status.ensure((size_t)chunk * 4 * 2))) return rc;
     if (a.iterations && (rc = D0.iters.ensure((size_t)chunk * 4 * 2))) return rc;
@@ -530,11 +545,14 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             c.unknown_of_row = P0.chain.identity_order ? nullptr : D0.chain_unknown;
             c.IN = IN; c.lanes = lanes; c.L = Lpad; c.n = n; c.input_freq = P0.input_freq; c.status = status_d;
             c.gen_rows = D0.block_gen; c.n_dict = P0.chain.block.n_dict; c.n_gen = (int)P0.chain.block.gen_rows.size();
-            c.OUT = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p;
+            if (sel_in_kernel) {          // compact rows straight from the kernel
+                c.OUT = out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)nsel * ts) : D0.selbuf[b].p;
+                c.select = (const int *)D0.select.p; c.n_select = nsel;
+            } else c.OUT = (out_dev && !sel_gather) ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p;
             // one bulk asynchronous copy per lane (TMA engine) when pivot row k is unknown k; complex results need a 16-byte aligned
             // buffer (real ones are handled at any 8-byte alignment).  KRB_BLOCK_NO_BULK=1: per-thread stores (A/B measurements)
             static const bool no_bulk = getenv("KRB_BLOCK_NO_BULK") != nullptr;
-            c.bulk_store = (P0.chain.identity_order && !no_bulk && (!cplx || ((size_t)c.OUT & 15u) == 0)) ? 1 : 0;
+            c.bulk_store = (P0.chain.identity_order && !sel_in_kernel && !no_bulk && (!cplx || ((size_t)c.OUT & 15u) == 0)) ? 1 : 0;
             if (block_stamped) {
                 // (a) stamping as its own launch: thread per (pivot row, lane), coalesced inputs, records transposed to lane-major
                 const int T = P0.chain.block.T, M = P0.chain.block.M;
@@ -557,7 +575,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             c.u2_rows = D0.chain_u2_rows; c.out_lanes = lanes; c.runs = D0.chain_runs; c.n_runs = (int)P0.chain.runs.size();
             { const char *dbg = getenv("KRB_CHAIN_DEBUG"); c.debug = dbg ? atoi(dbg) : 0; }
             { const char *pf = getenv("KRB_CHAIN_PF"); c.pf_units = pf ? atoi(pf) : 256; }
-            c.OUT = direct ? (out_dev ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p) : nullptr;
+            c.OUT = direct ? ((out_dev && !sel_gather) ? (void *)((char *)a.x_out + (size_t)lane0 * (size_t)n * ts) : D0.packed[b].p) : nullptr;
             if ((rc = launch_chain(cplx, tpb, direct, c, Lpad, st))) return rc;
         } else {
             VmParams p{};
@@ -586,7 +604,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
                 q.IN = IN; q.Bstep = (const double *)DS.Bstep.p; q.X = (double *)D0.X[b].p; q.L = Lpad; q.rows = rows;
                 q.h_comp = PS->h_comp; q.status = status_d;
                 q.propagate = getenv("KRB_DENSE_TRAN_LU") == nullptr;      // default: per-lane propagator steps
-                q.OUT = dense_direct ? (out_dev ? (double *)a.x_out + (size_t)lane0 * (size_t)rows * n : (double *)D0.packed[b].p) : nullptr;
+                q.OUT = dense_direct ? ((out_dev && !sel_gather) ? (double *)a.x_out + (size_t)lane0 * (size_t)rows * n : (double *)D0.packed[b].p) : nullptr;
                 q.out_lanes = lanes;
                 if ((rc = launch_dense(q, Lpad, st))) return rc;
             } else if (PS && rows > 1) {
@@ -611,16 +629,32 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         // ---- delivery ----
         NvtxRange nvtx_deliver("krb lanes: deliver (pack / D2H)");
         const size_t per_point = (size_t)rows * n;
+        const size_t per_point_out = (size_t)rows * (sel ? nsel : n);
+        auto pack_full = [&](void *dst) -> int {      // plane-staged results -> point-major full rows
+            dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)rows), block(32, 8);
+            if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)dst, rows, n, width, Lpad, lanes);
+            else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)dst, rows, n, width, Lpad, lanes);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+            return KRB_OK;
+        };
+        auto gather_selected = [&](void *dst) -> int {   // packed[b] (full rows) -> compact rows
+            const long long points = lanes * rows, work = points * nsel;
+            if (cplx) krb_select_columns<double2><<<(unsigned)((work + 255) / 256), 256, 0, st>>>((const double2 *)D0.packed[b].p, (double2 *)dst, (const int *)D0.select.p, n, nsel, points);
+            else krb_select_columns<double><<<(unsigned)((work + 255) / 256), 256, 0, st>>>((const double *)D0.packed[b].p, (double *)dst, (const int *)D0.select.p, n, nsel, points);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+            return KRB_OK;
+        };
+        const bool kernel_delivered = direct || dense_direct;   // the kernel wrote point-major rows itself (caller's buffer, packed[b] or selbuf[b])
         if (out_dev) {
-            if (direct || dense_direct) {
+            if (sel_gather) {
+                if (!kernel_delivered && (rc = pack_full(D0.packed[b].p))) return rc;
+                if ((rc = gather_selected((char *)a.x_out + (size_t)lane0 * per_point_out * ts))) return rc;
+            } else if (kernel_delivered) {
                 // already delivered by the kernel
             } else if (a.layout == KRB_LAYOUT_POINT_MAJOR) {
-                void *dst = (char *)a.x_out + (size_t)lane0 * per_point * ts;
-                dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)rows), block(32, 8);
-                if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)dst, rows, n, width, Lpad, lanes);
-                else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)dst, rows, n, width, Lpad, lanes);
-                g_launches++;
-                CUDA_TRY(cudaGetLastError());
+                if ((rc = pack_full((char *)a.x_out + (size_t)lane0 * per_point * ts))) return rc;
             } else {
                 for (int rr = 0; rr < (width == n ? 1 : rows); rr++)   // state columns are skipped row by row
                     CUDA_TRY(cudaMemcpy2DAsync((char *)a.x_out + ((size_t)rr * n * a.lanes + (size_t)lane0) * ts, (size_t)a.lanes * ts, (char *)D0.X[b].p + (size_t)rr * width * Lpad * ts,
@@ -630,17 +664,12 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             if (a.iterations) CUDA_TRY(cudaMemcpyAsync(a.iterations + lane0, iters_d, (size_t)lanes * 4, cudaMemcpyDeviceToDevice, st));
         } else {
             cudaStream_t cs = D0.copy_stream;
-            if (a.layout == KRB_LAYOUT_POINT_MAJOR && !direct && !dense_direct) {
-                dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)rows), block(32, 8);
-                if (cplx) krb_pack_point_major<double2><<<grid, block, 0, st>>>((const double2 *)D0.X[b].p, (double2 *)D0.packed[b].p, rows, n, width, Lpad, lanes);
-                else krb_pack_point_major<double><<<grid, block, 0, st>>>((const double *)D0.X[b].p, (double *)D0.packed[b].p, rows, n, width, Lpad, lanes);
-                g_launches++;
-                CUDA_TRY(cudaGetLastError());
-            }
+            if (a.layout == KRB_LAYOUT_POINT_MAJOR && !kernel_delivered && (rc = pack_full(D0.packed[b].p))) return rc;
+            if (sel_gather && (rc = gather_selected(D0.selbuf[b].p))) return rc;
             CUDA_TRY(cudaEventRecord(D0.compute_done[b], st));
             CUDA_TRY(cudaStreamWaitEvent(cs, D0.compute_done[b], 0));
             if (a.layout == KRB_LAYOUT_POINT_MAJOR)
-                CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * per_point * ts, D0.packed[b].p, (size_t)lanes * per_point * ts, cudaMemcpyDeviceToHost, cs));
+                CUDA_TRY(cudaMemcpyAsync((char *)a.x_out + (size_t)lane0 * per_point_out * ts, sel ? D0.selbuf[b].p : D0.packed[b].p, (size_t)lanes * per_point_out * ts, cudaMemcpyDeviceToHost, cs));
             else
                 for (int rr = 0; rr < (width == n ? 1 : rows); rr++)
                     CUDA_TRY(cudaMemcpy2DAsync((char *)a.x_out + ((size_t)rr * n * a.lanes + (size_t)lane0) * ts, (size_t)a.lanes * ts, (char *)D0.X[b].p + (size_t)rr * width * Lpad * ts,

@@ -31,6 +31,8 @@ struct RunArgs {
     int memory = KRB_MEM_HOST, layout = KRB_LAYOUT_POINT_MAJOR;
     void *stream = nullptr;
     long long chunk_lanes = 0;
+    const int32_t *select = nullptr;     // extension: deliver only these unknowns (host pointer), n_select of them per point
+    int n_select = 0;
 };
 
 void set_error(const std::string &s);

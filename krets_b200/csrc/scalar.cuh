@@ -58,4 +58,14 @@ template <> struct Sc<true> {
     static __device__ __forceinline__ bool finite(T a) { return isfinite(a.x) && isfinite(a.y); }
 };
 
+// result selection (extension, krb_io.select): out[point][k] = x[point][select[k]], point = (lane, row)
+template <typename V>
+__global__ void krb_select_columns(const V *__restrict__ x, V *__restrict__ out, const int *__restrict__ select, int n, int n_select, long long points) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < points * n_select) {
+        const long long pt = i / n_select;
+        out[i] = x[pt * n + __ldg(select + (int)(i - pt * n_select))];
+    }
+}
+
 }  // namespace krb

@@ -44,3 +44,64 @@ def solve_sharded(total_lanes: int, solve_shard: Callable[[int, int], "torch.Ten
     if rank != gather_to:
         return local
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+
+
+def solve_sharded_chunked(total_lanes: int, solve_chunk: Callable[[int, int, "torch.Tensor"], None], *, chunk_lanes: int, row_shape, dtype,
+                          device="cpu", gather_to: Optional[int] = None):
+    """Chunk-pipelined sharded sweep.  This rank's contiguous lane block is solved chunk by chunk:
+    `solve_chunk(lo, hi, out)` fills `out[0:hi-lo]` (shape [hi-lo, *row_shape]) with the results of the global lanes [lo, hi).
+
+    gather_to=None (the default): results stay sharded on their GPUs — returns (local_lo, local_results); nothing crosses NVLink.
+    gather_to=r: every chunk is sent to rank r as soon as it is solved (dist.isend: ncclSend on NCCL's stream / gloo on CPU) while the
+    next chunk is being solved into the other buffer; the root posts the matching receives of one chunk round as ONE grouped
+    operation (dist.batch_isend_irecv: ncclGroupStart/End) straight into the final [total_lanes, *row_shape] array, so the
+    transfers of all ranks run concurrently and overlap the root's own chunk.  Returns (0, full) on the root, (local_lo, None) elsewhere.
+    """
+    import torch
+    import torch.distributed as dist
+
+    row_shape = tuple(row_shape)
+    if not (dist.is_available() and dist.is_initialized()):
+        world, rank = 1, 0
+    else:
+        world, rank = dist.get_world_size(), dist.get_rank()
+    lo, hi = shard_bounds(total_lanes, world, rank)
+
+    def chunks(a, b):
+        return [(c, min(c + chunk_lanes, b)) for c in range(a, b, chunk_lanes)]
+
+    if gather_to is None or world == 1:
+        local = torch.empty((hi - lo,) + row_shape, dtype=dtype, device=device)
+        for c0, c1 in chunks(lo, hi):
+            solve_chunk(c0, c1, local[c0 - lo:c1 - lo])
+        return lo, local
+    if rank == gather_to:
+        full = torch.empty((total_lanes,) + row_shape, dtype=dtype, device=device)
+        remote = {r: chunks(*shard_bounds(total_lanes, world, r)) for r in range(world) if r != rank}
+        mine = chunks(lo, hi)
+        rounds = max([len(mine)] + [len(v) for v in remote.values()])
+        pending = []
+        for k in range(rounds):
+            ops = [dist.P2POp(dist.irecv, full[v[k][0]:v[k][1]], r) for r, v in remote.items() if k < len(v)]
+            if ops:
+                pending += dist.batch_isend_irecv(ops)
+            if k < len(mine):
+                solve_chunk(mine[k][0], mine[k][1], full[mine[k][0]:mine[k][1]])
+        for req in pending:
+            req.wait()
+        return 0, full
+    bufs = [torch.empty((min(chunk_lanes, max(hi - lo, 1)),) + row_shape, dtype=dtype, device=device) for _ in range(2)]
+    reqs = [None, None]
+    for k, (c0, c1) in enumerate(chunks(lo, hi)):
+        b = k & 1
+        if reqs[b] is not None:
+            for req in reqs[b]:
+                req.wait()                     # the send that last used this buffer has completed
+        out = bufs[b][: c1 - c0]
+        solve_chunk(c0, c1, out)
+        reqs[b] = dist.batch_isend_irecv([dist.P2POp(dist.isend, out, gather_to)])
+    for rq in reqs:
+        if rq is not None:
+            for req in rq:
+                req.wait()
+    return lo, None

@@ -22,7 +22,7 @@ _Static_assert(sizeof(krb_element) == 112 && offsetof(krb_element, value) == 24 
 _Static_assert(sizeof(krb_config) == 32 && offsetof(krb_config, maximum_iterations) == 24, "krb_config layout");
 _Static_assert(sizeof(krb_plan_opts) == 56 && offsetof(krb_plan_opts, time_step) == 16 && offsetof(krb_plan_opts, varied_elements) == 40 &&
                offsetof(krb_plan_opts, refine_steps) == 52, "krb_plan_opts layout");
-_Static_assert(sizeof(krb_io) == 24 && offsetof(krb_io, stream) == 16, "krb_io layout");
+_Static_assert(sizeof(krb_io) == 40 && offsetof(krb_io, stream) == 16 && offsetof(krb_io, select) == 24 && offsetof(krb_io, n_select) == 32, "krb_io layout");
 _Static_assert(sizeof(krb_overrides) == 16 && offsetof(krb_overrides, values) == 8, "krb_overrides layout");
 _Static_assert(sizeof(krb_plan_info) == 72 && offsetof(krb_plan_info, program_ops) == 32 && offsetof(krb_plan_info, executor) == 64, "krb_plan_info layout");
 
@@ -40,7 +40,7 @@ static int layout(void) {
     BEGIN(krb_plan_opts); F(krb_plan_opts, struct_size); F(krb_plan_opts, exec); F(krb_plan_opts, integrator); F(krb_plan_opts, scratch_slots);
     F(krb_plan_opts, time_step); F(krb_plan_opts, nominal_frequency); F(krb_plan_opts, sweep_element); F(krb_plan_opts, n_varied);
     F(krb_plan_opts, varied_elements); F(krb_plan_opts, threads_per_block); F(krb_plan_opts, refine_steps); END();
-    BEGIN(krb_io); F(krb_io, struct_size); F(krb_io, memory); F(krb_io, layout); F(krb_io, reserved); F(krb_io, stream); END();
+    BEGIN(krb_io); F(krb_io, struct_size); F(krb_io, memory); F(krb_io, layout); F(krb_io, reserved); F(krb_io, stream); F(krb_io, select); F(krb_io, n_select); F(krb_io, reserved2); END();
     BEGIN(krb_overrides); F(krb_overrides, n_varied); F(krb_overrides, reserved); F(krb_overrides, values); END();
     printf("\n}\n");
     return 0;

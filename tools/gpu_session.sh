@@ -21,8 +21,11 @@ try:
     r = d['roofline']
     print('headline: ms/step %.4f  value %.4g  kernel_ms %.4f  frac %.3f  frac_alg %.2f  e2e %s  parity %s' % (
         d['ms_per_step'], d['value'], r['kernel_ms'], r['frac'], r['frac_alg_model'], (d.get('e2e') or {}).get('value'), d.get('parity_spot_check')))
+    print('e2e:', {k: v for k, v in (d.get('e2e') or {}).items() if k in ('value', 'd2h_GBps', 'link_ceiling_GBps', 'frac_of_link_ceiling', 'selected')})
+    if d.get('gather'): print('gather:', d['gather'])
     for o in d.get('other_configs', []):
         if 'error' in o: print('  ', o['name'], 'ERROR', o['error']); continue
+        if 'roofline' not in o: print('   %-16s %s' % (o['name'], {k: v for k, v in o.items() if k not in ('workload', 'name')})); continue
         print('   %-16s ms/step %10.3f  value %.4g  frac %.3f  status %d  parity %s' % (o['name'], o['ms_per_step'], o['value'], o['roofline']['frac'], o['lanes_with_status'], o.get('parity_spot_check')))
 except Exception as e:
     print('bench parse error', e); print(open(f'gpurun_out/{tag}_bench.err').read()[-1500:])
