@@ -38,7 +38,7 @@ struct FBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
-struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int slot_elems; };
+struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int slot_elems; int stage_fwd = 0, stage_bwd = 0; };
 }  // namespace
 
 struct FrontDevice {
@@ -158,6 +158,25 @@ static int upload_front(Plan &plan) {
             L.slot_elems = m0 + nt;
             L.block = L.warp ? dim3(32, 16) : dim3(nt);      // WARP mode: 16 independent (front, lane) pairs per CTA, 64 warps per SM
             L.smem = (size_t)L.slot_elems * ts * (L.warp ? 16 : 1);
+            // staging of the factor block in shared memory (front_kernels.cuh: front_stage): largest block of the launch, when 16
+            // (WARP mode: at least 8) slots of it still fit a CTA; KRB_FRONT_NO_STAGE=1 switches it off (A/B)
+            if (getenv("KRB_FRONT_NO_STAGE") == nullptr) {
+                long long sf = 0, sb = 0;
+                for (int k = i; k < j; k++) {
+                    const int f = fp.level_fronts[k];
+                    const long long pp = fp.piv0[f + 1] - fp.piv0[f], qq = fp.idx_ptr[f + 1] - fp.idx_ptr[f];
+                    sf = std::max(sf, (pp + qq) * pp);
+                    sb = std::max(sb, (pp + qq) * pp + pp * qq);
+                }
+                const size_t budget = L.warp ? (size_t)96 * 1024 : (size_t)72 * 1024;     // per CTA
+                auto fits = [&](long long e, int slots) { return ((size_t)L.slot_elems + (size_t)e) * ts * slots <= budget; };
+                if (L.warp) {
+                    // fewer warps per CTA when the blocks are large: 16, 8 or 4 slots
+                    int slots = 16;
+                    while (slots > 4 && !fits(sb, slots)) slots /= 2;
+                    if (fits(sb, slots)) { L.block = dim3(32, slots); L.stage_fwd = (int)sf; L.stage_bwd = (int)sb; }
+                } else if (fits(sb, 1)) { L.stage_fwd = (int)sf; L.stage_bwd = (int)sb; }
+            }
             D.solve_launches[l].push_back(L);
             i = j;
         }
@@ -235,6 +254,10 @@ static int upload_front(Plan &plan) {
     CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     D.uploaded = true;
     return KRB_OK;
 }
@@ -280,16 +303,21 @@ template <bool FWD>
 static void launch_solve(const Plan &plan, const FrontLaunch &L, FrontParams Q, long long lanes, cudaStream_t st) {
     const size_t ts = plan.is_complex ? 16 : 8;
     Q.lanes = lanes;
+    const int stage = FWD ? L.stage_fwd : L.stage_bwd;
+    Q.stage_off = stage > 0 ? ((L.slot_elems + 1) & ~1) : 0;             // 16-byte aligned for the complex copies
+    const int slot = stage > 0 ? Q.stage_off + stage : L.slot_elems;
     if (L.warp) {
-        Q.smem_elems = L.slot_elems;
+        Q.smem_elems = slot;
+        const size_t smem = (size_t)slot * ts * L.block.y;
         dim3 grid((unsigned)L.count, (unsigned)((lanes + L.block.y - 1) / L.block.y));
-        if (plan.is_complex) { if (FWD) krb_front_forward<true, true><<<grid, L.block, L.smem, st>>>(Q); else krb_front_backward<true, true><<<grid, L.block, L.smem, st>>>(Q); }
-        else { if (FWD) krb_front_forward<false, true><<<grid, L.block, L.smem, st>>>(Q); else krb_front_backward<false, true><<<grid, L.block, L.smem, st>>>(Q); }
+        if (plan.is_complex) { if (FWD) krb_front_forward<true, true><<<grid, L.block, smem, st>>>(Q); else krb_front_backward<true, true><<<grid, L.block, smem, st>>>(Q); }
+        else { if (FWD) krb_front_forward<false, true><<<grid, L.block, smem, st>>>(Q); else krb_front_backward<false, true><<<grid, L.block, smem, st>>>(Q); }
     } else {
-        Q.smem_elems = (int)(L.smem / ts);
+        const size_t smem = (size_t)slot * ts;
+        Q.smem_elems = slot;
         dim3 grid((unsigned)L.count, (unsigned)lanes);
-        if (plan.is_complex) { if (FWD) krb_front_forward<true, false><<<grid, L.block, L.smem, st>>>(Q); else krb_front_backward<true, false><<<grid, L.block, L.smem, st>>>(Q); }
-        else { if (FWD) krb_front_forward<false, false><<<grid, L.block, L.smem, st>>>(Q); else krb_front_backward<false, false><<<grid, L.block, L.smem, st>>>(Q); }
+        if (plan.is_complex) { if (FWD) krb_front_forward<true, false><<<grid, L.block, smem, st>>>(Q); else krb_front_backward<true, false><<<grid, L.block, smem, st>>>(Q); }
+        else { if (FWD) krb_front_forward<false, false><<<grid, L.block, smem, st>>>(Q); else krb_front_backward<false, false><<<grid, L.block, smem, st>>>(Q); }
     }
     add_launches(1);
 }

@@ -57,6 +57,8 @@ struct FrontParams {
     int *IPIV;                // [lanes][n] row chosen for pivot k inside its front (local row index; == k when no swap)
     void *X;                  // result rows, point-major: X[lane * x_lane_stride + x_row_off + unknown]
     long long x_lane_stride, x_row_off;
+    int stage_off;            // solves: > 0 = the front's factor block is first copied to shared memory (cp.async, every load in flight at
+                              // once: ONE memory round trip per front instead of one per 8-column group) at this offset of the slot
 };
 
 struct FrontStampParams {
@@ -546,6 +548,16 @@ __device__ __forceinline__ void front_prefetch(const void *base, size_t bytes, i
     const size_t cap = lines < (size_t)nt * 2 ? lines : (size_t)nt * 2;
     for (size_t i = tid; i < cap; i += nt) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + i * 128));
 }
+// asynchronous global -> shared copy of `count` elements (8 or 16 bytes each); completion: front_stage_wait + front_sync
+template <typename T>
+__device__ __forceinline__ void front_stage(T *dst, const T *src, int count, int tid, int nt) {
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+    for (int i = tid; i < count; i += nt) {
+        if (sizeof(T) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)i * 16u), "l"(src + i) : "memory");
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + (uint32_t)i * 8u), "l"(src + i) : "memory");
+    }
+}
+__device__ __forceinline__ void front_stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <bool WARP> __device__ __forceinline__ void front_sync() { if (WARP) __syncwarp(); else __syncthreads(); }
 template <bool WARP> __device__ __forceinline__ int front_any(int pred) { return WARP ? __any_sync(0xffffffffu, pred) : __syncthreads_or(pred); }
 __device__ __forceinline__ double front_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -567,7 +579,10 @@ __global__ void krb_front_forward(const FrontParams P) {
     T *BP = reinterpret_cast<T *>(P.BP) + lane * P.n;
     T *CBV = reinterpret_cast<T *>(P.CBV) + lane * P.cbv_stride;
     const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
-    front_prefetch(L, (size_t)m * p * sizeof(T), tid, NT);      // the factor block streams in while the children are gathered
+    if (P.stage_off > 0) {                                      // the whole m x p block: one round trip, overlapped with the gather below
+        front_stage(w + P.stage_off, L, m * p, tid, NT);
+        L = w + P.stage_off;
+    } else front_prefetch(L, (size_t)m * p * sizeof(T), tid, NT);      // the factor block streams in while the children are gathered
     for (int i = tid; i < m; i += NT) w[i] = i < p ? BP[d.piv0 + i] : S::zero();
     front_sync<WARP>();
     for (int ci = d.child_begin; ci < d.child_end; ci++) {
@@ -586,6 +601,7 @@ __global__ void krb_front_forward(const FrontParams P) {
             front_sync<WARP>();
         }
     }
+    if (P.stage_off > 0) { front_stage_wait(); front_sync<WARP>(); }
     for (int kb = 0; kb < p; kb += 32) {
         const int nbk = (p - kb) < 32 ? (p - kb) : 32;
         if (tid < 32) {
@@ -642,8 +658,12 @@ __global__ void krb_front_backward(const FrontParams P) {
     const T *BP = reinterpret_cast<const T *>(P.BP) + lane * P.n;
     T *X = reinterpret_cast<T *>(P.X) + lane * P.x_lane_stride + P.x_row_off;
     const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
-    front_prefetch(L, ((size_t)m * p + (size_t)p * q) * sizeof(T), tid, NT);
+    if (P.stage_off > 0) {                                      // L block + U12, contiguous in the factor store
+        front_stage(w + P.stage_off, L, m * p + p * q, tid, NT);
+        L = w + P.stage_off;
+    } else front_prefetch(L, ((size_t)m * p + (size_t)p * q) * sizeof(T), tid, NT);
     for (int i = tid; i < m; i += NT) w[i] = i < p ? BP[d.piv0 + i] : X[P.idx_unknown[d.idx_off + (i - p)]];
+    if (P.stage_off > 0) front_stage_wait();
     front_sync<WARP>();
     const T *U12 = L + (size_t)m * p;
     if (q > 0) {
