@@ -658,9 +658,21 @@ __global__ void krb_front_backward(const FrontParams P) {
     const T *BP = reinterpret_cast<const T *>(P.BP) + lane * P.n;
     T *X = reinterpret_cast<T *>(P.X) + lane * P.x_lane_stride + P.x_row_off;
     const T *L = reinterpret_cast<const T *>(P.LU) + lane * P.lu_stride + d.lu_off;
-    if (P.stage_off > 0) {                                      // L block + U12, contiguous in the factor store
-        front_stage(w + P.stage_off, L, m * p + p * q, tid, NT);
-        L = w + P.stage_off;
+    if (P.stage_off > 0) {
+        // what the backward pass reads: the top p rows of the m x p block (U11 with the reciprocal pivots) and U12 (p x q, contiguous
+        // behind the block); the L21 rows below are not touched (half of a leaf front's block)
+        T *Ls = w + P.stage_off;
+        if (q > 0 && p < m) {
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(Ls);
+            for (int e = tid; e < p * p; e += NT) {
+                const int k = e / p, r = e - k * p;
+                const uint32_t off = (uint32_t)(r + m * k);
+                if (sizeof(T) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + off * 16u), "l"(L + off) : "memory");
+                else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + off * 8u), "l"(L + off) : "memory");
+            }
+            front_stage(Ls + m * p, L + (size_t)m * p, p * q, tid, NT);
+        } else front_stage(Ls, L, m * p + p * q, tid, NT);
+        L = Ls;
     } else front_prefetch(L, ((size_t)m * p + (size_t)p * q) * sizeof(T), tid, NT);
     for (int i = tid; i < m; i += NT) w[i] = i < p ? BP[d.piv0 + i] : X[P.idx_unknown[d.idx_off + (i - p)]];
     if (P.stage_off > 0) front_stage_wait();
