@@ -38,7 +38,7 @@ struct FBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
-struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int slot_elems; int stage_fwd = 0, stage_bwd = 0; };
+struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int slot_elems; int stage_fwd = 0, stage_bwd = 0; bool ll = false; };
 }  // namespace
 
 struct FrontDevice {
@@ -109,6 +109,8 @@ static int upload_front(Plan &plan) {
     while ((size_t)(m_smem + 1) * ((m_smem + 1) | 1) * ts <= (size_t)D.smem_cap) m_smem++;
     if (const char *e = getenv("KRB_FRONT_SMEM_M")) m_smem = std::max(1, std::min(m_smem, atoi(e)));
     const int nf = fp.n_fronts;
+    const bool use_ll = !(getenv("KRB_FRONT_LL") && getenv("KRB_FRONT_LL")[0] == '0');
+    const bool use_warpf = !(getenv("KRB_FRONT_WARPF") && getenv("KRB_FRONT_WARPF")[0] == '0');
     std::vector<FrontDesc> desc(nf);
     D.fw_size = 0;
     auto msize = [&](int f) { return (fp.piv0[f + 1] - fp.piv0[f]) + (fp.idx_ptr[f + 1] - fp.idx_ptr[f]); };
@@ -123,7 +125,9 @@ static int upload_front(Plan &plan) {
         d.lu_off = fp.lu_off[f]; d.cb_off = fp.cb_off[f];
         d.cbv_off = (int)fp.cbv_off[f]; d.pad = 0;
         const long long m = d.p + d.q;
-        if (m > m_smem) { d.fw_off = D.fw_size; D.fw_size += ((m * m + 1) / 2) * 2; }
+        // fronts beyond shared memory: left-looking by resident column blocks (krb_front_factor_ll, no workspace) up to 512 rows,
+        // above that the blocked right-looking kernel on a per-lane workspace; KRB_FRONT_LL=0 (A/B) sends all of them there
+        if (m > m_smem && (m > 512 || !use_ll)) { d.fw_off = D.fw_size; D.fw_size += ((m * m + 1) / 2) * 2; }
         else d.fw_off = -1;
     }
     // launch lists: each level's fronts are sorted by size (largest first); cut them into size classes
@@ -131,7 +135,13 @@ static int upload_front(Plan &plan) {
     D.solve_launches.assign(fp.n_levels, {});
     for (int l = 0; l < fp.n_levels; l++) {
         const int b = fp.level_ptr[l], e = fp.level_ptr[l + 1];
-        auto fclass = [&](int m) { return m > m_smem ? 0 : m > 96 ? 1 : m > 48 ? 2 : m > 16 ? 3 : 4; };
+        // size classes: -1 left-looking (beyond shared memory), 0 blocked on the workspace, 1..4 CTA per front in shared memory,
+        // 5..7 one warp per front (m <= 32; KRB_FRONT_WARPF=0 (A/B) keeps them on classes 3 / 4)
+        auto fclass = [&](int m) {
+            if (m > m_smem) return (m <= 512 && use_ll) ? -1 : 0;
+            if (use_warpf && m <= 32) return m > 24 ? 5 : m > 16 ? 6 : 7;
+            return m > 96 ? 1 : m > 48 ? 2 : m > 16 ? 3 : 4;
+        };
         auto sclass = [&](int m) { return m > 192 ? 0 : m > 64 ? 1 : 2; };
         for (int i = b; i < e;) {
             const int m0 = msize(fp.level_fronts[i]);
@@ -143,6 +153,14 @@ static int upload_front(Plan &plan) {
             L.block = c <= 1 ? dim3(32, 16) : c == 2 ? dim3(16, 16) : c == 3 ? dim3(16, 8) : dim3(8, 8);
             L.smem = c == 0 ? std::min<size_t>((size_t)D.smem_cap, ((size_t)2 * m0 * 32 + m0) * ts) : (size_t)m0 * (m0 | 1) * ts;
             L.warp = false; L.slot_elems = 0;
+            if (c < 0) { L.ll = true; L.smem = (size_t)D.smem_cap; }
+            if (c >= 5) {   // warp per (front, lane): 8 pairs per CTA while four CTAs still fit an SM, else 4
+                L.warp = true;
+                L.slot_elems = m0 * (m0 | 1);
+                const int wpb = (size_t)L.slot_elems * ts * 8 <= (size_t)56 * 1024 ? 8 : 4;
+                L.block = dim3(32, wpb);
+                L.smem = (size_t)L.slot_elems * ts * wpb;
+            }
             D.factor_launches[l].push_back(L);
             i = j;
         }
@@ -250,6 +268,10 @@ static int upload_front(Plan &plan) {
     if (const char *e = getenv("KRB_FRONT_REFINE")) D.refine_steps = std::max(0, atoi(e));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
@@ -291,7 +313,15 @@ static int front_factor(const Plan &plan, FrontParams P, long long lanes, cudaSt
             Q.lanes = lanes;
             dim3 grid((unsigned)L.count, (unsigned)lanes);
             const bool small = L.block.x * L.block.y <= 128;
-            if (plan.is_complex) { if (small) krb_front_factor<true, 2><<<grid, L.block, L.smem, st>>>(Q); else krb_front_factor<true, 4><<<grid, L.block, L.smem, st>>>(Q); }
+            if (L.ll) {
+                if (plan.is_complex) krb_front_factor_ll<true><<<grid, dim3(32, 16), L.smem, st>>>(Q);
+                else krb_front_factor_ll<false><<<grid, dim3(32, 16), L.smem, st>>>(Q);
+            } else if (L.warp) {
+                Q.smem_elems = L.slot_elems;
+                dim3 gw((unsigned)L.count, (unsigned)((lanes + L.block.y - 1) / L.block.y));
+                if (plan.is_complex) krb_front_factor_warp<true><<<gw, L.block, L.smem, st>>>(Q);
+                else krb_front_factor_warp<false><<<gw, L.block, L.smem, st>>>(Q);
+            } else if (plan.is_complex) { if (small) krb_front_factor<true, 2><<<grid, L.block, L.smem, st>>>(Q); else krb_front_factor<true, 4><<<grid, L.block, L.smem, st>>>(Q); }
             else { if (small) krb_front_factor<false, 2><<<grid, L.block, L.smem, st>>>(Q); else krb_front_factor<false, 4><<<grid, L.block, L.smem, st>>>(Q); }
             add_launches(1);
         }

@@ -208,6 +208,9 @@ template <> struct FrontAbs<true> {
     static constexpr double THRESH = 64.0;
 };
 
+__device__ __forceinline__ double front_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double2 front_shfl(double2 v, int src) { return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
+
 // warp 0 scans col[k+1 .. p) (unit stride) and publishes the chosen row in *s_ip
 template <bool CPLX, typename T>
 __device__ __forceinline__ void front_pivot_search(const T *col, int k, int p, int tid, int *s_ip) {
@@ -475,6 +478,512 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
     if (grow >= KRB_GROWTH_KEY && grow < KRB_NONFINITE_KEY && P.status) atomicOr(P.status + lane, KRB_LANE_INACCURATE);
 }
 
+// ---- (b') left-looking factorisation of a LARGE front: one column block at a time resident in shared memory --------------------
+// Fronts that do not fit shared memory used to live in a per-lane global workspace whose trailing block was re-read and re-written
+// once per 15-column panel (a 451 x 451 complex front moved 27x its size through DRAM: ncu r1, 26 % of the DRAM peak with the FP64
+// pipe 25 % active).  Here the front is processed by column blocks of W columns (m x W resident in shared memory, W = 51 real /
+// 29 complex for m = 451):
+//   for each block J:   assemble its columns straight into shared memory (stamped entries + the children's contribution-block
+//                       columns that land in it: no global workspace at all)
+//                       apply the interchanges of all earlier pivots
+//                       for each earlier pivot panel K:  U_KJ = L_KK^-1 C_K  (8 lanes per column, warp-synchronous)
+//                                                        C_below -= L_below,K U_KJ  on the FP64 tensor cores (DMMA m8n8k4; complex =
+//                                                        4 real DMMAs), A operands = finished L columns streamed from the factor store
+//                       factorise the block's own pivot columns in sub-panels of 8: every thread owns ONE ROW of the sub-panel in
+//                       registers, ONE barrier per pivot column (warp arg-max + published candidate rows, threshold pivoting as
+//                       in krb_front_factor), then the sub-panel's U rows and a DMMA update of the rest of the block
+//                       write the block to the factor store (L | U11, U12) and the contribution block
+// Each front entry is written once and every finished L panel is read once per later block: ~(2 + p/W ... ) x the front size instead
+// of 27x, and the rank-k updates run out of shared memory + registers.  blockDim = (32, 16), m <= 512.
+constexpr int FRONT_LL_AUX = 384;    // elements of T reserved at the start of the dynamic shared memory (published rows, arg-max slots)
+constexpr int FRONT_LL_SPW = 8;      // sub-panel width
+
+__device__ __forceinline__ int front_lower_bound(const int *__restrict__ a, int lo, int hi, int key) {
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// column-block width for a front of m rows (ldc = padded leading dimension) in `elems` elements of shared memory: W columns of the
+// front + a W x W staging block for L_KK; at most 64 (one pass of the 4 x 4 warp grid), then balanced over the blocks
+__host__ __device__ inline int front_ll_width(int m, int ldc, long long elems) {
+    int W = 1;
+    while (W < 64 && (long long)(W + 1) * ldc + (long long)(W + 1) * (W + 1) <= elems) W++;
+    const int nblk = (m + W - 1) / W;
+    return (m + nblk - 1) / nblk;
+}
+__host__ __device__ inline int front_ll_ldc(int m) { return m + ((4 - m) & 7); }   // == 4 (mod 8): conflict-free DMMA B-fragment reads
+
+// C(i, j) -= sum_{k < K} Lt(i, k) Up(k, j) on the FP64 tensor cores, operands prefetched one k-step ahead.  16 warps as 4 x 4, each warp a
+// 32 x 16 block of C (4 x 2 MMA tiles); real: 8 DMMAs per k-step of 4, complex: 32 (re/im parts as four real products).
+template <bool CPLX> struct FrontMma;
+template <> struct FrontMma<false> {
+    static __device__ __forceinline__ void update(double *C, int ldc, int rows, int cols, const double *Lt, int ldl, const double *Up, int ldu, int K, int lane, int warp) {
+        // warp grid WR x WC by the number of columns: narrow blocks (complex: W = 29) must not leave half of the warps without a tile
+        const int WC = cols <= 16 ? 1 : cols <= 32 ? 2 : 4, WR = 16 / WC;
+        const int g = lane >> 2, t = lane & 3, wr = warp % WR, wc = warp / WR;
+        for (int j0 = 0; j0 < cols; j0 += 16 * WC)
+            for (int i0 = 0; i0 < rows; i0 += 32 * WR) {
+                const int rbase = i0 + wr * 32, cbase = j0 + wc * 16;
+                if (rbase >= rows || cbase >= cols) continue;
+                double c[4][2][2];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++)
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const int r = rbase + a * 8 + g, cc = cbase + b * 8 + 2 * t + i;
+                            c[a][b][i] = (r < rows && cc < cols) ? C[r + (size_t)ldc * cc] : 0.0;
+                        }
+                const double *ap[4], *bp[2];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { const int r = rbase + a * 8 + g; ap[a] = Lt + (r < rows ? r : rows - 1); }
+#pragma unroll
+                for (int b = 0; b < 2; b++) { const int cc = cbase + b * 8 + g; bp[b] = Up + (size_t)ldu * (cc < cols ? cc : cols - 1); }
+                double af[4], bf[2];
+                {
+                    const bool kv = t < K;
+                    const int kc = kv ? t : K - 1;
+#pragma unroll
+                    for (int a = 0; a < 4; a++) { const double v = ap[a][(size_t)ldl * kc]; af[a] = kv ? -v : 0.0; }
+#pragma unroll
+                    for (int b = 0; b < 2; b++) { const double v = bp[b][kc]; bf[b] = kv ? v : 0.0; }
+                }
+                for (int k0 = 0; k0 < K; k0 += 4) {
+                    double an[4], bn[2];
+                    {
+                        const int kk = k0 + 4 + t;
+                        const bool kv = kk < K;
+                        const int kc = kv ? kk : K - 1;
+#pragma unroll
+                        for (int a = 0; a < 4; a++) { const double v = ap[a][(size_t)ldl * kc]; an[a] = kv ? -v : 0.0; }
+#pragma unroll
+                        for (int b = 0; b < 2; b++) { const double v = bp[b][kc]; bn[b] = kv ? v : 0.0; }
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 2; b++) front_dmma(c[a][b][0], c[a][b][1], af[a], bf[b]);
+#pragma unroll
+                    for (int a = 0; a < 4; a++) af[a] = an[a];
+#pragma unroll
+                    for (int b = 0; b < 2; b++) bf[b] = bn[b];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++)
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const int r = rbase + a * 8 + g, cc = cbase + b * 8 + 2 * t + i;
+                            if (r < rows && cc < cols) C[r + (size_t)ldc * cc] = c[a][b][i];
+                        }
+            }
+    }
+};
+template <> struct FrontMma<true> {
+    static __device__ __forceinline__ void update(double2 *C, int ldc, int rows, int cols, const double2 *Lt, int ldl, const double2 *Up, int ldu, int K, int lane, int warp) {
+        const int WC = cols <= 16 ? 1 : cols <= 32 ? 2 : 4, WR = 16 / WC;
+        const int g = lane >> 2, t = lane & 3, wr = warp % WR, wc = warp / WR;
+        for (int j0 = 0; j0 < cols; j0 += 16 * WC)
+            for (int i0 = 0; i0 < rows; i0 += 32 * WR) {
+                const int rbase = i0 + wr * 32, cbase = j0 + wc * 16;
+                if (rbase >= rows || cbase >= cols) continue;
+                double cr[4][2][2], ci[4][2][2];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++)
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const int r = rbase + a * 8 + g, cc = cbase + b * 8 + 2 * t + i;
+                            const double2 v = (r < rows && cc < cols) ? C[r + (size_t)ldc * cc] : make_double2(0.0, 0.0);
+                            cr[a][b][i] = v.x; ci[a][b][i] = v.y;
+                        }
+                const double2 *ap[4], *bp[2];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { const int r = rbase + a * 8 + g; ap[a] = Lt + (r < rows ? r : rows - 1); }
+#pragma unroll
+                for (int b = 0; b < 2; b++) { const int cc = cbase + b * 8 + g; bp[b] = Up + (size_t)ldu * (cc < cols ? cc : cols - 1); }
+                double2 af[4], bf[2];
+                {
+                    const bool kv = t < K;
+                    const int kc = kv ? t : K - 1;
+#pragma unroll
+                    for (int a = 0; a < 4; a++) { const double2 v = ap[a][(size_t)ldl * kc]; af[a] = kv ? v : make_double2(0.0, 0.0); }
+#pragma unroll
+                    for (int b = 0; b < 2; b++) { const double2 v = bp[b][kc]; bf[b] = kv ? v : make_double2(0.0, 0.0); }
+                }
+                for (int k0 = 0; k0 < K; k0 += 4) {
+                    double2 an[4], bn[2];
+                    {
+                        const int kk = k0 + 4 + t;
+                        const bool kv = kk < K;
+                        const int kc = kv ? kk : K - 1;
+#pragma unroll
+                        for (int a = 0; a < 4; a++) { const double2 v = ap[a][(size_t)ldl * kc]; an[a] = kv ? v : make_double2(0.0, 0.0); }
+#pragma unroll
+                        for (int b = 0; b < 2; b++) { const double2 v = bp[b][kc]; bn[b] = kv ? v : make_double2(0.0, 0.0); }
+                    }
+                    // C -= A B:  C_re += (-A_re) B_re + A_im B_im,  C_im += (-A_re) B_im + (-A_im) B_re
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        const double nar = -af[a].x, ai = af[a].y, nai = -af[a].y;
+#pragma unroll
+                        for (int b = 0; b < 2; b++) {
+                            front_dmma(cr[a][b][0], cr[a][b][1], nar, bf[b].x);
+                            front_dmma(cr[a][b][0], cr[a][b][1], ai, bf[b].y);
+                            front_dmma(ci[a][b][0], ci[a][b][1], nar, bf[b].y);
+                            front_dmma(ci[a][b][0], ci[a][b][1], nai, bf[b].x);
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; a++) af[a] = an[a];
+#pragma unroll
+                    for (int b = 0; b < 2; b++) bf[b] = bn[b];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++)
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const int r = rbase + a * 8 + g, cc = cbase + b * 8 + 2 * t + i;
+                            if (r < rows && cc < cols) C[r + (size_t)ldc * cc] = make_double2(cr[a][b][i], ci[a][b][i]);
+                        }
+            }
+    }
+};
+
+template <bool CPLX>
+__global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams P) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    constexpr int SPW = FRONT_LL_SPW, NT = 512, NW = 16;
+    extern __shared__ __align__(16) unsigned char front_smem[];
+    T *aux = reinterpret_cast<T *>(front_smem);
+    // published rows of the sub-panel factorisation, double-buffered by the parity of the pivot column
+    T *slot_rows = aux;                                  // [2][NW][SPW] a warp's best candidate row
+    T *rowk = aux + 2 * NW * SPW;                        // [2][SPW]     the row at the static pivot position
+    double *slot_mag = reinterpret_cast<double *>(aux + 2 * NW * SPW + 2 * SPW);   // [2][NW]
+    int *slot_idx = reinterpret_cast<int *>(slot_mag + 2 * NW);                    // [2][NW]
+    int *s_nswap = slot_idx + 2 * NW;
+    T *Cs = aux + FRONT_LL_AUX;
+    const int f = P.list[blockIdx.x];
+    const long long lane = blockIdx.y;
+    const FrontDesc d = P.fronts[f];
+    const int p = d.p, q = d.q, m = p + q;
+    const int lx = threadIdx.x, wy = threadIdx.y, tid = wy * 32 + lx;
+    const int ldc = front_ll_ldc(m);
+    const int W = front_ll_width(m, ldc, (long long)P.smem_elems - FRONT_LL_AUX);
+    T *Ls = Cs + (size_t)ldc * W;                        // [W][W] strictly lower part of L_KK
+    bool bad = false;
+    uint32_t grow = 0;
+    int *ipiv = P.IPIV + lane * P.n + d.piv0;
+    T *LUf = reinterpret_cast<T *>(P.LU) + lane * P.lu_stride + d.lu_off;
+    T *U12 = LUf + (size_t)m * p;
+    T *CBf = reinterpret_cast<T *>(P.CB) + lane * P.cb_stride + d.cb_off;
+    const T *A = reinterpret_cast<const T *>(P.A) + lane * P.a_stride;
+    if (tid == 0) *s_nswap = 0;
+
+    for (int c0 = 0; c0 < m; c0 += W) {
+        const int wj = (m - c0) < W ? (m - c0) : W;
+        // ---- (a) assemble the block: zero, stamped entries (sorted by position), children's contribution-block columns ----
+        for (int e = tid; e < ldc * wj; e += NT) Cs[e] = S::zero();
+        __syncthreads();
+        // (a front's list of stamped entries is short: every block scans it instead of searching its range, a chain of dependent loads)
+        for (int t = d.asm_begin + tid; t < d.asm_end; t += NT) {
+            const int pos = __ldg(P.asm_pos + t), c = pos / m, r = pos - c * m;
+            if (c >= c0 && c < c0 + wj) Cs[r + (size_t)ldc * (c - c0)] = A[__ldg(P.asm_ent + t)];
+        }
+        __syncthreads();
+        for (int ci = d.child_begin; ci < d.child_end; ci++) {
+            const FrontChild c = P.childrec[ci];
+            const int qc = c.q;
+            const int *rel = P.rel + c.idx_off;
+            // the child's columns that land in this block: rel is ascending, so two block-wide counts give the range
+            int j0 = 0, j1 = 0;
+            for (int b = 0; b < qc; b += NT) {
+                const int rv = (b + tid < qc) ? __ldg(rel + b + tid) : 0x7fffffff;
+                j0 += __syncthreads_count(rv < c0);
+                j1 += __syncthreads_count(rv < c0 + wj);
+            }
+            if (j0 < j1) {
+                const T *CBc = reinterpret_cast<const T *>(P.CB) + lane * P.cb_stride + c.cb_off;
+                for (int jc = j0 + wy; jc < j1; jc += NW) {
+                    T *dst = Cs + (size_t)ldc * (__ldg(rel + jc) - c0);
+                    const T *src = CBc + (size_t)qc * jc;
+                    for (int i = lx; i < qc; i += 32) { T *e = dst + __ldg(rel + i); *e = S::add(*e, src[i]); }
+                }
+            }
+            __syncthreads();          // the next child may add to the same entries
+        }
+        // ---- (b) interchanges of all earlier pivots (rare) ----
+        const int kdone = c0 < p ? c0 : p;
+        if (*s_nswap > 0 && kdone > 0) {
+            for (int j = tid; j < wj; j += NT) {
+                T *cj = Cs + (size_t)ldc * j;
+                for (int k = 0; k < kdone; k++) { const int ip = ipiv[k]; if (ip != k) { const T t = cj[k]; cj[k] = cj[ip]; cj[ip] = t; } }
+            }
+            __syncthreads();
+        }
+        // ---- (c) left-looking: the earlier pivot panels ----
+        for (int k0 = 0; k0 < kdone; k0 += W) {
+            const int wk = (p - k0) < W ? (p - k0) : W;
+            for (int e = tid; e < wk * wk; e += NT) {
+                const int k = e / wk, r = e - k * wk;
+                Ls[e] = r > k ? LUf[(k0 + r) + (size_t)m * (k0 + k)] : S::zero();
+            }
+            __syncthreads();
+            {   // U_KJ = L_KK^-1 C_K: 8 lanes per column; the 8 x 8 diagonal steps redundantly, the rows below them split over the lanes
+                const int col = tid >> 3, r8 = tid & 7;
+                const bool act = col < wj;
+                T *cj = Cs + k0 + (size_t)ldc * (act ? col : 0);
+                for (int s0 = 0; s0 < wk; s0 += 8) {
+                    const int ns = (wk - s0) < 8 ? (wk - s0) : 8;
+                    T v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = k < ns ? cj[s0 + k] : S::zero();
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+#pragma unroll
+                        for (int r = k + 1; r < 8; r++)
+                            if (r < ns) v[r] = S::fnma(v[r], Ls[(s0 + r) + wk * (s0 + k)], v[k]);
+                    __syncwarp();                 // every lane of the group has read the 8 rows
+                    if (act && r8 == 0)
+#pragma unroll
+                        for (int k = 0; k < 8; k++) if (k < ns) cj[s0 + k] = v[k];
+                    for (int r = s0 + 8 + r8; r < wk; r += 8) {
+                        T acc = cj[r];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) if (k < ns) acc = S::fnma(acc, Ls[r + wk * (s0 + k)], v[k]);
+                        if (act) cj[r] = acc;
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            if (m - (k0 + wk) > 0)
+                FrontMma<CPLX>::update(Cs + (k0 + wk), ldc, m - (k0 + wk), wj, LUf + (k0 + wk) + (size_t)m * k0, m, Cs + k0, ldc, wk, lx, wy);
+            __syncthreads();
+        }
+        // ---- (d) the block's own pivot columns, sub-panels of SPW columns, one row per thread in registers ----
+        const int npiv = (c0 < p) ? ((p - c0) < wj ? (p - c0) : wj) : 0;
+        for (int s0 = 0; s0 < npiv; s0 += SPW) {
+            const int ns = (npiv - s0) < SPW ? (npiv - s0) : SPW;
+            const int kk0 = c0 + s0;                  // front row / column of the sub-panel's first pivot
+            const int row = kk0 + tid;                // this thread's row (m - kk0 <= 512)
+            T a[SPW];
+#pragma unroll
+            for (int k = 0; k < SPW; k++) a[k] = (k < ns && row < m) ? Cs[row + (size_t)ldc * (s0 + k)] : S::zero();
+#pragma unroll
+            for (int k = 0; k < SPW; k++) {
+                if (k < ns) {
+                    const int kk = kk0 + k, par = k & 1;
+                    // candidates: fully-summed rows below the static pivot position
+                    double best = (row > kk && row < p) ? FrontAbs<CPLX>::mag(a[k]) : -1.0;
+                    if (!(best >= 0.0)) best = -1.0;          // nan never wins
+                    int bi = tid;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    }
+                    if (tid == bi && best >= 0.0) {
+#pragma unroll
+                        for (int j = 0; j < SPW; j++) slot_rows[(par * NW + wy) * SPW + j] = a[j];
+                    }
+                    if (lx == 0) { slot_mag[par * NW + wy] = best; slot_idx[par * NW + wy] = bi; }
+                    if (tid == k) {
+#pragma unroll
+                        for (int j = 0; j < SPW; j++) rowk[par * SPW + j] = a[j];
+                    }
+                    __syncthreads();
+                    double gb = -1.0;
+                    int gi = k, gw = 0;
+#pragma unroll
+                    for (int w = 0; w < NW; w++) { const double v = slot_mag[par * NW + w]; if (v > gb) { gb = v; gi = slot_idx[par * NW + w]; gw = w; } }
+                    const double dk = FrontAbs<CPLX>::mag(rowk[par * SPW + k]);
+                    const bool keep = (gb < 0.0) || (isfinite(dk) && dk > 0.0 && !(gb > FrontAbs<CPLX>::THRESH * dk));
+                    const T *prow = keep ? rowk + par * SPW : slot_rows + (par * NW + gw) * SPW;
+                    if (!keep) {
+                        // rows kk <-> ip = kk0 + gi: the two owners exchange their register rows, helper threads the rest of the block's
+                        // columns and the finished L columns left of the block
+                        const int ip = kk0 + gi;
+                        if (tid == gi) {
+#pragma unroll
+                            for (int j = 0; j < SPW; j++) a[j] = rowk[par * SPW + j];
+                        }
+                        if (tid == k) {
+#pragma unroll
+                            for (int j = 0; j < SPW; j++) a[j] = prow[j];
+                        }
+                        for (int j = tid; j < wj; j += NT)
+                            if (j < s0 || j >= s0 + ns) { T *x = Cs + kk + (size_t)ldc * j, *y = Cs + ip + (size_t)ldc * j; const T t = *x; *x = *y; *y = t; }
+                        for (int j = tid; j < c0; j += NT) { T *x = LUf + kk + (size_t)m * j, *y = LUf + ip + (size_t)m * j; const T t = *x; *x = *y; *y = t; }
+                        if (tid == 0) { ipiv[kk] = ip; *s_nswap += 1; }
+                    } else if (tid == 0) ipiv[kk] = kk;
+                    bool b1;
+                    const T rp = S::rcp(prow[k], b1);
+                    bad |= b1;
+                    if (tid > k && row < m) {
+                        const T l = S::mul(a[k], rp);
+                        a[k] = l;
+                        grow = max(grow, growth_key(l));
+#pragma unroll
+                        for (int j = k + 1; j < SPW; j++) if (j < ns) a[j] = S::fnma(a[j], l, prow[j]);
+                    }
+                }
+            }
+            if (row < m)
+#pragma unroll
+                for (int k = 0; k < SPW; k++) if (k < ns) Cs[row + (size_t)ldc * (s0 + k)] = a[k];
+            __syncthreads();
+            const int rest = wj - (s0 + ns);          // columns of the block right of the sub-panel
+            if (tid < rest) {                         // their U rows: unit-lower solve with the sub-panel's diagonal block
+                T *cj = Cs + kk0 + (size_t)ldc * (s0 + ns + tid);
+                T v[SPW];
+#pragma unroll
+                for (int k = 0; k < SPW; k++) v[k] = k < ns ? cj[k] : S::zero();
+#pragma unroll
+                for (int k = 0; k < SPW; k++)
+#pragma unroll
+                    for (int r = k + 1; r < SPW; r++)
+                        if (r < ns) v[r] = S::fnma(v[r], Cs[(kk0 + r) + (size_t)ldc * (s0 + k)], v[k]);
+#pragma unroll
+                for (int k = 0; k < SPW; k++) if (k < ns) cj[k] = v[k];
+            }
+            __syncthreads();
+            if (rest > 0 && m - (kk0 + ns) > 0)
+                FrontMma<CPLX>::update(Cs + (kk0 + ns) + (size_t)ldc * (s0 + ns), ldc, m - (kk0 + ns), rest, Cs + (kk0 + ns) + (size_t)ldc * s0, ldc,
+                                       Cs + kk0 + (size_t)ldc * (s0 + ns), ldc, ns, lx, wy);
+            __syncthreads();
+        }
+        // ---- (e) write the block out: pivot columns -> L | U11 (reciprocal pivot on the diagonal), the others -> U12 and the contribution block ----
+        for (int j = wy; j < wj; j += NW) {
+            const int c = c0 + j;
+            const T *cj = Cs + (size_t)ldc * j;
+            if (c < p) {
+                for (int i = lx; i < m; i += 32) {
+                    T v = cj[i];
+                    if (i == c) { bool b1; v = S::rcp(v, b1); }
+                    LUf[i + (size_t)m * c] = v;
+                }
+            } else {
+                for (int k = lx; k < p; k += 32) U12[k + (size_t)p * (c - p)] = cj[k];
+                for (int i = lx; i < q; i += 32) CBf[i + (size_t)q * (c - p)] = cj[p + i];
+            }
+        }
+        __syncthreads();
+    }
+    if (bad && tid == 0 && P.status) atomicOr(P.status + lane, KRB_LANE_ZERO_PIVOT);
+    if (grow >= KRB_GROWTH_KEY && grow < KRB_NONFINITE_KEY && P.status) atomicOr(P.status + lane, KRB_LANE_INACCURATE);
+}
+
+// ---- (b'') small fronts (m <= 32): one WARP per (front, lane), no block-wide barrier ----------------------------------------------
+// The two lowest tree levels of a mesh hold ~6 600 fronts of 16..31 rows per lane (half of the factor entries, a tenth of the flops).
+// With a 128-thread CTA per front they cost 3 barriers per pivot and ~15 000 warp instructions per front for ~500 useful ones
+// (ncu r1: 46 % issue-active, 6 % of the DRAM peak).  Here lane i of a warp owns row i of the front (shared memory, odd leading
+// dimension); a pivot step is one warp arg-max, a scaled column and a rank-1 update of the rows below with the pivot row broadcast,
+// separated by __syncwarp only.  blockDim = (32, W): W independent (front, lane) pairs per CTA.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) krb_front_factor_warp(const FrontParams P) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    extern __shared__ __align__(16) unsigned char front_smem[];
+    const long long lane = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    if (lane >= P.lanes) return;
+    T *F = reinterpret_cast<T *>(front_smem) + (size_t)threadIdx.y * P.smem_elems;
+    const int f = P.list[blockIdx.x];
+    const FrontDesc d = P.fronts[f];
+    const int p = d.p, q = d.q, m = p + q, ld = m | 1;
+    const int lx = threadIdx.x;
+    bool bad = false;
+    uint32_t grow = 0;
+    int *ipiv = P.IPIV + lane * P.n + d.piv0;
+    // ---- assemble ----
+    for (int e = lx; e < ld * m; e += 32) F[e] = S::zero();
+    __syncwarp();
+    {
+        const T *A = reinterpret_cast<const T *>(P.A) + lane * P.a_stride;
+        for (int t = d.asm_begin + lx; t < d.asm_end; t += 32) {
+            const int pos = __ldg(P.asm_pos + t), c = pos / m, r = pos - c * m;
+            F[r + ld * c] = A[__ldg(P.asm_ent + t)];
+        }
+    }
+    __syncwarp();
+    for (int ci = d.child_begin; ci < d.child_end; ci++) {
+        const FrontChild c = P.childrec[ci];
+        const int qc = c.q;
+        const T *CBc = reinterpret_cast<const T *>(P.CB) + lane * P.cb_stride + c.cb_off;
+        const int *rel = P.rel + c.idx_off;
+        for (int e = lx; e < qc * qc; e += 32) {
+            const int j = e / qc, i = e - j * qc;
+            T *dst = F + __ldg(rel + i) + ld * __ldg(rel + j);
+            *dst = S::add(*dst, CBc[e]);
+        }
+        __syncwarp();
+    }
+    // ---- eliminate the p pivot columns ----
+    const bool mine = lx < m;
+    for (int k = 0; k < p; k++) {
+        T v = mine ? F[lx + ld * k] : S::zero();
+        int ip = k;
+        if (k + 1 < p) {
+            double best = (lx > k && lx < p) ? FrontAbs<CPLX>::mag(v) : -1.0;
+            if (!(best >= 0.0)) best = -1.0;
+            int bi = lx;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            const double dk = __shfl_sync(0xffffffffu, FrontAbs<CPLX>::mag(v), k);
+            const bool keep = (best < 0.0) || (isfinite(dk) && dk > 0.0 && !(best > FrontAbs<CPLX>::THRESH * dk));
+            if (!keep) {
+                ip = bi;
+                if (mine) { T *x = F + k + ld * lx, *y = F + ip + ld * lx; const T t = *x; *x = *y; *y = t; }   // lane j swaps column j
+                __syncwarp();
+                v = mine ? F[lx + ld * k] : S::zero();
+            }
+        }
+        if (lx == 0) ipiv[k] = ip;
+        bool b1;
+        const T rp = S::rcp(front_shfl(v, k), b1);
+        bad |= b1;
+        T l = S::zero();
+        const bool below = lx > k && mine;
+        if (below) { l = S::mul(v, rp); F[lx + ld * k] = l; grow = max(grow, growth_key(l)); }
+        if (lx == k) F[k + ld * k] = rp;                    // the factor store keeps reciprocal pivots
+        int j = k + 1;
+        for (; j + 4 <= m; j += 4) {
+            const T u0 = F[k + ld * j], u1 = F[k + ld * (j + 1)], u2 = F[k + ld * (j + 2)], u3 = F[k + ld * (j + 3)];
+            if (below) {
+                T *c0 = F + lx + ld * j;
+                const T a0 = c0[0], a1 = c0[ld], a2 = c0[2 * ld], a3 = c0[3 * ld];
+                c0[0] = S::fnma(a0, l, u0); c0[ld] = S::fnma(a1, l, u1); c0[2 * ld] = S::fnma(a2, l, u2); c0[3 * ld] = S::fnma(a3, l, u3);
+            }
+        }
+        for (; j < m; j++) {
+            const T u0 = F[k + ld * j];
+            if (below) { T *c0 = F + lx + ld * j; *c0 = S::fnma(*c0, l, u0); }
+        }
+        __syncwarp();
+    }
+    // ---- write out: L | U11 (m x p), U12 (p x q), contribution block (q x q) ----
+    T *LUf = reinterpret_cast<T *>(P.LU) + lane * P.lu_stride + d.lu_off;
+    for (int k = 0; k < p; k++) if (mine) LUf[lx + m * k] = F[lx + ld * k];
+    T *U12 = LUf + m * p;
+    T *CBf = reinterpret_cast<T *>(P.CB) + lane * P.cb_stride + d.cb_off;
+    for (int j = 0; j < q; j++) {
+        if (lx < p) U12[lx + p * j] = F[lx + ld * (p + j)];
+        if (lx < q) CBf[lx + q * j] = F[p + lx + ld * (p + j)];
+    }
+    if (bad && lx == 0 && P.status) atomicOr(P.status + lane, KRB_LANE_ZERO_PIVOT);
+    if (grow >= KRB_GROWTH_KEY && grow < KRB_NONFINITE_KEY && P.status) atomicOr(P.status + lane, KRB_LANE_INACCURATE);
+}
+
 // ---- iterative refinement: r = b - A x on the stamped values, in pivot order; x += correction ------------------------
 struct FrontRefineParams {
     const int *res_ptr, *res_ent, *res_col;   // CSR of the permuted matrix: position k -> (CSC entry id, unknown)
@@ -560,8 +1069,6 @@ __device__ __forceinline__ void front_stage(T *dst, const T *src, int count, int
 __device__ __forceinline__ void front_stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <bool WARP> __device__ __forceinline__ void front_sync() { if (WARP) __syncwarp(); else __syncthreads(); }
 template <bool WARP> __device__ __forceinline__ int front_any(int pred) { return WARP ? __any_sync(0xffffffffu, pred) : __syncthreads_or(pred); }
-__device__ __forceinline__ double front_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ double2 front_shfl(double2 v, int src) { return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
 
 // forward: y_piv = L11^-1 P (b_piv + children), contribution = rest - L21 y_piv
 template <bool CPLX, bool WARP>

@@ -256,6 +256,8 @@ void build_front_plan(const Pattern &P, const std::vector<int> &match_row, const
             }
         fp.asm_ptr.assign(nf + 1, 0);
         for (int f = 0; f < nf; f++) {
+            // sorted by position (column-major): the left-looking kernel assembles a front one column block at a time
+            std::sort(per_front[f].begin(), per_front[f].end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.second < b.second; });
             for (auto &pr : per_front[f]) { fp.asm_ent.push_back(pr.first); fp.asm_pos.push_back(pr.second); }
             fp.asm_ptr[f + 1] = (int)fp.asm_ent.size();
         }
