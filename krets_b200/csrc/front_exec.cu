@@ -38,7 +38,7 @@ struct FBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
-struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int slot_elems; int stage_fwd = 0, stage_bwd = 0; bool ll = false; };
+struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int slot_elems; int stage_fwd = 0, stage_bwd = 0; int ll = 0; };   // ll: warps of krb_front_factor_ll, 0 = another kernel
 }  // namespace
 
 struct FrontDevice {
@@ -127,7 +127,7 @@ static int upload_front(Plan &plan) {
         const long long m = d.p + d.q;
         // fronts beyond shared memory: left-looking by resident column blocks (krb_front_factor_ll, no workspace) up to 512 rows,
         // above that the blocked right-looking kernel on a per-lane workspace; KRB_FRONT_LL=0 (A/B) sends all of them there
-        if (m > m_smem && (m > 512 || !use_ll)) { d.fw_off = D.fw_size; D.fw_size += ((m * m + 1) / 2) * 2; }
+        if (m > m_smem && (m > 512 || !use_ll)) { d.fw_off = D.fw_size; D.fw_size += ((m * m + 1) / 2) * 2; }   // (with use_ll only fronts beyond 512 rows)
         else d.fw_off = -1;
     }
     // launch lists: each level's fronts are sorted by size (largest first); cut them into size classes
@@ -138,8 +138,9 @@ static int upload_front(Plan &plan) {
         // size classes: -1 left-looking (beyond shared memory), 0 blocked on the workspace, 1..4 CTA per front in shared memory,
         // 5..7 one warp per front (m <= 32; KRB_FRONT_WARPF=0 (A/B) keeps them on classes 3 / 4)
         auto fclass = [&](int m) {
-            if (m > m_smem) return (m <= 512 && use_ll) ? -1 : 0;
-            if (use_warpf && m <= 32) return m > 24 ? 5 : m > 16 ? 6 : 7;
+            if (use_warpf && m <= 32 && m <= m_smem) return m > 24 ? 5 : m > 16 ? 6 : 7;
+            if (use_ll && m <= 512) return m > 256 ? -1 : m > 128 ? -2 : -3;      // left-looking kernel on 16 / 8 / 4 warps
+            if (m > m_smem) return 0;
             return m > 96 ? 1 : m > 48 ? 2 : m > 16 ? 3 : 4;
         };
         auto sclass = [&](int m) { return m > 192 ? 0 : m > 64 ? 1 : 2; };
@@ -153,7 +154,15 @@ static int upload_front(Plan &plan) {
             L.block = c <= 1 ? dim3(32, 16) : c == 2 ? dim3(16, 16) : c == 3 ? dim3(16, 8) : dim3(8, 8);
             L.smem = c == 0 ? std::min<size_t>((size_t)D.smem_cap, ((size_t)2 * m0 * 32 + m0) * ts) : (size_t)m0 * (m0 | 1) * ts;
             L.warp = false; L.slot_elems = 0;
-            if (c < 0) { L.ll = true; L.smem = (size_t)D.smem_cap; }
+            if (c < 0) {
+                // shared memory by residency: 4 warps -> 56 KB (four CTAs per SM), 8 -> 112 KB (two), 16 -> everything; doubled while the
+                // column blocks would be narrower than 8
+                L.ll = c == -1 ? 16 : c == -2 ? 8 : 4;
+                size_t sm_b = c == -1 ? (size_t)D.smem_cap : c == -2 ? (size_t)112 * 1024 : (size_t)56 * 1024;
+                while (sm_b < (size_t)D.smem_cap && front_ll_width(m0, front_ll_ldc(m0), (long long)(sm_b / ts) - FRONT_LL_AUX) < 8) sm_b *= 2;
+                L.smem = std::min(sm_b, (size_t)D.smem_cap);
+                L.block = dim3(32, L.ll);
+            }
             if (c >= 5) {   // warp per (front, lane): 8 pairs per CTA while four CTAs still fit an SM, else 4
                 L.warp = true;
                 L.slot_elems = m0 * (m0 | 1);
@@ -270,8 +279,12 @@ static int upload_front(Plan &plan) {
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
-    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
-    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_backward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
@@ -314,8 +327,15 @@ static int front_factor(const Plan &plan, FrontParams P, long long lanes, cudaSt
             dim3 grid((unsigned)L.count, (unsigned)lanes);
             const bool small = L.block.x * L.block.y <= 128;
             if (L.ll) {
-                if (plan.is_complex) krb_front_factor_ll<true><<<grid, dim3(32, 16), L.smem, st>>>(Q);
-                else krb_front_factor_ll<false><<<grid, dim3(32, 16), L.smem, st>>>(Q);
+                if (plan.is_complex) {
+                    if (L.ll == 16) krb_front_factor_ll<true, 16><<<grid, L.block, L.smem, st>>>(Q);
+                    else if (L.ll == 8) krb_front_factor_ll<true, 8><<<grid, L.block, L.smem, st>>>(Q);
+                    else krb_front_factor_ll<true, 4><<<grid, L.block, L.smem, st>>>(Q);
+                } else {
+                    if (L.ll == 16) krb_front_factor_ll<false, 16><<<grid, L.block, L.smem, st>>>(Q);
+                    else if (L.ll == 8) krb_front_factor_ll<false, 8><<<grid, L.block, L.smem, st>>>(Q);
+                    else krb_front_factor_ll<false, 4><<<grid, L.block, L.smem, st>>>(Q);
+                }
             } else if (L.warp) {
                 Q.smem_elems = L.slot_elems;
                 dim3 gw((unsigned)L.count, (unsigned)((lanes + L.block.y - 1) / L.block.y));
@@ -650,6 +670,19 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         }
         CUDA_TRY(cudaEventRecord(e1, st));
         CUDA_TRY(cudaGetLastError());
+#ifdef KRB_LL_PROFILE
+        if (getenv("KRB_LL_PROFILE")) {
+            cudaStreamSynchronize(st);
+            unsigned long long h[16] = {0};
+            cudaMemcpyFromSymbol(h, krb_ll_prof, sizeof(h));
+            const char *nm[8] = {"assemble+swaps", "stage L_KK", "U_KJ solve", "DMMA update", "pivot columns", "sub-panel U rows", "in-block DMMA", "write-out"};
+            unsigned long long tot = 0;
+            for (int i = 0; i < 8; i++) tot += h[i];
+            for (int i = 0; i < 8; i++) fprintf(stderr, "[krb ll] %-18s %6.2f %%  %12llu cycles\n", nm[i], 100.0 * (double)h[i] / (double)(tot ? tot : 1), h[i]);
+            unsigned long long z[16] = {0};
+            cudaMemcpyToSymbol(krb_ll_prof, z, sizeof(z));
+        }
+#endif
         if (dbg) {
             mark("end");
             cudaStreamSynchronize(st);

@@ -494,7 +494,16 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
 //                       in krb_front_factor), then the sub-panel's U rows and a DMMA update of the rest of the block
 //                       write the block to the factor store (L | U11, U12) and the contribution block
 // Each front entry is written once and every finished L panel is read once per later block: ~(2 + p/W ... ) x the front size instead
-// of 27x, and the rank-k updates run out of shared memory + registers.  blockDim = (32, 16), m <= 512.
+// of 27x, and the rank-k updates run out of shared memory + registers.  blockDim = (32, NW), m <= 32 NW.  The same kernel serves the
+// mid-size fronts (32 < m <= 128 on 4 warps with 56 KB: four CTAs per SM; m <= 256 on 8 warps with 112 KB): DMMA updates and one
+// barrier per pivot instead of the register-tile kernel's three, at four times its residency.
+#ifdef KRB_LL_PROFILE
+// per-phase cycles of thread 0, summed over all CTAs (profiling builds only: tools/build_variant.sh ... -DKRB_LL_PROFILE)
+__device__ unsigned long long krb_ll_prof[16];
+#define LLP(i) do { if (tid == 0) { const long long t1_ = clock64(); llp[i] += t1_ - t0_; t0_ = t1_; } } while (0)
+#else
+#define LLP(i) do { } while (0)
+#endif
 constexpr int FRONT_LL_AUX = 384;    // elements of T reserved at the start of the dynamic shared memory (published rows, arg-max slots)
 constexpr int FRONT_LL_SPW = 8;      // sub-panel width
 
@@ -512,13 +521,13 @@ __host__ __device__ inline int front_ll_width(int m, int ldc, long long elems) {
 }
 __host__ __device__ inline int front_ll_ldc(int m) { return m + ((4 - m) & 7); }   // == 4 (mod 8): conflict-free DMMA B-fragment reads
 
-// C(i, j) -= sum_{k < K} Lt(i, k) Up(k, j) on the FP64 tensor cores, operands prefetched one k-step ahead.  16 warps as 4 x 4, each warp a
+// C(i, j) -= sum_{k < K} Lt(i, k) Up(k, j) on the FP64 tensor cores, operands prefetched one k-step ahead.  NW warps as WR x WC, each warp a
 // 32 x 16 block of C (4 x 2 MMA tiles); real: 8 DMMAs per k-step of 4, complex: 32 (re/im parts as four real products).
-template <bool CPLX> struct FrontMma;
-template <> struct FrontMma<false> {
+template <bool CPLX, int NW> struct FrontMma;
+template <int NW> struct FrontMma<false, NW> {
     static __device__ __forceinline__ void update(double *C, int ldc, int rows, int cols, const double *Lt, int ldl, const double *Up, int ldu, int K, int lane, int warp) {
         // warp grid WR x WC by the number of columns: narrow blocks (complex: W = 29) must not leave half of the warps without a tile
-        const int WC = cols <= 16 ? 1 : cols <= 32 ? 2 : 4, WR = 16 / WC;
+        const int WC = cols <= 16 ? 1 : cols <= 32 ? 2 : 4, WR = NW / WC;
         const int g = lane >> 2, t = lane & 3, wr = warp % WR, wc = warp / WR;
         for (int j0 = 0; j0 < cols; j0 += 16 * WC)
             for (int i0 = 0; i0 < rows; i0 += 32 * WR) {
@@ -580,9 +589,9 @@ template <> struct FrontMma<false> {
             }
     }
 };
-template <> struct FrontMma<true> {
+template <int NW> struct FrontMma<true, NW> {
     static __device__ __forceinline__ void update(double2 *C, int ldc, int rows, int cols, const double2 *Lt, int ldl, const double2 *Up, int ldu, int K, int lane, int warp) {
-        const int WC = cols <= 16 ? 1 : cols <= 32 ? 2 : 4, WR = 16 / WC;
+        const int WC = cols <= 16 ? 1 : cols <= 32 ? 2 : 4, WR = NW / WC;
         const int g = lane >> 2, t = lane & 3, wr = warp % WR, wc = warp / WR;
         for (int j0 = 0; j0 < cols; j0 += 16 * WC)
             for (int i0 = 0; i0 < rows; i0 += 32 * WR) {
@@ -604,25 +613,30 @@ template <> struct FrontMma<true> {
                 for (int a = 0; a < 4; a++) { const int r = rbase + a * 8 + g; ap[a] = Lt + (r < rows ? r : rows - 1); }
 #pragma unroll
                 for (int b = 0; b < 2; b++) { const int cc = cbase + b * 8 + g; bp[b] = Up + (size_t)ldu * (cc < cols ? cc : cols - 1); }
+                // A fragments (finished L columns: global memory / L2) are fetched one k-step ahead, B fragments (shared memory) at use:
+                // prefetching both costs 24 more registers and spills inside this loop (ncu r2o: 9 % of the samples on spill reloads)
                 double2 af[4], bf[2];
                 {
                     const bool kv = t < K;
                     const int kc = kv ? t : K - 1;
 #pragma unroll
                     for (int a = 0; a < 4; a++) { const double2 v = ap[a][(size_t)ldl * kc]; af[a] = kv ? v : make_double2(0.0, 0.0); }
-#pragma unroll
-                    for (int b = 0; b < 2; b++) { const double2 v = bp[b][kc]; bf[b] = kv ? v : make_double2(0.0, 0.0); }
                 }
                 for (int k0 = 0; k0 < K; k0 += 4) {
-                    double2 an[4], bn[2];
+                    double2 an[4];
                     {
                         const int kk = k0 + 4 + t;
                         const bool kv = kk < K;
                         const int kc = kv ? kk : K - 1;
 #pragma unroll
                         for (int a = 0; a < 4; a++) { const double2 v = ap[a][(size_t)ldl * kc]; an[a] = kv ? v : make_double2(0.0, 0.0); }
+                    }
+                    {
+                        const int kk = k0 + t;
+                        const bool kv = kk < K;
+                        const int kc = kv ? kk : K - 1;
 #pragma unroll
-                        for (int b = 0; b < 2; b++) { const double2 v = bp[b][kc]; bn[b] = kv ? v : make_double2(0.0, 0.0); }
+                        for (int b = 0; b < 2; b++) { const double2 v = bp[b][kc]; bf[b] = kv ? v : make_double2(0.0, 0.0); }
                     }
                     // C -= A B:  C_re += (-A_re) B_re + A_im B_im,  C_im += (-A_re) B_im + (-A_im) B_re
 #pragma unroll
@@ -638,8 +652,6 @@ template <> struct FrontMma<true> {
                     }
 #pragma unroll
                     for (int a = 0; a < 4; a++) af[a] = an[a];
-#pragma unroll
-                    for (int b = 0; b < 2; b++) bf[b] = bn[b];
                 }
 #pragma unroll
                 for (int a = 0; a < 4; a++)
@@ -654,17 +666,18 @@ template <> struct FrontMma<true> {
     }
 };
 
-template <bool CPLX>
-__global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams P) {
+template <bool CPLX, int NW>   // NW warps per CTA: 16 (m <= 512, one CTA per SM), 8 (m <= 256, two), 4 (m <= 128, four)
+__global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const FrontParams P) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
-    constexpr int SPW = FRONT_LL_SPW, NT = 512, NW = 16;
+    constexpr int SPW = FRONT_LL_SPW, NT = NW * 32;
     extern __shared__ __align__(16) unsigned char front_smem[];
     T *aux = reinterpret_cast<T *>(front_smem);
     // published rows of the sub-panel factorisation, double-buffered by the parity of the pivot column
     T *slot_rows = aux;                                  // [2][NW][SPW] a warp's best candidate row
     T *rowk = aux + 2 * NW * SPW;                        // [2][SPW]     the row at the static pivot position
-    double *slot_mag = reinterpret_cast<double *>(aux + 2 * NW * SPW + 2 * SPW);   // [2][NW]
+    T *rp_slot = rowk + 2 * SPW;                         // [2]          reciprocal of the entry at the static pivot position
+    double *slot_mag = reinterpret_cast<double *>(rp_slot + 2);                    // [2][NW]
     int *slot_idx = reinterpret_cast<int *>(slot_mag + 2 * NW);                    // [2][NW]
     int *s_nswap = slot_idx + 2 * NW;
     T *Cs = aux + FRONT_LL_AUX;
@@ -684,6 +697,9 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
     T *CBf = reinterpret_cast<T *>(P.CB) + lane * P.cb_stride + d.cb_off;
     const T *A = reinterpret_cast<const T *>(P.A) + lane * P.a_stride;
     if (tid == 0) *s_nswap = 0;
+#ifdef KRB_LL_PROFILE
+    long long llp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0_ = clock64();
+#endif
 
     for (int c0 = 0; c0 < m; c0 += W) {
         const int wj = (m - c0) < W ? (m - c0) : W;
@@ -708,11 +724,21 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
                 j1 += __syncthreads_count(rv < c0 + wj);
             }
             if (j0 < j1) {
+                // a lane's rows (and their relative indices) are the same for every column: fetched once, four rows' loads in flight
                 const T *CBc = reinterpret_cast<const T *>(P.CB) + lane * P.cb_stride + c.cb_off;
-                for (int jc = j0 + wy; jc < j1; jc += NW) {
-                    T *dst = Cs + (size_t)ldc * (__ldg(rel + jc) - c0);
-                    const T *src = CBc + (size_t)qc * jc;
-                    for (int i = lx; i < qc; i += 32) { T *e = dst + __ldg(rel + i); *e = S::add(*e, src[i]); }
+                for (int ib = lx; ib < qc; ib += 128) {
+                    int ri[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) ri[u] = (ib + 32 * u < qc) ? __ldg(rel + ib + 32 * u) : -1;
+                    for (int jc = j0 + wy; jc < j1; jc += NW) {
+                        T *dst = Cs + (size_t)ldc * (__ldg(rel + jc) - c0);
+                        const T *src = CBc + (size_t)qc * jc + ib;
+                        T v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) v[u] = ri[u] >= 0 ? src[32 * u] : S::zero();
+#pragma unroll
+                        for (int u = 0; u < 4; u++) if (ri[u] >= 0) { T *e = dst + ri[u]; *e = S::add(*e, v[u]); }
+                    }
                 }
             }
             __syncthreads();          // the next child may add to the same entries
@@ -726,6 +752,7 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
             }
             __syncthreads();
         }
+        LLP(0);
         // ---- (c) left-looking: the earlier pivot panels ----
         for (int k0 = 0; k0 < kdone; k0 += W) {
             const int wk = (p - k0) < W ? (p - k0) : W;
@@ -734,8 +761,11 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
                 Ls[e] = r > k ? LUf[(k0 + r) + (size_t)m * (k0 + k)] : S::zero();
             }
             __syncthreads();
+            LLP(1);
             {   // U_KJ = L_KK^-1 C_K: 8 lanes per column; the 8 x 8 diagonal steps redundantly, the rows below them split over the lanes
-                const int col = tid >> 3, r8 = tid & 7;
+                const int r8 = tid & 7;
+                for (int cb = 0; cb < wj; cb += NT / 8) {
+                const int col = cb + (tid >> 3);
                 const bool act = col < wj;
                 T *cj = Cs + k0 + (size_t)ldc * (act ? col : 0);
                 for (int s0 = 0; s0 < wk; s0 += 8) {
@@ -760,11 +790,14 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
                     }
                     __syncwarp();
                 }
+                }
             }
             __syncthreads();
+            LLP(2);
             if (m - (k0 + wk) > 0)
-                FrontMma<CPLX>::update(Cs + (k0 + wk), ldc, m - (k0 + wk), wj, LUf + (k0 + wk) + (size_t)m * k0, m, Cs + k0, ldc, wk, lx, wy);
+                FrontMma<CPLX, NW>::update(Cs + (k0 + wk), ldc, m - (k0 + wk), wj, LUf + (k0 + wk) + (size_t)m * k0, m, Cs + k0, ldc, wk, lx, wy);
             __syncthreads();
+            LLP(3);
         }
         // ---- (d) the block's own pivot columns, sub-panels of SPW columns, one row per thread in registers ----
         const int npiv = (c0 < p) ? ((p - c0) < wj ? (p - c0) : wj) : 0;
@@ -797,6 +830,8 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
                     if (tid == k) {
 #pragma unroll
                         for (int j = 0; j < SPW; j++) rowk[par * SPW + j] = a[j];
+                        bool bb;
+                        rp_slot[par] = S::rcp(a[k], bb);     // the usual outcome (static pivot kept): one division per pivot, not one per thread
                     }
                     __syncthreads();
                     double gb = -1.0;
@@ -823,9 +858,9 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
                         for (int j = tid; j < c0; j += NT) { T *x = LUf + kk + (size_t)m * j, *y = LUf + ip + (size_t)m * j; const T t = *x; *x = *y; *y = t; }
                         if (tid == 0) { ipiv[kk] = ip; *s_nswap += 1; }
                     } else if (tid == 0) ipiv[kk] = kk;
-                    bool b1;
-                    const T rp = S::rcp(prow[k], b1);
-                    bad |= b1;
+                    T rp;
+                    if (keep) { rp = rp_slot[par]; bad |= !(dk > 0.0) || !isfinite(dk); }
+                    else { bool b1; rp = S::rcp(prow[k], b1); bad |= b1; }
                     if (tid > k && row < m) {
                         const T l = S::mul(a[k], rp);
                         a[k] = l;
@@ -835,6 +870,7 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
                     }
                 }
             }
+            LLP(4);
             if (row < m)
 #pragma unroll
                 for (int k = 0; k < SPW; k++) if (k < ns) Cs[row + (size_t)ldc * (s0 + k)] = a[k];
@@ -854,10 +890,12 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
                 for (int k = 0; k < SPW; k++) if (k < ns) cj[k] = v[k];
             }
             __syncthreads();
+            LLP(5);
             if (rest > 0 && m - (kk0 + ns) > 0)
-                FrontMma<CPLX>::update(Cs + (kk0 + ns) + (size_t)ldc * (s0 + ns), ldc, m - (kk0 + ns), rest, Cs + (kk0 + ns) + (size_t)ldc * s0, ldc,
+                FrontMma<CPLX, NW>::update(Cs + (kk0 + ns) + (size_t)ldc * (s0 + ns), ldc, m - (kk0 + ns), rest, Cs + (kk0 + ns) + (size_t)ldc * s0, ldc,
                                        Cs + kk0 + (size_t)ldc * (s0 + ns), ldc, ns, lx, wy);
             __syncthreads();
+            LLP(6);
         }
         // ---- (e) write the block out: pivot columns -> L | U11 (reciprocal pivot on the diagonal), the others -> U12 and the contribution block ----
         for (int j = wy; j < wj; j += NW) {
@@ -875,7 +913,12 @@ __global__ void __launch_bounds__(512, 1) krb_front_factor_ll(const FrontParams 
             }
         }
         __syncthreads();
+        LLP(7);
     }
+#ifdef KRB_LL_PROFILE
+    if (tid == 0)
+        for (int i = 0; i < 8; i++) atomicAdd(krb_ll_prof + i, (unsigned long long)llp[i]);
+#endif
     if (bad && tid == 0 && P.status) atomicOr(P.status + lane, KRB_LANE_ZERO_PIVOT);
     if (grow >= KRB_GROWTH_KEY && grow < KRB_NONFINITE_KEY && P.status) atomicOr(P.status + lane, KRB_LANE_INACCURATE);
 }

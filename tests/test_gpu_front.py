@@ -97,10 +97,12 @@ def test_front_transient_monte_carlo(oracle, integrator):
         assert_close(out[lane], ref, rtol=1e-8, what=f"mesh transient integrator {integrator} lane {lane}")
 
 
-def test_front_blocked_path_matches(oracle, monkeypatch):
-    """Fronts that do not fit in shared memory take the blocked path (panels in shared memory, trailing block in L2/HBM);
-    forcing every front larger than 6 onto it must give the same answers."""
+@pytest.mark.parametrize("ll", ["1", "0"])
+def test_front_blocked_path_matches(oracle, monkeypatch, ll):
+    """Fronts beyond shared memory: left-looking by resident column blocks (krb_front_factor_ll, ll = 1) or, with KRB_FRONT_LL=0,
+    the blocked right-looking kernel on the per-lane workspace; forcing every front larger than 6 onto them must give the same answers."""
     monkeypatch.setenv("KRB_FRONT_SMEM_M", "6")
+    monkeypatch.setenv("KRB_FRONT_LL", ll)
     text = netgen.rlc_mesh(12, 13, transient=False)
     circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
     freqs = kb.generate_frequencies("Decade", 3, 1e3, 1e9)
@@ -114,14 +116,17 @@ def test_front_blocked_path_matches(oracle, monkeypatch):
     assert_close(out[0], oc.solve_op(), what="blocked path OP")
 
 
-@pytest.mark.parametrize("smem_m", [None, 24])
+@pytest.mark.parametrize("smem_m", [None, 24, -24])
 def test_front_nominal_dc_pivots_inside_fronts(oracle, monkeypatch, smem_m):
     """Identical element values + inductor shorts: a static pivot cancels exactly (CPU tier shows it); the kernels' per-lane
     threshold pivoting inside the fully-summed block must recover it, on the shared-memory and on the blocked path."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spl
     if smem_m:
-        monkeypatch.setenv("KRB_FRONT_SMEM_M", str(smem_m))
+        monkeypatch.setenv("KRB_FRONT_SMEM_M", str(abs(smem_m)))
+        if smem_m < 0:                                      # the kernels the left-looking one replaced (CTA per front, workspace)
+            monkeypatch.setenv("KRB_FRONT_LL", "0")
+            monkeypatch.setenv("KRB_FRONT_WARPF", "0")
     text = netgen.rlc_mesh(40, 40, transient=True)
     circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
     out, status = kb.Plan(circuit, api.MODE_DC, executor=api.EXEC_STAGED).solve_op(1)

@@ -56,3 +56,26 @@ for (f, ln), s in outer.most_common(top):
 print('--- by innermost line ---')
 for (f, ln), s in agg.most_common(top // 2):
     print('%6.2f%%  %s:%d' % (100.0 * s / total, f, ln))
+# --- optional: samples by PHASE = the last kernel-body line (within [lo, hi]) seen in address order; inlined helper code is
+#     attributed to the call site that precedes it.  Extra args: lo hi boundary1,boundary2,...
+if len(sys.argv) > 7:
+    lo, hi = int(sys.argv[5]), int(sys.argv[6])
+    bounds = [int(x) for x in sys.argv[7].split(',')]
+    cur_line = lo
+    ph = collections.Counter()
+    phs = collections.defaultdict(collections.Counter)
+    for k, r in enumerate(inst):
+        loc = per_inst[k]
+        if loc and lo <= loc[1] <= hi and loc[0].startswith('front_kernels'):
+            cur_line = loc[1]
+        b = sum(1 for x in bounds if cur_line >= x)
+        s = int(r[ix['# Samples']] or 0)
+        ph[b] += s
+        for c in stall_cols:
+            v = int(r[ix[c]] or 0)
+            if v:
+                phs[b][c] += v
+    print('--- by phase (boundaries %s) ---' % bounds)
+    for b in sorted(ph):
+        st = ', '.join('%s %.1f%%' % (c.replace('stall_', ''), 100.0 * v / total) for c, v in phs[b].most_common(4))
+        print('phase %d: %6.2f%%   [%s]' % (b, 100.0 * ph[b] / total, st))
