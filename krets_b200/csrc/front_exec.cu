@@ -673,13 +673,16 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
 #ifdef KRB_LL_PROFILE
         if (getenv("KRB_LL_PROFILE")) {
             cudaStreamSynchronize(st);
-            unsigned long long h[16] = {0};
+            unsigned long long h[24] = {0};
             cudaMemcpyFromSymbol(h, krb_ll_prof, sizeof(h));
             const char *nm[8] = {"assemble+swaps", "stage L_KK", "U_KJ solve", "DMMA update", "pivot columns", "sub-panel U rows", "in-block DMMA", "write-out"};
-            unsigned long long tot = 0;
-            for (int i = 0; i < 8; i++) tot += h[i];
-            for (int i = 0; i < 8; i++) fprintf(stderr, "[krb ll] %-18s %6.2f %%  %12llu cycles\n", nm[i], 100.0 * (double)h[i] / (double)(tot ? tot : 1), h[i]);
-            unsigned long long z[16] = {0};
+            for (int g = 0; g < 3; g++) {
+                unsigned long long tot = 0;
+                for (int i = 0; i < 8; i++) tot += h[8 * g + i];
+                for (int i = 0; i < 8; i++)
+                    fprintf(stderr, "[krb ll %2d warps] %-18s %6.2f %%  %12llu cycles\n", g == 0 ? 16 : g == 1 ? 8 : 4, nm[i], 100.0 * (double)h[8 * g + i] / (double)(tot ? tot : 1), h[8 * g + i]);
+            }
+            unsigned long long z[24] = {0};
             cudaMemcpyToSymbol(krb_ll_prof, z, sizeof(z));
         }
 #endif

@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(R == 4 ? 512 : 128, R == 4 ? 1 : 6) krb_front_
 // barrier per pivot instead of the register-tile kernel's three, at four times its residency.
 #ifdef KRB_LL_PROFILE
 // per-phase cycles of thread 0, summed over all CTAs (profiling builds only: tools/build_variant.sh ... -DKRB_LL_PROFILE)
-__device__ unsigned long long krb_ll_prof[16];
+__device__ unsigned long long krb_ll_prof[24];   // [warps 16 | 8 | 4][phase]
 #define LLP(i) do { if (tid == 0) { const long long t1_ = clock64(); llp[i] += t1_ - t0_; t0_ = t1_; } } while (0)
 #else
 #define LLP(i) do { } while (0)
@@ -808,6 +808,68 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
             T a[SPW];
 #pragma unroll
             for (int k = 0; k < SPW; k++) a[k] = (k < ns && row < m) ? Cs[row + (size_t)ldc * (s0 + k)] : S::zero();
+            if (p - kk0 <= 32) {
+                // every candidate row of this sub-panel belongs to warp 0 (always the case for mid-size fronts, p <= 32): that warp runs the
+                // whole pivot sequence with shuffles and publishes the pivot rows; the other warps apply them to their rows after ONE barrier
+                T *pub = slot_rows;                  // [SPW][SPW] pivot rows, then [SPW] reciprocal pivots
+                if (wy == 0) {
+#pragma unroll
+                    for (int k = 0; k < SPW; k++) {
+                        if (k < ns) {
+                            const int kk = kk0 + k;
+                            const double mg = FrontAbs<CPLX>::mag(a[k]);
+                            // (magnitude, lowest row) in one 64-bit key: 10 index bits replace the low mantissa bits
+                            long long key = (lx > k && row < p && mg >= 0.0) ? ((__double_as_longlong(mg) & ~0x3ffLL) | (long long)(1023 - lx)) : -1LL;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(0xffffffffu, key, o); key = ok > key ? ok : key; }
+                            const double dk = __shfl_sync(0xffffffffu, mg, k);
+                            const double gb = key >= 0 ? __longlong_as_double(key & ~0x3ffLL) : -1.0;
+                            const bool keep = (key < 0) || (isfinite(dk) && dk > 0.0 && !(gb > FrontAbs<CPLX>::THRESH * dk));
+                            if (!keep) {
+                                const int gi = 1023 - (int)(key & 0x3ffLL), ip = kk0 + gi;
+                                const int src = lx == k ? gi : lx == gi ? k : lx;
+#pragma unroll
+                                for (int j = 0; j < SPW; j++) a[j] = front_shfl(a[j], src);
+                                for (int j = lx; j < wj; j += 32)
+                                    if (j < s0 || j >= s0 + ns) { T *x = Cs + kk + (size_t)ldc * j, *y = Cs + ip + (size_t)ldc * j; const T t = *x; *x = *y; *y = t; }
+                                for (int j = lx; j < c0; j += 32) { T *x = LUf + kk + (size_t)m * j, *y = LUf + ip + (size_t)m * j; const T t = *x; *x = *y; *y = t; }
+                                if (lx == 0) { ipiv[kk] = ip; *s_nswap += 1; }
+                            } else if (lx == 0) ipiv[kk] = kk;
+                            T prow[SPW];
+#pragma unroll
+                            for (int j = 0; j < SPW; j++) prow[j] = front_shfl(a[j], k);
+                            bool b1;
+                            const T rp = S::rcpf(prow[k], b1);
+                            bad |= b1;
+                            if (lx == k) {
+#pragma unroll
+                                for (int j = 0; j < SPW; j++) pub[k * SPW + j] = prow[j];
+                                pub[SPW * SPW + k] = rp;
+                            }
+                            if (lx > k && row < m) {
+                                const T l = S::mul(a[k], rp);
+                                a[k] = l;
+                                grow = max(grow, growth_key(l));
+#pragma unroll
+                                for (int j = k + 1; j < SPW; j++) if (j < ns) a[j] = S::fnma(a[j], l, prow[j]);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (wy > 0 && row < m) {
+#pragma unroll
+                    for (int k = 0; k < SPW; k++) {
+                        if (k < ns) {
+                            const T l = S::mul(a[k], pub[SPW * SPW + k]);
+                            a[k] = l;
+                            grow = max(grow, growth_key(l));
+#pragma unroll
+                            for (int j = k + 1; j < SPW; j++) if (j < ns) a[j] = S::fnma(a[j], l, pub[k * SPW + j]);
+                        }
+                    }
+                }
+            } else
 #pragma unroll
             for (int k = 0; k < SPW; k++) {
                 if (k < ns) {
@@ -831,7 +893,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
 #pragma unroll
                         for (int j = 0; j < SPW; j++) rowk[par * SPW + j] = a[j];
                         bool bb;
-                        rp_slot[par] = S::rcp(a[k], bb);     // the usual outcome (static pivot kept): one division per pivot, not one per thread
+                        rp_slot[par] = S::rcpf(a[k], bb);     // the usual outcome (static pivot kept): one division per pivot, not one per thread
                     }
                     __syncthreads();
                     double gb = -1.0;
@@ -860,7 +922,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
                     } else if (tid == 0) ipiv[kk] = kk;
                     T rp;
                     if (keep) { rp = rp_slot[par]; bad |= !(dk > 0.0) || !isfinite(dk); }
-                    else { bool b1; rp = S::rcp(prow[k], b1); bad |= b1; }
+                    else { bool b1; rp = S::rcpf(prow[k], b1); bad |= b1; }
                     if (tid > k && row < m) {
                         const T l = S::mul(a[k], rp);
                         a[k] = l;
@@ -904,7 +966,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
             if (c < p) {
                 for (int i = lx; i < m; i += 32) {
                     T v = cj[i];
-                    if (i == c) { bool b1; v = S::rcp(v, b1); }
+                    if (i == c) { bool b1; v = S::rcpf(v, b1); }
                     LUf[i + (size_t)m * c] = v;
                 }
             } else {
@@ -917,7 +979,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
     }
 #ifdef KRB_LL_PROFILE
     if (tid == 0)
-        for (int i = 0; i < 8; i++) atomicAdd(krb_ll_prof + i, (unsigned long long)llp[i]);
+        for (int i = 0; i < 8; i++) atomicAdd(krb_ll_prof + (NW == 16 ? 0 : NW == 8 ? 8 : 16) + i, (unsigned long long)llp[i]);
 #endif
     if (bad && tid == 0 && P.status) atomicOr(P.status + lane, KRB_LANE_ZERO_PIVOT);
     if (grow >= KRB_GROWTH_KEY && grow < KRB_NONFINITE_KEY && P.status) atomicOr(P.status + lane, KRB_LANE_INACCURATE);
@@ -973,19 +1035,16 @@ __global__ void __launch_bounds__(256) krb_front_factor_warp(const FrontParams P
         T v = mine ? F[lx + ld * k] : S::zero();
         int ip = k;
         if (k + 1 < p) {
-            double best = (lx > k && lx < p) ? FrontAbs<CPLX>::mag(v) : -1.0;
-            if (!(best >= 0.0)) best = -1.0;
-            int bi = lx;
+            // (magnitude, lowest row) in one 64-bit key: 10 index bits replace the low mantissa bits
+            const double mg = FrontAbs<CPLX>::mag(v);
+            long long key = (lx > k && lx < p && mg >= 0.0) ? ((__double_as_longlong(mg) & ~0x3ffLL) | (long long)(1023 - lx)) : -1LL;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            const double dk = __shfl_sync(0xffffffffu, FrontAbs<CPLX>::mag(v), k);
-            const bool keep = (best < 0.0) || (isfinite(dk) && dk > 0.0 && !(best > FrontAbs<CPLX>::THRESH * dk));
+            for (int o = 16; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(0xffffffffu, key, o); key = ok > key ? ok : key; }
+            const double dk = __shfl_sync(0xffffffffu, mg, k);
+            const double best = key >= 0 ? __longlong_as_double(key & ~0x3ffLL) : -1.0;
+            const bool keep = (key < 0) || (isfinite(dk) && dk > 0.0 && !(best > FrontAbs<CPLX>::THRESH * dk));
             if (!keep) {
-                ip = bi;
+                ip = 1023 - (int)(key & 0x3ffLL);
                 if (mine) { T *x = F + k + ld * lx, *y = F + ip + ld * lx; const T t = *x; *x = *y; *y = t; }   // lane j swaps column j
                 __syncwarp();
                 v = mine ? F[lx + ld * k] : S::zero();
@@ -993,7 +1052,7 @@ __global__ void __launch_bounds__(256) krb_front_factor_warp(const FrontParams P
         }
         if (lx == 0) ipiv[k] = ip;
         bool b1;
-        const T rp = S::rcp(front_shfl(v, k), b1);
+        const T rp = S::rcpf(front_shfl(v, k), b1);
         bad |= b1;
         T l = S::zero();
         const bool below = lx > k && mine;

@@ -18,6 +18,18 @@ constexpr uint32_t KRB_GROWTH_KEY = (uint32_t)(1023 + KRB_GROWTH_LIMIT_LOG2) << 
 constexpr uint32_t KRB_NONFINITE_KEY = 0x7ff00000u;
 
 
+// 1/x to ~1 ulp without the IEEE division's long instruction sequence (and its slow-path call): MUFU.RCP64H seed (2^-20) and two fused
+// correction steps, r0 (1 + e + e^2) with e = 1 - x r0.  Exponents near the ends of the range (the seed flushes / overflows) take the
+// exact division.  Used for pivot reciprocals on dependent chains; the LU is not bit-pinned (values are held to 1e-9).
+__device__ __forceinline__ double krb_fast_rcp(double x) {
+    const uint32_t e = ((uint32_t)__double2hiint(x) >> 20) & 0x7ffu;
+    if (e - 24u > 1999u) return 1.0 / x;
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    const double er = fma(-x, r0, 1.0);
+    return fma(r0, fma(er, er, er), r0);
+}
+
 template <bool CPLX> struct Sc;
 template <> struct Sc<false> {
     typedef double T;
@@ -30,6 +42,7 @@ template <> struct Sc<false> {
     static __device__ __forceinline__ T mul(T a, T b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ T fnma(T d, T a, T b) { return fma(-a, b, d); }
     static __device__ __forceinline__ T rcp(T a, bool &bad) { bad = !(fabs(a) > 0.0) || !isfinite(a); return 1.0 / a; }
+    static __device__ __forceinline__ T rcpf(T a, bool &bad) { bad = !(fabs(a) > 0.0) || !isfinite(a); return krb_fast_rcp(a); }
     static __device__ __forceinline__ T mulj(T a) { return a; }
     static __device__ __forceinline__ bool finite(T a) { return isfinite(a); }
 };
@@ -52,6 +65,12 @@ template <> struct Sc<true> {
         const double ns = fma(a.x, a.x, a.y * a.y);
         bad = !(ns > 0.0) || !isfinite(ns);
         const double r = 1.0 / ns;
+        return make_double2(a.x * r, -a.y * r);
+    }
+    static __device__ __forceinline__ T rcpf(T a, bool &bad) {
+        const double ns = fma(a.x, a.x, a.y * a.y);
+        bad = !(ns > 0.0) || !isfinite(ns);
+        const double r = krb_fast_rcp(ns);
         return make_double2(a.x * r, -a.y * r);
     }
     static __device__ __forceinline__ T mulj(T a) { return make_double2(0.0, a.x); }
