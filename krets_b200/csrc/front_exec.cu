@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -162,6 +163,10 @@ static int upload_front(Plan &plan) {
                 while (sm_b < (size_t)D.smem_cap && front_ll_width(m0, front_ll_ldc(m0), (long long)(sm_b / ts) - FRONT_LL_AUX) < 8) sm_b *= 2;
                 L.smem = std::min(sm_b, (size_t)D.smem_cap);
                 L.block = dim3(32, L.ll);
+                for (int k = i; k < j; k++) {      // per-front column-block width for this launch's shared memory
+                    const int f = fp.level_fronts[k], mf = msize(f);
+                    desc[f].pad = front_ll_width(mf, front_ll_ldc(mf), (long long)(L.smem / ts) - FRONT_LL_AUX);
+                }
             }
             if (c >= 5) {   // warp per (front, lane): 8 pairs per CTA while four CTAs still fit an SM, else 4
                 L.warp = true;

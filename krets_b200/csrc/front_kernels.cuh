@@ -28,7 +28,7 @@ struct FrontDesc {            // one per front, 64 B
     int p, q, piv0, idx_off;  // idx_off: into idx_unknown / rel
     int child_begin, child_end, asm_begin, asm_end;
     long long lu_off, cb_off, fw_off;   // fw_off < 0: the front is staged in shared memory
-    int cbv_off, pad;
+    int cbv_off, pad;         // pad: column-block width of krb_front_factor_ll for this front (its launch's shared memory)
 };
 struct FrontChild {           // one per tree edge, indexed like the child list: what a parent needs from the child, 32 B
     int q, idx_off, cbv_off, pad;
@@ -201,11 +201,13 @@ template <> struct FrontAbs<false> {
     static __device__ __forceinline__ double mag(double v) { return fabs(v); }
     static __device__ __forceinline__ double abs1(double v) { return fabs(v); }
     static constexpr double THRESH = 8.0;
+    static constexpr uint32_t LOG2T = 3;
 };
 template <> struct FrontAbs<true> {
     static __device__ __forceinline__ double mag(double2 v) { return fma(v.x, v.x, v.y * v.y); }
     static __device__ __forceinline__ double abs1(double2 v) { return fabs(v.x) + fabs(v.y); }
     static constexpr double THRESH = 64.0;
+    static constexpr uint32_t LOG2T = 6;
 };
 
 __device__ __forceinline__ double front_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -687,7 +689,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
     const int p = d.p, q = d.q, m = p + q;
     const int lx = threadIdx.x, wy = threadIdx.y, tid = wy * 32 + lx;
     const int ldc = front_ll_ldc(m);
-    const int W = front_ll_width(m, ldc, (long long)P.smem_elems - FRONT_LL_AUX);
+    const int W = d.pad;                                 // front_ll_width(m, ldc, shared memory of this launch), computed on the host
     T *Ls = Cs + (size_t)ldc * W;                        // [W][W] strictly lower part of L_KK
     bool bad = false;
     uint32_t grow = 0;
@@ -712,37 +714,39 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
             if (c >= c0 && c < c0 + wj) Cs[r + (size_t)ldc * (c - c0)] = A[__ldg(P.asm_ent + t)];
         }
         __syncthreads();
+        // children: warp w owns the block's columns w, w + NW, ... — two children that add into the same entry are handled by the same warp
+        // in program order, so the children need no block-wide barrier between them (ncu/cycle profile r2s: the assembly was a third of
+        // the mid-size fronts' time, a chain of dependent loads and barriers per child)
         for (int ci = d.child_begin; ci < d.child_end; ci++) {
             const FrontChild c = P.childrec[ci];
             const int qc = c.q;
             const int *rel = P.rel + c.idx_off;
-            // the child's columns that land in this block: rel is ascending, so two block-wide counts give the range
-            int j0 = 0, j1 = 0;
-            for (int b = 0; b < qc; b += NT) {
-                const int rv = (b + tid < qc) ? __ldg(rel + b + tid) : 0x7fffffff;
-                j0 += __syncthreads_count(rv < c0);
-                j1 += __syncthreads_count(rv < c0 + wj);
-            }
-            if (j0 < j1) {
-                // a lane's rows (and their relative indices) are the same for every column: fetched once, four rows' loads in flight
-                const T *CBc = reinterpret_cast<const T *>(P.CB) + lane * P.cb_stride + c.cb_off;
-                for (int ib = lx; ib < qc; ib += 128) {
-                    int ri[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) ri[u] = (ib + 32 * u < qc) ? __ldg(rel + ib + 32 * u) : -1;
-                    for (int jc = j0 + wy; jc < j1; jc += NW) {
-                        T *dst = Cs + (size_t)ldc * (__ldg(rel + jc) - c0);
-                        const T *src = CBc + (size_t)qc * jc + ib;
+            const T *CBc = reinterpret_cast<const T *>(P.CB) + lane * P.cb_stride + c.cb_off;
+            for (int jb = 0; jb < qc; jb += 32) {
+                const int dcol = (jb + lx < qc) ? __ldg(rel + jb + lx) - c0 : -1;
+                unsigned mask = __ballot_sync(0xffffffffu, dcol >= 0 && dcol < wj && (dcol & (NW - 1)) == wy);
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    T *dst = Cs + (size_t)ldc * __shfl_sync(0xffffffffu, dcol, b);
+                    const T *src = CBc + (size_t)qc * (jb + b);
+                    for (int ib = lx; ib < qc; ib += 128) {
+                        int ri[4];
                         T v[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) v[u] = ri[u] >= 0 ? src[32 * u] : S::zero();
+                        for (int u = 0; u < 4; u++) {
+                            const bool in = ib + 32 * u < qc;
+                            ri[u] = in ? __ldg(rel + ib + 32 * u) : -1;
+                            v[u] = in ? src[ib + 32 * u] : S::zero();
+                        }
 #pragma unroll
                         for (int u = 0; u < 4; u++) if (ri[u] >= 0) { T *e = dst + ri[u]; *e = S::add(*e, v[u]); }
                     }
                 }
             }
-            __syncthreads();          // the next child may add to the same entries
+            __syncwarp();
         }
+        __syncthreads();
         // ---- (b) interchanges of all earlier pivots (rare) ----
         const int kdone = c0 < p ? c0 : p;
         if (*s_nswap > 0 && kdone > 0) {
@@ -805,77 +809,88 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
             const int ns = (npiv - s0) < SPW ? (npiv - s0) : SPW;
             const int kk0 = c0 + s0;                  // front row / column of the sub-panel's first pivot
             const int row = kk0 + tid;                // this thread's row (m - kk0 <= 512)
+            // a[0] is always the CURRENT pivot column's entry of this thread's row, a[1..] the columns right of it: after every pivot the
+            // row shifts left by one, finished values (multipliers l, the pivot row's U entries) go to shared memory at once.  The pivot
+            // loops are therefore ROLLED: unrolled 8x (two paths) they were ~40 KB of straight-line code that every front runs once, on a
+            // single warp — instruction-fetch bound (cycle profile r2s: ~1 800 cycles per pivot for a ~300-cycle dependent chain).
             T a[SPW];
 #pragma unroll
             for (int k = 0; k < SPW; k++) a[k] = (k < ns && row < m) ? Cs[row + (size_t)ldc * (s0 + k)] : S::zero();
             if (p - kk0 <= 32) {
                 // every candidate row of this sub-panel belongs to warp 0 (always the case for mid-size fronts, p <= 32): that warp runs the
-                // whole pivot sequence with shuffles and publishes the pivot rows; the other warps apply them to their rows after ONE barrier
-                T *pub = slot_rows;                  // [SPW][SPW] pivot rows, then [SPW] reciprocal pivots
+                // whole pivot sequence with warp primitives and publishes the pivot rows; the other warps apply them after ONE barrier
+                T *pub = slot_rows;                  // [SPW][SPW] pivot rows (shifted: pub[k][j] = U(kk, kk + j)), then [SPW] reciprocal pivots
                 if (wy == 0) {
-#pragma unroll
-                    for (int k = 0; k < SPW; k++) {
-                        if (k < ns) {
-                            const int kk = kk0 + k;
-                            const double mg = FrontAbs<CPLX>::mag(a[k]);
+#pragma unroll 1
+                    for (int k = 0; k < ns; k++) {
+                        const int kk = kk0 + k;
+                        const double mg = FrontAbs<CPLX>::mag(a[0]);
+                        const bool cand = lx > k && row < p && mg >= 0.0;
+                        // usual outcome, one REDUX: no candidate's magnitude (high word) exceeds THRESH x the static pivot's
+                        const uint32_t mx = __reduce_max_sync(0xffffffffu, cand ? (uint32_t)__double2hiint(mg) : 0u);
+                        const double dk = __shfl_sync(0xffffffffu, mg, k);
+                        bool keep = isfinite(dk) && dk > 0.0 && mx <= (uint32_t)__double2hiint(dk) + (FrontAbs<CPLX>::LOG2T << 20);
+                        if (!keep) {
                             // (magnitude, lowest row) in one 64-bit key: 10 index bits replace the low mantissa bits
-                            long long key = (lx > k && row < p && mg >= 0.0) ? ((__double_as_longlong(mg) & ~0x3ffLL) | (long long)(1023 - lx)) : -1LL;
+                            long long key = cand ? ((__double_as_longlong(mg) & ~0x3ffLL) | (long long)(1023 - lx)) : -1LL;
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(0xffffffffu, key, o); key = ok > key ? ok : key; }
-                            const double dk = __shfl_sync(0xffffffffu, mg, k);
                             const double gb = key >= 0 ? __longlong_as_double(key & ~0x3ffLL) : -1.0;
-                            const bool keep = (key < 0) || (isfinite(dk) && dk > 0.0 && !(gb > FrontAbs<CPLX>::THRESH * dk));
+                            keep = (key < 0) || (isfinite(dk) && dk > 0.0 && !(gb > FrontAbs<CPLX>::THRESH * dk));
                             if (!keep) {
+                                // rows kk <-> ip: the two lanes exchange their register rows, the warp swaps the rest of the two rows (the
+                                // block's other columns incl. this sub-panel's finished ones, the finished L columns left of the block)
                                 const int gi = 1023 - (int)(key & 0x3ffLL), ip = kk0 + gi;
                                 const int src = lx == k ? gi : lx == gi ? k : lx;
 #pragma unroll
                                 for (int j = 0; j < SPW; j++) a[j] = front_shfl(a[j], src);
                                 for (int j = lx; j < wj; j += 32)
-                                    if (j < s0 || j >= s0 + ns) { T *x = Cs + kk + (size_t)ldc * j, *y = Cs + ip + (size_t)ldc * j; const T t = *x; *x = *y; *y = t; }
+                                    if (j < s0 + k || j >= s0 + ns) { T *x = Cs + kk + (size_t)ldc * j, *y = Cs + ip + (size_t)ldc * j; const T t = *x; *x = *y; *y = t; }
                                 for (int j = lx; j < c0; j += 32) { T *x = LUf + kk + (size_t)m * j, *y = LUf + ip + (size_t)m * j; const T t = *x; *x = *y; *y = t; }
                                 if (lx == 0) { ipiv[kk] = ip; *s_nswap += 1; }
-                            } else if (lx == 0) ipiv[kk] = kk;
-                            T prow[SPW];
-#pragma unroll
-                            for (int j = 0; j < SPW; j++) prow[j] = front_shfl(a[j], k);
-                            bool b1;
-                            const T rp = S::rcpf(prow[k], b1);
-                            bad |= b1;
-                            if (lx == k) {
-#pragma unroll
-                                for (int j = 0; j < SPW; j++) pub[k * SPW + j] = prow[j];
-                                pub[SPW * SPW + k] = rp;
                             }
-                            if (lx > k && row < m) {
-                                const T l = S::mul(a[k], rp);
-                                a[k] = l;
-                                grow = max(grow, growth_key(l));
+                        }
+                        if (keep && lx == 0) ipiv[kk] = kk;
+                        if (lx == k) {                // the pivot row: published for everybody, and final (its U entries)
 #pragma unroll
-                                for (int j = k + 1; j < SPW; j++) if (j < ns) a[j] = S::fnma(a[j], l, prow[j]);
+                            for (int j = 0; j < SPW; j++) {
+                                pub[k * SPW + j] = a[j];
+                                if (k + j < ns) Cs[kk + (size_t)ldc * (s0 + k + j)] = a[j];
                             }
+                        }
+                        __syncwarp();
+                        bool b1;
+                        const T rp = S::rcpf(pub[k * SPW], b1);
+                        bad |= b1;
+                        if (lx == k) pub[SPW * SPW + k] = rp;
+                        if (lx > k && row < m) {
+                            const T l = S::mul(a[0], rp);
+                            Cs[row + (size_t)ldc * (s0 + k)] = l;
+                            grow = max(grow, growth_key(l));
+#pragma unroll
+                            for (int j = 1; j < SPW; j++) a[j - 1] = S::fnma(a[j], l, pub[k * SPW + j]);
+                            a[SPW - 1] = S::zero();
                         }
                     }
                 }
                 __syncthreads();
                 if (wy > 0 && row < m) {
+#pragma unroll 1
+                    for (int k = 0; k < ns; k++) {
+                        const T l = S::mul(a[0], pub[SPW * SPW + k]);
+                        Cs[row + (size_t)ldc * (s0 + k)] = l;
+                        grow = max(grow, growth_key(l));
 #pragma unroll
-                    for (int k = 0; k < SPW; k++) {
-                        if (k < ns) {
-                            const T l = S::mul(a[k], pub[SPW * SPW + k]);
-                            a[k] = l;
-                            grow = max(grow, growth_key(l));
-#pragma unroll
-                            for (int j = k + 1; j < SPW; j++) if (j < ns) a[j] = S::fnma(a[j], l, pub[k * SPW + j]);
-                        }
+                        for (int j = 1; j < SPW; j++) a[j - 1] = S::fnma(a[j], l, pub[k * SPW + j]);
+                        a[SPW - 1] = S::zero();
                     }
                 }
-            } else
-#pragma unroll
-            for (int k = 0; k < SPW; k++) {
-                if (k < ns) {
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < ns; k++) {
                     const int kk = kk0 + k, par = k & 1;
                     // candidates: fully-summed rows below the static pivot position
-                    double best = (row > kk && row < p) ? FrontAbs<CPLX>::mag(a[k]) : -1.0;
+                    double best = (row > kk && row < p) ? FrontAbs<CPLX>::mag(a[0]) : -1.0;
                     if (!(best >= 0.0)) best = -1.0;          // nan never wins
                     int bi = tid;
 #pragma unroll
@@ -893,19 +908,18 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
 #pragma unroll
                         for (int j = 0; j < SPW; j++) rowk[par * SPW + j] = a[j];
                         bool bb;
-                        rp_slot[par] = S::rcpf(a[k], bb);     // the usual outcome (static pivot kept): one division per pivot, not one per thread
+                        rp_slot[par] = S::rcpf(a[0], bb);     // the usual outcome (static pivot kept): one division per pivot, not one per thread
                     }
                     __syncthreads();
                     double gb = -1.0;
                     int gi = k, gw = 0;
 #pragma unroll
                     for (int w = 0; w < NW; w++) { const double v = slot_mag[par * NW + w]; if (v > gb) { gb = v; gi = slot_idx[par * NW + w]; gw = w; } }
-                    const double dk = FrontAbs<CPLX>::mag(rowk[par * SPW + k]);
+                    const double dk = FrontAbs<CPLX>::mag(rowk[par * SPW]);
                     const bool keep = (gb < 0.0) || (isfinite(dk) && dk > 0.0 && !(gb > FrontAbs<CPLX>::THRESH * dk));
                     const T *prow = keep ? rowk + par * SPW : slot_rows + (par * NW + gw) * SPW;
                     if (!keep) {
-                        // rows kk <-> ip = kk0 + gi: the two owners exchange their register rows, helper threads the rest of the block's
-                        // columns and the finished L columns left of the block
+                        // rows kk <-> ip = kk0 + gi: the two owners exchange their register rows, helper threads the rest of the two rows
                         const int ip = kk0 + gi;
                         if (tid == gi) {
 #pragma unroll
@@ -916,26 +930,28 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
                             for (int j = 0; j < SPW; j++) a[j] = prow[j];
                         }
                         for (int j = tid; j < wj; j += NT)
-                            if (j < s0 || j >= s0 + ns) { T *x = Cs + kk + (size_t)ldc * j, *y = Cs + ip + (size_t)ldc * j; const T t = *x; *x = *y; *y = t; }
+                            if (j < s0 + k || j >= s0 + ns) { T *x = Cs + kk + (size_t)ldc * j, *y = Cs + ip + (size_t)ldc * j; const T t = *x; *x = *y; *y = t; }
                         for (int j = tid; j < c0; j += NT) { T *x = LUf + kk + (size_t)m * j, *y = LUf + ip + (size_t)m * j; const T t = *x; *x = *y; *y = t; }
                         if (tid == 0) { ipiv[kk] = ip; *s_nswap += 1; }
                     } else if (tid == 0) ipiv[kk] = kk;
                     T rp;
                     if (keep) { rp = rp_slot[par]; bad |= !(dk > 0.0) || !isfinite(dk); }
-                    else { bool b1; rp = S::rcpf(prow[k], b1); bad |= b1; }
+                    else { bool b1; rp = S::rcpf(prow[0], b1); bad |= b1; }
+                    if (tid == k) {                           // the pivot row is final: its U entries
+#pragma unroll
+                        for (int j = 0; j < SPW; j++) if (k + j < ns) Cs[kk + (size_t)ldc * (s0 + k + j)] = a[j];
+                    }
                     if (tid > k && row < m) {
-                        const T l = S::mul(a[k], rp);
-                        a[k] = l;
+                        const T l = S::mul(a[0], rp);
+                        Cs[row + (size_t)ldc * (s0 + k)] = l;
                         grow = max(grow, growth_key(l));
 #pragma unroll
-                        for (int j = k + 1; j < SPW; j++) if (j < ns) a[j] = S::fnma(a[j], l, prow[j]);
+                        for (int j = 1; j < SPW; j++) a[j - 1] = S::fnma(a[j], l, prow[j]);
+                        a[SPW - 1] = S::zero();
                     }
                 }
             }
             LLP(4);
-            if (row < m)
-#pragma unroll
-                for (int k = 0; k < SPW; k++) if (k < ns) Cs[row + (size_t)ldc * (s0 + k)] = a[k];
             __syncthreads();
             const int rest = wj - (s0 + ns);          // columns of the block right of the sub-panel
             if (tid < rest) {                         // their U rows: unit-lower solve with the sub-panel's diagonal block
