@@ -366,7 +366,9 @@ def make_workload(name, args, rank):
         circuit = kb.parse_circuit_description(text)
         kinds = [circuit.element(e).kind for e in range(circuit.num_elements)]
         varied = [e for e, k in enumerate(kinds) if k in (api.KIND_R, api.KIND_C, api.KIND_L)]
-        lanes = (512 if transient else 256) if dflt else args.lanes
+        # lanes per GPU: whole waves of the one-CTA-per-SM launches of the top tree levels (a single front per level: lanes CTAs)
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        lanes = ((4 if transient else 2) * sms) if dflt else args.lanes
         host_vals = mc_matrix(circuit, varied, lanes, rank * lanes)
         vals = torch.from_numpy(host_vals).cuda()
         n = circuit.n

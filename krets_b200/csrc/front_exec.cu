@@ -469,6 +469,10 @@ int run_front(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     chunk = std::min<long long>(chunk, a.lanes);
     chunk = std::min<long long>(chunk, 65535);
     long long window = 256;
+    {   // factor windows of whole waves: the top tree levels launch one CTA per (front, lane) at one CTA per SM
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) window = 2 * sms;
+    }
     if (const char *e = getenv("KRB_FRONT_WINDOW")) window = std::max(1, atoi(e));
     window = std::min(window, chunk);
     {

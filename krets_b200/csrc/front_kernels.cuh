@@ -516,6 +516,7 @@ __device__ __forceinline__ int front_lower_bound(const int *__restrict__ a, int 
 // column-block width for a front of m rows (ldc = padded leading dimension) in `elems` elements of shared memory: W columns of the
 // front + a W x W staging block for L_KK; at most 64 (one pass of the 4 x 4 warp grid), then balanced over the blocks
 __host__ __device__ inline int front_ll_width(int m, int ldc, long long elems) {
+    if ((long long)m * ldc <= elems) return m;           // the whole front is one block (no L_KK staging): mid-size fronts
     int W = 1;
     while (W < 64 && (long long)(W + 1) * ldc + (long long)(W + 1) * (W + 1) <= elems) W++;
     const int nblk = (m + W - 1) / W;
@@ -699,6 +700,17 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
     T *CBf = reinterpret_cast<T *>(P.CB) + lane * P.cb_stride + d.cb_off;
     const T *A = reinterpret_cast<const T *>(P.A) + lane * P.a_stride;
     if (tid == 0) *s_nswap = 0;
+    if (NW == 4) {
+        // mid-size fronts have ~4 small children each: their contribution blocks and index lists are requested from HBM now, so that
+        // the per-child chains of dependent loads below (record -> relative indices -> block) find them in L2
+        for (int ci = d.child_begin + wy; ci < d.child_end; ci += NW) {
+            const FrontChild c = P.childrec[ci];
+            const char *cb = reinterpret_cast<const char *>(reinterpret_cast<const T *>(P.CB) + lane * P.cb_stride + c.cb_off);
+            const size_t bytes = (size_t)c.q * c.q * sizeof(T);
+            for (size_t o = (size_t)lx * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(cb + o));
+            if (lx * 32 < c.q) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.rel + c.idx_off + lx * 32));
+        }
+    }
 #ifdef KRB_LL_PROFILE
     long long llp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0_ = clock64();
 #endif
