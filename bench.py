@@ -36,8 +36,8 @@ LANES_PER_GPU = 65536
 STEP = 2.0 ** -16
 METRIC = "solved sweep points/sec (batched sparse LU)"
 UNIT = "points/s"
-ALL_WORKLOADS = ["ladder_dc", "rc_ac", "dual_rc_tran", "dual_rc_tran_be", "mesh_tran", "mesh_ac", "ladder_mc"]
-OTHER_WORKLOADS = ["rc_ac", "ladder_mc", "dual_rc_tran", "dual_rc_tran_be", "mesh_ac", "mesh_tran"]   # other_configs of the default line
+ALL_WORKLOADS = ["ladder_dc", "rc_ac", "dual_rc_tran", "dual_rc_tran_be", "mesh_tran", "mesh_ac", "ladder_mc", "rectifier_tran"]
+OTHER_WORKLOADS = ["rc_ac", "ladder_mc", "dual_rc_tran", "dual_rc_tran_be", "mesh_ac", "mesh_tran", "rectifier_tran"]   # other_configs of the default line
 
 
 def workload_config(n_gpus):
@@ -359,6 +359,42 @@ def make_workload(name, args, rank):
                         alg=8 * (int(plan.info.nnz_lu) + 3 * circuit.n), alg_what="B_step = s*(nnz_lu + 3*n), SURVEY 8(d)",
                         moved=8 * circuit.n, moved_what="s*n: one result row per solved point (factors and state stay on chip)",
                         traffic_key="krb_dense_tran_config4_bytes_per_launch" if dflt and not args.tran_steps else None, check=check)
+    if name == "rectifier_tran":
+        # The nonlinear path (north star (d)): the reference's own rectifier test circuit (circuits/rectifier: four diodes, R, C, two sine
+        # sources; test_transient.rs) stepped with backward Euler, Newton-Raphson with the per-lane convergence mask at every step, on the
+        # lane VM; Monte-Carlo lanes vary R1 / C1.  Not a BASELINE config: it puts a number on the interpreter-bound path.
+        text = golden["netlists"]["rectifier"]
+        circuit = kb.parse_circuit_description(text)
+        names = ["C1", "R1"]
+        varied = [circuit.element_index(nm) for nm in names]
+        lanes = 16384 if dflt else args.lanes
+        nsteps = args.tran_steps or 1000
+        h = 50e-6
+        host_vals = np.array([[circuit.element_value(e) * netgen.mc_factor(l, j, 2) for l in range(rank * lanes, (rank + 1) * lanes)] for j, e in enumerate(varied)])
+        vals = torch.from_numpy(host_vals).cuda()
+        pdc = kb.Plan(circuit, api.MODE_DC, varied=varied)
+        plan = kb.Plan(circuit, api.MODE_TRAN, varied=varied, time_step=h)
+        out = torch.empty((lanes, nsteps + 1, circuit.n), dtype=torch.float64, device="cuda")
+
+        def check(k=2):
+            from oracle import oracle
+            idx = np.random.default_rng(7).choice(lanes, size=min(k, lanes), replace=False)
+            worst = 0.0
+            for l in idx:
+                oc = oracle.Circuit(text)
+                for j, nm in enumerate(names):
+                    oc.set_element_value(oc.element_index(nm), host_vals[j, l])
+                _, ref = oc.solve_tran(h, nsteps * h)
+                worst = max(worst, _rel_err(out[int(l)].cpu().numpy(), ref))
+            return {"lanes_checked": int(len(idx)), "rows_per_lane": nsteps + 1, "max_rel_err_vs_oracle": worst,
+                    "tolerance": "1e-6: Newton-Raphson with exp(); libm and CUDA exp differ in the last ulp (tests/test_gpu_parity.py::test_transient_rectifier)"}
+        return Workload(name=name, config="nonlinear", plan=plan, circuit=circuit, lanes=lanes, points=lanes * nsteps, dtype="f64", s=8, out=out,
+                        step=lambda: plan.solve_transient(pdc, nsteps, lanes, varied_values=vals, out=out),
+                        kernel="krb_lane_vm<f64> (interpreted lane program: stamp + LDU + solve per Newton iteration, per-lane convergence mask)",
+                        what=f"circuits/rectifier (4 diodes) transient, {nsteps} backward-Euler steps x {lanes} Monte-Carlo R/C variants per GPU, Newton-Raphson at every step (nonlinear path; not a BASELINE config)",
+                        alg=8 * (int(plan.info.nnz_lu) + 3 * circuit.n), alg_what="B_step = s*(nnz_lu + 3*n) per Newton iteration (at least two per point), SURVEY 8(d)",
+                        moved=8 * circuit.n, moved_what="s*n: one result row per solved point (the lane program's working set stays on chip)",
+                        traffic_key=None, check=check)
     if name in ("mesh_ac", "mesh_tran"):                # BASELINE config 5
         transient = name == "mesh_tran"
         g = args.mesh_grid
