@@ -770,50 +770,67 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
         }
         LLP(0);
         // ---- (c) left-looking: the earlier pivot panels ----
-        for (int k0 = 0; k0 < kdone; k0 += W) {
-            const int wk = (p - k0) < W ? (p - k0) : W;
-            for (int e = tid; e < wk * wk; e += NT) {
-                const int k = e / wk, r = e - k * wk;
-                Ls[e] = r > k ? LUf[(k0 + r) + (size_t)m * (k0 + k)] : S::zero();
-            }
-            __syncthreads();
-            LLP(1);
+        // earlier panels are taken in PAIRS: after the first panel's U rows only the second panel's own rows are updated (a small
+        // product), then both panels update everything below them in ONE pass with K = 2W — half as many accumulator round trips through
+        // shared memory and exposed first-fragment loads per DMMA flop (cycle profile r2s: the DMMA phases ran at ~35 % of the tensor peak
+        // with 8-10 k-steps per accumulator tile)
+        for (int k0 = 0; k0 < kdone;) {
+            const int wk0 = (p - k0) < W ? (p - k0) : W;
+            const int k1 = k0 + wk0;
+            const bool pair = k1 < kdone;
+            const int wk1 = pair ? ((p - k1) < W ? (p - k1) : W) : 0;
+            for (int h = 0; h < (pair ? 2 : 1); h++) {
+                const int kb = h ? k1 : k0, wb = h ? wk1 : wk0;
+                if (h) {
+                    FrontMma<CPLX, NW>::update(Cs + k1, ldc, wk1, wj, LUf + k1 + (size_t)m * k0, m, Cs + k0, ldc, wk0, lx, wy);
+                    __syncthreads();
+                    LLP(3);
+                }
+                for (int e = tid; e < wb * wb; e += NT) {
+                    const int k = e / wb, r = e - k * wb;
+                    Ls[e] = r > k ? LUf[(kb + r) + (size_t)m * (kb + k)] : S::zero();
+                }
+                __syncthreads();
+                LLP(1);
             {   // U_KJ = L_KK^-1 C_K: 8 lanes per column; the 8 x 8 diagonal steps redundantly, the rows below them split over the lanes
-                const int r8 = tid & 7;
-                for (int cb = 0; cb < wj; cb += NT / 8) {
-                const int col = cb + (tid >> 3);
-                const bool act = col < wj;
-                T *cj = Cs + k0 + (size_t)ldc * (act ? col : 0);
-                for (int s0 = 0; s0 < wk; s0 += 8) {
-                    const int ns = (wk - s0) < 8 ? (wk - s0) : 8;
-                    T v[8];
+                    const int r8 = tid & 7;
+                    for (int cb = 0; cb < wj; cb += NT / 8) {
+                    const int col = cb + (tid >> 3);
+                    const bool act = col < wj;
+                    T *cj = Cs + kb + (size_t)ldc * (act ? col : 0);
+                    for (int s0 = 0; s0 < wb; s0 += 8) {
+                        const int ns = (wb - s0) < 8 ? (wb - s0) : 8;
+                        T v[8];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = k < ns ? cj[s0 + k] : S::zero();
+                        for (int k = 0; k < 8; k++) v[k] = k < ns ? cj[s0 + k] : S::zero();
 #pragma unroll
-                    for (int k = 0; k < 8; k++)
+                        for (int k = 0; k < 8; k++)
 #pragma unroll
-                        for (int r = k + 1; r < 8; r++)
-                            if (r < ns) v[r] = S::fnma(v[r], Ls[(s0 + r) + wk * (s0 + k)], v[k]);
-                    __syncwarp();                 // every lane of the group has read the 8 rows
-                    if (act && r8 == 0)
+                            for (int r = k + 1; r < 8; r++)
+                                if (r < ns) v[r] = S::fnma(v[r], Ls[(s0 + r) + wb * (s0 + k)], v[k]);
+                        __syncwarp();                 // every lane of the group has read the 8 rows
+                        if (act && r8 == 0)
 #pragma unroll
-                        for (int k = 0; k < 8; k++) if (k < ns) cj[s0 + k] = v[k];
-                    for (int r = s0 + 8 + r8; r < wk; r += 8) {
-                        T acc = cj[r];
+                            for (int k = 0; k < 8; k++) if (k < ns) cj[s0 + k] = v[k];
+                        for (int r = s0 + 8 + r8; r < wb; r += 8) {
+                            T acc = cj[r];
 #pragma unroll
-                        for (int k = 0; k < 8; k++) if (k < ns) acc = S::fnma(acc, Ls[r + wk * (s0 + k)], v[k]);
-                        if (act) cj[r] = acc;
+                            for (int k = 0; k < 8; k++) if (k < ns) acc = S::fnma(acc, Ls[r + wb * (s0 + k)], v[k]);
+                            if (act) cj[r] = acc;
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
+                    }
                 }
-                }
+                __syncthreads();
+                LLP(2);
             }
-            __syncthreads();
-            LLP(2);
-            if (m - (k0 + wk) > 0)
-                FrontMma<CPLX, NW>::update(Cs + (k0 + wk), ldc, m - (k0 + wk), wj, LUf + (k0 + wk) + (size_t)m * k0, m, Cs + k0, ldc, wk, lx, wy);
+            const int kend = k1 + wk1;
+            if (m - kend > 0)
+                FrontMma<CPLX, NW>::update(Cs + kend, ldc, m - kend, wj, LUf + kend + (size_t)m * k0, m, Cs + k0, ldc, wk0 + wk1, lx, wy);
             __syncthreads();
             LLP(3);
+            k0 = kend;
         }
         // ---- (d) the block's own pivot columns, sub-panels of SPW columns, one row per thread in registers ----
         const int npiv = (c0 < p) ? ((p - c0) < wj ? (p - c0) : wj) : 0;
