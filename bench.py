@@ -770,7 +770,7 @@ def main():
             "config": workload_config(world) if (args.workload == "ladder_dc" and lanes == LANES_PER_GPU) else
                       {"workload": main_res["workload"], "n_unknowns": n, "nnz": int(info.nnz), "lanes_per_gpu": lanes, "lanes_total": lanes * world,
                        "sharding": f"independent lanes, {world} rank(s), no data-path collective",
-                       "l2": f"per-step working set ({main_res['roofline']['bytes_per_point'] * main_res['lanes_per_gpu'] / 1e9:.2f} GB of inputs + results per step) >> 126 MB L2; no explicit flush",
+                       "l2": f"per-step working set ({main_res['roofline']['bytes_per_point'] * main_res['value'] * main_res['ms_per_step'] * 1e-3 / world / 1e9:.2f} GB per GPU and step on the roofline's byte model) >> 126 MB L2; no explicit flush",
                        "result_layout": "point-major x[lane][unknown] (one vector per solved point, as the reference returns)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
             "plan": {"executor": {0: "lane_vm", 1: "chain", 2: "front"}[int(info.executor)], "nnz_lu": int(info.nnz_lu), "flops_per_point": int(info.flops_per_point)},
