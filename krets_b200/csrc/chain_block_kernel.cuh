@@ -57,6 +57,15 @@ constexpr int KRB_BLOCK_DMAX = 256;   // entries of the shared-memory dictionary
 constexpr int KRB_BLOCK_DMAX_CPLX = 64;   // complex plans: two 80 KB lane buffers leave room for 64 entries (227 KB per CTA)
 template <bool CPLX> struct BlockDmax { static constexpr int value = CPLX ? KRB_BLOCK_DMAX_CPLX : KRB_BLOCK_DMAX; };
 // shared-memory footprint in elements of V (runtime.cu sizes the launch with the same expression)
+template <bool CPLX> struct BlockShfl;
+template <> struct BlockShfl<false> {
+    static __device__ __forceinline__ double up(double v, int s) { return __shfl_up_sync(0xffffffffu, v, s); }
+    static __device__ __forceinline__ double down(double v, int s) { return __shfl_down_sync(0xffffffffu, v, s); }
+};
+template <> struct BlockShfl<true> {
+    static __device__ __forceinline__ double2 up(double2 v, int s) { return make_double2(__shfl_up_sync(0xffffffffu, v.x, s), __shfl_up_sync(0xffffffffu, v.y, s)); }
+    static __device__ __forceinline__ double2 down(double2 v, int s) { return make_double2(__shfl_down_sync(0xffffffffu, v.x, s), __shfl_down_sync(0xffffffffu, v.y, s)); }
+};
 template <bool CPLX, int T, int M, bool SD> constexpr size_t block_smem_elems() {
     return (size_t)T * ((M & 1) ? M : M + 1) + ((size_t)T * M + 2) + (size_t)6 * T + 16 + (SD ? (size_t)5 * BlockDmax<CPLX>::value : 0);
 }
@@ -534,6 +543,32 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) krb_chain_block_kernel(co
                 reduce_row(ini2[t], ini2[TQ + t], ini2[2 * TQ + t], ap, cp, dq, true);
                 pa[t] = a; pa[TQ + t] = c; pa[2 * TQ + t] = d;
                 bar_lower(2, TQ);
+#ifndef KRB_OLD_SMEM_PCR
+                // real plans (TQ = 64): a third cyclic-reduction level leaves 32 rows, which ONE warp reduces by parallel cyclic reduction
+                // in registers (neighbour rows by shuffle: no shared-memory round trips, no barriers) instead of six shared-memory PCR steps
+                // with a two-warp barrier each; the even rows of the 64 follow by substitution
+                if (!CPLX && TQ == 64) {
+                    if (t < 32) {
+                        const V ea = pa[2 * t], ec = pa[TQ + 2 * t], ed = pa[2 * TQ + 2 * t];            // row 2t: kept for the substitution
+                        a = pa[2 * t + 1]; c = pa[TQ + 2 * t + 1]; d = pa[2 * TQ + 2 * t + 1];
+                        V ap3 = S::zero(), cp3 = S::zero(), dq3 = S::zero();
+                        if (2 * t + 2 < TQ) { ap3 = pa[2 * t + 2]; cp3 = pa[TQ + 2 * t + 2]; dq3 = pa[2 * TQ + 2 * t + 2]; }
+                        reduce_row(ea, ec, ed, ap3, cp3, dq3, true);
+#pragma unroll
+                        for (int s = 1; s < 32; s <<= 1) {
+                            V am = BlockShfl<CPLX>::up(a, s), cm = BlockShfl<CPLX>::up(c, s), dm = BlockShfl<CPLX>::up(d, s);
+                            V ap2 = BlockShfl<CPLX>::down(a, s), cp2 = BlockShfl<CPLX>::down(c, s), dq2 = BlockShfl<CPLX>::down(d, s);
+                            if (t < s) { am = S::zero(); cm = S::zero(); dm = S::zero(); }
+                            if (t + s >= 32) { ap2 = S::zero(); cp2 = S::zero(); dq2 = S::zero(); }
+                            reduce_row(am, cm, dm, ap2, cp2, dq2, 2 * s < 32);
+                        }
+                        V xm = BlockShfl<CPLX>::up(d, 1);
+                        if (t == 0) xm = S::zero();
+                        sol2[2 * t] = S::fnma(S::fnma(ed, ea, xm), ec, d);
+                        sol2[2 * t + 1] = d;
+                    }
+                } else
+#endif
 #pragma unroll
                 for (int s = 1; s < TQ; s <<= 1) {
                     V am = S::zero(), cm = S::zero(), dm = S::zero(), ap2 = S::zero(), cp2 = S::zero(), dq2 = S::zero();
