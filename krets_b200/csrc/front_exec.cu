@@ -112,6 +112,8 @@ static int upload_front(Plan &plan) {
     const int nf = fp.n_fronts;
     const bool use_ll = !(getenv("KRB_FRONT_LL") && getenv("KRB_FRONT_LL")[0] == '0');
     const bool use_warpf = !(getenv("KRB_FRONT_WARPF") && getenv("KRB_FRONT_WARPF")[0] == '0');
+    int ll_max = 512;         // largest front of the left-looking kernel (one row per thread); KRB_FRONT_LL_MAX_M lowers it (tests: mixed routing)
+    if (const char *e = getenv("KRB_FRONT_LL_MAX_M")) ll_max = std::max(32, std::min(512, atoi(e)));
     std::vector<FrontDesc> desc(nf);
     D.fw_size = 0;
     auto msize = [&](int f) { return (fp.piv0[f + 1] - fp.piv0[f]) + (fp.idx_ptr[f + 1] - fp.idx_ptr[f]); };
@@ -128,7 +130,7 @@ static int upload_front(Plan &plan) {
         const long long m = d.p + d.q;
         // fronts beyond shared memory: left-looking by resident column blocks (krb_front_factor_ll, no workspace) up to 512 rows,
         // above that the blocked right-looking kernel on a per-lane workspace; KRB_FRONT_LL=0 (A/B) sends all of them there
-        if (m > m_smem && (m > 512 || !use_ll)) { d.fw_off = D.fw_size; D.fw_size += ((m * m + 1) / 2) * 2; }   // (with use_ll only fronts beyond 512 rows)
+        if (m > m_smem && (m > ll_max || !use_ll)) { d.fw_off = D.fw_size; D.fw_size += ((m * m + 1) / 2) * 2; }   // (with use_ll only fronts beyond 512 rows)
         else d.fw_off = -1;
     }
     // launch lists: each level's fronts are sorted by size (largest first); cut them into size classes
@@ -140,7 +142,7 @@ static int upload_front(Plan &plan) {
         // 5..7 one warp per front (m <= 32; KRB_FRONT_WARPF=0 (A/B) keeps them on classes 3 / 4)
         auto fclass = [&](int m) {
             if (use_warpf && m <= 32 && m <= m_smem) return m > 24 ? 5 : m > 16 ? 6 : 7;
-            if (use_ll && m <= 512) return m > 256 ? -1 : m > 128 ? -2 : -3;      // left-looking kernel on 16 / 8 / 4 warps
+            if (use_ll && m <= ll_max) return m > 256 ? -1 : m > 128 ? -2 : -3;      // left-looking kernel on 16 / 8 / 4 warps
             if (m > m_smem) return 0;
             return m > 96 ? 1 : m > 48 ? 2 : m > 16 ? 3 : 4;
         };

@@ -116,6 +116,21 @@ def test_front_blocked_path_matches(oracle, monkeypatch, ll):
     assert_close(out[0], oc.solve_op(), what="blocked path OP")
 
 
+def test_front_mixed_kernel_routing(oracle, monkeypatch):
+    """Fronts beyond the left-looking kernel's one-row-per-thread limit (512 rows; lowered to 40 here) fall back to the blocked kernel on
+    the per-lane workspace or the CTA-per-front kernel, smaller ones stay on the left-looking / warp kernels: one factorisation mixes all
+    of them and children's contribution blocks cross between the kernels."""
+    monkeypatch.setenv("KRB_FRONT_LL_MAX_M", "40")
+    monkeypatch.setenv("KRB_FRONT_SMEM_M", "56")
+    text = netgen.rlc_mesh(30, 31, transient=False)
+    circuit, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    freqs = kb.generate_frequencies("Decade", 2, 1e4, 1e8)
+    out, status = kb.Plan(circuit, api.MODE_AC, nominal_frequency=1e6, executor=api.EXEC_STAGED).solve_ac(freqs)
+    _, ref = oc.solve_ac(freqs)
+    assert not status.any()
+    assert_close(out, ref, what="mixed kernel routing AC")
+
+
 @pytest.mark.parametrize("smem_m", [None, 24, -24])
 def test_front_nominal_dc_pivots_inside_fronts(oracle, monkeypatch, smem_m):
     """Identical element values + inductor shorts: a static pivot cancels exactly (CPU tier shows it); the kernels' per-lane
