@@ -39,7 +39,7 @@ struct FBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
-struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int slot_elems; int stage_fwd = 0, stage_bwd = 0; int ll = 0; };   // ll: warps of krb_front_factor_ll, 0 = another kernel
+struct FrontLaunch { int first, count; dim3 block; size_t smem; bool warp; int slot_elems; int stage_fwd = 0, stage_bwd = 0; int ll = 0, rpt = 1; };   // ll: warps of krb_front_factor_ll, 0 = another kernel
 }  // namespace
 
 struct FrontDevice {
@@ -114,6 +114,10 @@ static int upload_front(Plan &plan) {
     const bool use_warpf = !(getenv("KRB_FRONT_WARPF") && getenv("KRB_FRONT_WARPF")[0] == '0');
     int ll_max = 512;         // largest front of the left-looking kernel (one row per thread); KRB_FRONT_LL_MAX_M lowers it (tests: mixed routing)
     if (const char *e = getenv("KRB_FRONT_LL_MAX_M")) ll_max = std::max(32, std::min(512, atoi(e)));
+    // fronts the left-looking kernel takes: one row per thread up to 512 rows; real plans up to 1024 rows with two rows per thread when
+    // the pivot block has at most 512 (the second rows are never pivot candidates)
+    const bool cplx_plan = plan.is_complex;
+    auto ll_ok = [&](int m, int p) { return use_ll && (m <= ll_max || (ll_max == 512 && !cplx_plan && m <= 1024 && p <= 512)); };
     std::vector<FrontDesc> desc(nf);
     D.fw_size = 0;
     auto msize = [&](int f) { return (fp.piv0[f + 1] - fp.piv0[f]) + (fp.idx_ptr[f + 1] - fp.idx_ptr[f]); };
@@ -130,7 +134,7 @@ static int upload_front(Plan &plan) {
         const long long m = d.p + d.q;
         // fronts beyond shared memory: left-looking by resident column blocks (krb_front_factor_ll, no workspace) up to 512 rows,
         // above that the blocked right-looking kernel on a per-lane workspace; KRB_FRONT_LL=0 (A/B) sends all of them there
-        if (m > m_smem && (m > ll_max || !use_ll)) { d.fw_off = D.fw_size; D.fw_size += ((m * m + 1) / 2) * 2; }   // (with use_ll only fronts beyond 512 rows)
+        if (m > m_smem && !ll_ok((int)m, d.p)) { d.fw_off = D.fw_size; D.fw_size += ((m * m + 1) / 2) * 2; }   // (with use_ll only fronts beyond the kernel's row limits)
         else d.fw_off = -1;
     }
     // launch lists: each level's fronts are sorted by size (largest first); cut them into size classes
@@ -140,18 +144,19 @@ static int upload_front(Plan &plan) {
         const int b = fp.level_ptr[l], e = fp.level_ptr[l + 1];
         // size classes: -1 left-looking (beyond shared memory), 0 blocked on the workspace, 1..4 CTA per front in shared memory,
         // 5..7 one warp per front (m <= 32; KRB_FRONT_WARPF=0 (A/B) keeps them on classes 3 / 4)
-        auto fclass = [&](int m) {
+        auto fclass = [&](int f) {
+            const int m = msize(f), pf = fp.piv0[f + 1] - fp.piv0[f];
             if (use_warpf && m <= 32 && m <= m_smem) return m > 24 ? 5 : m > 16 ? 6 : 7;
-            if (use_ll && m <= ll_max) return m > 256 ? -1 : m > 128 ? -2 : -3;      // left-looking kernel on 16 / 8 / 4 warps
+            if (ll_ok(m, pf)) return m > 512 ? -4 : m > 256 ? -1 : m > 128 ? -2 : -3;   // left-looking kernel on 16 (two rows per thread) / 16 / 8 / 4 warps
             if (m > m_smem) return 0;
             return m > 96 ? 1 : m > 48 ? 2 : m > 16 ? 3 : 4;
         };
         auto sclass = [&](int m) { return m > 192 ? 0 : m > 64 ? 1 : 2; };
         for (int i = b; i < e;) {
             const int m0 = msize(fp.level_fronts[i]);
-            const int c = fclass(m0);
+            const int c = fclass(fp.level_fronts[i]);
             int j = i;
-            while (j < e && fclass(msize(fp.level_fronts[j])) == c) j++;
+            while (j < e && fclass(fp.level_fronts[j]) == c) j++;
             FrontLaunch L;
             L.first = i; L.count = j - i;
             L.block = c <= 1 ? dim3(32, 16) : c == 2 ? dim3(16, 16) : c == 3 ? dim3(16, 8) : dim3(8, 8);
@@ -160,8 +165,9 @@ static int upload_front(Plan &plan) {
             if (c < 0) {
                 // shared memory by residency: 4 warps -> 56 KB (four CTAs per SM), 8 -> 112 KB (two), 16 -> everything; doubled while the
                 // column blocks would be narrower than 8
-                L.ll = c == -1 ? 16 : c == -2 ? 8 : 4;
-                size_t sm_b = c == -1 ? (size_t)D.smem_cap : c == -2 ? (size_t)112 * 1024 : (size_t)56 * 1024;
+                L.ll = (c == -1 || c == -4) ? 16 : c == -2 ? 8 : 4;
+                L.rpt = c == -4 ? 2 : 1;
+                size_t sm_b = (c == -1 || c == -4) ? (size_t)D.smem_cap : c == -2 ? (size_t)112 * 1024 : (size_t)56 * 1024;
                 while (sm_b < (size_t)D.smem_cap && front_ll_width(m0, front_ll_ldc(m0), (long long)(sm_b / ts) - FRONT_LL_AUX) < 8) sm_b *= 2;
                 L.smem = std::min(sm_b, (size_t)D.smem_cap);
                 L.block = dim3(32, L.ll);
@@ -287,6 +293,7 @@ static int upload_front(Plan &plan) {
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
+    CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<false, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
     CUDA_TRY(cudaFuncSetAttribute(krb_front_factor_ll<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.smem_cap));
@@ -339,7 +346,8 @@ static int front_factor(const Plan &plan, FrontParams P, long long lanes, cudaSt
                     else if (L.ll == 8) krb_front_factor_ll<true, 8><<<grid, L.block, L.smem, st>>>(Q);
                     else krb_front_factor_ll<true, 4><<<grid, L.block, L.smem, st>>>(Q);
                 } else {
-                    if (L.ll == 16) krb_front_factor_ll<false, 16><<<grid, L.block, L.smem, st>>>(Q);
+                    if (L.ll == 16 && L.rpt == 2) krb_front_factor_ll<false, 16, 2><<<grid, L.block, L.smem, st>>>(Q);
+                    else if (L.ll == 16) krb_front_factor_ll<false, 16><<<grid, L.block, L.smem, st>>>(Q);
                     else if (L.ll == 8) krb_front_factor_ll<false, 8><<<grid, L.block, L.smem, st>>>(Q);
                     else krb_front_factor_ll<false, 4><<<grid, L.block, L.smem, st>>>(Q);
                 }

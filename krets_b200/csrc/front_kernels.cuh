@@ -669,7 +669,10 @@ template <int NW> struct FrontMma<true, NW> {
     }
 };
 
-template <bool CPLX, int NW>   // NW warps per CTA: 16 (m <= 512, one CTA per SM), 8 (m <= 256, two), 4 (m <= 128, four)
+// NW warps per CTA: 16 (m <= 512, one CTA per SM), 8 (m <= 256, two), 4 (m <= 128, four).  RPT = 2 (real plans, 16 warps): a thread owns a
+// SECOND row, 512 below its first, in the sub-panel factorisation — fronts up to 1024 rows whose pivot block has at most 512 (the second
+// rows are never pivot candidates: they only receive the updates).  DC plans of inductor-heavy meshes have such fronts (config 5: 694 rows).
+template <bool CPLX, int NW, int RPT = 1>
 __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const FrontParams P) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
@@ -837,7 +840,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
         for (int s0 = 0; s0 < npiv; s0 += SPW) {
             const int ns = (npiv - s0) < SPW ? (npiv - s0) : SPW;
             const int kk0 = c0 + s0;                  // front row / column of the sub-panel's first pivot
-            const int row = kk0 + tid;                // this thread's row (m - kk0 <= 512)
+            const int row = kk0 + tid;                // this thread's row (m - kk0 <= 32 NW; RPT == 2: its second row is NT below)
             // a[0] is always the CURRENT pivot column's entry of this thread's row, a[1..] the columns right of it: after every pivot the
             // row shifts left by one, finished values (multipliers l, the pivot row's U entries) go to shared memory at once.  The pivot
             // loops are therefore ROLLED: unrolled 8x (two paths) they were ~40 KB of straight-line code that every front runs once, on a
@@ -845,6 +848,23 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
             T a[SPW];
 #pragma unroll
             for (int k = 0; k < SPW; k++) a[k] = (k < ns && row < m) ? Cs[row + (size_t)ldc * (s0 + k)] : S::zero();
+            const int row2 = row + NT;                // RPT == 2: the thread's second row
+            T a2[RPT == 2 ? SPW : 1];
+            if (RPT == 2) {
+#pragma unroll
+                for (int k = 0; k < SPW; k++) a2[RPT == 2 ? k : 0] = (k < ns && row2 < m) ? Cs[row2 + (size_t)ldc * (s0 + k)] : S::zero();
+            }
+            // a second row is updated like any row below the pivot: l = a2[0] / pivot, shift-update with the pivot row
+            auto second_row = [&](int k, T rp, const T *prow) {
+                if (RPT == 2 && row2 < m) {
+                    const T l = S::mul(a2[0], rp);
+                    Cs[row2 + (size_t)ldc * (s0 + k)] = l;
+                    grow = max(grow, growth_key(l));
+#pragma unroll
+                    for (int j = 1; j < SPW; j++) a2[RPT == 2 ? j - 1 : 0] = S::fnma(a2[RPT == 2 ? j : 0], l, prow[j]);
+                    a2[RPT == 2 ? SPW - 1 : 0] = S::zero();
+                }
+            };
             if (p - kk0 <= 32) {
                 // every candidate row of this sub-panel belongs to warp 0 (always the case for mid-size fronts, p <= 32): that warp runs the
                 // whole pivot sequence with warp primitives and publishes the pivot rows; the other warps apply them after ONE barrier
@@ -914,6 +934,10 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
                         a[SPW - 1] = S::zero();
                     }
                 }
+                if (RPT == 2) {
+#pragma unroll 1
+                    for (int k = 0; k < ns; k++) second_row(k, pub[SPW * SPW + k], pub + k * SPW);
+                }
             } else {
 #pragma unroll 1
                 for (int k = 0; k < ns; k++) {
@@ -970,6 +994,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) krb_front_factor_ll(const Fr
 #pragma unroll
                         for (int j = 0; j < SPW; j++) if (k + j < ns) Cs[kk + (size_t)ldc * (s0 + k + j)] = a[j];
                     }
+                    second_row(k, rp, prow);
                     if (tid > k && row < m) {
                         const T l = S::mul(a[0], rp);
                         Cs[row + (size_t)ldc * (s0 + k)] = l;
