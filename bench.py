@@ -552,7 +552,9 @@ def strong_scaling_rc_ac(ctx):
         ctx["barrier"]()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        res = None
         for _ in range(reps):
+            res = None      # the previous sweep's results go back to the caching allocator first: no cudaMalloc of a second 80/N GB buffer inside the timed region
             lo, res = solve_sharded_chunked(total, solve_chunk, chunk_lanes=chunk, row_shape=(n,), dtype=torch.complex128, device="cuda", gather_to=gather_to)
         e1.record()
         ctx["barrier"]()
