@@ -1342,7 +1342,17 @@ __global__ void krb_front_backward(const FrontParams P) {
         // behind the block); the L21 rows below are not touched (half of a leaf front's block)
         T *Ls = w + P.stage_off;
         if (q > 0 && p < m) {
+            // column by column, thread r takes row r of each (no integer division per element: ncu r3, leaf levels of a 592-lane solve —
+            // the e / p, e % p form of this loop was 15 % of the kernel's executed instructions)
             const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(Ls);
+            if (p <= NT) {
+                if (tid < p)
+                    for (int k = 0; k < p; k++) {
+                        const uint32_t off = (uint32_t)(tid + m * k);
+                        if (sizeof(T) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + off * 16u), "l"(L + off) : "memory");
+                        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + off * 8u), "l"(L + off) : "memory");
+                    }
+            } else
             for (int e = tid; e < p * p; e += NT) {
                 const int k = e / p, r = e - k * p;
                 const uint32_t off = (uint32_t)(r + m * k);
