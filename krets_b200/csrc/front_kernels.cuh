@@ -1284,18 +1284,18 @@ __global__ void krb_front_forward(const FrontParams P) {
     for (int kb = 0; kb < p; kb += 32) {
         const int nbk = (p - kb) < 32 ? (p - kb) : 32;
         if (tid < 32) {
-            // unit-lower diagonal block: lane t owns row kb + t; its entries left of the diagonal are loaded first
+            // unit-lower diagonal block, column by column: lane t owns row kb + t and reads ITS element of column k (one conflict-free
+            // column access, fetched one column ahead), y_k is broadcast by shuffle.  (ncu r3: the row-oriented form with 8 predicated
+            // loads per group spent a third of a leaf front's ~630 instructions here.)
             const T *Lr = L + (kb + tid) + (size_t)m * kb;
             T val = tid < nbk ? w[kb + tid] : S::zero();
-            for (int k0 = 0; k0 < nbk; k0 += 8) {
-                T lrow[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) lrow[k] = (k0 + k < tid && tid < nbk) ? Lr[(size_t)m * (k0 + k)] : S::zero();
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const T yk = front_shfl(val, k0 + k);
-                    if (k0 + k < tid) val = S::fnma(val, lrow[k], yk);
-                }
+            T ln = tid < nbk ? Lr[0] : S::zero();
+#pragma unroll 4
+            for (int k = 0; k < nbk; k++) {
+                const T l = ln;
+                if (k + 1 < nbk) ln = tid < nbk ? Lr[(size_t)m * (k + 1)] : S::zero();
+                const T yk = front_shfl(val, k);
+                if (tid > k) val = S::fnma(val, l, yk);
             }
             if (tid < nbk) w[kb + tid] = val;
         }
@@ -1389,19 +1389,17 @@ __global__ void krb_front_backward(const FrontParams P) {
     for (int kb = ((p - 1) / 32) * 32; kb >= 0; kb -= 32) {
         const int nbk = (p - kb) < 32 ? (p - kb) : 32;
         if (tid < 32) {
-            // upper-triangular diagonal block (reciprocal pivots on the diagonal): lane t owns row kb + t
+            // upper-triangular diagonal block (reciprocal pivots on the diagonal), column by column from the last: lane t owns row kb + t
             const T *Ur = L + (kb + tid) + (size_t)m * kb;
             T val = tid < nbk ? w[kb + tid] : S::zero();
-            for (int k0 = ((nbk - 1) / 8) * 8; k0 >= 0; k0 -= 8) {
-                T urow[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) urow[k] = (k0 + k >= tid && k0 + k < nbk) ? Ur[(size_t)m * (k0 + k)] : S::zero();
-#pragma unroll
-                for (int k = 7; k >= 0; k--) {
-                    if (k0 + k == tid) val = S::mul(val, urow[k]);        // x_k = rhs_k / pivot_k
-                    const T xk = front_shfl(val, k0 + k);
-                    if (k0 + k > tid) val = S::fnma(val, urow[k], xk);
-                }
+            T un = tid < nbk ? Ur[(size_t)m * (nbk - 1)] : S::zero();
+#pragma unroll 4
+            for (int k = nbk - 1; k >= 0; k--) {
+                const T u = un;
+                if (k > 0) un = tid < nbk ? Ur[(size_t)m * (k - 1)] : S::zero();
+                if (tid == k) val = S::mul(val, u);                    // x_k = rhs_k / pivot_k
+                const T xk = front_shfl(val, k);
+                if (tid < k) val = S::fnma(val, u, xk);
             }
             if (tid < nbk) w[kb + tid] = val;
         }
