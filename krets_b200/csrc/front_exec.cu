@@ -370,7 +370,7 @@ static void launch_solve(const Plan &plan, const FrontLaunch &L, FrontParams Q, 
     Q.lanes = lanes;
     const int stage = FWD ? L.stage_fwd : L.stage_bwd;
     Q.stage_off = stage > 0 ? ((L.slot_elems + 1) & ~1) : 0;             // 16-byte aligned for the complex copies
-    const int slot = stage > 0 ? Q.stage_off + stage : L.slot_elems;
+    const int slot = stage > 0 ? ((Q.stage_off + stage + 1) & ~1) : L.slot_elems;   // even: every warp's slot stays 16-byte aligned
     if (L.warp) {
         Q.smem_elems = slot;
         const size_t smem = (size_t)slot * ts * L.block.y;
