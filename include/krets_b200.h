@@ -163,6 +163,14 @@ int32_t krb_plan_get_pivot_order(const krb_plan *p, int32_t *row_order /*n*/, in
  * section 0 = first/only section, 1 = factor-once section, 2 = per-step section.  ops are 2 x uint32 each. */
 int64_t krb_plan_program_size(const krb_plan *p, int32_t section);
 int32_t krb_plan_get_program(const krb_plan *p, int32_t section, uint32_t *ops /*2*size*/);
+/* Circuit-specialised lane kernel.  Lane programs of up to KRB_VM_JIT_MAX_OPS (default 2500: NVRTC needs about a second per thousand operations) operations are not interpreted: at
+ * first use the library writes the program out as straight-line CUDA (one statement per operation, scratch cells in registers),
+ * compiles it with NVRTC for sm_100a and launches that kernel (KRB_VM_JIT=0: always interpret).  The two entry points below expose
+ * the generated text and the NVRTC step without a device.  krb_plan_jit_source: returns the size of the text incl. the terminating
+ * NUL (0: plan not eligible, -1: bad arguments) and copies at most cap bytes; host_mode != 0 prefixes the text for a host build
+ * behind tests/jit_host_shim.h (the CPU tests run the generated statements against the oracle that way). */
+int64_t krb_plan_jit_source(const krb_plan *p, int32_t host_mode, char *buf, int64_t cap);
+int32_t krb_plan_jit_compile(const krb_plan *p, int64_t *cubin_bytes /* may be NULL */);
 
 /* ---- I/O descriptors -------------------------------------------------------------------------------- */
 enum { KRB_MEM_HOST = 0, KRB_MEM_DEVICE = 1 };

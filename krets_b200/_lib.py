@@ -64,6 +64,8 @@ SYMBOLS = {
     "krb_plan_get_pivot_order": (_i32, [_vp, _pi32, _pi32]),
     "krb_plan_program_size": (_i64, [_vp, _i32]),
     "krb_plan_get_program": (_i32, [_vp, _i32, C.POINTER(C.c_uint32)]),
+    "krb_plan_jit_source": (_i64, [_vp, _i32, C.c_char_p, _i64]),
+    "krb_plan_jit_compile": (_i32, [_vp, C.POINTER(_i64)]),
     "krb_solve_op": (_i32, [_vp, C.POINTER(KrbConfig), _i64, C.POINTER(KrbOverrides), _vp, _vp, _vp, C.POINTER(KrbIO)]),
     "krb_solve_dc_sweep": (_i32, [_vp, C.POINTER(KrbConfig), _vp, _i64, C.POINTER(KrbOverrides), _vp, _vp, C.POINTER(KrbIO)]),
     "krb_solve_ac": (_i32, [_vp, C.POINTER(KrbConfig), _vp, _i64, C.POINTER(KrbOverrides), _vp, _i64, _vp, _vp, C.POINTER(KrbIO)]),
@@ -112,6 +114,7 @@ _DEBUG_SYMBOLS = {
     "krb_plan_has_step_sections": (_i32, [_vp]),
     "krb_plan_state_columns": (_i32, [_vp]),
     "krb_plan_integrator": (_i32, [_vp]),
+    "krb_plan_jit_active": (_i32, [_vp]),
     "krb_plan_chain_size": (_i64, [_vp]),
     "krb_plan_get_chain": (_i32, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), _pi32]),
     "krb_plan_front_array": (_i64, [_vp, _i32, _pi32]),

@@ -6,6 +6,7 @@
 
 #include "plan.hpp"
 #include "runtime.hpp"
+#include "vm_jit.hpp"
 
 using namespace krb;
 
@@ -124,6 +125,26 @@ int32_t krb_plan_get_pivot_order(const krb_plan *p, int32_t *row_order, int32_t 
     for (int k = 0; k < s.n; k++) { row_order[k] = s.row_order[k]; col_order[k] = s.col_order[k]; }
     return KRB_OK;
 }
+int64_t krb_plan_jit_source(const krb_plan *p, int32_t host_mode, char *buf, int64_t cap) {
+    if (!p || cap < 0 || (cap > 0 && !buf)) return -1;
+    if (!vm_jit_eligible(p->p)) return 0;
+    const std::string src = vm_jit_source(p->p, vm_params_size(), host_mode != 0);
+    if (buf && cap > 0) {
+        const size_t k = std::min<size_t>(src.size(), (size_t)cap - 1);
+        std::memcpy(buf, src.data(), k);
+        buf[k] = '\0';
+    }
+    return (int64_t)src.size() + 1;
+}
+int32_t krb_plan_jit_compile(const krb_plan *p, int64_t *cubin_bytes) {
+    if (!p) return KRB_ERR_INVALID_ARGUMENT;
+    if (cubin_bytes) *cubin_bytes = 0;
+    if (!vm_jit_eligible(p->p)) { set_error("the plan's lane program is not eligible for a specialised kernel (executor or length)"); return KRB_ERR_UNSUPPORTED; }
+    std::string cubin, err;
+    if (!vm_jit_compile(vm_jit_source(p->p, vm_params_size(), false), cubin, err)) { set_error(err); return KRB_ERR_INTERNAL; }
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    return KRB_OK;
+}
 int64_t krb_plan_program_size(const krb_plan *p, int32_t section) {
     if (!p || section < 0 || section > 2) return -1;
     return (int64_t)p->p.sec[section].ops.size() / 2;
@@ -202,6 +223,8 @@ int32_t krb_plan_front_info(const krb_plan *p, int64_t *out) {
 int32_t krb_plan_integrator(const krb_plan *p) { return p ? p->p.opts.integrator : -1; }
 int32_t krb_plan_state_columns(const krb_plan *p) { return p ? (int32_t)p->p.state_elems.size() : -1; }
 int32_t krb_plan_has_step_sections(const krb_plan *p) { return p ? (p->p.has_step_sections ? 1 : 0) : -1; }
+// 1: the plan's lane program runs as a circuit-specialised kernel on this device (after its first solve), 0: interpreter / other executor
+int32_t krb_plan_jit_active(const krb_plan *p) { return p ? (device_state_has_jit(p->p.dev) ? 1 : 0) : -1; }
 
 static int check_io(const krb_io *io, krb_io &o) {
     krb_default_io(&o);

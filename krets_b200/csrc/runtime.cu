@@ -22,6 +22,7 @@
 #include "dense_tran_kernel.cuh"
 #include "plan.hpp"
 #include "runtime.hpp"
+#include "vm_jit.hpp"
 #include "vm_kernel.cuh"
 
 namespace krb {
@@ -97,9 +98,12 @@ struct DeviceState {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     size_t events_used = 0;
     long long chunk_lanes = 0;           // lane capacity the buffers were sized for
+    JitKernel *jit = nullptr;            // circuit-specialised lane kernel (vm_jit.cpp); null: interpreter
 };
 
 DeviceState *device_state_new() { return new DeviceState(); }
+size_t vm_params_size() { return sizeof(VmParams); }
+bool device_state_has_jit(const DeviceState *d) { return d && d->jit; }
 
 static double (*g_last_fn)(void *) = nullptr;
 static void *g_last_obj = nullptr;
@@ -125,6 +129,7 @@ double last_kernel_ms() { return g_last_fn ? g_last_fn(g_last_obj) : g_last_ms; 
 void device_state_free(DeviceState *d) {
     if (!d) return;
     retire_last_timer(d);
+    vm_jit_free(d->jit);
     for (int i = 0; i < 3; i++) if (d->sec[i]) cudaFree(d->sec[i]);
     if (d->chain_rowinfo) cudaFree(d->chain_rowinfo);
     if (d->chain_stream) cudaFree(d->chain_stream);
@@ -198,6 +203,17 @@ static int upload_plan(Plan &plan, DeviceState &d) {
         CUDA_TRY(cudaEventCreateWithFlags(&d.compute_done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&d.copy_done[i], cudaEventDisableTiming));
     }
+    if (!plan.use_chain && !plan.use_front && vm_jit_enabled() && vm_jit_eligible(plan)) {
+        // small lane programs run as a kernel specialised to the circuit (scratch cells in registers, no op decode)
+        NvtxRange nvtx_jit("krb plan: specialise the lane kernel (NVRTC)");
+        std::string why;
+        d.jit = vm_jit_build(plan, sizeof(VmParams), why);
+        static bool warned = false;
+        if (!d.jit && !warned) {
+            warned = true;
+            fprintf(stderr, "krets_b200: specialised lane kernel unavailable, lane programs stay on the interpreter: %s\n", why.c_str());
+        }
+    }
     d.uploaded = true;
     return KRB_OK;
 }
@@ -216,7 +232,13 @@ static int launch_vm_t(const VmParams &p, long long Lpad, int n_slots, cudaStrea
     CUDA_TRY(cudaGetLastError());
     return KRB_OK;
 }
-static int launch_vm(bool cplx, int tpb, const VmParams &p, long long Lpad, int n_slots, cudaStream_t st) {
+static int launch_vm(bool cplx, int tpb, const VmParams &p, long long Lpad, int n_slots, cudaStream_t st, JitKernel *jit) {
+    if (jit) {
+        std::string why;
+        if (!vm_jit_launch(jit, &p, (unsigned)(Lpad / tpb), (unsigned)tpb, (void *)st, why)) { set_error(why); return KRB_ERR_CUDA; }
+        g_launches++;
+        return KRB_OK;
+    }
     if (cplx) {
         if (tpb == 32) return launch_vm_t<true, 32>(p, Lpad, n_slots, st);
         if (tpb == 128) return launch_vm_t<true, 128>(p, Lpad, n_slots, st);
@@ -592,7 +614,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             p.h = P0.opts.time_step; p.reltol = a.cfg.relative_tolerance; p.iabstol = a.cfg.current_absolute_tolerance; p.vabstol = a.cfg.voltage_absolute_tolerance;
             p.status = status_d; p.iters = iters_d;
             if (width > n) CUDA_TRY(cudaMemsetAsync((char *)D0.X[b].p + (size_t)n * Lpad * ts, 0, (size_t)(width - n) * Lpad * ts, st));   // i_C(0) = 0
-            if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st))) return rc;
+            if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st, D0.jit))) return rc;
             if (PS && rows > 1 && PS->dense.valid && getenv("KRB_NO_DENSE_TRAN") == nullptr) {
                 // small linear circuit: native stepping kernel (row 0 = the operating point just written by the DC plan)
                 DeviceState &DS = *PS->dev;
@@ -620,7 +642,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
                 q.guess_empty_at_iter0 = 0; q.pseudo_time = 1;
                 q.h = PS->opts.time_step;
                 q.iters = nullptr;
-                if ((rc = launch_vm(false, tpb, q, Lpad, PS->n_slots, st))) return rc;
+                if ((rc = launch_vm(false, tpb, q, Lpad, PS->n_slots, st, DS.jit))) return rc;
             }
         }
         CUDA_TRY(cudaEventRecord(e1, st));

@@ -38,9 +38,11 @@ struct RunArgs {
 void set_error(const std::string &s);
 const char *get_error();
 int device_count();
+size_t vm_params_size();   // sizeof(krb::VmParams): the specialised lane kernels (vm_jit.cpp) take the same object by value
 long long launch_count();
 double last_kernel_ms();
 void device_state_free(DeviceState *d);
+bool device_state_has_jit(const DeviceState *d);
 void front_device_free(FrontDevice *d);
 void add_launches(long long k);
 // krb_last_kernel_ms(): the most recent call registers how its device time is read back (events are resolved lazily so that

@@ -1,0 +1,310 @@
+// Circuit-specialised lane kernels (see vm_jit.hpp): source generation, NVRTC compilation, module loading and launch.
+// NVRTC and the driver API are bound with dlopen at first use, so the library itself links against neither; a box without
+// NVRTC keeps the interpreter (runtime.cu reports why once on stderr).
+#include "vm_jit.hpp"
+
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace krb {
+
+static const char *const PRELUDE =
+#include "vm_jit_prelude.inc"
+    ;
+
+int64_t vm_jit_max_ops() {
+    static const int64_t v = [] {
+        const char *e = getenv("KRB_VM_JIT_MAX_OPS");
+        return e ? (int64_t)atoll(e) : (int64_t)2500;
+    }();
+    return v;
+}
+bool vm_jit_enabled() {
+    const char *e = getenv("KRB_VM_JIT");
+    return !(e && e[0] == '0');
+}
+bool vm_jit_eligible(const Plan &plan) {
+    if (plan.use_chain || plan.use_front) return false;
+    const int64_t total = plan.sec[0].n_ops + plan.sec[1].n_ops + plan.sec[2].n_ops;
+    return total > 0 && total <= vm_jit_max_ops();
+}
+
+// ---- source generation -----------------------------------------------------------------------------------------------------
+static void put(std::string &o, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+static void put(std::string &o, const char *fmt, ...) {
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    o += buf;
+}
+
+// one section: the op stream written out, one statement per operation (same order, same arithmetic as vm_kernel.cuh)
+static void emit_section(const Program &prog, std::string &o) {
+    const std::vector<uint32_t> &w = prog.ops;
+    const size_t n = w.size() / 2;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t w0 = w[2 * i], imm = w[2 * i + 1];
+        const uint32_t opc = w0 & 0xffu, d = (w0 >> 8) & 0xffu, a = (w0 >> 16) & 0xffu, b = w0 >> 24;
+        switch (opc) {
+        case KOP_END: return;
+        case KOP_LDB: put(o, "s[%u] = k_real(c.Bc[%u]);\n", d, imm); break;
+        case KOP_LDBS: put(o, "s[%u] = k_real(c.Bs[%u]);\n", d, imm); break;
+        case KOP_LDI: put(o, "s[%u] = k_real(c.IN[(size_t)%uu * c.L]);\n", d, imm); break;
+        case KOP_LDG: put(o, "s[%u] = c.G[(size_t)%uu * c.L];\n", d, imm); break;
+        case KOP_STG: put(o, "c.G[(size_t)%uu * c.L] = s[%u];\n", imm, a); break;
+        case KOP_LDX: put(o, "s[%u] = k_ldx(c, %uu, %uu);\n", d, imm, b); break;
+        case KOP_XOUT: put(o, "k_xout(c, s[%u], %uu, %uu, status, notconv);\n", a, imm, b); break;
+        case KOP_ZERO: put(o, "s[%u] = k_zero();\n", d); break;
+        case KOP_MOV: put(o, "s[%u] = s[%u];\n", d, a); break;
+        case KOP_NEG: put(o, "s[%u] = k_neg(s[%u]);\n", d, a); break;
+        case KOP_ADD: put(o, "s[%u] = k_add(s[%u], s[%u]);\n", d, a, b); break;
+        case KOP_SUB: put(o, "s[%u] = k_sub(s[%u], s[%u]);\n", d, a, b); break;
+        case KOP_MUL: put(o, "s[%u] = k_mul(s[%u], s[%u]);\n", d, a, b); break;
+        case KOP_FNMA: put(o, "s[%u] = k_fnma(s[%u], s[%u], s[%u]);\n", d, d, a, b); break;
+        case KOP_RCP: put(o, "s[%u] = k_rcp(s[%u], status);\n", d, a); break;
+        case KOP_INV: put(o, "s[%u] = k_inv(s[%u]);\n", d, a); break;
+        case KOP_DIVR: put(o, "s[%u] = k_divr(s[%u], s[%u]);\n", d, a, b); break;
+        case KOP_MULJ: put(o, "s[%u] = k_mulj(s[%u]);\n", d, a); break;
+        case KOP_DIOG: put(o, "s[%u] = k_diog(s[%u], c.Bc + %u);\n", d, a, imm); break;
+        case KOP_DIOI: put(o, "s[%u] = k_dioi(s[%u], c.Bc + %u);\n", d, a, imm); break;
+        case KOP_LDK: {   // the constant sits in the next op slot (both words)
+            if (i + 1 >= n) return;
+            const uint64_t bits = (uint64_t)w[2 * i + 2] | ((uint64_t)w[2 * i + 3] << 32);
+            put(o, "s[%u] = k_const(0x%016llxull);\n", d, (unsigned long long)bits);
+            i++;
+            break;
+        }
+        case KOP_MULG: put(o, "s[%u] = k_mulg(s[%u], s[%u], grow);\n", d, a, b); break;
+        case KOP_NOP:
+        case KOP_WAIT:   // loads are synchronous here: the compiler schedules them
+        default: break;
+        }
+    }
+}
+
+static int max_slot(const Program &prog) {
+    int m = 0;
+    const size_t n = prog.ops.size() / 2;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t w0 = prog.ops[2 * i];
+        const uint32_t opc = w0 & 0xffu;
+        if (opc == KOP_END) break;
+        if (opc == KOP_LDK) { m = std::max<int>(m, (w0 >> 8) & 0xff); i++; continue; }
+        m = std::max<int>(m, (w0 >> 8) & 0xff);
+        m = std::max<int>(m, (w0 >> 16) & 0xff);
+        if (opc != KOP_LDX && opc != KOP_XOUT) m = std::max<int>(m, w0 >> 24);
+    }
+    return m;
+}
+
+std::string vm_jit_source(const Plan &plan, size_t vm_params_size, bool host_mode) {
+    std::string o;
+    o.reserve(64 * 1024);
+    if (host_mode) o += "#define KRB_JIT_HOST 1\n#include \"jit_host_shim.h\"\n";
+    put(o, "#define KRB_JIT_CPLX %d\n", plan.is_complex ? 1 : 0);
+    put(o, "#define KRB_LANE_ZERO_PIVOT %d\n#define KRB_LANE_NOT_CONVERGED %d\n#define KRB_LANE_NONFINITE %d\n#define KRB_LANE_INACCURATE %d\n",
+        (int)KRB_LANE_ZERO_PIVOT, (int)KRB_LANE_NOT_CONVERGED, (int)KRB_LANE_NONFINITE, (int)KRB_LANE_INACCURATE);
+    put(o, "#define KRB_GROWTH_LIMIT_LOG2 %d\n", (int)KRB_GROWTH_LIMIT_LOG2);
+    int ns = 0;
+    for (int k = 0; k < 3; k++) ns = std::max(ns, max_slot(plan.sec[k]));
+    put(o, "#define KRB_JIT_NSLOTS %d\n", ns + 1);
+    o += PRELUDE;
+    put(o, "static_assert(sizeof(VmParams) == %zu, \"VmParams layout differs from the library's\");\n", vm_params_size);
+    o += R"KRBJIT(
+KRB_JIT_ENTRY {
+#ifndef KRB_JIT_HOST
+    const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#endif
+    const size_t L = (size_t)p.L;
+    KCtx c;
+    c.IN = p.IN + lane; c.G = (T *)p.G + lane; c.Bc = p.B; c.L = L;
+    c.reltol = p.reltol; c.iabstol = p.iabstol; c.vabstol = p.vabstol; c.nonlinear = p.nonlinear != 0;
+    int status = 0, it_used = 0;
+    uint32_t grow = 0;
+    T s[KRB_JIT_NSLOTS];   // the interpreter's scratch cells: constant indices only, so they live in registers
+    for (int i = 0; i < KRB_JIT_NSLOTS; i++) s[i] = k_zero();
+    for (int row = p.row_begin; row < p.row_end; ++row) {
+        T *Xcur = (T *)p.X + (size_t)row * (size_t)p.row_width * L + lane;
+        const double *Xprev;
+        if (row == p.row_begin && p.Xprev0) Xprev = p.Xprev0 + lane;
+        else Xprev = (const double *)((T *)p.X + (size_t)(row > 0 ? row - 1 : 0) * (size_t)p.row_width * L) + lane;
+        c.Xcur = Xcur; c.Xprev = Xprev; c.lane_active = true;
+        const int n_pass = (p.sec1 && row == p.row_begin) ? 2 : 1;
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int prog = p.sec1 ? ((n_pass == 2 && pass == 0) ? 1 : 2) : 0;
+            const bool solve_pass = !(n_pass == 2 && pass == 0);
+            for (int iter = 0; iter < p.max_iter; ++iter) {
+                c.guess_empty = p.guess_empty_at_iter0 && iter == 0;
+                c.Xguess = (iter == 0 && !p.guess_empty_at_iter0) ? Xprev : (const double *)Xcur;
+                c.Bs = p.Bstep + ((size_t)row * 2 + (iter > 0 ? 1 : 0)) * (size_t)p.n_wave;
+                bool notconv = false;
+                if (prog == 0) {
+)KRBJIT";
+    emit_section(plan.sec[0], o);
+    o += "                } else if (prog == 1) {\n";
+    emit_section(plan.sec[1], o);
+    o += "                } else {\n";
+    emit_section(plan.sec[2], o);
+    o += R"KRBJIT(                }
+                // ---- NR bookkeeping (op.rs:65-81, dc.rs:99-110, transient.rs:97-109), as vm_kernel.cuh ----
+                if (!solve_pass || !p.nonlinear) break;
+                bool pseudo_ok = true;
+                if (p.pseudo_time && iter == 0) {
+                    const double tn = (double)row * p.h, tp = (double)(row - 1) * p.h;
+                    pseudo_ok = fabs(tn - tp) <= p.reltol * fmax(fabs(tn), fabs(tp)) + p.vabstol;
+                }
+                if (c.lane_active) it_used = iter + 1;
+                const bool conv = !c.guess_empty && !notconv && pseudo_ok;
+                if (c.lane_active && conv) c.lane_active = false;
+                if (c.lane_active && iter == p.max_iter - 1) status |= KRB_LANE_NOT_CONVERGED;
+                if (KRB_JIT_ALL(!c.lane_active)) break;
+            }
+        }
+    }
+    if (!p.nonlinear && grow >= KRB_GROWTH_KEY_V && grow < KRB_NONFINITE_KEY_V) status |= KRB_LANE_INACCURATE;
+    if (p.status) p.status[lane] |= status;
+    if (p.iters) p.iters[lane] = it_used;
+}
+)KRBJIT";
+    return o;
+}
+
+// ---- NVRTC -----------------------------------------------------------------------------------------------------------------
+namespace {
+struct Nvrtc {
+    void *h = nullptr;
+    nvrtcResult (*create)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+    nvrtcResult (*compile)(nvrtcProgram, int, const char *const *) = nullptr;
+    nvrtcResult (*cubin_size)(nvrtcProgram, size_t *) = nullptr;
+    nvrtcResult (*cubin)(nvrtcProgram, char *) = nullptr;
+    nvrtcResult (*log_size)(nvrtcProgram, size_t *) = nullptr;
+    nvrtcResult (*log)(nvrtcProgram, char *) = nullptr;
+    nvrtcResult (*destroy)(nvrtcProgram *) = nullptr;
+    const char *(*errstr)(nvrtcResult) = nullptr;
+    std::string why;
+    bool ok = false;
+};
+struct Driver {
+    void *h = nullptr;
+    CUresult (*ctx_current)(CUcontext *) = nullptr;
+    CUresult (*load)(CUmodule *, const void *) = nullptr;
+    CUresult (*get_fn)(CUfunction *, CUmodule, const char *) = nullptr;
+    CUresult (*launch)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **) = nullptr;
+    CUresult (*unload)(CUmodule) = nullptr;
+    CUresult (*errstr)(CUresult, const char **) = nullptr;
+    std::string why;
+    bool ok = false;
+};
+template <class F> bool bind(void *h, const char *name, F &fn, std::string &why) {
+    fn = reinterpret_cast<F>(dlsym(h, name));
+    if (!fn) { why = std::string("symbol ") + name + " not found"; return false; }
+    return true;
+}
+Nvrtc &nvrtc() {
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (const char *nm : names) if ((n.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!n.h) { n.why = "libnvrtc.so.12 not found"; return; }
+        n.ok = bind(n.h, "nvrtcCreateProgram", n.create, n.why) && bind(n.h, "nvrtcCompileProgram", n.compile, n.why) &&
+               bind(n.h, "nvrtcGetCUBINSize", n.cubin_size, n.why) && bind(n.h, "nvrtcGetCUBIN", n.cubin, n.why) &&
+               bind(n.h, "nvrtcGetProgramLogSize", n.log_size, n.why) && bind(n.h, "nvrtcGetProgramLog", n.log, n.why) &&
+               bind(n.h, "nvrtcDestroyProgram", n.destroy, n.why) && bind(n.h, "nvrtcGetErrorString", n.errstr, n.why);
+    });
+    return n;
+}
+Driver &driver() {
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libcuda.so.1", "libcuda.so"};
+        for (const char *nm : names) if ((d.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!d.h) { d.why = "libcuda.so.1 not found"; return; }
+        d.ok = bind(d.h, "cuCtxGetCurrent", d.ctx_current, d.why) && bind(d.h, "cuModuleLoadData", d.load, d.why) &&
+               bind(d.h, "cuModuleGetFunction", d.get_fn, d.why) && bind(d.h, "cuLaunchKernel", d.launch, d.why) &&
+               bind(d.h, "cuModuleUnload", d.unload, d.why) && bind(d.h, "cuGetErrorString", d.errstr, d.why);
+    });
+    return d;
+}
+std::string cu_err(Driver &d, CUresult r) {
+    const char *s = nullptr;
+    if (d.errstr) d.errstr(r, &s);
+    return s ? s : ("CUresult " + std::to_string((int)r));
+}
+}  // namespace
+
+bool vm_jit_compile(const std::string &src, std::string &cubin, std::string &err) {
+    Nvrtc &n = nvrtc();
+    if (!n.ok) { err = "NVRTC unavailable: " + n.why; return false; }
+    nvrtcProgram prog = nullptr;
+    nvrtcResult r = n.create(&prog, src.c_str(), "krb_jit_vm.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) { err = std::string("nvrtcCreateProgram: ") + n.errstr(r); return false; }
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+    r = n.compile(prog, 3, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t ls = 0;
+        n.log_size(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) n.log(prog, &log[0]);
+        if (log.size() > 2000) log.resize(2000);
+        err = std::string("nvrtcCompileProgram: ") + n.errstr(r) + "\n" + log;
+        n.destroy(&prog);
+        return false;
+    }
+    size_t cs = 0;
+    r = n.cubin_size(prog, &cs);
+    if (r != NVRTC_SUCCESS || cs == 0) { err = "nvrtcGetCUBINSize failed"; n.destroy(&prog); return false; }
+    cubin.assign(cs, '\0');
+    r = n.cubin(prog, &cubin[0]);
+    n.destroy(&prog);
+    if (r != NVRTC_SUCCESS) { err = "nvrtcGetCUBIN failed"; return false; }
+    return true;
+}
+
+struct JitKernel {
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+};
+
+JitKernel *vm_jit_build(const Plan &plan, size_t vm_params_size, std::string &err) {
+    Driver &d = driver();
+    if (!d.ok) { err = "CUDA driver API unavailable: " + d.why; return nullptr; }
+    std::string cubin;
+    if (!vm_jit_compile(vm_jit_source(plan, vm_params_size, false), cubin, err)) return nullptr;
+    CUcontext ctx = nullptr;
+    if (d.ctx_current(&ctx) != CUDA_SUCCESS || !ctx) { err = "no current CUDA context"; return nullptr; }
+    JitKernel *k = new JitKernel();
+    CUresult r = d.load(&k->mod, cubin.data());
+    if (r != CUDA_SUCCESS) { err = "cuModuleLoadData: " + cu_err(d, r); delete k; return nullptr; }
+    r = d.get_fn(&k->fn, k->mod, "krb_jit_vm");
+    if (r != CUDA_SUCCESS) { err = "cuModuleGetFunction: " + cu_err(d, r); d.unload(k->mod); delete k; return nullptr; }
+    return k;
+}
+
+bool vm_jit_launch(JitKernel *k, const void *params, unsigned grid, unsigned block, void *stream, std::string &err) {
+    Driver &d = driver();
+    void *args[1] = {const_cast<void *>(params)};
+    const CUresult r = d.launch(k->fn, grid, 1, 1, block, 1, 1, 0, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) { err = "cuLaunchKernel (specialised lane kernel): " + cu_err(d, r); return false; }
+    return true;
+}
+
+void vm_jit_free(JitKernel *k) {
+    if (!k) return;
+    Driver &d = driver();
+    if (d.ok && k->mod) d.unload(k->mod);
+    delete k;
+}
+
+}  // namespace krb
