@@ -64,18 +64,24 @@ enum {
 /* element kinds; same order as the reference's parser `alt`, elements.rs:45-55 */
 enum { KRB_R = 0, KRB_C = 1, KRB_L = 2, KRB_V = 3, KRB_I = 4, KRB_D = 5, KRB_NMOS = 6 };
 enum { KRB_WAVE_NONE = 0, KRB_WAVE_PULSE = 1, KRB_WAVE_SIN = 2 };
-enum { KRB_ELEM_FLAG_G2 = 1 };          /* capacitor with the G2 token (capacitor.rs:31,38) */
+enum { KRB_ELEM_FLAG_G2 = 1,            /* capacitor with the G2 token (capacitor.rs:31,38) */
+       /* EXTENSION (not reference behaviour): this NMOS stamps the level-1 companion model the reference's
+        * nmosfet.rs:51-102 equations define (g_m, g_ds, i_d; documentation/main.typ:375-424) with KCL-consistent signs.
+        * Without the flag an NMOS reproduces the reference: its stamps look up bare node names, never match the index map
+        * and stamp nothing (stampable.rs:842-844, circuits/inverter/dc/result.parquet). */
+       KRB_ELEM_FLAG_LEVEL1 = 2 };
 
 typedef struct krb_element {
     int32_t kind;
     int32_t ip;            /* index_map["V(<plus>)"]   or -1 (ground / absent)   NMOS: drain  */
     int32_t im;            /* index_map["V(<minus>)"]  or -1                     NMOS: gate   */
-    int32_t ic;            /* index_map["I(<ident>)"]  or -1 (group-1 element)                 */
+    int32_t ic;            /* index_map["I(<ident>)"]  or -1 (group-1 element)   NMOS: source */
     int32_t waveform;      /* KRB_WAVE_* for V sources (voltage_source.rs:244-252) */
     int32_t flags;
     double value;          /* R/C/L value, V dc_value, I value */
     double ac_amplitude;   /* V sources */
-    double wave[7];        /* PULSE: v0 v1 td tr tf pw per (voltage_source.rs:15-31); SIN: off amp freq delay damp phase */
+    double wave[7];        /* PULSE: v0 v1 td tr tf pw per (voltage_source.rs:15-31); SIN: off amp freq delay damp phase;
+                              NMOS: Vth, beta = KP*(W/L), lambda (models/nmosfet.rs:24-45) */
     double is;             /* diode saturation current   (models/diode.rs:14-23) */
     double n;              /* diode emission coefficient */
 } krb_element;

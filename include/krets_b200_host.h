@@ -42,6 +42,12 @@ int32_t krh_circuit_num_elements(const krh_circuit *c);
 const char *krh_circuit_element_identifier(const krh_circuit *c, int32_t e);
 const krb_element *krh_circuit_elements(const krh_circuit *c);    /* the flattened table krb_circuit_create takes */
 const uint8_t *krh_circuit_is_current(const krh_circuit *c);
+/* EXTENSION (not reference behaviour).  models = KRH_DEVICES_REFERENCE (default): an NMOS reproduces the reference and
+ * stamps nothing (stampable.rs:842-844).  KRH_DEVICES_LEVEL1: every NMOS of the circuit gets KRB_ELEM_FLAG_LEVEL1 and stamps the
+ * level-1 companion model of nmosfet.rs:51-102 (OP / DC / transient: Newton-Raphson; AC: small-signal g_m, g_ds at the operating
+ * point).  Call before the circuit is handed to krh_solver_new / krb_circuit_create.  Returns the number of NMOS elements, < 0 on error. */
+enum { KRH_DEVICES_REFERENCE = 0, KRH_DEVICES_LEVEL1 = 1 };
+int32_t krh_circuit_set_device_models(krh_circuit *c, int32_t models);
 
 /* ---- krets_parser::analyses::AcAnalysis::generate_frequencies ---- */
 enum { KRH_SWEEP_LINEAR = 0, KRH_SWEEP_DECADE = 1, KRH_SWEEP_OCTAVE = 2 };

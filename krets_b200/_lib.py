@@ -86,6 +86,7 @@ SYMBOLS = {
     "krh_circuit_element_identifier": (C.c_char_p, [_vp, _i32]),
     "krh_circuit_elements": (C.POINTER(KrbElement), [_vp]),
     "krh_circuit_is_current": (C.POINTER(C.c_uint8), [_vp]),
+    "krh_circuit_set_device_models": (_i32, [_vp, _i32]),
     "krh_generate_frequencies": (_i64, [_i32, C.c_uint32, _f64, _f64, _pf64, _i64]),
     "krh_dc_num_steps": (_i32, [_f64, _f64, _f64]),
     "krh_transient_num_steps": (_i32, [_f64, _f64]),

@@ -160,6 +160,9 @@ def generate_frequencies(variation: str, points: int, fstart: float, fstop: floa
 
 
 # ---- krets_parser::circuit::Circuit ---------------------------------------------------------------------------
+DEVICES_REFERENCE, DEVICES_LEVEL1 = 0, 1
+
+
 class Circuit:
     def __init__(self, handle):
         L = _lib.lib()
@@ -186,6 +189,14 @@ class Circuit:
 
     def element_value(self, e: int) -> float:
         return float(self.element(e).value)
+
+    def set_device_models(self, models: int) -> int:
+        """EXTENSION (krets_b200_host.h): DEVICES_LEVEL1 makes every NMOS stamp the level-1 companion model (nmosfet.rs:51-102);
+        DEVICES_REFERENCE (default) reproduces the reference, whose NMOS stamps nothing.  Call before building Solver / Plan objects."""
+        k = int(_lib.lib().krh_circuit_set_device_models(self._h, models))
+        if k < 0:
+            raise ValueError("set_device_models: unknown model set")
+        return k
 
 
 def parse_circuit_description(text: str) -> Circuit:

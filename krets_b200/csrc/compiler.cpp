@@ -92,6 +92,18 @@ struct Builder {
         diode_pool_base[e] = base;
         return base;
     }
+    std::map<int, int> mos_pool_base;
+    int mos_base(int e) {
+        auto it = mos_pool_base.find(e);
+        if (it != mos_pool_base.end()) return it->second;
+        // three consecutive entries: {Vth, beta, lambda}
+        plan.pool.push_back({P_MOS_VTH, false, e, 0.0});
+        int base = (int)plan.pool.size() - 1;
+        plan.pool.push_back({P_MOS_BETA, false, e, 0.0});
+        plan.pool.push_back({P_MOS_LAMBDA, false, e, 0.0});
+        mos_pool_base[e] = base;
+        return base;
+    }
 };
 
 // A source reference that can be materialised either as a shared read-only cell or a fresh mutable one
@@ -128,7 +140,7 @@ struct Section {
         }
         return op(KOP_LDX, B.new_cell(), -1, -1, (uint32_t)unknown, (uint8_t)((which & 1) | (half_default ? 2 : 0)));
     }
-    enum Tag { T_G = 1, T_VAL, T_VOH, T_TWOPIF, T_JWV, T_VD, T_DIOG, T_DIOI, T_CAPH, T_INDH, T_CAPI, T_INDV };
+    enum Tag { T_G = 1, T_VAL, T_VOH, T_TWOPIF, T_JWV, T_VD, T_DIOG, T_DIOI, T_CAPH, T_INDH, T_CAPI, T_INDV, T_MOSVGS, T_MOSVDS, T_MOSGM, T_MOSGDS, T_MOSGDSGM, T_MOSIEQ };
     int cached(Tag t, int e, bool neg, int (Section::*make)(int)) {
         auto key = std::make_tuple((int)t, e, (int)neg);
         auto it = derived.find(key);
@@ -165,6 +177,22 @@ struct Section {
     }
     int make_diog(int e) { return un(KOP_DIOG, cached(T_VD, e, false, &Section::make_vd), (uint32_t)B.diode_base(e)); }
     int make_dioi(int e) { return un(KOP_DIOI, cached(T_VD, e, false, &Section::make_vd), (uint32_t)B.diode_base(e)); }
+    // level-1 NMOS (extension, KRB_ELEM_FLAG_LEVEL1): node voltages of the linearisation point default to 0.0 (stampable.rs:825-833)
+    int mos_node(int u) { return u >= 0 ? ldx(ldx_which_guess, u, false) : B.shared_pool_cell(B.pool_idx(P_CONST, false, -1, 0.0)); }
+    int make_mos_vgs(int e) { const krb_element &el = B.plan.circuit.el[e]; return bin(KOP_SUB, mos_node(el.im), mos_node(el.ic)); }   // v_g - v_s
+    int make_mos_vds(int e) { const krb_element &el = B.plan.circuit.el[e]; return bin(KOP_SUB, mos_node(el.ip), mos_node(el.ic)); }   // v_d - v_s
+    int mos_op(uint8_t opc, int e) {
+        return op(opc, B.new_cell(), cached(T_MOSVGS, e, false, &Section::make_mos_vgs), cached(T_MOSVDS, e, false, &Section::make_mos_vds), (uint32_t)B.mos_base(e));
+    }
+    int make_mos_gm(int e) { return mos_op(KOP_MOSGM, e); }
+    int make_mos_gds(int e) { return mos_op(KOP_MOSGDS, e); }
+    int make_mos_gdsgm(int e) { return bin(KOP_ADD, cached(T_MOSGDS, e, false, &Section::make_mos_gds), cached(T_MOSGM, e, false, &Section::make_mos_gm)); }
+    int make_mos_ieq(int e) {                                                                  // i_d - g_ds * v_ds - g_m * v_gs  (stampable.rs:889)
+        const int vgs = cached(T_MOSVGS, e, false, &Section::make_mos_vgs), vds = cached(T_MOSVDS, e, false, &Section::make_mos_vds);
+        const int t1 = bin(KOP_MUL, cached(T_MOSGDS, e, false, &Section::make_mos_gds), vds);
+        const int t2 = bin(KOP_MUL, cached(T_MOSGM, e, false, &Section::make_mos_gm), vgs);
+        return bin(KOP_SUB, bin(KOP_SUB, mos_op(KOP_MOSID, e), t1), t2);
+    }
     int make_caph(int e) {                                                                     // (value/h) * (v+_prev - v-_prev)
         const krb_element &el = B.plan.circuit.el[e];
         int coef = varied(e) ? cached(T_VOH, e, false, &Section::make_voh) : make_voh(e);
@@ -220,6 +248,10 @@ struct Section {
         }
         case S_DIODE_G: return cached(T_DIOG, e, s.neg, &Section::make_diog);
         case S_DIODE_IEQ: return cached(T_DIOI, e, s.neg, &Section::make_dioi);
+        case S_MOS_GDS: return cached(T_MOSGDS, e, s.neg, &Section::make_mos_gds);
+        case S_MOS_GM: return cached(T_MOSGM, e, s.neg, &Section::make_mos_gm);
+        case S_MOS_GDSGM: return cached(T_MOSGDSGM, e, s.neg, &Section::make_mos_gdsgm);
+        case S_MOS_IEQ: return cached(T_MOSIEQ, e, s.neg, &Section::make_mos_ieq);
         case S_CAP_HIST: return cached(T_CAPH, e, s.neg, &Section::make_caph);
         case S_IND_HIST: return cached(T_INDH, e, s.neg, &Section::make_indh);
         case S_CAP_IPREV: return cached(T_CAPI, e, s.neg, &Section::make_capi);

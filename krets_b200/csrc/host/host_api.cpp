@@ -150,6 +150,16 @@ const char *krh_circuit_element_identifier(const krh_circuit *c, int32_t e) {
 }
 const krb_element *krh_circuit_elements(const krh_circuit *c) { return c ? c->pc.pod.data() : nullptr; }
 const uint8_t *krh_circuit_is_current(const krh_circuit *c) { return c ? c->pc.is_current.data() : nullptr; }
+int32_t krh_circuit_set_device_models(krh_circuit *c, int32_t models) {
+    if (!c || (models != KRH_DEVICES_REFERENCE && models != KRH_DEVICES_LEVEL1)) return -1;
+    int32_t k = 0;
+    for (krb_element &e : c->pc.pod)
+        if (e.kind == KRB_NMOS) {
+            if (models == KRH_DEVICES_LEVEL1) e.flags |= KRB_ELEM_FLAG_LEVEL1; else e.flags &= ~KRB_ELEM_FLAG_LEVEL1;
+            k++;
+        }
+    return k;
+}
 
 int64_t krh_generate_frequencies(int32_t kind, uint32_t points, double fstart, double fstop, double *out, int64_t cap) {
     if (kind < 0 || kind > 2) return -1;

@@ -114,7 +114,10 @@ bool paren_values(Cursor &c, double *v, int count) {
     return true;
 }
 
-struct ModelCard { int type; double is, n; };   // type: 0 D, 1 NMOS, 2 PMOS
+struct ModelCard {   // type: 0 D, 1 NMOS, 2 PMOS
+    int type; double is, n;
+    double w = 1e-6, l = 1e-6, vto = 0.0, kp = 2e-5, lambda = 0.02;   // models/nmosfet.rs:24-36 defaults
+};
 
 std::string trim(const std::string &s) {
     size_t b = 0, e = s.size();
@@ -346,7 +349,8 @@ int parse_circuit_description(const std::string &text, ParsedCircuit &out, std::
             c.i = 6;
             std::string name;
             if (!c.space1() || !c.ident(name) || !c.space1()) return fail(PARSE_ERROR, line);
-            ModelCard m{0, 1e-12, 1.0};                                             // models/diode.rs:14-23
+            ModelCard m;                                                            // models/diode.rs:14-23
+            m.type = 0; m.is = 1e-12; m.n = 1.0;
             if (body.compare(c.i, 4, "NMOS") == 0) { m.type = 1; c.i += 4; }
             else if (body.compare(c.i, 4, "PMOS") == 0) { m.type = 2; c.i += 4; }
             else if (c.peek() == 'D') { m.type = 0; c.i += 1; }
@@ -366,6 +370,10 @@ int parse_circuit_description(const std::string &text, ParsedCircuit &out, std::
                 if (!t.value(v)) break;
                 for (auto &ch : key) ch = (char)std::tolower((unsigned char)ch);
                 if (m.type == 0) { if (key == "is") m.is = v; else if (key == "n") m.n = v; }   // models/diode.rs:26-39
+                else if (m.type == 1) {                                                         // models/nmosfet.rs:48-61
+                    if (key == "w") m.w = v; else if (key == "l") m.l = v; else if (key == "vto") m.vto = v;
+                    else if (key == "kp") m.kp = v; else if (key == "lambda") m.lambda = v;
+                }
                 c.i = t.i;
             }
             models[name] = m;
@@ -409,6 +417,11 @@ int parse_circuit_description(const std::string &text, ParsedCircuit &out, std::
             if (it == models.end() || it->second.type != want) { err = "model '" + e.model_name + "' is not defined"; return PARSE_MISSING_MODEL; }
             e.pod.is = it->second.is;
             e.pod.n = it->second.n;
+            if (e.pod.kind == KRB_NMOS) {   // level-1 parameters (nmosfet.rs:39-49): wave[0] = Vth, wave[1] = beta = KP * (W / L), wave[2] = lambda
+                e.pod.wave[0] = it->second.vto;
+                e.pod.wave[1] = it->second.kp * (it->second.w / it->second.l);   // models/nmosfet.rs:43-45
+                e.pod.wave[2] = it->second.lambda;
+            }
         }
     }
     auto lookup = [&](const std::string &key) { auto it = out.index_map.find(key); return it == out.index_map.end() ? -1 : it->second; };
@@ -416,6 +429,7 @@ int parse_circuit_description(const std::string &text, ParsedCircuit &out, std::
         e.pod.ip = lookup("V(" + e.nodes[0] + ")");
         e.pod.im = lookup("V(" + e.nodes[1] + ")");
         e.pod.ic = lookup("I(" + e.identifier + ")");
+        if (e.pod.kind == KRB_NMOS) e.pod.ic = lookup("V(" + e.nodes[2] + ")");   // NMOS: the source node (group 1: no branch current)
         out.pod.push_back(e.pod);
     }
     out.is_current.resize(out.unknown_names.size());

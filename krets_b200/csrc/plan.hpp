@@ -33,7 +33,12 @@ enum SrcKind : uint8_t {
     S_IND_HIST,   // (value/h) * i_prev                    :806-812
     // trapezoidal companions (north-star extension; not in the reference). value/h is taken with h/2, i.e. 2*value/h.
     S_CAP_IPREV,  // capacitor current of the previous time point (per-lane state column)
-    S_IND_VPREV   // v+_prev - v-_prev across an inductor
+    S_IND_VPREV,  // v+_prev - v-_prev across an inductor
+    // level-1 NMOS companion (extension, KRB_ELEM_FLAG_LEVEL1; equations nmosfet.rs:51-102 at the linearisation point)
+    S_MOS_GDS,    // g_ds
+    S_MOS_GM,     // g_m
+    S_MOS_GDSGM,  // g_ds + g_m
+    S_MOS_IEQ     // i_d - g_ds * v_ds - g_m * v_gs          (stampable.rs:889)
 };
 struct Src { SrcKind kind; bool neg; int elem; };
 struct MatContrib { int row, col; Src s; };
@@ -84,7 +89,7 @@ struct Symbolic {
 void symbolic_lu(const Pattern &p, const std::vector<int> &match_row, const std::vector<int> &order, Symbolic &s);
 
 // ---- compiled lane program -----------------------------------------------------------------------------
-enum PoolKind : uint8_t { P_CONST, P_G, P_VAL, P_VOH, P_ACAMP, P_DIO_ISNVT, P_DIO_NVT, P_DIO_IS, P_DIO_VCRIT };
+enum PoolKind : uint8_t { P_CONST, P_G, P_VAL, P_VOH, P_ACAMP, P_DIO_ISNVT, P_DIO_NVT, P_DIO_IS, P_DIO_VCRIT, P_MOS_VTH, P_MOS_BETA, P_MOS_LAMBDA };
 struct PoolEntry { PoolKind kind; bool neg; int elem; double c; };
 
 struct Program {

@@ -90,6 +90,23 @@ int build_stamps(const Circuit &c, int mode, int integrator, Stamps &out) {
             }
             break;
         case KRB_NMOS:
+            if (el.flags & KRB_ELEM_FLAG_LEVEL1) {
+                // EXTENSION: the level-1 companion at the linearisation point, drain d = ip, gate g = im, source s = ic.
+                // i_d enters the drain and leaves the source: rows d and s carry opposite signs (the reference's unreachable stamp,
+                // stampable.rs:846-868, pushes (s,d) and (s,g) with the drain row's signs, which violates KCL at the source).
+                // AC: the small-signal conductances at the operating point, no excitation (:897-912 returns none).
+                const int d = ip, g = im, s = ic;
+                E.m(d, d, S_MOS_GDS, false, e);
+                E.m(s, s, S_MOS_GDSGM, false, e);
+                if (d >= 0 && s >= 0) { E.m(d, s, S_MOS_GDSGM, true, e); E.m(s, d, S_MOS_GDS, true, e); }
+                if (s >= 0 && g >= 0) E.m(s, g, S_MOS_GM, true, e);
+                if (d >= 0 && g >= 0) E.m(d, g, S_MOS_GM, false, e);
+                if (mode != KRB_MODE_AC) {   // :889-899 order: source row first
+                    E.b(s, S_MOS_IEQ, false, e);
+                    E.b(d, S_MOS_IEQ, true, e);
+                }
+                break;
+            }
             if (mode == KRB_MODE_AC) return KRB_ERR_UNSUPPORTED;   // :914-921 todo!()
             break;                            // :842-844: index lookups never match -> stamps nothing
         case KRB_V:                           // :960-1050
@@ -182,6 +199,11 @@ void nominal_magnitudes(const Circuit &c, const Stamps &s, const Pattern &p, int
                 vr = el.is / nvt;
                 break;
             }
+            // level-1 NMOS one volt into saturation (v_ov = 1, v_ds = 1): like the diode, its conductances vanish in cut-off, so
+            // the static pivot plan prefers any resistor / source-coupling entry of comparable size
+            case S_MOS_GM: vr = el.wave[1] * (1.0 + el.wave[2]); break;
+            case S_MOS_GDS: vr = 0.5 * el.wave[1] * el.wave[2]; break;
+            case S_MOS_GDSGM: vr = el.wave[1] * (1.0 + el.wave[2]) + 0.5 * el.wave[1] * el.wave[2]; break;
             default: break;
             }
             if (src.neg) { vr = -vr; vi = -vi; }
@@ -207,6 +229,9 @@ void evaluate_pool(const Plan &plan, const Circuit &c, double h, std::vector<dou
         case P_DIO_ISNVT: v = el->is / (el->n * thermal_voltage()); break;   // diode.rs:47
         case P_DIO_NVT: v = el->n * thermal_voltage(); break;
         case P_DIO_IS: v = el->is; break;
+        case P_MOS_VTH: v = el->wave[0]; break;
+        case P_MOS_BETA: v = el->wave[1]; break;
+        case P_MOS_LAMBDA: v = el->wave[2]; break;
         case P_DIO_VCRIT: {                                          // diode.rs:65-70
             // n * Vt * ln(f64::MAX * n * Vt / is), evaluated left to right as the reference does (f64::MAX * n may overflow)
             v = el->n * thermal_voltage() * std::log(1.7976931348623157e308 * el->n * thermal_voltage() / el->is);

@@ -84,6 +84,9 @@ static void emit_section(const Program &prog, std::string &o) {
             i++;
             break;
         }
+        case KOP_MOSGM:
+        case KOP_MOSGDS:
+        case KOP_MOSID: put(o, "s[%u] = k_mos(%d, s[%u], s[%u], c.Bc + %u);\n", d, (int)opc - (int)KOP_MOSGM, a, b, imm); break;
         case KOP_MULG: put(o, "s[%u] = k_mulg(s[%u], s[%u], grow);\n", d, a, b); break;
         case KOP_NOP:
         case KOP_WAIT:   // loads are synchronous here: the compiler schedules them

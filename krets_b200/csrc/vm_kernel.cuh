@@ -41,6 +41,25 @@ struct VmParams {
 // diode.rs:42-70
 __device__ __forceinline__ double diode_limit(double vd, double vcrit) { return fmin(fmax(vd, -vcrit), vcrit); }
 
+// level-1 NMOS, nmosfet.rs:51-102 (extension: reached only through KRB_ELEM_FLAG_LEVEL1).  what: 0 g_m, 1 g_ds, 2 i_d.  The region
+// tests and the evaluation order of every product are the reference's; single operations are rounded separately (no contraction).
+__device__ __forceinline__ double nmos_level1(int what, double vgs, double vds, double vth, double beta, double lambda) {
+    if (vgs <= vth) return 0.0;
+    const double vov = __dsub_rn(vgs, vth);
+    if (vds >= 0.0 && vds <= vov) {          // linear region
+        if (what == 0) return __dmul_rn(beta, vds);
+        if (what == 1) return __dmul_rn(beta, __dsub_rn(vov, vds));
+        return __dmul_rn(beta, __dsub_rn(__dmul_rn(vov, vds), __ddiv_rn(__dmul_rn(vds, vds), 2.0)));
+    }
+    if (vds >= vov && vds >= 0.0) {          // saturation region
+        const double clm = __dadd_rn(1.0, __dmul_rn(lambda, vds));
+        if (what == 0) return __dmul_rn(__dmul_rn(beta, vov), clm);
+        if (what == 1) return __dmul_rn(__dmul_rn(__ddiv_rn(beta, 2.0), lambda), __dmul_rn(vov, vov));
+        return __dmul_rn(__dmul_rn(__ddiv_rn(beta, 2.0), __dmul_rn(vov, vov)), clm);
+    }
+    return 0.0;
+}
+
 // ---- shared-memory scratch access with 32-bit addresses (no generic-pointer arithmetic in the interpreter loop) ----
 template <bool CPLX> struct ScrIO;
 template <> struct ScrIO<false> {
@@ -201,6 +220,12 @@ __global__ void __launch_bounds__(TPB) krb_lane_vm(const VmParams p) {
                             IO::st(ad, S::from_real(__dsub_rn(id, __dmul_rn(g, vd))));
                             break;
                         }
+                        case KOP_MOSGM:
+                        case KOP_MOSGDS:
+                        case KOP_MOSID:
+                            IO::st(ad, S::from_real(nmos_level1((int)opc - (int)KOP_MOSGM, S::re(IO::ld(aa)), S::re(IO::ld(ab)), __ldg(Bc + imm),
+                                                                __ldg(Bc + imm + 1), __ldg(Bc + imm + 2))));
+                            break;
                         default: break;   // KOP_NOP
                         }
                         t += step;

@@ -39,7 +39,11 @@ enum KrbOp : uint32_t {
     KOP_NOP = 22,   // padding
     KOP_WAIT = 23,  // wait for the asynchronous loads (LDI/LDG/LDX/LDBS are issued as cp.async straight into the scratch slot)
     KOP_MULG = 24,  // scr[d] = scr[a] * scr[b], a scaled factor entry u^ = u * (1/pivot): also tracks the lane's pivot growth (KRB_LANE_INACCURATE)
-    KOP_COUNT = 25
+    // level-1 NMOS at v_gs = re(scr[a]), v_ds = re(scr[b]); B[imm..imm+2] = {Vth, beta, lambda}  (nmosfet.rs:51-102; extension, see KRB_ELEM_FLAG_LEVEL1)
+    KOP_MOSGM = 25,   // scr[d] = g_m
+    KOP_MOSGDS = 26,  // scr[d] = g_ds
+    KOP_MOSID = 27,   // scr[d] = i_d
+    KOP_COUNT = 28
 };
 
 static inline uint32_t krb_op_w0(uint32_t opc, uint32_t d, uint32_t a, uint32_t b) { return opc | (d << 8) | (a << 16) | (b << 24); }

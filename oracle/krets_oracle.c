@@ -83,9 +83,12 @@ typedef struct {
     char model_name[KO_NAME];
     double is, n_emis;       /* models/diode.rs:14-23 */
     int ip, im, ic;          /* cached index_map lookups; -1 = key absent */
+    int is3;                 /* NMOS: index of V(<source>) (extension below) */
+    double vth, beta, lambda;/* NMOS level-1 parameters: models/nmosfet.rs:24-45 (beta = KP * (W / L)) */
 } ko_elem;
 
-typedef struct { char name[KO_NAME]; int type; /* 0 D, 1 NMOS, 2 PMOS */ double is, n_emis; } ko_model;
+typedef struct { char name[KO_NAME]; int type; /* 0 D, 1 NMOS, 2 PMOS */ double is, n_emis;
+                 double w, l, vto, kp, lambda; /* models/nmosfet.rs:24-36 */ } ko_model;
 
 struct ko_circuit {
     ko_elem *e; int ne, ecap;
@@ -341,6 +344,7 @@ static int parse_model_line(const char *line, ko_model *m) {
     else if (*p == 'D') { m->type = 0; p += 1; }
     else return 0;
     m->is = 1e-12; m->n_emis = 1.0;
+    m->w = 1e-6; m->l = 1e-6; m->vto = 0.0; m->kp = 2e-5; m->lambda = 0.02;   /* models/nmosfet.rs:24-36 */
     p = space0(p);
     if (*p == '(') p++;
     for (;;) {
@@ -355,6 +359,10 @@ static int parse_model_line(const char *line, ko_model *m) {
         if (!(r = value_parser(r, &v))) break;
         for (char *k = key; *k; k++) *k = (char)tolower((unsigned char)*k);
         if (m->type == 0) { if (!strcmp(key, "is")) m->is = v; else if (!strcmp(key, "n")) m->n_emis = v; }
+        else if (m->type == 1) {                                                     /* models/nmosfet.rs:48-61 */
+            if (!strcmp(key, "w")) m->w = v; else if (!strcmp(key, "l")) m->l = v; else if (!strcmp(key, "vto")) m->vto = v;
+            else if (!strcmp(key, "kp")) m->kp = v; else if (!strcmp(key, "lambda")) m->lambda = v;
+        }
         p = r;
     }
     return 1;
@@ -618,6 +626,8 @@ ko_circuit *ko_parse(const char *text, int *err, char *errmsg, int errmsg_len) {
             for (int k = 0; k < c->nmodels; k++) if (!strcmp(c->models[k].name, e->model_name) && c->models[k].type == want) found = k;
             if (found < 0) { set_err(err, KO_ERR_MISSING_MODEL, errmsg, errmsg_len, "model not defined (element %d): %s", i, e->model_name); ko_free(c); return NULL; }
             e->is = c->models[found].is; e->n_emis = c->models[found].n_emis;
+            e->vth = c->models[found].vto; e->lambda = c->models[found].lambda;
+            e->beta = c->models[found].kp * (c->models[found].w / c->models[found].l);   /* models/nmosfet.rs:43-45 */
         }
     }
     c->is_current = (int *)malloc(sizeof(int) * (c->n ? c->n : 1));
@@ -628,6 +638,8 @@ ko_circuit *ko_parse(const char *text, int *err, char *errmsg, int errmsg_len) {
         snprintf(key, sizeof(key), "V(%s)", e->plus); e->ip = ko_index_of(c, key);
         snprintf(key, sizeof(key), "V(%s)", e->minus); e->im = ko_index_of(c, key);
         snprintf(key, sizeof(key), "I(%s)", e->ident); e->ic = ko_index_of(c, key);
+        e->is3 = -1;
+        if (e->kind == KO_NMOS) { snprintf(key, sizeof(key), "V(%s)", e->third); e->is3 = ko_index_of(c, key); }
     }
     return c;
 }
@@ -700,6 +712,35 @@ static double diode_ieq(const ko_elem *e, const ko_map *m) {    /* diode.rs:58-6
     double vd = diode_vd(e, m);
     return diode_i(e, m) - diode_g(e, m) * vd;
 }
+/* nmosfet.rs:51-102: g_m, g_ds, i_d of the level-1 model, region tests and evaluation order as written there.
+ * The REFERENCE never reaches these through a stamp (stampable.rs:842-844: bare node names never match the index map); they
+ * are used only by the level-1 EXTENSION below (ko_set_device_models), which has no upstream oracle: tests pin it against an
+ * independent Newton solve of the KCL equations (tests/test_nmos_level1.py). */
+static double nmos_gm(const ko_elem *e, double vgs, double vds) {
+    double vth = e->vth, beta = e->beta, lambda = e->lambda;
+    if (vgs <= vth) return 0.0;
+    else if (vds >= 0.0 && vds <= (vgs - vth)) return beta * vds;
+    else if (vds >= (vgs - vth) && vds >= 0.0) return beta * (vgs - vth) * (1.0 + lambda * vds);
+    return 0.0;
+}
+static double nmos_gds(const ko_elem *e, double vgs, double vds) {
+    double vth = e->vth, beta = e->beta, lambda = e->lambda;
+    if (vgs <= vth) return 0.0;
+    else if (vds >= 0.0 && vds <= (vgs - vth)) return beta * (vgs - vth - vds);
+    else if (vds >= (vgs - vth) && vds >= 0.0) return (beta / 2.0) * lambda * ((vgs - vth) * (vgs - vth));
+    return 0.0;
+}
+static double nmos_id(const ko_elem *e, double vgs, double vds) {
+    double vth = e->vth, beta = e->beta, lambda = e->lambda;
+    if (vgs <= vth) return 0.0;
+    else if (vds >= 0.0 && vds <= (vgs - vth)) return beta * ((vgs - vth) * vds - ((vds * vds) / 2.0));
+    else if (vds >= (vgs - vth) && vds >= 0.0) return (beta / 2.0) * ((vgs - vth) * (vgs - vth)) * (1.0 + lambda * vds);
+    return 0.0;
+}
+/* 0 = reference behaviour (NMOS stamps nothing); 1 = level-1 companion stamps (EXTENSION) */
+static int ko_device_models = 0;
+void ko_set_device_models(int models) { ko_device_models = models ? 1 : 0; }
+
 static double pulse_value_at(const double *p, double time) {    /* voltage_source.rs:70-93 */
     double v0 = p[0], v1 = p[1], td = p[2], tr = p[3], tf = p[4], pw = p[5], per = p[6];
     if (time < td) return v0;
@@ -850,6 +891,27 @@ static int stamp_element(const ko_elem *e, int mode, const ko_map *guess, const 
         }
         break;
     case KO_NMOS:
+        if (ko_device_models) {
+            /* EXTENSION: level-1 companion at the linearisation point (voltages default to 0.0, :825-833); drain d, gate gt, source s.
+             * KCL-consistent signs: i_d enters the drain and leaves the source (the unreachable reference stamp :846-868 gives the
+             * source row the drain row's signs).  AC: small-signal g_m / g_ds at the operating point, no excitation (:897-912). */
+            int d = ip, gt = im, s = e->is3;
+            double vg = (guess->x && gt >= 0) ? guess->x[gt] : 0.0, vs = (guess->x && s >= 0) ? guess->x[s] : 0.0;
+            double vdn = (guess->x && d >= 0) ? guess->x[d] : 0.0;
+            double vgs = vg - vs, vds = vdn - vs;
+            double gm = nmos_gm(e, vgs, vds), gds = nmos_gds(e, vgs, vds);
+            if (d >= 0) trip_push(g, d, d, gds, 0.0);
+            if (s >= 0) trip_push(g, s, s, gds + gm, 0.0);
+            if (d >= 0 && s >= 0) { trip_push(g, d, s, -(gds + gm), 0.0); trip_push(g, s, d, -gds, 0.0); }
+            if (s >= 0 && gt >= 0) trip_push(g, s, gt, -gm, 0.0);
+            if (d >= 0 && gt >= 0) trip_push(g, d, gt, gm, 0.0);
+            if (mode != MODE_AC) {
+                double ieq = nmos_id(e, vgs, vds) - gds * vds - gm * vgs;   /* :889 */
+                if (s >= 0) trip_push(b, s, 0, ieq, 0.0);
+                if (d >= 0) trip_push(b, d, 0, -ieq, 0.0);
+            }
+            break;
+        }
         if (mode == MODE_AC) return KO_ERR_UNSUPPORTED;      /* :914-921 todo!() */
         break;                                               /* :842-844,895,899: lookups never match -> no stamps */
     case KO_V:                                               /* :960-1050 */

@@ -69,6 +69,8 @@ def lib():
         L.ko_set_element_value.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.ko_element_indices.argtypes = [C.c_void_p, C.c_int, ip, ip, ip]
         L.ko_is_nonlinear.argtypes = [C.c_void_p]
+        L.ko_set_device_models.argtypes = [C.c_int]
+        L.ko_set_device_models.restype = None
         L.ko_stamp_matrix.argtypes = [C.c_void_p, C.c_int, C.c_double, dp, ip, ip, dp, C.c_int]
         L.ko_generate_frequencies.argtypes = [C.c_int, C.c_uint, C.c_double, C.c_double, dp, C.c_int]
         L.ko_transient_value_at.restype = C.c_double
@@ -95,6 +97,12 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def set_device_models(models: int):
+    """EXTENSION (no upstream oracle): 1 = NMOS elements stamp the level-1 companion model of nmosfet.rs:51-102; 0 (default) = the
+    reference's behaviour (an NMOS stamps nothing, stampable.rs:842-844).  Process-wide switch of the restatement."""
+    lib().ko_set_device_models(int(models))
 
 
 class SolverConfig:

@@ -10,7 +10,7 @@ import numpy as np
 
 from krets_b200 import _lib
 
-(END, LDB, LDBS, LDI, LDG, STG, LDX, XOUT, ZERO, MOV, NEG, ADD, SUB, MUL, FNMA, RCP, INV, DIVR, MULJ, DIOG, DIOI, LDK, NOP, WAIT, MULG) = range(25)
+(END, LDB, LDBS, LDI, LDG, STG, LDX, XOUT, ZERO, MOV, NEG, ADD, SUB, MUL, FNMA, RCP, INV, DIVR, MULJ, DIOG, DIOI, LDK, NOP, WAIT, MULG, MOSGM, MOSGDS, MOSID) = range(28)
 ZERO_PIVOT, NOT_CONVERGED, NONFINITE, INACCURATE = 1, 2, 4, 8
 GROWTH_LIMIT = 2.0 ** 24   # KRB_GROWTH_LIMIT_LOG2
 
@@ -70,7 +70,7 @@ class Emulator:
                 pci += 1
                 opc, d, a, b = w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF, (w0 >> 24) & 0xFF
                 self.stats["ops"] += 1
-                if opc in (ADD, SUB, MUL, MULG, FNMA, DIVR):
+                if opc in (ADD, SUB, MUL, MULG, FNMA, DIVR, MOSGM, MOSGDS, MOSID):
                     touched = {d, a, b}
                 elif opc in (MOV, NEG, RCP, INV, MULJ, DIOG, DIOI):
                     touched = {d, a}
@@ -158,6 +158,20 @@ class Emulator:
                     ex = np.exp(vl / nvt)
                     g = isnvt * ex
                     scr[d] = (g if opc == DIOG else (is_ * (ex - 1.0) - g * vd)).astype(self.dtype)
+                elif opc in (MOSGM, MOSGDS, MOSID):     # level-1 NMOS, nmosfet.rs:51-102 (extension)
+                    vgs, vds = scr[a].real, scr[b].real
+                    vth, beta, lam = self.pool[imm: imm + 3]
+                    vov = vgs - vth
+                    on = vgs > vth
+                    lin = on & (vds >= 0.0) & (vds <= vov)
+                    sat = on & ~lin & (vds >= vov) & (vds >= 0.0)
+                    if opc == MOSGM:
+                        v = np.where(lin, beta * vds, np.where(sat, (beta * vov) * (1.0 + lam * vds), 0.0))
+                    elif opc == MOSGDS:
+                        v = np.where(lin, beta * (vov - vds), np.where(sat, ((beta / 2.0) * lam) * (vov * vov), 0.0))
+                    else:
+                        v = np.where(lin, beta * (vov * vds - (vds * vds) / 2.0), np.where(sat, ((beta / 2.0) * (vov * vov)) * (1.0 + lam * vds), 0.0))
+                    scr[d] = v.astype(self.dtype)
                 else:
                     raise ValueError(f"bad opcode {opc}")
         return notconv
