@@ -362,7 +362,7 @@ def make_workload(name, args, rank):
     if name == "rectifier_tran":
         # The nonlinear path (north star (d)): the reference's own rectifier test circuit (circuits/rectifier: four diodes, R, C, two sine
         # sources; test_transient.rs) stepped with backward Euler, Newton-Raphson with the per-lane convergence mask at every step, on the
-        # lane VM; Monte-Carlo lanes vary R1 / C1.  Not a BASELINE config: it puts a number on the interpreter-bound path.
+        # lane VM (specialised kernel, vm_jit.cpp); Monte-Carlo lanes vary R1 / C1.  Not a BASELINE config: it puts a number on the nonlinear path.
         text = golden["netlists"]["rectifier"]
         circuit = kb.parse_circuit_description(text)
         names = ["C1", "R1"]
@@ -390,7 +390,7 @@ def make_workload(name, args, rank):
                     "tolerance": "1e-6: Newton-Raphson with exp(); libm and CUDA exp differ in the last ulp (tests/test_gpu_parity.py::test_transient_rectifier)"}
         return Workload(name=name, config="nonlinear", plan=plan, circuit=circuit, lanes=lanes, points=lanes * nsteps, dtype="f64", s=8, out=out,
                         step=lambda: plan.solve_transient(pdc, nsteps, lanes, varied_values=vals, out=out),
-                        kernel="krb_lane_vm<f64> (interpreted lane program: stamp + LDU + solve per Newton iteration, per-lane convergence mask)",
+                        kernel="krb_jit_vm (the lane program as a circuit-specialised kernel, NVRTC for sm_100a at first use: stamp + LDU + solve per Newton iteration, per-lane convergence mask; KRB_VM_JIT=0: krb_lane_vm interpreter)",
                         what=f"circuits/rectifier (4 diodes) transient, {nsteps} backward-Euler steps x {lanes} Monte-Carlo R/C variants per GPU, Newton-Raphson at every step (nonlinear path; not a BASELINE config)",
                         alg=8 * (int(plan.info.nnz_lu) + 3 * circuit.n), alg_what="B_step = s*(nnz_lu + 3*n) per Newton iteration (at least two per point), SURVEY 8(d)",
                         moved=8 * circuit.n, moved_what="s*n: one result row per solved point (the lane program's working set stays on chip)",
