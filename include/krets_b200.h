@@ -169,8 +169,9 @@ int32_t krb_plan_get_pivot_order(const krb_plan *p, int32_t *row_order /*n*/, in
  * section 0 = first/only section, 1 = factor-once section, 2 = per-step section.  ops are 2 x uint32 each. */
 int64_t krb_plan_program_size(const krb_plan *p, int32_t section);
 int32_t krb_plan_get_program(const krb_plan *p, int32_t section, uint32_t *ops /*2*size*/);
-/* Circuit-specialised lane kernel.  Lane programs of up to KRB_VM_JIT_MAX_OPS (default 2500: NVRTC needs about a second per thousand operations) operations are not interpreted: at
- * first use the library writes the program out as straight-line CUDA (one statement per operation, scratch cells in registers),
+/* Circuit-specialised lane kernel.  Lane programs of up to KRB_VM_JIT_MAX_OPS (default 20000) operations are not interpreted: at
+ * the plan's first solve (always up to 2500 operations; above, when that solve has at least KRB_VM_JIT_MIN_POINTS = 32768 lanes x rows to
+ * pay for NVRTC's half second per thousand operations) the library writes the program out as straight-line CUDA (one statement per operation, scratch cells in registers),
  * compiles it with NVRTC for sm_100a and launches that kernel (KRB_VM_JIT=0: always interpret).  The two entry points below expose
  * the generated text and the NVRTC step without a device.  krb_plan_jit_source: returns the size of the text incl. the terminating
  * NUL (0: plan not eligible, -1: bad arguments) and copies at most cap bytes; host_mode != 0 prefixes the text for a host build

@@ -163,7 +163,7 @@ static int upload_vec(const std::vector<V> &v, V **out) {
     return KRB_OK;
 }
 
-static int upload_plan(Plan &plan, DeviceState &d) {
+static int upload_plan(Plan &plan, DeviceState &d, long long points) {
     if (d.uploaded) return KRB_OK;
     int rc;
     for (int s = 0; s < 3; s++) {
@@ -203,8 +203,8 @@ static int upload_plan(Plan &plan, DeviceState &d) {
         CUDA_TRY(cudaEventCreateWithFlags(&d.compute_done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&d.copy_done[i], cudaEventDisableTiming));
     }
-    if (!plan.use_chain && !plan.use_front && vm_jit_enabled() && vm_jit_eligible(plan)) {
-        // small lane programs run as a kernel specialised to the circuit (scratch cells in registers, no op decode)
+    if (!plan.use_chain && !plan.use_front && vm_jit_enabled() && vm_jit_eligible(plan) && vm_jit_worthwhile(plan, points)) {
+        // lane programs run as a kernel specialised to the circuit (scratch cells in registers, no op decode); decided at the plan's first solve
         NvtxRange nvtx_jit("krb plan: specialise the lane kernel (NVRTC)");
         std::string why;
         d.jit = vm_jit_build(plan, sizeof(VmParams), why);
@@ -399,8 +399,8 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     const int rows = a.rows;
     const int tpb = pick_tpb(P0);
     int rc;
-    if ((rc = upload_plan(P0, D0))) return rc;
-    if (PS && (rc = upload_plan(*PS, *PS->dev))) return rc;
+    if ((rc = upload_plan(P0, D0, PS ? a.lanes : a.lanes * (long long)a.rows))) return rc;
+    if (PS && (rc = upload_plan(*PS, *PS->dev, a.lanes * (long long)a.rows))) return rc;
     if (PS && PS->n_inputs != P0.n_inputs) { set_error("plan_dc and plan_tran must be analysed with the same varied elements"); return KRB_ERR_INVALID_ARGUMENT; }
     if (n == 0 || a.lanes <= 0) return KRB_OK;
     const bool chain = P0.use_chain && !PS;

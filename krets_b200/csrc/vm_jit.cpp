@@ -20,10 +20,12 @@ static const char *const PRELUDE =
 #include "vm_jit_prelude.inc"
     ;
 
+static const int64_t KRB_VM_JIT_SMALL_OPS = 2500;   // about a second of NVRTC: always specialised
+
 int64_t vm_jit_max_ops() {
     static const int64_t v = [] {
         const char *e = getenv("KRB_VM_JIT_MAX_OPS");
-        return e ? (int64_t)atoll(e) : (int64_t)2500;
+        return e ? (int64_t)atoll(e) : (int64_t)20000;
     }();
     return v;
 }
@@ -37,6 +39,12 @@ bool vm_jit_eligible(const Plan &plan) {
     return total > 0 && total <= vm_jit_max_ops();
 }
 
+bool vm_jit_worthwhile(const Plan &plan, long long points) {
+    const int64_t total = plan.sec[0].n_ops + plan.sec[1].n_ops + plan.sec[2].n_ops;
+    static const long long min_points = [] { const char *e = getenv("KRB_VM_JIT_MIN_POINTS"); return e ? atoll(e) : 32768ll; }();
+    return total <= KRB_VM_JIT_SMALL_OPS || points >= min_points;
+}
+
 // ---- source generation -----------------------------------------------------------------------------------------------------
 static void put(std::string &o, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 static void put(std::string &o, const char *fmt, ...) {
@@ -48,81 +56,148 @@ static void put(std::string &o, const char *fmt, ...) {
     o += buf;
 }
 
-// one section: the op stream written out, one statement per operation (same order, same arithmetic as vm_kernel.cuh)
-static void emit_section(const Program &prog, std::string &o) {
+// ---- decoded lane-program operations ----
+struct DecOp { uint32_t opc, d, a, b, imm; uint64_t bits; };
+static std::vector<DecOp> decode(const Program &prog) {
+    std::vector<DecOp> v;
     const std::vector<uint32_t> &w = prog.ops;
     const size_t n = w.size() / 2;
     for (size_t i = 0; i < n; i++) {
-        const uint32_t w0 = w[2 * i], imm = w[2 * i + 1];
-        const uint32_t opc = w0 & 0xffu, d = (w0 >> 8) & 0xffu, a = (w0 >> 16) & 0xffu, b = w0 >> 24;
-        switch (opc) {
-        case KOP_END: return;
-        case KOP_LDB: put(o, "s[%u] = k_real(c.Bc[%u]);\n", d, imm); break;
-        case KOP_LDBS: put(o, "s[%u] = k_real(c.Bs[%u]);\n", d, imm); break;
-        case KOP_LDI: put(o, "s[%u] = k_real(c.IN[(size_t)%uu * c.L]);\n", d, imm); break;
-        case KOP_LDG: put(o, "s[%u] = c.G[(size_t)%uu * c.L];\n", d, imm); break;
-        case KOP_STG: put(o, "c.G[(size_t)%uu * c.L] = s[%u];\n", imm, a); break;
-        case KOP_LDX: put(o, "s[%u] = k_ldx(c, %uu, %uu);\n", d, imm, b); break;
-        case KOP_XOUT: put(o, "k_xout(c, s[%u], %uu, %uu, status, notconv);\n", a, imm, b); break;
-        case KOP_ZERO: put(o, "s[%u] = k_zero();\n", d); break;
-        case KOP_MOV: put(o, "s[%u] = s[%u];\n", d, a); break;
-        case KOP_NEG: put(o, "s[%u] = k_neg(s[%u]);\n", d, a); break;
-        case KOP_ADD: put(o, "s[%u] = k_add(s[%u], s[%u]);\n", d, a, b); break;
-        case KOP_SUB: put(o, "s[%u] = k_sub(s[%u], s[%u]);\n", d, a, b); break;
-        case KOP_MUL: put(o, "s[%u] = k_mul(s[%u], s[%u]);\n", d, a, b); break;
-        case KOP_FNMA: put(o, "s[%u] = k_fnma(s[%u], s[%u], s[%u]);\n", d, d, a, b); break;
-        case KOP_RCP: put(o, "s[%u] = k_rcp(s[%u], status);\n", d, a); break;
-        case KOP_INV: put(o, "s[%u] = k_inv(s[%u]);\n", d, a); break;
-        case KOP_DIVR: put(o, "s[%u] = k_divr(s[%u], s[%u]);\n", d, a, b); break;
-        case KOP_MULJ: put(o, "s[%u] = k_mulj(s[%u]);\n", d, a); break;
-        case KOP_DIOG: put(o, "s[%u] = k_diog(s[%u], c.Bc + %u);\n", d, a, imm); break;
-        case KOP_DIOI: put(o, "s[%u] = k_dioi(s[%u], c.Bc + %u);\n", d, a, imm); break;
-        case KOP_LDK: {   // the constant sits in the next op slot (both words)
-            if (i + 1 >= n) return;
-            const uint64_t bits = (uint64_t)w[2 * i + 2] | ((uint64_t)w[2 * i + 3] << 32);
-            put(o, "s[%u] = k_const(0x%016llxull);\n", d, (unsigned long long)bits);
+        const uint32_t w0 = w[2 * i];
+        DecOp o{w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu, w0 >> 24, w[2 * i + 1], 0};
+        if (o.opc == KOP_END) break;
+        if (o.opc == KOP_NOP || o.opc == KOP_WAIT) continue;   // loads are synchronous here: the compiler schedules them
+        if (o.opc == KOP_LDK) {                                  // the constant sits in the next op slot (both words)
+            if (i + 1 >= n) break;
+            o.bits = (uint64_t)w[2 * i + 2] | ((uint64_t)w[2 * i + 3] << 32);
             i++;
-            break;
         }
-        case KOP_MOSGM:
-        case KOP_MOSGDS:
-        case KOP_MOSID: put(o, "s[%u] = k_mos(%d, s[%u], s[%u], c.Bc + %u);\n", d, (int)opc - (int)KOP_MOSGM, a, b, imm); break;
-        case KOP_MULG: put(o, "s[%u] = k_mulg(s[%u], s[%u], grow);\n", d, a, b); break;
-        case KOP_NOP:
-        case KOP_WAIT:   // loads are synchronous here: the compiler schedules them
-        default: break;
-        }
+        v.push_back(o);
+    }
+    return v;
+}
+// scratch cells an operation reads (n_r of them in r[]) and the one it writes (-1: none)
+static void op_slots(const DecOp &o, int r[3], int &n_r, int &w) {
+    n_r = 0; w = -1;
+    switch (o.opc) {
+    case KOP_LDB: case KOP_LDBS: case KOP_LDI: case KOP_LDG: case KOP_LDX: case KOP_ZERO: case KOP_LDK: w = (int)o.d; break;
+    case KOP_STG: case KOP_XOUT: r[n_r++] = (int)o.a; break;
+    case KOP_MOV: case KOP_NEG: case KOP_RCP: case KOP_INV: case KOP_MULJ: case KOP_DIOG: case KOP_DIOI: r[n_r++] = (int)o.a; w = (int)o.d; break;
+    case KOP_ADD: case KOP_SUB: case KOP_MUL: case KOP_MULG: case KOP_DIVR: case KOP_MOSGM: case KOP_MOSGDS: case KOP_MOSID:
+        r[n_r++] = (int)o.a; r[n_r++] = (int)o.b; w = (int)o.d; break;
+    case KOP_FNMA: r[n_r++] = (int)o.d; r[n_r++] = (int)o.a; r[n_r++] = (int)o.b; w = (int)o.d; break;
+    default: break;
     }
 }
 
-static int max_slot(const Program &prog) {
-    int m = 0;
-    const size_t n = prog.ops.size() / 2;
-    for (size_t i = 0; i < n; i++) {
-        const uint32_t w0 = prog.ops[2 * i];
-        const uint32_t opc = w0 & 0xffu;
-        if (opc == KOP_END) break;
-        if (opc == KOP_LDK) { m = std::max<int>(m, (w0 >> 8) & 0xff); i++; continue; }
-        m = std::max<int>(m, (w0 >> 8) & 0xff);
-        m = std::max<int>(m, (w0 >> 16) & 0xff);
-        if (opc != KOP_LDX && opc != KOP_XOUT) m = std::max<int>(m, w0 >> 24);
+// one operation = one statement (same order, same arithmetic as vm_kernel.cuh); scratch cell k is written as pre<k>post
+static void emit_stmt(const DecOp &op, const char *pre, const char *post, std::string &o) {
+    char D[24], A[24], Bn[24];
+    snprintf(D, sizeof D, "%s%u%s", pre, op.d, post);
+    snprintf(A, sizeof A, "%s%u%s", pre, op.a, post);
+    snprintf(Bn, sizeof Bn, "%s%u%s", pre, op.b, post);
+    const uint32_t imm = op.imm;
+    switch (op.opc) {
+    case KOP_LDB: put(o, "%s = k_real(c.Bc[%u]);\n", D, imm); break;
+    case KOP_LDBS: put(o, "%s = k_real(c.Bs[%u]);\n", D, imm); break;
+    case KOP_LDI: put(o, "%s = k_real(c.IN[(size_t)%uu * c.L]);\n", D, imm); break;
+    case KOP_LDG: put(o, "%s = c.G[(size_t)%uu * c.L];\n", D, imm); break;
+    case KOP_STG: put(o, "c.G[(size_t)%uu * c.L] = %s;\n", imm, A); break;
+    case KOP_LDX: put(o, "%s = k_ldx(c, %uu, %uu);\n", D, imm, op.b); break;
+    case KOP_XOUT: put(o, "k_xout(c, %s, %uu, %uu, status, notconv);\n", A, imm, op.b); break;
+    case KOP_ZERO: put(o, "%s = k_zero();\n", D); break;
+    case KOP_MOV: put(o, "%s = %s;\n", D, A); break;
+    case KOP_NEG: put(o, "%s = k_neg(%s);\n", D, A); break;
+    case KOP_ADD: put(o, "%s = k_add(%s, %s);\n", D, A, Bn); break;
+    case KOP_SUB: put(o, "%s = k_sub(%s, %s);\n", D, A, Bn); break;
+    case KOP_MUL: put(o, "%s = k_mul(%s, %s);\n", D, A, Bn); break;
+    case KOP_FNMA: put(o, "%s = k_fnma(%s, %s, %s);\n", D, D, A, Bn); break;
+    case KOP_RCP: put(o, "%s = k_rcp(%s, status);\n", D, A); break;
+    case KOP_INV: put(o, "%s = k_inv(%s);\n", D, A); break;
+    case KOP_DIVR: put(o, "%s = k_divr(%s, %s);\n", D, A, Bn); break;
+    case KOP_MULJ: put(o, "%s = k_mulj(%s);\n", D, A); break;
+    case KOP_DIOG: put(o, "%s = k_diog(%s, c.Bc + %u);\n", D, A, imm); break;
+    case KOP_DIOI: put(o, "%s = k_dioi(%s, c.Bc + %u);\n", D, A, imm); break;
+    case KOP_LDK: put(o, "%s = k_const(0x%016llxull);\n", D, (unsigned long long)op.bits); break;
+    case KOP_MOSGM:
+    case KOP_MOSGDS:
+    case KOP_MOSID: put(o, "%s = k_mos(%d, %s, %s, c.Bc + %u);\n", D, (int)op.opc - (int)KOP_MOSGM, A, Bn, imm); break;
+    case KOP_MULG: put(o, "%s = k_mulg(%s, %s, grow);\n", D, A, Bn); break;
+    default: break;
+    }
+}
+
+static int max_slot(const std::vector<DecOp> &ops) {
+    int m = 0, r[3], n_r, w;
+    for (const DecOp &op : ops) {
+        op_slots(op, r, n_r, w);
+        for (int k = 0; k < n_r; k++) m = std::max(m, r[k]);
+        m = std::max(m, w);
     }
     return m;
+}
+
+// Long programs: NVVM's time grows faster than linearly with the length of one basic block, so a section of more than
+// KRB_JIT_INLINE_OPS operations is cut into chunks of KRB_JIT_CHUNK_OPS, each a __noinline__ device function.  Inside a chunk the
+// scratch cells are local variables (registers); at its boundaries only the cells some chunk reads before it writes them
+// (the live-in set of any chunk of any section: sound across Newton iterations, time steps and pinned cells) travel through
+// the per-thread array s[].
+static const int KRB_JIT_INLINE_OPS = 1200;
+static const int KRB_JIT_CHUNK_OPS = [] { const char *e = getenv("KRB_VM_JIT_CHUNK_OPS"); const int v = e ? atoi(e) : 320; return v > 8 ? v : 320; }();
+struct Chunk { size_t begin, end; std::vector<int> live_in, written; };
+static std::vector<Chunk> make_chunks(const std::vector<DecOp> &ops) {
+    std::vector<Chunk> out;
+    for (size_t b = 0; b < ops.size(); b += KRB_JIT_CHUNK_OPS) {
+        Chunk ch;
+        ch.begin = b; ch.end = std::min(ops.size(), b + (size_t)KRB_JIT_CHUNK_OPS);
+        char wr[KRB_MAX_SLOTS] = {}, in[KRB_MAX_SLOTS] = {};
+        for (size_t i = ch.begin; i < ch.end; i++) {
+            int r[3], n_r, w;
+            op_slots(ops[i], r, n_r, w);
+            for (int k = 0; k < n_r; k++) if (!wr[r[k]]) in[r[k]] = 1;
+            if (w >= 0) wr[w] = 1;
+        }
+        for (int s = 0; s < KRB_MAX_SLOTS; s++) { if (in[s]) ch.live_in.push_back(s); if (wr[s]) ch.written.push_back(s); }
+        out.push_back(ch);
+    }
+    return out;
 }
 
 std::string vm_jit_source(const Plan &plan, size_t vm_params_size, bool host_mode) {
     std::string o;
     o.reserve(64 * 1024);
+    std::vector<DecOp> ops[3];
+    int ns = 0;
+    size_t longest = 0;
+    for (int k = 0; k < 3; k++) { ops[k] = decode(plan.sec[k]); ns = std::max(ns, max_slot(ops[k])); longest = std::max(longest, ops[k].size()); }
+    const bool chunked = longest > (size_t)KRB_JIT_INLINE_OPS;
     if (host_mode) o += "#define KRB_JIT_HOST 1\n#include \"jit_host_shim.h\"\n";
     put(o, "#define KRB_JIT_CPLX %d\n", plan.is_complex ? 1 : 0);
     put(o, "#define KRB_LANE_ZERO_PIVOT %d\n#define KRB_LANE_NOT_CONVERGED %d\n#define KRB_LANE_NONFINITE %d\n#define KRB_LANE_INACCURATE %d\n",
         (int)KRB_LANE_ZERO_PIVOT, (int)KRB_LANE_NOT_CONVERGED, (int)KRB_LANE_NONFINITE, (int)KRB_LANE_INACCURATE);
     put(o, "#define KRB_GROWTH_LIMIT_LOG2 %d\n", (int)KRB_GROWTH_LIMIT_LOG2);
-    int ns = 0;
-    for (int k = 0; k < 3; k++) ns = std::max(ns, max_slot(plan.sec[k]));
     put(o, "#define KRB_JIT_NSLOTS %d\n", ns + 1);
     o += PRELUDE;
     put(o, "static_assert(sizeof(VmParams) == %zu, \"VmParams layout differs from the library's\");\n", vm_params_size);
+    std::vector<Chunk> chunks[3];
+    if (chunked) {
+        char any_in[KRB_MAX_SLOTS] = {};
+        for (int k = 0; k < 3; k++) {
+            chunks[k] = make_chunks(ops[k]);
+            for (const Chunk &ch : chunks[k]) for (int sl : ch.live_in) any_in[sl] = 1;
+        }
+        for (int k = 0; k < 3; k++)
+            for (size_t q = 0; q < chunks[k].size(); q++) {
+                const Chunk &ch = chunks[k][q];
+                put(o, "static __device__ __noinline__ void krb_s%d_c%zu(T *__restrict__ s, const KCtx &c, int &status, bool &notconv, uint32_t &grow) {\n", k, q);
+                char is_in[KRB_MAX_SLOTS] = {};
+                for (int sl : ch.live_in) { is_in[sl] = 1; put(o, "T v%d = s[%d];\n", sl, sl); }
+                for (int sl : ch.written) if (!is_in[sl]) put(o, "T v%d;\n", sl);
+                for (size_t i = ch.begin; i < ch.end; i++) emit_stmt(ops[k][i], "v", "", o);
+                for (int sl : ch.written) if (any_in[sl]) put(o, "s[%d] = v%d;\n", sl, sl);
+                o += "}\n";
+            }
+    }
     o += R"KRBJIT(
 KRB_JIT_ENTRY {
 #ifndef KRB_JIT_HOST
@@ -134,7 +209,7 @@ KRB_JIT_ENTRY {
     c.reltol = p.reltol; c.iabstol = p.iabstol; c.vabstol = p.vabstol; c.nonlinear = p.nonlinear != 0;
     int status = 0, it_used = 0;
     uint32_t grow = 0;
-    T s[KRB_JIT_NSLOTS];   // the interpreter's scratch cells: constant indices only, so they live in registers
+    T s[KRB_JIT_NSLOTS];   // the interpreter's scratch cells: constant indices only (registers), or the hand-over array between chunks
     for (int i = 0; i < KRB_JIT_NSLOTS; i++) s[i] = k_zero();
     for (int row = p.row_begin; row < p.row_end; ++row) {
         T *Xcur = (T *)p.X + (size_t)row * (size_t)p.row_width * L + lane;
@@ -151,13 +226,12 @@ KRB_JIT_ENTRY {
                 c.Xguess = (iter == 0 && !p.guess_empty_at_iter0) ? Xprev : (const double *)Xcur;
                 c.Bs = p.Bstep + ((size_t)row * 2 + (iter > 0 ? 1 : 0)) * (size_t)p.n_wave;
                 bool notconv = false;
-                if (prog == 0) {
 )KRBJIT";
-    emit_section(plan.sec[0], o);
-    o += "                } else if (prog == 1) {\n";
-    emit_section(plan.sec[1], o);
-    o += "                } else {\n";
-    emit_section(plan.sec[2], o);
+    for (int k = 0; k < 3; k++) {
+        put(o, k == 0 ? "                if (prog == 0) {\n" : k == 1 ? "                } else if (prog == 1) {\n" : "                } else {\n");
+        if (chunked) for (size_t q = 0; q < chunks[k].size(); q++) put(o, "krb_s%d_c%zu(s, c, status, notconv, grow);\n", k, q);
+        else for (const DecOp &op : ops[k]) emit_stmt(op, "s[", "]", o);
+    }
     o += R"KRBJIT(                }
                 // ---- NR bookkeeping (op.rs:65-81, dc.rs:99-110, transient.rs:97-109), as vm_kernel.cuh ----
                 if (!solve_pass || !p.nonlinear) break;
@@ -253,8 +327,9 @@ bool vm_jit_compile(const std::string &src, std::string &cubin, std::string &err
     nvrtcProgram prog = nullptr;
     nvrtcResult r = n.create(&prog, src.c_str(), "krb_jit_vm.cu", 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS) { err = std::string("nvrtcCreateProgram: ") + n.errstr(r); return false; }
+    // -lineinfo only for short programs (it triples the cubin and nobody reads the source view of a 10 000-line kernel)
     const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
-    r = n.compile(prog, 3, opts);
+    r = n.compile(prog, src.size() < 400000 ? 3 : 2, opts);
     if (r != NVRTC_SUCCESS) {
         size_t ls = 0;
         n.log_size(prog, &ls);

@@ -16,6 +16,9 @@ int64_t vm_jit_max_ops();
 // KRB_VM_JIT=0 switches the specialised kernels off (A/B measurements, tests of the interpreter)
 bool vm_jit_enabled();
 bool vm_jit_eligible(const Plan &plan);
+// NVRTC needs about half a second per thousand operations: programs above KRB_VM_JIT_SMALL_OPS are specialised only when the plan's
+// first solve has enough points (lanes x rows) to pay for it
+bool vm_jit_worthwhile(const Plan &plan, long long points);
 // CUDA source of the plan's kernel; host_mode: the same text behind KRB_JIT_HOST (tests/jit_host_shim.h) for the CPU tests
 std::string vm_jit_source(const Plan &plan, size_t vm_params_size, bool host_mode);
 // NVRTC only (no device needed): cubin for sm_100a; false + err when NVRTC is missing or rejects the source

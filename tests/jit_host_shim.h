@@ -9,6 +9,7 @@
 
 #define __device__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }

@@ -121,3 +121,35 @@ def test_long_programs_stay_on_the_interpreter():
     assert plan.info.program_ops > 2500
     out, status = plan.solve_dc_sweep(np.linspace(0.0, 1.0, 64))
     assert _active(plan) == 0 and not status.any()
+
+
+def test_mid_size_program_chunked_kernel(oracle):
+    """A 7 x 7 RLC mesh forced onto the lane VM (4.8 k operations: beyond the always-specialise limit, cut into __noinline__ chunks) is
+    specialised once its first solve has >= 32768 points; a small batch of the same plan stays on the interpreter.  Both agree bit for bit."""
+    text = netgen.rlc_mesh(7, 7, transient=True)
+    kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    names = ["Rs", "RL", "Rh3"]
+    varied = [kc.element_index(nm) for nm in names]
+    lanes = 32768
+    vals = np.array([[kc.element_value(e) * netgen.mc_factor(l, j, 3) for l in range(lanes)] for j, e in enumerate(varied)])
+
+    def run(n):
+        plan = kb.Plan(kc, api.MODE_DC, varied=varied, force_lane_vm=True)
+        assert 2500 < plan.info.program_ops <= 20000
+        v = vals[:, :n].copy()
+        plan.solve_op(n, varied_values=v)                    # first solve: upload (+ NVRTC)
+        out, status = plan.solve_op(n, varied_values=v)
+        return out, status, _active(plan), kb.last_kernel_ms()
+
+    out_j, st_j, a, ms_j = _with_jit(True, lambda: run(lanes))
+    out_i, st_i, b, ms_i = _with_jit(False, lambda: run(lanes))
+    out_s, st_s, c, _ = _with_jit(True, lambda: run(64))
+    assert (a, b, c) == (1, 0, 0)
+    assert not st_j.any() and not st_i.any()
+    assert np.array_equal(out_j, out_i) and np.array_equal(out_s, out_i[:64])
+    for l in (0, 12345, lanes - 1):
+        o = oracle.Circuit(text)
+        for j, nm in enumerate(names):
+            o.set_element_value(o.element_index(nm), vals[j, l])
+        assert_close(out_j[l], o.solve_op(), what=f"mesh OP lane {l}")
+    print(f"\n7x7 mesh OP x {lanes} lanes: specialised (chunked) {ms_j:.3f} ms, interpreter {ms_i:.3f} ms (device time of the second solve)")

@@ -141,3 +141,19 @@ def test_jit_host_monte_carlo_transient(oracle, golden):
             oc.set_element_value(oc.element_index(nm), vals[j, l])
         _, ref = oc.solve_tran(h, nsteps * h)
         assert_close(X[:, :, l], ref, what=f"lane {l}")
+
+
+def test_jit_host_chunked_complex_mesh(oracle):
+    """A program beyond the inline limit (1200 operations per section) is cut into __noinline__ chunks that hand live cells over
+    through the per-thread array: a 5 x 6 RLC mesh in AC (complex arithmetic, fill-in, spill planes with 12 scratch cells)."""
+    text = netgen.rlc_mesh(5, 6, transient=False)
+    kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+    freqs = np.array([1.0, 1e3, 1e6, 1e9])
+    plan = kb.Plan(kc, api.MODE_AC, nominal_frequency=1e4, scratch_slots=12, force_lane_vm=True)
+    src = jit_source(plan)
+    assert plan.info.program_ops > 1200 and src.count("__noinline__ void krb_s0_c") >= 4
+    X = JitHost(plan, len(freqs)).run(freqs[None, :])
+    _, ref = oc.solve_ac(freqs)
+    assert_close(X[0].T, ref, what="mesh AC, chunked specialised kernel")
+    nbytes = C.c_int64()
+    assert _lib.lib().krb_plan_jit_compile(plan._h, C.byref(nbytes)) == 0 and nbytes.value > 1000
