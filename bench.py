@@ -34,6 +34,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 LADDER_N = 5000
 LANES_PER_GPU = 65536
 STEP = 2.0 ** -16
+FP64_PEAK_TFLOPS = 37.2   # measured, see roofline.compute.peak_source
 METRIC = "solved sweep points/sec (batched sparse LU)"
 UNIT = "points/s"
 ALL_WORKLOADS = ["ladder_dc", "rc_ac", "dual_rc_tran", "dual_rc_tran_be", "mesh_tran", "mesh_ac", "ladder_mc", "rectifier_tran"]
@@ -437,6 +438,14 @@ def make_workload(name, args, rank):
                      moved_what="the contract bytes themselves: the factor store does not fit on chip, so stamp -> factor -> solve streams it through HBM",
                      traffic_key=None, check=check)
         w.kernel_is_step = True
+        # FP64 work of one step (B200's FP64 pipe, not HBM, is the nearer roof of the supernodal factorisation): the plan compiler's count
+        # of real flops, factor + one pair of triangular solves per plan (AC: the two refinement solves and residuals are not counted)
+        if transient:
+            w.flops_per_step = lanes * (int(pdc.info.flops_per_point) + int(plan.info.flops_per_point) + (nsteps - 1) * 2 * int(plan.info.nnz_lu))
+            w.flops_what = "lanes x (DC-plan factor + solve, transient-plan factor + solve, 2*nnz_lu per further step); krb_plan_info.flops_per_point"
+        else:
+            w.flops_per_step = lanes * int(plan.info.flops_per_point)
+            w.flops_what = "lanes x (complex factor + one solve, 4 real multiply-adds per complex one); krb_plan_info.flops_per_point"
         w.extra["nnz_lu"] = int(plan.info.nnz_lu)
         w.heavy = True
         return w
@@ -523,6 +532,11 @@ def time_workload(w, W, K, ctx):
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, round-2 capture (profiles/traffic.json)" if traffic else None},
         **w.extra,
     }
+    if getattr(w, "flops_per_step", None):
+        tf = w.flops_per_step / t_roof / 1e12
+        res["roofline"]["compute"] = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
+                                      "flops_per_step": int(w.flops_per_step), "flops_model": w.flops_what,
+                                      "peak_source": "tools/microbench/dmma_rate.cu on this pool's B200: DFMA and DMMA.8x8x4 both sustain 64 FMA lanes / clk / SM = 37.2 TFLOP/s at 1965 MHz (profiles/r2_notes.md)"}
     return res, clocks.summary()
 
 

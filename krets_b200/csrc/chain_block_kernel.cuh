@@ -130,13 +130,18 @@ template <> struct BlockSc<true> {
 };
 
 // One GENERIC row: ordered term run, same decoding and summation order as chain_kernel.cuh (bit-identical stamps).
-template <bool CPLX>
+template <bool CPLX, bool KEEP_INV = false>
 __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, int nt, const double *__restrict__ IN, long long L, double w,
                                                  long long prefetch_ahead, typename ChainSc<CPLX>::T &e0, typename ChainSc<CPLX>::T &e1,
                                                  typename ChainSc<CPLX>::T &e2, typename ChainSc<CPLX>::T &e3, typename ChainSc<CPLX>::T &e4) {
     typedef ChainSc<CPLX> S;
     typedef typename S::T V;
     e0 = S::zero(); e1 = S::zero(); e2 = S::zero(); e3 = S::zero(); e4 = S::zero();
+    // KEEP_INV (the pre-stamping kernel of Monte-Carlo plans): a two-terminal element stamps its conductance twice into a node's row
+    // (diagonal, then off-diagonal: consecutive terms of the run, stampable.rs:229-244): the second 1.0 / value is the first one again,
+    // bit for bit, so it is kept instead of redone (half of the IEEE divisions of a ladder row)
+    uint32_t inv_plane = 0xffffffffu;
+    double inv_val = 0.0;
     for (int q = 0; q < nt; ++q) {
         const uint4 cur = __ldg(dp + q);
         const double K = u4hi(cur);
@@ -144,12 +149,13 @@ __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, i
         double re = 0.0, im = 0.0;
         if (kind == CK_CONST) re = K;
         else if (kind == CK_JW_K) im = __dmul_rn(w, K);
+        else if (KEEP_INV && kind == CK_INV_IN && cur.y == inv_plane) re = inv_val;
         else {
             const double *src = IN + (size_t)cur.y * L;
             const double v = __ldg(src);
             if (prefetch_ahead > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + prefetch_ahead));
             if (kind == CK_IN) re = v;
-            else if (kind == CK_INV_IN) re = __ddiv_rn(1.0, v);
+            else if (kind == CK_INV_IN) { re = __ddiv_rn(1.0, v); if (KEEP_INV) { inv_plane = cur.y; inv_val = re; } }
             else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
             else im = __dmul_rn(w, v);
         }
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(256) krb_block_stamp_rows(const BlockStampPara
                 e0 = S::make(u4lo(c0), 0.0); e1 = S::make(u4hi(c0), 0.0); e2 = S::make(u4lo(c1), 0.0); e4 = S::make(u4hi(c1), 0.0);
             }
         } else {
-            block_eval_terms<CPLX>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), IN, p.L, w, 0, e0, e1, e2, e3, e4);
+            block_eval_terms<CPLX, true>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), IN, p.L, w, 0, e0, e1, e2, e3, e4);
             if ((rw.y & BR_HAS_U2) && live) reinterpret_cast<V *>(p.U2)[(size_t)lane * p.T + slot % p.T] = e3;
         }
         tile[r * 4 + 0][lx] = e0; tile[r * 4 + 1][lx] = e1; tile[r * 4 + 2][lx] = e2; tile[r * 4 + 3][lx] = e4;
