@@ -142,8 +142,12 @@ __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, i
     // bit for bit, so it is kept instead of redone (half of the IEEE divisions of a ladder row)
     uint32_t inv_plane = 0xffffffffu;
     double inv_val = 0.0;
+    uint4 ahead = make_uint4(0u, 0u, 0u, 0u);
+    if (KEEP_INV && nt > 0) ahead = __ldg(dp);      // KEEP_INV: term q + 1 is fetched while term q is evaluated (the stream ends with 4 zero units)
     for (int q = 0; q < nt; ++q) {
-        const uint4 cur = __ldg(dp + q);
+        uint4 cur;
+        if (KEEP_INV) { cur = ahead; ahead = __ldg(dp + q + 1); }
+        else cur = __ldg(dp + q);
         const double K = u4hi(cur);
         const uint32_t kind = (cur.x >> 4) & 0xfu;
         double re = 0.0, im = 0.0;
@@ -155,12 +159,24 @@ __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, i
             const double v = __ldg(src);
             if (prefetch_ahead > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + prefetch_ahead));
             if (kind == CK_IN) re = v;
-            else if (kind == CK_INV_IN) { re = __ddiv_rn(1.0, v); if (KEEP_INV) { inv_plane = cur.y; inv_val = re; } }
+            else if (kind == CK_INV_IN) {
+                // 1.0 / value (stampable.rs:232): __drcp_rn is the same correctly rounded quotient as __ddiv_rn(1.0, v) in half the instructions
+                if (KEEP_INV) { re = __drcp_rn(v); inv_plane = cur.y; inv_val = re; }
+                else re = __ddiv_rn(1.0, v);
+            }
             else if (kind == CK_IN_OVER_K) re = __ddiv_rn(v, K);
             else im = __dmul_rn(w, v);
         }
         if (cur.x & CT_NEG) { re = -re; im = -im; }
         const uint32_t tgt = cur.x & 7u;
+        if (KEEP_INV) {   // the pre-stamping kernel: a warp = 32 lanes of ONE row, so the target is warp-uniform and this branches without diverging
+            if (tgt == CT_SUB) S::add(e0, re, im);
+            else if (tgt == CT_DIAG) S::add(e1, re, im);
+            else if (tgt == CT_SUP1) S::add(e2, re, im);
+            else if (tgt == CT_SUP2) S::add(e3, re, im);
+            else S::add(e4, re, im);
+            continue;
+        }
         // the target differs from thread to thread: select the accumulator, add once, select back
         V acc = tgt == CT_SUB ? e0 : tgt == CT_DIAG ? e1 : tgt == CT_SUP1 ? e2 : tgt == CT_SUP2 ? e3 : e4;
         S::add(acc, re, im);
