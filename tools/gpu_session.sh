@@ -26,7 +26,9 @@ try:
     for o in d.get('other_configs', []):
         if 'error' in o: print('  ', o['name'], 'ERROR', o['error']); continue
         if 'roofline' not in o: print('   %-16s %s' % (o['name'], {k: v for k, v in o.items() if k not in ('workload', 'name')})); continue
-        print('   %-16s ms/step %10.3f  value %.4g  frac %.3f  status %d  parity %s' % (o['name'], o['ms_per_step'], o['value'], o['roofline']['frac'], o['lanes_with_status'], o.get('parity_spot_check')))
+        comp = o['roofline'].get('compute')
+        print('   %-16s ms/step %10.3f  value %.4g  frac %.3f%s  status %d  parity %s' % (o['name'], o['ms_per_step'], o['value'], o['roofline']['frac'],
+              ('  fp64 %.3f' % comp['frac']) if comp else '', o['lanes_with_status'], o.get('parity_spot_check')))
 except Exception as e:
     print('bench parse error', e); print(open(f'gpurun_out/{tag}_bench.err').read()[-1500:])
 PY
