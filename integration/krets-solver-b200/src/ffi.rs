@@ -25,6 +25,7 @@ pub const KRB_WAVE_NONE: i32 = 0;
 pub const KRB_WAVE_PULSE: i32 = 1;
 pub const KRB_WAVE_SIN: i32 = 2;
 pub const KRB_ELEM_FLAG_G2: i32 = 1;
+pub const KRB_ELEM_FLAG_LEVEL1: i32 = 2; // extension: NMOS stamps the level-1 companion model (krets_b200.h)
 
 pub const KRB_MODE_DC: i32 = 0;
 pub const KRB_MODE_AC: i32 = 1;

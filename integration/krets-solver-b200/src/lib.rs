@@ -139,10 +139,20 @@ impl Solver {
                     pod.is = d.model.saturation_current;
                     pod.n = d.model.emission_coefficient;
                 }
-                Element::NMOSFET(_) => {
+                Element::NMOSFET(m) => {
                     // drain / gate in ip / im; the reference's index lookups never match (stampable.rs:842-844),
                     // so the element stamps nothing in DC/transient and is rejected in AC, as upstream's todo!()
                     pod.kind = KRB_NMOS;
+                    // source node and level-1 parameters travel with the element either way; only the feature
+                    // `nmos-level1` (a krets build whose NMOS stamp is fixed) sets KRB_ELEM_FLAG_LEVEL1, which makes
+                    // the backend stamp the companion model of nmosfet.rs:51-102 (krets_b200.h)
+                    pod.ic = self.idx(format!("V({})", m.source));
+                    pod.wave[0] = m.threshold_voltage();
+                    pod.wave[1] = m.beta();
+                    pod.wave[2] = m.lambda();
+                    if cfg!(feature = "nmos-level1") {
+                        pod.flags |= KRB_ELEM_FLAG_LEVEL1;
+                    }
                 }
                 Element::BJT(_) => return Err(Error::Unexpected("BJT stamps are todo!() upstream (stampable.rs:327)".into())),
                 Element::SubcktInstance(_) => return Err(Error::Unexpected("subcircuits are flattened by the parser (parser.rs:93-98)".into())),
