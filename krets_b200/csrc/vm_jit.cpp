@@ -5,6 +5,7 @@
 
 #include <cuda.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nvrtc.h>
 
 #include <algorithm>
@@ -355,15 +356,57 @@ struct JitKernel {
     CUfunction fn = nullptr;
 };
 
+// ---- on-disk cubin cache ---------------------------------------------------------------------------------------------------
+// KRB_VM_JIT_CACHE=<directory>: compiled kernels are kept there as <fnv1a64(source + NVRTC version)>.cubin, so that a later process
+// (the next sweep of the same circuit) skips NVRTC.  Off unless the variable is set: the library never writes outside /tmp or the
+// caller's directories on its own.
+static std::string cache_path(const std::string &src) {
+    const char *dir = getenv("KRB_VM_JIT_CACHE");
+    if (!dir || !dir[0]) return std::string();
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
+    for (const char *v = "nvrtc-12/sm_100a/v1"; *v; ++v) { h ^= (unsigned char)*v; h *= 1099511628211ull; }
+    char name[40];
+    snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)h);
+    return std::string(dir) + name;
+}
+static bool cache_read(const std::string &path, std::string &cubin) {
+    if (path.empty()) return false;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char buf[65536];
+    size_t k;
+    cubin.clear();
+    while ((k = fread(buf, 1, sizeof buf, f)) > 0) cubin.append(buf, k);
+    fclose(f);
+    return cubin.size() > 64;
+}
+static void cache_write(const std::string &path, const std::string &cubin) {
+    if (path.empty()) return;
+    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    fclose(f);
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());   // atomic publish: concurrent ranks write the same bytes
+}
+
 JitKernel *vm_jit_build(const Plan &plan, size_t vm_params_size, std::string &err) {
     Driver &d = driver();
     if (!d.ok) { err = "CUDA driver API unavailable: " + d.why; return nullptr; }
-    std::string cubin;
-    if (!vm_jit_compile(vm_jit_source(plan, vm_params_size, false), cubin, err)) return nullptr;
     CUcontext ctx = nullptr;
     if (d.ctx_current(&ctx) != CUDA_SUCCESS || !ctx) { err = "no current CUDA context"; return nullptr; }
+    const std::string src = vm_jit_source(plan, vm_params_size, false);
+    const std::string path = cache_path(src);
+    std::string cubin;
     JitKernel *k = new JitKernel();
-    CUresult r = d.load(&k->mod, cubin.data());
+    CUresult r = CUDA_ERROR_UNKNOWN;
+    if (cache_read(path, cubin)) r = d.load(&k->mod, cubin.data());          // a stale or truncated file just falls through to NVRTC
+    if (r != CUDA_SUCCESS) {
+        if (!vm_jit_compile(src, cubin, err)) { delete k; return nullptr; }
+        r = d.load(&k->mod, cubin.data());
+        if (r == CUDA_SUCCESS) cache_write(path, cubin);
+    }
     if (r != CUDA_SUCCESS) { err = "cuModuleLoadData: " + cu_err(d, r); delete k; return nullptr; }
     r = d.get_fn(&k->fn, k->mod, "krb_jit_vm");
     if (r != CUDA_SUCCESS) { err = "cuModuleGetFunction: " + cu_err(d, r); d.unload(k->mod); delete k; return nullptr; }

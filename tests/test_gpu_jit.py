@@ -153,3 +153,28 @@ def test_mid_size_program_chunked_kernel(oracle):
             o.set_element_value(o.element_index(nm), vals[j, l])
         assert_close(out_j[l], o.solve_op(), what=f"mesh OP lane {l}")
     print(f"\n7x7 mesh OP x {lanes} lanes: specialised (chunked) {ms_j:.3f} ms, interpreter {ms_i:.3f} ms (device time of the second solve)")
+
+
+def test_cubin_cache_directory(golden, tmp_path, monkeypatch):
+    """KRB_VM_JIT_CACHE: the compiled kernel is published there once; a second plan of the same program loads it instead of calling NVRTC
+    (same results), and a corrupt file falls back to NVRTC."""
+    import time
+    monkeypatch.setenv("KRB_VM_JIT_CACHE", str(tmp_path))
+    monkeypatch.setenv("KRB_VM_JIT", "1")
+    kc = kcirc(golden, "diode_iv_curve")
+
+    def run():
+        t0 = time.time()
+        plan = kb.Plan(kc, api.MODE_DC)
+        out, status = plan.solve_op()
+        return out, _active(plan), time.time() - t0
+
+    out1, a1, t1 = run()
+    files = sorted(tmp_path.glob("*.cubin"))
+    assert a1 == 1 and len(files) == 1 and files[0].stat().st_size > 1000
+    out2, a2, t2 = run()
+    assert a2 == 1 and np.array_equal(out1, out2) and len(list(tmp_path.glob("*"))) == 1
+    files[0].write_bytes(b"not a cubin" * 20)
+    out3, a3, _ = run()
+    assert a3 == 1 and np.array_equal(out1, out3) and files[0].stat().st_size > 1000      # recompiled and republished
+    print(f"\nfirst solve {t1 * 1e3:.0f} ms (NVRTC), from the cache {t2 * 1e3:.0f} ms")
