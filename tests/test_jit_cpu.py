@@ -157,3 +157,28 @@ def test_jit_host_chunked_complex_mesh(oracle):
     assert_close(X[0].T, ref, what="mesh AC, chunked specialised kernel")
     nbytes = C.c_int64()
     assert _lib.lib().krb_plan_jit_compile(plan._h, C.byref(nbytes)) == 0 and nbytes.value > 1000
+
+
+def test_vmparams_text_matches_the_interpreter_struct():
+    """The specialised kernels take krb::VmParams by value through a struct re-declared in vm_jit_prelude.inc (NVRTC sees no project
+    headers; the generated text static_asserts the size).  Field order and kinds must match vm_kernel.cuh declaration by declaration."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "krets_b200", "csrc")
+
+    def fields(path):
+        text = open(os.path.join(root, path)).read()
+        body = re.search(r"struct VmParams \{(.*?)\n\};", text, re.S).group(1)
+        out = []
+        for decl in re.sub(r"//[^\n]*", "", body).split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            base = "ptr" if "*" in decl.split(",")[0] else ("ll" if "long long" in decl else "double" if decl.startswith("double") else "int")
+            for nm in decl.split(","):
+                kind = "ptr" if "*" in nm or (base == "ptr" and nm is decl.split(",")[0]) else base
+                out.append((re.findall(r"[A-Za-z_][A-Za-z_0-9]*", nm)[-1], kind))
+        return out
+
+    a, b = fields("vm_kernel.cuh"), fields("vm_jit_prelude.inc")
+    assert a == b and len(a) == 25, (a, b)
