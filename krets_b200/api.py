@@ -419,6 +419,21 @@ class Plan:
             _check_krb(_lib.lib().krb_plan_get_program(self._h, section, ops.ctypes.data_as(C.POINTER(C.c_uint32))))
         return ops
 
+    def jit_source(self, host_mode: bool = False) -> str | None:
+        """CUDA text of the plan's circuit-specialised lane kernel (krb_plan_jit_source), None when the plan is not eligible."""
+        L = _lib.lib()
+        need = int(L.krb_plan_jit_source(self._h, 1 if host_mode else 0, None, 0))
+        if need <= 0:
+            return None
+        buf = C.create_string_buffer(need)
+        L.krb_plan_jit_source(self._h, 1 if host_mode else 0, buf, need)
+        return buf.value.decode()
+
+    @property
+    def specialised(self) -> bool:
+        """True once the plan's lane program runs as an NVRTC-compiled kernel on this device (decided at its first solve)."""
+        return int(_lib.lib().krb_plan_jit_active(self._h)) == 1
+
     # -- solves --
     def _io(self, arrays, layout, select=None):
         io = KrbIO()

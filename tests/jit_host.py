@@ -28,15 +28,7 @@ class VmParams(C.Structure):   # krb::VmParams (vm_kernel.cuh) == the struct in 
 
 
 def jit_source(plan, host_mode=False):
-    L = _lib.lib()
-    L.krb_plan_jit_source.restype = C.c_int64
-    L.krb_plan_jit_source.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int64]
-    need = int(L.krb_plan_jit_source(plan._h, 1 if host_mode else 0, None, 0))
-    if need <= 0:
-        return None
-    buf = C.create_string_buffer(need)
-    L.krb_plan_jit_source(plan._h, 1 if host_mode else 0, buf, need)
-    return buf.value.decode()
+    return plan.jit_source(host_mode)
 
 
 class JitHost:
