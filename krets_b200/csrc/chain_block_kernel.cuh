@@ -130,10 +130,13 @@ template <> struct BlockSc<true> {
 };
 
 // One GENERIC row: ordered term run, same decoding and summation order as chain_kernel.cuh (bit-identical stamps).
+// INV / inv_base / inv_n (KEEP_INV callers only): input planes [inv_base, inv_base + inv_n) are read from INV (lane stride inv_L) instead
+// of IN — the caller's own Monte-Carlo array when it already has the kernels' layout, so that it is never copied into the plan's buffer.
 template <bool CPLX, bool KEEP_INV = false>
 __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, int nt, const double *__restrict__ IN, long long L, double w,
                                                  long long prefetch_ahead, typename ChainSc<CPLX>::T &e0, typename ChainSc<CPLX>::T &e1,
-                                                 typename ChainSc<CPLX>::T &e2, typename ChainSc<CPLX>::T &e3, typename ChainSc<CPLX>::T &e4) {
+                                                 typename ChainSc<CPLX>::T &e2, typename ChainSc<CPLX>::T &e3, typename ChainSc<CPLX>::T &e4,
+                                                 const double *__restrict__ INV = nullptr, uint32_t inv_base = 0, uint32_t inv_n = 0, long long inv_L = 0) {
     typedef ChainSc<CPLX> S;
     typedef typename S::T V;
     e0 = S::zero(); e1 = S::zero(); e2 = S::zero(); e3 = S::zero(); e4 = S::zero();
@@ -156,6 +159,7 @@ __device__ __forceinline__ void block_eval_terms(const uint4 *__restrict__ dp, i
         else if (KEEP_INV && kind == CK_INV_IN && cur.y == inv_plane) re = inv_val;
         else {
             const double *src = IN + (size_t)cur.y * L;
+            if (KEEP_INV && cur.y - inv_base < inv_n) src = INV + (size_t)(cur.y - inv_base) * inv_L;
             const double v = __ldg(src);
             if (prefetch_ahead > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + prefetch_ahead));
             if (kind == CK_IN) re = v;
@@ -213,6 +217,9 @@ struct BlockStampParams {
     int input_freq, slots;       // slots = T * M
     int T;
     void *E, *U2;
+    const double *INV;           // planes [inv_base, inv_base + inv_n) come from here (lane stride inv_L); inv_n = 0: everything from IN
+    unsigned inv_base, inv_n;
+    long long inv_L;
 };
 
 // (a) of the north star for Monte-Carlo chain plans: one thread stamps one pivot row of one lane — ordered term run, exact IEEE
@@ -230,6 +237,7 @@ __global__ void __launch_bounds__(256) krb_block_stamp_rows(const BlockStampPara
     const long long lane0 = (long long)blockIdx.y * 32, lane = lane0 + lx;
     const bool live = lane < p.lanes;
     const double *__restrict__ IN = p.IN + (live ? lane : 0);
+    const double *__restrict__ INV = p.INV + (live ? lane : 0);
     double w = 0.0;
     if (CPLX && p.input_freq >= 0) w = __dmul_rn(2.0 * 3.14159265358979323846264338327950288, __ldg(IN + (size_t)p.input_freq * p.L));
     const int slot0 = blockIdx.x * RT;
@@ -250,7 +258,8 @@ __global__ void __launch_bounds__(256) krb_block_stamp_rows(const BlockStampPara
                 e0 = S::make(u4lo(c0), 0.0); e1 = S::make(u4hi(c0), 0.0); e2 = S::make(u4lo(c1), 0.0); e4 = S::make(u4hi(c1), 0.0);
             }
         } else {
-            block_eval_terms<CPLX, true>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), IN, p.L, w, 0, e0, e1, e2, e3, e4);
+            block_eval_terms<CPLX, true>(p.stream + (rw.x >> 1), (int)((rw.y >> BR_NT_SHIFT) & BR_NT_MASK), IN, p.L, w, 0, e0, e1, e2, e3, e4,
+                                         INV, p.inv_base, p.inv_n, p.inv_L);
             if ((rw.y & BR_HAS_U2) && live) reinterpret_cast<V *>(p.U2)[(size_t)lane * p.T + slot % p.T] = e3;
         }
         tile[r * 4 + 0][lx] = e0; tile[r * 4 + 1][lx] = e1; tile[r * 4 + 2][lx] = e2; tile[r * 4 + 3][lx] = e4;

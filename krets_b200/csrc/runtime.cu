@@ -504,6 +504,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
         const long long Lpad = ((lanes + tpb - 1) / tpb) * tpb;
         const int b = out_dev ? 0 : (chunk_idx & 1);
         double *IN = (double *)D0.IN.p;
+        bool mc_in_place = false;
         int *status_d = (int *)D0.status.p + (size_t)b * chunk;
         int *iters_d = a.iterations ? (int *)D0.iters.p + (size_t)b * chunk : nullptr;
         if (!out_dev && chunk_idx >= 2) CUDA_TRY(cudaStreamWaitEvent(st, D0.copy_done[b], 0));   // buffer set b is free again
@@ -517,7 +518,10 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             bool run = nv > 1 && a.varied_values != nullptr;
             for (int q = 1; q < nv && run; q++) run = P0.input_of_varied[q] == P0.input_of_varied[0] + q;
             for (int q = 0; q < nv && run; q++) run = P0.input_of_varied[q] != P0.input_sweep && P0.input_of_varied[q] != P0.input_freq;
-            if (run)
+            // device-resident Monte-Carlo values that already have the kernels' layout ([plane][lane], one chunk, no lane padding) are read in
+            // place by the pre-stamping kernel of the block chain executor — its only reader — instead of being copied into the plan's buffer
+            mc_in_place = run && block_stamped && out_dev && lane0 == 0 && lanes == a.lanes && Lpad == lanes;
+            if (run && !mc_in_place)
                 CUDA_TRY(cudaMemcpy2DAsync(IN + (size_t)P0.input_of_varied[0] * Lpad, (size_t)Lpad * 8, a.varied_values + lane0, (size_t)a.lanes * 8,
                                            (size_t)lanes * 8, (size_t)nv, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
             for (int k = 0; k < P0.n_inputs; k++) {
@@ -582,6 +586,8 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
                 sp.rows = D0.block_rows; sp.dict = D0.block_dict; sp.stream = D0.chain_stream; sp.IN = IN; sp.L = Lpad; sp.lanes = lanes;
                 sp.input_freq = P0.input_freq; sp.slots = T * M; sp.T = T;
                 sp.E = D0.G.p; sp.U2 = (char *)D0.G.p + (size_t)chunk * (size_t)T * M * 4 * ts;
+                sp.INV = IN; sp.inv_base = 0; sp.inv_n = 0; sp.inv_L = Lpad;
+                if (mc_in_place) { sp.INV = a.varied_values; sp.inv_base = (unsigned)P0.input_of_varied[0]; sp.inv_n = (unsigned)P0.input_of_varied.size(); sp.inv_L = a.lanes; }
                 const dim3 grid((unsigned)(T * M / (cplx ? 16 : 32)), (unsigned)((lanes + 31) / 32)), blk(32, 8);
                 if (cplx) krb_block_stamp_rows<true><<<grid, blk, 0, st>>>(sp);
                 else krb_block_stamp_rows<false><<<grid, blk, 0, st>>>(sp);

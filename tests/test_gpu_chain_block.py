@@ -202,3 +202,38 @@ def test_block_prestamped_rows_monte_carlo(oracle, cplx):
             oc.set_element_value(e, vals[k, l])
         ref = oc.solve_ac([freqs[l]])[1][0] if cplx else oc.solve_op()
         assert_close(a[l], ref, what=f"pre-stamped block kernel lane {l}")
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_block_prestamped_rows_read_device_values_in_place(oracle, cplx):
+    """Device-resident Monte-Carlo values that already have the kernels' layout (one chunk, lane count a multiple of the block size) are
+    read in place by krb_block_stamp_rows instead of being copied into the plan's input planes: same bits as the copying path (host
+    arrays), and the caller's array is left untouched."""
+    import torch
+    nodes = 600
+    text = netgen.rc_ladder(nodes) if cplx else netgen.resistor_ladder(nodes)
+    circuit = kb.parse_circuit_description(text)
+    varied = [e for e in range(circuit.num_elements) if circuit.element(e).kind in (api.KIND_R, api.KIND_C)]
+    lanes = 1344                                   # 21 x 64: no lane padding
+    rng = np.random.default_rng(5)
+    vals = np.array([[circuit.element_value(e) * (0.95 + 0.1 * rng.random()) for _ in range(lanes)] for e in varied])
+    plan = kb.Plan(circuit, api.MODE_AC if cplx else api.MODE_DC, varied=varied, nominal_frequency=1e4)
+    assert plan.info.executor == 1 and chain_block_info(plan)[0]
+    v_dev = torch.from_numpy(vals).cuda()
+    freqs = np.logspace(1, 7, lanes)
+    if cplx:
+        dev = plan.solve_ac(torch.from_numpy(freqs).cuda(), varied_values=v_dev)
+        host = plan.solve_ac(freqs, varied_values=vals)
+    else:
+        dev = plan.solve_op(lanes, varied_values=v_dev)
+        host = plan.solve_op(lanes, varied_values=vals)
+    torch.cuda.synchronize()
+    assert int(dev[1].abs().max().item()) == 0 and not host[1].any()
+    assert np.array_equal(dev[0].cpu().numpy(), host[0])
+    assert np.array_equal(v_dev.cpu().numpy(), vals)
+    for l in (0, 777, lanes - 1):
+        oc = oracle.Circuit(text)
+        for k, e in enumerate(varied):
+            oc.set_element_value(e, vals[k, l])
+        ref = oc.solve_ac([freqs[l]])[1][0] if cplx else oc.solve_op()
+        assert_close(host[0][l], ref, what=f"lane {l}")
