@@ -226,8 +226,14 @@ struct BlockStampParams {
 // divisions, same summation order as sum_triplets (solver.rs:59-70) — from the lane-interleaved inputs (a warp = 32 consecutive
 // lanes of one row: coalesced), and the tile is transposed through shared memory so that every lane receives 32 consecutive
 // records (1 / 2 KB) at once.  blockDim = (32, 8); grid = (slots / 32, ceil(lanes / 32)).
+// resident CTAs per SM the register allocation must allow.  Measured on ladder_mc (r6b, one gpurun call): 5 CTAs (48 registers, 28 bytes
+// of spills) 4.34 ms per step, 6 CTAs (40 registers, 60 bytes) 4.75 ms, no bound (the allocator takes what it likes) 4.99 ms; the
+// complex instantiation keeps its natural 80 registers (3 CTAs)
+#ifndef KRB_STAMP_MIN_BLOCKS
+#define KRB_STAMP_MIN_BLOCKS (CPLX ? 3 : 5)
+#endif
 template <bool CPLX>
-__global__ void __launch_bounds__(256) krb_block_stamp_rows(const BlockStampParams p) {
+__global__ void __launch_bounds__(256, KRB_STAMP_MIN_BLOCKS) krb_block_stamp_rows(const BlockStampParams p) {
     typedef ChainSc<CPLX> S;
     typedef typename S::T V;
     constexpr int FIX_UNITS = CPLX ? 4 : 2;

@@ -8,5 +8,5 @@ cd "$(dirname "$0")/../krets_b200/csrc"
 mkdir -p ../variants build/var_$name
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -ccbin g++ -Xcompiler -fPIC "$@" -c runtime.cu -o build/var_$name/runtime.o
 objs=$(ls build/*.o build/host/*.o | grep -v "build/runtime.o")
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libkrets_b200_$name.so $objs build/var_$name/runtime.o -cudart static
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libkrets_b200_$name.so $objs build/var_$name/runtime.o -cudart static -ldl
 echo built ../variants/libkrets_b200_$name.so
