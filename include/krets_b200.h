@@ -214,10 +214,22 @@ typedef struct krb_overrides {
 int32_t krb_solve_op(krb_plan *plan_dc, const krb_config *cfg, int64_t lanes, const krb_overrides *ov, double *x_out,
                      int32_t *iterations, int32_t *lane_status, const krb_io *io);
 
-/* dc.rs:14-124: lane l solves with the plan's sweep element set to sweep_values[l] (= start + l*step on the host).
- * Nonlinear circuits start every lane from the empty guess (documented deviation from dc.rs:58 warm start). */
+/* dc.rs:14-124 with the sweep points as parallel lanes: lane l solves with the plan's sweep element set to sweep_values[l]
+ * (= start + l*step on the host).  Every lane starts Newton-Raphson from the empty guess, so for NONLINEAR circuits this is not the
+ * reference's iteration history (dc.rs:58 warm start) — use krb_solve_dc_sweep_sequential for that; for linear circuits the two agree. */
 int32_t krb_solve_dc_sweep(krb_plan *plan_dc, const krb_config *cfg, const double *sweep_values, int64_t lanes,
                            const krb_overrides *ov, double *x_out, int32_t *lane_status, const krb_io *io);
+
+/* dc.rs:47-113 as written, for nonlinear circuits: the n_points sweep points are the result ROWS of a lane and are solved in order, the
+ * sweep element at start + r*step_size (dc.rs:48); row 0 starts Newton-Raphson from the empty map (dc.rs:41), row r from row r-1's
+ * solution (dc.rs:58,112), and the "step" key of the result map (dc.rs:97) takes part in the convergence check (solver.rs:86-103).
+ * The parallel dimension is the Monte-Carlo lane (lanes == 1 and ov == NULL is the reference call).
+ * x_out: lanes*n_points*n doubles, x[lane][row][unknown] (krb_io.layout POINT_MAJOR) — the layout of krb_solve_transient.
+ * iterations (optional, [lanes]): NR iterations of the last row.  Plans that do not run on the lane VM (linear chain / front plans,
+ * where the warm start cannot matter) return KRB_ERR_UNSUPPORTED. */
+int32_t krb_solve_dc_sweep_sequential(krb_plan *plan_dc, const krb_config *cfg, double start, double step_size, int64_t n_points,
+                                      int64_t lanes, const krb_overrides *ov, double *x_out, int32_t *iterations, int32_t *lane_status,
+                                      const krb_io *io);
 
 /* ac.rs:39-105: lane l solves at frequencies[l] (> 0; the host drops f <= 0 as ac.rs:40-45).
  * op_solution: [n] (lanes_op == 1) or [lanes][n] point-major DC operating point, needed only for nonlinear

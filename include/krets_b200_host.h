@@ -59,7 +59,13 @@ int32_t krh_transient_num_steps(double time_step, double stop_time);         /* 
 int32_t krh_solver_new(const krh_circuit *c, const krb_config *cfg, krh_solver **out);
 void krh_solver_free(krh_solver *s);
 int32_t krh_solver_solve_op(krh_solver *s, krh_result **out);                                        /* Analysis::Op */
+/* Analysis::Dc, dc.rs:14-124.  Linear circuits: the sweep points are parallel lanes.  Nonlinear circuits: the points are solved in order,
+ * Newton-Raphson warm-started from the previous point exactly as dc.rs:58,112 (krb_solve_dc_sweep_sequential). */
 int32_t krh_solver_solve_dc(krh_solver *s, const char *element, double start, double stop, double step_size, krh_result **out);
+/* extension (not in the reference): KRH_DC_PARALLEL_COLD_START solves the points of a NONLINEAR sweep as parallel lanes, each from the
+ * empty guess — the fast path when the sweep is long; results agree with the reference's within the Newton-Raphson tolerances, not to 1e-9 */
+enum { KRH_DC_REFERENCE = 0, KRH_DC_PARALLEL_COLD_START = 1 };
+int32_t krh_solver_solve_dc_with(krh_solver *s, const char *element, double start, double stop, double step_size, int32_t mode, krh_result **out);
 int32_t krh_solver_solve_ac(krh_solver *s, int32_t sweep_kind, uint32_t points, double fstart, double fstop, krh_result **out);
 int32_t krh_solver_solve_transient(krh_solver *s, double time_step, double stop_time, krh_result **out);
 /* extension (not in the reference): same driver with KRB_INTEGRATOR_TRAP / KRB_INTEGRATOR_BE instead of the reference's lagged backward Euler */

@@ -136,6 +136,19 @@ unsafe extern "C" {
         lane_status: *mut i32,
         io: *const krb_io,
     ) -> i32;
+    pub fn krb_solve_dc_sweep_sequential(
+        plan_dc: *mut krb_plan,
+        cfg: *const krb_config,
+        start: f64,
+        step_size: f64,
+        n_points: i64,
+        lanes: i64,
+        ov: *const krb_overrides,
+        x_out: *mut f64,
+        iterations: *mut i32,
+        lane_status: *mut i32,
+        io: *const krb_io,
+    ) -> i32;
     pub fn krb_solve_ac(
         plan_ac: *mut krb_plan,
         cfg: *const krb_config,

@@ -240,6 +240,32 @@ impl Solver {
                 let values: Vec<f64> = (0..num_steps).map(|i| start + (i as f64 * step_size)).collect(); // dc.rs:48
                 let plan = self.analyze(&kc, KRB_MODE_DC, |o| o.sweep_element = sweep as i32)?; // V / I check: dc.rs:31-39
                 let mut x = vec![0.0f64; num_steps * n];
+                if self.circuit.elements.iter().any(|e| e.is_nonlinear()) {
+                    // dc.rs:58,112: Newton-Raphson at every point starts from the previous point's solution, so the points are
+                    // sequential: one lane whose result rows are the sweep points (x[0][row][unknown] is already the result layout)
+                    let mut st1 = [0i32; 1];
+                    check(
+                        unsafe {
+                            krb_solve_dc_sweep_sequential(
+                                plan.0,
+                                &cfg,
+                                start,
+                                step_size,
+                                num_steps as i64,
+                                1,
+                                null(),
+                                x.as_mut_ptr(),
+                                null_mut(),
+                                st1.as_mut_ptr(),
+                                null(),
+                            )
+                        },
+                        max_iter,
+                    )?;
+                    first_failed_lane(&st1, max_iter)?;
+                    return Ok(AnalysisResult::Dc(self.rows_f64(&x, n, Some("step"), |r| r as f64))); // dc.rs:92-97
+                }
+                // linear circuit: one solve per point, nothing carried between points — the points are parallel lanes
                 let mut st = vec![0i32; num_steps];
                 check(
                     unsafe { krb_solve_dc_sweep(plan.0, &cfg, values.as_ptr(), num_steps as i64, null(), x.as_mut_ptr(), st.as_mut_ptr(), null()) },

@@ -68,6 +68,7 @@ SYMBOLS = {
     "krb_plan_jit_compile": (_i32, [_vp, C.POINTER(_i64)]),
     "krb_solve_op": (_i32, [_vp, C.POINTER(KrbConfig), _i64, C.POINTER(KrbOverrides), _vp, _vp, _vp, C.POINTER(KrbIO)]),
     "krb_solve_dc_sweep": (_i32, [_vp, C.POINTER(KrbConfig), _vp, _i64, C.POINTER(KrbOverrides), _vp, _vp, C.POINTER(KrbIO)]),
+    "krb_solve_dc_sweep_sequential": (_i32, [_vp, C.POINTER(KrbConfig), _f64, _f64, _i64, _i64, C.POINTER(KrbOverrides), _vp, _vp, _vp, C.POINTER(KrbIO)]),
     "krb_solve_ac": (_i32, [_vp, C.POINTER(KrbConfig), _vp, _i64, C.POINTER(KrbOverrides), _vp, _i64, _vp, _vp, C.POINTER(KrbIO)]),
     "krb_solve_transient": (_i32, [_vp, _vp, C.POINTER(KrbConfig), _i64, _i64, C.POINTER(KrbOverrides), _vp, _vp, C.POINTER(KrbIO)]),
     "krb_last_error_string": (C.c_char_p, []),
@@ -94,6 +95,7 @@ SYMBOLS = {
     "krh_solver_free": (None, [_vp]),
     "krh_solver_solve_op": (_i32, [_vp, C.POINTER(_vp)]),
     "krh_solver_solve_dc": (_i32, [_vp, C.c_char_p, _f64, _f64, _f64, C.POINTER(_vp)]),
+    "krh_solver_solve_dc_with": (_i32, [_vp, C.c_char_p, _f64, _f64, _f64, _i32, C.POINTER(_vp)]),
     "krh_solver_solve_ac": (_i32, [_vp, _i32, C.c_uint32, _f64, _f64, C.POINTER(_vp)]),
     "krh_solver_solve_transient": (_i32, [_vp, _f64, _f64, C.POINTER(_vp)]),
     "krh_solver_solve_transient_with": (_i32, [_vp, _f64, _f64, _i32, C.POINTER(_vp)]),

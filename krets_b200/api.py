@@ -84,6 +84,7 @@ class DcAnalysis:            # analyses.rs:44-54
     start: float
     stop: float
     step_size: float
+    mode: int = 0            # extension: 0 = the reference (nonlinear sweeps sequential, warm-started dc.rs:58), 1 = nonlinear points as parallel cold-start lanes
 
 
 @dataclass
@@ -115,6 +116,7 @@ class AcAnalysis:            # analyses.rs:68-76
 
 
 INTEGRATOR_BE_KRETS, INTEGRATOR_TRAP, INTEGRATOR_BE = 0, 1, 2
+DC_REFERENCE, DC_PARALLEL_COLD_START = 0, 1        # DcAnalysis.mode (krets_b200_host.h KRH_DC_*)
 
 
 @dataclass
@@ -270,7 +272,7 @@ class Solver:
         if analysis.kind == "op":
             _check_krh(L.krh_solver_solve_op(self._h, C.byref(r)))
         elif analysis.kind == "dc":
-            _check_krh(L.krh_solver_solve_dc(self._h, p.element.encode(), p.start, p.stop, p.step_size, C.byref(r)))
+            _check_krh(L.krh_solver_solve_dc_with(self._h, p.element.encode(), p.start, p.stop, p.step_size, p.mode, C.byref(r)))
         elif analysis.kind == "ac":
             _check_krh(L.krh_solver_solve_ac(self._h, _SWEEP_KIND[p.sweep.variation], p.sweep.points, p.fstart, p.fstop, C.byref(r)))
         elif analysis.kind == "transient":
@@ -489,6 +491,26 @@ class Plan:
         _check_krb(_lib.lib().krb_solve_dc_sweep(self._h, C.byref(cfg.c), _ptr(sweep_values), lanes, C.byref(ov) if ov else None,
                                                  _ptr(out), _ptr(status), C.byref(io)))
         return out, status
+
+    def solve_dc_sweep_sequential(self, start: float, step_size: float, n_points: int, lanes: int = 1, varied_values=None, out=None,
+                                  cfg: SolverConfig | None = None, layout=LAYOUT_POINT_MAJOR, return_iterations=False, select=None):
+        """dc.rs:47-113 as written (nonlinear circuits): the sweep points are the rows of a lane, solved in order, Newton-Raphson
+        warm-started from the previous point (dc.rs:58,112); lanes are Monte-Carlo variants.  Returns x[lane][row][unknown]."""
+        cfg = cfg or SolverConfig()
+        varied_values = _f64_in(varied_values, (len(self.varied), lanes) if self.varied else None, "varied_values")
+        cols = self.n if select is None else len(select)
+        shape = (lanes, n_points, cols) if layout == LAYOUT_POINT_MAJOR else (n_points, cols, lanes)
+        if out is None:
+            out = _like_out(varied_values, shape, False) if varied_values is not None else np.zeros(shape, dtype=np.float64)
+        else:
+            _check_out(out, shape, False)
+        status = _like_int(out, lanes)
+        iters = _like_int(out, lanes) if return_iterations else None
+        ov, _keep = self._ov(varied_values)
+        io = self._io([out, varied_values], layout, select)
+        _check_krb(_lib.lib().krb_solve_dc_sweep_sequential(self._h, C.byref(cfg.c), float(start), float(step_size), int(n_points), lanes,
+                                                            C.byref(ov) if ov else None, _ptr(out), _ptr(iters), _ptr(status), C.byref(io)))
+        return (out, status, iters) if return_iterations else (out, status)
 
     def solve_ac(self, frequencies, varied_values=None, op_solution=None, out=None, cfg: SolverConfig | None = None,
                  layout=LAYOUT_POINT_MAJOR, select=None):

@@ -283,6 +283,22 @@ int32_t krb_solve_dc_sweep(krb_plan *plan_dc, const krb_config *cfg, const doubl
     return run_lanes(&plan_dc->p, nullptr, a);
 }
 
+int32_t krb_solve_dc_sweep_sequential(krb_plan *plan_dc, const krb_config *cfg, double start, double step_size, int64_t n_points, int64_t lanes,
+                                      const krb_overrides *ov, double *x_out, int32_t *iterations, int32_t *lane_status, const krb_io *io) {
+    if (!plan_dc || !cfg || !x_out || lanes < 0 || n_points < 1 || plan_dc->p.mode != KRB_MODE_DC) { set_error("krb_solve_dc_sweep_sequential: invalid argument"); return KRB_ERR_INVALID_ARGUMENT; }
+    if (plan_dc->p.input_sweep < 0) { set_error("krb_solve_dc_sweep_sequential: plan has no sweep element (krb_plan_opts.sweep_element)"); return KRB_ERR_ELEMENT_NOT_FOUND; }
+    if (n_points > 0x3fffffff) { set_error("krb_solve_dc_sweep_sequential: too many sweep points"); return KRB_ERR_INVALID_ARGUMENT; }
+    krb_io o; int rc;
+    if ((rc = check_io(io, o))) return rc;
+    RunArgs a;
+    if ((rc = check_ov(plan_dc->p, ov, &a.varied_values))) return rc;
+    a.cfg = *cfg; a.lanes = lanes; a.rows = (int)n_points; a.x_out = x_out; a.lane_status = lane_status; a.iterations = iterations;
+    a.sweep_rows = true; a.sweep_start = start; a.sweep_step = step_size;
+    a.memory = o.memory; a.layout = o.layout; a.stream = o.stream;
+    if ((rc = set_select(plan_dc->p, o, a))) return rc;
+    return run_lanes(&plan_dc->p, nullptr, a);
+}
+
 int32_t krb_solve_ac(krb_plan *plan_ac, const krb_config *cfg, const double *frequencies, int64_t lanes, const krb_overrides *ov,
                      const double *op_solution, int64_t lanes_op, double *x_out, int32_t *lane_status, const krb_io *io) {
     if (!plan_ac || !cfg || !x_out || !frequencies || lanes < 0 || plan_ac->p.mode != KRB_MODE_AC) { set_error("krb_solve_ac: invalid argument"); return KRB_ERR_INVALID_ARGUMENT; }

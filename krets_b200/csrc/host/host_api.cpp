@@ -231,7 +231,11 @@ int32_t krh_solver_solve_op(krh_solver *s, krh_result **out) {
 
 // dc.rs:14-124
 int32_t krh_solver_solve_dc(krh_solver *s, const char *element, double start, double stop, double step_size, krh_result **out) {
+    return krh_solver_solve_dc_with(s, element, start, stop, step_size, KRH_DC_REFERENCE, out);
+}
+int32_t krh_solver_solve_dc_with(krh_solver *s, const char *element, double start, double stop, double step_size, int32_t mode, krh_result **out) {
     if (!s || !out || !element) return fail(KRB_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode != KRH_DC_REFERENCE && mode != KRH_DC_PARALLEL_COLD_START) return fail(KRB_ERR_INVALID_ARGUMENT, "DC sweep: unknown mode");
     int ei = -1;
     for (size_t i = 0; i < s->pc.elements.size(); i++)
         if (s->pc.elements[i].identifier == element) { ei = (int)i; break; }          // dc.rs:21-24
@@ -253,6 +257,17 @@ int32_t krh_solver_solve_dc(krh_solver *s, const char *element, double start, do
     r->axis.resize(num);
     std::vector<double> vals(num);
     for (int i = 0; i < num; i++) { vals[i] = start + ((double)i * step_size); r->axis[i] = (double)i; }   // dc.rs:48, :97
+    if (!circuit_is_linear(s) && mode == KRH_DC_REFERENCE) {
+        // dc.rs:58,112: with Newton-Raphson every sweep point starts from its predecessor's solution, so the points are sequential:
+        // one lane, the sweep points as its rows (x[0][row][unknown] is exactly the result layout)
+        int32_t st1 = 0;
+        rc = krb_solve_dc_sweep_sequential(p, &s->cfg, start, step_size, num, 1, nullptr, r->data.data(), nullptr, &st1, nullptr);
+        if (rc) return fail_krb(rc);
+        std::vector<int32_t> sv(1, st1);
+        if ((rc = status_to_error(sv))) return rc;
+        *out = r.release();
+        return KRB_OK;
+    }
     std::vector<int32_t> st(num, 0);
     rc = krb_solve_dc_sweep(p, &s->cfg, vals.data(), num, nullptr, r->data.data(), st.data(), nullptr);
     if (rc) return fail_krb(rc);

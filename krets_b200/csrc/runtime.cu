@@ -377,6 +377,11 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
     if (device_count() <= 0) { set_error("no CUDA device: krets_b200 has no CPU fallback"); return KRB_ERR_NO_DEVICE; }
     Plan &P0 = *plan_first;
     Plan *PS = plan_steps;
+    if (a.sweep_rows && (P0.use_front || P0.use_chain || PS || P0.input_sweep < 0)) {
+        // only Newton-Raphson makes a sweep point depend on its predecessor, and nonlinear circuits always compile to a lane program
+        set_error("sequential DC sweep: the plan does not run on the lane VM (linear chain / front plans: results do not depend on the warm start, use krb_solve_dc_sweep)");
+        return KRB_ERR_UNSUPPORTED;
+    }
     if (P0.use_front) return run_front(plan_first, plan_steps, a);
     if (PS && PS->use_front) { set_error("transient: plan_tran uses the front executor but plan_dc does not (analyse both with KRB_EXEC_STAGED)"); return KRB_ERR_UNSUPPORTED; }
     if (!P0.dev) P0.dev = device_state_new();
@@ -526,6 +531,7 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
                                            (size_t)lanes * 8, (size_t)nv, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
             for (int k = 0; k < P0.n_inputs; k++) {
                 const double *src = nullptr;
+                if (k == P0.input_sweep && a.sweep_rows) continue;   // filled row by row in front of each launch
                 if (k == P0.input_sweep || k == P0.input_freq) src = a.lane_param;
                 else {
                     if (run) continue;
@@ -620,7 +626,20 @@ int run_lanes(Plan *plan_first, Plan *plan_steps, const RunArgs &a) {
             p.h = P0.opts.time_step; p.reltol = a.cfg.relative_tolerance; p.iabstol = a.cfg.current_absolute_tolerance; p.vabstol = a.cfg.voltage_absolute_tolerance;
             p.status = status_d; p.iters = iters_d;
             if (width > n) CUDA_TRY(cudaMemsetAsync((char *)D0.X[b].p + (size_t)n * Lpad * ts, 0, (size_t)(width - n) * Lpad * ts, st));   // i_C(0) = 0
-            if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st, D0.jit))) return rc;
+            if (a.sweep_rows) {
+                // dc.rs:47-113: sweep points are the result rows of a lane, one launch per row (every lane of the chunk advances together).
+                // Row 0 starts from the empty map (dc.rs:41), row r from row r - 1 (dc.rs:58,112); the "step" key of the result map
+                // (dc.rs:97) takes part in the convergence check like the transient "time" key: |r - (r - 1)| against the voltage tolerance
+                // (solver.rs:96-103, SURVEY B-5), which the kernels evaluate as |row h - (row - 1) h| with h = 1
+                p.pseudo_time = 1; p.h = 1.0;
+                for (int r = 0; r < rows; r++) {
+                    krb_fill_plane<<<(unsigned)((Lpad + 255) / 256), 256, 0, st>>>(IN + (size_t)P0.input_sweep * Lpad, Lpad, a.sweep_start + ((double)r * a.sweep_step));   // dc.rs:48
+                    g_launches++;
+                    p.row_begin = r; p.row_end = r + 1;
+                    p.guess_empty_at_iter0 = r == 0 ? 1 : 0;
+                    if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st, D0.jit))) return rc;
+                }
+            } else if ((rc = launch_vm(cplx, tpb, p, Lpad, P0.n_slots, st, D0.jit))) return rc;
             if (PS && rows > 1 && PS->dense.valid && getenv("KRB_NO_DENSE_TRAN") == nullptr) {
                 // small linear circuit: native stepping kernel (row 0 = the operating point just written by the DC plan)
                 DeviceState &DS = *PS->dev;

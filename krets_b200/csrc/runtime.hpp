@@ -33,6 +33,10 @@ struct RunArgs {
     long long chunk_lanes = 0;
     const int32_t *select = nullptr;     // extension: deliver only these unknowns (host pointer), n_select of them per point
     int n_select = 0;
+    // sequential DC sweep (dc.rs:47-113 as written): row r of every lane solves with the sweep element at sweep_start + r * sweep_step,
+    // Newton-Raphson warm-started from row r - 1 (dc.rs:58,112); lane_param is unused
+    bool sweep_rows = false;
+    double sweep_start = 0.0, sweep_step = 0.0;
 };
 
 void set_error(const std::string &s);

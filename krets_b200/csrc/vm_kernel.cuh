@@ -300,6 +300,12 @@ __global__ void krb_fill_pad(double *plane, long long L, long long lanes, long l
     }
 }
 
+// one input plane <- the same value on every lane (sequential DC sweep: the sweep element's value of the current row)
+__global__ void krb_fill_plane(double *__restrict__ plane, long long L, double value) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < L) plane[i] = value;
+}
+
 // op_solution[lane][u] (point-major) or [u] broadcast  ->  plane [u][L]
 __global__ void krb_spread_op(const double *__restrict__ op, double *__restrict__ plane, int n, long long L, long long lanes, int broadcast) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

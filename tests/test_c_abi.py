@@ -81,3 +81,56 @@ def test_c_client_host_side(abi_check):
 def test_c_client_solves_on_the_gpu(abi_check):
     out = subprocess.check_output([abi_check, "--solve"], text=True)
     assert "solved 3 sweep points on the GPU" in out
+
+
+# ---- sequential DC sweep (dc.rs:58,112 warm start) from plain C ---------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def seq_sweep(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("c_abi_seq") / "seq_sweep")
+    libdir = os.path.join(ROOT, "krets_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi", "seq_sweep.c"), "-o", exe, "-L", libdir, "-lkrets_b200", f"-Wl,-rpath,{libdir}", "-lm"])
+    return exe
+
+
+def _netlist_file(golden, key, tmp_path):
+    path = str(tmp_path / (key + ".cir"))
+    with open(path, "w") as f:
+        f.write(golden["netlists"][key])
+    return path
+
+
+def test_c_client_sequential_sweep_host_side(seq_sweep, golden, tmp_path):
+    import krets_b200 as kb
+    if kb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    out = json.loads(subprocess.check_output([seq_sweep, _netlist_file(golden, "diode_iv_curve", tmp_path), "V1", "0", "2", "0.125"]))
+    assert out == {"no_device": True}
+
+
+def check_sequential_sweep_output(out, oracle, golden):
+    """shared with tools/seq_sweep_check.py: the C client's JSON for circuits/diode_iv_curve against the oracle"""
+    import numpy as np
+    from helpers import assert_close
+    oc = oracle.Circuit(golden["netlists"]["diode_iv_curve"])
+    warm = oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=True)
+    cold = oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=False)
+    assert out["rows"] == 17 and out["n"] == warm.shape[1]
+    assert_close(np.array(out["reference"]), warm, rtol=1e-9, what="Solver DC sweep (sequential) vs the reference's warm start")
+    assert_close(np.array(out["parallel"]), cold, rtol=1e-8, what="parallel cold-start extension vs the oracle run the same way")
+    if "lanes" in out:
+        lanes = np.array(out["lanes"]).reshape(-1, 17, out["n"])
+        e = oc.element_index("R1")
+        for l, r in enumerate(out["_values"]):
+            oc.set_element_value(e, r)
+            assert_close(lanes[l], oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=True), rtol=1e-9, what=f"Monte-Carlo lane {l} (R1 = {r})")
+        assert not any(out["status"]) and all(i >= 2 for i in out["iterations"])
+
+
+@pytest.mark.gpu
+def test_c_client_sequential_sweep_on_the_gpu(seq_sweep, oracle, golden, tmp_path):
+    values = [1000.0, 900.0, 1500.0]
+    out = json.loads(subprocess.check_output([seq_sweep, _netlist_file(golden, "diode_iv_curve", tmp_path), "V1", "0", "2", "0.125", "R1"] +
+                                             [repr(v) for v in values]))
+    out["_values"] = values
+    check_sequential_sweep_output(out, oracle, golden)

@@ -5,6 +5,7 @@ which bounds both the magnitude and the phase error.  The reference's own test a
 full-precision golden parquets are replayed through the Solver-shaped API so these read like crates/krets-solver/tests.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -88,15 +89,60 @@ def test_dc_inverter_golden(oracle, golden):
             np.testing.assert_allclose(res.array[:, circuit.index_map[name]], col, rtol=1e-12, atol=1e-15, err_msg=name)
 
 
-def test_dc_diode_sweep_cold_start(oracle, golden):
-    """Nonlinear DC sweep: every lane starts from the empty guess (documented deviation from dc.rs:58); parity is
-    against the oracle run the same way, and within NR tolerance against the reference's sequential warm start."""
+def test_dc_diode_sweep_reference_warm_start(oracle, golden):
+    """Nonlinear DC sweep through the Solver: the reference's sequential sweep, every point warm-started from its predecessor
+    (dc.rs:58,112) — parity with the oracle's warm-started sweep at 1e-9 (the iteration history is the reference's)."""
     circuit, oc = both(oracle, golden, "diode_iv_curve")
     res = kb.Solver(circuit).solve(kb.Analysis.Dc(kb.DcAnalysis("V1", 0.0, 2.0, 0.125)))
+    warm = oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=True)
+    cold = oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=False)
+    assert res.array.shape == warm.shape and res.axis.tolist() == [float(i) for i in range(17)]
+    assert_close(res.array, warm, rtol=1e-9, what="diode sweep vs the reference's warm-started sweep")
+    assert np.max(np.abs(warm - cold)) > 1e-9     # the two iteration histories differ measurably: 1e-9 tells them apart
+
+
+def test_dc_diode_sweep_parallel_cold_start(oracle, golden):
+    """Extension (DcAnalysis.mode = DC_PARALLEL_COLD_START): the points of a nonlinear sweep as parallel lanes, every lane from the empty
+    guess; parity is against the oracle run the same way, and within NR tolerance against the reference's sequential warm start."""
+    circuit, oc = both(oracle, golden, "diode_iv_curve")
+    res = kb.Solver(circuit).solve(kb.Analysis.Dc(kb.DcAnalysis("V1", 0.0, 2.0, 0.125, mode=api.DC_PARALLEL_COLD_START)))
     cold = oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=False)
     warm = oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=True)
     assert_close(res.array, cold, rtol=1e-8, what="diode sweep vs cold-start oracle")
     assert np.max(np.abs(res.array - warm)) < 2e-3
+
+
+def test_dc_sweep_sequential_monte_carlo_lanes(oracle, golden):
+    """krb_solve_dc_sweep_sequential: Monte-Carlo lanes (R1 per lane), each a warm-started sequential sweep; interpreter and
+    circuit-specialised kernel agree bit for bit; every lane equals the oracle's warm-started sweep of that variant."""
+    circuit, oc = both(oracle, golden, "diode_iv_curve")
+    r1 = circuit.element_index("R1")
+    vals = np.array([[1000.0, 900.0, 1500.0, 330.0, 4700.0]])
+    outs = []
+    for jit in ("1", "0"):
+        os.environ["KRB_VM_JIT"] = jit
+        try:
+            plan = kb.Plan(circuit, api.MODE_DC, sweep_element=circuit.element_index("V1"), varied=[r1])
+            x, status, iters = plan.solve_dc_sweep_sequential(0.0, 0.125, 17, lanes=5, varied_values=vals, return_iterations=True)
+        finally:
+            os.environ.pop("KRB_VM_JIT", None)
+        assert x.shape == (5, 17, circuit.n) and not status.any() and (iters >= 2).all()
+        outs.append(x)
+    assert np.array_equal(outs[0], outs[1])
+    e = oc.element_index("R1")
+    for l in range(5):
+        oc.set_element_value(e, float(vals[0, l]))
+        assert_close(outs[0][l], oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=True), rtol=1e-9, what=f"lane {l}")
+    oc.set_element_value(e, 1000.0)
+
+
+def test_dc_sweep_sequential_rejects_plans_off_the_lane_vm(oracle):
+    """Linear chain plans cannot depend on a warm start: the sequential entry point refuses them instead of running something else."""
+    kc = kb.parse_circuit_description(netgen.resistor_ladder(600))
+    plan = kb.Plan(kc, api.MODE_DC, sweep_element=0)
+    with pytest.raises(kb.KretsError) as e:
+        plan.solve_dc_sweep_sequential(0.0, 1.0, 3)
+    assert e.value.kind == "Unsupported"
 
 
 # ---- tests/test_ac.rs + golden parquet -------------------------------------------------------------------------

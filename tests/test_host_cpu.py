@@ -9,7 +9,7 @@ import pytest
 
 import netgen
 from helpers import assert_close
-from vm_emulator import Emulator, input_layout
+from vm_emulator import Emulator, input_layout, run_sequential_sweep
 
 import krets_b200 as kb
 from krets_b200 import _lib, api
@@ -152,6 +152,36 @@ def test_program_op_small_circuits(oracle, golden, slots):
         em = Emulator(plan, 1)
         X = em.run(np.zeros((0, 1)))
         assert_close(X[0][:, 0], oc.solve_op(), what=key)
+
+
+def test_program_dc_sweep_sequential_warm_start(oracle, golden):
+    """dc.rs:58,112: a nonlinear DC sweep is sequential, every point warm-started from its predecessor.  The DC lane program run on the
+    sequential launch schedule reproduces the reference's iteration history (oracle warm_start=True) to 1e-9 — the lane-parallel
+    cold start only agrees within the Newton-Raphson tolerance."""
+    kc, oc = kcirc(golden, "diode_iv_curve"), ocirc(oracle, golden, "diode_iv_curve")
+    plan = kb.Plan(kc, api.MODE_DC, sweep_element=kc.element_index("V1"))
+    X, em, its = run_sequential_sweep(Emulator, plan, 0.0, 0.125, 17)
+    warm = oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=True)
+    cold = oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=False)
+    assert warm.shape == (17, plan.n) and not em.status.any()
+    assert_close(X[:, : plan.n, 0], warm, rtol=1e-9, what="sequential sweep vs the reference's warm start")
+    assert np.max(np.abs(warm - cold)) > 1e-9            # the two iteration histories really differ: the test can tell them apart
+    # the `step` pseudo-unknown (dc.rs:97) forces a second iteration at every warm-started point (|r - (r-1)| = 1 > reltol*r + 1e-6)
+    assert (its[1:, 0] >= 2).all()
+
+
+def test_program_dc_sweep_sequential_inverter_golden(oracle, golden):
+    """circuits/inverter/dc/result.parquet through the sequential schedule (NMOS stamps nothing, but the circuit counts as nonlinear)."""
+    g = golden["parquet"]["inverter_dc"]
+    kc = kcirc(golden, "inverter")
+    s = g["spec"]
+    plan = kb.Plan(kc, api.MODE_DC, sweep_element=kc.element_index(s["element"]))
+    num = len(g["columns"]["step"])
+    X, em, _ = run_sequential_sweep(Emulator, plan, s["start"], s["step_size"], num)
+    assert not em.status.any()
+    for name, col in g["columns"].items():
+        if name != "step":
+            np.testing.assert_allclose(X[:, kc.index_map[name], 0], col, rtol=1e-12, atol=1e-15, err_msg=name)
 
 
 def test_program_nr_diode(oracle, golden):

@@ -78,6 +78,18 @@ def test_jit_host_nr_diode(oracle, golden):
     assert jh.iters[0] == it and jh.status[0] == 0
 
 
+def test_jit_host_dc_sweep_sequential_warm_start(oracle, golden):
+    """The specialised kernel on the sequential DC-sweep schedule (dc.rs:58,112 warm start) == the reference's iteration history."""
+    from vm_emulator import Emulator, run_sequential_sweep
+    kc, oc = kcirc(golden, "diode_iv_curve"), ocirc(oracle, golden, "diode_iv_curve")
+    plan = kb.Plan(kc, api.MODE_DC, sweep_element=kc.element_index("V1"))
+    X, jh, its = run_sequential_sweep(JitHost, plan, 0.0, 0.125, 17)
+    assert_close(X[:, : plan.n, 0], oc.solve_dc("V1", 0.0, 2.0, 0.125, warm_start=True), rtol=1e-9, what="sequential sweep (specialised kernel)")
+    Xe, em, ite = run_sequential_sweep(Emulator, plan, 0.0, 0.125, 17)
+    assert_close(X[:, : plan.n, 0], Xe[:, : plan.n, 0], rtol=1e-12, what="specialised kernel vs interpreter emulator")
+    assert np.array_equal(its, ite) and not jh.status.any()
+
+
 def test_jit_host_dc_sweep_with_spills(oracle):
     """A 100-section ladder forced onto the lane VM with 12 scratch cells: LDG/STG planes, LDI sweep input."""
     text = netgen.resistor_ladder(100)

@@ -208,6 +208,22 @@ class Emulator:
         return X
 
 
+def run_sequential_sweep(driver, plan, start, step, num, lanes=1, IN_extra=None):
+    """The launch schedule of krb_solve_dc_sweep_sequential (runtime.cu run_lanes, `sweep_rows`) on a CPU driver (Emulator or
+    jit_host.JitHost): one launch per sweep point, the sweep element's input plane filled with start + r*step (dc.rs:48), row 0 from the
+    empty guess (dc.rs:41), row r warm-started from row r-1 (dc.rs:58,112), the `step` pseudo-unknown as |r h - (r-1) h| with h = 1."""
+    i_sweep, _, _ = input_layout(plan)
+    IN = np.zeros((i_sweep + 1, lanes)) if IN_extra is None else np.array(IN_extra, dtype=np.float64)
+    em = driver(plan, lanes, rows=num, h=1.0)
+    X = None
+    its = []
+    for r in range(num):
+        IN[i_sweep, :] = start + (float(r) * step)
+        X = em.run(IN, X=X, row_begin=r, row_end=r + 1, guess_empty_at_iter0=(r == 0), pseudo_time=True)
+        its.append(em.iters.copy())
+    return X, em, np.array(its)
+
+
 # ---- chain executor term stream (chain_kernel.cuh) --------------------------------------------------------------
 def run_chain(plan, IN, cplx):
     """numpy restatement of krb_chain_kernel (row-info words + 16-byte record stream): IN [n_inputs][L] -> X [n][L]."""
