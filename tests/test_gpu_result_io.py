@@ -52,3 +52,47 @@ def test_cuda_dc_and_transient_result_files(tmp_path, golden, oracle):
     assert np.array_equal(cols["time"], t)
     for k in names[1:]:
         np.testing.assert_allclose(cols[k], rows[:, oc.index_map[k]], rtol=1e-9, atol=1e-12, err_msg=k)
+
+
+# ---- `krets <krets.toml>` (crates/krets-cli/src/main.rs:33-125) on the reference's three checked-in specs --------------------------
+def _spec_dir(golden, key, tmp_path):
+    from krets_b200 import spec
+    s = golden["specs"][key]
+    an = spec.AnalysisSpec.from_str(s["toml"])
+    d = tmp_path / key
+    d.mkdir()
+    (d / an.circuit_path).write_text(golden["netlists"][s["netlist"]])
+    (d / "krets.toml").write_text(s["toml"])
+    return str(d / "krets.toml"), d
+
+
+def test_run_spec_writes_the_reference_result_files(tmp_path, golden, oracle):
+    """circuits/low_pass_filter/ac/krets.toml and circuits/inverter/dc/krets.toml run like `krets <file>`: result.parquet next to the spec
+    equals the result.parquet the reference checked in; circuits/high_pass_filter/transient/krets.toml against the oracle's rows."""
+    from krets_b200 import spec
+    k, d = _spec_dir(golden, "low_pass_filter_ac", tmp_path)
+    res, out = spec.run_spec(k)
+    assert res.kind == "ac" and out == str(d / "result.parquet")
+    g = golden["parquet"]["low_pass_filter_ac"]
+    names, cols = _read(out)
+    assert names == ["frequency", "I(V1)_mag", "I(V1)_phase_deg", "V(in)_mag", "V(in)_phase_deg", "V(out)_mag", "V(out)_phase_deg"]
+    assert np.array_equal(cols["frequency"], np.array(g["columns"]["frequency"]))
+    for c in names[1:]:
+        np.testing.assert_allclose(cols[c], g["columns"][c], rtol=1e-9, atol=1e-12, err_msg=c)
+
+    k, d = _spec_dir(golden, "inverter_dc", tmp_path)
+    assert spec.main([k]) == 0                       # the module's entry point: same run, exit status 0
+    g = golden["parquet"]["inverter_dc"]
+    names, cols = _read(str(d / "result.parquet"))
+    assert names == sorted(g["columns"].keys())
+    for c in names:
+        np.testing.assert_allclose(cols[c], g["columns"][c], rtol=1e-9, atol=1e-15, err_msg=c)
+
+    k, d = _spec_dir(golden, "high_pass_filter_transient", tmp_path)
+    res, out = spec.run_spec(k)
+    oc = oracle.Circuit(golden["netlists"][golden["specs"]["high_pass_filter_transient"]["netlist"]])
+    t, rows = oc.solve_tran(10e-6, 2e-3)
+    names, cols = _read(out)
+    assert names[0] == "time" and names[1:] == sorted(names[1:]) and np.array_equal(cols["time"], t) and len(t) == 201
+    for c in names[1:]:
+        np.testing.assert_allclose(cols[c], rows[:, oc.index_map[c]], rtol=1e-9, atol=1e-12, err_msg=c)
