@@ -37,8 +37,8 @@ STEP = 2.0 ** -16
 FP64_PEAK_TFLOPS = 37.2   # measured, see roofline.compute.peak_source
 METRIC = "solved sweep points/sec (batched sparse LU)"
 UNIT = "points/s"
-ALL_WORKLOADS = ["ladder_dc", "rc_ac", "dual_rc_tran", "dual_rc_tran_be", "mesh_tran", "mesh_ac", "ladder_mc", "rectifier_tran"]
-OTHER_WORKLOADS = ["rc_ac", "ladder_mc", "dual_rc_tran", "dual_rc_tran_be", "mesh_ac", "mesh_tran", "rectifier_tran"]   # other_configs of the default line
+ALL_WORKLOADS = ["ladder_dc", "rc_ac", "dual_rc_tran", "dual_rc_tran_be", "mesh_tran", "mesh_ac", "ladder_mc", "rectifier_tran", "diode_dc_seq"]
+OTHER_WORKLOADS = ["rc_ac", "ladder_mc", "dual_rc_tran", "dual_rc_tran_be", "mesh_ac", "mesh_tran", "rectifier_tran", "diode_dc_seq"]   # other_configs of the default line
 
 
 def workload_config(n_gpus):
@@ -394,6 +394,38 @@ def make_workload(name, args, rank):
                         kernel="krb_jit_vm (the lane program as a circuit-specialised kernel, NVRTC for sm_100a at first use: stamp + LDU + solve per Newton iteration, per-lane convergence mask; KRB_VM_JIT=0: krb_lane_vm interpreter)",
                         what=f"circuits/rectifier (4 diodes) transient, {nsteps} backward-Euler steps x {lanes} Monte-Carlo R/C variants per GPU, Newton-Raphson at every step (nonlinear path; not a BASELINE config)",
                         alg=8 * (int(plan.info.nnz_lu) + 3 * circuit.n), alg_what="B_step = s*(nnz_lu + 3*n) per Newton iteration (at least two per point), SURVEY 8(d)",
+                        moved=8 * circuit.n, moved_what="s*n: one result row per solved point (the lane program's working set stays on chip)",
+                        traffic_key=None, check=check)
+    if name == "diode_dc_seq":
+        # The reference's nonlinear DC sweep as written (dc.rs:47-113): the sweep points of circuits/diode_iv_curve are solved in order,
+        # Newton-Raphson warm-started from the previous point (dc.rs:58,112) — the points are the rows of a lane, the lanes are Monte-Carlo
+        # variants of R1.  Not a BASELINE config: it puts a number on krb_solve_dc_sweep_sequential.
+        text = golden["netlists"]["diode_iv_curve"]
+        circuit = kb.parse_circuit_description(text)
+        varied = [circuit.element_index("R1")]
+        lanes = 65536 if dflt else args.lanes
+        npts, start, step_size = 101, 0.0, 0.02
+        host_vals = np.array([[circuit.element_value(e) * netgen.mc_factor(l, j, 2) for l in range(rank * lanes, (rank + 1) * lanes)] for j, e in enumerate(varied)])
+        vals = torch.from_numpy(host_vals).cuda()
+        plan = kb.Plan(circuit, api.MODE_DC, sweep_element=circuit.element_index("V1"), varied=varied)
+        out = torch.empty((lanes, npts, circuit.n), dtype=torch.float64, device="cuda")
+
+        def check(k=2):
+            from oracle import oracle
+            idx = np.random.default_rng(7).choice(lanes, size=min(k, lanes), replace=False)
+            worst = 0.0
+            for l in idx:
+                oc = oracle.Circuit(text)
+                oc.set_element_value(oc.element_index("R1"), host_vals[0, l])
+                ref = oc.solve_dc("V1", start, start + (npts - 1) * step_size, step_size, warm_start=True)
+                worst = max(worst, _rel_err(out[int(l)].cpu().numpy(), ref[:npts]))
+            return {"lanes_checked": int(len(idx)), "rows_per_lane": npts, "max_rel_err_vs_oracle": worst,
+                    "oracle": "the reference's sequential warm-started sweep (dc.rs:58,112)"}
+        return Workload(name=name, config="nonlinear-dc", plan=plan, circuit=circuit, lanes=lanes, points=lanes * npts, dtype="f64", s=8, out=out,
+                        step=lambda: plan.solve_dc_sweep_sequential(start, step_size, npts, lanes, varied_values=vals, out=out),
+                        kernel="krb_jit_vm, one launch per sweep point (rows of a lane in order, warm-started from the previous row; KRB_VM_JIT=0: krb_lane_vm)",
+                        what=f"circuits/diode_iv_curve DC sweep of V1, {npts} points in order (Newton-Raphson warm-started from the previous point, dc.rs:58) x {lanes} Monte-Carlo R1 variants per GPU (nonlinear path; not a BASELINE config)",
+                        alg=8 * (int(plan.info.nnz_lu) + 3 * circuit.n), alg_what="s*(nnz_lu + 3*n) per Newton iteration (two per point), SURVEY 8(d)",
                         moved=8 * circuit.n, moved_what="s*n: one result row per solved point (the lane program's working set stays on chip)",
                         traffic_key=None, check=check)
     if name in ("mesh_ac", "mesh_tran"):                # BASELINE config 5
