@@ -40,8 +40,10 @@ def test_solver_op_dc_transient_ac(oracle, level1, executor):
     ref = oc.solve_op()
     assert_close(np.array([op[nm] for nm in oc.names]), ref, what="common-source OP")
     dc = solver.solve(kb.Analysis.Dc(kb.DcAnalysis("VG", 0.0, 2.25, 0.25)))
+    assert_close(dc.array, oc.solve_dc("VG", 0.0, 2.25, 0.25, warm_start=True), rtol=1e-8, what="gate sweep vs the sequential warm-started oracle (dc.rs:58)")
+    dc = solver.solve(kb.Analysis.Dc(kb.DcAnalysis("VG", 0.0, 2.25, 0.25, mode=api.DC_PARALLEL_COLD_START)))
     cold = oc.solve_dc("VG", 0.0, 2.25, 0.25, warm_start=False)
-    assert_close(dc.array, cold, rtol=1e-8, what="gate sweep vs cold-start oracle")
+    assert_close(dc.array, cold, rtol=1e-8, what="gate sweep, parallel lanes vs cold-start oracle")
     ac = solver.solve(kb.Analysis.Ac(kb.AcAnalysis(kb.AcSweep.Decade(5), 10.0, 1e6)))
     fr, refa = oc.solve_ac(oracle.generate_frequencies("Decade", 5, 10.0, 1e6))
     assert ac.axis.tobytes() == fr.tobytes()

@@ -109,6 +109,11 @@ def test_lane_program_op_and_sweep_lanes(oracle, level1, runner):
     assert cold.shape[0] == len(vals)
     assert_close(X[0].T, cold, what="gate sweep vs cold-start oracle")
     assert not r.status.any()
+    # the reference's sweep order (dc.rs:58,112): the same points as the rows of one lane, warm-started from the previous point
+    from vm_emulator import run_sequential_sweep
+    Xs, rs, _ = run_sequential_sweep(Run, sweep, 0.0, 0.25, len(vals))
+    assert_close(Xs[:, : sweep.n, 0], oc.solve_dc("VG", 0.0, 2.25, 0.25, warm_start=True), what="gate sweep vs the sequential warm-started oracle")
+    assert not rs.status.any()
     # deep in the linear region the reference's un-limited Newton iteration cycles from an empty guess (v_ds < 0 falls into the
     # all-zero branch of nmosfet.rs:51-102): the oracle reports MaximumIterationsExceeded, the lane its NOT_CONVERGED bit
     cfg = dict(reltol=1e-3, iabstol=1e-12, vabstol=1e-6, max_iter=40)
