@@ -118,6 +118,7 @@ _DEBUG_SYMBOLS = {
     "krb_plan_state_columns": (_i32, [_vp]),
     "krb_plan_integrator": (_i32, [_vp]),
     "krb_plan_jit_active": (_i32, [_vp]),
+    "krb_plan_repivoted": (_i32, [_vp]),
     "krb_plan_chain_size": (_i64, [_vp]),
     "krb_plan_get_chain": (_i32, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), _pi32]),
     "krb_plan_front_array": (_i64, [_vp, _i32, _pi32]),

@@ -220,6 +220,8 @@ int32_t krb_plan_front_info(const krb_plan *p, int64_t *out) {
     out[0] = f.n_fronts; out[1] = f.n_levels; out[2] = f.max_m; out[3] = f.max_p; out[4] = f.lu_size; out[5] = f.cb_size; out[6] = f.cbv_size; out[7] = f.flops;
     return KRB_OK;
 }
+// 1: the transversal's static pivot sequence cancelled at the nominal values and was re-pivoted numerically (compiler.cpp static_pivots_ok)
+int32_t krb_plan_repivoted(const krb_plan *p) { return p ? (p->p.repivoted ? 1 : 0) : -1; }
 int32_t krb_plan_integrator(const krb_plan *p) { return p ? p->p.opts.integrator : -1; }
 int32_t krb_plan_state_columns(const krb_plan *p) { return p ? (int32_t)p->p.state_elems.size() : -1; }
 int32_t krb_plan_has_step_sections(const krb_plan *p) { return p ? (p->p.has_step_sections ? 1 : 0) : -1; }

@@ -10,6 +10,7 @@
 // (farthest-next-use) eviction, rematerialises constants/inputs instead of spilling them, and spills the rest to
 // HBM value planes in production order (so the fused back substitution re-reads them as a reverse stream).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <complex>
@@ -843,6 +844,76 @@ void build_chain_plan(Plan &plan, const std::vector<int> &input_of_elem) {
     build_chain_block(plan, row_off, input_of_elem);
 }
 
+// ---- numeric check of the static pivot plan of a lane program ------------------------------------------------------------------
+// The row matching is a maximum-product transversal of |values| and the elimination order comes from the pattern alone, so nothing
+// above sees SIGNS: a floating voltage source whose terminals are also joined through companion conductances (V between nodes a, b;
+// C from a to c; R from c to b) gives a pivot sequence in which the branch current's pivot cancels EXACTLY, for any element values
+// (the source's KCL rows sum to an equation without the current) — the reference never notices because faer pivots numerically at
+// every factorisation (op.rs:50).  So the up-looking elimination of the lane program is run once on the host at the nominal values,
+// and a pivot that cancels to rounding level (|d| <= 1e-13 of the largest term of its own sum), vanishes or overflows rejects the plan.
+static bool static_pivots_ok(const Symbolic &S, const std::vector<cd> &val) {
+    const int n = S.n;
+    std::vector<cd> W(n, cd(0.0, 0.0));
+    std::vector<std::vector<cd>> Uhat(n);
+    for (int k = 0; k < n; k++) {
+        const auto &Lp = S.Lpat[k];
+        const auto &Up = S.Upat[k];
+        for (size_t t = 0; t < Lp.size(); t++) W[Lp[t]] = S.Lent[k][t] >= 0 ? val[S.Lent[k][t]] : cd(0.0, 0.0);
+        for (size_t t = 0; t < Up.size(); t++) W[Up[t]] = S.Uent[k][t] >= 0 ? val[S.Uent[k][t]] : cd(0.0, 0.0);
+        W[k] = S.Dent[k] >= 0 ? val[S.Dent[k]] : cd(0.0, 0.0);
+        double big = std::abs(W[k]);
+        for (int j : Lp) {                                   // ascending: row j of U^ is final
+            const cd l = W[j];
+            const auto &Uj = S.Upat[j];
+            for (size_t t = 0; t < Uj.size(); t++) {
+                const cd term = l * Uhat[j][t];
+                if (Uj[t] == k) big = std::max(big, std::abs(term));
+                W[Uj[t]] -= term;
+            }
+        }
+        const double d = std::abs(W[k]);
+        if (!(d > 0.0) || !std::isfinite(d) || !(d > 1e-13 * big)) return false;
+        Uhat[k].resize(Up.size());
+        for (size_t t = 0; t < Up.size(); t++) Uhat[k][t] = W[Up[t]] / W[k];
+    }
+    return true;
+}
+
+// Repair: what a numerically pivoting LU would choose at the nominal values — dense elimination in the given unknown order with
+// threshold partial pivoting over the equations not used yet; the equation the transversal matched to the unknown is kept whenever it
+// is within a factor 10 of the column maximum (the plan stays as close to the sparse one as the numbers allow).
+static bool repivot_at_nominal(const Pattern &p, const std::vector<cd> &val, const std::vector<int> &order, std::vector<int> &match_row) {
+    const int n = p.n;
+    if (n > 2048) return false;                              // dense n x n work matrix: lane programs are far smaller
+    std::vector<cd> A((size_t)n * n, cd(0.0, 0.0));          // A[row * n + position of the unknown in `order`]
+    std::vector<int> pos_of_col(n);
+    for (int k = 0; k < n; k++) pos_of_col[order[k]] = k;
+    for (int col = 0; col < n; col++)
+        for (int q = p.colptr[col]; q < p.colptr[col + 1]; q++) A[(size_t)p.rowidx[q] * n + pos_of_col[col]] = val[q];
+    std::vector<char> used(n, 0);
+    std::vector<int> chosen(n, -1);
+    for (int k = 0; k < n; k++) {
+        double best = 0.0;
+        int rbest = -1;
+        for (int r = 0; r < n; r++)
+            if (!used[r]) { const double a = std::abs(A[(size_t)r * n + k]); if (a > best) { best = a; rbest = r; } }
+        if (rbest < 0 || !(best > 0.0) || !std::isfinite(best)) return false;     // numerically singular at the nominal point
+        const int pref = match_row[order[k]];
+        if (!used[pref] && std::abs(A[(size_t)pref * n + k]) >= 0.1 * best) rbest = pref;
+        used[rbest] = 1;
+        chosen[k] = rbest;
+        const cd piv = A[(size_t)rbest * n + k];
+        for (int r = 0; r < n; r++) {
+            if (used[r]) continue;
+            const cd f = A[(size_t)r * n + k] / piv;
+            if (f == cd(0.0, 0.0)) continue;
+            for (int l = k + 1; l < n; l++) A[(size_t)r * n + l] -= f * A[(size_t)rbest * n + l];
+        }
+    }
+    for (int k = 0; k < n; k++) match_row[order[k]] = chosen[k];
+    return true;
+}
+
 }  // namespace
 
 int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan, std::string &err) {
@@ -897,6 +968,23 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
     if (use_front && c.nonlinear) { err = "the front executor (KRB_EXEC_STAGED) handles linear circuits only"; return KRB_ERR_UNSUPPORTED; }
     if (!use_front) {
         symbolic_lu(plan.pattern, match_row, order, plan.sym);
+        // numeric check of the static pivots at the nominal values; a cancelling sequence is re-pivoted (see static_pivots_ok).  Plans
+        // that go to the front executor below are skipped: the fronts pivot numerically per lane, and their pivot-free symbolic LU is large
+        if (!(plan.opts.exec == KRB_EXEC_FUSED && !banded && !c.nonlinear && plan.sym.flops > 250000)) {
+            std::vector<cd> val;
+            nominal_values(c, plan.stamps, plan.pattern, mode, plan.h_comp, fnom, val);
+            const bool no_check = getenv("KRB_NO_PIVOT_CHECK") != nullptr;             // tests: the plan as the transversal alone gives it
+            if (!no_check && !static_pivots_ok(plan.sym, val)) {
+                std::vector<int> order2 = order, match2 = match_row;
+                if (banded) minimum_degree(plan.pattern, match2, order2);               // the band orders have no freedom left
+                if (repivot_at_nominal(plan.pattern, val, order2, match2)) {
+                    Symbolic s2;
+                    symbolic_lu(plan.pattern, match2, order2, s2);
+                    if (static_pivots_ok(s2, val)) { match_row = match2; order = order2; plan.sym = s2; banded = false; plan.repivoted = true; }
+                }
+                if (getenv("KRB_PIVOT_DEBUG")) fprintf(stderr, "krets_b200: static pivot sequence cancels at the nominal values (mode %d, n = %d): %s\n", mode, n, plan.repivoted ? "re-pivoted" : "no repair found");
+            }
+        }
         if (plan.opts.exec == KRB_EXEC_FUSED && !banded && !c.nonlinear && plan.sym.flops > 250000) use_front = true;
     }
     if (use_front) {

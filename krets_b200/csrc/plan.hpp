@@ -2,6 +2,7 @@
 // written in C++ because this image has no Rust toolchain).
 #pragma once
 #include <cstdint>
+#include <complex>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,8 @@ void build_pattern(int n, const Stamps &s, Pattern &p);
 
 // nominal |value| of every entry (for the weighted static pivot matching)
 void nominal_magnitudes(const Circuit &c, const Stamps &s, const Pattern &p, int mode, double h, double fnom, std::vector<double> &mag);
+// the signed complex values the magnitudes are taken of
+void nominal_values(const Circuit &c, const Stamps &s, const Pattern &p, int mode, double h, double fnom, std::vector<std::complex<double>> &val);
 
 // ---- static pivot plan ----------------------------------------------------------------------------------
 // maximum-product transversal: match_row[col] = row used as the pivot equation of unknown `col`; false if
@@ -174,6 +177,7 @@ struct Plan {
     // program
     Program sec[3];                     // 0: main (one-shot / per-NR-iteration), 1: factor-once, 2: per-step
     bool has_step_sections = false;     // linear transient: sec[1] once + sec[2] per step
+    bool repivoted = false;             // the transversal's pivot sequence cancelled at the nominal values and was re-pivoted numerically (compiler.cpp)
     std::vector<PoolEntry> pool;        // B table layout (static part)
     std::vector<int> wave_elems;        // per-step table columns (LDBS): V sources with a transient RHS
     int n_slots = 0, n_planes = 0, n_inputs = 0;

@@ -3,6 +3,7 @@
 // triplets in push order — solver.rs:59-70 — and f64 addition is not associative).
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <map>
 
 #include "plan.hpp"
@@ -176,8 +177,17 @@ static const double KB = 1.380649e-23, QE = 1.602176634e-19, TEMP = 300.0;   // 
 static inline double thermal_voltage() { return KB * TEMP / QE; }            // constants.rs:4
 
 void nominal_magnitudes(const Circuit &c, const Stamps &s, const Pattern &p, int mode, double h, double fnom, std::vector<double> &mag) {
-    const double PI = 3.14159265358979323846264338327950288;
+    std::vector<std::complex<double>> val;
+    nominal_values(c, s, p, mode, h, fnom, val);
     mag.assign(p.nnz, 0.0);
+    for (int q = 0; q < p.nnz; q++) mag[q] = std::hypot(val[q].real(), val[q].imag());
+}
+
+// the signed (complex) nominal value of every entry: what the magnitudes above are taken of, and what the static pivot plan of
+// the lane programs is checked against (compiler.cpp: static_pivots_ok)
+void nominal_values(const Circuit &c, const Stamps &s, const Pattern &p, int mode, double h, double fnom, std::vector<std::complex<double>> &val) {
+    const double PI = 3.14159265358979323846264338327950288;
+    val.assign(p.nnz, std::complex<double>(0.0, 0.0));
     for (int q = 0; q < p.nnz; q++) {
         double re = 0.0, imv = 0.0;
         for (int ci : p.contribs[q]) {
@@ -209,7 +219,7 @@ void nominal_magnitudes(const Circuit &c, const Stamps &s, const Pattern &p, int
             if (src.neg) { vr = -vr; vi = -vi; }
             re += vr; imv += vi;
         }
-        mag[q] = std::hypot(re, imv);
+        val[q] = std::complex<double>(re, imv);
     }
     (void)mode;
 }

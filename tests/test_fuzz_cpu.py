@@ -1,0 +1,139 @@
+"""CPU tier: randomly generated small circuits through the plan compiler, the lane program run on the CPU emulator, against the oracle
+(OP, AC, backward-Euler transient; linear and diode circuits).  The generator is deterministic (numpy Generator, fixed seeds).
+
+This is how the static pivot plan was found to need a numeric check: a floating voltage source whose terminals are also joined through
+companion conductances gives a pivot sequence that cancels exactly for any element values (compiler.cpp: static_pivots_ok); the
+reference never sees it because faer pivots numerically at every factorisation (op.rs:50)."""
+import numpy as np
+import pytest
+
+import krets_b200 as kb
+from helpers import rel_err
+from krets_b200 import _lib, api
+from vm_emulator import Emulator
+
+FLOATING_SOURCE = "R2 2 0 1031.41\nR3 3 2 200.105\nC1 4 3 1.01013e-07\nV2 4 2 -1.689\n"
+
+
+def random_circuit(rng, diode):
+    """nodes 1..nn on a random resistor tree to ground (every node has a DC path), one grounded source, up to five more elements between
+    random node pairs; diodes come with a series resistor (a diode straight across a source has no meaningful solution)."""
+    nn = int(rng.integers(2, 7))
+    lines = [f"R{k} {k} {int(rng.integers(0, k))} {10 ** rng.uniform(1, 4):.6g}" for k in range(1, nn + 1)]
+    lines.append(f"V1 1 0 {rng.uniform(0.5, 5):.4g} AC 1")
+    cnt = {"R": nn, "C": 0, "L": 0, "I": 0, "V": 1, "D": 0}
+    for _ in range(int(rng.integers(1, 6))):
+        a, b = rng.choice(nn + 1, size=2, replace=False)
+        kind = rng.choice(["R", "C", "L", "I", "V"] + (["D"] if diode else []))
+        if kind == "V" and (a == 1 or b == 1 or cnt["V"] >= 2):
+            kind = "R"
+        cnt[kind] += 1
+        nm = f"{kind}{cnt[kind]}"
+        if kind == "R":
+            lines.append(f"{nm} {a} {b} {10 ** rng.uniform(1, 4):.6g}")
+        elif kind == "C":
+            lines.append(f"{nm} {a} {b} {10 ** rng.uniform(-9, -6):.6g}")
+        elif kind == "L":
+            lines.append(f"{nm} {a} {b} {10 ** rng.uniform(-6, -3):.6g}")
+        elif kind == "I":
+            lines.append(f"{nm} {a} {b} {rng.uniform(-1e-3, 1e-3):.6g}")
+        elif kind == "V":
+            lines.append(f"{nm} {a} {b} {rng.uniform(-2, 2):.4g}")
+        else:
+            lines.append(f"{nm} {a} x{cnt['D']} DMOD")
+            lines.append(f"RD{cnt['D']} x{cnt['D']} {b} {10 ** rng.uniform(2, 4):.6g}")
+    if cnt["D"]:
+        lines.append(".model DMOD D (is=1e-12)")
+    return "\n".join(lines) + "\n"
+
+
+def _oracle(fn):
+    try:
+        return fn(), None
+    except Exception as e:      # singular at this operating point, not convergent ...: the CUDA side must fail as well
+        return None, str(e)
+
+
+def _emulated(fn):
+    try:
+        X, status = fn()
+        return (None, f"lane status {status}") if np.any(status) else (X, None)
+    except kb.KretsError as e:
+        return None, str(e)
+
+
+def run_transient(kc, h, nsteps):
+    pdc = kb.Plan(kc, api.MODE_DC, force_lane_vm=True)
+    ptr = kb.Plan(kc, api.MODE_TRAN, time_step=h, force_lane_vm=True)
+    X = Emulator(pdc, 1, rows=nsteps + 1).run(np.zeros((0, 1)), row_begin=0, row_end=1)
+    em = Emulator(ptr, 1, rows=nsteps + 1, h=h)
+    X = em.run(np.zeros((0, 1)), X=X, row_begin=1, guess_empty_at_iter0=False, pseudo_time=True)
+    return X[:, : kc.n, 0], em.status, ptr
+
+
+def check_circuit(oracle, text, diode):
+    oc, kc = oracle.Circuit(text), kb.parse_circuit_description(text)
+    assert kc.names == oc.names
+    problems = []
+
+    def compare(what, ref, oerr, got, kerr, tol):
+        if (ref is None) != (got is None):
+            problems.append(f"{what}: oracle {'failed: ' + oerr if ref is None else 'solved'}, lane program {'failed: ' + kerr if got is None else 'solved'}")
+        elif ref is not None and not rel_err(got, ref) < tol:
+            problems.append(f"{what}: max rel err {rel_err(got, ref):.3g}")
+
+    ref, oerr = _oracle(oc.solve_op)
+
+    def op():
+        em = Emulator(kb.Plan(kc, api.MODE_DC, force_lane_vm=True), 1)
+        return em.run(np.zeros((0, 1)))[0][:, 0], em.status
+    got, kerr = _emulated(op)
+    compare("OP", ref, oerr, got, kerr, 1e-8)
+    if ref is None:
+        return problems
+    if not diode:
+        freqs = np.array([1.0, 1e3, 1e6])
+        refa, oerr = _oracle(lambda: oc.solve_ac(freqs)[1])
+
+        def ac():
+            em = Emulator(kb.Plan(kc, api.MODE_AC, nominal_frequency=1e3, force_lane_vm=True), 3)
+            return em.run(freqs[None, :])[0].T, em.status
+        got, kerr = _emulated(ac)
+        compare("AC", refa, oerr, got, kerr, 1e-8)
+    reft, oerr = _oracle(lambda: oc.solve_tran(1e-6, 20e-6)[1])
+    got, kerr = _emulated(lambda: run_transient(kc, 1e-6, 20)[:2])
+    compare("transient", reft, oerr, got, kerr, 1e-6 if diode else 1e-7)
+    return problems
+
+
+@pytest.mark.parametrize("diode, seeds", [(False, range(0, 300)), (True, range(300, 600))])
+def test_random_circuits_lane_program_vs_oracle(oracle, diode, seeds):
+    bad = {}
+    for seed in seeds:
+        text = random_circuit(np.random.default_rng(seed), diode)
+        problems = check_circuit(oracle, text, diode)
+        if problems:
+            bad[seed] = (problems, text)
+    assert not bad, bad
+
+
+def test_found_by_the_fuzz_floating_source_with_companion_path(oracle, monkeypatch):
+    """The transversal + minimum-degree pivot sequence of this transient plan cancels exactly (I(V2)'s pivot: the KCL rows of the source's
+    terminals sum to an equation without the current).  The numeric check at the nominal values re-pivots it; without the check every lane
+    reports a zero pivot where the reference solves."""
+    kc, oc = kb.parse_circuit_description(FLOATING_SOURCE), oracle.Circuit(FLOATING_SOURCE)
+    _, ref = oc.solve_tran(1e-6, 20e-6)
+    X, status, plan = run_transient(kc, 1e-6, 20)
+    assert _lib.lib().krb_plan_repivoted(plan._h) == 1 and not status.any()
+    assert np.max(np.abs(X - ref)) < 1e-12
+    assert _lib.lib().krb_plan_repivoted(kb.Plan(kc, api.MODE_DC, force_lane_vm=True)._h) == 0        # the DC plan (no capacitor) never needed it
+    monkeypatch.setenv("KRB_NO_PIVOT_CHECK", "1")
+    _, status, plan = run_transient(kc, 1e-6, 20)
+    assert _lib.lib().krb_plan_repivoted(plan._h) == 0 and (status[0] & 1)          # KRB_LANE_ZERO_PIVOT
+
+
+def test_found_by_the_fuzz_nonlinear_variant(oracle):
+    """the same sub-circuit inside a diode circuit (lane VM with Newton-Raphson: no pivoting fallback exists for nonlinear plans)"""
+    text = ("R1 1 0 2069.22\nR2 2 0 1031.41\nR3 3 2 200.105\nR4 4 2 9813.09\nV1 1 0 4.765\nC1 4 3 1.01013e-07\nI1 2 4 0.00031127\nV2 4 2 -1.689\n"
+            "D1 1 x1 DMOD\nRD1 x1 0 110.868\n.model DMOD D (is=1e-12)\n")
+    assert check_circuit(oracle, text, True) == []
