@@ -137,3 +137,75 @@ def test_found_by_the_fuzz_nonlinear_variant(oracle):
     text = ("R1 1 0 2069.22\nR2 2 0 1031.41\nR3 3 2 200.105\nR4 4 2 9813.09\nV1 1 0 4.765\nC1 4 3 1.01013e-07\nI1 2 4 0.00031127\nV2 4 2 -1.689\n"
             "D1 1 x1 DMOD\nRD1 x1 0 110.868\n.model DMOD D (is=1e-12)\n")
     assert check_circuit(oracle, text, True) == []
+
+
+# ---- ladder-like circuits through the default executor selection (chain executor when the plan is banded) ------------------------
+def random_line(rng, mixed):
+    """a line of 4..40 nodes: series R between neighbours (mixed: also L, and now and then a floating voltage source — those take the plan
+    out of the chain executor's band class), shunt R / C / nothing to ground, a source at one end, a load at the other"""
+    nn = int(rng.integers(4, 41))
+    lines = [f"V1 1 0 {rng.uniform(0.5, 5):.4g} AC 1"]
+    nv = 1
+    for k in range(1, nn):
+        kind = rng.choice(["R", "R", "R", "L", "V"]) if mixed else "R"
+        if kind == "R":
+            lines.append(f"RS{k} {k} {k + 1} {10 ** rng.uniform(0, 4):.6g}")
+        elif kind == "L":
+            lines.append(f"LS{k} {k} {k + 1} {10 ** rng.uniform(-7, -3):.6g}")
+        else:
+            nv += 1
+            lines.append(f"V{nv} {k} {k + 1} {rng.uniform(-1, 1):.4g}")
+        sh = rng.choice(["R", "C", "-"])
+        if sh == "R":
+            lines.append(f"RP{k} {k + 1} 0 {10 ** rng.uniform(1, 5):.6g}")
+        elif sh == "C":
+            lines.append(f"CP{k} {k + 1} 0 {10 ** rng.uniform(-12, -7):.6g}")
+    lines.append(f"RL {nn} 0 {10 ** rng.uniform(1, 4):.6g}")
+    return "\n".join(lines) + "\n"
+
+
+def _solve_default(plan, IN, cplx):
+    from vm_emulator import run_chain
+    if plan.info.executor == 1:
+        X, status = run_chain(plan, IN, cplx)
+        return X.T, status
+    assert plan.info.executor == 0
+    em = Emulator(plan, IN.shape[1])
+    return em.run(IN)[0].T, em.status
+
+
+def test_random_lines_default_executor_vs_oracle(oracle):
+    bad, chain_plans = {}, 0
+    for seed in range(1000, 1150):
+        text = random_line(np.random.default_rng(seed), mixed=seed >= 1100)
+        oc, kc = oracle.Circuit(text), kb.parse_circuit_description(text)
+        vals = np.array([-1.0, 0.5, 2.0])
+        ref, oerr = _oracle(lambda: np.array([oc.solve_dc("V1", v, v, 1.0)[0] for v in vals]))
+        try:
+            plan = kb.Plan(kc, api.MODE_DC, sweep_element=kc.element_index("V1"))
+            chain_plans += plan.info.executor == 1
+            got, status = _solve_default(plan, vals[None, :], False)
+            kerr = f"lane status {status}" if status.any() else None
+        except kb.KretsError as e:
+            got, kerr = None, str(e)
+        if (ref is None) != (got is None or kerr is not None):
+            bad[seed] = ("DC", oerr, kerr, text)
+            continue
+        if ref is not None and not rel_err(got, ref) < 1e-8:
+            bad[seed] = ("DC", rel_err(got, ref), text)
+            continue
+        freqs = np.array([10.0, 1e4, 1e7])
+        refa, oerr = _oracle(lambda: oc.solve_ac(freqs)[1])
+        try:
+            plan = kb.Plan(kc, api.MODE_AC, nominal_frequency=1e4)
+            chain_plans += plan.info.executor == 1
+            got, status = _solve_default(plan, freqs[None, :], True)
+            kerr = f"lane status {status}" if status.any() else None
+        except kb.KretsError as e:
+            got, kerr = None, str(e)
+        if (refa is None) != (got is None or kerr is not None):
+            bad[seed] = ("AC", oerr, kerr, text)
+        elif refa is not None and not rel_err(got, refa) < 1e-8:
+            bad[seed] = ("AC", rel_err(got, refa), text)
+    assert not bad, bad
+    assert chain_plans >= 50          # the generator really exercises the chain executor's tables
