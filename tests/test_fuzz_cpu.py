@@ -209,3 +209,43 @@ def test_random_lines_default_executor_vs_oracle(oracle):
             bad[seed] = ("AC", rel_err(got, refa), text)
     assert not bad, bad
     assert chain_plans >= 50          # the generator really exercises the chain executor's tables
+
+
+# ---- the front executor's tables (fronts.cpp) on random circuits, through the numpy multifrontal emulator ------------------------
+def test_random_circuits_front_tables_vs_superlu(oracle):
+    """Random circuits and lines analysed with KRB_EXEC_STAGED: supernodes, relative indices, assembly lists and level order are run by
+    tests/front_emulator.py (threshold pivoting inside the fully-summed blocks, as the kernels do) on the oracle-stamped matrix and
+    compared with SuperLU.  Matrices that are singular or worse conditioned than 1e13 are skipped."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    import front_emulator as fe
+    from test_front_cpu import _check_tables
+    done, bad = 0, {}
+    for seed in range(2000, 2120):
+        rng = np.random.default_rng(seed)
+        text = random_circuit(rng, False) if seed % 2 else random_line(rng, True)
+        oc, kc = oracle.Circuit(text), kb.parse_circuit_description(text)
+        n = kc.n
+        for mode, kmode, par in (("dc", api.MODE_DC, 0.0), ("ac", api.MODE_AC, 2.5e4), ("tran", api.MODE_TRAN, 1e-6)):
+            try:
+                ocp, ori, vals = oc.stamp_matrix(mode, par)
+                A = sp.csc_matrix((vals, ori, ocp), shape=(n, n))
+                b = np.random.default_rng(7).standard_normal(n) + (1j * np.random.default_rng(8).standard_normal(n) if mode == "ac" else 0.0)
+                with np.errstate(all="ignore"):
+                    xr = spl.splu(A).solve(b)
+                    if not np.all(np.isfinite(xr)) or np.linalg.cond(A.toarray()) > 1e13:
+                        continue
+            except Exception:      # singular for SuperLU / the oracle: nothing to compare
+                continue
+            plan = kb.Plan(kc, kmode, executor=api.EXEC_STAGED, time_step=1e-6 if mode == "tran" else 0.0, nominal_frequency=2.5e4)
+            ft = plan.front_tables()
+            _check_tables(ft, n)
+            ro, co = plan.pivot_order()
+            x = fe.factor_and_solve(ft, ro, co, vals, b, dtype=np.complex128 if mode == "ac" else np.float64)
+            done += 1
+            err = np.max(np.abs(x - xr)) / np.max(np.abs(xr))
+            if not err <= 1e-8:
+                bad[(seed, mode)] = (err, text)
+    assert not bad, bad
+    assert done >= 200
