@@ -249,3 +249,66 @@ def test_random_circuits_front_tables_vs_superlu(oracle):
                 bad[(seed, mode)] = (err, text)
     assert not bad, bad
     assert done >= 200
+
+
+# ---- netlist front end: random formatting, value suffixes and source forms, against the oracle's restatement of the parser -----------
+_SUFFIXES = ["", "k", "K", "meg", "MEG", "Meg", "m", "u", "n", "p", "f", "g", "G", "t", "T", "mil", "e3", "e-3", "E6", "kohm", "uF", "nH", "V", "A", "Hz", "x"]
+
+
+def _value(rng):
+    m = rng.choice([f"{rng.uniform(0.1, 999):.4g}", f"{int(rng.integers(1, 1000))}", f"{rng.uniform(0.1, 9):.3f}", f".{int(rng.integers(1, 99))}", f"{int(rng.integers(1, 99))}."])
+    return m + (rng.choice(_SUFFIXES[:12]) if rng.random() < 0.9 else rng.choice(_SUFFIXES))
+
+
+def random_netlist_text(rng):
+    nn = int(rng.integers(2, 6))
+    names = [rng.choice(["n", "N", "out", "in", "a", "x_"]) + str(k) for k in range(nn)]
+    nodes = ["0"] + names
+    lines = []
+    if rng.random() < 0.3:
+        lines.append(rng.choice(["* title line", "% comment", "", "   "]))
+    for k, nm in enumerate(names):
+        lines.append(f"R{k} {nm} {nodes[int(rng.integers(0, k + 1))]} {_value(rng)}" + (rng.choice(["", " extra", " ; c", " $ c"]) if rng.random() < 0.2 else ""))
+    for j in range(int(rng.integers(1, 6))):
+        a, b = rng.choice(len(nodes), size=2, replace=False)
+        kind = rng.choice(["R", "C", "L", "V", "I", "r", "c", "v"])
+        ident = f"{kind}x{j}"
+        if kind in "Vv":
+            form = rng.choice(["dc", "plain", "ac", "sin", "pulse"])
+            v = {"dc": f"DC {_value(rng)}", "plain": _value(rng), "ac": f"DC {_value(rng)} AC {_value(rng)}",
+                 "sin": f"SIN({_value(rng)} {_value(rng)} {_value(rng)} 0 0 0)", "pulse": f"PULSE(0 {_value(rng)} 1n 1n 1n 1u 2u)"}[form]
+            lines.append(f"{ident} {nodes[a]} {nodes[b]} {v}")
+        else:
+            lines.append(f"{ident} {nodes[a]} {nodes[b]} {_value(rng)}" + (" G2" if kind in "Cc" and rng.random() < 0.3 else ""))
+        if rng.random() < 0.15:
+            lines.append(rng.choice(["* c", "%c", "", ".control\nop\n.endc"]))
+    return "\n".join(lines) + "\n"
+
+
+def test_random_netlists_front_end_vs_oracle(oracle):
+    """accept / reject decisions, the MNA index map (parser.rs:105-125: bit-exact) and every parsed element value (utils.rs:32-88 suffix
+    rules, voltage_source.rs:194 implicit DC) agree between the C++ host front end and the oracle's restatement of the parser"""
+    bad, parsed = {}, 0
+    for seed in range(3000, 3300):
+        text = random_netlist_text(np.random.default_rng(seed))
+        oc, oerr = _oracle(lambda: oracle.Circuit(text))
+        try:
+            kc, kerr = kb.parse_circuit_description(text), None
+        except kb.KretsError as e:
+            kc, kerr = None, str(e)
+        if (oc is None) != (kc is None):
+            bad[seed] = ("accept/reject", oerr, kerr, text)
+            continue
+        if oc is None:
+            continue
+        parsed += 1
+        if oc.names != kc.names:
+            bad[seed] = ("index map", oc.names, kc.names, text)
+            continue
+        for e in range(kc.num_elements):
+            a, b = oc.element_value(e), kc.element_value(e)
+            if not (a == b or (a != a and b != b)):
+                bad[seed] = ("value", kc.identifiers[e], a, b, text)
+                break
+    assert not bad, bad
+    assert parsed >= 100
