@@ -312,3 +312,44 @@ def test_random_netlists_front_end_vs_oracle(oracle):
                 break
     assert not bad, bad
     assert parsed >= 100
+
+
+# ---- the block-partitioned chain kernel's tables (the headline kernel) on random NON-uniform lines ---------------------------------
+def test_random_long_lines_block_chain_tables_vs_oracle(oracle):
+    """Lines of 515..900 nodes with series resistors over four decades and random R / C shunts: the numpy restatements of
+    krb_chain_block_kernel (Wang partition + cyclic reduction) and of the sequential chain kernel against the oracle, DC sweep and AC."""
+    from vm_emulator import chain_block_info, run_chain, run_chain_block
+    bad, blocks = {}, 0
+    for seed in range(4000, 4030):
+        rng = np.random.default_rng(seed)
+        nn = int(rng.integers(515, 900))
+        lines = [f"V1 1 0 {rng.uniform(0.5, 5):.4g} AC 1"]
+        for k in range(1, nn):
+            lines.append(f"RS{k} {k} {k + 1} {10 ** rng.uniform(0, 4):.6g}")
+            sh = rng.choice(["R", "C", "-"])
+            if sh == "R":
+                lines.append(f"RP{k} {k + 1} 0 {10 ** rng.uniform(1, 5):.6g}")
+            elif sh == "C":
+                lines.append(f"CP{k} {k + 1} 0 {10 ** rng.uniform(-12, -7):.6g}")
+        lines.append(f"RL {nn} 0 {10 ** rng.uniform(1, 4):.6g}")
+        text = "\n".join(lines) + "\n"
+        oc, kc = oracle.Circuit(text), kb.parse_circuit_description(text)
+        for mode in ("dc", "ac"):
+            if mode == "dc":
+                plan, IN, cplx = kb.Plan(kc, api.MODE_DC, sweep_element=kc.element_index("V1")), np.array([[-1.0, 0.5, 2.0]]), False
+                ref = np.array([oc.solve_dc("V1", v, v, 1.0)[0] for v in IN[0]])
+            else:
+                plan, IN, cplx = kb.Plan(kc, api.MODE_AC, nominal_frequency=1e4), np.array([[10.0, 1e4, 1e7]]), True
+                ref = oc.solve_ac(IN[0])[1]
+            assert plan.info.executor == 1
+            Xs, st = run_chain(plan, IN, cplx)
+            if st.any() or not rel_err(Xs.T, ref) < 1e-8:
+                bad[(seed, mode, "sequential")] = (rel_err(Xs.T, ref), st)
+            valid = chain_block_info(plan)[0]
+            if valid:
+                blocks += 1
+                X, stb = run_chain_block(plan, IN, cplx)
+                if stb.any() or not rel_err(X.T, ref) < 1e-8:
+                    bad[(seed, mode, "block")] = (rel_err(X.T, ref), stb)
+    assert not bad, bad
+    assert blocks >= 50
