@@ -353,3 +353,41 @@ def test_random_long_lines_block_chain_tables_vs_oracle(oracle):
                     bad[(seed, mode, "block")] = (rel_err(X.T, ref), stb)
     assert not bad, bad
     assert blocks >= 50
+
+
+# ---- the circuit-specialised kernel's generated statements (vm_jit.cpp, host build) against the interpreter emulator ----------------
+def test_random_circuits_specialised_kernel_vs_emulator(oracle):
+    """vm_jit.cpp writes the lane program out as straight-line code; tests/jit_host.py compiles the same text for the host.  On random
+    circuits (every second one with diodes) the OP + 10 backward-Euler steps and the AC sweep must agree with the interpreter emulator:
+    same failed / solved lanes, same Newton-Raphson iteration counts, values to 1e-8."""
+    from jit_host import JitHost
+    checked = 0
+    for seed in range(5000, 5024):
+        diode = seed % 2 == 1
+        text = random_circuit(np.random.default_rng(seed), diode)
+        kc = kb.parse_circuit_description(text)
+        try:
+            pdc = kb.Plan(kc, api.MODE_DC, force_lane_vm=True)
+            ptr = kb.Plan(kc, api.MODE_TRAN, time_step=1e-6, force_lane_vm=True)
+        except kb.KretsError:
+            continue
+        outs = []
+        for driver in (Emulator, JitHost):
+            d0 = driver(pdc, 1, rows=11)
+            X = d0.run(np.zeros((0, 1)), row_begin=0, row_end=1)
+            d = driver(ptr, 1, rows=11, h=1e-6)
+            X = d.run(np.zeros((0, 1)), X=X, row_begin=1, guess_empty_at_iter0=False, pseudo_time=True)
+            outs.append((X[:, : kc.n, 0].copy(), bool(d0.status[0] or d.status[0]), int(d0.iters[0]), int(d.iters[0])))
+        (xa, fa, i0a, ia), (xb, fb, i0b, ib) = outs
+        assert fa == fb and (i0a, ia) == (i0b, ib), (seed, outs, text)
+        if not fa:
+            assert rel_err(xb, xa) < 1e-8, (seed, rel_err(xb, xa), text)
+            checked += 1
+        if not diode:
+            try:
+                pa = kb.Plan(kc, api.MODE_AC, nominal_frequency=1e3, force_lane_vm=True)
+            except kb.KretsError:      # AC with a current source: structurally singular (SURVEY B-3)
+                continue
+            f = np.array([[1.0, 1e3, 1e6]])
+            assert rel_err(JitHost(pa, 3).run(f)[0].T, Emulator(pa, 3).run(f)[0].T) < 1e-8, (seed, text)
+    assert checked >= 12
