@@ -937,6 +937,14 @@ int analyze(const Circuit &c, int mode, const krb_plan_opts &opts_in, Plan &plan
     }
     int rc = build_stamps(c, mode, plan.opts.integrator, plan.stamps);
     if (rc) { err = "element not supported in this analysis mode (the reference panics here)"; return rc; }
+    // A voltage source without a waveform has transient value = its DC value (voltage_source.rs:244-252), so when that value varies per
+    // lane (Monte-Carlo) the transient right-hand side must read the lane's input plane like the DC one does — the per-row source table
+    // (S_WAVE) is lane-invariant and would keep the nominal value on every lane.  Sources with a PULSE / SIN waveform stay table-driven
+    // (their DC value only enters the operating point of row 0).
+    if (mode == KRB_MODE_TRAN)
+        for (RhsContrib &rc : plan.stamps.rhs)
+            if (rc.s.kind == S_WAVE && c.el[rc.s.elem].waveform == KRB_WAVE_NONE &&
+                std::find(plan.varied.begin(), plan.varied.end(), rc.s.elem) != plan.varied.end()) rc.s.kind = S_VAL;
     build_pattern(n, plan.stamps, plan.pattern);
 
     // ---- static pivot plan ----

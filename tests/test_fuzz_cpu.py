@@ -391,3 +391,67 @@ def test_random_circuits_specialised_kernel_vs_emulator(oracle):
             f = np.array([[1.0, 1e3, 1e6]])
             assert rel_err(JitHost(pa, 3).run(f)[0].T, Emulator(pa, 3).run(f)[0].T) < 1e-8, (seed, text)
     assert checked >= 12
+
+
+# ---- Monte-Carlo lanes (R / C / L / V / I values per lane) x the three integrators ----------------------------------------------------
+def _mc_transient(oracle, text, varied, vals, integ, h=1e-6, nsteps=12):
+    """OP + nsteps steps of every lane on the emulator and on the oracle (element values set per lane); returns the list of problems"""
+    from vm_emulator import input_layout
+    kc = kb.parse_circuit_description(text)
+    lanes = vals.shape[1]
+    pdc = kb.Plan(kc, api.MODE_DC, varied=varied, force_lane_vm=True)
+    ptr = kb.Plan(kc, api.MODE_TRAN, varied=varied, time_step=h, integrator=integ, force_lane_vm=True)
+    assert input_layout(pdc)[2] == input_layout(ptr)[2]               # one input buffer serves both plans (runtime.cu)
+    IN = np.zeros((max(ptr.info.n_inputs, 1), lanes))
+    for k, pl in enumerate(input_layout(ptr)[2]):
+        IN[pl] = vals[k]
+    rows = nsteps + 1
+    e0 = Emulator(pdc, lanes, rows=rows)
+    X = e0.run(IN, row_begin=0, row_end=1)
+    et = Emulator(ptr, lanes, rows=rows, h=h)
+    if et.width > kc.n:                                               # trapezoidal: capacitor-current state columns, i_C(0) = 0
+        X2 = np.zeros((rows, et.width, lanes))
+        X2[:, : kc.n] = X[:, : kc.n]
+        X = X2
+    X = et.run(IN, X=X, row_begin=1, guess_empty_at_iter0=False, pseudo_time=True)
+    problems = []
+    for l in range(lanes):
+        oc = oracle.Circuit(text)
+        for k, e in enumerate(varied):
+            oc.set_element_value(e, vals[k, l])
+        ref, _ = _oracle(lambda: oc.solve_tran(h, nsteps * h, integrator=integ)[1])
+        failed = bool(e0.status[l] or et.status[l])
+        if (ref is None) != failed:
+            problems.append(f"lane {l}: oracle {'failed' if ref is None else 'solved'}, lane status {e0.status[l]} / {et.status[l]}")
+        elif ref is not None and not rel_err(X[:, : kc.n, l], ref) < 1e-7:
+            problems.append(f"lane {l}: max rel err {rel_err(X[:, : kc.n, l], ref):.3g}")
+    return problems
+
+
+def test_random_circuits_monte_carlo_lanes_and_integrators(oracle):
+    bad, done = {}, 0
+    for seed in range(6000, 6150):
+        rng = np.random.default_rng(seed)
+        text = random_circuit(rng, False)
+        kc = kb.parse_circuit_description(text)
+        cand = [e for e in range(kc.num_elements) if kc.element(e).kind in (api.KIND_R, api.KIND_C, api.KIND_L, api.KIND_V, api.KIND_I)]
+        varied = sorted(rng.choice(cand, size=min(len(cand), int(rng.integers(1, 5))), replace=False).tolist())
+        integ = int(rng.choice([api.INTEGRATOR_BE_KRETS, api.INTEGRATOR_TRAP, api.INTEGRATOR_BE]))
+        vals = np.array([[kc.element_value(e) * (1.0 if l == 0 else 0.95 + 0.1 * rng.random()) for l in range(3)] for e in varied])
+        try:
+            problems = _mc_transient(oracle, text, varied, vals, integ)
+        except kb.KretsError:          # structurally singular circuit: rejected at analysis time
+            continue
+        done += 1
+        if problems:
+            bad[seed] = (problems, integ, varied, text)
+    assert not bad, bad
+    assert done >= 100
+
+
+def test_found_by_the_fuzz_varied_dc_source_in_a_transient_plan(oracle):
+    """A voltage source without a waveform whose DC value varies per lane: its transient value is that DC value (voltage_source.rs:244-252),
+    so every lane must step with ITS value — the lane-invariant per-row source table used to hold the nominal value for all of them."""
+    text = "R1 1 0 2220.02\nR2 2 1 792.65\nV1 1 0 2.975\nL1 2 1 0.000121718\nR3 1 0 550.966\n"
+    for integ in (api.INTEGRATOR_BE_KRETS, api.INTEGRATOR_TRAP):
+        assert _mc_transient(oracle, text, [2], np.array([[2.975, 3.1, 1.0]]), integ) == []
