@@ -455,3 +455,63 @@ def test_found_by_the_fuzz_varied_dc_source_in_a_transient_plan(oracle):
     text = "R1 1 0 2220.02\nR2 2 1 792.65\nV1 1 0 2.975\nL1 2 1 0.000121718\nR3 1 0 550.966\n"
     for integ in (api.INTEGRATOR_BE_KRETS, api.INTEGRATOR_TRAP):
         assert _mc_transient(oracle, text, [2], np.array([[2.975, 3.1, 1.0]]), integ) == []
+
+
+def test_random_monte_carlo_dc_sweep_and_ac_all_lane_executors(oracle):
+    """DC-sweep lanes and AC lanes with per-lane element values, on whichever lane executor the plan selects (sequential chain tables or
+    the lane program; half of the plans forced onto the lane VM), every lane against the oracle with that lane's values."""
+    from vm_emulator import input_layout, run_chain
+    bad, done = {}, 0
+
+    def solve(plan, IN, cplx):
+        if plan.info.executor == 1:
+            X, st = run_chain(plan, IN, cplx)
+            return X.T, st
+        em = Emulator(plan, IN.shape[1])
+        return em.run(IN)[0].T, em.status
+
+    for seed in range(7000, 7150):
+        rng = np.random.default_rng(seed)
+        diode = seed % 3 == 2
+        text = random_line(rng, False) if seed % 3 == 0 else random_circuit(rng, diode)
+        kc = kb.parse_circuit_description(text)
+        cand = [e for e in range(kc.num_elements)
+                if kc.element(e).kind in (api.KIND_R, api.KIND_C, api.KIND_L, api.KIND_V, api.KIND_I) and kc.identifiers[e] != "V1"]
+        varied = sorted(rng.choice(cand, size=min(len(cand), int(rng.integers(1, 5))), replace=False).tolist())
+        vals = np.array([[kc.element_value(e) * (1.0 if l == 0 else 0.95 + 0.1 * rng.random()) for l in range(3)] for e in varied])
+        force = bool(rng.integers(0, 2))
+
+        def lane_oracle(l):
+            oc = oracle.Circuit(text)
+            for k, e in enumerate(varied):
+                oc.set_element_value(e, vals[k, l])
+            return oc
+
+        sweep = np.array([0.3, 1.7, -0.8])
+        cases = [("DC", api.MODE_DC, dict(sweep_element=kc.element_index("V1")), sweep, lambda oc, l: oc.solve_dc("V1", sweep[l], sweep[l], 1.0, warm_start=False)[0])]
+        if not diode:
+            f = np.array([10.0, 1e4, 1e7])
+            cases.append(("AC", api.MODE_AC, dict(nominal_frequency=1e4), f, lambda oc, l: oc.solve_ac([f[l]])[1][0]))
+        for what, mode, kw, param, ref_of in cases:
+            try:
+                plan = kb.Plan(kc, mode, varied=varied, force_lane_vm=force, **kw)
+            except kb.KretsError:
+                continue
+            si, fi, iov = input_layout(plan)
+            IN = np.zeros((plan.info.n_inputs, 3))
+            IN[si if mode == api.MODE_DC else fi] = param
+            for k, pl in enumerate(iov):
+                IN[pl] = vals[k]
+            X, st = solve(plan, IN, mode == api.MODE_AC)
+            for l in range(3):
+                ref, _ = _oracle(lambda: ref_of(lane_oracle(l), l))
+                if ref is None and what == "AC" and _oracle(lane_oracle(l).solve_op)[0] is None:
+                    continue      # ac.rs:25: the reference's AC analysis fails in its operating point (a V / L loop); the plan-level AC solve has no OP
+                if (ref is None) != bool(st[l]):
+                    bad[(seed, what, l)] = ("solved / failed mismatch", st[l], text)
+                elif ref is not None:
+                    done += 1
+                    if not rel_err(X[l], ref) < (1e-6 if diode else 1e-8):
+                        bad[(seed, what, l)] = (rel_err(X[l], ref), plan.info.executor, text)
+    assert not bad, bad
+    assert done >= 400
