@@ -515,3 +515,31 @@ def test_random_monte_carlo_dc_sweep_and_ac_all_lane_executors(oracle):
                         bad[(seed, what, l)] = (rel_err(X[l], ref), plan.info.executor, text)
     assert not bad, bad
     assert done >= 400
+
+
+def test_random_diode_circuits_sequential_dc_sweep_vs_the_reference_order(oracle):
+    """krb_solve_dc_sweep_sequential's launch schedule (vm_emulator.run_sequential_sweep) on random diode circuits: 13 sweep points in
+    order, each warm-started from its predecessor, against the oracle's restatement of dc.rs:47-113 (warm_start = True)."""
+    from vm_emulator import run_sequential_sweep
+    bad, done = {}, 0
+    for seed in range(8000, 8300):
+        text = random_circuit(np.random.default_rng(seed), True)
+        if "DMOD" not in text:
+            continue
+        kc, oc = kb.parse_circuit_description(text), oracle.Circuit(text)
+        start, step, num = -1.0, 0.25, 13
+        ref, _ = _oracle(lambda: oc.solve_dc("V1", start, start + (num - 1) * step, step, warm_start=True))
+        try:
+            plan = kb.Plan(kc, api.MODE_DC, sweep_element=kc.element_index("V1"))
+            X, em, _ = run_sequential_sweep(Emulator, plan, start, step, num)
+            failed = bool(em.status.any())
+        except kb.KretsError:
+            failed = True
+        if (ref is None) != failed:
+            bad[seed] = ("solved / failed mismatch", text)
+        elif ref is not None:
+            done += 1
+            if not rel_err(X[:, : kc.n, 0], ref) < 1e-7:
+                bad[seed] = (rel_err(X[:, : kc.n, 0], ref), text)
+    assert not bad, bad
+    assert done >= 50
