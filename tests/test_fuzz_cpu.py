@@ -543,3 +543,42 @@ def test_random_diode_circuits_sequential_dc_sweep_vs_the_reference_order(oracle
                 bad[seed] = (rel_err(X[:, : kc.n, 0], ref), text)
     assert not bad, bad
     assert done >= 20
+
+
+# ---- transient with SIN / PULSE sources (per-row source table, the reference's source lag) -------------------------------------------
+# Known limit: a source that jumps by volts within one time step across a diode drives the reference's un-limited
+# Newton-Raphson (diode.rs:65-70: the clamp is a no-op) through conductances of 1e20 S and more; there the Schur complements cancel
+# completely, the answer of ANY elimination order is rounding noise, and a static order can land on an exactly zero pivot (NaN, the lane
+# is flagged) where a per-factorisation pivot search happens to step around it.  Seeds of this generator that do so:
+WAVEFORM_KNOWN_FLAGGED = {9027, 9139}        # (9139 lies beyond the range the test runs by default)
+
+
+def test_random_circuits_transient_with_waveforms(oracle):
+    import re
+    bad, done = {}, 0
+    for seed in range(9000, 9060):
+        rng = np.random.default_rng(seed - 9000)
+        diode = seed % 2 == 1
+        text = random_circuit(rng, diode)
+        if rng.random() < 0.5:
+            w = (f"SIN({rng.uniform(-1, 1):.3g} {rng.uniform(0.1, 3):.3g} {10 ** rng.uniform(3, 5.5):.4g} {rng.choice([0, 2e-6, 5e-6])} "
+                 f"{rng.choice([0, 1e4])} {rng.choice([0, 30, 90])})")
+        else:
+            w = (f"PULSE({rng.uniform(-1, 1):.3g} {rng.uniform(0.5, 3):.3g} {rng.choice([0, 1e-6, 3e-6])} {rng.choice([1e-6, 2e-6, 1e-9])} "
+                 f"{rng.choice([1e-6, 3e-6])} {rng.choice([2e-6, 5e-6])} {rng.choice([8e-6, 2e-5])})")
+        text = re.sub(r"^V1 1 0 .*$", f"V1 1 0 {w}", text, flags=re.M)
+        oc, kc = oracle.Circuit(text), kb.parse_circuit_description(text)
+        ref, _ = _oracle(lambda: oc.solve_tran(1e-6, 25e-6)[1])
+        try:
+            X, st, _ = run_transient(kc, 1e-6, 25)
+            failed = bool(st.any())
+        except kb.KretsError:
+            failed = True
+        if (ref is None) != failed:
+            bad[seed] = ("solved / failed mismatch", text)
+        elif ref is not None:
+            done += 1
+            if not rel_err(X, ref) < (1e-6 if diode else 1e-7):
+                bad[seed] = (rel_err(X, ref), text)
+    assert set(bad) <= WAVEFORM_KNOWN_FLAGGED, {k: v for k, v in bad.items() if k not in WAVEFORM_KNOWN_FLAGGED}
+    assert done >= 45
